@@ -1,0 +1,299 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front end of the CPU oracle (oracle/liborc.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+The product (uppasd_b200/) never does.
+
+`build_system()` chains the restated setup routines in the order the reference's `setup_simulation` does
+(source/uppasd.f90:914-1200): geometry -> read_exchange/dm/bq/anisotropy -> setup_hamiltonian ->
+setup_moment -> magninit.  `sd_run()` replays `sd_mphase` (source/sd_driver.f90:517-849): measure, then
+field / evolve_first / field / evolve_second / moment_update.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+# source/Parameters/constants.f90:14-29
+CONST = dict(gama=1.760859644e11, k_bolt=1.38064852e-23, mub=9.274009994e-24, mry=2.179872325e-21)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, 'liborc.so')
+    srcs = [os.path.join(_HERE, f) for f in ('orc_setup.cpp', 'orc_dynamics.cpp', 'orc_rng.cpp')]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(['make', '-C', _HERE, '-s'])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_nm_create.restype = C.c_void_p
+        _LIB.orc_effective_field.restype = C.c_double
+        _LIB.orc_rng_raw32.restype = C.c_uint
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _d(x):
+    return C.c_double(x)
+
+
+class OrcHam(C.Structure):
+    _fields_ = [('Natom', C.c_int), ('Mensemble', C.c_int), ('nHam', C.c_int), ('max_no_neigh', C.c_int),
+                ('nlist', C.c_void_p), ('nlistsize', C.c_void_p), ('ncoup', C.c_void_p), ('aHam', C.c_void_p),
+                ('do_dm', C.c_int), ('max_no_dmneigh', C.c_int), ('dmlist', C.c_void_p),
+                ('dmlistsize', C.c_void_p), ('dm_vect', C.c_void_p),
+                ('do_bq', C.c_int), ('nn_bq_tot', C.c_int), ('bqlist', C.c_void_p), ('bqlistsize', C.c_void_p),
+                ('j_bq', C.c_void_p),
+                ('do_anisotropy', C.c_int), ('taniso', C.c_void_p), ('eaniso', C.c_void_p),
+                ('kaniso', C.c_void_p), ('sb', C.c_void_p)]
+
+
+def neighbour_table(S, nn, redcoord, xc, nntype, sym, hdim, lexp, do_sortcoup=False, map_multiple=False):
+    """setup_nm + setup_neighbour_hamiltonian for one pair interaction.  Returns dict(list, listsize, coup, z)."""
+    L = lib()
+    N, NT, NA = S['Natom'], S['NT'], S['NA']
+    N1, N2, N3 = S['ncell']
+    cell = S['cell']
+    c1, c2, c3 = (np.ascontiguousarray(cell[i], dtype=np.float64) for i in range(3))
+    nn = np.ascontiguousarray(nn, dtype=np.int32)
+    ms = redcoord.shape[1]
+    redcoord = np.asfortranarray(redcoord, dtype=np.float64)
+    nnt = np.asfortranarray(nntype, dtype=np.int32) if nntype is not None else None
+    h = L.orc_nm_create(N, NT, NA, N1, N2, N3, _p(c1), _p(c2), _p(c3), C.c_char(S['bc'][0].encode()),
+                        C.c_char(S['bc'][1].encode()), C.c_char(S['bc'][2].encode()), _p(S['atype']), _p(S['bas']),
+                        ms, sym, _p(nn), _p(redcoord), _p(nnt))
+    h = C.c_void_p(h)
+    z = L.orc_nm_max_no_neigh(h)
+    NH = S['nHam']
+    nlist = np.zeros((z, N), dtype=np.int32, order='F')
+    nlistsize = np.zeros(NH, dtype=np.int32)
+    ncoup = np.zeros((hdim, z, NH), order='F')
+    xc = np.asfortranarray(xc, dtype=np.float64)
+    L.orc_mount(h, N, NT, NA, NH, _p(S['anumb']), _p(S['atype']), z, _p(nn), _p(xc), _p(S['ammom_inp']), hdim, lexp,
+                int(do_sortcoup), int(map_multiple), _d(CONST['mry']), _d(CONST['mub']), _p(nlistsize), _p(nlist),
+                _p(ncoup))
+    me, mnn = L.orc_nm_max_no_equiv(h), L.orc_nm_maxnn(h)
+    nm_cell = np.zeros((me, ms, NA), dtype=np.int32, order='F')
+    nm_trunk = np.zeros((3, me, ms, NA), dtype=np.int32, order='F')
+    nnm_cell = np.zeros((ms, NA), dtype=np.int32, order='F')
+    L.orc_nm_get_stencil(h, _p(nm_cell), _p(nm_trunk), _p(nnm_cell))
+    L.orc_nm_free(h)
+    if hdim == 1:
+        ncoup = np.asfortranarray(ncoup[0])
+    return dict(list=nlist, listsize=nlistsize, coup=ncoup, z=z, nm_cell=nm_cell, nm_trunk=nm_trunk,
+                nnm_cell=nnm_cell, maxnn=mnn)
+
+
+def build_system(inp, bas, atype_inp, ammom_inp, aemom_inp, landeg_ch, exchange, dm=None, bq=None, aniso=None):
+    """exchange/dm/bq: callables (S) -> (nn, redcoord, xc, nntype) evaluated AFTER the basis has been folded
+    (read_exchange runs after setup_geometry, source/uppasd.f90:921-930), or ready tuples."""
+    L = lib()
+    N1, N2, N3 = inp['ncell']
+    NA = bas.shape[1]
+    N = NA * N1 * N2 * N3
+    M = inp['mensemble']
+    cell = np.array(inp['cell'], dtype=np.float64)
+    S = dict(Natom=N, NA=NA, NT=int(atype_inp.max()), ncell=(N1, N2, N3), cell=cell, bc=inp['bc'], Mensemble=M)
+    S['bas'] = np.asfortranarray(bas, dtype=np.float64).copy(order='F')
+    S['atype_inp'] = np.ascontiguousarray(atype_inp, dtype=np.int32)
+    anumb_inp = np.arange(1, NA + 1, dtype=np.int32)
+    S['coord'] = np.zeros((3, N), order='F')
+    S['atype'] = np.zeros(N, dtype=np.int32)
+    S['anumb'] = np.zeros(N, dtype=np.int32)
+    c1, c2, c3 = (np.ascontiguousarray(cell[i]) for i in range(3))
+    L.orc_setup_geometry(NA, N1, N2, N3, _p(c1), _p(c2), _p(c3), _p(S['bas']), _p(S['atype_inp']), _p(anumb_inp),
+                         _p(S['coord']), _p(S['atype']), _p(S['anumb']))
+    S['ammom_inp'] = np.ascontiguousarray(ammom_inp, dtype=np.float64)
+    reduced = inp['do_reduced'] == 'Y'
+    S['nHam'] = NA if reduced else N
+    S['aHam'] = (S['anumb'].copy() if reduced else np.arange(1, N + 1, dtype=np.int32))
+    sortc = inp['do_sortcoup'] == 'Y'
+    ex = exchange(S) if callable(exchange) else exchange
+    S['exchange'] = neighbour_table(S, ex[0], ex[1], ex[2], ex[3], inp['sym'], 1, 1, sortc, inp['map_multiple'])
+    S['dm'] = None
+    if dm is not None:
+        t = dm(S) if callable(dm) else dm
+        S['dm'] = neighbour_table(S, t[0], t[1], t[2], None, 0, 3, 1, sortc, inp['map_multiple'])
+    S['bq'] = None
+    if bq is not None:
+        t = bq(S) if callable(bq) else bq
+        S['bq'] = neighbour_table(S, t[0], t[1], t[2], None, inp['sym'], 1, 2, sortc, inp['map_multiple'])
+    S['aniso'] = None
+    if aniso is not None:
+        atyp, an = aniso
+        ta = np.zeros(N, dtype=np.int32)
+        ea = np.zeros((3, N), order='F')
+        ka = np.zeros((2, N), order='F')
+        sb = np.zeros(N)
+        L.orc_setup_anisotropies(N, NA, _p(S['anumb']), _p(np.ascontiguousarray(atyp, dtype=np.int32)),
+                                 _p(np.asfortranarray(an)), _p(S['ammom_inp']), _d(CONST['mry']), _d(CONST['mub']),
+                                 _p(ta), _p(ea), _p(ka), _p(sb))
+        S['aniso'] = dict(taniso=ta, eaniso=ea, kaniso=ka, sb=sb)
+    for k in ('mmom', 'mmom0', 'mmomi'):
+        S[k] = np.zeros((N, M), order='F')
+    S['Landeg'] = np.zeros(N)
+    S['emom'] = np.zeros((3, N, M), order='F')
+    S['emomM'] = np.zeros((3, N, M), order='F')
+    L.orc_setup_moments(N, M, NA, N1, N2, N3, _p(S['ammom_inp']), _p(np.asfortranarray(aemom_inp)),
+                        _p(np.ascontiguousarray(landeg_ch, dtype=np.float64)), _p(S['mmom']), _p(S['mmom0']),
+                        _p(S['mmomi']), _p(S['Landeg']), _p(S['emom']), _p(S['emomM']))
+    S['external_field'] = np.zeros((3, N, M), order='F')
+    for a in range(3):
+        S['external_field'][a, :, :] = inp['hfield'][a]
+    return S
+
+
+def ham_struct(S):
+    """OrcHam view over a system dict (keeps references alive in S['_keep'])."""
+    H = OrcHam()
+    H.Natom, H.Mensemble, H.nHam = S['Natom'], S['Mensemble'], S['nHam']
+    ex = S['exchange']
+    H.max_no_neigh = ex['z']
+    H.nlist, H.nlistsize, H.ncoup, H.aHam = _p(ex['list']), _p(ex['listsize']), _p(ex['coup']), _p(S['aHam'])
+    if S.get('dm') is not None:
+        t = S['dm']
+        H.do_dm, H.max_no_dmneigh = 1, t['z']
+        H.dmlist, H.dmlistsize, H.dm_vect = _p(t['list']), _p(t['listsize']), _p(t['coup'])
+    if S.get('bq') is not None:
+        t = S['bq']
+        H.do_bq, H.nn_bq_tot = 1, t['z']
+        H.bqlist, H.bqlistsize, H.j_bq = _p(t['list']), _p(t['listsize']), _p(t['coup'])
+    if S.get('aniso') is not None:
+        t = S['aniso']
+        H.do_anisotropy = 1
+        H.taniso, H.eaniso, H.kaniso, H.sb = _p(t['taniso']), _p(t['eaniso']), _p(t['kaniso']), _p(t['sb'])
+    return H
+
+
+def effective_field(S, emomM=None, want_parts=False):
+    L = lib()
+    H = ham_struct(S)
+    N, M = S['Natom'], S['Mensemble']
+    emomM = S['emomM'] if emomM is None else np.asfortranarray(emomM)
+    beff = np.zeros((3, N, M), order='F')
+    b1 = np.zeros((3, N, M), order='F') if want_parts else None
+    b2 = np.zeros((3, N, M), order='F') if want_parts else None
+    e = L.orc_effective_field(C.byref(H), _p(emomM), _p(S['external_field']), _p(beff), _p(b1), _p(b2),
+                              _d(CONST['mub']), _d(CONST['mry']))
+    return (beff, b1, b2, e) if want_parts else (beff, e)
+
+
+class SdState:
+    """Mutable LLG state + work arrays for repeated orc_sd_step calls."""
+
+    def __init__(self, S, sdealgh, delta_t, damping, temp=0.0, mompar=0, temprescale=1.0):
+        N, M = S['Natom'], S['Mensemble']
+        self.S, self.sdealgh, self.delta_t, self.mompar, self.temprescale = S, sdealgh, delta_t, mompar, temprescale
+        self.H = ham_struct(S)
+        self.emom = S['emom'].copy(order='F')
+        self.emomM = S['emomM'].copy(order='F')
+        self.mmom = S['mmom'].copy(order='F')
+        self.mmom0 = S['mmom0'].copy(order='F')
+        self.lambda1 = np.full(N, damping) if np.isscalar(damping) else np.ascontiguousarray(damping, dtype=np.float64)
+        self.temp = np.full(N, temp) if np.isscalar(temp) else np.ascontiguousarray(temp, dtype=np.float64)
+        self.work = np.zeros(14 * N * M)
+
+    def step(self, gauss=None):
+        L = lib()
+        S = self.S
+        g = np.asfortranarray(gauss) if gauss is not None else None
+        L.orc_sd_step(C.byref(self.H), self.sdealgh, _p(self.emom), _p(self.emomM), _p(self.mmom), _p(self.mmom0),
+                      _p(S['external_field']), _p(S['Landeg']), _p(self.lambda1), _p(self.temp),
+                      _d(self.temprescale), _d(self.delta_t), self.mompar, _p(g), _d(CONST['gama']),
+                      _d(CONST['k_bolt']), _d(CONST['mub']), _d(CONST['mry']), _p(self.work))
+
+    def sum_moments(self):
+        N, M = self.S['Natom'], self.S['Mensemble']
+        m = np.zeros((3, M), order='F')
+        lib().orc_sum_moments(N, M, _p(self.emomM), _p(m))
+        return m
+
+
+class Cumulants:
+    """calc_and_print_cumulant (source/Measurement/prn_averages.f90:919-1034): weighted running means."""
+
+    def __init__(self, natom):
+        self.natom = natom
+        self.cumuw = 0.0
+        self.cumutotw = 0.0
+        self.navrg = 0
+        self.m1 = self.m2 = self.m4 = 0.0
+        self.binder = 0.0
+
+    def sample(self, msum):  # msum (3,M) = sum_i emomM
+        for k in range(msum.shape[1]):
+            m = msum[:, k]
+            avrgme = np.sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]) / self.natom
+            a2 = avrgme ** 2
+            a4 = a2 ** 2
+            self.cumuw += 1.0
+            w, W = self.cumuw, self.cumutotw
+            t1 = (self.m1 * W + avrgme * w) / (W + w)
+            t2 = (self.m2 * W + a2 * w) / (W + w)
+            t4 = (self.m4 * W + a4 * w) / (W + w)
+            self.binder = 1 - (t4 / 3 / t2 ** 2)
+            self.m1, self.m2, self.m4 = t1, t2, t4
+            self.navrg += 1
+            self.cumutotw += self.cumuw
+        return self.m1, self.m2, self.m4, self.binder
+
+
+def sd_run(S, inp, nstep=None, traj_atoms=(), want_rows=None):
+    """Replay of sd_mphase (source/sd_driver.f90:517-849) at T=0: returns averages rows {iter: (mx,my,mz,m)},
+    cumulant rows {sample_no: (m,m2,m4,U)}, trajectories {atom: {iter: (ex,ey,ez,m)}} and the final state."""
+    nstep = inp['nstep'] if nstep is None else nstep
+    st = SdState(S, inp['sdealgh'], inp['timestep'], inp['damping'], temp=0.0, mompar=inp['mompar'])
+    N, M = S['Natom'], S['Mensemble']
+    avg, cum, traj = {}, {}, {a: {} for a in traj_atoms}
+    cu = Cumulants(N)
+    avrg_step, cumu_step = inp['avrg_step'], inp['cumu_step']
+    traj_step = inp.get('traj_step', 100)
+
+    def measure(mstep):
+        if inp['do_avrg'] == 'Y' and (mstep - 1) % avrg_step == 0:
+            m = st.sum_moments()
+            av = m / N
+            nrm = np.sqrt((av ** 2).sum(axis=0))
+            avg[mstep - 1] = (av[0].mean(), av[1].mean(), av[2].mean(), nrm.mean())
+        for a in traj_atoms:
+            if (mstep - 1) % traj_step == 0:
+                traj[a][mstep - 1] = tuple(st.emom[:, a - 1, 0]) + (st.mmom[a - 1, 0],)
+        if inp['do_cumu'] == 'Y' and mstep % cumu_step == 0:
+            r = cu.sample(st.sum_moments())
+            cum[cu.navrg // M] = r
+
+    for mstep in range(1, nstep + 1):
+        measure(mstep)
+        st.step()
+    measure(nstep + 1)
+    return dict(averages=avg, cumulants=cum, traj=traj, state=st)
+
+
+# ---- reference RNG access (MT variant + ziggurat) ---------------------------------------------
+def rng_init(seed):
+    lib().orc_rng_init(int(seed))
+
+
+def rng_uniform(n):
+    out = np.zeros(n)
+    lib().orc_rng_uniform(_p(out), C.c_long(n))
+    return out
+
+
+def zig_setup(seed):
+    lib().orc_zig_setup(int(seed))
+
+
+def fill_rngarray(n):
+    out = np.zeros(n)
+    lib().orc_fill_rngarray(_p(out), C.c_long(n))
+    return out

@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.json from the reference's own regression fixtures.
+
+Run in the build container (where /root/reference is mounted):  python tests/golden/make_fixtures.py
+Each JSON holds (a) the reference fixture's inputs, token for token (inpsd.dat keywords, posfile, momfile,
+jfile, dmfile rows), and (b) the expected values the reference's own test YAML pins for it
+(tests/regulartests.yaml, tests/regressionResaro.yaml, tests/cudatests.yaml), with the YAML file:line cited.
+The GPU box has no /root/reference; tests read only these JSON files.
+"""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, '..', '..'))
+from oracle import inputs  # noqa: E402
+
+REF = '/root/reference/tests'
+
+
+def fixture(dirname, inpname='inpsd.dat', extra_inp=None):
+    d = os.path.join(REF, dirname)
+    inp = inputs.read_inpsd(os.path.join(d, inpname))
+    if extra_inp:
+        inp.update(extra_inp)
+    files = inp.pop('files')
+    out = {'source': 'tests/%s/%s' % (dirname, inpname)}
+    keymap = {'posfile': 'posfile', 'momfile': 'momfile', 'exchange': 'jfile', 'dm': 'dmfile', 'bq': 'bqfile',
+              'anisotropy': 'kfile'}
+    for k, v in files.items():
+        out[keymap[k]] = inputs._rows(v)
+    inp['cell'] = [list(map(float, r)) for r in inp['cell']]
+    out['inp'] = inp
+    return out
+
+
+def main():
+    fx = {}
+    # --- tests/kagome: midpoint + DMI + reduced Hamiltonian, T=0 (regulartests.yaml:132-156), tol 1e-8 abs
+    f = fixture('kagome')
+    f['inp']['traj_step'] = 100
+    f['expected'] = {
+        'averages': {'13000': [1.72521729, 1.00850955, -0.0656709236, 1.99944464]},
+        'trajectory': {'atom': 2, '2400': [0.861611883, 0.507363131, -0.014408889, 2.0]},
+        'tol': 1e-8, 'yaml': 'tests/regulartests.yaml:132-156'}
+    fx['kagome'] = f
+    # --- tests/Regression megaTest: 2-type cell, sym 1, maptype 2, hfield, T=0 (regressionResaro.yaml), 1e-8 abs
+    f = fixture('Regression')
+    f['expected'] = {
+        'averages': {'11000': [0.145574347, 0.252312246, 1.87753739, 1.9]},
+        'moment': {'atom': 128, '11000': [0.0766180766, 0.132795919, 0.988177572]},
+        'coord': {'atom': 128, 'row': [3.5, 3.5, 3.51], 'type': 2, 'numb': 2},
+        'tol': 1e-8, 'yaml': 'tests/regressionResaro.yaml:18-27,64-73,145-154'}
+    fx['megatest'] = f
+    # --- tests/FeCo: B2 two sublattices, sym 0, maptype 2, alpha=0.001 (regulartests.yaml:219-242), sloppy 2e-2
+    f = fixture('FeCo')
+    f['expected'] = {
+        'averages_M': {'4700': 1.97771406},
+        'cumulants': {'221': [1.86049127, 3.46770589, 12.1090509, 0.664336331]},
+        'tol_abs': 2e-2, 'tol_rel': 2e-2, 'yaml': 'tests/regulartests.yaml:219-242'}
+    fx['feco'] = f
+    # --- tests/bccFe_cuda: reference CUDA path => Depondt actually runs (cudatests.yaml:24-46), sloppy
+    f = fixture('bccFe_cuda', extra_inp={'sdealgh': 5})
+    f['expected'] = {
+        'averages_M': {'1700': 2.16117297},
+        'cumulants': {'41': [2.09307165, 4.38839661, 19.3810564, 0.664537137]},
+        'tol_abs': 2e-2, 'tol_rel': 2e-2, 'yaml': 'tests/cudatests.yaml:24-46',
+        'note': 'gpu_mode 1: the reference CUDA path always integrates with Depondt (cudaMdSimulation.cu:319)'}
+    fx['bccfe_cuda'] = f
+    # --- tests/FeCo_cuda: same inputs as FeCo on the reference CUDA path (cudatests.yaml:48-70), sloppy
+    f = fixture('FeCo_cuda', extra_inp={'sdealgh': 5})
+    f['expected'] = {
+        'averages_M': {'4700': 1.97771406},
+        'cumulants': {'221': [1.86058404, 3.46805484, 12.1115283, 0.664335215]},
+        'tol_abs': 2e-2, 'tol_rel': 2e-2, 'yaml': 'tests/cudatests.yaml:48-70'}
+    fx['feco_cuda'] = f
+    # --- tests/bccFe (inputs only; thermal goldens pin the reference's own RNG stream => statistical targets)
+    f = fixture('bccFe', inpname='inpsd.dat.base')
+    f['expected'] = {'note': 'thermal (T=500 K, tseed 5); these goldens pin the reference MT+Ziggurat stream and are '
+                             'statistical targets for the GPU path', 'yaml': 'tests/regulartests.yaml:244-347',
+                     'S_averages_2700': [1.69336666, -0.0338763749, 0.61172735, 1.8007911],
+                     'S_cumulants_41': [1.7980927, 3.23410613, 10.4720508, 0.666264851, 0.000377665603, 1.10522259]}
+    fx['bccfe'] = f
+    for k, v in fx.items():
+        with open(os.path.join(HERE, k + '.json'), 'w') as fh:
+            json.dump(v, fh, indent=1, default=lambda o: list(o))
+        print('wrote', k)
+
+
+if __name__ == '__main__':
+    main()
