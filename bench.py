@@ -1,0 +1,258 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native UppASD hot path.
+
+Metric (BASELINE.json): atom-steps/s of the stochastic LLG step (semi-implicit midpoint, SDEalgh 1) on the
+bcc Fe 128x128x128 supercell (4 194 304 spins, 4 exchange shells, z = 50, reduced Hamiltonian), T = 300 K.
+One "step" = one full LLG time step of every spin (field / predictor / field / corrector / moment update).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched by torchrun, one rank/GPU)
+  python bench.py --impl reference --gpus N --steps K ...  # reference arm: restated CPU path on the host cores
+
+N > 1 shards independent ensembles (Mensemble = N, one per GPU, no data-path communication): weak scaling.
+All timing is on the device (CUDA events on the engine's stream), max over ranks, after a barrier.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONST = dict(gama=1.760859644e11, k_bolt=1.38064852e-23, mub=9.274009994e-24, mry=2.179872325e-21)
+# tests/bccFe/{posfile,momfile,jfile}: bcc Fe, 4 shells (mRy), m = 2.23 mu_B
+BCC = dict(cell=np.eye(3), bas=np.array([[0.0, 0.5], [0.0, 0.5], [0.0, 0.5]]), atype=np.array([1, 1]),
+           mom=np.array([2.23, 2.23]),
+           shells=np.array([[0.5, 0.5, 0.5], [1.0, 0.0, 0.0], [1.0, 1.0, 0.0], [1.5, 0.5, 0.5]]),
+           J=np.array([1.33767484769984, 0.75703576545650, -0.05975437643846, -0.08819834160658]))
+B_ALG = {1: (256.0, 280.0), 5: (280.0, 304.0)}  # algorithmic bytes/atom of stage 1, stage 2 (z = 50)
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def bcc_engine(ncell, solver, temp, damping, mensemble, ens_offset, device):
+    """bcc Fe supercell built entirely on the device (tables + tilted start), through the C ABI."""
+    from uppasd_b200 import host, lattice
+    nn = np.array([4])
+    red = BCC['shells'][None]                       # (NT=1, 4, 3)
+    ns, ca, cs, sh = lattice.stencil(BCC['cell'], BCC['bas'], BCC['atype'], nn, red, 1, np.ones((1, 4), dtype=int))
+    cp = lattice.couplings(ns, ca, sh, BCC['atype'], BCC['J'][None, None, :], BCC['mom'], CONST['mry'], CONST['mub'])
+    e = host.Engine(device)
+    e.set_constants(CONST['gama'], CONST['k_bolt'], CONST['mub'], CONST['mry'])
+    n = 2 * ncell[0] * ncell[1] * ncell[2]
+    aham = (np.arange(n, dtype=np.int32) % 2) + 1
+    e.set_system(n, mensemble, 2, aham)
+    e.build_lattice_table(0, 2, ncell, ('P', 'P', 'P'), ns, ca, cs, cp)
+    e.set_llg(solver, 1e-16, landeg=1.0, lambda1=damping, temp=temp, seed=20261017 + 7919 * ens_offset)
+    e.commit()
+    e.init_moments_tilted(0.1, BCC['mom'])
+    return e, n
+
+
+def oracle_bcc(ncell, mensemble=1):
+    """Same system through the CPU oracle (test infrastructure; used only for the CPU baseline legs)."""
+    from oracle import orc
+    inp = dict(ncell=tuple(ncell), bc=('P', 'P', 'P'), cell=BCC['cell'], sym=1, mensemble=mensemble, do_reduced='Y',
+               do_sortcoup='N', map_multiple=False, hfield=(0.0, 0.0, 0.0))
+    ex = (np.array([4], dtype=np.int32), BCC['shells'][None].copy(), BCC['J'][None, None, :].copy(),
+          np.ones((1, 4), dtype=np.int32))
+    aemom = np.array([[1.0, 1.0], [0.0, 0.0], [0.0, 0.0]])
+    S = orc.build_system(inp, BCC['bas'], BCC['atype'], BCC['mom'], aemom, np.array([2.0, 2.0]), ex)
+    n = S['Natom']
+    i = np.arange(1, n + 1, dtype=np.float64)
+    h = np.modf(i * 0.6180339887)[0]
+    e = np.stack([np.ones(n), 0.1 * np.sin(2 * np.pi * h), 0.1 * np.cos(2 * np.pi * h)])
+    e /= np.sqrt((e ** 2).sum(axis=0))
+    for k in range(mensemble):
+        S['emom'][:, :, k] = e
+        S['emomM'][:, :, k] = e * S['mmom'][:, k]
+    return S
+
+
+def cpu_leg(ncell, solver, temp, damping, steps, warmup):
+    """Times the restated reference CPU path (oracle, OpenMP over all host cores) on a bounded sample."""
+    from oracle import orc
+    S = oracle_bcc(ncell)
+    n = S['Natom']
+    st = orc.SdState(S, solver, 1e-16, damping, temp=temp)
+    rng = np.random.default_rng(1)
+    g = np.asfortranarray(rng.normal(size=(3, n, 1))) if temp > 0 else None   # noise generation not timed (favours the CPU)
+    for _ in range(warmup):
+        st.step(gauss=g)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        st.step(gauss=g)
+    dt = time.perf_counter() - t0
+    return n * steps / dt, dt / steps * 1e3, n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--ncell', type=int, nargs=3, default=[128, 128, 128])
+    ap.add_argument('--solver', type=int, default=1, choices=[1, 5])
+    ap.add_argument('--temp', type=float, default=300.0)
+    ap.add_argument('--damping', type=float, default=0.5)
+    ap.add_argument('--cpu-ncell', type=int, nargs=3, default=[64, 64, 64])
+    ap.add_argument('--no-cpu', action='store_true')
+    a = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    steps, warmup = a.steps, max(a.warmup, 3)
+    cores = os.cpu_count() or 1
+    workload = 'bccFe %dx%dx%d LLG midpoint (SDEalgh %d), T=%g K, damping %g, dt 1e-16, z=50, do_reduced Y' % (
+        a.ncell[0], a.ncell[1], a.ncell[2], a.solver, a.temp, a.damping)
+
+    if a.impl == 'reference':
+        if rank != 0:
+            return
+        os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+        k = max(1, min(steps, 10))
+        v, ms, n = cpu_leg(a.cpu_ncell, a.solver, a.temp, a.damping, k, min(warmup, 3))
+        sample = 'bcc %dx%dx%d (%d spins) x %d steps of the same lattice/solver; restated Fortran loops ' \
+                 '(oracle/), OpenMP static schedule, noise array pre-generated' % (*a.cpu_ncell, n, k)
+        print(json.dumps({
+            'impl': 'reference', 'metric': 'atom-steps/sec', 'value': v, 'unit': 'atom-steps/s', 'n_gpus': a.gpus,
+            'steps': k, 'warmup': min(warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': {'workload': workload},
+            'cpu_baseline': {'value': v, 'unit': 'atom-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': v, 'unit': 'atom-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    torch.cuda.set_device(local)
+    e, n = bcc_engine(a.ncell, a.solver, a.temp, a.damping, 1, rank, local)
+    sync = torch.zeros(1, device='cuda')
+
+    def barrier():
+        if world > 1:
+            dist.all_reduce(sync)
+        torch.cuda.synchronize()
+        e.synchronize()
+
+    l0 = e.launch_count()
+    e.sd_steps(warmup, first_step=1)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = e.time_sd_steps(steps, first_step=warmup + 1)
+    launches = e.launch_count() - l0 - 2 * warmup
+    barrier()
+    # per-kernel durations of the two stage kernels (CUDA events on the engine's stream), averaged
+    st1, st2 = [], []
+    for r in range(8):
+        _, (x, y) = e.time_sd_steps(0, first_step=warmup + steps + 1 + r, stages=True)
+        st1.append(x); st2.append(y)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    t = torch.tensor([ms], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * n * steps / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer API: H2D of the moments, K steps with a D2H observable read every
+    #      step (what a measuring driver does), D2H of the final state
+    emom, emomM, mmom = e.get_moments()
+    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x.ravel(order='F'))).pin_memory()
+    p_e, p_m = pin(emom), pin(mmom)
+    from uppasd_b200 import host as _h
+    k2 = max(10, steps // 4)
+    barrier()
+    t0 = time.perf_counter()
+    e._chk(e.lib.asd_set_moments(e.h, p_e.data_ptr(), p_m.data_ptr(), None))
+    for s in range(k2):
+        e.sd_steps(1, first_step=10_000 + s)
+        e.measure()
+    e.get_moments()
+    e.synchronize()
+    dt = time.perf_counter() - t0
+    te = torch.tensor([dt], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = world * n * k2 / float(te.item())
+    h2d = 32.0 * n / k2
+    d2h = 56.0 * n / k2 + 32.0
+
+    if rank == 0:
+        peak, how = peaks()
+        b1, b2 = B_ALG[a.solver]
+        t2 = float(np.median(st2)) * 1e-3
+        t1 = float(np.median(st1)) * 1e-3
+        ach = b2 * n / t2 / 1e9
+        out = {
+            'metric': 'atom-steps/sec', 'value': value, 'unit': 'atom-steps/s', 'n_gpus': world, 'steps': steps,
+            'warmup': warmup, 'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': workload, 'spins_per_gpu': n, 'ensembles': world, 'parallelism': 'ensemble-sharded x%d' % world,
+                       'l2_policy': 'inputs larger than L2 (neighbour table %.0f MB per GPU)' % (50 * 4 * n / 1e6)},
+            'clocks': sampler.summary(),
+            'e2e': {'value': e2e, 'unit': 'atom-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'steps': k2, 'note': 'asd_set_moments from pinned host memory + K steps each followed by asd_measure '
+                                         '(D2H of sum M) + asd_get_moments of the final state; copies amortised over K'},
+            'gpu_launches': int(launches),
+            'roofline': {'bound': 'hbm', 'kernel': 'llg_stage_kernel<solver=%d,stage=2,reduced>' % a.solver,
+                         'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+                         'peak_source': how, 'alg_bytes_per_atom': b2, 'kernel_ms': t2 * 1e3,
+                         'stage1': {'alg_bytes_per_atom': b1, 'kernel_ms': t1 * 1e3, 'achieved': b1 * n / t1 / 1e9},
+                         'step_alg_bytes_per_atom': b1 + b2,
+                         'step_frac_of_peak': (b1 + b2) * n * steps / (ms * 1e-3) / 1e9 / peak},
+        }
+        if world == 1 and not a.no_cpu:
+            os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+            v, cms, cn = cpu_leg(a.cpu_ncell, a.solver, a.temp, a.damping, 5, 1)
+            out['cpu_baseline'] = {'value': v, 'unit': 'atom-steps/s', 'cores': cores, 'kind': 'port',
+                                   'sample': 'bcc %dx%dx%d (%d spins) x 5 steps, restated Fortran loops (oracle/), OpenMP over '
+                                             'all host cores, noise pre-generated' % (*a.cpu_ncell, cn)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

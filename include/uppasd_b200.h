@@ -1,0 +1,182 @@
+/*
+ * uppasd_b200.h -- C ABI of libuppasd_b200.so, the B200-native replacement for UppASD's per-time-step
+ * spin-dynamics hot path.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * Two layers are exported:
+ *
+ *  (1) LEGACY BOUNDARY -- the exact symbols the reference's Fortran host already calls when built with
+ *      -DCUDA (reference: source/chelper.f90:166-186, source/sd_driver.f90:1118-1153).  They replace
+ *      source/gpu_files/fortranData.cpp:141-185 and source/gpu_files/fort_helper.cpp:18-64 one for one:
+ *      gfortran implicit-interface calling convention, every argument by reference, 4-byte integers,
+ *      column-major arrays, 1-based atom indices.
+ *
+ *  (2) EXPLICIT API (asd_*) -- the same engine with every input passed explicitly, for the parts of the
+ *      hot path the reference never put behind its native boundary: solver choice (SDEalgh 1 midpoint /
+ *      5 Depondt), per-site damping / temperature / Lande arrays, biquadratic tables, Monte Carlo sweeps
+ *      (mc_evolve, source/MonteCarlo/montecarlo.f90:44), effective field + energy
+ *      (source/Hamiltonian/hamiltonianactions.f90:108), on-device observables
+ *      (source/Measurement/prn_averages.f90:414-456) and on-device table construction
+ *      (source/Hamiltonian/neighbourmap.f90:32, hamiltonianinit.f90:985).  INTEGRATION.md shows the
+ *      iso_c_binding interface blocks a maintainer adds to sd_driver.f90 / mc_driver.f90.
+ *
+ * All asd_* functions return 0 on success and a negative code on failure; asd_last_error() returns the
+ * message.  There is no CPU fallback: without a CUDA device every compute entry fails loudly.
+ */
+#ifndef UPPASD_B200_H
+#define UPPASD_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Legacy boundary (drop-in for source/gpu_files)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* replaces fortranData.cpp:141-148; argument order fixed by chelper.f90:171-173.  Stores pointers only. */
+void fortrandata_setconstants_(char* stt, int* SDEalgh, unsigned int* rstep, unsigned int* nstep,
+                               unsigned int* Natom, unsigned int* Mensemble, unsigned int* max_no_neigh,
+                               double* delta_t, double* gamma, double* k_bolt, double* mub, double* damping,
+                               double* binderc, double* mavg, int* mompar, char* initexc, unsigned int* do_dm,
+                               unsigned int* max_no_dmneigh, unsigned int* do_jtensor,
+                               unsigned int* do_anisotropy, unsigned int* nHam);
+
+/* replaces fortranData.cpp:151-180; argument order fixed by chelper.f90:181-184.  Stores pointers only. */
+void fortrandata_setmatrices_(double* ncoup, unsigned int* nlist, unsigned int* nlistsize, double* beff,
+                              double* b2eff, double* emomM, double* emom, double* emom2,
+                              double* external_field, double* mmom, double* btorque, double* Temp_array,
+                              double* mmom0, double* mmom2, double* mmomi, double* dm_vect,
+                              unsigned int* dmlist, unsigned int* dmlistsize, double* j_tens, double* kaniso,
+                              double* eaniso, unsigned int* taniso, double* sb, unsigned int* aHam);
+
+/* replaces fortranData.cpp:183-185 (chelper.f90:186). */
+void fortrandata_setinputdata_(int* gpu_mode, int* gpu_rng, int* gpu_rng_seed);
+
+/* replace fort_helper.cpp:52-64 (called from sd_driver.f90:1140-1142). */
+void cudamdsim_initiateconstants_(void);
+void cudamdsim_initiatematrices_(void);
+void cudamdsim_measurementphase_(void);
+
+/* gpu_mode 2 entry points (fort_helper.cpp:18-45, sd_driver.f90:1145-1147).  This build has no CPU twin:
+ * they run the same CUDA engine. */
+void cmdsim_initiateconstants_(void);
+void cmdsim_initiatefortran_(void);
+void cmdsim_measurementphase_(void);
+
+/* Extra inputs the reference never passes through fortrandata_* but whose Fortran semantics the engine
+ * honours when given (all optional; NULL keeps the legacy behaviour of one global damping, g=2):
+ *   Landeg(N), lambda1_array(N) (evolution.f90:38-44), bqlist/j_bq/bqlistsize (hamiltoniandatatype.f90:58-61). */
+void fortrandata_setextras_(double* Landeg, double* lambda1_array, double* temprescale, unsigned int* do_bq,
+                            unsigned int* nn_bq_tot, unsigned int* bqlist, unsigned int* bqlistsize,
+                            double* j_bq);
+
+/* Callbacks into the host (reference: source/gpu_files/c_helper.h:30-37, bodies in chelper.f90:73-160).
+ * When the library is linked into the Fortran program the gfortran-mangled symbols
+ * __chelper_MOD_fortran_* are picked up automatically (weak references).  A non-Fortran host registers
+ * them here instead.  mstep is passed as size_t* like the reference does (c_helper.h:30-36). */
+typedef void (*asd_cb_do_measurements)(const size_t* mstep, int* do_copy);
+typedef void (*asd_cb_measure_moment)(const double* emomM, const double* emom, const double* mmom,
+                                      const size_t* mstep);
+typedef void (*asd_cb_flush_measurements)(const size_t* mstep);
+typedef void (*asd_cb_status)(double* mavg);
+void asd_set_callbacks(asd_cb_do_measurements do_meas, asd_cb_measure_moment measure,
+                       asd_cb_flush_measurements flush, asd_cb_status status);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Explicit API
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct asd_engine asd_engine;
+
+const char* asd_last_error(void);
+int asd_device_count(void);
+
+/* device < 0: current device.  Fails when no CUDA device is present. */
+int asd_create(asd_engine** out, int device);
+void asd_destroy(asd_engine* e);
+
+/* physical constants, passed like the reference does (constants.f90:14-29 are mutable; chelper.f90:171). */
+int asd_set_constants(asd_engine* e, double gamma, double k_bolt, double mub, double mry);
+
+/* sizes + Hamiltonian look-up table aHam(N) (hamiltonianinit.f90:818-838); nHam==Natom => aHam may be NULL. */
+int asd_set_system(asd_engine* e, int Natom, int Mensemble, int nHam, const int* aHam);
+
+/* Heisenberg table: nlist(z,N) 1-based, nlistsize(NH), ncoup(z,NH) (hamiltoniandatatype.f90:14-40). */
+int asd_set_exchange(asd_engine* e, int max_no_neigh, const int* nlist, const int* nlistsize,
+                     const double* ncoup);
+/* DM table: dmlist(zdm,N), dmlistsize(NH), dm_vect(3,zdm,NH). */
+int asd_set_dm(asd_engine* e, int max_no_dmneigh, const int* dmlist, const int* dmlistsize,
+               const double* dm_vect);
+/* biquadratic table: bqlist(zbq,N), bqlistsize(NH), j_bq(zbq,NH). */
+int asd_set_bq(asd_engine* e, int nn_bq_tot, const int* bqlist, const int* bqlistsize, const double* j_bq);
+/* single-ion anisotropy: taniso(N) in {0,1,2,7}, eaniso(3,N), kaniso(2,N), sb(N). */
+int asd_set_anisotropy(asd_engine* e, const int* taniso, const double* eaniso, const double* kaniso,
+                       const double* sb);
+/* external_field(3,N,M) (calculatefields.f90:23-82) and optional spin-transfer torque field btorque(3,N,M). */
+int asd_set_external_field(asd_engine* e, const double* external_field);
+int asd_set_torque(asd_engine* e, const double* btorque);
+
+/* LLG parameters (evolution.f90:38-44): SDEalgh 1 (midpoint) or 5 (Depondt); per-site arrays of length N.
+ * mompar as updatemoments.f90:105-145; seed keys the counter-based noise generator. */
+int asd_set_llg(asd_engine* e, int SDEalgh, double delta_t, const double* Landeg, const double* lambda1_array,
+                const double* Temp_array, double temprescale, int mompar, unsigned long long seed);
+
+/* moments: emom(3,N,M) unit vectors, mmom(N,M) magnitudes, mmom0(N,M) (NULL => mmom). */
+int asd_set_moments(asd_engine* e, const double* emom, const double* mmom, const double* mmom0);
+int asd_get_moments(asd_engine* e, double* emom, double* emomM, double* mmom);
+
+/* Freeze the tables into the device layout.  Must be called after the set_* calls and before compute. */
+int asd_commit(asd_engine* e);
+
+/* effective_field (hamiltonianactions.f90:108-252): beff(3,N,M) [, beff1, beff2] on the host (any may be
+ * NULL), energy[M] in mRy with the reference's estimator (:245-250), summed over atoms per ensemble. */
+int asd_effective_field(asd_engine* e, double* beff, double* beff1, double* beff2, double* energy);
+
+/* nsteps LLG steps = field / evolve_first / field / evolve_second / moment_update each
+ * (sd_driver.f90:668-764).  first_step is the value of mstep for the first step (keys the noise). */
+int asd_sd_steps(asd_engine* e, long nsteps, long first_step);
+
+/* nsweeps Monte Carlo sweeps (mc_evolve, montecarlo.f90:44-273): mode 'M' Metropolis / 'H' heat bath,
+ * N*M single-spin trials per sweep visited colour by colour (graph colouring of the union of all
+ * neighbour tables).  extfield[3] is mc_evolve's uniform field argument. */
+int asd_mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, double temperature,
+                  double temprescale, const double* extfield);
+
+/* On-device observables: msum(3,M) = sum_i emomM(:,i,k) (prn_averages.f90:437-447); energy[M] as above
+ * (NULL to skip). */
+int asd_measure(asd_engine* e, double* msum, double* energy);
+
+/* Device-timing helper for bench.py: runs nsteps steps bracketed by CUDA events on the engine's stream
+ * and returns the elapsed milliseconds; per-kernel time of the two stage kernels in stage_ms[2]. */
+int asd_time_sd_steps(asd_engine* e, long nsteps, long first_step, float* total_ms, float* stage_ms);
+int asd_time_mc_sweeps(asd_engine* e, char mode, long nsweeps, double temperature, float* total_ms);
+
+/* number of kernel launches issued by this engine so far (bench.py's gpu_launches). */
+long asd_launch_count(asd_engine* e);
+int asd_synchronize(asd_engine* e);
+
+/* ---- on-device table construction ----------------------------------------------
+ * Builds nlist / couplings for a periodic or open supercell directly in device memory from the unit-cell
+ * stencil, bit-identical to setup_nm + setup_neighbour_hamiltonian (neighbourmap.f90:248-321,
+ * hamiltonianinit.f90:1040-1091).  kind: 0 exchange, 1 DM (3 components), 2 biquadratic.
+ *   nslot[NA]                 number of stencil entries of basis atom i0
+ *   cell_atom[NA*maxslot]     j0 (1-based basis atom hit), stencil order = shell-major, image order
+ *   cell_shift[NA*maxslot*3]  (dx,dy,dz) cell translation of each entry
+ *   coupling[NA*maxslot*ncomp] coupling of each entry, already unit-converted (what ncoup would hold)
+ * The engine must have been given asd_set_system with do_reduced semantics (nHam = NA or Natom). */
+int asd_build_lattice_table(asd_engine* e, int kind, int NA, int N1, int N2, int N3, const char* bc3,
+                            int maxslot, const int* nslot, const int* cell_atom, const int* cell_shift,
+                            const double* coupling);
+/* copies a built / uploaded table back in Fortran layout: list(z,N) 1-based, listsize(NH), coup(ncomp,z,NH). */
+int asd_get_table_dims(asd_engine* e, int kind, int* z, int* ncomp);
+int asd_get_table(asd_engine* e, int kind, int* list, int* listsize, double* coup);
+
+/* moments generated on the device for large synthetic runs (bench): e_i = normalize(1, a sin(2 pi h_i),
+ * a cos(2 pi h_i)), h_i = frac(i * 0.6180339887), i the 1-based atom index; magnitude per basis atom. */
+int asd_init_moments_tilted(asd_engine* e, double amplitude, int NA, const double* mmom_basis);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UPPASD_B200_H */

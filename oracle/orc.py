@@ -297,3 +297,56 @@ def fill_rngarray(n):
     out = np.zeros(n)
     lib().orc_fill_rngarray(_p(out), C.c_long(n))
     return out
+
+
+# ---- thermal LLG and Monte Carlo replays (reference RNG streams) --------------------------------
+def sd_run_thermal(S, sdealgh, delta_t, damping, temp, nstep, seed=1, sample_every=10, burn=0):
+    """Thermal LLG with the reference's noise source: each step draws 3*N*M ziggurat normals in memory order
+    (rannum -> fill_rngarray, randomnumbers.f90:709-732).  Returns per-sample |M|/N per ensemble."""
+    zig_setup(seed)
+    st = SdState(S, sdealgh, delta_t, damping, temp=temp)
+    N, M = S['Natom'], S['Mensemble']
+    out = []
+    for step in range(1, nstep + 1):
+        g = fill_rngarray(3 * N * M).reshape((3, N, M), order='F')
+        st.step(gauss=g)
+        if step > burn and step % sample_every == 0:
+            m = st.sum_moments() / N
+            out.append(np.sqrt((m ** 2).sum(axis=0)))
+    return np.array(out), st
+
+
+def mc_run(S, mode, temperature, nsweeps, seed=1, sample_every=1, burn=0, extfield=(0.0, 0.0, 0.0)):
+    """mc_mphase replay (source/mc_driver.f90:234-430): visiting order from choose_random_atom_x, redrawn every
+    mcnstep/10 sweeps; per sweep the bulk draws of mc_evolve in the reference's order."""
+    L = lib()
+    rng_init(seed)
+    zig_setup(seed)
+    N, M = S['Natom'], S['Mensemble']
+    H = ham_struct(S)
+    emom = S['emom'].copy(order='F')
+    emomM = S['emomM'].copy(order='F')
+    mmom = S['mmom'].copy(order='F')
+    iflip = np.zeros(N, dtype=np.int32)
+    L.orc_choose_random_atom_x(N, _p(iflip))
+    ef = np.ascontiguousarray(extfield, dtype=np.float64)
+    mags, ens = [], []
+    for sweep in range(1, nsweeps + 1):
+        fm = rng_uniform(3 * N * M)
+        fg = fill_rngarray(3 * N * M)
+        mf = rng_uniform(N * M) if mode == 'H' else None
+        fa = rng_uniform(N * M)
+        L.orc_mc_sweep(C.byref(H), C.c_char(mode.encode()), _p(iflip), _p(emomM), _p(emom), _p(mmom), _p(ef),
+                       _p(S['external_field']), _d(temperature), _d(1.0), _p(fm), _p(fg), _p(mf), _p(fa),
+                       _d(CONST['k_bolt']), _d(CONST['mub']))
+        if sweep % max(1, nsweeps // 10) == 0:
+            L.orc_choose_random_atom_x(N, _p(iflip))
+        if sweep > burn and sweep % sample_every == 0:
+            m = np.zeros((3, M), order='F')
+            L.orc_sum_moments(N, M, _p(emomM), _p(m))
+            mags.append(np.sqrt(((m / N) ** 2).sum(axis=0)))
+            beff = np.zeros((3, N, M), order='F')
+            e = L.orc_effective_field(C.byref(H), _p(emomM), _p(S['external_field']), _p(beff), None, None,
+                                      _d(CONST['mub']), _d(CONST['mry']))
+            ens.append(e / (N * M))
+    return np.array(mags), np.array(ens), (emom, emomM, mmom)

@@ -1,0 +1,186 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the reference goldens.
+
+Tolerances: T=0 field and trajectory within 1e-12 relative in FP64 (BASELINE.json north_star); table
+construction bit-exact; thermal / Monte Carlo runs on observables within statistical error bars.
+"""
+import numpy as np
+import pytest
+
+from oracle import orc
+from util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+FIX = ['kagome', 'megatest', 'feco', 'bccfe_cuda']
+
+
+def _engine(S, inp, **kw):
+    from uppasd_b200 import host
+    args = dict(sdealgh=inp['sdealgh'], delta_t=inp['timestep'], damping=inp['damping'], temp=0.0, mompar=inp['mompar'])
+    args.update(kw)
+    return host.engine_from_system(S, orc.CONST, **args)
+
+
+@pytest.mark.parametrize('name', FIX)
+def test_field_parity(name):
+    fx, inp, S = load_golden(name)
+    e = _engine(S, inp)
+    beff, b1, b2, en = e.effective_field(parts=True)
+    rb, r1, r2, ren = orc.effective_field(S, want_parts=True)
+    scale = np.abs(rb).max()
+    assert np.abs(beff - rb).max() <= 1e-12 * scale
+    assert np.abs(b1 - r1).max() <= 1e-12 * scale
+    assert np.abs(b2 - r2).max() <= 1e-12 * scale + 1e-300
+    assert abs(en[0] - ren) <= 1e-12 * abs(ren)
+
+
+@pytest.mark.parametrize('name', FIX)
+@pytest.mark.parametrize('alg', [1, 5])
+def test_t0_trajectory(name, alg):
+    fx, inp, S = load_golden(name)
+    e = _engine(S, inp, sdealgh=alg)
+    st = orc.SdState(S, alg, inp['timestep'], inp['damping'])
+    done = 0
+    for n in (1, 9, 190):
+        e.sd_steps(n, first_step=done + 1)
+        for _ in range(n):
+            st.step()
+        done += n
+        emom, emomM, mmom = e.get_moments()
+        assert np.abs(emom - st.emom).max() <= 1e-12, (name, alg, done)
+        assert np.abs(emomM - st.emomM).max() <= 1e-12 * np.abs(st.emomM).max()
+    # norm is conserved by both schemes
+    assert np.abs(np.sqrt((emom ** 2).sum(axis=0)) - 1.0).max() < 1e-12
+
+
+def test_kagome_golden_on_gpu():
+    fx, inp, S = load_golden('kagome')
+    e = _engine(S, inp)
+    e.sd_steps(2400)
+    emom, emomM, mmom = e.get_moments()
+    exp = fx['expected']['trajectory']['2400']
+    for a, b in zip(list(emom[:, 1, 0]) + [mmom[1, 0]], exp):
+        assert abs(a - b) <= 1e-8
+    e.sd_steps(13000 - 2400, first_step=2401)
+    msum = e.measure()
+    av = msum[:, 0] / S['Natom']
+    got = list(av) + [float(np.sqrt((av ** 2).sum()))]
+    for a, b in zip(got, fx['expected']['averages']['13000']):
+        assert abs(a - b) <= 1e-8, (got, fx['expected'])
+
+
+def test_megatest_golden_on_gpu():
+    fx, inp, S = load_golden('megatest')
+    e = _engine(S, inp)
+    e.sd_steps(11000)
+    emom, emomM, mmom = e.get_moments()
+    exp = fx['expected']
+    av = emomM[:, :, 0].sum(axis=1) / S['Natom']
+    got = list(av) + [float(np.sqrt((av ** 2).sum()))]
+    for a, b in zip(got, exp['averages']['11000']):
+        assert abs(a - b) <= 1e-8
+    for a, b in zip(emom[:, exp['moment']['atom'] - 1, 0], exp['moment']['11000']):
+        assert abs(a - b) <= 1e-8
+
+
+def test_legacy_boundary_kagome():
+    """Drives the drop-in symbols the way FortranData_Initiate + sd_mphaseCUDA do (chelper.f90:166-186)."""
+    from uppasd_b200 import host
+    fx, inp, S = load_golden('kagome')
+    fh = host.FortranHost(S, orc.CONST, sdealgh=1, nstep=13001, delta_t=inp['timestep'], damping=inp['damping'],
+                          avrg_step=inp['avrg_step']).run()
+    for a, b in zip(fh.averages[13000], fx['expected']['averages']['13000']):
+        assert abs(a - b) <= 1e-8
+    assert fh.flushed_at == 13002
+    # final state written back to the host arrays (restart file is written from them, uppasd.f90:344-350)
+    st = orc.sd_run(S, inp, nstep=13001)['state']
+    assert np.abs(fh.arr['emom'] - st.emom).max() <= 1e-10
+    assert np.allclose(fh.arr['mmomi'], 1.0 / fh.arr['mmom'])
+
+
+def test_ensembles_and_external_field_array():
+    fx, inp, S = load_golden('megatest')
+    # 3 ensembles with different starting states and a non-uniform external field array
+    from oracle import inputs
+    args = list(inputs.load_fixture(fx))
+    args[0] = dict(args[0], mensemble=3)
+    S = orc.build_system(*args)
+    rng = np.random.default_rng(7)
+    N, M = S['Natom'], 3
+    e0 = rng.normal(size=(3, N, M))
+    e0 /= np.sqrt((e0 ** 2).sum(axis=0))
+    S['emom'] = np.asfortranarray(e0)
+    S['emomM'] = np.asfortranarray(e0 * S['mmom'][None])
+    S['external_field'] = np.asfortranarray(rng.normal(size=(3, N, M)) * 0.1)
+    e = _engine(S, inp)
+    st = orc.SdState(S, 1, inp['timestep'], inp['damping'])
+    e.sd_steps(50)
+    for _ in range(50):
+        st.step()
+    emom, _, _ = e.get_moments()
+    assert np.abs(emom - st.emom).max() <= 1e-12
+
+
+def test_anisotropy_bq_mompar_terms():
+    """Uniaxial+cubic (taniso 7/1/2), biquadratic and mompar paths against the oracle on a perturbed megaTest."""
+    fx, inp, S = load_golden('megatest')
+    N = S['Natom']
+    rng = np.random.default_rng(11)
+    ta = np.array([1, 2, 7, 0] * (N // 4), dtype=np.int32)
+    ea = rng.normal(size=(3, N)); ea /= np.sqrt((ea ** 2).sum(axis=0))
+    S['aniso'] = dict(taniso=ta, eaniso=np.asfortranarray(ea), kaniso=np.asfortranarray(rng.normal(size=(2, N)) * 0.5),
+                      sb=rng.uniform(0.1, 1.0, size=N))
+    # biquadratic table: reuse the exchange lists with their own couplings
+    ex = S['exchange']
+    S['bq'] = dict(list=ex['list'], listsize=ex['listsize'], coup=np.asfortranarray(ex['coup'] * 0.03), z=ex['z'])
+    e0 = rng.normal(size=(3, N, 1)); e0 /= np.sqrt((e0 ** 2).sum(axis=0))
+    S['emom'] = np.asfortranarray(e0)
+    S['emomM'] = np.asfortranarray(e0 * S['mmom'][None])
+    for mompar in (0, 1, 2):
+        e = _engine(S, inp, mompar=mompar)
+        beff, en = e.effective_field()
+        rb, ren = orc.effective_field(S)
+        assert np.abs(beff - rb).max() <= 1e-12 * np.abs(rb).max()
+        assert abs(en[0] - ren) <= 1e-11 * abs(ren)
+        for alg in (1, 5):
+            e = _engine(S, inp, mompar=mompar, sdealgh=alg)
+            st = orc.SdState(S, alg, inp['timestep'], inp['damping'], mompar=mompar)
+            e.sd_steps(40)
+            for _ in range(40):
+                st.step()
+            emom, emomM, mmom = e.get_moments()
+            assert np.abs(emom - st.emom).max() <= 1e-12
+            assert np.abs(mmom - st.mmom).max() <= 1e-12 * st.mmom.max()
+
+
+def test_full_hamiltonian_matches_reduced():
+    """do_reduced N (NH = Natom, per-atom couplings) must give the same dynamics as do_reduced Y."""
+    from oracle import inputs
+    fx, inp, S = load_golden('bccfe_cuda')
+    args = list(inputs.load_fixture(fx))
+    args[0] = dict(args[0], do_reduced='N')
+    Sf = orc.build_system(*args)
+    assert Sf['nHam'] == Sf['Natom']
+    e1, e2 = _engine(S, inp, sdealgh=1), _engine(Sf, inp, sdealgh=1)
+    e1.sd_steps(100); e2.sd_steps(100)
+    a, _, _ = e1.get_moments(); b, _, _ = e2.get_moments()
+    assert np.abs(a - b).max() <= 1e-13
+    st = orc.SdState(Sf, 1, inp['timestep'], inp['damping'])
+    for _ in range(100):
+        st.step()
+    assert np.abs(b - st.emom).max() <= 1e-12
+
+
+def test_errors_are_loud():
+    from uppasd_b200 import host
+    fx, inp, S = load_golden('kagome')
+    e = host.Engine()
+    with pytest.raises(host.AsdError):
+        e.commit()
+    e.set_system(S['Natom'], 1, S['nHam'], S['aHam'])
+    with pytest.raises(host.AsdError):
+        e.set_llg(2, 1e-16)            # Heun is not on this path
+    bad = S['exchange']['list'].copy(order='F'); bad[0, 5] = 0
+    e.set_exchange(bad, S['exchange']['listsize'], S['exchange']['coup'])
+    with pytest.raises(host.AsdError):
+        e.commit()                     # reduced Hamiltonian with a missing neighbour

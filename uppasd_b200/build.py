@@ -1,0 +1,32 @@
+"""Builds libuppasd_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, 'csrc', 'asd_engine.cu')
+DEPS = [os.path.join(HERE, 'csrc', f) for f in os.listdir(os.path.join(HERE, 'csrc'))] + \
+       [os.path.join(HERE, '..', 'include', 'uppasd_b200.h')]
+OUT = os.path.join(HERE, 'libuppasd_b200.so')
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math=false',
+         '-Xcompiler', '-fPIC', '-shared', '-ccbin', 'g++']
+
+
+def build(force=False, verbose=False):
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS):
+        return OUT
+    flags = [f for f in FLAGS if f != '--use_fast_math=false']
+    cmd = [NVCC] + flags + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT, SRC]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError('nvcc failed')
+    if verbose:
+        print(res.stderr)
+    return OUT
+
+
+if __name__ == '__main__':
+    build(force=True, verbose='-v' in sys.argv)
+    print('built', OUT)

@@ -1,0 +1,555 @@
+// Device code of the B200-native spin-dynamics hot path (sm_100a).
+//
+// Data layout in HBM:
+//   * spins are packed as 32-byte vectors {ex, ey, ez, m} (unit direction + magnitude), one 256-bit
+//     load (LDG.E.256) per gathered neighbour, two buffers per ensemble: `cur` (state at t) and `pred`
+//     (midpoint / predictor state);
+//   * atoms are stored in DEVICE ORDER: grouped by Hamiltonian index (aHam) and padded per group to a
+//     multiple of 32, so that a warp always works on one sublattice: its coupling reads are broadcasts
+//     and its neighbour gathers are unit-stride;
+//   * neighbour tables are slot-major  nl[j][Npad]  (device indices), so a warp reads 128 contiguous bytes
+//     per neighbour slot; reduced-Hamiltonian couplings are staged in shared memory once per CTA.
+//
+// What each routine restates (reference paths relative to the reference root):
+//   site_field        source/Hamiltonian/hamiltonianactions.f90:185-243 (term order kept: Heisenberg, DM,
+//                     BQ, anisotropy, external field; neighbour order j = 1..nlistsize kept)
+//   midpoint stages   source/Evolution/midpoint.f90:123-178, :274-319
+//   Depondt stages    source/Evolution/depondt.f90:136-190, :284-331
+//   moment update     source/Evolution/updatemoments.f90:48-145
+//   noise amplitude   source/RNG/randomnumbers.f90:667-670,735-746 (midpoint), depondt.f90:143-145
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace asd {
+
+struct __align__(32) SpinVec {
+   double x, y, z, m;
+};
+
+// Kernel parameter block (passed by value; < 4 KB).
+struct Tables {
+   int N;      // real atoms
+   int Npad;   // device slots (groups padded to 32)
+   int M;      // ensembles
+   int NH;     // Hamiltonian rows
+   int reduced;  // 1: couplings indexed by ham row (shared by a whole sublattice), 0: per atom
+   const int* __restrict__ ham;   // [Npad] 0-based ham row of the slot, -1 for padding slots
+   const int* __restrict__ orig;  // [Npad] 0-based original atom index, -1 for padding slots
+   // Heisenberg
+   int z;
+   const int* __restrict__ nl;      // [z][Npad] device index of neighbour
+   const double* __restrict__ cp;   // reduced: [NH][z]; else [z][Npad]
+   const int* __restrict__ lsize;   // reduced: [NH]; else unused (zero-padded couplings)
+   // DM
+   int zdm;
+   const int* __restrict__ dml;     // [zdm][Npad]
+   const double* __restrict__ dmv;  // reduced: [NH][zdm][3]; else [3][zdm][Npad]
+   const int* __restrict__ dmsize;
+   // BQ
+   int zbq;
+   const int* __restrict__ bql;
+   const double* __restrict__ jbq;  // reduced: [NH][zbq]; else [zbq][Npad]
+   const int* __restrict__ bqsize;
+   // anisotropy (device order)
+   int do_aniso;
+   const int* __restrict__ taniso;     // [Npad]
+   const double* __restrict__ eaniso;  // [3][Npad]
+   const double* __restrict__ kaniso;  // [2][Npad]
+   const double* __restrict__ sb;      // [Npad]
+   // external field: uniform vector or per-slot array [M][3][Npad]
+   int ext_uniform;
+   double hext[3];
+   const double* __restrict__ ext;
+   // spin-transfer torque field btorque [M][3][Npad] or null
+   const double* __restrict__ btorque;
+   // shared-memory staging of reduced couplings (doubles): cp | dmv | jbq
+   int sm_cp, sm_dm, sm_bq;  // element counts (0 => read from global)
+};
+
+struct LlgParams {
+   int per_site;        // 1: read Landeg/lambda/Temp arrays (device order), 0: uniform scalars
+   double landeg, lambda, temp;
+   const double* __restrict__ landeg_a;
+   const double* __restrict__ lambda_a;
+   const double* __restrict__ temp_a;
+   double delta_t, gamma, k_bolt, mub, temprescale;
+   int mompar;
+   const double* __restrict__ mmom0;  // [M][Npad], only read when mompar != 0
+   unsigned long long seed;
+   unsigned long long step;  // value of mstep for this step (keys the noise)
+   int thermal;              // 0: skip noise entirely
+};
+
+// ------------------------------------------------------------------------------------------------
+// Counter-based Gaussian noise: Philox4x32-10 (Salmon et al. 2011) keyed by the run seed; the counter is
+// (original atom index, ensemble, step, draw) so the stream is independent of device order, of the slab /
+// ensemble decomposition and of the GPU count.  Two calls give four 64-bit words -> two Box-Muller pairs.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t* out) {
+   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+   for (int r = 0; r < 10; r++) {
+      uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+      uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+      uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      k0 += W0; k1 += W1;
+   }
+   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, uint32_t c, uint32_t d, double& g0, double& g1) {
+   const uint64_t w0 = ((uint64_t)a << 32) | b, w1 = ((uint64_t)c << 32) | d;
+   const double u1 = (double)((w0 >> 11) + 1ull) * (1.0 / 9007199254740992.0);  // (0,1]
+   const double u2 = (double)(w1 >> 11) * (1.0 / 9007199254740992.0);           // [0,1)
+   const double rad = sqrt(-2.0 * log(u1));
+   double s, c2;
+   sincospi(2.0 * u2, &s, &c2);
+   g0 = rad * c2;
+   g1 = rad * s;
+}
+
+// three N(0,1) numbers for (atom, ensemble, step); `stream` separates LLG noise from MC draws.
+__device__ __forceinline__ void gauss3(unsigned long long seed, uint32_t atom, uint32_t ens, unsigned long long step,
+                                       uint32_t stream, double& g0, double& g1, double& g2) {
+   uint32_t r[4];
+   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+   const uint32_t s_lo = (uint32_t)step, s_hi = (uint32_t)(step >> 32) ^ (stream << 24);
+   philox4x32_10(atom, ens, s_lo, s_hi, k0, k1, r);
+   box_muller(r[0], r[1], r[2], r[3], g0, g1);
+   double dummy;
+   philox4x32_10(atom, ens | 0x80000000u, s_lo, s_hi, k0, k1, r);
+   box_muller(r[0], r[1], r[2], r[3], g2, dummy);
+}
+
+// four U[0,1) numbers (53-bit) for Monte Carlo draws
+__device__ __forceinline__ void uniform4(unsigned long long seed, uint32_t atom, uint32_t ens, unsigned long long step,
+                                         uint32_t stream, double* u) {
+   uint32_t r[4];
+   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+   const uint32_t s_lo = (uint32_t)step, s_hi = (uint32_t)(step >> 32) ^ (stream << 24);
+   philox4x32_10(atom, ens, s_lo, s_hi, k0, k1, r);
+   u[0] = (double)((((uint64_t)r[0] << 32) | r[1]) >> 11) * (1.0 / 9007199254740992.0);
+   u[1] = (double)((((uint64_t)r[2] << 32) | r[3]) >> 11) * (1.0 / 9007199254740992.0);
+   philox4x32_10(atom, ens | 0x80000000u, s_lo, s_hi, k0, k1, r);
+   u[2] = (double)((((uint64_t)r[0] << 32) | r[1]) >> 11) * (1.0 / 9007199254740992.0);
+   u[3] = (double)((((uint64_t)r[2] << 32) | r[3]) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Effective field of one site.  S = spin buffer of this ensemble (device order).  Returns the bilinear
+// part (bs: exchange, DM, uniaxial) and the "q" part (bq: biquadratic, cubic part of taniso 7), like
+// beff_s / beff_q in hamiltonianactions.f90:185-238.  own = this site's packed spin in S.
+// smc/smd/smb: shared-memory copies of the reduced couplings (or null -> global).
+// ------------------------------------------------------------------------------------------------
+template <bool REDUCED>
+__device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __restrict__ S, int i, int ih,
+                                           const SpinVec& own, const double* smc, const double* smd,
+                                           const double* smb, double bs[3], double bq[3]) {
+   double fx = 0.0, fy = 0.0, fz = 0.0;
+   const int Npad = t.Npad;
+   // ---- Heisenberg (hamiltonianactions.f90:461-464) ----
+   {
+      const int* __restrict__ nl = t.nl + i;
+      if (REDUCED) {
+         const int n = __ldg(t.lsize + ih);
+         const double* __restrict__ c = smc ? smc + (size_t)ih * t.z : t.cp + (size_t)ih * t.z;
+#pragma unroll 10
+         for (int j = 0; j < n; j++) {
+            const int nb = __ldg(nl + (size_t)j * Npad);
+            const SpinVec v = S[nb];
+            const double cj = c[j];
+            fx = fma(cj, v.x * v.m, fx);
+            fy = fma(cj, v.y * v.m, fy);
+            fz = fma(cj, v.z * v.m, fz);
+         }
+      } else {
+         const double* __restrict__ c = t.cp + i;
+#pragma unroll 10
+         for (int j = 0; j < t.z; j++) {
+            const int nb = __ldg(nl + (size_t)j * Npad);
+            const double cj = __ldg(c + (size_t)j * Npad);
+            const SpinVec v = S[nb];
+            fx = fma(cj, v.x * v.m, fx);
+            fy = fma(cj, v.y * v.m, fy);
+            fz = fma(cj, v.z * v.m, fz);
+         }
+      }
+   }
+   // ---- Dzyaloshinskii-Moriya (hamiltonianactions.f90:565-571) ----
+   if (t.zdm > 0) {
+      const int* __restrict__ nl = t.dml + i;
+      const int n = REDUCED ? __ldg(t.dmsize + ih) : t.zdm;
+      for (int j = 0; j < n; j++) {
+         const int nb = __ldg(nl + (size_t)j * Npad);
+         double Dx, Dy, Dz;
+         if (REDUCED) {
+            const double* __restrict__ d = (smd ? smd : t.dmv) + ((size_t)ih * t.zdm + j) * 3;
+            Dx = d[0]; Dy = d[1]; Dz = d[2];
+         } else {
+            const size_t o = (size_t)j * Npad + i, s = (size_t)t.zdm * Npad;
+            Dx = __ldg(t.dmv + o); Dy = __ldg(t.dmv + s + o); Dz = __ldg(t.dmv + 2 * s + o);
+         }
+         const SpinVec v = S[nb];
+         const double mx = v.x * v.m, my = v.y * v.m, mz = v.z * v.m;
+         fx = fx + Dz * my - Dy * mz;
+         fy = fy + Dx * mz - Dz * mx;
+         fz = fz + Dy * mx - Dx * my;
+      }
+   }
+   double qx = 0.0, qy = 0.0, qz = 0.0;
+   const double ox = own.x * own.m, oy = own.y * own.m, oz = own.z * own.m;  // emomM of this site
+   // ---- biquadratic (hamiltonianactions.f90:790-795) ----
+   if (t.zbq > 0) {
+      const int* __restrict__ nl = t.bql + i;
+      const int n = REDUCED ? __ldg(t.bqsize + ih) : t.zbq;
+      for (int j = 0; j < n; j++) {
+         const int nb = __ldg(nl + (size_t)j * Npad);
+         const double jb = REDUCED ? (smb ? smb : t.jbq)[(size_t)ih * t.zbq + j] : __ldg(t.jbq + (size_t)j * Npad + i);
+         const SpinVec v = S[nb];
+         const double mx = v.x * v.m, my = v.y * v.m, mz = v.z * v.m;
+         const double dot = mx * ox + my * oy + mz * oz;
+         const double c = 2.0 * jb * dot;
+         qx = fma(c, mx, qx);
+         qy = fma(c, my, qy);
+         qz = fma(c, mz, qz);
+      }
+   }
+   // ---- single-ion anisotropy (hamiltonianactions.f90:225-239, 842-919); uses the FULL moment ----
+   if (t.do_aniso) {
+      const int ta = __ldg(t.taniso + i);
+      if (ta == 1 || ta == 2 || ta == 7) {
+         const double k1 = __ldg(t.kaniso + i), k2 = __ldg(t.kaniso + Npad + i);
+         if (ta == 1 || ta == 7) {
+            const double ex = __ldg(t.eaniso + i), ey = __ldg(t.eaniso + Npad + i), ez = __ldg(t.eaniso + 2 * (size_t)Npad + i);
+            const double tt1 = ox * ex + oy * ey + oz * ez;
+            const double tt2 = k1 + 2.0 * k2 * (1.0 - tt1 * tt1);
+            const double tt3 = 2.0 * tt1 * tt2;
+            fx -= tt3 * ex; fy -= tt3 * ey; fz -= tt3 * ez;
+         }
+         if (ta == 2 || ta == 7) {
+            const double x2 = ox * ox, y2 = oy * oy, z2 = oz * oz;
+            const double cx = 2.0 * k1 * ox * (y2 + z2) + 2.0 * k2 * ox * (y2 * z2);
+            const double cy = 2.0 * k1 * oy * (z2 + x2) + 2.0 * k2 * oy * (z2 * x2);
+            const double cz = 2.0 * k1 * oz * (x2 + y2) + 2.0 * k2 * oz * (x2 * y2);
+            if (ta == 2) { fx += cx; fy += cy; fz += cz; }
+            else { const double s = __ldg(t.sb + i); qx += cx * s; qy += cy * s; qz += cz * s; }
+         }
+      }
+   }
+   bs[0] = fx; bs[1] = fy; bs[2] = fz;
+   bq[0] = qx; bq[1] = qy; bq[2] = qz;
+}
+
+// external field of slot i, ensemble k (external_field + time_external_field(=0), hamiltonianactions.f90:241)
+__device__ __forceinline__ void ext_field(const Tables& t, int i, int k, double h[3]) {
+   if (t.ext_uniform) { h[0] = t.hext[0]; h[1] = t.hext[1]; h[2] = t.hext[2]; }
+   else {
+      const double* __restrict__ p = t.ext + (size_t)k * 3 * t.Npad + i;
+      h[0] = __ldg(p); h[1] = __ldg(p + t.Npad); h[2] = __ldg(p + 2 * (size_t)t.Npad);
+   }
+}
+
+// stage the reduced couplings into shared memory (once per CTA); returns pointers (null => use global)
+__device__ __forceinline__ void stage_couplings(const Tables& t, double* sm, const double*& smc, const double*& smd,
+                                                const double*& smb) {
+   smc = smd = smb = nullptr;
+   const int n0 = t.sm_cp, n1 = t.sm_dm, n2 = t.sm_bq;
+   if (n0 + n1 + n2 == 0) return;
+   for (int q = threadIdx.x; q < n0; q += blockDim.x) sm[q] = t.cp[q];
+   for (int q = threadIdx.x; q < n1; q += blockDim.x) sm[n0 + q] = t.dmv[q];
+   for (int q = threadIdx.x; q < n2; q += blockDim.x) sm[n0 + n1 + q] = t.jbq[q];
+   __syncthreads();
+   if (n0) smc = sm;
+   if (n1) smd = sm + n0;
+   if (n2) smb = sm + n0 + n1;
+}
+
+// Cayley transform of the semi-implicit midpoint scheme (midpoint.f90:153-164): (I+skew A)^-1 (I+skew A)^T e
+__device__ __forceinline__ void cayley(const double e[3], const double A[3], double out[3]) {
+   const double detAi = 1.0 / (1.0 + (A[0] * A[0] + A[1] * A[1] + A[2] * A[2]));
+   const double a0 = e[0] + e[1] * A[2] - e[2] * A[1];
+   const double a1 = e[1] + e[2] * A[0] - e[0] * A[2];
+   const double a2 = e[2] + e[0] * A[1] - e[1] * A[0];
+   const double t0 = a0 * (1 + A[0] * A[0]) + a1 * (A[0] * A[1] + A[2]) + a2 * (A[0] * A[2] - A[1]);
+   const double t1 = a0 * (A[1] * A[0] - A[2]) + a1 * (1 + A[1] * A[1]) + a2 * (A[1] * A[2] + A[0]);
+   const double t2 = a0 * (A[2] * A[0] + A[1]) + a1 * (A[2] * A[1] - A[0]) + a2 * (1 + A[2] * A[2]);
+   out[0] = t0 * detAi; out[1] = t1 * detAi; out[2] = t2 * detAi;
+}
+
+// Rodrigues rotation of the Depondt scheme (depondt.f90:157-179)
+__device__ __forceinline__ void rodrigues(const double bd[3], const double e[3], double dtg_lldamp, double out[3]) {
+   double Bnorm = sqrt(bd[0] * bd[0] + bd[1] * bd[1] + bd[2] * bd[2]) + 1.0e-15;
+   const double hx = bd[0] / Bnorm, hy = bd[1] / Bnorm, hz = bd[2] / Bnorm;
+   const double v = Bnorm * dtg_lldamp;
+   double sinv, cosv;
+   sincos(v, &sinv, &cosv);
+   const double u = 1.0 - cosv;
+   out[0] = hx * hx * u * e[0] + cosv * e[0] + hx * hy * u * e[1] - hz * sinv * e[1] + hx * hz * u * e[2] + hy * sinv * e[2];
+   out[1] = hy * hx * u * e[0] + hz * sinv * e[0] + hy * hy * u * e[1] + cosv * e[1] + hy * hz * u * e[2] - hx * sinv * e[2];
+   out[2] = hx * hz * u * e[0] - hy * sinv * e[0] + hz * hy * u * e[1] + hx * sinv * e[1] + hz * hz * u * e[2] + cosv * e[2];
+}
+
+// moment magnitude update (updatemoments.f90:105-145)
+__device__ __forceinline__ double calcm(int mompar, double m, double m0, double ez) {
+   if (mompar == 1) return fmax(m0 * fabs(ez), 1e-4);
+   if (mompar == 2) return fmax(m0 * (ez * ez), 1.0e-4);
+   return m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One stage of one LLG step, field evaluation fused with the integrator.
+//   SOLVER 1 = semi-implicit midpoint, 5 = Depondt.   STAGE 1 = predictor, 2 = corrector (+ moment update).
+//   STAGE 1: gathers from `cur`, writes `pred` (midpoint spin for SOLVER 1, rotated spin for SOLVER 5);
+//   STAGE 2: gathers from `pred`, reads own `cur`, writes the new spin to `cur` (own slot only).
+//   b2eff (Depondt only): [M][3][Npad] predictor field kept for the Heun average.
+// ------------------------------------------------------------------------------------------------
+template <int SOLVER, int STAGE, bool REDUCED>
+__global__ void __launch_bounds__(256)
+llg_stage_kernel(const Tables t, const LlgParams p, SpinVec* __restrict__ cur, SpinVec* __restrict__ pred,
+                 double* __restrict__ b2eff) {
+   extern __shared__ double sm[];
+   const double *smc, *smd, *smb;
+   stage_couplings(t, sm, smc, smd, smb);
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   const int k = blockIdx.y;
+   if (i >= t.Npad) return;
+   int ih = 0;
+   if (REDUCED) { ih = __ldg(t.ham + i); if (ih < 0) return; }
+   else if (__ldg(t.orig + i) < 0) return;
+   SpinVec* __restrict__ curk = cur + (size_t)k * t.Npad;
+   SpinVec* __restrict__ predk = pred + (size_t)k * t.Npad;
+   const SpinVec* __restrict__ S = (STAGE == 1) ? curk : predk;
+   const SpinVec own = S[i];
+   double bs[3], bq[3], h[3];
+   site_field<REDUCED>(t, S, i, ih, own, smc, smd, smb, bs, bq);
+   ext_field(t, i, k, h);
+   // beff = beff1 + beff2, beff2 = beff_q + external_field (hamiltonianactions.f90:240-243)
+   double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
+   double lam, lg, temp;
+   if (p.per_site) { lam = __ldg(p.lambda_a + i); lg = __ldg(p.landeg_a + i); temp = __ldg(p.temp_a + i); }
+   else { lam = p.lambda; lg = p.landeg; temp = p.temp; }
+   const SpinVec c0 = (STAGE == 1) ? own : curk[i];  // spin at time t
+   const double e[3] = {c0.x, c0.y, c0.z};
+   const double m = c0.m;
+   double g[3] = {0.0, 0.0, 0.0};
+   if (p.thermal) gauss3(p.seed, (uint32_t)__ldg(t.orig + i), (uint32_t)k, p.step, 0u, g[0], g[1], g[2]);
+   double bt[3] = {0.0, 0.0, 0.0};
+   if (t.btorque) {
+      const double* __restrict__ q = t.btorque + (size_t)k * 3 * t.Npad + i;
+      bt[0] = __ldg(q); bt[1] = __ldg(q + t.Npad); bt[2] = __ldg(q + 2 * (size_t)t.Npad);
+   }
+   const double lldamp = 1.0 / (1.0 + lam * lam);
+   if (SOLVER == 1) {
+      // ---- Mentink's semi-implicit midpoint (midpoint.f90) ----
+      const double dt = p.delta_t * 1.0 * p.gamma * lldamp;  // bn = 1
+      const double sqrtdt = sqrt(dt);
+      const double dtg = dt * lg, sqrtdtg = sqrtdt * lg;
+      // rannum (randomnumbers.f90:667-670,735-746): sigma = sqrt(2 D), D = lam/(1+lam^2) k_B/(gamma mu_B) gamma / m * T
+      double sigma = 0.0;
+      if (p.thermal) {
+         const double Dk = (lam / (1 + lam * lam) * p.k_bolt / p.gamma / (p.mub)) * (p.gamma / 1.0);
+         const double D = Dk * (1.0 / m) * temp * p.temprescale;
+         sigma = sqrt(2.0 * D);
+      }
+      const double r[3] = {g[0] * sigma, g[1] * sigma, g[2] * sigma};
+      // etp: the spin the torque is evaluated with (old spin in stage 1, midpoint spin in stage 2)
+      const double etp[3] = {own.x, own.y, own.z};
+      double a1[3], s1[3], A[3];
+      a1[0] = -bt[0] - b[0] - lam * (etp[1] * b[2] - etp[2] * b[1]);
+      a1[1] = -bt[1] - b[1] - lam * (etp[2] * b[0] - etp[0] * b[2]);
+      a1[2] = -bt[2] - b[2] - lam * (etp[0] * b[1] - etp[1] * b[0]);
+      s1[0] = -r[0] - lam * (etp[1] * r[2] - etp[2] * r[1]);
+      s1[1] = -r[1] - lam * (etp[2] * r[0] - etp[0] * r[2]);
+      s1[2] = -r[2] - lam * (etp[0] * r[1] - etp[1] * r[0]);
+#pragma unroll
+      for (int a = 0; a < 3; a++) A[a] = 0.5 * dtg * a1[a] + 0.5 * sqrtdtg * s1[a];
+      double et[3];
+      cayley(e, A, et);
+      if (STAGE == 1) {
+         SpinVec o;
+         o.x = 0.5 * (e[0] + et[0]); o.y = 0.5 * (e[1] + et[1]); o.z = 0.5 * (e[2] + et[2]); o.m = m;
+         predk[i] = o;
+      } else {
+         SpinVec o;
+         o.x = et[0]; o.y = et[1]; o.z = et[2];
+         o.m = p.mompar ? calcm(p.mompar, m, __ldg(p.mmom0 + (size_t)k * t.Npad + i), et[2]) : m;
+         curk[i] = o;
+      }
+   } else {
+      // ---- Depondt (depondt.f90) ----
+      double sigma = 0.0;
+      if (p.thermal) {
+         const double Dp = (2.0 * lam * p.k_bolt) / (p.delta_t * p.gamma * p.mub);
+         sigma = sqrt(Dp * p.temprescale * temp / m);
+      }
+      const double bl[3] = {b[0] + g[0] * sigma, b[1] + g[1] * sigma, b[2] + g[2] * sigma};
+      // damping cross product uses the spin the field was evaluated with (old spin / predictor spin)
+      const double ep[3] = {own.x, own.y, own.z};
+      double bd[3];
+      bd[0] = bt[0] + bl[0] + lam * ep[1] * bl[2] - lam * ep[2] * bl[1];
+      bd[1] = bt[1] + bl[1] + lam * ep[2] * bl[0] - lam * ep[0] * bl[2];
+      bd[2] = bt[2] + bl[2] + lam * ep[0] * bl[1] - lam * ep[1] * bl[0];
+      double* __restrict__ b2 = b2eff + (size_t)k * 3 * t.Npad + i;
+      const double rot = p.delta_t * p.gamma * lldamp;
+      double out[3];
+      if (STAGE == 1) {
+         rodrigues(bd, e, rot, out);
+         b2[0] = bd[0]; b2[t.Npad] = bd[1]; b2[2 * (size_t)t.Npad] = bd[2];
+         SpinVec o; o.x = out[0]; o.y = out[1]; o.z = out[2]; o.m = m;
+         predk[i] = o;
+      } else {
+         bd[0] = 0.5 * bd[0] + 0.5 * b2[0];
+         bd[1] = 0.5 * bd[1] + 0.5 * b2[t.Npad];
+         bd[2] = 0.5 * bd[2] + 0.5 * b2[2 * (size_t)t.Npad];
+         rodrigues(bd, e, rot, out);
+         SpinVec o; o.x = out[0]; o.y = out[1]; o.z = out[2];
+         o.m = p.mompar ? calcm(p.mompar, m, __ldg(p.mmom0 + (size_t)k * t.Npad + i), out[2]) : m;
+         curk[i] = o;
+      }
+   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Field-only kernel (effective_field_full): writes beff / beff1 / beff2 in ORIGINAL atom order,
+// Fortran shape (3,N,M), and the per-site energy term (hamiltonianactions.f90:245-250) for reduction.
+// ------------------------------------------------------------------------------------------------
+template <bool REDUCED>
+__global__ void __launch_bounds__(256)
+field_kernel(const Tables t, const SpinVec* __restrict__ cur, double* __restrict__ beff, double* __restrict__ beff1,
+             double* __restrict__ beff2, double* __restrict__ esite) {
+   extern __shared__ double sm[];
+   const double *smc, *smd, *smb;
+   stage_couplings(t, sm, smc, smd, smb);
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   const int k = blockIdx.y;
+   if (i >= t.Npad) return;
+   const int o = __ldg(t.orig + i);
+   if (o < 0) return;
+   const int ih = REDUCED ? __ldg(t.ham + i) : 0;
+   const SpinVec* __restrict__ S = cur + (size_t)k * t.Npad;
+   const SpinVec own = S[i];
+   double bs[3], bq[3], h[3];
+   site_field<REDUCED>(t, S, i, ih, own, smc, smd, smb, bs, bq);
+   ext_field(t, i, k, h);
+   const size_t q = 3 * ((size_t)o + (size_t)t.N * k);
+#pragma unroll
+   for (int a = 0; a < 3; a++) {
+      const double b2 = bq[a] + h[a];
+      if (beff1) beff1[q + a] = bs[a];
+      if (beff2) beff2[q + a] = b2;
+      if (beff) beff[q + a] = bs[a] + b2;
+   }
+   if (esite) {
+      const double mx = own.x * own.m, my = own.y * own.m, mz = own.z * own.m;
+      const double tx = 0.5 * (bs[0] + 2.0 * bq[0] + 2.0 * h[0]);
+      const double ty = 0.5 * (bs[1] + 2.0 * bq[1] + 2.0 * h[1]);
+      const double tz = 0.5 * (bs[2] + 2.0 * bq[2] + 2.0 * h[2]);
+      esite[(size_t)k * t.Npad + i] = -mx * tx - my * ty - mz * tz;
+   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Observables: per-ensemble sum of emomM (and of esite) with a fixed-shape two-pass tree reduction
+// (deterministic for a given Npad): pass 1 = one partial per CTA, pass 2 = one CTA per ensemble.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+   return v;
+}
+
+__global__ void __launch_bounds__(256)
+moment_partial_kernel(int Npad, const int* __restrict__ orig, const SpinVec* __restrict__ cur,
+                      const double* __restrict__ esite, double* __restrict__ part /*[M][gridDim.x][4]*/) {
+   __shared__ double red[4][8];
+   const int k = blockIdx.y;
+   double s[4] = {0, 0, 0, 0};
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Npad; i += gridDim.x * blockDim.x) {
+      if (__ldg(orig + i) < 0) continue;
+      const SpinVec v = cur[(size_t)k * Npad + i];
+      s[0] += v.x * v.m; s[1] += v.y * v.m; s[2] += v.z * v.m;
+      if (esite) s[3] += esite[(size_t)k * Npad + i];
+   }
+   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+   for (int a = 0; a < 4; a++) { s[a] = warp_sum(s[a]); if (l == 0) red[a][w] = s[a]; }
+   __syncthreads();
+   if (w == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+         double v = (l < 8) ? red[a][l] : 0.0;
+         v = warp_sum(v);
+         if (l == 0) part[((size_t)k * gridDim.x + blockIdx.x) * 4 + a] = v;
+      }
+   }
+}
+
+__global__ void __launch_bounds__(256)
+moment_final_kernel(int nblk, const double* __restrict__ part, double* __restrict__ out /*[M][4]*/) {
+   __shared__ double red[4][8];
+   const int k = blockIdx.x;
+   double s[4] = {0, 0, 0, 0};
+   for (int b = threadIdx.x; b < nblk; b += blockDim.x)
+#pragma unroll
+      for (int a = 0; a < 4; a++) s[a] += part[((size_t)k * nblk + b) * 4 + a];
+   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+   for (int a = 0; a < 4; a++) { s[a] = warp_sum(s[a]); if (l == 0) red[a][w] = s[a]; }
+   __syncthreads();
+   if (w == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+         double v = (l < 8) ? red[a][l] : 0.0;
+         v = warp_sum(v);
+         if (l == 0) out[k * 4 + a] = v;
+      }
+   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layout conversion between the host's Fortran arrays and the packed device order.
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_kernel(int N, int Npad, int M, const int* __restrict__ orig, const double* __restrict__ emom,
+                            const double* __restrict__ mmom, SpinVec* __restrict__ cur) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+   if (i >= Npad) return;
+   const int o = orig[i];
+   SpinVec v;
+   if (o < 0) { v.x = 0; v.y = 0; v.z = 1.0; v.m = 0.0; }
+   else {
+      const size_t q = (size_t)o + (size_t)N * k;
+      v.x = emom[3 * q]; v.y = emom[3 * q + 1]; v.z = emom[3 * q + 2]; v.m = mmom[q];
+   }
+   cur[(size_t)k * Npad + i] = v;
+}
+
+__global__ void unpack_kernel(int N, int Npad, int M, const int* __restrict__ orig, const SpinVec* __restrict__ cur,
+                              double* __restrict__ emom, double* __restrict__ emomM, double* __restrict__ mmom) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+   if (i >= Npad) return;
+   const int o = orig[i];
+   if (o < 0) return;
+   const SpinVec v = cur[(size_t)k * Npad + i];
+   const size_t q = (size_t)o + (size_t)N * k;
+   if (emom) { emom[3 * q] = v.x; emom[3 * q + 1] = v.y; emom[3 * q + 2] = v.z; }
+   if (emomM) { emomM[3 * q] = v.x * v.m; emomM[3 * q + 1] = v.y * v.m; emomM[3 * q + 2] = v.z * v.m; }
+   if (mmom) mmom[q] = v.m;
+}
+
+// scatter a per-atom host-order array (ncomp,N[,M]) into device order [M][ncomp][Npad]
+__global__ void scatter_kernel(int N, int Npad, int ncomp, int per_ens, const int* __restrict__ orig,
+                               const double* __restrict__ src, double* __restrict__ dst) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+   if (i >= Npad) return;
+   const int o = orig[i];
+   for (int a = 0; a < ncomp; a++) {
+      double v = 0.0;
+      if (o >= 0) v = src[a + (size_t)ncomp * ((size_t)o + (per_ens ? (size_t)N * k : 0))];
+      dst[((size_t)k * ncomp + a) * Npad + i] = v;
+   }
+}
+
+}  // namespace asd

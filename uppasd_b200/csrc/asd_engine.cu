@@ -1,0 +1,779 @@
+// Host side of libuppasd_b200.so: the engine that owns device memory, lays the reference's tables out for
+// the B200 and sequences the fused kernels; plus the C ABI (include/uppasd_b200.h).
+//
+// Mirrors, on the host, the call order of the reference drivers for this path:
+//   sd_mphase loop   source/sd_driver.f90:517-849  (measure -> field -> evolve_first -> field -> evolve_second
+//                                                  -> moment_update)
+//   native boundary  source/gpu_files/cudaMdSimulation.cu:300-512, fortranData.cpp:141-185, fort_helper.cpp
+//   mc_mphase loop   source/mc_driver.f90:310-430  (measure -> mc_evolve)
+// None of the reference's native code is reused: two fused kernels per LLG step instead of ~14 launches, a
+// packed 32-byte spin layout in device order, counter-based in-register noise, colour-parallel MC.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/uppasd_b200.h"
+#include "asd_device.cuh"
+#include "asd_mc.cuh"
+#include "asd_lattice.cuh"
+
+using namespace asd;
+
+// ------------------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+   char buf[1024];
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(buf, sizeof buf, fmt, ap);
+   va_end(ap);
+   g_err = buf;
+   return code;
+}
+#define CU(x)                                                                                          \
+   do {                                                                                                \
+      cudaError_t err__ = (x);                                                                         \
+      if (err__ != cudaSuccess) return fail(-100, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(err__), \
+                                            __FILE__, __LINE__, cudaGetErrorString(err__));            \
+   } while (0)
+
+template <class T>
+struct DevBuf {
+   T* p = nullptr;
+   size_t n = 0;
+   int alloc(size_t count) {
+      release();
+      if (count == 0) return 0;
+      cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+      if (e != cudaSuccess) { p = nullptr; return fail(-101, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e)); }
+      n = count;
+      return 0;
+   }
+   int upload(const std::vector<T>& h, cudaStream_t s) {
+      int r = alloc(h.size());
+      if (r) return r;
+      if (h.empty()) return 0;
+      CU(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+      CU(cudaStreamSynchronize(s));
+      return 0;
+   }
+   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+   ~DevBuf() { release(); }
+};
+
+// host-side description of one pair-interaction table exactly as the reference holds it
+struct HostTable {
+   int z = 0, ncomp = 1;
+   std::vector<int> list;      // (z, N) column-major, 1-based, 0 = empty
+   std::vector<int> lsize;     // (NH)
+   std::vector<double> coup;   // (ncomp, z, NH)
+   bool present() const { return z > 0; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Layout: one device ordering of the atoms + the tables permuted/transposed into it.
+// ------------------------------------------------------------------------------------------------
+struct Layout {
+   int N = 0, Npad = 0, NH = 0, M = 0;
+   bool reduced = false;
+   std::vector<int> orig;     // [Npad] original 0-based atom of slot, -1 padding
+   std::vector<int> slot_of;  // [N] slot of original atom
+   // colour classes (MC layout only): slot ranges
+   std::vector<int> colour_first, colour_count;
+   DevBuf<int> d_ham, d_orig, d_nl, d_lsize, d_dml, d_dmsize, d_bql, d_bqsize, d_taniso;
+   DevBuf<int> d_cnt[3];  // per-atom list lengths of device-built tables (exchange, DM, BQ)
+   int zs[3] = {0, 0, 0};
+   DevBuf<double> d_cp, d_dmv, d_jbq, d_eaniso, d_kaniso, d_sb, d_ext, d_btorque, d_landeg, d_lambda, d_temp, d_mmom0;
+   Tables t{};
+   size_t smem_bytes = 0;
+};
+
+struct asd_engine {
+   int device = 0;
+   cudaStream_t stream = nullptr;
+   // constants
+   double gamma = 1.760859644e11, k_bolt = 1.38064852e-23, mub = 9.274009994e-24, mry = 2.179872325e-21;
+   // system
+   int N = 0, M = 0, NH = 0;
+   std::vector<int> aHam;  // 1-based ham row per atom
+   HostTable ex, dm, bq;
+   bool have_aniso = false;
+   std::vector<int> taniso;
+   std::vector<double> eaniso, kaniso, sb;
+   std::vector<double> ext;      // (3,N,M) or empty
+   std::vector<double> btorque;  // (3,N,M) or empty
+   // llg
+   int SDEalgh = 1, mompar = 0;
+   double delta_t = 1e-16, temprescale = 1.0;
+   std::vector<double> landeg, lambda, temp;  // (N)
+   unsigned long long seed = 20261017ull;
+   bool llg_uniform = true, llg_thermal = false;
+   // moments (host copies, original order) used when (re)building layouts
+   std::vector<double> h_emom, h_mmom, h_mmom0;
+   // layouts
+   Layout sd, mc;
+   bool sd_built = false, mc_built = false;
+   bool lattice_built = false;  // tables live on the device only (asd_build_lattice_table)
+   int state_layout = 0;  // 0 = none, 1 = sd, 2 = mc
+   DevBuf<SpinVec> cur, pred;
+   DevBuf<double> b2eff, esite, part, red;
+   DevBuf<unsigned int> acc;
+   long launches = 0;
+   bool committed = false;
+   // lattice description (when built on device)
+   LatticeDesc lat{};
+};
+
+static void launch_cfg(int Npad, int M, dim3& grid, dim3& block) {
+   block = dim3(256, 1, 1);
+   grid = dim3((Npad + 255) / 256, M, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layout construction from host tables
+// ------------------------------------------------------------------------------------------------
+static int host_orig(asd_engine* e, Layout& L);
+
+// shared tail of layout construction: shared-memory plan, per-atom arrays (anisotropy, fields) in device order
+static int finish_layout(asd_engine* e, Layout& L) {
+   const int N = e->N, NH = e->NH, M = e->M;
+   const long Npad = L.Npad;
+   cudaStream_t st = e->stream;
+   Tables& t = L.t;
+   int r;
+   // ---- shared-memory staging plan for reduced couplings ----
+   L.smem_bytes = 0; t.sm_cp = t.sm_dm = t.sm_bq = 0;
+   if (L.reduced) {
+      size_t n0 = (size_t)NH * t.z, n1 = (size_t)NH * t.zdm * 3, n2 = (size_t)NH * t.zbq;
+      if ((n0 + n1 + n2) * 8 <= 40 * 1024) { t.sm_cp = (int)n0; t.sm_dm = (int)n1; t.sm_bq = (int)n2; L.smem_bytes = (n0 + n1 + n2) * 8; }
+   }
+   // ---- per-atom arrays in device order ----
+   auto permute = [&](const std::vector<double>& src, int ncomp, bool per_ens, DevBuf<double>& dst) -> int {
+      int rr = host_orig(e, L);
+      if (rr) return rr;
+      const int K = per_ens ? M : 1;
+      std::vector<double> h((size_t)K * ncomp * Npad, 0.0);
+      for (int k = 0; k < K; k++)
+         for (long s = 0; s < Npad; s++) {
+            const int o = L.orig[s];
+            if (o < 0) continue;
+            for (int a = 0; a < ncomp; a++) h[((size_t)k * ncomp + a) * Npad + s] = src[a + (size_t)ncomp * ((size_t)o + (per_ens ? (size_t)N * k : 0))];
+         }
+      return dst.upload(h, st);
+   };
+   if (e->have_aniso) {
+      if ((r = host_orig(e, L))) return r;
+      std::vector<int> ta(Npad, 0);
+      for (long s = 0; s < Npad; s++) if (L.orig[s] >= 0) ta[s] = e->taniso[L.orig[s]];
+      if ((r = L.d_taniso.upload(ta, st))) return r;
+      if ((r = permute(e->eaniso, 3, false, L.d_eaniso))) return r;
+      if ((r = permute(e->kaniso, 2, false, L.d_kaniso))) return r;
+      if ((r = permute(e->sb, 1, false, L.d_sb))) return r;
+      t.do_aniso = 1; t.taniso = L.d_taniso.p; t.eaniso = L.d_eaniso.p; t.kaniso = L.d_kaniso.p; t.sb = L.d_sb.p;
+   }
+   // external field: uniform?
+   t.ext_uniform = 1; t.hext[0] = t.hext[1] = t.hext[2] = 0.0;
+   if (!e->ext.empty()) {
+      bool uni = true;
+      for (size_t q = 0; q < (size_t)N * M && uni; q++)
+         for (int a = 0; a < 3; a++) if (e->ext[3 * q + a] != e->ext[a]) { uni = false; break; }
+      if (uni) { for (int a = 0; a < 3; a++) t.hext[a] = e->ext[a]; }
+      else { t.ext_uniform = 0; if ((r = permute(e->ext, 3, true, L.d_ext))) return r; t.ext = L.d_ext.p; }
+   }
+   if (!e->btorque.empty()) { if ((r = permute(e->btorque, 3, true, L.d_btorque))) return r; t.btorque = L.d_btorque.p; }
+   return 0;
+}
+
+// greedy colouring of the symmetrised union of the neighbour tables (host, O(N z))
+static int colour_graph(const asd_engine* e, std::vector<int>& colour) {
+   const int N = e->N;
+   std::vector<std::vector<int>> extra(0);
+   // adjacency = union of lists; lists are symmetric for every physical table, but symmetrise defensively
+   std::vector<int> deg(N, 0);
+   auto for_each_nb = [&](int i, auto&& f) {
+      const HostTable* T[3] = {&e->ex, &e->dm, &e->bq};
+      for (auto* t : T) {
+         if (!t->present()) continue;
+         for (int j = 0; j < t->z; j++) {
+            int nb = t->list[(size_t)j + (size_t)t->z * i];
+            if (nb > 0 && nb - 1 != i) f(nb - 1);
+         }
+      }
+   };
+   // reverse edges that are not present forward
+   std::vector<std::vector<int>> rev(N);
+   {
+      // cheap symmetry check via sorted forward lists
+      std::vector<int> fw;
+      for (int i = 0; i < N; i++) {
+         for_each_nb(i, [&](int nb) {
+            bool back = false;
+            for_each_nb(nb, [&](int x) { if (x == i) back = true; });
+            if (!back) rev[nb].push_back(i);
+         });
+      }
+   }
+   colour.assign(N, -1);
+   std::vector<int> mark;
+   int ncol = 0;
+   for (int i = 0; i < N; i++) {
+      mark.assign(ncol + 1, 0);
+      auto see = [&](int nb) { int c = colour[nb]; if (c >= 0 && c <= ncol) mark[c] = 1; };
+      for_each_nb(i, see);
+      for (int nb : rev[i]) see(nb);
+      int c = 0;
+      while (c < ncol && mark[c]) c++;
+      colour[i] = c;
+      if (c == ncol) ncol++;
+   }
+   return ncol;
+}
+
+static int build_layout(asd_engine* e, Layout& L, bool colour_major) {
+   const int N = e->N, NH = e->NH, M = e->M;
+   L.N = N; L.NH = NH; L.M = M;
+   L.reduced = NH < N;
+   // ---- ordering: groups = (colour, ham row) for MC, (ham row) for SD; stable within a group ----
+   std::vector<int> colour;
+   int ncol = 1;
+   if (colour_major) ncol = colour_graph(e, colour);
+   const int nrow = L.reduced ? NH : 1;
+   std::vector<long> gcount((size_t)ncol * nrow, 0);
+   auto group_of = [&](int i) { return (size_t)(colour_major ? colour[i] : 0) * nrow + (L.reduced ? e->aHam[i] - 1 : 0); };
+   for (int i = 0; i < N; i++) gcount[group_of(i)]++;
+   std::vector<long> gstart(gcount.size() + 1, 0);
+   for (size_t g = 0; g < gcount.size(); g++) gstart[g + 1] = gstart[g] + ((gcount[g] + 31) / 32) * 32;
+   const long Npad = gstart.back();
+   if (Npad > 2000000000L) return fail(-3, "too many atoms for 32-bit device indices");
+   L.Npad = (int)Npad;
+   L.orig.assign(Npad, -1);
+   L.slot_of.assign(N, -1);
+   {
+      std::vector<long> fill(gstart.begin(), gstart.end() - 1);
+      for (int i = 0; i < N; i++) { long s = fill[group_of(i)]++; L.orig[s] = i; L.slot_of[i] = (int)s; }
+   }
+   L.colour_first.clear(); L.colour_count.clear();
+   if (colour_major)
+      for (int c = 0; c < ncol; c++) {
+         L.colour_first.push_back((int)gstart[(size_t)c * nrow]);
+         L.colour_count.push_back((int)(gstart[(size_t)(c + 1) * nrow] - gstart[(size_t)c * nrow]));
+      }
+   std::vector<int> ham(Npad, -1);
+   for (long s = 0; s < Npad; s++) if (L.orig[s] >= 0) ham[s] = L.reduced ? e->aHam[L.orig[s]] - 1 : 0;
+   cudaStream_t st = e->stream;
+   int r;
+   if ((r = L.d_ham.upload(ham, st))) return r;
+   if ((r = L.d_orig.upload(L.orig, st))) return r;
+   Tables& t = L.t;
+   memset(&t, 0, sizeof t);
+   t.N = N; t.Npad = L.Npad; t.M = M; t.NH = NH; t.reduced = L.reduced ? 1 : 0;
+   t.ham = L.d_ham.p; t.orig = L.d_orig.p;
+   // ---- pair tables ----
+   auto do_table = [&](const HostTable& T, DevBuf<int>& d_list, DevBuf<double>& d_coup, DevBuf<int>& d_size, const char* name) -> int {
+      if (!T.present()) return 0;
+      const int z = T.z, nc = T.ncomp;
+      std::vector<int> nl((size_t)z * Npad);
+      for (long s = 0; s < Npad; s++) {
+         const int o = L.orig[s];
+         for (int j = 0; j < z; j++) nl[(size_t)j * Npad + s] = (int)s;  // padding -> self
+         if (o < 0) continue;
+         const int row = L.reduced ? e->aHam[o] - 1 : o;
+         const int n = T.lsize[row];
+         for (int j = 0; j < n; j++) {
+            const int nb = T.list[(size_t)j + (size_t)z * o];
+            if (nb < 1 || nb > N)
+               return fail(-4, "%s table: atom %d has no neighbour in slot %d although nlistsize(aHam)=%d "
+                               "(do_reduced needs complete neighbour sets on every atom)", name, o + 1, j + 1, n);
+            nl[(size_t)j * Npad + s] = L.slot_of[nb - 1];
+         }
+      }
+      int rr;
+      if ((rr = d_list.upload(nl, st))) return rr;
+      if (L.reduced) {
+         // [NH][z][ncomp]: row-major copy of coup(ncomp,z,NH)
+         std::vector<double> c((size_t)NH * z * nc);
+         for (int h = 0; h < NH; h++)
+            for (int j = 0; j < z; j++)
+               for (int a = 0; a < nc; a++) c[((size_t)h * z + j) * nc + a] = T.coup[a + (size_t)nc * (j + (size_t)z * h)];
+         if ((rr = d_coup.upload(c, st))) return rr;
+         if ((rr = d_size.upload(T.lsize, st))) return rr;
+      } else {
+         // [ncomp][z][Npad], zero beyond nlistsize
+         std::vector<double> c((size_t)nc * z * Npad, 0.0);
+         for (long s = 0; s < Npad; s++) {
+            const int o = L.orig[s];
+            if (o < 0) continue;
+            const int n = T.lsize[o];
+            for (int j = 0; j < n; j++)
+               for (int a = 0; a < nc; a++) c[((size_t)a * z + j) * Npad + s] = T.coup[a + (size_t)nc * (j + (size_t)z * o)];
+         }
+         if ((rr = d_coup.upload(c, st))) return rr;
+      }
+      return 0;
+   };
+   if ((r = do_table(e->ex, L.d_nl, L.d_cp, L.d_lsize, "exchange"))) return r;
+   if ((r = do_table(e->dm, L.d_dml, L.d_dmv, L.d_dmsize, "DM"))) return r;
+   if ((r = do_table(e->bq, L.d_bql, L.d_jbq, L.d_bqsize, "BQ"))) return r;
+   t.z = e->ex.z; t.nl = L.d_nl.p; t.cp = L.d_cp.p; t.lsize = L.d_lsize.p;
+   t.zdm = e->dm.z; t.dml = L.d_dml.p; t.dmv = L.d_dmv.p; t.dmsize = L.d_dmsize.p;
+   t.zbq = e->bq.z; t.bql = L.d_bql.p; t.jbq = L.d_jbq.p; t.bqsize = L.d_bqsize.p;
+   L.zs[0] = e->ex.z; L.zs[1] = e->dm.z; L.zs[2] = e->bq.z;
+   return finish_layout(e, L);
+}
+
+// per-site LLG parameter arrays of a layout (uniform -> scalars)
+static int fill_llg(asd_engine* e, Layout& L, LlgParams& p, unsigned long long step) {
+   memset(&p, 0, sizeof p);
+   const bool uni = e->llg_uniform;
+   p.per_site = uni ? 0 : 1;
+   p.landeg = e->landeg.empty() ? 1.0 : e->landeg[0];
+   p.lambda = e->lambda.empty() ? 0.05 : e->lambda[0];
+   p.temp = e->temp.empty() ? 0.0 : e->temp[0];
+   if (!uni && L.d_lambda.p == nullptr) {
+      auto perm = [&](const std::vector<double>& src, DevBuf<double>& dst) -> int {
+         int rr = host_orig(e, L);
+         if (rr) return rr;
+         std::vector<double> h(L.Npad, 0.0);
+         for (int s = 0; s < L.Npad; s++) if (L.orig[s] >= 0) h[s] = src[L.orig[s]];
+         return dst.upload(h, e->stream);
+      };
+      int r;
+      if ((r = perm(e->landeg, L.d_landeg))) return r;
+      if ((r = perm(e->lambda, L.d_lambda))) return r;
+      if ((r = perm(e->temp, L.d_temp))) return r;
+   }
+   p.landeg_a = L.d_landeg.p; p.lambda_a = L.d_lambda.p; p.temp_a = L.d_temp.p;
+   p.delta_t = e->delta_t; p.gamma = e->gamma; p.k_bolt = e->k_bolt; p.mub = e->mub; p.temprescale = e->temprescale;
+   p.mompar = e->mompar; p.mmom0 = L.d_mmom0.p;
+   p.seed = e->seed; p.step = step;
+   p.thermal = e->llg_thermal ? 1 : 0;
+   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// state movement
+// ------------------------------------------------------------------------------------------------
+static int upload_state(asd_engine* e, Layout& L) {
+   const size_t NM = (size_t)e->N * e->M;
+   DevBuf<double> d_e, d_m;
+   int r;
+   if ((r = d_e.upload(e->h_emom, e->stream))) return r;
+   if ((r = d_m.upload(e->h_mmom, e->stream))) return r;
+   if ((r = e->cur.alloc((size_t)L.Npad * e->M))) return r;
+   if ((r = e->pred.alloc((size_t)L.Npad * e->M))) return r;
+   dim3 g, b;
+   launch_cfg(L.Npad, e->M, g, b);
+   pack_kernel<<<g, b, 0, e->stream>>>(e->N, L.Npad, e->M, L.d_orig.p, d_e.p, d_m.p, e->cur.p);
+   pack_kernel<<<g, b, 0, e->stream>>>(e->N, L.Npad, e->M, L.d_orig.p, d_e.p, d_m.p, e->pred.p);
+   e->launches += 2;
+   CU(cudaGetLastError());
+   if (e->mompar != 0) {
+      if ((r = host_orig(e, L))) return r;
+      std::vector<double> h((size_t)e->M * L.Npad, 0.0);
+      const std::vector<double>& src = e->h_mmom0.empty() ? e->h_mmom : e->h_mmom0;
+      for (int k = 0; k < e->M; k++)
+         for (int s = 0; s < L.Npad; s++) if (L.orig[s] >= 0) h[(size_t)k * L.Npad + s] = src[(size_t)L.orig[s] + (size_t)e->N * k];
+      if ((r = L.d_mmom0.upload(h, e->stream))) return r;
+   }
+   CU(cudaStreamSynchronize(e->stream));
+   (void)NM;
+   return 0;
+}
+
+static int download_state(asd_engine* e, Layout& L, double* emom, double* emomM, double* mmom) {
+   const size_t NM = (size_t)e->N * e->M;
+   DevBuf<double> d_e, d_eM, d_m;
+   int r;
+   if (emom && (r = d_e.alloc(3 * NM))) return r;
+   if (emomM && (r = d_eM.alloc(3 * NM))) return r;
+   if (mmom && (r = d_m.alloc(NM))) return r;
+   dim3 g, b;
+   launch_cfg(L.Npad, e->M, g, b);
+   unpack_kernel<<<g, b, 0, e->stream>>>(e->N, L.Npad, e->M, L.d_orig.p, e->cur.p, d_e.p, d_eM.p, d_m.p);
+   e->launches++;
+   CU(cudaGetLastError());
+   if (emom) CU(cudaMemcpyAsync(emom, d_e.p, 3 * NM * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   if (emomM) CU(cudaMemcpyAsync(emomM, d_eM.p, 3 * NM * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   if (mmom) CU(cudaMemcpyAsync(mmom, d_m.p, NM * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   CU(cudaStreamSynchronize(e->stream));
+   return 0;
+}
+
+// make sure the spin buffers are in layout `want` (1 sd, 2 mc); converts through the host copy when switching
+static int ensure_layout(asd_engine* e, int want) {
+   if (!e->committed) return fail(-2, "asd_commit has not been called");
+   if (want == 2 && !e->mc_built) {
+      if (e->lattice_built) return fail(-5, "Monte Carlo on device-built lattice tables needs asd_get_table + asd_set_exchange first");
+      int r = build_layout(e, e->mc, true);
+      if (r) return r;
+      e->mc_built = true;
+   }
+   if (e->state_layout == want) return 0;
+   if (e->state_layout != 0) {
+      Layout& from = (e->state_layout == 1) ? e->sd : e->mc;
+      e->h_emom.resize(3 * (size_t)e->N * e->M);
+      e->h_mmom.resize((size_t)e->N * e->M);
+      int r = download_state(e, from, e->h_emom.data(), nullptr, e->h_mmom.data());
+      if (r) return r;
+   }
+   if (e->h_emom.empty()) return fail(-6, "moments have not been set (asd_set_moments)");
+   Layout& to = (want == 1) ? e->sd : e->mc;
+   int r = upload_state(e, to);
+   if (r) return r;
+   e->state_layout = want;
+   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// compute
+// ------------------------------------------------------------------------------------------------
+template <int SOLVER, int STAGE>
+static void launch_stage(asd_engine* e, Layout& L, const LlgParams& p) {
+   dim3 g, b;
+   launch_cfg(L.Npad, e->M, g, b);
+   if (L.reduced) llg_stage_kernel<SOLVER, STAGE, true><<<g, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p, e->pred.p, e->b2eff.p);
+   else llg_stage_kernel<SOLVER, STAGE, false><<<g, b, 0, e->stream>>>(L.t, p, e->cur.p, e->pred.p, e->b2eff.p);
+   e->launches++;
+}
+
+static int sd_steps(asd_engine* e, long nsteps, long first_step, cudaEvent_t* ev /*optional per-stage events*/) {
+   int r = ensure_layout(e, 1);
+   if (r) return r;
+   Layout& L = e->sd;
+   if (e->SDEalgh != 1 && e->SDEalgh != 5) return fail(-7, "SDEalgh %d is not on this path (1 = midpoint, 5 = Depondt)", e->SDEalgh);
+   if (e->SDEalgh == 5 && e->b2eff.n < (size_t)3 * L.Npad * e->M) { if ((r = e->b2eff.alloc((size_t)3 * L.Npad * e->M))) return r; }
+   LlgParams p;
+   if ((r = fill_llg(e, L, p, 0))) return r;
+   for (long s = 0; s < nsteps; s++) {
+      p.step = (unsigned long long)(first_step + s);
+      if (e->SDEalgh == 1) { launch_stage<1, 1>(e, L, p); launch_stage<1, 2>(e, L, p); }
+      else { launch_stage<5, 1>(e, L, p); launch_stage<5, 2>(e, L, p); }
+   }
+   (void)ev;
+   CU(cudaGetLastError());
+   return 0;
+}
+
+static int measure(asd_engine* e, Layout& L, double* msum, double* energy) {
+   int r;
+   const int nblk = std::min(296, (L.Npad + 255) / 256);
+   if ((r = e->part.alloc((size_t)e->M * nblk * 4))) return r;
+   if ((r = e->red.alloc((size_t)e->M * 4))) return r;
+   dim3 g, b;
+   double* es = nullptr;
+   if (energy) {
+      if ((r = e->esite.alloc((size_t)e->M * L.Npad))) return r;
+      launch_cfg(L.Npad, e->M, g, b);
+      if (L.reduced) field_kernel<true><<<g, b, L.smem_bytes, e->stream>>>(L.t, e->cur.p, nullptr, nullptr, nullptr, e->esite.p);
+      else field_kernel<false><<<g, b, 0, e->stream>>>(L.t, e->cur.p, nullptr, nullptr, nullptr, e->esite.p);
+      e->launches++;
+      es = e->esite.p;
+   }
+   moment_partial_kernel<<<dim3(nblk, e->M), 256, 0, e->stream>>>(L.Npad, L.d_orig.p, e->cur.p, es, e->part.p);
+   moment_final_kernel<<<e->M, 256, 0, e->stream>>>(nblk, e->part.p, e->red.p);
+   e->launches += 2;
+   CU(cudaGetLastError());
+   std::vector<double> h((size_t)e->M * 4);
+   CU(cudaMemcpyAsync(h.data(), e->red.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   CU(cudaStreamSynchronize(e->stream));
+   for (int k = 0; k < e->M; k++) {
+      if (msum) for (int a = 0; a < 3; a++) msum[3 * k + a] = h[4 * k + a];
+      if (energy) energy[k] = h[4 * k + 3] * e->mub / e->mry;
+   }
+   return 0;
+}
+
+static int mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, double temperature, double temprescale,
+                     const double* extfield) {
+   if (mode != 'M' && mode != 'H') return fail(-8, "MC mode '%c' is not on this path ('M' Metropolis, 'H' heat bath)", mode);
+   int r = ensure_layout(e, 2);
+   if (r) return r;
+   Layout& L = e->mc;
+   McParams p;
+   memset(&p, 0, sizeof p);
+   p.mode = mode; p.temperature = temperature; p.temprescale = temprescale; p.k_bolt = e->k_bolt; p.mub = e->mub;
+   for (int a = 0; a < 3; a++) p.extfield[a] = extfield ? extfield[a] : 0.0;
+   p.seed = e->seed ^ 0x5bd1e995u;
+   const int ncol = (int)L.colour_first.size();
+   for (long s = 0; s < nsweeps; s++)
+      for (int c = 0; c < ncol; c++) {
+         p.sweep = (unsigned long long)(first_sweep + s);
+         p.first = L.colour_first[c]; p.count = L.colour_count[c];
+         if (p.count == 0) continue;
+         dim3 g((p.count + 255) / 256, e->M), b(256);
+         if (L.reduced) mc_colour_kernel<true><<<g, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p, nullptr);
+         else mc_colour_kernel<false><<<g, b, 0, e->stream>>>(L.t, p, e->cur.p, nullptr);
+         e->launches++;
+      }
+   CU(cudaGetLastError());
+   return 0;
+}
+
+// ================================================================================================
+// C ABI -- explicit API
+// ================================================================================================
+extern "C" {
+
+const char* asd_last_error(void) { return g_err.c_str(); }
+
+int asd_device_count(void) {
+   int n = 0;
+   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+   return n;
+}
+
+int asd_create(asd_engine** out, int device) {
+   if (!out) return fail(-1, "null output pointer");
+   *out = nullptr;
+   int n = asd_device_count();
+   if (n <= 0) return fail(-9, "no CUDA device available: this library has no CPU fallback");
+   if (device < 0) { CU(cudaGetDevice(&device)); }
+   if (device >= n) return fail(-9, "device %d requested but only %d present", device, n);
+   CU(cudaSetDevice(device));
+   asd_engine* e = new asd_engine();
+   e->device = device;
+   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+   *out = e;
+   return 0;
+}
+
+void asd_destroy(asd_engine* e) {
+   if (!e) return;
+   cudaSetDevice(e->device);
+   if (e->stream) { cudaStreamSynchronize(e->stream); }
+   cudaStream_t s = e->stream;
+   delete e;
+   if (s) cudaStreamDestroy(s);
+}
+
+int asd_set_constants(asd_engine* e, double gamma, double k_bolt, double mub, double mry) {
+   e->gamma = gamma; e->k_bolt = k_bolt; e->mub = mub; e->mry = mry;
+   return 0;
+}
+
+int asd_set_system(asd_engine* e, int Natom, int Mensemble, int nHam, const int* aHam) {
+   if (Natom <= 0 || Mensemble <= 0 || nHam <= 0 || nHam > Natom) return fail(-1, "bad sizes Natom=%d Mensemble=%d nHam=%d", Natom, Mensemble, nHam);
+   e->N = Natom; e->M = Mensemble; e->NH = nHam;
+   e->aHam.resize(Natom);
+   for (int i = 0; i < Natom; i++) {
+      e->aHam[i] = aHam ? aHam[i] : i + 1;
+      if (e->aHam[i] < 1 || e->aHam[i] > nHam) return fail(-1, "aHam(%d)=%d outside 1..nHam", i + 1, e->aHam[i]);
+   }
+   e->landeg.assign(Natom, 1.0); e->lambda.assign(Natom, 0.05); e->temp.assign(Natom, 0.0);
+   e->llg_uniform = true; e->llg_thermal = false;
+   e->committed = false; e->sd_built = e->mc_built = false; e->state_layout = 0;
+   return 0;
+}
+
+static int set_table(asd_engine* e, HostTable& T, int z, int ncomp, const int* list, const int* lsize, const double* coup) {
+   if (e->N == 0) return fail(-2, "asd_set_system must be called first");
+   if (z <= 0 || !list || !lsize || !coup) return fail(-1, "bad table arguments");
+   T.z = z; T.ncomp = ncomp;
+   T.list.assign(list, list + (size_t)z * e->N);
+   T.lsize.assign(lsize, lsize + e->NH);
+   for (int h = 0; h < e->NH; h++) if (T.lsize[h] < 0 || T.lsize[h] > z) return fail(-1, "listsize(%d)=%d outside 0..%d", h + 1, T.lsize[h], z);
+   T.coup.assign(coup, coup + (size_t)ncomp * z * e->NH);
+   e->committed = false;
+   return 0;
+}
+int asd_set_exchange(asd_engine* e, int z, const int* nlist, const int* nlistsize, const double* ncoup) { return set_table(e, e->ex, z, 1, nlist, nlistsize, ncoup); }
+int asd_set_dm(asd_engine* e, int z, const int* dmlist, const int* dmlistsize, const double* dm_vect) { return set_table(e, e->dm, z, 3, dmlist, dmlistsize, dm_vect); }
+int asd_set_bq(asd_engine* e, int z, const int* bqlist, const int* bqlistsize, const double* j_bq) { return set_table(e, e->bq, z, 1, bqlist, bqlistsize, j_bq); }
+
+int asd_set_anisotropy(asd_engine* e, const int* taniso, const double* eaniso, const double* kaniso, const double* sb) {
+   if (e->N == 0) return fail(-2, "asd_set_system must be called first");
+   e->taniso.assign(taniso, taniso + e->N);
+   e->eaniso.assign(eaniso, eaniso + 3 * (size_t)e->N);
+   e->kaniso.assign(kaniso, kaniso + 2 * (size_t)e->N);
+   e->sb.assign(sb, sb + e->N);
+   e->have_aniso = true; e->committed = false;
+   return 0;
+}
+
+int asd_set_external_field(asd_engine* e, const double* f) {
+   if (e->N == 0) return fail(-2, "asd_set_system must be called first");
+   if (f) e->ext.assign(f, f + 3 * (size_t)e->N * e->M); else e->ext.clear();
+   e->committed = false;
+   return 0;
+}
+int asd_set_torque(asd_engine* e, const double* f) {
+   if (e->N == 0) return fail(-2, "asd_set_system must be called first");
+   if (f) e->btorque.assign(f, f + 3 * (size_t)e->N * e->M); else e->btorque.clear();
+   e->committed = false;
+   return 0;
+}
+
+int asd_set_llg(asd_engine* e, int SDEalgh, double delta_t, const double* Landeg, const double* lambda1_array,
+                const double* Temp_array, double temprescale, int mompar, unsigned long long seed) {
+   if (e->N == 0) return fail(-2, "asd_set_system must be called first");
+   if (SDEalgh != 1 && SDEalgh != 5) return fail(-7, "SDEalgh %d is not on this path (1 = midpoint, 5 = Depondt)", SDEalgh);
+   e->SDEalgh = SDEalgh; e->delta_t = delta_t; e->temprescale = temprescale; e->mompar = mompar; e->seed = seed;
+   if (Landeg) e->landeg.assign(Landeg, Landeg + e->N);
+   if (lambda1_array) e->lambda.assign(lambda1_array, lambda1_array + e->N);
+   if (Temp_array) e->temp.assign(Temp_array, Temp_array + e->N);
+   e->sd.d_lambda.release(); e->sd.d_landeg.release(); e->sd.d_temp.release();
+   auto uniform = [&](const std::vector<double>& v) { for (double x : v) if (x != v[0]) return false; return true; };
+   e->llg_uniform = uniform(e->landeg) && uniform(e->lambda) && uniform(e->temp);
+   e->llg_thermal = false;
+   for (double x : e->temp) if (x > 0.0) e->llg_thermal = true;
+   if (mompar != 0 && e->committed && e->state_layout == 1 && e->sd.d_mmom0.p == nullptr) {
+      // moments were uploaded before mompar was switched on: re-stage through the host copy
+      e->state_layout = 0;
+   }
+   return 0;
+}
+
+int asd_set_moments(asd_engine* e, const double* emom, const double* mmom, const double* mmom0) {
+   if (e->N == 0) return fail(-2, "asd_set_system must be called first");
+   const size_t NM = (size_t)e->N * e->M;
+   e->h_emom.assign(emom, emom + 3 * NM);
+   e->h_mmom.assign(mmom, mmom + NM);
+   if (mmom0) e->h_mmom0.assign(mmom0, mmom0 + NM); else e->h_mmom0.clear();
+   e->state_layout = 0;
+   return 0;
+}
+
+int asd_get_moments(asd_engine* e, double* emom, double* emomM, double* mmom) {
+   if (e->state_layout == 0) return fail(-6, "no device state to read back");
+   CU(cudaSetDevice(e->device));
+   return download_state(e, e->state_layout == 1 ? e->sd : e->mc, emom, emomM, mmom);
+}
+
+int asd_commit(asd_engine* e) {
+   if (e->N == 0) return fail(-2, "asd_set_system must be called first");
+   CU(cudaSetDevice(e->device));
+   if (!e->lattice_built) {
+      if (!e->ex.present()) return fail(-2, "no exchange table (asd_set_exchange / asd_build_lattice_table)");
+      int r = build_layout(e, e->sd, false);
+      if (r) return r;
+   } else {
+      if (e->sd.zs[0] == 0) return fail(-2, "no exchange table built");
+      int r = finish_layout(e, e->sd);
+      if (r) return r;
+   }
+   e->sd_built = true; e->mc_built = false;
+   e->committed = true;
+   if (e->state_layout != 0) e->state_layout = 0;
+   return 0;
+}
+
+int asd_effective_field(asd_engine* e, double* beff, double* beff1, double* beff2, double* energy) {
+   CU(cudaSetDevice(e->device));
+   int r = ensure_layout(e, e->state_layout == 2 ? 2 : 1);
+   if (r) return r;
+   Layout& L = (e->state_layout == 2) ? e->mc : e->sd;
+   const size_t NM3 = 3 * (size_t)e->N * e->M;
+   DevBuf<double> d0, d1, d2;
+   if (beff && (r = d0.alloc(NM3))) return r;
+   if (beff1 && (r = d1.alloc(NM3))) return r;
+   if (beff2 && (r = d2.alloc(NM3))) return r;
+   if (energy && (r = e->esite.alloc((size_t)e->M * L.Npad))) return r;
+   dim3 g, b;
+   launch_cfg(L.Npad, e->M, g, b);
+   if (L.reduced) field_kernel<true><<<g, b, L.smem_bytes, e->stream>>>(L.t, e->cur.p, d0.p, d1.p, d2.p, energy ? e->esite.p : nullptr);
+   else field_kernel<false><<<g, b, 0, e->stream>>>(L.t, e->cur.p, d0.p, d1.p, d2.p, energy ? e->esite.p : nullptr);
+   e->launches++;
+   CU(cudaGetLastError());
+   if (beff) CU(cudaMemcpyAsync(beff, d0.p, NM3 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   if (beff1) CU(cudaMemcpyAsync(beff1, d1.p, NM3 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   if (beff2) CU(cudaMemcpyAsync(beff2, d2.p, NM3 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   CU(cudaStreamSynchronize(e->stream));
+   if (energy) {
+      // reuse the reduction path without recomputing the field
+      const int nblk = std::min(296, (L.Npad + 255) / 256);
+      if ((r = e->part.alloc((size_t)e->M * nblk * 4))) return r;
+      if ((r = e->red.alloc((size_t)e->M * 4))) return r;
+      moment_partial_kernel<<<dim3(nblk, e->M), 256, 0, e->stream>>>(L.Npad, L.d_orig.p, e->cur.p, e->esite.p, e->part.p);
+      moment_final_kernel<<<e->M, 256, 0, e->stream>>>(nblk, e->part.p, e->red.p);
+      e->launches += 2;
+      std::vector<double> h((size_t)e->M * 4);
+      CU(cudaMemcpyAsync(h.data(), e->red.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+      CU(cudaStreamSynchronize(e->stream));
+      for (int k = 0; k < e->M; k++) energy[k] = h[4 * k + 3] * e->mub / e->mry;
+   }
+   return 0;
+}
+
+int asd_sd_steps(asd_engine* e, long nsteps, long first_step) {
+   CU(cudaSetDevice(e->device));
+   return sd_steps(e, nsteps, first_step, nullptr);
+}
+
+int asd_mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, double temperature, double temprescale,
+                  const double* extfield) {
+   CU(cudaSetDevice(e->device));
+   return mc_sweeps(e, mode, nsweeps, first_sweep, temperature, temprescale, extfield);
+}
+
+int asd_measure(asd_engine* e, double* msum, double* energy) {
+   CU(cudaSetDevice(e->device));
+   int r = ensure_layout(e, e->state_layout == 2 ? 2 : 1);
+   if (r) return r;
+   return measure(e, e->state_layout == 2 ? e->mc : e->sd, msum, energy);
+}
+
+int asd_time_sd_steps(asd_engine* e, long nsteps, long first_step, float* total_ms, float* stage_ms) {
+   CU(cudaSetDevice(e->device));
+   int r = ensure_layout(e, 1);
+   if (r) return r;
+   cudaEvent_t a, b;
+   CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+   CU(cudaStreamSynchronize(e->stream));
+   CU(cudaEventRecord(a, e->stream));
+   r = sd_steps(e, nsteps, first_step, nullptr);
+   CU(cudaEventRecord(b, e->stream));
+   CU(cudaEventSynchronize(b));
+   if (total_ms) CU(cudaEventElapsedTime(total_ms, a, b));
+   if (stage_ms && r == 0) {
+      // time each stage kernel alone (one extra step, state advanced by it as well)
+      Layout& L = e->sd;
+      LlgParams p;
+      if ((r = fill_llg(e, L, p, (unsigned long long)(first_step + nsteps)))) return r;
+      cudaEvent_t c;
+      CU(cudaEventCreate(&c));
+      CU(cudaEventRecord(a, e->stream));
+      if (e->SDEalgh == 1) launch_stage<1, 1>(e, L, p); else launch_stage<5, 1>(e, L, p);
+      CU(cudaEventRecord(b, e->stream));
+      if (e->SDEalgh == 1) launch_stage<1, 2>(e, L, p); else launch_stage<5, 2>(e, L, p);
+      CU(cudaEventRecord(c, e->stream));
+      CU(cudaEventSynchronize(c));
+      CU(cudaEventElapsedTime(&stage_ms[0], a, b));
+      CU(cudaEventElapsedTime(&stage_ms[1], b, c));
+      cudaEventDestroy(c);
+   }
+   cudaEventDestroy(a); cudaEventDestroy(b);
+   return r;
+}
+
+int asd_time_mc_sweeps(asd_engine* e, char mode, long nsweeps, double temperature, float* total_ms) {
+   CU(cudaSetDevice(e->device));
+   int r = ensure_layout(e, 2);
+   if (r) return r;
+   cudaEvent_t a, b;
+   CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+   CU(cudaStreamSynchronize(e->stream));
+   CU(cudaEventRecord(a, e->stream));
+   r = mc_sweeps(e, mode, nsweeps, 1, temperature, 1.0, nullptr);
+   CU(cudaEventRecord(b, e->stream));
+   CU(cudaEventSynchronize(b));
+   if (total_ms) CU(cudaEventElapsedTime(total_ms, a, b));
+   cudaEventDestroy(a); cudaEventDestroy(b);
+   return r;
+}
+
+long asd_launch_count(asd_engine* e) { return e->launches; }
+int asd_synchronize(asd_engine* e) { CU(cudaSetDevice(e->device)); CU(cudaStreamSynchronize(e->stream)); return 0; }
+
+}  // extern "C"
+
+#include "asd_lattice_host.inl"
+#include "asd_legacy.inl"

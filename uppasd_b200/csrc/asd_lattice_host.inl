@@ -1,0 +1,215 @@
+// C ABI: on-device table construction + table export (included by asd_engine.cu)
+
+static int host_orig(asd_engine* e, Layout& L) {
+   if (!L.orig.empty()) return 0;
+   L.orig.resize(L.Npad);
+   CU(cudaMemcpy(L.orig.data(), L.d_orig.p, (size_t)L.Npad * sizeof(int), cudaMemcpyDeviceToHost));
+   L.slot_of.assign(e->N, -1);
+   for (int s = 0; s < L.Npad; s++) if (L.orig[s] >= 0) L.slot_of[L.orig[s]] = s;
+   return 0;
+}
+
+extern "C" {
+
+int asd_build_lattice_table(asd_engine* e, int kind, int NA, int N1, int N2, int N3, const char* bc3, int maxslot,
+                            const int* nslot, const int* cell_atom, const int* cell_shift, const double* coupling) {
+   if (e->N == 0) return fail(-2, "asd_set_system must be called first");
+   CU(cudaSetDevice(e->device));
+   if ((long)NA * N1 * N2 * N3 != e->N) return fail(-1, "NA*N1*N2*N3 = %ld does not match Natom = %d", (long)NA * N1 * N2 * N3, e->N);
+   if (!(e->NH == NA || e->NH == e->N)) return fail(-1, "nHam must be NA (do_reduced Y) or Natom");
+   if (kind < 0 || kind > 2) return fail(-1, "kind must be 0 (exchange), 1 (DM) or 2 (BQ)");
+   const int ncomp = (kind == 1) ? 3 : 1;
+   Layout& L = e->sd;
+   LatticeDesc& d = e->lat;
+   if (!e->lattice_built) {
+      d.NA = NA; d.N1 = N1; d.N2 = N2; d.N3 = N3;
+      for (int a = 0; a < 3; a++) d.periodic[a] = (bc3[a] == 'P' || bc3[a] == 'p') ? 1 : 0;
+      d.reduced = (e->NH < e->N) ? 1 : 0;
+      d.Ncell = N1 * N2 * N3;
+      d.Ncell_pad = ((d.Ncell + 31) / 32) * 32;
+      d.N = e->N;
+      d.Npad = d.reduced ? NA * d.Ncell_pad : ((e->N + 31) / 32) * 32;
+      if (d.reduced)
+         for (int i = 0; i < e->N; i++) if (e->aHam[i] != i % NA + 1) return fail(-1, "aHam is not the basis-atom number; cannot use the lattice builder");
+      L.N = e->N; L.Npad = d.Npad; L.NH = e->NH; L.M = e->M; L.reduced = d.reduced;
+      L.orig.clear(); L.slot_of.clear();
+      int r;
+      if ((r = L.d_orig.alloc(d.Npad))) return r;
+      if ((r = L.d_ham.alloc(d.Npad))) return r;
+      lattice_index_kernel<<<(d.Npad + 255) / 256, 256, 0, e->stream>>>(d, L.d_orig.p, L.d_ham.p);
+      e->launches++;
+      memset(&L.t, 0, sizeof L.t);
+      L.t.N = e->N; L.t.Npad = d.Npad; L.t.M = e->M; L.t.NH = e->NH; L.t.reduced = d.reduced;
+      L.t.ham = L.d_ham.p; L.t.orig = L.d_orig.p;
+      L.t.ext_uniform = 1;
+      e->lattice_built = true;
+      e->ex = HostTable(); e->dm = HostTable(); e->bq = HostTable();
+   } else if (d.NA != NA || d.N1 != N1 || d.N2 != N2 || d.N3 != N3) return fail(-1, "lattice differs from the first asd_build_lattice_table call");
+   int z = 1;
+   for (int i0 = 0; i0 < NA; i0++) { if (nslot[i0] < 0 || nslot[i0] > maxslot) return fail(-1, "nslot out of range"); z = std::max(z, nslot[i0]); }
+   // can two stencil entries of one basis atom land on the same atom? (small periodic cells) -> need de-duplication
+   int dedup = 0;
+   const int Nd[3] = {N1, N2, N3};
+   for (int i0 = 0; i0 < NA && !dedup; i0++)
+      for (int a = 0; a < nslot[i0] && !dedup; a++)
+         for (int b = a + 1; b < nslot[i0]; b++) {
+            if (cell_atom[i0 * maxslot + a] != cell_atom[i0 * maxslot + b]) continue;
+            bool same = true;
+            for (int c = 0; c < 3; c++) {
+               const int df = cell_shift[3 * (i0 * maxslot + a) + c] - cell_shift[3 * (i0 * maxslot + b) + c];
+               if (d.periodic[c] ? (df % Nd[c] != 0) : (df != 0)) same = false;
+            }
+            if (same) { dedup = 1; break; }
+         }
+   DevBuf<int> d_nslot, d_catom, d_cshift;
+   DevBuf<double> d_coupl;
+   int r;
+   if ((r = d_nslot.upload(std::vector<int>(nslot, nslot + NA), e->stream))) return r;
+   if ((r = d_catom.upload(std::vector<int>(cell_atom, cell_atom + (size_t)NA * maxslot), e->stream))) return r;
+   if ((r = d_cshift.upload(std::vector<int>(cell_shift, cell_shift + (size_t)3 * NA * maxslot), e->stream))) return r;
+   if ((r = d_coupl.upload(std::vector<double>(coupling, coupling + (size_t)ncomp * NA * maxslot), e->stream))) return r;
+   DevBuf<int>& d_list = (kind == 0) ? L.d_nl : (kind == 1) ? L.d_dml : L.d_bql;
+   DevBuf<double>& d_cp = (kind == 0) ? L.d_cp : (kind == 1) ? L.d_dmv : L.d_jbq;
+   DevBuf<int>& d_size = (kind == 0) ? L.d_lsize : (kind == 1) ? L.d_dmsize : L.d_bqsize;
+   DevBuf<int>& d_cnt = (kind == 0) ? L.d_cnt[0] : (kind == 1) ? L.d_cnt[1] : L.d_cnt[2];
+   if ((r = d_list.alloc((size_t)z * d.Npad))) return r;
+   if ((r = d_cnt.alloc(d.Npad))) return r;
+   if (!d.reduced && (r = d_cp.alloc((size_t)ncomp * z * d.Npad))) return r;
+   lattice_table_kernel<<<(d.Npad + 127) / 128, 128, 0, e->stream>>>(d, maxslot, z, ncomp, dedup, d_nslot.p, d_catom.p, d_cshift.p,
+                                                                   d_coupl.p, d_list.p, d_cnt.p, d.reduced ? nullptr : d_cp.p);
+   e->launches++;
+   CU(cudaGetLastError());
+   if (d.reduced) {
+      // coupling rows and list lengths come from the atoms of the first cell (i <= nHam, hamiltonianinit.f90:1059)
+      std::vector<int> lsize(NA, 0);
+      std::vector<double> rows((size_t)NA * z * ncomp, 0.0);
+      for (int i0 = 0; i0 < NA; i0++) {
+         std::vector<long> acc;
+         for (int q = 0; q < nslot[i0]; q++) {
+            const int* sh = cell_shift + 3 * (i0 * maxslot + q);
+            int j[3] = {sh[0], sh[1], sh[2]};
+            bool ok = true;
+            for (int c = 0; c < 3; c++) {
+               if (d.periodic[c]) j[c] = (j[c] + 1000 * Nd[c]) % Nd[c];
+               if (j[c] < 0 || j[c] >= Nd[c]) ok = false;
+            }
+            if (!ok) continue;
+            const long jat = (cell_atom[i0 * maxslot + q] - 1) + (long)NA * (j[0] + (long)N1 * (j[1] + (long)N2 * j[2]));
+            if (dedup && std::find(acc.begin(), acc.end(), jat) != acc.end()) continue;
+            for (int a = 0; a < ncomp; a++) rows[((size_t)i0 * z + acc.size()) * ncomp + a] = coupling[(size_t)(i0 * maxslot + q) * ncomp + a];
+            acc.push_back(jat);
+         }
+         lsize[i0] = (int)acc.size();
+      }
+      if ((r = d_cp.upload(rows, e->stream))) return r;
+      if ((r = d_size.upload(lsize, e->stream))) return r;
+      DevBuf<int> bad;
+      if ((r = bad.upload(std::vector<int>(1, 0), e->stream))) return r;
+      lattice_check_kernel<<<(d.Npad + 255) / 256, 256, 0, e->stream>>>(d.Npad, L.d_ham.p, d_cnt.p, d_size.p, bad.p);
+      e->launches++;
+      int nbad = 0;
+      CU(cudaMemcpyAsync(&nbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+      CU(cudaStreamSynchronize(e->stream));
+      if (nbad) return fail(-4, "do_reduced: %d atoms do not have the complete neighbour set of their basis atom "
+                                "(open boundary in a direction that has neighbours)", nbad);
+   }
+   CU(cudaStreamSynchronize(e->stream));
+   Tables& t = L.t;
+   if (kind == 0) { t.z = z; t.nl = d_list.p; t.cp = d_cp.p; t.lsize = d_size.p; }
+   if (kind == 1) { t.zdm = z; t.dml = d_list.p; t.dmv = d_cp.p; t.dmsize = d_size.p; }
+   if (kind == 2) { t.zbq = z; t.bql = d_list.p; t.jbq = d_cp.p; t.bqsize = d_size.p; }
+   L.zs[kind] = z;
+   e->committed = false;
+   return 0;
+}
+
+int asd_get_table_dims(asd_engine* e, int kind, int* z, int* ncomp) {
+   if (kind < 0 || kind > 2) return fail(-1, "bad kind");
+   const HostTable& T = (kind == 0) ? e->ex : (kind == 1) ? e->dm : e->bq;
+   int zz = e->lattice_built ? e->sd.zs[kind] : T.z;
+   if (z) *z = zz;
+   if (ncomp) *ncomp = (kind == 1) ? 3 : 1;
+   return 0;
+}
+
+int asd_get_table(asd_engine* e, int kind, int* list, int* listsize, double* coup) {
+   if (kind < 0 || kind > 2) return fail(-1, "bad kind");
+   CU(cudaSetDevice(e->device));
+   const int ncomp = (kind == 1) ? 3 : 1;
+   if (!e->lattice_built) {
+      const HostTable& T = (kind == 0) ? e->ex : (kind == 1) ? e->dm : e->bq;
+      if (!T.present()) return fail(-2, "table not set");
+      if (list) std::copy(T.list.begin(), T.list.end(), list);
+      if (listsize) std::copy(T.lsize.begin(), T.lsize.end(), listsize);
+      if (coup) std::copy(T.coup.begin(), T.coup.end(), coup);
+      return 0;
+   }
+   Layout& L = e->sd;
+   const int z = L.zs[kind];
+   if (z == 0) return fail(-2, "table not built");
+   DevBuf<int>& d_list = (kind == 0) ? L.d_nl : (kind == 1) ? L.d_dml : L.d_bql;
+   DevBuf<double>& d_cp = (kind == 0) ? L.d_cp : (kind == 1) ? L.d_dmv : L.d_jbq;
+   DevBuf<int>& d_size = (kind == 0) ? L.d_lsize : (kind == 1) ? L.d_dmsize : L.d_bqsize;
+   DevBuf<int>& d_cnt = L.d_cnt[kind];
+   int r;
+   if (list) {
+      DevBuf<int> out;
+      if ((r = out.alloc((size_t)z * e->N))) return r;
+      CU(cudaMemsetAsync(out.p, 0, (size_t)z * e->N * sizeof(int), e->stream));
+      table_export_kernel<<<(L.Npad + 255) / 256, 256, 0, e->stream>>>(e->N, L.Npad, z, L.d_orig.p, d_list.p, d_cnt.p, L.d_ham.p, d_size.p, out.p);
+      e->launches++;
+      CU(cudaMemcpyAsync(list, out.p, (size_t)z * e->N * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+      CU(cudaStreamSynchronize(e->stream));
+   }
+   if (L.reduced) {
+      if (listsize) CU(cudaMemcpy(listsize, d_size.p, (size_t)e->NH * sizeof(int), cudaMemcpyDeviceToHost));
+      if (coup) {
+         std::vector<double> rows((size_t)e->NH * z * ncomp);
+         CU(cudaMemcpy(rows.data(), d_cp.p, rows.size() * sizeof(double), cudaMemcpyDeviceToHost));
+         for (int h = 0; h < e->NH; h++)
+            for (int j = 0; j < z; j++)
+               for (int a = 0; a < ncomp; a++) coup[a + (size_t)ncomp * (j + (size_t)z * h)] = rows[((size_t)h * z + j) * ncomp + a];
+      }
+   } else {
+      if ((r = host_orig(e, L))) return r;
+      if (listsize) {
+         std::vector<int> cnt(L.Npad);
+         CU(cudaMemcpy(cnt.data(), d_cnt.p, (size_t)L.Npad * sizeof(int), cudaMemcpyDeviceToHost));
+         for (int s = 0; s < L.Npad; s++) if (L.orig[s] >= 0) listsize[L.orig[s]] = cnt[s];
+      }
+      if (coup) {
+         std::vector<double> c((size_t)ncomp * z * L.Npad);
+         CU(cudaMemcpy(c.data(), d_cp.p, c.size() * sizeof(double), cudaMemcpyDeviceToHost));
+         for (int s = 0; s < L.Npad; s++) {
+            const int o = L.orig[s];
+            if (o < 0) continue;
+            for (int j = 0; j < z; j++)
+               for (int a = 0; a < ncomp; a++) coup[a + (size_t)ncomp * (j + (size_t)z * o)] = c[((size_t)a * z + j) * L.Npad + s];
+         }
+      }
+   }
+   return 0;
+}
+
+int asd_init_moments_tilted(asd_engine* e, double amplitude, int NA, const double* mmom_basis) {
+   if (!e->committed) return fail(-2, "asd_commit has not been called");
+   CU(cudaSetDevice(e->device));
+   Layout& L = e->sd;
+   int r;
+   if ((r = e->cur.alloc((size_t)L.Npad * e->M))) return r;
+   if ((r = e->pred.alloc((size_t)L.Npad * e->M))) return r;
+   DevBuf<double> mb;
+   if ((r = mb.upload(std::vector<double>(mmom_basis, mmom_basis + NA), e->stream))) return r;
+   dim3 g, b;
+   launch_cfg(L.Npad, e->M, g, b);
+   tilted_moments_kernel<<<g, b, 0, e->stream>>>(L.Npad, e->M, NA, amplitude, L.d_orig.p, mb.p, e->cur.p, e->pred.p);
+   e->launches++;
+   CU(cudaGetLastError());
+   CU(cudaStreamSynchronize(e->stream));
+   e->state_layout = 1;
+   e->h_emom.clear(); e->h_mmom.clear();
+   if (e->mompar != 0) return fail(-1, "mompar != 0 needs asd_set_moments (mmom0)");
+   return 0;
+}
+
+}  // extern "C"

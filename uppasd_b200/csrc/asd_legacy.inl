@@ -1,0 +1,206 @@
+// Legacy native boundary (drop-in for source/gpu_files/fortranData.cpp + fort_helper.cpp + the time loop of
+// cudaMdSimulation.cu:300-512).  Included by asd_engine.cu.
+//
+// Contract kept from the reference:
+//  * fortrandata_set*_ store raw pointers into the Fortran module arrays; Fortran owns the storage;
+//  * cudamdsim_initiateconstants_ dereferences the scalars and exits on an unsupported solver;
+//  * cudamdsim_initiatematrices_ allocates device memory and uploads tables + state;
+//  * cudamdsim_measurementphase_ runs nstep steps, calling back into the host's measurement routines with
+//    mstep passed as size_t* (c_helper.h:30-36), and -- unlike the reference, which only copied state back as
+//    a side effect of sampled measurements -- always writes the final emom/emomM/mmom/mmom2/mmomi/emom2 back
+//    to the Fortran arrays before returning (uppasd.f90:344-350 writes the restart file from them).
+// Deliberate differences: SDEalgh is honoured (1 = midpoint, 5 = Depondt; the reference CUDA path always ran
+// Depondt -- set ASD_LEGACY_FORCE_DEPONDT=1 to mimic that); do_jtensor=1 is refused loudly.
+
+#include <ctime>
+
+extern "C" {
+// gfortran-mangled host callbacks (c_helper.h:12-37); weak so that a non-Fortran host can register pointers instead
+void __chelper_MOD_fortran_do_measurements(const size_t*, int*) __attribute__((weak));
+void __chelper_MOD_fortran_measure_moment(const double*, const double*, const double*, const size_t*) __attribute__((weak));
+void __chelper_MOD_fortran_flush_measurements(const size_t*) __attribute__((weak));
+void __chelper_MOD_fortran_calc_simulation_status_variables(double*) __attribute__((weak));
+}
+
+namespace legacy {
+struct FortranData {
+   // constants (chelper.f90:171-173)
+   char* stt = nullptr; int* SDEalgh = nullptr;
+   unsigned int *rstep = nullptr, *nstep = nullptr, *Natom = nullptr, *Mensemble = nullptr, *max_no_neigh = nullptr;
+   double *delta_t = nullptr, *gamma = nullptr, *k_bolt = nullptr, *mub = nullptr, *damping = nullptr, *binderc = nullptr, *mavg = nullptr;
+   int* mompar = nullptr; char* initexc = nullptr;
+   unsigned int *do_dm = nullptr, *max_no_dmneigh = nullptr, *do_jtensor = nullptr, *do_aniso = nullptr, *nHam = nullptr;
+   // matrices (chelper.f90:181-184)
+   double* ncoup = nullptr; unsigned int *nlist = nullptr, *nlistsize = nullptr;
+   double *beff = nullptr, *b2eff = nullptr, *emomM = nullptr, *emom = nullptr, *emom2 = nullptr, *external_field = nullptr,
+          *mmom = nullptr, *btorque = nullptr, *temperature = nullptr, *mmom0 = nullptr, *mmom2 = nullptr, *mmomi = nullptr, *dmvect = nullptr;
+   unsigned int *dmlist = nullptr, *dmlistsize = nullptr;
+   double *j_tensor = nullptr, *kaniso = nullptr, *eaniso = nullptr; unsigned int* taniso = nullptr; double* sb = nullptr; unsigned int* aHam = nullptr;
+   // input data (chelper.f90:186)
+   int *gpu_mode = nullptr, *gpu_rng = nullptr, *gpu_rng_seed = nullptr;
+   // extras (new)
+   double *Landeg = nullptr, *lambda1_array = nullptr, *temprescale = nullptr;
+   unsigned int *do_bq = nullptr, *nn_bq_tot = nullptr, *bqlist = nullptr, *bqlistsize = nullptr; double* j_bq = nullptr;
+};
+static FortranData fd;
+static asd_engine* eng = nullptr;
+static bool constants_ok = false, matrices_ok = false;
+static asd_cb_do_measurements cb_do = nullptr;
+static asd_cb_measure_moment cb_measure = nullptr;
+static asd_cb_flush_measurements cb_flush = nullptr;
+static asd_cb_status cb_status = nullptr;
+
+static int do_measurements(size_t mstep) {
+   int do_copy = 0;
+   if (cb_do) cb_do(&mstep, &do_copy);
+   else if (__chelper_MOD_fortran_do_measurements) __chelper_MOD_fortran_do_measurements(&mstep, &do_copy);
+   return do_copy;
+}
+static void measure_moment(size_t mstep) {
+   if (cb_measure) cb_measure(fd.emomM, fd.emom, fd.mmom, &mstep);
+   else if (__chelper_MOD_fortran_measure_moment) __chelper_MOD_fortran_measure_moment(fd.emomM, fd.emom, fd.mmom, &mstep);
+}
+static void flush_measurements(size_t mstep) {
+   if (cb_flush) cb_flush(&mstep);
+   else if (__chelper_MOD_fortran_flush_measurements) __chelper_MOD_fortran_flush_measurements(&mstep);
+}
+static void status(double* mavg) {
+   if (cb_status) cb_status(mavg);
+   else if (__chelper_MOD_fortran_calc_simulation_status_variables) __chelper_MOD_fortran_calc_simulation_status_variables(mavg);
+}
+[[noreturn]] static void die(const char* what) {
+   std::fprintf(stderr, "uppasd_b200: %s: %s\n", what, asd_last_error());
+   std::exit(EXIT_FAILURE);
+}
+static void copy_to_fortran(bool all) {
+   if (asd_get_moments(eng, fd.emom, fd.emomM, fd.mmom)) die("copy to host");
+   if (all) {
+      const size_t NM = (size_t)eng->N * eng->M;
+      for (size_t q = 0; q < NM; q++) {
+         if (fd.mmom2) fd.mmom2[q] = fd.mmom[q];
+         if (fd.mmomi) fd.mmomi[q] = 1.0 / fd.mmom[q];
+      }
+      if (fd.emom2) std::memcpy(fd.emom2, fd.emom, 3 * NM * sizeof(double));
+   }
+}
+}  // namespace legacy
+
+extern "C" {
+
+void fortrandata_setconstants_(char* p1, int* p2, unsigned int* p3, unsigned int* p4, unsigned int* p5, unsigned int* p6,
+                               unsigned int* p7, double* p8, double* p9, double* p10, double* p11, double* p12,
+                               double* p13, double* p14, int* p15, char* p16, unsigned int* p17, unsigned int* p18,
+                               unsigned int* p19, unsigned int* p20, unsigned int* p21) {
+   auto& f = legacy::fd;
+   f.stt = p1; f.SDEalgh = p2; f.rstep = p3; f.nstep = p4; f.Natom = p5; f.Mensemble = p6; f.max_no_neigh = p7;
+   f.delta_t = p8; f.gamma = p9; f.k_bolt = p10; f.mub = p11; f.damping = p12; f.binderc = p13; f.mavg = p14;
+   f.mompar = p15; f.initexc = p16; f.do_dm = p17; f.max_no_dmneigh = p18; f.do_jtensor = p19; f.do_aniso = p20; f.nHam = p21;
+}
+
+void fortrandata_setmatrices_(double* p1, unsigned int* p2, unsigned int* p3, double* p4, double* p5, double* p6, double* p7,
+                              double* p8, double* p9, double* p10, double* p11, double* p12, double* p13, double* p14,
+                              double* p15, double* p16, unsigned int* p17, unsigned int* p18, double* p19, double* p20,
+                              double* p21, unsigned int* p22, double* p23, unsigned int* p24) {
+   auto& f = legacy::fd;
+   f.ncoup = p1; f.nlist = p2; f.nlistsize = p3; f.beff = p4; f.b2eff = p5; f.emomM = p6; f.emom = p7; f.emom2 = p8;
+   f.external_field = p9; f.mmom = p10; f.btorque = p11; f.temperature = p12; f.mmom0 = p13; f.mmom2 = p14; f.mmomi = p15;
+   f.dmvect = p16; f.dmlist = p17; f.dmlistsize = p18; f.j_tensor = p19; f.kaniso = p20; f.eaniso = p21; f.taniso = p22;
+   f.sb = p23; f.aHam = p24;
+}
+
+void fortrandata_setinputdata_(int* p1, int* p2, int* p3) {
+   legacy::fd.gpu_mode = p1; legacy::fd.gpu_rng = p2; legacy::fd.gpu_rng_seed = p3;
+}
+
+void fortrandata_setextras_(double* Landeg, double* lambda1_array, double* temprescale, unsigned int* do_bq,
+                            unsigned int* nn_bq_tot, unsigned int* bqlist, unsigned int* bqlistsize, double* j_bq) {
+   auto& f = legacy::fd;
+   f.Landeg = Landeg; f.lambda1_array = lambda1_array; f.temprescale = temprescale;
+   f.do_bq = do_bq; f.nn_bq_tot = nn_bq_tot; f.bqlist = bqlist; f.bqlistsize = bqlistsize; f.j_bq = j_bq;
+}
+
+void asd_set_callbacks(asd_cb_do_measurements a, asd_cb_measure_moment b, asd_cb_flush_measurements c, asd_cb_status d) {
+   legacy::cb_do = a; legacy::cb_measure = b; legacy::cb_flush = c; legacy::cb_status = d;
+}
+
+void cudamdsim_initiateconstants_(void) {
+   using namespace legacy;
+   if (!fd.SDEalgh || !fd.Natom) { std::fprintf(stderr, "uppasd_b200: fortrandata_setconstants_ has not been called\n"); std::exit(EXIT_FAILURE); }
+   const int alg = *fd.SDEalgh;
+   // the reference accepts 1, 4, 5, 11 and always integrates with Depondt (cudaMdSimulation.cu:35-38,319);
+   // this build honours the two solvers on its path and refuses the rest the same way the reference does
+   if (!(alg == 1 || alg == 5)) { std::fprintf(stderr, "Invalid SDEalgh!\n"); std::exit(EXIT_FAILURE); }
+   if (fd.gpu_rng && (*fd.gpu_rng < 0 || *fd.gpu_rng > 3)) { std::fprintf(stderr, "Unknown gpu_rng %d\n", *fd.gpu_rng); std::exit(EXIT_FAILURE); }
+   if (fd.do_jtensor && *fd.do_jtensor == 1) { std::fprintf(stderr, "uppasd_b200: do_jtensor=1 (tensor exchange) is outside this build's hot path\n"); std::exit(EXIT_FAILURE); }
+   if (eng) { asd_destroy(eng); eng = nullptr; }
+   if (asd_create(&eng, -1)) die("cudamdsim_initiateconstants_");
+   asd_set_constants(eng, *fd.gamma, *fd.k_bolt, *fd.mub, eng->mry);
+   constants_ok = true; matrices_ok = false;
+}
+
+void cudamdsim_initiatematrices_(void) {
+   using namespace legacy;
+   if (!constants_ok) { std::fprintf(stderr, "uppasd_b200: constants not initiated!\n"); std::exit(EXIT_FAILURE); }
+   const int N = (int)*fd.Natom, M = (int)*fd.Mensemble, NH = (int)*fd.nHam;
+   if (asd_set_system(eng, N, M, NH, (const int*)fd.aHam)) die("set_system");
+   if (asd_set_exchange(eng, (int)*fd.max_no_neigh, (const int*)fd.nlist, (const int*)fd.nlistsize, fd.ncoup)) die("set_exchange");
+   if (fd.do_dm && *fd.do_dm == 1)
+      if (asd_set_dm(eng, (int)*fd.max_no_dmneigh, (const int*)fd.dmlist, (const int*)fd.dmlistsize, fd.dmvect)) die("set_dm");
+   if (fd.do_bq && *fd.do_bq == 1)
+      if (asd_set_bq(eng, (int)*fd.nn_bq_tot, (const int*)fd.bqlist, (const int*)fd.bqlistsize, fd.j_bq)) die("set_bq");
+   if (fd.do_aniso && *fd.do_aniso != 0)
+      if (asd_set_anisotropy(eng, (const int*)fd.taniso, fd.eaniso, fd.kaniso, fd.sb)) die("set_anisotropy");
+   if (asd_set_external_field(eng, fd.external_field)) die("set_external_field");
+   if (fd.stt && *fd.stt != 'N' && fd.btorque) if (asd_set_torque(eng, fd.btorque)) die("set_torque");
+   std::vector<double> lam(N, *fd.damping);
+   int alg = *fd.SDEalgh;
+   const char* force = std::getenv("ASD_LEGACY_FORCE_DEPONDT");
+   if (force && force[0] == '1') alg = 5;
+   unsigned long long seed = (fd.gpu_rng_seed && *fd.gpu_rng_seed != 0) ? (unsigned long long)*fd.gpu_rng_seed : (unsigned long long)std::time(nullptr);
+   if (asd_set_llg(eng, alg, *fd.delta_t, fd.Landeg, fd.lambda1_array ? fd.lambda1_array : lam.data(), fd.temperature,
+                   fd.temprescale ? *fd.temprescale : 1.0, *fd.mompar, seed)) die("set_llg");
+   if (asd_set_moments(eng, fd.emom, fd.mmom, fd.mmom0)) die("set_moments");
+   if (asd_commit(eng)) {
+      // like the reference (cudaMdSimulation.cu:171-181): report and leave the state un-initiated
+      std::fprintf(stderr, "uppasd_b200: initiateMatrices failed: %s\n", asd_last_error());
+      matrices_ok = false;
+      return;
+   }
+   matrices_ok = true;
+}
+
+void cudamdsim_measurementphase_(void) {
+   using namespace legacy;
+   std::setbuf(stdout, nullptr);
+   std::printf("uppasd_b200: md simulation starting\n");
+   if (!matrices_ok) { std::fprintf(stderr, "uppasd_b200: not initiated!\n"); return; }
+   const size_t rstep = *fd.rstep, nstep = *fd.nstep;
+   size_t pending_first = 0, pending = 0;  // steps enqueued lazily so that runs of unsampled steps cost no host sync
+   auto flush_steps = [&]() {
+      if (pending) { if (asd_sd_steps(eng, (long)pending, (long)pending_first)) die("sd_steps"); pending = 0; }
+   };
+   for (size_t mstep = rstep + 1; mstep <= rstep + nstep; mstep++) {
+      if (do_measurements(mstep)) { flush_steps(); copy_to_fortran(false); measure_moment(mstep); }
+      // progress line every 5 % (cudaMdSimulation.cu:283-297)
+      if (nstep > 20 ? (mstep % ((rstep + nstep) / 20) == 0) : true) {
+         flush_steps(); copy_to_fortran(false);
+         if (fd.mavg) status(fd.mavg);
+         if (nstep > 20) std::printf("CUDA: %3ld%% done. Mbar: %10.6f. U: %8.5f.\n", (long)(mstep * 100 / (rstep + nstep)), fd.mavg ? *fd.mavg : 0.0, fd.binderc ? *fd.binderc : 0.0);
+         else std::printf("CUDA: Iteration %ld Mbar %13.6f\n", (long)mstep, fd.mavg ? *fd.mavg : 0.0);
+      }
+      if (!pending) pending_first = mstep;
+      pending++;
+   }
+   flush_steps();
+   const size_t last = rstep + nstep + 1;
+   copy_to_fortran(true);
+   if (do_measurements(last)) measure_moment(last);
+   flush_measurements(last);
+   if (asd_synchronize(eng)) die("synchronize");
+}
+
+void cmdsim_initiateconstants_(void) { cudamdsim_initiateconstants_(); }
+void cmdsim_initiatefortran_(void) { cudamdsim_initiatematrices_(); }
+void cmdsim_measurementphase_(void) { cudamdsim_measurementphase_(); }
+
+}  // extern "C"

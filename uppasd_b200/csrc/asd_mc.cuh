@@ -1,0 +1,165 @@
+// Monte Carlo sweeps on the device: Metropolis and heat bath, one kernel launch per colour class.
+//
+// The reference visits spins one at a time in a random order (mc_evolve, source/MonteCarlo/montecarlo.f90:
+// 44-273; OpenMP sweep racy unless one thread).  Here the conflict graph (union of all neighbour tables,
+// symmetrised) is coloured once; all spins of one colour are updated concurrently while every spin they
+// interact with is frozen, so each launch is an exact single-site update for every one of its spins.
+// This is a different but equally valid Markov chain: parity with the reference is on observables.
+//
+// Restated pieces:
+//   trial move   choose_random_flip   source/MonteCarlo/montecarlo_common.f90:25-79 (Hinzke-Nowak mixture)
+//   delta E      calculate_energy     source/MonteCarlo/montecarlo_common.f90:431-865
+//   Metropolis   flip_a               source/MonteCarlo/montecarlo_common.f90:190-200
+//   heat bath    flip_h               source/MonteCarlo/montecarlo_common.f90:371-422
+// Deviation (documented in DESIGN.md): the DM term of delta E uses emomM consistently
+// (-m_i . (m_j x D)); the reference mixes emom/emomM there (:611-616), identical for |m| = 1.
+#pragma once
+#include "asd_device.cuh"
+
+namespace asd {
+
+struct McParams {
+   int mode;  // 'M' or 'H'
+   double temperature, temprescale, k_bolt, mub;
+   double extfield[3];  // mc_evolve's uniform field argument (Metropolis Zeeman term)
+   unsigned long long seed, sweep;
+   int first, count;  // device-slot range [first, first+count) of this colour class
+};
+
+template <bool REDUCED>
+__global__ void __launch_bounds__(256)
+mc_colour_kernel(const Tables t, const McParams p, SpinVec* __restrict__ cur, unsigned int* __restrict__ accepted) {
+   extern __shared__ double sm[];
+   const double *smc, *smd, *smb;
+   stage_couplings(t, sm, smc, smd, smb);
+   const int li = blockIdx.x * blockDim.x + threadIdx.x;
+   const int k = blockIdx.y;
+   if (li >= p.count) return;
+   const int i = p.first + li;
+   const int o = __ldg(t.orig + i);
+   if (o < 0) return;
+   const int ih = REDUCED ? __ldg(t.ham + i) : 0;
+   SpinVec* __restrict__ S = cur + (size_t)k * t.Npad;
+   const SpinVec own = S[i];
+   const double m = own.m;
+   double bs[3], bq[3];
+   // bilinear field from frozen neighbours (exchange + DM [+ uniaxial]); bq = BQ/cubic field at the CURRENT spin
+   site_field<REDUCED>(t, S, i, ih, own, smc, smd, smb, bs, bq);
+   double u[4];
+   uniform4(p.seed, (uint32_t)o, (uint32_t)k, p.sweep, 1u, u);
+   const double pi = 3.141592653589793;
+   SpinVec out = own;
+   if (p.mode == 'H') {
+      // ---- heat bath (flip_h): field = beff1 + beff2 from effective_field_single, external field from the
+      //      external_field array / uniform vector of the tables (reference quirk, montecarlo.f90:231-237)
+      double h[3];
+      ext_field(t, i, k, h);
+      const double tot[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
+      const double beta = 1.0 / p.k_bolt / (p.temprescale * p.temperature);
+      const double zx = beta * tot[0] * p.mub * m, zy = beta * tot[1] * p.mub * m, zz = beta * tot[2] * p.mub * m;
+      const double zarg = sqrt(zx * zx + zy * zy + zz * zz);
+      const double zctheta = zz / zarg;
+      const double zstheta = sqrt(1.0 - zctheta * zctheta) + 1e-14;
+      const double zcphi = zx / (zarg * zstheta), zsphi = zy / (zarg * zstheta);
+      const double em2 = exp(-2.0 * zarg);
+      const double ctheta = 1.0 + (1.0 / zarg) * log((1.0 - em2) * u[0] + em2 + 1e-14);
+      const double stheta = sqrt(fmax(1.0 - ctheta * ctheta, 0.0));
+      double sphi, cphi;
+      sincos(pi * (2.0 * u[1] - 1.0), &sphi, &cphi);
+      const double s0 = stheta * cphi, s1 = stheta * sphi, s2 = ctheta;
+      out.x = zcphi * zctheta * s0 - zsphi * s1 + zcphi * zstheta * s2;
+      out.y = zsphi * zctheta * s0 + zcphi * s1 + zsphi * zstheta * s2;
+      out.z = -zstheta * s0 + zctheta * s2;
+      S[i] = out;
+      return;
+   }
+   // ---- Metropolis: trial move (choose_random_flip) ----
+   double nx, ny, nz;
+   const int ftype = (int)floor(3.0 * u[0]);
+   if (ftype == 0) {
+      double sphi, cphi;
+      sincos(u[1] * 2 * pi, &sphi, &cphi);
+      const double ct = 1.0 - 2.0 * u[2];
+      const double st = sqrt(fmax(1.0 - ct * ct, 0.0));
+      nx = st * cphi; ny = st * sphi; nz = ct;
+   } else if (ftype == 1) {
+      double g0, g1, g2;
+      gauss3(p.seed, (uint32_t)o, (uint32_t)k, p.sweep, 2u, g0, g1, g2);
+      // delta = (2/25) (k_B T / mu_B)^(1/5)  (montecarlo.f90:142; ignores temprescale like the reference)
+      const double delta = (2.0 / 25.0) * pow(p.k_bolt * p.temperature / p.mub, 0.20);
+      const double ax = own.x + g0 * delta, ay = own.y + g1 * delta, az = own.z + g2 * delta;
+      const double l = sqrt(ax * ax + ay * ay + az * az);
+      nx = ax / l; ny = ay / l; nz = az / l;
+   } else {
+      nx = -own.x; ny = -own.y; nz = -own.z;
+   }
+   // ---- delta E (calculate_energy): bilinear terms via the frozen-neighbour field, the rest explicitly ----
+   const double cx = own.x * m, cy = own.y * m, cz = own.z * m;  // current emomM
+   const double tx = nx * m, ty = ny * m, tz = nz * m;           // trial moment
+   // exchange + DM:  e = -m_i . f   (f = sum_j J m_j + sum_j m_j x D)
+   double fx = bs[0], fy = bs[1], fz = bs[2];
+   double e_c = 0.0, e_t = 0.0;
+   if (t.do_aniso) {
+      // remove the uniaxial field that site_field folded into bs, then add the reference's anisotropy ENERGY
+      const int ta = __ldg(t.taniso + i);
+      if (ta == 1 || ta == 2 || ta == 7) {
+         const double k1 = __ldg(t.kaniso + i), k2 = __ldg(t.kaniso + t.Npad + i);
+         if (ta == 1 || ta == 7) {
+            const double ex = __ldg(t.eaniso + i), ey = __ldg(t.eaniso + t.Npad + i), ez = __ldg(t.eaniso + 2 * (size_t)t.Npad + i);
+            const double tt1 = cx * ex + cy * ey + cz * ez;
+            const double tt3 = 2.0 * tt1 * (k1 + 2.0 * k2 * (1.0 - tt1 * tt1));
+            fx += tt3 * ex; fy += tt3 * ey; fz += tt3 * ez;
+            const double ttb = tx * ex + ty * ey + tz * ez;
+            e_c += k1 * (tt1 * tt1) + k2 * (tt1 * tt1) * (tt1 * tt1);
+            e_t += k1 * (ttb * ttb) + k2 * (ttb * ttb) * (ttb * ttb);
+         }
+         if (ta == 2 || ta == 7) {
+            const double c4 = (cx * cx) * (cy * cy) + (cy * cy) * (cz * cz) + (cz * cz) * (cx * cx);
+            const double c6 = (cx * cx) * (cy * cy) * (cz * cz);
+            const double t4 = (tx * tx) * (ty * ty) + (ty * ty) * (tz * tz) + (tz * tz) * (tx * tx);
+            const double t6 = (tx * tx) * (ty * ty) * (tz * tz);
+            if (ta == 2) {
+               // cubic field of taniso 2 was folded into bs as well: remove it
+               const double x2 = cx * cx, y2 = cy * cy, z2 = cz * cz;
+               fx -= 2.0 * k1 * cx * (y2 + z2) + 2.0 * k2 * cx * (y2 * z2);
+               fy -= 2.0 * k1 * cy * (z2 + x2) + 2.0 * k2 * cy * (z2 * x2);
+               fz -= 2.0 * k1 * cz * (x2 + y2) + 2.0 * k2 * cz * (x2 * y2);
+               e_c += -k1 * c4 - k2 * c6;
+               e_t += -k1 * t4 - k2 * t6;
+            } else {
+               const double s = __ldg(t.sb + i);
+               e_c += (k1 * s) * c4 + (k2 * s) * c6;
+               e_t += (k1 * s) * t4 + (k2 * s) * t6;
+            }
+         }
+      }
+   }
+   e_c -= cx * fx + cy * fy + cz * fz;
+   e_t -= tx * fx + ty * fy + tz * fz;
+   // biquadratic: -j_bq (m_i . m_j)^2 for current and trial moment
+   if (t.zbq > 0) {
+      const int* __restrict__ nl = t.bql + i;
+      const int n = REDUCED ? __ldg(t.bqsize + ih) : t.zbq;
+      for (int j = 0; j < n; j++) {
+         const int nb = __ldg(nl + (size_t)j * t.Npad);
+         const double jb = REDUCED ? (smb ? smb : t.jbq)[(size_t)ih * t.zbq + j] : __ldg(t.jbq + (size_t)j * t.Npad + i);
+         const SpinVec v = S[nb];
+         const double mx = v.x * v.m, my = v.y * v.m, mz = v.z * v.m;
+         const double dc = mx * cx + my * cy + mz * cz, dt = mx * tx + my * ty + mz * tz;
+         e_c -= jb * dc * dc;
+         e_t -= jb * dt * dt;
+      }
+   }
+   // Zeeman with mc_evolve's extfield argument
+   e_c -= p.extfield[0] * cx + p.extfield[1] * cy + p.extfield[2] * cz;
+   e_t -= p.extfield[0] * tx + p.extfield[1] * ty + p.extfield[2] * tz;
+   const double de = p.mub * (e_t - e_c);
+   const double beta = 1.0 / p.k_bolt / (p.temprescale * p.temperature + 1.0e-15);
+   if (de <= 0.0 || u[3] < exp(-beta * de)) {
+      out.x = nx; out.y = ny; out.z = nz;
+      S[i] = out;
+      if (accepted) atomicAdd(accepted, 1u);
+   }
+}
+
+}  // namespace asd
