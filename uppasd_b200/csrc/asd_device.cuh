@@ -65,7 +65,22 @@ struct Tables {
    const double* __restrict__ btorque;
    // shared-memory staging of reduced couplings (doubles): cp | dmv | jbq
    int sm_cp, sm_dm, sm_bq;  // element counts (0 => read from global)
+   // vectorised exchange table: nl4[zq][Npad] holds slots 4q..4q+3 of every atom (one 16-byte load per lane
+   // per four neighbours); cp4[zq][Npad] the matching per-atom couplings (non-reduced only)
+   int zq;
+   const int4* __restrict__ nl4;
+   const double4* __restrict__ cp4;
+   int pf_tiles;    // L2 bulk-prefetch distance in 256-atom tiles (0 = off)
+   int cpl_param;   // 1: reduced exchange couplings live in cpl_small (kernel parameter = constant bank)
+   double cpl_small[256];
 };
+
+#ifndef ASD_MINB
+#define ASD_MINB 2
+#endif
+#ifndef ASD_CHUNK
+#define ASD_CHUNK 8
+#endif
 
 struct LlgParams {
    int per_site;        // 1: read Landeg/lambda/Temp arrays (device order), 0: uniform scalars
@@ -144,6 +159,77 @@ __device__ __forceinline__ void uniform4(unsigned long long seed, uint32_t atom,
 // beff_s / beff_q in hamiltonianactions.f90:185-238.  own = this site's packed spin in S.
 // smc/smd/smb: shared-memory copies of the reduced couplings (or null -> global).
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double4 ld_nc_d4(const double4* p) {
+   double4 v;
+   asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+   return v;
+}
+
+// Heisenberg sum with explicit memory-level parallelism (hamiltonianactions.f90:461-464, same j order):
+// neighbour indices arrive as 16-byte vectors, one chunk (ASD_CHUNK slots) ahead of the gathers that use
+// them; the ASD_CHUNK 256-bit gathers of a chunk are all issued before the first FMA consumes one.
+template <bool REDUCED>
+__device__ __forceinline__ void exchange_chunked(const Tables& t, const SpinVec* __restrict__ S, int i, int ih,
+                                                 const double* smc, double& fx, double& fy, double& fz) {
+   constexpr int CH = ASD_CHUNK, CQ = CH / 4;
+   const size_t Npad = t.Npad;
+   const int n = REDUCED ? __ldg(t.lsize + ih) : t.z;
+   const int nq = (n + 3) >> 2;
+   const int4* __restrict__ p = t.nl4 + i;
+   const double4* __restrict__ pc = REDUCED ? nullptr : t.cp4 + i;
+   const double* __restrict__ crow = REDUCED ? (smc ? smc + (size_t)ih * t.z : t.cp + (size_t)ih * t.z) : nullptr;
+   const int cbase = ih * t.z;
+   int4 cur[CQ], nxt[CQ];
+   double4 ccur[REDUCED ? 1 : CQ], cnxt[REDUCED ? 1 : CQ];
+#pragma unroll
+   for (int q = 0; q < CQ; q++) {
+      if (q < nq) { cur[q] = __ldg(p + q * Npad); if (!REDUCED) ccur[q] = ld_nc_d4(pc + q * Npad); }
+   }
+   for (int j0 = 0; j0 < n; j0 += CH) {
+      const int q1 = (j0 + CH) >> 2;
+#pragma unroll
+      for (int q = 0; q < CQ; q++)
+         if (q1 + q < nq) { nxt[q] = __ldg(p + (size_t)(q1 + q) * Npad); if (!REDUCED) cnxt[q] = ld_nc_d4(pc + (size_t)(q1 + q) * Npad); }
+      SpinVec v[CH];
+#pragma unroll
+      for (int u = 0; u < CH; u++) {
+         const int4 w = cur[u >> 2];
+         const int nb = (u & 3) == 0 ? w.x : (u & 3) == 1 ? w.y : (u & 3) == 2 ? w.z : w.w;
+         if (j0 + u < n) v[u] = S[nb];
+      }
+#pragma unroll
+      for (int u = 0; u < CH; u++) {
+         if (j0 + u < n) {
+            double cj;
+            if (REDUCED) cj = t.cpl_param ? t.cpl_small[cbase + j0 + u] : crow[j0 + u];
+            else { const double4 w = ccur[u >> 2]; cj = (u & 3) == 0 ? w.x : (u & 3) == 1 ? w.y : (u & 3) == 2 ? w.z : w.w; }
+            fx = fma(cj, v[u].x * v[u].m, fx);
+            fy = fma(cj, v[u].y * v[u].m, fy);
+            fz = fma(cj, v[u].z * v[u].m, fz);
+         }
+      }
+#pragma unroll
+      for (int q = 0; q < CQ; q++) { cur[q] = nxt[q]; if (!REDUCED) ccur[q] = cnxt[q]; }
+   }
+}
+
+// L2 bulk prefetch (cp.async.bulk.prefetch.L2) of the index rows and spins of the tile that a CTA scheduled
+// ~one wave later will work on: turns the DRAM latency of the index stream into an L2 hit.
+__device__ __forceinline__ void prefetch_tile(const Tables& t, const SpinVec* S) {
+   if (t.pf_tiles == 0 || t.nl4 == nullptr) return;
+   const size_t tile = (size_t)blockIdx.x + t.pf_tiles;
+   const size_t first = tile * blockDim.x;
+   if (first >= (size_t)t.Npad) return;
+   const unsigned cnt = (unsigned)min((size_t)blockDim.x, (size_t)t.Npad - first);
+   if ((int)threadIdx.x < t.zq) {
+      const int4* a = t.nl4 + (size_t)threadIdx.x * t.Npad + first;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(cnt * 16u) : "memory");
+   } else if ((int)threadIdx.x == t.zq) {
+      const SpinVec* a = S + first;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(cnt * 32u) : "memory");
+   }
+}
+
 template <bool REDUCED>
 __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __restrict__ S, int i, int ih,
                                            const SpinVec& own, const double* smc, const double* smd,
@@ -151,7 +237,8 @@ __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __res
    double fx = 0.0, fy = 0.0, fz = 0.0;
    const int Npad = t.Npad;
    // ---- Heisenberg (hamiltonianactions.f90:461-464) ----
-   {
+   if (t.nl4) exchange_chunked<REDUCED>(t, S, i, ih, smc, fx, fy, fz);
+   else {
       const int* __restrict__ nl = t.nl + i;
       if (REDUCED) {
          const int n = __ldg(t.lsize + ih);
@@ -256,7 +343,7 @@ __device__ __forceinline__ void ext_field(const Tables& t, int i, int k, double 
 __device__ __forceinline__ void stage_couplings(const Tables& t, double* sm, const double*& smc, const double*& smd,
                                                 const double*& smb) {
    smc = smd = smb = nullptr;
-   const int n0 = t.sm_cp, n1 = t.sm_dm, n2 = t.sm_bq;
+   const int n0 = t.cpl_param ? 0 : t.sm_cp, n1 = t.sm_dm, n2 = t.sm_bq;
    if (n0 + n1 + n2 == 0) return;
    for (int q = threadIdx.x; q < n0; q += blockDim.x) sm[q] = t.cp[q];
    for (int q = threadIdx.x; q < n1; q += blockDim.x) sm[n0 + q] = t.dmv[q];
@@ -307,11 +394,12 @@ __device__ __forceinline__ double calcm(int mompar, double m, double m0, double 
 //   b2eff (Depondt only): [M][3][Npad] predictor field kept for the Heun average.
 // ------------------------------------------------------------------------------------------------
 template <int SOLVER, int STAGE, bool REDUCED>
-__global__ void __launch_bounds__(256)
-llg_stage_kernel(const Tables t, const LlgParams p, SpinVec* __restrict__ cur, SpinVec* __restrict__ pred,
-                 double* __restrict__ b2eff) {
+__global__ void __launch_bounds__(256, ASD_MINB)
+llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgParams p, SpinVec* __restrict__ cur,
+                 SpinVec* __restrict__ pred, double* __restrict__ b2eff) {
    extern __shared__ double sm[];
    const double *smc, *smd, *smb;
+   prefetch_tile(t, ((STAGE == 1) ? cur : pred) + (size_t)blockIdx.y * t.Npad);
    stage_couplings(t, sm, smc, smd, smb);
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
    const int k = blockIdx.y;
@@ -418,7 +506,7 @@ llg_stage_kernel(const Tables t, const LlgParams p, SpinVec* __restrict__ cur, S
 // ------------------------------------------------------------------------------------------------
 template <bool REDUCED>
 __global__ void __launch_bounds__(256)
-field_kernel(const Tables t, const SpinVec* __restrict__ cur, double* __restrict__ beff, double* __restrict__ beff1,
+field_kernel(const __grid_constant__ Tables t, const SpinVec* __restrict__ cur, double* __restrict__ beff, double* __restrict__ beff1,
              double* __restrict__ beff2, double* __restrict__ esite) {
    extern __shared__ double sm[];
    const double *smc, *smd, *smb;
@@ -537,6 +625,22 @@ __global__ void unpack_kernel(int N, int Npad, int M, const int* __restrict__ or
    if (emom) { emom[3 * q] = v.x; emom[3 * q + 1] = v.y; emom[3 * q + 2] = v.z; }
    if (emomM) { emomM[3 * q] = v.x * v.m; emomM[3 * q + 1] = v.y * v.m; emomM[3 * q + 2] = v.z * v.m; }
    if (mmom) mmom[q] = v.m;
+}
+
+// vectorised copies of a slot-major table: nl[z][Npad] -> nl4[zq][Npad], cp[z][Npad] -> cp4[zq][Npad]
+__global__ void vectorise_table_kernel(int Npad, int z, int zq, const int* __restrict__ nl, const double* __restrict__ cp,
+                                       int4* __restrict__ nl4, double4* __restrict__ cp4) {
+   const int s = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y;
+   if (s >= Npad) return;
+   int v[4];
+   double c[4];
+   for (int a = 0; a < 4; a++) {
+      const int j = 4 * q + a;
+      v[a] = (j < z) ? nl[(size_t)j * Npad + s] : s;
+      c[a] = (cp && j < z) ? cp[(size_t)j * Npad + s] : 0.0;
+   }
+   nl4[(size_t)q * Npad + s] = make_int4(v[0], v[1], v[2], v[3]);
+   if (cp4) cp4[(size_t)q * Npad + s] = make_double4(c[0], c[1], c[2], c[3]);
 }
 
 // scatter a per-atom host-order array (ncomp,N[,M]) into device order [M][ncomp][Npad]

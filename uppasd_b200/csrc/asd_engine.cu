@@ -90,6 +90,8 @@ struct Layout {
    // colour classes (MC layout only): slot ranges
    std::vector<int> colour_first, colour_count;
    DevBuf<int> d_ham, d_orig, d_nl, d_lsize, d_dml, d_dmsize, d_bql, d_bqsize, d_taniso;
+   DevBuf<int4> d_nl4;
+   DevBuf<double4> d_cp4;
    DevBuf<int> d_cnt[3];  // per-atom list lengths of device-built tables (exchange, DM, BQ)
    int zs[3] = {0, 0, 0};
    DevBuf<double> d_cp, d_dmv, d_jbq, d_eaniso, d_kaniso, d_sb, d_ext, d_btorque, d_landeg, d_lambda, d_temp, d_mmom0;
@@ -155,6 +157,32 @@ static int finish_layout(asd_engine* e, Layout& L) {
    if (L.reduced) {
       size_t n0 = (size_t)NH * t.z, n1 = (size_t)NH * t.zdm * 3, n2 = (size_t)NH * t.zbq;
       if ((n0 + n1 + n2) * 8 <= 40 * 1024) { t.sm_cp = (int)n0; t.sm_dm = (int)n1; t.sm_bq = (int)n2; L.smem_bytes = (n0 + n1 + n2) * 8; }
+   }
+   // ---- vectorised exchange table + coupling placement (experiment knobs: ASD_VARIANT, ASD_PF) ----
+   {
+      const char* var = std::getenv("ASD_VARIANT");
+      const int variant = var ? atoi(var) : 3;
+      t.nl4 = nullptr; t.cp4 = nullptr; t.zq = (t.z + 3) / 4; t.pf_tiles = 0; t.cpl_param = 0;
+      if (variant >= 3 && t.z > 0) {
+         if ((r = L.d_nl4.alloc((size_t)t.zq * Npad))) return r;
+         if (!L.reduced && (r = L.d_cp4.alloc((size_t)t.zq * Npad))) return r;
+         vectorise_table_kernel<<<dim3((unsigned)((Npad + 255) / 256), t.zq), 256, 0, st>>>((int)Npad, t.z, t.zq, t.nl, L.reduced ? nullptr : t.cp,
+                                                                                 L.d_nl4.p, L.reduced ? nullptr : L.d_cp4.p);
+         e->launches++;
+         CU(cudaGetLastError());
+         CU(cudaStreamSynchronize(st));
+         t.nl4 = L.d_nl4.p; t.cp4 = L.d_cp4.p;
+         const char* pf = std::getenv("ASD_PF");
+         int sms = 148;
+         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+         t.pf_tiles = pf ? atoi(pf) : sms * 3;
+         if (L.reduced && (size_t)NH * t.z <= 256) {
+            std::vector<double> rows((size_t)NH * t.z);
+            CU(cudaMemcpy(rows.data(), t.cp, rows.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            for (size_t q = 0; q < rows.size(); q++) t.cpl_small[q] = rows[q];
+            t.cpl_param = 1;
+         }
+      }
    }
    // ---- per-atom arrays in device order ----
    auto permute = [&](const std::vector<double>& src, int ncomp, bool per_ens, DevBuf<double>& dst) -> int {
@@ -643,8 +671,8 @@ int asd_set_moments(asd_engine* e, const double* emom, const double* mmom, const
 }
 
 int asd_get_moments(asd_engine* e, double* emom, double* emomM, double* mmom) {
-   if (e->state_layout == 0) return fail(-6, "no device state to read back");
    CU(cudaSetDevice(e->device));
+   if (e->state_layout == 0) { int r = ensure_layout(e, 1); if (r) return r; }
    return download_state(e, e->state_layout == 1 ? e->sd : e->mc, emom, emomM, mmom);
 }
 

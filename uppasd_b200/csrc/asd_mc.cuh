@@ -28,7 +28,7 @@ struct McParams {
 
 template <bool REDUCED>
 __global__ void __launch_bounds__(256)
-mc_colour_kernel(const Tables t, const McParams p, SpinVec* __restrict__ cur, unsigned int* __restrict__ accepted) {
+mc_colour_kernel(const __grid_constant__ Tables t, const __grid_constant__ McParams p, SpinVec* __restrict__ cur, unsigned int* __restrict__ accepted) {
    extern __shared__ double sm[];
    const double *smc, *smd, *smb;
    stage_couplings(t, sm, smc, smd, smb);
