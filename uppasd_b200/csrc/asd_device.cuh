@@ -70,6 +70,15 @@ struct Tables {
    int zq;
    const int4* __restrict__ nl4;
    const double4* __restrict__ cp4;
+   // staged tile gather: per 256-slot tile a sorted list (ulist) of the unique slots its atoms gather from; the
+   // tile's CTA stages emomM of those slots in shared memory once, and nl16 holds the exchange neighbours as
+   // 16-bit positions in that list (8 per 16-byte word) -- half the index bytes of nl, no global gathers
+   int staged;            // 1: the LLG stage kernels use the tile path
+   int ucap;              // row stride of ulist (largest unique count over the tiles, multiple of 32)
+   const int* __restrict__ ulist;     // [ntile][ucap]
+   const int* __restrict__ ucount;    // [ntile]
+   const uint4* __restrict__ nl16;    // [zq8][Npad]
+   int zq8;               // ceil(z / 8)
    int pf_tiles;    // L2 bulk-prefetch distance in 256-atom tiles (0 = off)
    int cpl_param;   // 1: reduced exchange couplings live in cpl_small (kernel parameter = constant bank)
    double cpl_small[256];
@@ -80,6 +89,9 @@ struct Tables {
 #endif
 #ifndef ASD_CHUNK
 #define ASD_CHUNK 8
+#endif
+#ifndef ASD_MINB_STAGED
+#define ASD_MINB_STAGED 4   // CTAs per SM the staged stage kernels are compiled for (register budget 65536/(256*n))
 #endif
 
 struct LlgParams {
@@ -94,6 +106,9 @@ struct LlgParams {
    unsigned long long seed;
    unsigned long long step;  // value of mstep for this step (keys the noise)
    int thermal;              // 0: skip noise entirely
+   // uniform case (per_site == 0): site-independent factors evaluated once on the host with the same IEEE
+   // operations the kernel would use (division and square root are correctly rounded on both sides)
+   double u_lldamp, u_dt, u_sqrtdt, u_Dk, u_Dp;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -137,6 +152,31 @@ __device__ __forceinline__ void gauss3(unsigned long long seed, uint32_t atom, u
    double dummy;
    philox4x32_10(atom, ens | 0x80000000u, s_lo, s_hi, k0, k1, r);
    box_muller(r[0], r[1], r[2], r[3], g2, dummy);
+}
+
+// Langevin noise of the LLG stages: three N(0,1) numbers from ONE Philox call, Box-Muller evaluated in single
+// precision (accurate logf, MUFU sin/cos on [-pi,pi)) and widened to FP64.  The reference's own Gaussian source
+// is the single-precision-resolution Ziggurat r4_nor (source/RNG/randomnumbers.f90:330-438: a 32-bit integer hz
+// times a table entry), so 32-bit-resolution variates are what the Fortran path feeds into the same formulas.
+// Uniforms use all 32 bits (u = r 2^-32 + 2^-33, tail to 6.7 sigma).  ~5x fewer instructions than the FP64 form.
+__device__ __forceinline__ void gauss3f(unsigned long long seed, uint32_t atom, uint32_t ens, unsigned long long step,
+                                        uint32_t stream, double& g0, double& g1, double& g2) {
+   uint32_t r[4];
+   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+   const uint32_t s_lo = (uint32_t)step, s_hi = (uint32_t)(step >> 32) ^ (stream << 24);
+   philox4x32_10(atom, ens, s_lo, s_hi, k0, k1, r);
+   const float two_m32 = 2.3283064365386963e-10f, two_m33 = 1.1641532182693481e-10f;
+   const float u1 = fmaf((float)r[0], two_m32, two_m33), u3 = fmaf((float)r[2], two_m32, two_m33);
+   const float a1 = ((float)r[1] * two_m32 - 0.5f) * 6.283185307179586f;
+   const float a2 = ((float)r[3] * two_m32 - 0.5f) * 6.283185307179586f;
+   const float rad1 = sqrtf(fmaxf(-2.0f * logf(u1), 0.0f)), rad2 = sqrtf(fmaxf(-2.0f * logf(u3), 0.0f));
+   float s1, c1, s2, c2;
+   __sincosf(a1, &s1, &c1);
+   __sincosf(a2, &s2, &c2);
+   (void)s2;
+   g0 = (double)(rad1 * c1);
+   g1 = (double)(rad1 * s1);
+   g2 = (double)(rad2 * c2);
 }
 
 // four U[0,1) numbers (53-bit) for Monte Carlo draws
@@ -213,6 +253,80 @@ __device__ __forceinline__ void exchange_chunked(const Tables& t, const SpinVec*
    }
 }
 
+// streaming 16-byte load of the index table: read-only path, do not allocate in L1 (the words are used once)
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+   uint4 v;
+   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+   return v;
+}
+
+#ifndef ASD_NPF
+#define ASD_NPF 2   // index words (8 neighbours each) kept in flight per thread
+#endif
+
+// first ASD_NPF index words of atom i (issued before the tile is staged so that they overlap the staging)
+__device__ __forceinline__ void idx_prologue(const Tables& t, int i, int nq, uint4 w[ASD_NPF]) {
+   const uint4* __restrict__ p = t.nl16 + i;
+#pragma unroll
+   for (int q = 0; q < ASD_NPF; q++)
+      if (q < nq) w[q] = ld_stream_u4(p + (size_t)q * t.Npad);
+}
+
+// Heisenberg sum from the staged tile (hamiltonianactions.f90:461-464, same j order): neighbours arrive as 16-bit
+// positions into the CTA's shared-memory copy of emomM (sx/sy/sz), three conflict-free LDS.64 per neighbour.
+template <bool REDUCED>
+__device__ __forceinline__ void exchange_staged(const Tables& t, const double* __restrict__ sx, const double* __restrict__ sy,
+                                                const double* __restrict__ sz, int i, int ih, int n, int nq,
+                                                uint4 w[ASD_NPF], const double* smc, double& fx, double& fy, double& fz) {
+   const size_t Npad = t.Npad;
+   const uint4* __restrict__ p = t.nl16 + i;
+   const double4* __restrict__ pc = REDUCED ? nullptr : t.cp4 + i;
+   const double* __restrict__ crow = REDUCED ? (smc ? smc + (size_t)ih * t.z : t.cp + (size_t)ih * t.z) : nullptr;
+   const int cbase = ih * t.z;
+   for (int q0 = 0; q0 < nq; q0 += ASD_NPF) {
+#pragma unroll
+      for (int s = 0; s < ASD_NPF; s++) {
+         const int q = q0 + s;
+         if (q < nq) {
+            const uint4 c = w[s];
+            if (q + ASD_NPF < nq) w[s] = ld_stream_u4(p + (size_t)(q + ASD_NPF) * Npad);
+            double4 ca, cb;
+            if (!REDUCED) { ca = ld_nc_d4(pc + (size_t)(2 * q) * Npad); if (8 * q + 4 < n) cb = ld_nc_d4(pc + (size_t)(2 * q + 1) * Npad); }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+               const int j = 8 * q + u;
+               if (j < n) {
+                  const unsigned word = (u >> 1) == 0 ? c.x : (u >> 1) == 1 ? c.y : (u >> 1) == 2 ? c.z : c.w;
+                  const unsigned li = (u & 1) ? (word >> 16) : (word & 0xffffu);
+                  double cj;
+                  if (REDUCED) cj = t.cpl_param ? t.cpl_small[cbase + j] : crow[j];
+                  else { const double4 cc = (u < 4) ? ca : cb; cj = (u & 3) == 0 ? cc.x : (u & 3) == 1 ? cc.y : (u & 3) == 2 ? cc.z : cc.w; }
+                  fx = fma(cj, sx[li], fx);
+                  fy = fma(cj, sy[li], fy);
+                  fz = fma(cj, sz[li], fz);
+               }
+            }
+         }
+      }
+   }
+}
+
+// L2 bulk prefetch of the index words and gather list of the tile `pf_tiles` ahead (staged path)
+__device__ __forceinline__ void prefetch_tile_staged(const Tables& t) {
+   if (t.pf_tiles == 0) return;
+   const size_t tile = (size_t)blockIdx.x + t.pf_tiles;
+   const size_t first = tile * blockDim.x;
+   if (first >= (size_t)t.Npad) return;
+   const unsigned cnt = (unsigned)min((size_t)blockDim.x, (size_t)t.Npad - first);
+   if ((int)threadIdx.x < t.zq8) {
+      const uint4* a = t.nl16 + (size_t)threadIdx.x * t.Npad + first;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(cnt * 16u) : "memory");
+   } else if ((int)threadIdx.x == t.zq8) {
+      const int* a = t.ulist + tile * t.ucap;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((unsigned)t.ucap * 4u) : "memory");
+   }
+}
+
 // L2 bulk prefetch (cp.async.bulk.prefetch.L2) of the index rows and spins of the tile that a CTA scheduled
 // ~one wave later will work on: turns the DRAM latency of the index stream into an L2 hit.
 __device__ __forceinline__ void prefetch_tile(const Tables& t, const SpinVec* S) {
@@ -230,14 +344,16 @@ __device__ __forceinline__ void prefetch_tile(const Tables& t, const SpinVec* S)
    }
 }
 
-template <bool REDUCED>
+// EXCH = false: the Heisenberg sum was already accumulated into bs[] by the caller (staged tile path).
+template <bool REDUCED, bool EXCH = true>
 __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __restrict__ S, int i, int ih,
                                            const SpinVec& own, const double* smc, const double* smd,
                                            const double* smb, double bs[3], double bq[3]) {
-   double fx = 0.0, fy = 0.0, fz = 0.0;
+   double fx = EXCH ? 0.0 : bs[0], fy = EXCH ? 0.0 : bs[1], fz = EXCH ? 0.0 : bs[2];
    const int Npad = t.Npad;
    // ---- Heisenberg (hamiltonianactions.f90:461-464) ----
-   if (t.nl4) exchange_chunked<REDUCED>(t, S, i, ih, smc, fx, fy, fz);
+   if (!EXCH) {}
+   else if (t.nl4) exchange_chunked<REDUCED>(t, S, i, ih, smc, fx, fy, fz);
    else {
       const int* __restrict__ nl = t.nl + i;
       if (REDUCED) {
@@ -393,26 +509,57 @@ __device__ __forceinline__ double calcm(int mompar, double m, double m0, double 
 //   STAGE 2: gathers from `pred`, reads own `cur`, writes the new spin to `cur` (own slot only).
 //   b2eff (Depondt only): [M][3][Npad] predictor field kept for the Heun average.
 // ------------------------------------------------------------------------------------------------
-template <int SOLVER, int STAGE, bool REDUCED>
-__global__ void __launch_bounds__(256, ASD_MINB)
+template <int SOLVER, int STAGE, bool REDUCED, bool STAGED>
+__global__ void __launch_bounds__(256, STAGED ? ASD_MINB_STAGED : ASD_MINB)
 llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgParams p, SpinVec* __restrict__ cur,
                  SpinVec* __restrict__ pred, double* __restrict__ b2eff) {
    extern __shared__ double sm[];
    const double *smc, *smd, *smb;
-   prefetch_tile(t, ((STAGE == 1) ? cur : pred) + (size_t)blockIdx.y * t.Npad);
-   stage_couplings(t, sm, smc, smd, smb);
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
    const int k = blockIdx.y;
-   if (i >= t.Npad) return;
-   int ih = 0;
-   if (REDUCED) { ih = __ldg(t.ham + i); if (ih < 0) return; }
-   else if (__ldg(t.orig + i) < 0) return;
    SpinVec* __restrict__ curk = cur + (size_t)k * t.Npad;
    SpinVec* __restrict__ predk = pred + (size_t)k * t.Npad;
    const SpinVec* __restrict__ S = (STAGE == 1) ? curk : predk;
-   const SpinVec own = S[i];
-   double bs[3], bq[3], h[3];
-   site_field<REDUCED>(t, S, i, ih, own, smc, smd, smb, bs, bq);
+   // padding slots and the tail of the last tile take part in the staging but compute nothing
+   int ih = 0;
+   bool active = i < t.Npad;
+   if (active) {
+      if (REDUCED) { ih = __ldg(t.ham + i); active = ih >= 0; }
+      else active = __ldg(t.orig + i) >= 0;
+   }
+   double bs[3] = {0.0, 0.0, 0.0}, bq[3], h[3];
+   SpinVec own;
+   if (STAGED) {
+      prefetch_tile_staged(t);
+      // (1) index words in flight first, (2) stage emomM of the tile's gather list, (3) sum from shared memory
+      const int n = active ? (REDUCED ? __ldg(t.lsize + ih) : t.z) : 0;
+      const int nq = (n + 7) >> 3;
+      uint4 w[ASD_NPF];
+      idx_prologue(t, active ? i : 0, nq, w);
+      const int ncpl = (t.cpl_param ? 0 : t.sm_cp) + t.sm_dm + t.sm_bq;
+      double* __restrict__ sx = sm + ncpl;
+      double* __restrict__ sy = sx + t.ucap;
+      double* __restrict__ sz = sy + t.ucap;
+      const int cnt = __ldg(t.ucount + blockIdx.x);
+      const int* __restrict__ ul = t.ulist + (size_t)blockIdx.x * t.ucap;
+#pragma unroll 4
+      for (int u = threadIdx.x; u < cnt; u += 256) {
+         const SpinVec v = S[__ldg(ul + u)];
+         sx[u] = v.x * v.m; sy[u] = v.y * v.m; sz[u] = v.z * v.m;
+      }
+      if (active) own = S[i];
+      stage_couplings(t, sm, smc, smd, smb);   // ends with __syncthreads() when it stages anything
+      if (ncpl == 0) __syncthreads();
+      if (!active) return;
+      exchange_staged<REDUCED>(t, sx, sy, sz, i, ih, n, nq, w, smc, bs[0], bs[1], bs[2]);
+      site_field<REDUCED, false>(t, S, i, ih, own, smc, smd, smb, bs, bq);
+   } else {
+      prefetch_tile(t, S);
+      stage_couplings(t, sm, smc, smd, smb);
+      if (!active) return;
+      own = S[i];
+      site_field<REDUCED>(t, S, i, ih, own, smc, smd, smb, bs, bq);
+   }
    ext_field(t, i, k, h);
    // beff = beff1 + beff2, beff2 = beff_q + external_field (hamiltonianactions.f90:240-243)
    double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
@@ -423,22 +570,22 @@ llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPa
    const double e[3] = {c0.x, c0.y, c0.z};
    const double m = c0.m;
    double g[3] = {0.0, 0.0, 0.0};
-   if (p.thermal) gauss3(p.seed, (uint32_t)__ldg(t.orig + i), (uint32_t)k, p.step, 0u, g[0], g[1], g[2]);
+   if (p.thermal) gauss3f(p.seed, (uint32_t)__ldg(t.orig + i), (uint32_t)k, p.step, 0u, g[0], g[1], g[2]);
    double bt[3] = {0.0, 0.0, 0.0};
    if (t.btorque) {
       const double* __restrict__ q = t.btorque + (size_t)k * 3 * t.Npad + i;
       bt[0] = __ldg(q); bt[1] = __ldg(q + t.Npad); bt[2] = __ldg(q + 2 * (size_t)t.Npad);
    }
-   const double lldamp = 1.0 / (1.0 + lam * lam);
+   const double lldamp = p.per_site ? 1.0 / (1.0 + lam * lam) : p.u_lldamp;
    if (SOLVER == 1) {
       // ---- Mentink's semi-implicit midpoint (midpoint.f90) ----
-      const double dt = p.delta_t * 1.0 * p.gamma * lldamp;  // bn = 1
-      const double sqrtdt = sqrt(dt);
+      const double dt = p.per_site ? p.delta_t * 1.0 * p.gamma * lldamp : p.u_dt;  // bn = 1
+      const double sqrtdt = p.per_site ? sqrt(dt) : p.u_sqrtdt;
       const double dtg = dt * lg, sqrtdtg = sqrtdt * lg;
       // rannum (randomnumbers.f90:667-670,735-746): sigma = sqrt(2 D), D = lam/(1+lam^2) k_B/(gamma mu_B) gamma / m * T
       double sigma = 0.0;
       if (p.thermal) {
-         const double Dk = (lam / (1 + lam * lam) * p.k_bolt / p.gamma / (p.mub)) * (p.gamma / 1.0);
+         const double Dk = p.per_site ? (lam / (1 + lam * lam) * p.k_bolt / p.gamma / (p.mub)) * (p.gamma / 1.0) : p.u_Dk;
          const double D = Dk * (1.0 / m) * temp * p.temprescale;
          sigma = sqrt(2.0 * D);
       }
@@ -470,7 +617,7 @@ llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPa
       // ---- Depondt (depondt.f90) ----
       double sigma = 0.0;
       if (p.thermal) {
-         const double Dp = (2.0 * lam * p.k_bolt) / (p.delta_t * p.gamma * p.mub);
+         const double Dp = p.per_site ? (2.0 * lam * p.k_bolt) / (p.delta_t * p.gamma * p.mub) : p.u_Dp;
          sigma = sqrt(Dp * p.temprescale * temp / m);
       }
       const double bl[3] = {b[0] + g[0] * sigma, b[1] + g[1] * sigma, b[2] + g[2] * sigma};

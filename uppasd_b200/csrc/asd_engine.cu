@@ -22,6 +22,7 @@
 #include "../../include/uppasd_b200.h"
 #include "asd_device.cuh"
 #include "asd_mc.cuh"
+#include "asd_tiles.cuh"
 #include "asd_lattice.cuh"
 
 using namespace asd;
@@ -91,6 +92,9 @@ struct Layout {
    std::vector<int> colour_first, colour_count;
    DevBuf<int> d_ham, d_orig, d_nl, d_lsize, d_dml, d_dmsize, d_bql, d_bqsize, d_taniso;
    DevBuf<int4> d_nl4;
+   DevBuf<int> d_ucount, d_ulist;   // staged tile path (asd_tiles.cuh)
+   DevBuf<uint4> d_nl16;
+   bool is_mc = false;
    DevBuf<double4> d_cp4;
    DevBuf<int> d_cnt[3];  // per-atom list lengths of device-built tables (exchange, DM, BQ)
    int zs[3] = {0, 0, 0};
@@ -145,6 +149,39 @@ static void launch_cfg(int Npad, int M, dim3& grid, dim3& block) {
 // ------------------------------------------------------------------------------------------------
 static int host_orig(asd_engine* e, Layout& L);
 
+// staged tile path: gather lists + 16-bit neighbour table (asd_tiles.cuh).  Leaves t.staged = 0 when a tile would
+// need more than TILE_UMAX unique slots (layout without locality) or when switched off (ASD_STAGED=0).
+static int build_tiles(asd_engine* e, Layout& L) {
+   Tables& t = L.t;
+   t.staged = 0; t.ucap = 0; t.ulist = nullptr; t.ucount = nullptr; t.nl16 = nullptr; t.zq8 = (t.z + 7) / 8;
+   const char* env = std::getenv("ASD_STAGED");
+   if ((env && atoi(env) == 0) || L.is_mc || t.z <= 0) return 0;
+   const long Npad = L.Npad;
+   const int ntile = (int)((Npad + TILE - 1) / TILE);
+   cudaStream_t st = e->stream;
+   int r;
+   if ((r = L.d_ucount.alloc(ntile))) return r;
+   const size_t smem = (size_t)(TILE_HASH + 8192) * sizeof(int);
+   CU(cudaFuncSetAttribute(tile_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+   tile_gather_kernel<<<ntile, TILE, smem, st>>>((int)Npad, t.z, t.nl, 0, 0, L.d_ucount.p, nullptr, nullptr, t.zq8);
+   e->launches++;
+   CU(cudaGetLastError());
+   std::vector<int> cnt(ntile);
+   CU(cudaMemcpyAsync(cnt.data(), L.d_ucount.p, (size_t)ntile * sizeof(int), cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   const int mx = *std::max_element(cnt.begin(), cnt.end());
+   if (mx > TILE_UMAX) return 0;
+   const int ucap = ((mx + 31) / 32) * 32;
+   if ((r = L.d_ulist.alloc((size_t)ntile * ucap))) return r;
+   if ((r = L.d_nl16.alloc((size_t)t.zq8 * Npad))) return r;
+   tile_gather_kernel<<<ntile, TILE, smem, st>>>((int)Npad, t.z, t.nl, 1, ucap, L.d_ucount.p, L.d_ulist.p, L.d_nl16.p, t.zq8);
+   e->launches++;
+   CU(cudaGetLastError());
+   CU(cudaStreamSynchronize(st));
+   t.staged = 1; t.ucap = ucap; t.ulist = L.d_ulist.p; t.ucount = L.d_ucount.p; t.nl16 = L.d_nl16.p;
+   return 0;
+}
+
 // shared tail of layout construction: shared-memory plan, per-atom arrays (anisotropy, fields) in device order
 static int finish_layout(asd_engine* e, Layout& L) {
    const int N = e->N, NH = e->NH, M = e->M;
@@ -163,7 +200,9 @@ static int finish_layout(asd_engine* e, Layout& L) {
       const char* var = std::getenv("ASD_VARIANT");
       const int variant = var ? atoi(var) : 3;
       t.nl4 = nullptr; t.cp4 = nullptr; t.zq = (t.z + 3) / 4; t.pf_tiles = 0; t.cpl_param = 0;
+      if ((r = build_tiles(e, L))) return r;
       if (variant >= 3 && t.z > 0) {
+         // staged layouts need the int4 index copy only for the non-LLG kernels; keep it unless memory is tight
          if ((r = L.d_nl4.alloc((size_t)t.zq * Npad))) return r;
          if (!L.reduced && (r = L.d_cp4.alloc((size_t)t.zq * Npad))) return r;
          vectorise_table_kernel<<<dim3((unsigned)((Npad + 255) / 256), t.zq), 256, 0, st>>>((int)Npad, t.z, t.zq, t.nl, L.reduced ? nullptr : t.cp,
@@ -270,6 +309,7 @@ static int build_layout(asd_engine* e, Layout& L, bool colour_major) {
    const int N = e->N, NH = e->NH, M = e->M;
    L.N = N; L.NH = NH; L.M = M;
    L.reduced = NH < N;
+   L.is_mc = colour_major;
    // ---- ordering: groups = (colour, ham row) for MC, (ham row) for SD; stable within a group ----
    std::vector<int> colour;
    int ncol = 1;
@@ -384,6 +424,28 @@ static int fill_llg(asd_engine* e, Layout& L, LlgParams& p, unsigned long long s
    p.mompar = e->mompar; p.mmom0 = L.d_mmom0.p;
    p.seed = e->seed; p.step = step;
    p.thermal = e->llg_thermal ? 1 : 0;
+   {
+      // same expressions, same order as the per-site branch of llg_stage_kernel (volatile: no host-side contraction)
+      volatile double lam = p.lambda, one = 1.0;
+      volatile double lam2 = lam * lam;
+      volatile double den = one + lam2;
+      p.u_lldamp = one / den;
+      volatile double dt0 = p.delta_t * one;
+      volatile double dt1 = dt0 * p.gamma;
+      p.u_dt = dt1 * p.u_lldamp;
+      p.u_sqrtdt = std::sqrt(p.u_dt);
+      volatile double d0 = lam / den;
+      volatile double d1 = d0 * p.k_bolt;
+      volatile double d2 = d1 / p.gamma;
+      volatile double d3 = d2 / p.mub;
+      volatile double gg = p.gamma / one;
+      p.u_Dk = d3 * gg;
+      volatile double n0 = 2.0 * lam;
+      volatile double n1 = n0 * p.k_bolt;
+      volatile double q0 = p.delta_t * p.gamma;
+      volatile double q1 = q0 * p.mub;
+      p.u_Dp = n1 / q1;
+   }
    return 0;
 }
 
@@ -464,12 +526,31 @@ static int ensure_layout(asd_engine* e, int want) {
 // ------------------------------------------------------------------------------------------------
 // compute
 // ------------------------------------------------------------------------------------------------
+template <class K>
+static void allow_smem(K kernel, size_t bytes) {
+   // opt in to > 48 KB of dynamic shared memory (once per kernel instantiation and size)
+   static size_t granted = 0;
+   if (bytes > 48 * 1024 && bytes > granted) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      granted = bytes;
+   }
+}
+
 template <int SOLVER, int STAGE>
 static void launch_stage(asd_engine* e, Layout& L, const LlgParams& p) {
    dim3 g, b;
    launch_cfg(L.Npad, e->M, g, b);
-   if (L.reduced) llg_stage_kernel<SOLVER, STAGE, true><<<g, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p, e->pred.p, e->b2eff.p);
-   else llg_stage_kernel<SOLVER, STAGE, false><<<g, b, 0, e->stream>>>(L.t, p, e->cur.p, e->pred.p, e->b2eff.p);
+   if (L.t.staged) {
+      const size_t smem = L.smem_bytes + (size_t)3 * L.t.ucap * sizeof(double);
+      if (L.reduced) {
+         allow_smem(llg_stage_kernel<SOLVER, STAGE, true, true>, smem);
+         llg_stage_kernel<SOLVER, STAGE, true, true><<<g, b, smem, e->stream>>>(L.t, p, e->cur.p, e->pred.p, e->b2eff.p);
+      } else {
+         allow_smem(llg_stage_kernel<SOLVER, STAGE, false, true>, smem);
+         llg_stage_kernel<SOLVER, STAGE, false, true><<<g, b, smem, e->stream>>>(L.t, p, e->cur.p, e->pred.p, e->b2eff.p);
+      }
+   } else if (L.reduced) llg_stage_kernel<SOLVER, STAGE, true, false><<<g, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p, e->pred.p, e->b2eff.p);
+   else llg_stage_kernel<SOLVER, STAGE, false, false><<<g, b, 0, e->stream>>>(L.t, p, e->cur.p, e->pred.p, e->b2eff.p);
    e->launches++;
 }
 

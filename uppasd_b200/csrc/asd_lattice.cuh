@@ -15,25 +15,46 @@ namespace asd {
 struct LatticeDesc {
    int NA, N1, N2, N3;
    int periodic[3];
-   int reduced;      // 1: device order = basis-atom major (one group per ham row), 0: original order
+   int reduced;      // 1: couplings per basis atom (ham row = basis atom), 0: per atom
    int Ncell;        // N1*N2*N3
-   int Ncell_pad;    // Ncell rounded up to 32
    int N, Npad;
+   // Device order = BRICK order: the supercell is cut into bricks of BX x BY x BZ cells (P = BX*BY*BZ, a multiple
+   // of 32); a brick holds NA runs of P slots, one per basis atom (so a warp always works on one sublattice),
+   // cells x-fastest inside the brick.  One 256-thread CTA then covers a compact 3-D block of atoms whose
+   // neighbour sets overlap heavily: the set of distinct spins a tile gathers from stays small enough to be
+   // staged in shared memory (asd_tiles.cuh) instead of being gathered from L2 fifty times.
+   int BX, BY, BZ, P;
+   int NTX, NTY, NTZ;   // bricks per direction (the last one may be partly empty -> padding slots)
 };
 
-__device__ __host__ __forceinline__ int lattice_slot(const LatticeDesc& d, int i0, int cell) {
-   return d.reduced ? i0 * d.Ncell_pad + cell : cell * d.NA + i0;
+// slot of basis atom i0 in cell (ix,iy,iz)
+__device__ __host__ __forceinline__ int lattice_slot(const LatticeDesc& d, int i0, int ix, int iy, int iz) {
+   const int tx = ix / d.BX, ty = iy / d.BY, tz = iz / d.BZ;
+   const int lx = ix - tx * d.BX, ly = iy - ty * d.BY, lz = iz - tz * d.BZ;
+   const int brick = tx + d.NTX * (ty + d.NTY * tz);
+   return (brick * d.NA + i0) * d.P + lx + d.BX * (ly + d.BY * lz);
 }
 
-// orig[] / ham[] of every device slot
+// inverse: slot -> (i0, ix, iy, iz); returns false for a padding slot (cell outside the supercell)
+__device__ __host__ __forceinline__ bool lattice_unslot(const LatticeDesc& d, int s, int& i0, int& ix, int& iy, int& iz) {
+   const int run = s / d.P, c = s - run * d.P;
+   const int brick = run / d.NA;
+   i0 = run - brick * d.NA;
+   const int tx = brick % d.NTX, ty = (brick / d.NTX) % d.NTY, tz = brick / (d.NTX * d.NTY);
+   const int lx = c % d.BX, ly = (c / d.BX) % d.BY, lz = c / (d.BX * d.BY);
+   ix = tx * d.BX + lx; iy = ty * d.BY + ly; iz = tz * d.BZ + lz;
+   return ix < d.N1 && iy < d.N2 && iz < d.N3;
+}
+
+// orig[] / ham[] of every device slot (original atom index = i0 + NA*(ix + N1*(iy + N2*iz)), geometry.f90:337-488)
 __global__ void lattice_index_kernel(const LatticeDesc d, int* __restrict__ orig, int* __restrict__ ham) {
    const int s = blockIdx.x * blockDim.x + threadIdx.x;
    if (s >= d.Npad) return;
-   int o = -1, h = -1;
-   if (d.reduced) {
-      const int i0 = s / d.Ncell_pad, cell = s - i0 * d.Ncell_pad;
-      if (cell < d.Ncell) { o = cell * d.NA + i0; h = i0; }
-   } else if (s < d.N) { o = s; h = 0; }
+   int i0, ix, iy, iz, o = -1, h = -1;
+   if (lattice_unslot(d, s, i0, ix, iy, iz)) {
+      o = i0 + d.NA * (ix + d.N1 * (iy + d.N2 * iz));
+      h = d.reduced ? i0 : 0;
+   }
    orig[s] = o;
    ham[s] = h;
 }
@@ -47,13 +68,10 @@ lattice_table_kernel(const LatticeDesc d, int maxslot, int z, int ncomp, int ded
                      int* __restrict__ nl, int* __restrict__ count, double* __restrict__ cp) {
    const int s = blockIdx.x * blockDim.x + threadIdx.x;
    if (s >= d.Npad) return;
-   int i0, cell;
-   bool real;
-   if (d.reduced) { i0 = s / d.Ncell_pad; cell = s - i0 * d.Ncell_pad; real = cell < d.Ncell; }
-   else { real = s < d.N; cell = s / d.NA; i0 = s - cell * d.NA; }
+   int i0, ix, iy, iz;
+   const bool real = lattice_unslot(d, s, i0, ix, iy, iz);
    int n = 0;
    if (real) {
-      const int ix = cell % d.N1, iy = (cell / d.N1) % d.N2, iz = cell / (d.N1 * d.N2);
       const int ns = nslot[i0];
       for (int q = 0; q < ns; q++) {
          const int j0 = cell_atom[i0 * maxslot + q] - 1;
@@ -63,7 +81,7 @@ lattice_table_kernel(const LatticeDesc d, int maxslot, int z, int ncomp, int ded
          if (d.periodic[1]) jy = (jy + 1000 * d.N2) % d.N2;
          if (d.periodic[2]) jz = (jz + 1000 * d.N3) % d.N3;
          if (jx < 0 || jx >= d.N1 || jy < 0 || jy >= d.N2 || jz < 0 || jz >= d.N3) continue;
-         const int jslot = lattice_slot(d, j0, jx + d.N1 * (jy + d.N2 * jz));
+         const int jslot = lattice_slot(d, j0, jx, jy, jz);
          if (dedup) {
             bool exis = false;
             for (int l = 0; l < n; l++) if (nl[(size_t)l * d.Npad + s] == jslot) exis = true;

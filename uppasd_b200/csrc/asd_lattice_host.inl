@@ -9,6 +9,35 @@ static int host_orig(asd_engine* e, Layout& L) {
    return 0;
 }
 
+// Brick shape of the device order (LatticeDesc): P = BX*BY*BZ cells, a multiple of 32, with NA*P close to one
+// 256-thread tile; minimises (padding of partly empty bricks) x (halo of a brick for a 2-cell interaction range).
+static void choose_brick(LatticeDesc& d) {
+   const int Nd[3] = {d.N1, d.N2, d.N3};
+   int target = 256 / d.NA;
+   int p2 = 32;
+   while (p2 * 2 <= target) p2 *= 2;
+   target = p2;
+   double best = 1e300;
+   int bb[3] = {32, 1, 1};
+   for (int bx = 1; bx <= 256; bx *= 2)
+      for (int by = 1; by <= 256; by *= 2)
+         for (int bz = 1; bz <= 256; bz *= 2) {
+            const int P = bx * by * bz;
+            if (P % 32 != 0 || P > target) continue;
+            const int b[3] = {bx, by, bz};
+            double pad = 1.0, halo = 1.0;
+            for (int a = 0; a < 3; a++) {
+               pad *= (double)((Nd[a] + b[a] - 1) / b[a]) * b[a] / Nd[a];
+               halo *= (double)(b[a] + (Nd[a] > 1 ? 4 : 0)) / b[a];
+            }
+            // small preference for full-size bricks and for long x runs (coalesced rows)
+            const double score = pad * halo * (1.0 + 0.02 * std::log2((double)target / P)) * (1.0 - 0.001 * std::log2((double)bx));
+            if (score < best) { best = score; bb[0] = bx; bb[1] = by; bb[2] = bz; }
+         }
+   d.BX = bb[0]; d.BY = bb[1]; d.BZ = bb[2]; d.P = bb[0] * bb[1] * bb[2];
+   d.NTX = (d.N1 + d.BX - 1) / d.BX; d.NTY = (d.N2 + d.BY - 1) / d.BY; d.NTZ = (d.N3 + d.BZ - 1) / d.BZ;
+}
+
 extern "C" {
 
 int asd_build_lattice_table(asd_engine* e, int kind, int NA, int N1, int N2, int N3, const char* bc3, int maxslot,
@@ -26,9 +55,13 @@ int asd_build_lattice_table(asd_engine* e, int kind, int NA, int N1, int N2, int
       for (int a = 0; a < 3; a++) d.periodic[a] = (bc3[a] == 'P' || bc3[a] == 'p') ? 1 : 0;
       d.reduced = (e->NH < e->N) ? 1 : 0;
       d.Ncell = N1 * N2 * N3;
-      d.Ncell_pad = ((d.Ncell + 31) / 32) * 32;
       d.N = e->N;
-      d.Npad = d.reduced ? NA * d.Ncell_pad : ((e->N + 31) / 32) * 32;
+      choose_brick(d);
+      {
+         const long np = (long)d.NTX * d.NTY * d.NTZ * d.NA * d.P;
+         if (np > 2000000000L) return fail(-3, "too many atoms for 32-bit device indices");
+         d.Npad = (int)np;
+      }
       if (d.reduced)
          for (int i = 0; i < e->N; i++) if (e->aHam[i] != i % NA + 1) return fail(-1, "aHam is not the basis-atom number; cannot use the lattice builder");
       L.N = e->N; L.Npad = d.Npad; L.NH = e->NH; L.M = e->M; L.reduced = d.reduced;

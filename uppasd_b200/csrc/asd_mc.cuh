@@ -60,7 +60,11 @@ mc_colour_kernel(const __grid_constant__ Tables t, const __grid_constant__ McPar
       const double zarg = sqrt(zx * zx + zy * zy + zz * zz);
       const double zctheta = zz / zarg;
       const double zstheta = sqrt(1.0 - zctheta * zctheta) + 1e-14;
-      const double zcphi = zx / (zarg * zstheta), zsphi = zy / (zarg * zstheta);
+      double zcphi = zx / (zarg * zstheta), zsphi = zy / (zarg * zstheta);
+      // Deviation from flip_h (documented in DESIGN.md): a field exactly along +-z makes the reference's frame
+      // degenerate (zcphi = zsphi = 0 -> the new spin loses its transverse part and is no longer a unit vector);
+      // any azimuth is valid there, take phi_field = 0.
+      if (zx == 0.0 && zy == 0.0) { zcphi = 1.0; zsphi = 0.0; }
       const double em2 = exp(-2.0 * zarg);
       const double ctheta = 1.0 + (1.0 / zarg) * log((1.0 - em2) * u[0] + em2 + 1e-14);
       const double stheta = sqrt(fmax(1.0 - ctheta * ctheta, 0.0));

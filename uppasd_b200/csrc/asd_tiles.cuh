@@ -1,0 +1,96 @@
+// Setup kernel of the staged tile path: turns the slot-major neighbour table nl[z][Npad] into
+//   * ulist[tile][ucap] : the sorted unique slots that the 256 atoms of a tile gather from (plus their own slots),
+//   * nl16[zq8][Npad]   : the same neighbour table as 16-bit positions in the tile's ulist, 8 per 16-byte word.
+// The per-step kernels then stage emomM of ulist in shared memory once per CTA and never gather from global
+// memory (asd_device.cuh: llg_stage_kernel<.,.,.,true>).  What the table means is unchanged: entry j of atom i is
+// still nlist(j,i) of the reference (source/Hamiltonian/hamiltoniandatatype.f90:30-33), neighbour order kept.
+//
+// One CTA per tile.  pass 0 only counts the unique slots (so the host can size ucap); pass 1 builds both arrays.
+#pragma once
+#include <cuda_runtime.h>
+#include <limits.h>
+
+namespace asd {
+
+constexpr int TILE = 256;          // slots per tile = threads per CTA of the stage kernels
+constexpr int TILE_HASH = 16384;   // open-addressing table (ints) used to find the unique slots
+constexpr int TILE_UMAX = 6144;    // beyond this many unique slots per tile the staged path is not used
+
+__global__ void __launch_bounds__(TILE)
+tile_gather_kernel(int Npad, int z, const int* __restrict__ nl, int pass, int ucap, int* __restrict__ ucount,
+                   int* __restrict__ ulist, uint4* __restrict__ nl16, int zq8) {
+   extern __shared__ int tsm[];
+   int* tab = tsm;                 // [TILE_HASH]
+   int* lst = tsm + TILE_HASH;     // [8192] (pass 1)
+   __shared__ int nuniq, over, nfill;
+   const int tile = blockIdx.x;
+   const int s = tile * TILE + threadIdx.x;
+   for (int q = threadIdx.x; q < TILE_HASH; q += TILE) tab[q] = -1;
+   if (threadIdx.x == 0) { nuniq = 0; over = 0; nfill = 0; }
+   __syncthreads();
+   auto insert = [&](int key) {
+      unsigned hsh = ((unsigned)key * 2654435761u) >> 18;   // 14 bits
+      while (true) {
+         if (*(volatile int*)&over) return;
+         const int old = atomicCAS(&tab[hsh], -1, key);
+         if (old == key) return;
+         if (old == -1) { if (atomicAdd(&nuniq, 1) + 1 > TILE_UMAX) over = 1; return; }
+         hsh = (hsh + 1) & (TILE_HASH - 1);
+      }
+   };
+   if (s < Npad) {
+      insert(s);
+      for (int j = 0; j < z; j++) insert(nl[(size_t)j * Npad + s]);
+   }
+   __syncthreads();
+   if (pass == 0) {
+      if (threadIdx.x == 0) ucount[tile] = over ? INT_MAX : nuniq;
+      return;
+   }
+   if (over) { if (threadIdx.x == 0) ucount[tile] = INT_MAX; return; }
+   // compact, pad to a power of two, bitonic sort (ascending: a staged tile is read in address order)
+   const int cnt = nuniq;
+   int np2 = 32;
+   while (np2 < cnt) np2 <<= 1;
+   for (int q = threadIdx.x; q < TILE_HASH; q += TILE) {
+      const int v = tab[q];
+      if (v >= 0) lst[atomicAdd(&nfill, 1)] = v;
+   }
+   for (int q = cnt + threadIdx.x; q < np2; q += TILE) lst[q] = INT_MAX;
+   __syncthreads();
+   for (int kk = 2; kk <= np2; kk <<= 1)
+      for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+         for (int idx = threadIdx.x; idx < np2; idx += TILE) {
+            const int ixj = idx ^ jj;
+            if (ixj > idx) {
+               const int a = lst[idx], b = lst[ixj];
+               const bool asc = (idx & kk) == 0;
+               if ((a > b) == asc) { lst[idx] = b; lst[ixj] = a; }
+            }
+         }
+         __syncthreads();
+      }
+   for (int q = threadIdx.x; q < ucap; q += TILE) ulist[(size_t)tile * ucap + q] = (q < cnt) ? lst[q] : lst[0];
+   if (threadIdx.x == 0) ucount[tile] = cnt;
+   if (s >= Npad) return;
+   auto find = [&](int key) -> unsigned {
+      int lo = 0, hi = cnt - 1;
+      while (lo < hi) {
+         const int mid = (lo + hi) >> 1;
+         if (lst[mid] < key) lo = mid + 1; else hi = mid;
+      }
+      return (unsigned)lo;
+   };
+   const unsigned self = find(s);
+   for (int q = 0; q < zq8; q++) {
+      unsigned v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+         const int j = 8 * q + u;
+         v[u] = (j < z) ? find(nl[(size_t)j * Npad + s]) : self;
+      }
+      nl16[(size_t)q * Npad + s] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+   }
+}
+
+}  // namespace asd
