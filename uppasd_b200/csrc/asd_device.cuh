@@ -273,16 +273,19 @@ __device__ __forceinline__ void idx_prologue(const Tables& t, int i, int nq, uin
 }
 
 // Heisenberg sum from the staged tile (hamiltonianactions.f90:461-464, same j order): neighbours arrive as 16-bit
-// positions into the CTA's shared-memory copy of emomM (sx/sy/sz), three conflict-free LDS.64 per neighbour.
-template <bool REDUCED>
-__device__ __forceinline__ void exchange_staged(const Tables& t, const double* __restrict__ sx, const double* __restrict__ sy,
-                                                const double* __restrict__ sz, int i, int ih, int n, int nq,
-                                                uint4 w[ASD_NPF], const double* smc, double& fx, double& fy, double& fz) {
+// positions into the CTA's shared-memory copy of emomM (s3: 24-byte records {mx,my,mz}; the 24-byte stride is
+// conflict-free for 8-byte accesses), three LDS.64 per neighbour off one address.
+// CSRC: 0 = reduced couplings in the kernel-parameter constant bank, 1 = reduced couplings through a pointer
+// (shared or global), 2 = per-atom couplings streamed from cp4.
+template <int CSRC>
+__device__ __forceinline__ void exchange_staged_impl(const Tables& t, const double* __restrict__ s3, int i, int ih, int n,
+                                                     int nq, uint4 w[ASD_NPF], const double* __restrict__ crow,
+                                                     double& fx, double& fy, double& fz) {
    const size_t Npad = t.Npad;
    const uint4* __restrict__ p = t.nl16 + i;
-   const double4* __restrict__ pc = REDUCED ? nullptr : t.cp4 + i;
-   const double* __restrict__ crow = REDUCED ? (smc ? smc + (size_t)ih * t.z : t.cp + (size_t)ih * t.z) : nullptr;
+   const double4* __restrict__ pc = (CSRC == 2) ? t.cp4 + i : nullptr;
    const int cbase = ih * t.z;
+   const int nfull = n >> 3;
    for (int q0 = 0; q0 < nq; q0 += ASD_NPF) {
 #pragma unroll
       for (int s = 0; s < ASD_NPF; s++) {
@@ -290,25 +293,48 @@ __device__ __forceinline__ void exchange_staged(const Tables& t, const double* _
          if (q < nq) {
             const uint4 c = w[s];
             if (q + ASD_NPF < nq) w[s] = ld_stream_u4(p + (size_t)(q + ASD_NPF) * Npad);
-            double4 ca, cb;
-            if (!REDUCED) { ca = ld_nc_d4(pc + (size_t)(2 * q) * Npad); if (8 * q + 4 < n) cb = ld_nc_d4(pc + (size_t)(2 * q + 1) * Npad); }
+            double cj[8];
+            if (CSRC == 2) {
+               const double4 ca = ld_nc_d4(pc + (size_t)(2 * q) * Npad);
+               double4 cb = make_double4(0.0, 0.0, 0.0, 0.0);
+               if (8 * q + 4 < n) cb = ld_nc_d4(pc + (size_t)(2 * q + 1) * Npad);
+               cj[0] = ca.x; cj[1] = ca.y; cj[2] = ca.z; cj[3] = ca.w; cj[4] = cb.x; cj[5] = cb.y; cj[6] = cb.z; cj[7] = cb.w;
+            }
+            const unsigned li[8] = {c.x & 0xffffu, c.x >> 16, c.y & 0xffffu, c.y >> 16,
+                                    c.z & 0xffffu, c.z >> 16, c.w & 0xffffu, c.w >> 16};
+            if (q < nfull) {
+               // full word: eight neighbours, no predicates
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-               const int j = 8 * q + u;
-               if (j < n) {
-                  const unsigned word = (u >> 1) == 0 ? c.x : (u >> 1) == 1 ? c.y : (u >> 1) == 2 ? c.z : c.w;
-                  const unsigned li = (u & 1) ? (word >> 16) : (word & 0xffffu);
-                  double cj;
-                  if (REDUCED) cj = t.cpl_param ? t.cpl_small[cbase + j] : crow[j];
-                  else { const double4 cc = (u < 4) ? ca : cb; cj = (u & 3) == 0 ? cc.x : (u & 3) == 1 ? cc.y : (u & 3) == 2 ? cc.z : cc.w; }
-                  fx = fma(cj, sx[li], fx);
-                  fy = fma(cj, sy[li], fy);
-                  fz = fma(cj, sz[li], fz);
+               for (int u = 0; u < 8; u++) {
+                  const double* __restrict__ m = s3 + li[u] * 3u;
+                  const double cc = (CSRC == 0) ? t.cpl_small[cbase + 8 * q + u] : (CSRC == 1) ? crow[8 * q + u] : cj[u];
+                  fx = fma(cc, m[0], fx);
+                  fy = fma(cc, m[1], fy);
+                  fz = fma(cc, m[2], fz);
+               }
+            } else {
+#pragma unroll
+               for (int u = 0; u < 8; u++) {
+                  if (8 * q + u < n) {
+                     const double* __restrict__ m = s3 + li[u] * 3u;
+                     const double cc = (CSRC == 0) ? t.cpl_small[cbase + 8 * q + u] : (CSRC == 1) ? crow[8 * q + u] : cj[u];
+                     fx = fma(cc, m[0], fx);
+                     fy = fma(cc, m[1], fy);
+                     fz = fma(cc, m[2], fz);
+                  }
                }
             }
          }
       }
    }
+}
+
+template <bool REDUCED>
+__device__ __forceinline__ void exchange_staged(const Tables& t, const double* __restrict__ s3, int i, int ih, int n, int nq,
+                                                uint4 w[ASD_NPF], const double* smc, double& fx, double& fy, double& fz) {
+   if (!REDUCED) exchange_staged_impl<2>(t, s3, i, ih, n, nq, w, nullptr, fx, fy, fz);
+   else if (t.cpl_param) exchange_staged_impl<0>(t, s3, i, ih, n, nq, w, nullptr, fx, fy, fz);
+   else exchange_staged_impl<1>(t, s3, i, ih, n, nq, w, smc ? smc + (size_t)ih * t.z : t.cp + (size_t)ih * t.z, fx, fy, fz);
 }
 
 // L2 bulk prefetch of the index words and gather list of the tile `pf_tiles` ahead (staged path)
@@ -537,21 +563,20 @@ llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPa
       uint4 w[ASD_NPF];
       idx_prologue(t, active ? i : 0, nq, w);
       const int ncpl = (t.cpl_param ? 0 : t.sm_cp) + t.sm_dm + t.sm_bq;
-      double* __restrict__ sx = sm + ncpl;
-      double* __restrict__ sy = sx + t.ucap;
-      double* __restrict__ sz = sy + t.ucap;
+      double* __restrict__ s3 = sm + ncpl;
       const int cnt = __ldg(t.ucount + blockIdx.x);
       const int* __restrict__ ul = t.ulist + (size_t)blockIdx.x * t.ucap;
 #pragma unroll 4
       for (int u = threadIdx.x; u < cnt; u += 256) {
          const SpinVec v = S[__ldg(ul + u)];
-         sx[u] = v.x * v.m; sy[u] = v.y * v.m; sz[u] = v.z * v.m;
+         double* __restrict__ m = s3 + 3 * u;
+         m[0] = v.x * v.m; m[1] = v.y * v.m; m[2] = v.z * v.m;
       }
       if (active) own = S[i];
       stage_couplings(t, sm, smc, smd, smb);   // ends with __syncthreads() when it stages anything
       if (ncpl == 0) __syncthreads();
       if (!active) return;
-      exchange_staged<REDUCED>(t, sx, sy, sz, i, ih, n, nq, w, smc, bs[0], bs[1], bs[2]);
+      exchange_staged<REDUCED>(t, s3, i, ih, n, nq, w, smc, bs[0], bs[1], bs[2]);
       site_field<REDUCED, false>(t, S, i, ih, own, smc, smd, smb, bs, bq);
    } else {
       prefetch_tile(t, S);

@@ -10,7 +10,10 @@ static int host_orig(asd_engine* e, Layout& L) {
 }
 
 // Brick shape of the device order (LatticeDesc): P = BX*BY*BZ cells, a multiple of 32, with NA*P close to one
-// 256-thread tile; minimises (padding of partly empty bricks) x (halo of a brick for a 2-cell interaction range).
+// 256-thread tile.  Cost model (shared-memory wavefronts per tile of the staged stage kernel, measured with ncu on
+// bcc Fe, profiles/): the gather loop costs 2 wavefronts per 8-byte LDS when a warp is one 32-cell x-run (its
+// neighbours are then at most two contiguous runs of the gather list -> conflict-free), ~3 for 16-cell and ~3.6 for
+// 8-cell rows; staging costs ~0.44 wavefronts per distinct spin, which grows with the brick's halo.
 static void choose_brick(LatticeDesc& d) {
    const int Nd[3] = {d.N1, d.N2, d.N3};
    int target = 256 / d.NA;
@@ -30,8 +33,10 @@ static void choose_brick(LatticeDesc& d) {
                pad *= (double)((Nd[a] + b[a] - 1) / b[a]) * b[a] / Nd[a];
                halo *= (double)(b[a] + (Nd[a] > 1 ? 4 : 0)) / b[a];
             }
-            // small preference for full-size bricks and for long x runs (coalesced rows)
-            const double score = pad * halo * (1.0 + 0.02 * std::log2((double)target / P)) * (1.0 - 0.001 * std::log2((double)bx));
+            const double wf = (bx >= 32) ? 2.0 : (bx == 16) ? 3.0 : (bx == 8) ? 3.6 : 4.0;
+            const double loop = wf * 150.0;             // 50 neighbours x 3 loads, per atom
+            const double stage = 0.44 * 0.55 * halo;    // distinct spins per atom ~ 0.55 x bounding box
+            const double score = pad * (loop + stage) * (1.0 + 0.02 * std::log2((double)target / P));
             if (score < best) { best = score; bb[0] = bx; bb[1] = by; bb[2] = bz; }
          }
    d.BX = bb[0]; d.BY = bb[1]; d.BZ = bb[2]; d.P = bb[0] * bb[1] * bb[2];
