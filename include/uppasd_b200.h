@@ -176,6 +176,30 @@ int asd_get_table(asd_engine* e, int kind, int* list, int* listsize, double* cou
  * a cos(2 pi h_i)), h_i = frac(i * 0.6180339887), i the 1-based atom index; magnitude per basis atom. */
 int asd_init_moments_tilted(asd_engine* e, double amplitude, int NA, const double* mmom_basis);
 
+/* ---- multi-GPU (neither mode exists in the reference, which is single-device) ------------------
+ * Ensemble sharding: every engine holds Mensemble/G whole ensembles and all tables; no communication.  The
+ * noise is keyed by the GLOBAL ensemble index so that results do not depend on G. */
+int asd_set_ensemble_offset(asd_engine* e, unsigned int first_ensemble);
+
+/* Slab decomposition of ONE supercell along z: engine `slab_index` of `nslabs` owns N3/nslabs consecutive cell
+ * planes (the atom index i0 + NA*(ix + N1*(iy + N2*iz)) of geometry.f90 makes that a contiguous index range).
+ * Call after asd_set_system (Natom = atoms of the local slab) and before asd_build_lattice_table, which then
+ * takes the GLOBAL N3.  halo_planes = interaction range along z in cell planes (2 for the 4-shell bcc table).
+ * Neighbour entries that leave the slab point at halo slots; the stage kernels of the boundary tiles store
+ * their new spins directly into the ring neighbours' halo slots (peer memory over NVLink) and publish an epoch
+ * flag; the next stage waits on the flags.  Noise and tilted initial moments are keyed by the global atom index.
+ * Arrays passed to / returned by asd_set_moments / asd_get_moments / asd_measure are those of the local slab. */
+int asd_set_slab(asd_engine* e, int nslabs, int slab_index, int halo_planes);
+/* after asd_commit: IPC handles (asd_slab_handle_bytes() bytes) of this slab's cur / pred / flag buffers ... */
+int asd_slab_handle_bytes(void);
+int asd_slab_export(asd_engine* e, void* handles);
+/* ... which the ring neighbours open (one process per GPU; exchange the bytes with any host transport) */
+int asd_slab_connect_ipc(asd_engine* e, const void* lower_handles, const void* upper_handles);
+/* same, for engines that live in one process (also: a single slab whose halos are its own periodic images) */
+int asd_slab_connect_local(asd_engine* e, asd_engine* lower, asd_engine* upper);
+/* exchanges completed so far; error_flag != 0 (and a negative return) if a halo wait timed out */
+int asd_slab_status(asd_engine* e, unsigned long long* epoch, int* error_flag);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,94 @@
+"""Slab decomposition + fused halo push: a supercell cut into z-slabs must reproduce the undecomposed run bit for
+bit (same kernels, same summation order, noise keyed by the global atom index) -- T = 0 and thermal, both solvers."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _bcc(ncell, solver, temp, nslabs=0, mens=1, damping=0.5, seed=77):
+    """list of engines: one undecomposed (nslabs = 0) or `nslabs` slabs living in this process on device 0"""
+    import bench
+    from uppasd_b200 import host, lattice, slab
+    B, CONST = bench.BCC, bench.CONST
+    ns, ca, cs, sh = lattice.stencil(B['cell'], B['bas'], B['atype'], np.array([4]), B['shells'][None], 1, np.ones((1, 4), dtype=int))
+    cp = lattice.couplings(ns, ca, sh, B['atype'], B['J'][None, None, :], B['mom'], CONST['mry'], CONST['mub'])
+    H = slab.halo_depth(cs, ns)
+    assert H == 2
+    out = []
+    for g in range(max(nslabs, 1)):
+        e = host.Engine(0)
+        e.set_constants(CONST['gama'], CONST['k_bolt'], CONST['mub'], CONST['mry'])
+        nz = ncell[2] // max(nslabs, 1)
+        n = 2 * ncell[0] * ncell[1] * nz
+        e.set_system(n, mens, 2, (np.arange(n, dtype=np.int32) % 2) + 1)
+        if nslabs:
+            e.set_slab(nslabs, g, H)
+        e.build_lattice_table(0, 2, ncell, ('P', 'P', 'P'), ns, ca, cs, cp)
+        e.set_llg(solver, 1e-16, landeg=1.0, lambda1=damping, temp=temp, seed=seed)
+        e.commit()
+        out.append(e)
+    if nslabs:
+        for g, e in enumerate(out):
+            e.slab_connect_local(out[(g - 1) % nslabs], out[(g + 1) % nslabs])
+    for e in out:
+        e.init_moments_tilted(0.3, B['mom'])
+    return out
+
+
+def _gather(engines):
+    return np.concatenate([e.get_moments()[0] for e in engines], axis=1)
+
+
+@pytest.mark.parametrize('solver', [1, 5])
+@pytest.mark.parametrize('temp', [0.0, 300.0])
+@pytest.mark.parametrize('nslabs', [1, 2, 4])
+def test_slab_matches_undecomposed(solver, temp, nslabs):
+    ncell = (32, 6, 16)
+    ref = _bcc(ncell, solver, temp)[0]
+    sl = _bcc(ncell, solver, temp, nslabs=nslabs)
+    assert np.array_equal(_gather(sl), ref.get_moments()[0])          # same tilted start (global index)
+    done = 0
+    for n in (1, 3, 20):
+        ref.sd_steps(n, first_step=done + 1)
+        # interleave the slabs step by step: inside one process a slab's halo wait needs its neighbours' launches queued
+        for s in range(n):
+            for e in sl:
+                e.sd_steps(1, first_step=done + 1 + s)
+        done += n
+        a, b = _gather(sl), ref.get_moments()[0]
+        assert np.array_equal(a, b), (solver, temp, nslabs, done, np.abs(a - b).max())
+    for e in sl:
+        ep, err = e.slab_status()
+        assert err == 0 and ep == 1 + 2 * done
+
+
+def test_slab_observables_and_ensembles():
+    ncell = (32, 4, 8)
+    ref = _bcc(ncell, 1, 300.0, mens=3)[0]
+    sl = _bcc(ncell, 1, 300.0, nslabs=2, mens=3)
+    for s in range(10):
+        ref.sd_steps(1, first_step=s + 1)
+        for e in sl:
+            e.sd_steps(1, first_step=s + 1)
+    m_ref = ref.measure()
+    m_sl = sum(e.measure() for e in sl)
+    assert np.allclose(m_sl, m_ref, rtol=1e-13, atol=1e-9)
+    assert np.array_equal(_gather(sl), ref.get_moments()[0])
+
+
+def test_slab_errors_are_loud():
+    from uppasd_b200 import host
+    sl = _bcc((32, 4, 8), 1, 0.0, nslabs=2)
+    with pytest.raises(host.AsdError):
+        sl[0].mc_sweeps('M', 1, 300.0)          # Monte Carlo is not decomposed yet
+    e = host.Engine(0)
+    e.set_system(2 * 32 * 4 * 3, 1, 2, (np.arange(2 * 32 * 4 * 3, dtype=np.int32) % 2) + 1)
+    e.set_slab(2, 0, 2)
+    import bench
+    from uppasd_b200 import lattice
+    B, CONST = bench.BCC, bench.CONST
+    ns, ca, cs, sh = lattice.stencil(B['cell'], B['bas'], B['atype'], np.array([4]), B['shells'][None], 1, np.ones((1, 4), dtype=int))
+    cp = lattice.couplings(ns, ca, sh, B['atype'], B['J'][None, None, :], B['mom'], CONST['mry'], CONST['mub'])
+    with pytest.raises(host.AsdError):
+        e.build_lattice_table(0, 2, (32, 4, 7), ('P', 'P', 'P'), ns, ca, cs, cp)   # 7 planes do not split in two

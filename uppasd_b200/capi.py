@@ -56,6 +56,13 @@ SYMBOLS = {
     'asd_get_table_dims': (C.c_int, [vp, C.c_int, c_int_p, c_int_p]),
     'asd_get_table': (C.c_int, [vp, C.c_int, vp, vp, vp]),
     'asd_init_moments_tilted': (C.c_int, [vp, C.c_double, C.c_int, vp]),
+    'asd_set_ensemble_offset': (C.c_int, [vp, C.c_uint]),
+    'asd_set_slab': (C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
+    'asd_slab_handle_bytes': (C.c_int, []),
+    'asd_slab_export': (C.c_int, [vp, vp]),
+    'asd_slab_connect_ipc': (C.c_int, [vp, vp, vp]),
+    'asd_slab_connect_local': (C.c_int, [vp, vp, vp]),
+    'asd_slab_status': (C.c_int, [vp, C.POINTER(C.c_ulonglong), c_int_p]),
 }
 
 _lib = None

@@ -30,12 +30,16 @@ struct __align__(32) SpinVec {
 // Kernel parameter block (passed by value; < 4 KB).
 struct Tables {
    int N;      // real atoms
-   int Npad;   // device slots (groups padded to 32)
+   int Npad;   // device slots (groups padded to 32; in slab mode the neighbours' halo slots come last)
+   int Nown;   // slots that are computed ( = Npad unless this engine holds a slab with halos)
+   unsigned int atom_offset;  // global index of local atom 0 (slab decomposition): keys the noise, never the data
+   unsigned int ens_offset;   // global index of local ensemble 0 (ensemble sharding): keys the noise
    int M;      // ensembles
    int NH;     // Hamiltonian rows
    int reduced;  // 1: couplings indexed by ham row (shared by a whole sublattice), 0: per atom
    const int* __restrict__ ham;   // [Npad] 0-based ham row of the slot, -1 for padding slots
    const int* __restrict__ orig;  // [Npad] 0-based original atom index, -1 for padding slots
+   const int2* __restrict__ meta; // [Npad] {ham, orig} zipped: one 8-byte load in the stage kernels
    // Heisenberg
    int z;
    const int* __restrict__ nl;      // [z][Npad] device index of neighbour
@@ -338,12 +342,12 @@ __device__ __forceinline__ void exchange_staged(const Tables& t, const double* _
 }
 
 // L2 bulk prefetch of the index words and gather list of the tile `pf_tiles` ahead (staged path)
-__device__ __forceinline__ void prefetch_tile_staged(const Tables& t) {
+__device__ __forceinline__ void prefetch_tile_staged(const Tables& t, int this_tile) {
    if (t.pf_tiles == 0) return;
-   const size_t tile = (size_t)blockIdx.x + t.pf_tiles;
+   const size_t tile = (size_t)this_tile + t.pf_tiles;
    const size_t first = tile * blockDim.x;
-   if (first >= (size_t)t.Npad) return;
-   const unsigned cnt = (unsigned)min((size_t)blockDim.x, (size_t)t.Npad - first);
+   if (first >= (size_t)t.Nown) return;
+   const unsigned cnt = (unsigned)min((size_t)blockDim.x, (size_t)t.Nown - first);
    if ((int)threadIdx.x < t.zq8) {
       const uint4* a = t.nl16 + (size_t)threadIdx.x * t.Npad + first;
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(cnt * 16u) : "memory");
@@ -355,12 +359,12 @@ __device__ __forceinline__ void prefetch_tile_staged(const Tables& t) {
 
 // L2 bulk prefetch (cp.async.bulk.prefetch.L2) of the index rows and spins of the tile that a CTA scheduled
 // ~one wave later will work on: turns the DRAM latency of the index stream into an L2 hit.
-__device__ __forceinline__ void prefetch_tile(const Tables& t, const SpinVec* S) {
+__device__ __forceinline__ void prefetch_tile(const Tables& t, const SpinVec* S, int this_tile) {
    if (t.pf_tiles == 0 || t.nl4 == nullptr) return;
-   const size_t tile = (size_t)blockIdx.x + t.pf_tiles;
+   const size_t tile = (size_t)this_tile + t.pf_tiles;
    const size_t first = tile * blockDim.x;
-   if (first >= (size_t)t.Npad) return;
-   const unsigned cnt = (unsigned)min((size_t)blockDim.x, (size_t)t.Npad - first);
+   if (first >= (size_t)t.Nown) return;
+   const unsigned cnt = (unsigned)min((size_t)blockDim.x, (size_t)t.Nown - first);
    if ((int)threadIdx.x < t.zq) {
       const int4* a = t.nl4 + (size_t)threadIdx.x * t.Npad + first;
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(cnt * 16u) : "memory");
@@ -535,73 +539,93 @@ __device__ __forceinline__ double calcm(int mompar, double m, double m0, double 
 //   STAGE 2: gathers from `pred`, reads own `cur`, writes the new spin to `cur` (own slot only).
 //   b2eff (Depondt only): [M][3][Npad] predictor field kept for the Heun average.
 // ------------------------------------------------------------------------------------------------
-template <int SOLVER, int STAGE, bool REDUCED, bool STAGED>
-__global__ void __launch_bounds__(256, STAGED ? ASD_MINB_STAGED : ASD_MINB)
-llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgParams p, SpinVec* __restrict__ cur,
-                 SpinVec* __restrict__ pred, double* __restrict__ b2eff) {
-   extern __shared__ double sm[];
-   const double *smc, *smd, *smb;
-   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-   const int k = blockIdx.y;
-   SpinVec* __restrict__ curk = cur + (size_t)k * t.Npad;
-   SpinVec* __restrict__ predk = pred + (size_t)k * t.Npad;
-   const SpinVec* __restrict__ S = (STAGE == 1) ? curk : predk;
-   // padding slots and the tail of the last tile take part in the staging but compute nothing
-   int ih = 0;
-   bool active = i < t.Npad;
-   if (active) {
-      if (REDUCED) { ih = __ldg(t.ham + i); active = ih >= 0; }
-      else active = __ldg(t.orig + i) >= 0;
-   }
-   double bs[3] = {0.0, 0.0, 0.0}, bq[3], h[3];
-   SpinVec own;
-   if (STAGED) {
-      prefetch_tile_staged(t);
-      // (1) index words in flight first, (2) stage emomM of the tile's gather list, (3) sum from shared memory
-      const int n = active ? (REDUCED ? __ldg(t.lsize + ih) : t.z) : 0;
-      const int nq = (n + 7) >> 3;
-      uint4 w[ASD_NPF];
-      idx_prologue(t, active ? i : 0, nq, w);
-      const int ncpl = (t.cpl_param ? 0 : t.sm_cp) + t.sm_dm + t.sm_bq;
-      double* __restrict__ s3 = sm + ncpl;
-      const int cnt = __ldg(t.ucount + blockIdx.x);
-      const int* __restrict__ ul = t.ulist + (size_t)blockIdx.x * t.ucap;
-#pragma unroll 4
-      for (int u = threadIdx.x; u < cnt; u += 256) {
-         const SpinVec v = S[__ldg(ul + u)];
-         double* __restrict__ m = s3 + 3 * u;
-         m[0] = v.x * v.m; m[1] = v.y * v.m; m[2] = v.z * v.m;
+// Halo push of the slab decomposition (one slab of the supercell per GPU): an EDGE launch covers the
+// tiles that hold the H boundary planes of this slab; every atom of those planes also stores its new spin straight
+// into the halo slots of the ring neighbour that gathers it (peer-mapped memory over NVLink), and the last CTA of
+// the launch publishes the exchange epoch in the neighbours' flag words.  No separate pack / send / unpack passes.
+struct EdgeParams {
+   const int* __restrict__ hdst_lo;   // [Nown] halo slot in the LOWER neighbour that mirrors this atom, or -1
+   const int* __restrict__ hdst_hi;   // [Nown] halo slot in the UPPER neighbour, or -1
+   SpinVec* peer_lo;                  // the buffer this stage writes (cur or pred), as mapped from the neighbours
+   SpinVec* peer_hi;
+   unsigned long long* flag_lo;       // flag word of the lower neighbour that THIS rank owns (its "upper" word)
+   unsigned long long* flag_hi;
+   unsigned long long epoch;          // value to publish
+   unsigned int* ctr;                 // CTA completion counter (self-resetting)
+};
+
+// which tiles a launch covers: blockIdx.x < split -> first + blockIdx.x, else second + (blockIdx.x - split)
+struct TileRange { int first, split, second; };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+   unsigned long long v;
+   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+   return v;
+}
+
+// waits until both neighbours have published `epoch` (their halo stores are then visible); gives up after
+// `timeout` clock ticks and raises *err so that a lost peer cannot hang the GPU
+__global__ void halo_wait_kernel(const unsigned long long* flags, int wait_lo, int wait_hi, unsigned long long epoch,
+                                 long long timeout, int* err) {
+   const long long t0 = clock64();
+   for (int side = 0; side < 2; side++) {
+      if (!(side == 0 ? wait_lo : wait_hi)) continue;
+      while (ld_acquire_sys(flags + side) < epoch) {
+         if (clock64() - t0 > timeout) { *err = 1 + side; return; }
+         __nanosleep(200);
       }
-      if (active) own = S[i];
-      stage_couplings(t, sm, smc, smd, smb);   // ends with __syncthreads() when it stages anything
-      if (ncpl == 0) __syncthreads();
-      if (!active) return;
-      exchange_staged<REDUCED>(t, s3, i, ih, n, nq, w, smc, bs[0], bs[1], bs[2]);
-      site_field<REDUCED, false>(t, S, i, ih, own, smc, smd, smb, bs, bq);
-   } else {
-      prefetch_tile(t, S);
-      stage_couplings(t, sm, smc, smd, smb);
-      if (!active) return;
-      own = S[i];
-      site_field<REDUCED>(t, S, i, ih, own, smc, smd, smb, bs, bq);
    }
-   ext_field(t, i, k, h);
-   // beff = beff1 + beff2, beff2 = beff_q + external_field (hamiltonianactions.f90:240-243)
-   double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
+}
+
+// copies the boundary planes of buffer S into the neighbours' halos (initial fill / after Monte Carlo colours)
+__global__ void halo_push_kernel(int Nown, int M, size_t Npad, const SpinVec* __restrict__ S, EdgeParams ep) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+   if (i < Nown) {
+      const int lo = __ldg(ep.hdst_lo + i), hi = __ldg(ep.hdst_hi + i);
+      if (lo >= 0 || hi >= 0) {
+         const SpinVec v = S[(size_t)k * Npad + i];
+         if (lo >= 0) ep.peer_lo[(size_t)k * Npad + lo] = v;
+         if (hi >= 0) ep.peer_hi[(size_t)k * Npad + hi] = v;
+      }
+   }
+   __threadfence_system();
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      const unsigned int total = gridDim.x * gridDim.y;
+      if (atomicAdd(ep.ctr, 1u) == total - 1) {
+         *ep.ctr = 0;
+         __threadfence_system();
+         if (ep.flag_lo) st_release_sys(ep.flag_lo, ep.epoch);
+         if (ep.flag_hi) st_release_sys(ep.flag_hi, ep.epoch);
+      }
+   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The integrator of one site: midpoint (SOLVER 1) or Depondt (SOLVER 5), predictor (STAGE 1) or corrector +
+// moment update (STAGE 2).  b = effective field at the spin `own` the field was evaluated with; c0 = spin at
+// time t.  Returns the spin to store (pred in stage 1, cur in stage 2).
+// ------------------------------------------------------------------------------------------------
+template <int SOLVER, int STAGE>
+__device__ __forceinline__ SpinVec integrate_site(const Tables& t, const LlgParams& p, int i, int k, int io, const double b[3],
+                                                  const SpinVec& own, const SpinVec& c0, double* __restrict__ b2eff) {
    double lam, lg, temp;
    if (p.per_site) { lam = __ldg(p.lambda_a + i); lg = __ldg(p.landeg_a + i); temp = __ldg(p.temp_a + i); }
    else { lam = p.lambda; lg = p.landeg; temp = p.temp; }
-   const SpinVec c0 = (STAGE == 1) ? own : curk[i];  // spin at time t
    const double e[3] = {c0.x, c0.y, c0.z};
    const double m = c0.m;
    double g[3] = {0.0, 0.0, 0.0};
-   if (p.thermal) gauss3f(p.seed, (uint32_t)__ldg(t.orig + i), (uint32_t)k, p.step, 0u, g[0], g[1], g[2]);
+   if (p.thermal) gauss3f(p.seed, (uint32_t)io + t.atom_offset, (uint32_t)k + t.ens_offset, p.step, 0u, g[0], g[1], g[2]);
    double bt[3] = {0.0, 0.0, 0.0};
    if (t.btorque) {
       const double* __restrict__ q = t.btorque + (size_t)k * 3 * t.Npad + i;
       bt[0] = __ldg(q); bt[1] = __ldg(q + t.Npad); bt[2] = __ldg(q + 2 * (size_t)t.Npad);
    }
    const double lldamp = p.per_site ? 1.0 / (1.0 + lam * lam) : p.u_lldamp;
+   SpinVec o;
    if (SOLVER == 1) {
       // ---- Mentink's semi-implicit midpoint (midpoint.f90) ----
       const double dt = p.per_site ? p.delta_t * 1.0 * p.gamma * lldamp : p.u_dt;  // bn = 1
@@ -629,14 +653,10 @@ llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPa
       double et[3];
       cayley(e, A, et);
       if (STAGE == 1) {
-         SpinVec o;
          o.x = 0.5 * (e[0] + et[0]); o.y = 0.5 * (e[1] + et[1]); o.z = 0.5 * (e[2] + et[2]); o.m = m;
-         predk[i] = o;
       } else {
-         SpinVec o;
          o.x = et[0]; o.y = et[1]; o.z = et[2];
          o.m = p.mompar ? calcm(p.mompar, m, __ldg(p.mmom0 + (size_t)k * t.Npad + i), et[2]) : m;
-         curk[i] = o;
       }
    } else {
       // ---- Depondt (depondt.f90) ----
@@ -658,16 +678,122 @@ llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPa
       if (STAGE == 1) {
          rodrigues(bd, e, rot, out);
          b2[0] = bd[0]; b2[t.Npad] = bd[1]; b2[2 * (size_t)t.Npad] = bd[2];
-         SpinVec o; o.x = out[0]; o.y = out[1]; o.z = out[2]; o.m = m;
-         predk[i] = o;
+         o.x = out[0]; o.y = out[1]; o.z = out[2]; o.m = m;
       } else {
          bd[0] = 0.5 * bd[0] + 0.5 * b2[0];
          bd[1] = 0.5 * bd[1] + 0.5 * b2[t.Npad];
          bd[2] = 0.5 * bd[2] + 0.5 * b2[2 * (size_t)t.Npad];
          rodrigues(bd, e, rot, out);
-         SpinVec o; o.x = out[0]; o.y = out[1]; o.z = out[2];
+         o.x = out[0]; o.y = out[1]; o.z = out[2];
          o.m = p.mompar ? calcm(p.mompar, m, __ldg(p.mmom0 + (size_t)k * t.Npad + i), out[2]) : m;
-         curk[i] = o;
+      }
+   }
+   return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One stage of one LLG step, field evaluation fused with the integrator.
+//   SOLVER 1 = semi-implicit midpoint, 5 = Depondt.   STAGE 1 = predictor, 2 = corrector (+ moment update).
+//   STAGE 1: gathers from `cur`, writes `pred` (midpoint spin for SOLVER 1, rotated spin for SOLVER 5);
+//   STAGE 2: gathers from `pred`, reads own `cur`, writes the new spin to `cur` (own slot only).
+//   b2eff (Depondt only): [M][3][Npad] predictor field kept for the Heun average.
+//   STAGED: tile path (shared-memory gather list).  EDGE: boundary tiles of a slab, see EdgeParams.
+// ------------------------------------------------------------------------------------------------
+template <int SOLVER, int STAGE, bool REDUCED, bool STAGED, bool EDGE>
+__global__ void __launch_bounds__(256, STAGED ? ASD_MINB_STAGED : ASD_MINB)
+llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgParams p, const __grid_constant__ EdgeParams ep,
+                 const TileRange tr, SpinVec* __restrict__ cur, SpinVec* __restrict__ pred, double* __restrict__ b2eff) {
+   extern __shared__ double sm[];
+   const double *smc, *smd, *smb;
+   const int tile = ((int)blockIdx.x < tr.split) ? tr.first + (int)blockIdx.x : tr.second + ((int)blockIdx.x - tr.split);
+   const int i = tile * 256 + threadIdx.x;
+   const int k = blockIdx.y;
+   SpinVec* __restrict__ curk = cur + (size_t)k * t.Npad;
+   SpinVec* __restrict__ predk = pred + (size_t)k * t.Npad;
+   const SpinVec* __restrict__ S = (STAGE == 1) ? curk : predk;
+   // padding slots and the tail of the last tile take part in the staging but compute nothing
+   int ih = 0, io = -1;
+   bool active = i < t.Nown;
+   double bs[3] = {0.0, 0.0, 0.0}, bq[3] = {0.0, 0.0, 0.0};
+   SpinVec own;
+   uint4 w[ASD_NPF];
+   double* __restrict__ s3 = nullptr;
+   if (STAGED) {
+      // (1) every independent global load in flight first: index words, {ham, orig}, own spins, gather list;
+      // (2) stage emomM of the tile's gather list in shared memory; (3) sum from shared memory
+      const int ii = active ? i : 0;
+      idx_prologue(t, ii, t.zq8, w);       // words beyond this atom's list length hold the atom itself: harmless
+      const int2 mt = __ldg(t.meta + ii);
+      own = S[ii];
+      if (STAGE == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(curk + ii));   // old spin, read after the sum
+      const int cnt = __ldg(t.ucount + tile);
+      const int* __restrict__ ul = t.ulist + (size_t)tile * t.ucap;
+      prefetch_tile_staged(t, tile);
+      const int ncpl = (t.cpl_param ? 0 : t.sm_cp) + t.sm_dm + t.sm_bq;
+      s3 = sm + ncpl;
+      for (int u0 = threadIdx.x; u0 < cnt; u0 += 3 * 256) {
+         int sl[3];
+#pragma unroll
+         for (int a = 0; a < 3; a++) sl[a] = (u0 + a * 256 < cnt) ? __ldg(ul + u0 + a * 256) : 0;
+         SpinVec v[3];
+#pragma unroll
+         for (int a = 0; a < 3; a++) v[a] = S[sl[a]];
+#pragma unroll
+         for (int a = 0; a < 3; a++)
+            if (u0 + a * 256 < cnt) {
+               double* __restrict__ m = s3 + 3 * (u0 + a * 256);
+               m[0] = v[a].x * v[a].m; m[1] = v[a].y * v[a].m; m[2] = v[a].z * v[a].m;
+            }
+      }
+      ih = REDUCED ? mt.x : 0;
+      io = mt.y;
+      active = active && io >= 0;
+      stage_couplings(t, sm, smc, smd, smb);   // ends with __syncthreads() when it stages anything
+      if (ncpl == 0) __syncthreads();
+   } else {
+      if (active) {
+         io = __ldg(t.orig + i);
+         ih = REDUCED ? __ldg(t.ham + i) : 0;
+         active = io >= 0;
+      }
+      prefetch_tile(t, S, tile);
+      stage_couplings(t, sm, smc, smd, smb);
+   }
+   if (active) {
+      if (STAGED) {
+         const int n = REDUCED ? __ldg(t.lsize + ih) : t.z;
+         const int nq = (n + 7) >> 3;
+         exchange_staged<REDUCED>(t, s3, i, ih, n, nq, w, smc, bs[0], bs[1], bs[2]);
+         site_field<REDUCED, false>(t, S, i, ih, own, smc, smd, smb, bs, bq);
+      } else {
+         own = S[i];
+         site_field<REDUCED>(t, S, i, ih, own, smc, smd, smb, bs, bq);
+      }
+      double h[3];
+      ext_field(t, i, k, h);
+      // beff = beff1 + beff2, beff2 = beff_q + external_field (hamiltonianactions.f90:240-243)
+      const double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
+      SpinVec old;
+      if (STAGE == 2) old = curk[i];
+      const SpinVec o = integrate_site<SOLVER, STAGE>(t, p, i, k, io, b, own, (STAGE == 1) ? own : old, b2eff);
+      if (STAGE == 1) predk[i] = o; else curk[i] = o;
+      if (EDGE) {
+         const int lo = __ldg(ep.hdst_lo + i), hi = __ldg(ep.hdst_hi + i);
+         if (lo >= 0) ep.peer_lo[(size_t)k * t.Npad + lo] = o;
+         if (hi >= 0) ep.peer_hi[(size_t)k * t.Npad + hi] = o;
+      }
+   }
+   if (EDGE) {
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+         const unsigned int total = gridDim.x * gridDim.y;
+         if (atomicAdd(ep.ctr, 1u) == total - 1) {
+            *ep.ctr = 0;
+            __threadfence_system();
+            if (ep.flag_lo) st_release_sys(ep.flag_lo, ep.epoch);
+            if (ep.flag_hi) st_release_sys(ep.flag_hi, ep.epoch);
+         }
       }
    }
 }
@@ -772,10 +898,10 @@ moment_final_kernel(int nblk, const double* __restrict__ part, double* __restric
 // ------------------------------------------------------------------------------------------------
 // Layout conversion between the host's Fortran arrays and the packed device order.
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_kernel(int N, int Npad, int M, const int* __restrict__ orig, const double* __restrict__ emom,
+__global__ void pack_kernel(int N, int Nown, int Npad, int M, const int* __restrict__ orig, const double* __restrict__ emom,
                             const double* __restrict__ mmom, SpinVec* __restrict__ cur) {
    const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
-   if (i >= Npad) return;
+   if (i >= Nown) return;
    const int o = orig[i];
    SpinVec v;
    if (o < 0) { v.x = 0; v.y = 0; v.z = 1.0; v.m = 0.0; }
@@ -797,6 +923,11 @@ __global__ void unpack_kernel(int N, int Npad, int M, const int* __restrict__ or
    if (emom) { emom[3 * q] = v.x; emom[3 * q + 1] = v.y; emom[3 * q + 2] = v.z; }
    if (emomM) { emomM[3 * q] = v.x * v.m; emomM[3 * q + 1] = v.y * v.m; emomM[3 * q + 2] = v.z * v.m; }
    if (mmom) mmom[q] = v.m;
+}
+
+__global__ void zip_meta_kernel(int Npad, const int* __restrict__ ham, const int* __restrict__ orig, int2* __restrict__ meta) {
+   const int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s < Npad) meta[s] = make_int2(ham[s], orig[s]);
 }
 
 // vectorised copies of a slot-major table: nl[z][Npad] -> nl4[zq][Npad], cp[z][Npad] -> cp4[zq][Npad]

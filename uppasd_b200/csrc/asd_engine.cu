@@ -52,6 +52,7 @@ struct DevBuf {
    T* p = nullptr;
    size_t n = 0;
    int alloc(size_t count) {
+      if (p && n == count) return 0;   // keep the allocation (peers of a slab hold IPC mappings of cur / pred)
       release();
       if (count == 0) return 0;
       cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
@@ -94,6 +95,8 @@ struct Layout {
    DevBuf<int4> d_nl4;
    DevBuf<int> d_ucount, d_ulist;   // staged tile path (asd_tiles.cuh)
    DevBuf<uint4> d_nl16;
+   DevBuf<int2> d_meta;
+   DevBuf<int> d_okey;              // sort key of the gather lists when it differs from orig (lattice builder)
    bool is_mc = false;
    DevBuf<double4> d_cp4;
    DevBuf<int> d_cnt[3];  // per-atom list lengths of device-built tables (exchange, DM, BQ)
@@ -103,8 +106,29 @@ struct Layout {
    size_t smem_bytes = 0;
 };
 
+// Slab decomposition of one supercell along z, one slab per engine / GPU.  The ring neighbours' cur,
+// pred and flag buffers are mapped into this process (CUDA IPC, or plain pointers inside one process); the EDGE
+// launches of the stage kernels store boundary spins straight into them.
+struct Slab {
+   int on = 0, G = 1, g = 0, H = 0;
+   DevBuf<int> hdst_lo, hdst_hi;
+   DevBuf<unsigned long long> flags;   // [0] published by the lower neighbour, [1] by the upper neighbour
+   DevBuf<unsigned int> ctr;
+   DevBuf<int> err;
+   SpinVec* peer_cur[2] = {nullptr, nullptr};    // [0] lower neighbour, [1] upper neighbour
+   SpinVec* peer_pred[2] = {nullptr, nullptr};
+   unsigned long long* peer_flags[2] = {nullptr, nullptr};
+   void* opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+   int n_opened = 0;
+   unsigned long long epoch = 0;       // exchanges completed (identical on every rank)
+   bool connected = false;
+   int tile_a = 0, tile_b = 0, ntile = 0;   // tiles [0,a) and [b,ntile) hold the boundary planes
+   long long timeout_ticks = 8000000000LL;  // ~4 s at 1.9 GHz
+};
+
 struct asd_engine {
    int device = 0;
+   Slab slab;
    cudaStream_t stream = nullptr;
    // constants
    double gamma = 1.760859644e11, k_bolt = 1.38064852e-23, mub = 9.274009994e-24, mry = 2.179872325e-21;
@@ -122,6 +146,7 @@ struct asd_engine {
    double delta_t = 1e-16, temprescale = 1.0;
    std::vector<double> landeg, lambda, temp;  // (N)
    unsigned long long seed = 20261017ull;
+   unsigned int ens_offset = 0;   // global index of local ensemble 0 (ensemble sharding)
    bool llg_uniform = true, llg_thermal = false;
    // moments (host copies, original order) used when (re)building layouts
    std::vector<double> h_emom, h_mmom, h_mmom0;
@@ -148,6 +173,8 @@ static void launch_cfg(int Npad, int M, dim3& grid, dim3& block) {
 // Layout construction from host tables
 // ------------------------------------------------------------------------------------------------
 static int host_orig(asd_engine* e, Layout& L);
+static int slab_commit(asd_engine* e);
+static int slab_push_state(asd_engine* e);
 
 // staged tile path: gather lists + 16-bit neighbour table (asd_tiles.cuh).  Leaves t.staged = 0 when a tile would
 // need more than TILE_UMAX unique slots (layout without locality) or when switched off (ASD_STAGED=0).
@@ -157,13 +184,15 @@ static int build_tiles(asd_engine* e, Layout& L) {
    const char* env = std::getenv("ASD_STAGED");
    if ((env && atoi(env) == 0) || L.is_mc || t.z <= 0) return 0;
    const long Npad = L.Npad;
-   const int ntile = (int)((Npad + TILE - 1) / TILE);
+   if (t.Nown <= 0) t.Nown = L.Npad;
+   const int ntile = (t.Nown + TILE - 1) / TILE;
+   const int* key = L.d_okey.p ? L.d_okey.p : t.orig;
    cudaStream_t st = e->stream;
    int r;
    if ((r = L.d_ucount.alloc(ntile))) return r;
-   const size_t smem = (size_t)(TILE_HASH + 8192) * sizeof(int);
+   const size_t smem = TILE_BUILD_SMEM;
    CU(cudaFuncSetAttribute(tile_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-   tile_gather_kernel<<<ntile, TILE, smem, st>>>((int)Npad, t.z, t.nl, 0, 0, L.d_ucount.p, nullptr, nullptr, t.zq8);
+   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 0, 0, L.d_ucount.p, nullptr, nullptr, t.zq8);
    e->launches++;
    CU(cudaGetLastError());
    std::vector<int> cnt(ntile);
@@ -174,10 +203,16 @@ static int build_tiles(asd_engine* e, Layout& L) {
    const int ucap = ((mx + 31) / 32) * 32;
    if ((r = L.d_ulist.alloc((size_t)ntile * ucap))) return r;
    if ((r = L.d_nl16.alloc((size_t)t.zq8 * Npad))) return r;
-   tile_gather_kernel<<<ntile, TILE, smem, st>>>((int)Npad, t.z, t.nl, 1, ucap, L.d_ucount.p, L.d_ulist.p, L.d_nl16.p, t.zq8);
+   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 1, ucap, L.d_ucount.p, L.d_ulist.p, L.d_nl16.p, t.zq8);
    e->launches++;
    CU(cudaGetLastError());
    CU(cudaStreamSynchronize(st));
+   if ((r = L.d_meta.alloc(Npad))) return r;
+   zip_meta_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>((int)Npad, t.ham, t.orig, L.d_meta.p);
+   e->launches++;
+   CU(cudaGetLastError());
+   CU(cudaStreamSynchronize(st));
+   t.meta = L.d_meta.p;
    t.staged = 1; t.ucap = ucap; t.ulist = L.d_ulist.p; t.ucount = L.d_ucount.p; t.nl16 = L.d_nl16.p;
    return 0;
 }
@@ -343,7 +378,8 @@ static int build_layout(asd_engine* e, Layout& L, bool colour_major) {
    if ((r = L.d_orig.upload(L.orig, st))) return r;
    Tables& t = L.t;
    memset(&t, 0, sizeof t);
-   t.N = N; t.Npad = L.Npad; t.M = M; t.NH = NH; t.reduced = L.reduced ? 1 : 0;
+   t.N = N; t.Npad = L.Npad; t.Nown = L.Npad; t.M = M; t.NH = NH; t.reduced = L.reduced ? 1 : 0;
+   t.ens_offset = e->ens_offset;
    t.ham = L.d_ham.p; t.orig = L.d_orig.p;
    // ---- pair tables ----
    auto do_table = [&](const HostTable& T, DevBuf<int>& d_list, DevBuf<double>& d_coup, DevBuf<int>& d_size, const char* name) -> int {
@@ -462,8 +498,9 @@ static int upload_state(asd_engine* e, Layout& L) {
    if ((r = e->pred.alloc((size_t)L.Npad * e->M))) return r;
    dim3 g, b;
    launch_cfg(L.Npad, e->M, g, b);
-   pack_kernel<<<g, b, 0, e->stream>>>(e->N, L.Npad, e->M, L.d_orig.p, d_e.p, d_m.p, e->cur.p);
-   pack_kernel<<<g, b, 0, e->stream>>>(e->N, L.Npad, e->M, L.d_orig.p, d_e.p, d_m.p, e->pred.p);
+   // only the owned slots: the halo slots of a slab belong to the neighbours' pushes
+   pack_kernel<<<g, b, 0, e->stream>>>(e->N, L.t.Nown, L.Npad, e->M, L.d_orig.p, d_e.p, d_m.p, e->cur.p);
+   pack_kernel<<<g, b, 0, e->stream>>>(e->N, L.t.Nown, L.Npad, e->M, L.d_orig.p, d_e.p, d_m.p, e->pred.p);
    e->launches += 2;
    CU(cudaGetLastError());
    if (e->mompar != 0) {
@@ -476,7 +513,7 @@ static int upload_state(asd_engine* e, Layout& L) {
    }
    CU(cudaStreamSynchronize(e->stream));
    (void)NM;
-   return 0;
+   return slab_push_state(e);
 }
 
 static int download_state(asd_engine* e, Layout& L, double* emom, double* emomM, double* mmom) {
@@ -536,22 +573,72 @@ static void allow_smem(K kernel, size_t bytes) {
    }
 }
 
-template <int SOLVER, int STAGE>
-static void launch_stage(asd_engine* e, Layout& L, const LlgParams& p) {
-   dim3 g, b;
-   launch_cfg(L.Npad, e->M, g, b);
+template <int SOLVER, int STAGE, bool EDGE>
+static void launch_stage_range(asd_engine* e, Layout& L, const LlgParams& p, const EdgeParams& ep, const TileRange& tr, int ntiles) {
+   if (ntiles <= 0) return;
+   const dim3 g(ntiles, e->M, 1), b(256, 1, 1);
    if (L.t.staged) {
       const size_t smem = L.smem_bytes + (size_t)3 * L.t.ucap * sizeof(double);
       if (L.reduced) {
-         allow_smem(llg_stage_kernel<SOLVER, STAGE, true, true>, smem);
-         llg_stage_kernel<SOLVER, STAGE, true, true><<<g, b, smem, e->stream>>>(L.t, p, e->cur.p, e->pred.p, e->b2eff.p);
+         allow_smem(llg_stage_kernel<SOLVER, STAGE, true, true, EDGE>, smem);
+         llg_stage_kernel<SOLVER, STAGE, true, true, EDGE><<<g, b, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
       } else {
-         allow_smem(llg_stage_kernel<SOLVER, STAGE, false, true>, smem);
-         llg_stage_kernel<SOLVER, STAGE, false, true><<<g, b, smem, e->stream>>>(L.t, p, e->cur.p, e->pred.p, e->b2eff.p);
+         allow_smem(llg_stage_kernel<SOLVER, STAGE, false, true, EDGE>, smem);
+         llg_stage_kernel<SOLVER, STAGE, false, true, EDGE><<<g, b, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
       }
-   } else if (L.reduced) llg_stage_kernel<SOLVER, STAGE, true, false><<<g, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p, e->pred.p, e->b2eff.p);
-   else llg_stage_kernel<SOLVER, STAGE, false, false><<<g, b, 0, e->stream>>>(L.t, p, e->cur.p, e->pred.p, e->b2eff.p);
+   } else if (L.reduced) llg_stage_kernel<SOLVER, STAGE, true, false, EDGE><<<g, b, L.smem_bytes, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
+   else llg_stage_kernel<SOLVER, STAGE, false, false, EDGE><<<g, b, 0, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
    e->launches++;
+}
+
+static EdgeParams edge_params(asd_engine* e, int stage, unsigned long long epoch) {
+   Slab& sb = e->slab;
+   EdgeParams ep;
+   memset(&ep, 0, sizeof ep);
+   ep.hdst_lo = sb.hdst_lo.p; ep.hdst_hi = sb.hdst_hi.p;
+   ep.peer_lo = (stage == 1) ? sb.peer_pred[0] : sb.peer_cur[0];
+   ep.peer_hi = (stage == 1) ? sb.peer_pred[1] : sb.peer_cur[1];
+   // this rank is the UPPER neighbour of its lower neighbour: it owns word [1] there, and word [0] above
+   ep.flag_lo = e->lat.has_lo ? sb.peer_flags[0] + 1 : nullptr;
+   ep.flag_hi = e->lat.has_hi ? sb.peer_flags[1] + 0 : nullptr;
+   ep.epoch = epoch;
+   ep.ctr = sb.ctr.p;
+   return ep;
+}
+
+// one stage over the whole engine: plain launch, or (slab) wait for the halos -> boundary tiles with the fused halo
+// push -> interior tiles, which overlap the NVLink stores of the boundary launch
+template <int SOLVER, int STAGE>
+static void launch_stage(asd_engine* e, Layout& L, const LlgParams& p) {
+   Slab& sb = e->slab;
+   const int ntile = (L.t.Nown + 255) / 256;
+   EdgeParams none;
+   memset(&none, 0, sizeof none);
+   if (!sb.on) {
+      launch_stage_range<SOLVER, STAGE, false>(e, L, p, none, TileRange{0, ntile, 0}, ntile);
+      return;
+   }
+   halo_wait_kernel<<<1, 1, 0, e->stream>>>(sb.flags.p, e->lat.has_lo, e->lat.has_hi, sb.epoch, sb.timeout_ticks, sb.err.p);
+   e->launches++;
+   const EdgeParams ep = edge_params(e, STAGE, sb.epoch + 1);
+   const int nedge = sb.tile_a + (ntile - sb.tile_b);
+   launch_stage_range<SOLVER, STAGE, true>(e, L, p, ep, TileRange{0, sb.tile_a, sb.tile_b}, nedge);
+   launch_stage_range<SOLVER, STAGE, false>(e, L, p, none, TileRange{sb.tile_a, sb.tile_b - sb.tile_a, 0}, sb.tile_b - sb.tile_a);
+   sb.epoch += 1;
+}
+
+// copies the boundary planes of `cur` into the neighbours' halos (after the state was set from outside)
+static int slab_push_state(asd_engine* e) {
+   Slab& sb = e->slab;
+   if (!sb.on) return 0;
+   if (!sb.connected) return fail(-11, "slab: asd_slab_connect_* must be called before the moments are set");
+   Layout& L = e->sd;
+   const EdgeParams ep = edge_params(e, 2, sb.epoch + 1);
+   halo_push_kernel<<<dim3((L.t.Nown + 255) / 256, e->M), 256, 0, e->stream>>>(L.t.Nown, e->M, (size_t)L.Npad, e->cur.p, ep);
+   e->launches++;
+   CU(cudaGetLastError());
+   sb.epoch += 1;
+   return 0;
 }
 
 static int sd_steps(asd_engine* e, long nsteps, long first_step, cudaEvent_t* ev /*optional per-stage events*/) {
@@ -562,6 +649,7 @@ static int sd_steps(asd_engine* e, long nsteps, long first_step, cudaEvent_t* ev
    if (e->SDEalgh == 5 && e->b2eff.n < (size_t)3 * L.Npad * e->M) { if ((r = e->b2eff.alloc((size_t)3 * L.Npad * e->M))) return r; }
    LlgParams p;
    if ((r = fill_llg(e, L, p, 0))) return r;
+   if (e->slab.on && !e->slab.connected) return fail(-11, "slab: not connected to the ring neighbours");
    for (long s = 0; s < nsteps; s++) {
       p.step = (unsigned long long)(first_step + s);
       if (e->SDEalgh == 1) { launch_stage<1, 1>(e, L, p); launch_stage<1, 2>(e, L, p); }
@@ -627,6 +715,32 @@ static int mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, d
    return 0;
 }
 
+// buffers a slab shares with its ring neighbours + the boundary / interior tile split
+static int slab_commit(asd_engine* e) {
+   Slab& sb = e->slab;
+   Layout& L = e->sd;
+   const LatticeDesc& d = e->lat;
+   int r;
+   if ((r = e->cur.alloc((size_t)L.Npad * e->M))) return r;
+   if ((r = e->pred.alloc((size_t)L.Npad * e->M))) return r;
+   if ((r = sb.flags.alloc(2))) return r;
+   if ((r = sb.ctr.alloc(1))) return r;
+   if ((r = sb.err.alloc(1))) return r;
+   CU(cudaMemset(e->cur.p, 0, (size_t)L.Npad * e->M * sizeof(SpinVec)));
+   CU(cudaMemset(e->pred.p, 0, (size_t)L.Npad * e->M * sizeof(SpinVec)));
+   CU(cudaMemset(sb.flags.p, 0, 2 * sizeof(unsigned long long)));
+   CU(cudaMemset(sb.ctr.p, 0, sizeof(unsigned int)));
+   CU(cudaMemset(sb.err.p, 0, sizeof(int)));
+   sb.epoch = 0;
+   sb.ntile = (d.Nown + 255) / 256;
+   const long layer = (long)d.NTX * d.NTY * d.NA * d.P;     // slots per brick layer
+   const long nl = (d.H + d.BZ - 1) / d.BZ;                 // brick layers that hold the H boundary planes
+   long a = (layer * nl + 255) / 256, b = (d.Nown - layer * nl) / 256;
+   if (b < a) { a = sb.ntile; b = sb.ntile; }               // thin slab: every tile is a boundary tile
+   sb.tile_a = (int)a; sb.tile_b = (int)b;
+   return 0;
+}
+
 // ================================================================================================
 // C ABI -- explicit API
 // ================================================================================================
@@ -659,6 +773,7 @@ void asd_destroy(asd_engine* e) {
    if (!e) return;
    cudaSetDevice(e->device);
    if (e->stream) { cudaStreamSynchronize(e->stream); }
+   for (int q = 0; q < e->slab.n_opened; q++) cudaIpcCloseMemHandle(e->slab.opened[q]);
    cudaStream_t s = e->stream;
    delete e;
    if (s) cudaStreamDestroy(s);
@@ -769,6 +884,11 @@ int asd_commit(asd_engine* e) {
       int r = finish_layout(e, e->sd);
       if (r) return r;
    }
+   if (e->slab.on) {
+      if (!e->lattice_built) return fail(-11, "slab decomposition needs the on-device lattice builder (asd_build_lattice_table)");
+      int r = slab_commit(e);
+      if (r) return r;
+   }
    e->sd_built = true; e->mc_built = false;
    e->committed = true;
    if (e->state_layout != 0) e->state_layout = 0;
@@ -877,6 +997,87 @@ int asd_time_mc_sweeps(asd_engine* e, char mode, long nsweeps, double temperatur
    if (total_ms) CU(cudaEventElapsedTime(total_ms, a, b));
    cudaEventDestroy(a); cudaEventDestroy(b);
    return r;
+}
+
+int asd_set_ensemble_offset(asd_engine* e, unsigned int first_ensemble) {
+   e->ens_offset = first_ensemble;
+   e->sd.t.ens_offset = first_ensemble; e->mc.t.ens_offset = first_ensemble;
+   return 0;
+}
+
+int asd_set_slab(asd_engine* e, int nslabs, int slab_index, int halo_planes) {
+   if (e->N == 0) return fail(-2, "asd_set_system must be called first");
+   if (e->lattice_built) return fail(-2, "asd_set_slab must precede asd_build_lattice_table");
+   if (nslabs < 1 || slab_index < 0 || slab_index >= nslabs || halo_planes < 1) return fail(-1, "bad slab arguments");
+   e->slab.on = 1; e->slab.G = nslabs; e->slab.g = slab_index; e->slab.H = halo_planes;
+   e->slab.connected = false;
+   return 0;
+}
+
+int asd_slab_export(asd_engine* e, void* handles) {
+   if (!e->slab.on || !e->committed) return fail(-11, "slab: asd_set_slab + asd_commit first");
+   CU(cudaSetDevice(e->device));
+   cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)handles;
+   CU(cudaIpcGetMemHandle(&h[0], e->cur.p));
+   CU(cudaIpcGetMemHandle(&h[1], e->pred.p));
+   CU(cudaIpcGetMemHandle(&h[2], e->slab.flags.p));
+   return 0;
+}
+
+int asd_slab_handle_bytes(void) { return (int)(3 * sizeof(cudaIpcMemHandle_t)); }
+
+int asd_slab_connect_ipc(asd_engine* e, const void* lower, const void* upper) {
+   Slab& sb = e->slab;
+   if (!sb.on || !e->committed) return fail(-11, "slab: asd_set_slab + asd_commit first");
+   CU(cudaSetDevice(e->device));
+   const cudaIpcMemHandle_t* hs[2] = {(const cudaIpcMemHandle_t*)lower, (const cudaIpcMemHandle_t*)upper};
+   const bool same = memcmp(lower, upper, 3 * sizeof(cudaIpcMemHandle_t)) == 0;   // two slabs: one neighbour on both sides
+   for (int side = 0; side < 2; side++) {
+      if (side == 1 && same) { sb.peer_cur[1] = sb.peer_cur[0]; sb.peer_pred[1] = sb.peer_pred[0]; sb.peer_flags[1] = sb.peer_flags[0]; break; }
+      void* p[3];
+      for (int q = 0; q < 3; q++) {
+         CU(cudaIpcOpenMemHandle(&p[q], hs[side][q], cudaIpcMemLazyEnablePeerAccess));
+         sb.opened[sb.n_opened++] = p[q];
+      }
+      sb.peer_cur[side] = (SpinVec*)p[0]; sb.peer_pred[side] = (SpinVec*)p[1]; sb.peer_flags[side] = (unsigned long long*)p[2];
+   }
+   sb.connected = true;
+   return 0;
+}
+
+int asd_slab_connect_local(asd_engine* e, asd_engine* lower, asd_engine* upper) {
+   Slab& sb = e->slab;
+   if (!sb.on || !e->committed) return fail(-11, "slab: asd_set_slab + asd_commit first");
+   asd_engine* nb[2] = {lower, upper};
+   for (int side = 0; side < 2; side++) {
+      if (!nb[side]->slab.on || !nb[side]->committed || nb[side]->sd.Npad != e->sd.Npad) return fail(-11, "slab: neighbour engine is not a committed slab of the same shape");
+      if (nb[side]->device != e->device) {
+         int can = 0;
+         CU(cudaDeviceCanAccessPeer(&can, e->device, nb[side]->device));
+         if (!can) return fail(-11, "slab: no peer access between devices %d and %d", e->device, nb[side]->device);
+         CU(cudaSetDevice(e->device));
+         cudaError_t pe = cudaDeviceEnablePeerAccess(nb[side]->device, 0);
+         if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CU(pe);
+         cudaGetLastError();
+      }
+      sb.peer_cur[side] = nb[side]->cur.p; sb.peer_pred[side] = nb[side]->pred.p; sb.peer_flags[side] = nb[side]->slab.flags.p;
+   }
+   sb.connected = true;
+   return 0;
+}
+
+int asd_slab_status(asd_engine* e, unsigned long long* epoch, int* error_flag) {
+   CU(cudaSetDevice(e->device));
+   if (epoch) *epoch = e->slab.epoch;
+   if (error_flag) {
+      *error_flag = 0;
+      if (e->slab.on && e->slab.err.p) {
+         CU(cudaStreamSynchronize(e->stream));
+         CU(cudaMemcpy(error_flag, e->slab.err.p, sizeof(int), cudaMemcpyDeviceToHost));
+         if (*error_flag) return fail(-12, "slab: timed out waiting for the halo of the %s neighbour", *error_flag == 1 ? "lower" : "upper");
+      }
+   }
+   return 0;
 }
 
 long asd_launch_count(asd_engine* e) { return e->launches; }

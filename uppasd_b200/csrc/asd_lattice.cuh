@@ -25,7 +25,18 @@ struct LatticeDesc {
    // staged in shared memory (asd_tiles.cuh) instead of being gathered from L2 fifty times.
    int BX, BY, BZ, P;
    int NTX, NTY, NTZ;   // bricks per direction (the last one may be partly empty -> padding slots)
+   // Slab decomposition along z, one slab per GPU: this engine owns the global planes
+   // [z0, z0 + N3) of N3g; N1, N2, N3, Ncell, N describe the LOCAL slab.  Slots [0, Nown) are the owned bricks;
+   // the H halo planes of the lower ring neighbour and then of the upper one follow.  Halo slots hold copies of
+   // the neighbours' boundary spins: gathered from, never computed (orig = -1).
+   int slab, z0, N3g, H, Nown;
+   int has_lo, has_hi;  // a neighbour exists below / above (always, when z is periodic)
 };
+
+// halo slot of basis atom i0 in cell (ix,iy) of halo plane hz (0..H-1) on side 0 (below) / 1 (above)
+__device__ __host__ __forceinline__ int halo_slot(const LatticeDesc& d, int side, int hz, int i0, int ix, int iy) {
+   return d.Nown + ((((side * d.H + hz) * d.NA + i0) * d.N2 + iy) * d.N1 + ix);
+}
 
 // slot of basis atom i0 in cell (ix,iy,iz)
 __device__ __host__ __forceinline__ int lattice_slot(const LatticeDesc& d, int i0, int ix, int iy, int iz) {
@@ -46,17 +57,40 @@ __device__ __host__ __forceinline__ bool lattice_unslot(const LatticeDesc& d, in
    return ix < d.N1 && iy < d.N2 && iz < d.N3;
 }
 
-// orig[] / ham[] of every device slot (original atom index = i0 + NA*(ix + N1*(iy + N2*iz)), geometry.f90:337-488)
-__global__ void lattice_index_kernel(const LatticeDesc d, int* __restrict__ orig, int* __restrict__ ham) {
+// orig[] / ham[] of every device slot (original atom index = i0 + NA*(ix + N1*(iy + N2*iz)), geometry.f90:337-488),
+// the sort key of the tile gather lists (okey: atom index extended over the halo planes, so that x-runs of a
+// slab's halo stay contiguous in the lists) and, for a slab, the halo slots of the neighbours that mirror an atom.
+__global__ void lattice_index_kernel(const LatticeDesc d, int* __restrict__ orig, int* __restrict__ ham, int* __restrict__ okey,
+                                     int* __restrict__ hdst_lo, int* __restrict__ hdst_hi) {
    const int s = blockIdx.x * blockDim.x + threadIdx.x;
    if (s >= d.Npad) return;
-   int i0, ix, iy, iz, o = -1, h = -1;
-   if (lattice_unslot(d, s, i0, ix, iy, iz)) {
-      o = i0 + d.NA * (ix + d.N1 * (iy + d.N2 * iz));
-      h = d.reduced ? i0 : 0;
+   int i0, ix, iy, iz, o = -1, h = -1, key = -1;
+   if (s < d.Nown) {
+      if (lattice_unslot(d, s, i0, ix, iy, iz)) {
+         o = i0 + d.NA * (ix + d.N1 * (iy + d.N2 * iz));
+         h = d.reduced ? i0 : 0;
+         key = i0 + d.NA * (ix + d.N1 * (iy + d.N2 * (iz + d.H)));
+         if (hdst_lo) {
+            // planes [0,H) are the upper halo (side 1) of the lower neighbour, planes [N3-H,N3) the lower halo of the upper one
+            hdst_lo[s] = (d.slab && d.has_lo && iz < d.H) ? halo_slot(d, 1, iz, i0, ix, iy) : -1;
+            hdst_hi[s] = (d.slab && d.has_hi && iz >= d.N3 - d.H) ? halo_slot(d, 0, iz - (d.N3 - d.H), i0, ix, iy) : -1;
+         }
+      } else if (hdst_lo) { hdst_lo[s] = -1; hdst_hi[s] = -1; }
+   } else {
+      int q = s - d.Nown;
+      if (q < 2 * d.H * d.NA * d.N2 * d.N1) {
+         ix = q % d.N1; q /= d.N1;
+         iy = q % d.N2; q /= d.N2;
+         i0 = q % d.NA; q /= d.NA;
+         const int hz = q % d.H, side = q / d.H;
+         const int lz = side == 0 ? hz - d.H : d.N3 + hz;   // local plane index, outside [0, N3)
+         h = d.reduced ? i0 : 0;
+         key = i0 + d.NA * (ix + d.N1 * (iy + d.N2 * (lz + d.H)));
+      }
    }
    orig[s] = o;
    ham[s] = h;
+   okey[s] = key;
 }
 
 // One thread per atom.  nl[z][Npad] (device slots, self beyond the list), count[Npad] accepted entries,
@@ -68,8 +102,8 @@ lattice_table_kernel(const LatticeDesc d, int maxslot, int z, int ncomp, int ded
                      int* __restrict__ nl, int* __restrict__ count, double* __restrict__ cp) {
    const int s = blockIdx.x * blockDim.x + threadIdx.x;
    if (s >= d.Npad) return;
-   int i0, ix, iy, iz;
-   const bool real = lattice_unslot(d, s, i0, ix, iy, iz);
+   int i0 = 0, ix = 0, iy = 0, iz = 0;
+   const bool real = s < d.Nown && lattice_unslot(d, s, i0, ix, iy, iz);
    int n = 0;
    if (real) {
       const int ns = nslot[i0];
@@ -79,9 +113,21 @@ lattice_table_kernel(const LatticeDesc d, int maxslot, int z, int ncomp, int ded
          int jx = sh[0] + ix, jy = sh[1] + iy, jz = sh[2] + iz;
          if (d.periodic[0]) jx = (jx + 1000 * d.N1) % d.N1;
          if (d.periodic[1]) jy = (jy + 1000 * d.N2) % d.N2;
-         if (d.periodic[2]) jz = (jz + 1000 * d.N3) % d.N3;
-         if (jx < 0 || jx >= d.N1 || jy < 0 || jy >= d.N2 || jz < 0 || jz >= d.N3) continue;
-         const int jslot = lattice_slot(d, j0, jx, jy, jz);
+         if (jx < 0 || jx >= d.N1 || jy < 0 || jy >= d.N2) continue;
+         int jslot;
+         if (!d.slab) {
+            if (d.periodic[2]) jz = (jz + 1000 * d.N3) % d.N3;
+            if (jz < 0 || jz >= d.N3) continue;
+            jslot = lattice_slot(d, j0, jx, jy, jz);
+         } else {
+            // slab: jz is the UNWRAPPED local plane; the neighbour exists iff its global plane does
+            const int gz = d.z0 + jz;
+            if (!d.periodic[2] && (gz < 0 || gz >= d.N3g)) continue;
+            if (jz >= 0 && jz < d.N3) jslot = lattice_slot(d, j0, jx, jy, jz);
+            else if (jz < 0 && jz >= -d.H) jslot = halo_slot(d, 0, jz + d.H, j0, jx, jy);
+            else if (jz >= d.N3 && jz < d.N3 + d.H) jslot = halo_slot(d, 1, jz - d.N3, j0, jx, jy);
+            else continue;   // cannot happen: the host sizes H from the stencil
+         }
          if (dedup) {
             bool exis = false;
             for (int l = 0; l < n; l++) if (nl[(size_t)l * d.Npad + s] == jslot) exis = true;
@@ -123,16 +169,16 @@ __global__ void table_export_kernel(int N, int Npad, int z, const int* __restric
 }
 
 // synthetic start for large runs: e_i = normalize(1, a sin(2 pi h), a cos(2 pi h)), h = frac(i*0.6180339887)
-__global__ void tilted_moments_kernel(int Npad, int M, int NA, double amp, const int* __restrict__ orig,
+__global__ void tilted_moments_kernel(int Nown, int Npad, int M, int NA, double amp, unsigned int atom_offset, const int* __restrict__ orig,
                                       const double* __restrict__ mmom_basis, SpinVec* __restrict__ cur,
                                       SpinVec* __restrict__ pred) {
    const int s = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
-   if (s >= Npad) return;
+   if (s >= Nown) return;   // halo slots of a slab are filled by the neighbours
    const int o = orig[s];
    SpinVec v;
    if (o < 0) { v.x = 0; v.y = 0; v.z = 1; v.m = 0; }
    else {
-      const double t = (double)(o + 1) * 0.6180339887;
+      const double t = (double)((unsigned int)o + atom_offset + 1u) * 0.6180339887;
       const double h = t - floor(t);
       double sn, cs;
       sincospi(2.0 * h, &sn, &cs);

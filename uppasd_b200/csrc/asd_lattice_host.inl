@@ -49,23 +49,31 @@ int asd_build_lattice_table(asd_engine* e, int kind, int NA, int N1, int N2, int
                             const int* nslot, const int* cell_atom, const int* cell_shift, const double* coupling) {
    if (e->N == 0) return fail(-2, "asd_set_system must be called first");
    CU(cudaSetDevice(e->device));
-   if ((long)NA * N1 * N2 * N3 != e->N) return fail(-1, "NA*N1*N2*N3 = %ld does not match Natom = %d", (long)NA * N1 * N2 * N3, e->N);
    if (!(e->NH == NA || e->NH == e->N)) return fail(-1, "nHam must be NA (do_reduced Y) or Natom");
    if (kind < 0 || kind > 2) return fail(-1, "kind must be 0 (exchange), 1 (DM) or 2 (BQ)");
    const int ncomp = (kind == 1) ? 3 : 1;
    Layout& L = e->sd;
    LatticeDesc& d = e->lat;
+   Slab& sb = e->slab;
+   // slab decomposition: N3 is the GLOBAL plane count, this engine owns N3 / nslabs planes starting at z0
+   const int N3l = sb.on ? N3 / sb.G : N3;
+   if (sb.on && (N3 % sb.G != 0 || N3l < sb.H)) return fail(-1, "slab: N3 = %d must be a multiple of the %d slabs and each slab at least %d planes thick", N3, sb.G, sb.H);
+   if ((long)NA * N1 * N2 * N3l != e->N) return fail(-1, "NA*N1*N2*N3%s = %ld does not match Natom = %d", sb.on ? "/nslabs" : "", (long)NA * N1 * N2 * N3l, e->N);
    if (!e->lattice_built) {
-      d.NA = NA; d.N1 = N1; d.N2 = N2; d.N3 = N3;
+      d.NA = NA; d.N1 = N1; d.N2 = N2; d.N3 = N3l;
       for (int a = 0; a < 3; a++) d.periodic[a] = (bc3[a] == 'P' || bc3[a] == 'p') ? 1 : 0;
       d.reduced = (e->NH < e->N) ? 1 : 0;
-      d.Ncell = N1 * N2 * N3;
+      d.Ncell = N1 * N2 * N3l;
       d.N = e->N;
+      d.slab = sb.on; d.N3g = N3; d.z0 = sb.on ? sb.g * N3l : 0; d.H = sb.on ? sb.H : 0;
+      d.has_lo = sb.on && (d.periodic[2] || sb.g > 0);
+      d.has_hi = sb.on && (d.periodic[2] || sb.g < sb.G - 1);
       choose_brick(d);
       {
-         const long np = (long)d.NTX * d.NTY * d.NTZ * d.NA * d.P;
+         const long nown = (long)d.NTX * d.NTY * d.NTZ * d.NA * d.P;
+         const long np = ((nown + 2L * d.H * NA * N1 * N2 + 31) / 32) * 32;
          if (np > 2000000000L) return fail(-3, "too many atoms for 32-bit device indices");
-         d.Npad = (int)np;
+         d.Nown = (int)nown; d.Npad = (int)np;
       }
       if (d.reduced)
          for (int i = 0; i < e->N; i++) if (e->aHam[i] != i % NA + 1) return fail(-1, "aHam is not the basis-atom number; cannot use the lattice builder");
@@ -74,20 +82,28 @@ int asd_build_lattice_table(asd_engine* e, int kind, int NA, int N1, int N2, int
       int r;
       if ((r = L.d_orig.alloc(d.Npad))) return r;
       if ((r = L.d_ham.alloc(d.Npad))) return r;
-      lattice_index_kernel<<<(d.Npad + 255) / 256, 256, 0, e->stream>>>(d, L.d_orig.p, L.d_ham.p);
+      if ((r = L.d_okey.alloc(d.Npad))) return r;
+      if (sb.on) { if ((r = sb.hdst_lo.alloc(d.Nown))) return r; if ((r = sb.hdst_hi.alloc(d.Nown))) return r; }
+      lattice_index_kernel<<<(d.Npad + 255) / 256, 256, 0, e->stream>>>(d, L.d_orig.p, L.d_ham.p, L.d_okey.p, sb.hdst_lo.p, sb.hdst_hi.p);
       e->launches++;
       memset(&L.t, 0, sizeof L.t);
-      L.t.N = e->N; L.t.Npad = d.Npad; L.t.M = e->M; L.t.NH = e->NH; L.t.reduced = d.reduced;
+      L.t.N = e->N; L.t.Npad = d.Npad; L.t.Nown = d.Nown; L.t.M = e->M; L.t.NH = e->NH; L.t.reduced = d.reduced;
+      L.t.atom_offset = (unsigned int)((long)NA * N1 * N2 * d.z0);
       L.t.ham = L.d_ham.p; L.t.orig = L.d_orig.p;
       L.t.ext_uniform = 1;
       e->lattice_built = true;
       e->ex = HostTable(); e->dm = HostTable(); e->bq = HostTable();
-   } else if (d.NA != NA || d.N1 != N1 || d.N2 != N2 || d.N3 != N3) return fail(-1, "lattice differs from the first asd_build_lattice_table call");
+   } else if (d.NA != NA || d.N1 != N1 || d.N2 != N2 || d.N3 != N3l) return fail(-1, "lattice differs from the first asd_build_lattice_table call");
+   if (sb.on)
+      for (int i0 = 0; i0 < NA; i0++)
+         for (int q = 0; q < nslot[i0] && q < maxslot; q++)
+            if (std::abs(cell_shift[3 * (i0 * maxslot + q) + 2]) > sb.H)
+               return fail(-1, "slab: the stencil reaches %d planes along z but the halo holds %d", std::abs(cell_shift[3 * (i0 * maxslot + q) + 2]), sb.H);
    int z = 1;
    for (int i0 = 0; i0 < NA; i0++) { if (nslot[i0] < 0 || nslot[i0] > maxslot) return fail(-1, "nslot out of range"); z = std::max(z, nslot[i0]); }
    // can two stencil entries of one basis atom land on the same atom? (small periodic cells) -> need de-duplication
    int dedup = 0;
-   const int Nd[3] = {N1, N2, N3};
+   const int Nd[3] = {N1, N2, N3};   // GLOBAL extents: the table is the one of the whole supercell
    for (int i0 = 0; i0 < NA && !dedup; i0++)
       for (int a = 0; a < nslot[i0] && !dedup; a++)
          for (int b = a + 1; b < nslot[i0]; b++) {
@@ -99,6 +115,7 @@ int asd_build_lattice_table(asd_engine* e, int kind, int NA, int N1, int N2, int
             }
             if (same) { dedup = 1; break; }
          }
+   if (dedup && sb.on) return fail(-1, "slab: supercell too small along some direction (a neighbour appears twice through the periodic wrap)");
    DevBuf<int> d_nslot, d_catom, d_cshift;
    DevBuf<double> d_coupl;
    int r;
@@ -143,7 +160,7 @@ int asd_build_lattice_table(asd_engine* e, int kind, int NA, int N1, int N2, int
       if ((r = d_size.upload(lsize, e->stream))) return r;
       DevBuf<int> bad;
       if ((r = bad.upload(std::vector<int>(1, 0), e->stream))) return r;
-      lattice_check_kernel<<<(d.Npad + 255) / 256, 256, 0, e->stream>>>(d.Npad, L.d_ham.p, d_cnt.p, d_size.p, bad.p);
+      lattice_check_kernel<<<(d.Nown + 255) / 256, 256, 0, e->stream>>>(d.Nown, L.d_ham.p, d_cnt.p, d_size.p, bad.p);
       e->launches++;
       int nbad = 0;
       CU(cudaMemcpyAsync(&nbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
@@ -240,11 +257,12 @@ int asd_init_moments_tilted(asd_engine* e, double amplitude, int NA, const doubl
    if ((r = mb.upload(std::vector<double>(mmom_basis, mmom_basis + NA), e->stream))) return r;
    dim3 g, b;
    launch_cfg(L.Npad, e->M, g, b);
-   tilted_moments_kernel<<<g, b, 0, e->stream>>>(L.Npad, e->M, NA, amplitude, L.d_orig.p, mb.p, e->cur.p, e->pred.p);
+   tilted_moments_kernel<<<g, b, 0, e->stream>>>(L.t.Nown, L.Npad, e->M, NA, amplitude, L.t.atom_offset, L.d_orig.p, mb.p, e->cur.p, e->pred.p);
    e->launches++;
    CU(cudaGetLastError());
    CU(cudaStreamSynchronize(e->stream));
    e->state_layout = 1;
+   if ((r = slab_push_state(e))) return r;
    e->h_emom.clear(); e->h_mmom.clear();
    if (e->mompar != 0) return fail(-1, "mompar != 0 needs asd_set_moments (mmom0)");
    return 0;

@@ -1,5 +1,5 @@
 // Setup kernel of the staged tile path: turns the slot-major neighbour table nl[z][Npad] into
-//   * ulist[tile][ucap] : the sorted unique slots that the 256 atoms of a tile gather from (plus their own slots),
+//   * ulist[tile][ucap] : the unique slots, ordered by (ham row, original atom index), that the 256 atoms of a tile gather from (plus their own slots),
 //   * nl16[zq8][Npad]   : the same neighbour table as 16-bit positions in the tile's ulist, 8 per 16-byte word.
 // The per-step kernels then stage emomM of ulist in shared memory once per CTA and never gather from global
 // memory (asd_device.cuh: llg_stage_kernel<.,.,.,true>).  What the table means is unchanged: entry j of atom i is
@@ -13,15 +13,29 @@
 namespace asd {
 
 constexpr int TILE = 256;          // slots per tile = threads per CTA of the stage kernels
-constexpr int TILE_HASH = 16384;   // open-addressing table (ints) used to find the unique slots
-constexpr int TILE_UMAX = 6144;    // beyond this many unique slots per tile the staged path is not used
+constexpr int TILE_HASH = 8192;    // open-addressing table (ints) used to find the unique slots
+constexpr int TILE_UMAX = 4096;    // beyond this many unique slots per tile the staged path is not used
+constexpr size_t TILE_BUILD_SMEM = (size_t)TILE_HASH * 4 + (size_t)TILE_UMAX * (8 + 4);
+
+// `orig` here is the SORT KEY array (Layout::okey): the original atom index for ordinary layouts, the extended
+// local index (halo planes included) for a slab.
+// Order of a tile's gather list: by (Hamiltonian row, original atom index), i.e. sublattice-major and then the
+// reference's own atom order (x fastest).  For a lattice this makes the neighbours that the 32 lanes of a warp
+// (one x-run of cells) read for a given shell a CONTIGUOUS run of the list -- including the part that lies in the
+// next brick -- so the shared-memory reads of the stage kernels are bank-conflict free.
+__device__ __forceinline__ unsigned long long tile_key(const int* __restrict__ ham, const int* __restrict__ orig, int slot) {
+   const int o = orig[slot];
+   if (o < 0) return (0x7fffffull << 40) | (unsigned long long)(unsigned)slot;   // padding slots last
+   return ((unsigned long long)(unsigned)ham[slot] << 40) | (unsigned long long)(unsigned)o;
+}
 
 __global__ void __launch_bounds__(TILE)
-tile_gather_kernel(int Npad, int z, const int* __restrict__ nl, int pass, int ucap, int* __restrict__ ucount,
-                   int* __restrict__ ulist, uint4* __restrict__ nl16, int zq8) {
-   extern __shared__ int tsm[];
-   int* tab = tsm;                 // [TILE_HASH]
-   int* lst = tsm + TILE_HASH;     // [8192] (pass 1)
+tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const int* __restrict__ ham, const int* __restrict__ orig,
+                   int pass, int ucap, int* __restrict__ ucount, int* __restrict__ ulist, uint4* __restrict__ nl16, int zq8) {
+   extern __shared__ unsigned long long tsm64[];
+   unsigned long long* keys = tsm64;                       // [TILE_UMAX] (pass 1)
+   int* lst = (int*)(tsm64 + TILE_UMAX);                   // [TILE_UMAX] slot of each key (pass 1)
+   int* tab = lst + TILE_UMAX;                             // [TILE_HASH]
    __shared__ int nuniq, over, nfill;
    const int tile = blockIdx.x;
    const int s = tile * TILE + threadIdx.x;
@@ -29,7 +43,7 @@ tile_gather_kernel(int Npad, int z, const int* __restrict__ nl, int pass, int uc
    if (threadIdx.x == 0) { nuniq = 0; over = 0; nfill = 0; }
    __syncthreads();
    auto insert = [&](int key) {
-      unsigned hsh = ((unsigned)key * 2654435761u) >> 18;   // 14 bits
+      unsigned hsh = ((unsigned)key * 2654435761u) >> 19;   // 13 bits
       while (true) {
          if (*(volatile int*)&over) return;
          const int old = atomicCAS(&tab[hsh], -1, key);
@@ -38,7 +52,7 @@ tile_gather_kernel(int Npad, int z, const int* __restrict__ nl, int pass, int uc
          hsh = (hsh + 1) & (TILE_HASH - 1);
       }
    };
-   if (s < Npad) {
+   if (s < Nown) {
       insert(s);
       for (int j = 0; j < z; j++) insert(nl[(size_t)j * Npad + s]);
    }
@@ -48,36 +62,40 @@ tile_gather_kernel(int Npad, int z, const int* __restrict__ nl, int pass, int uc
       return;
    }
    if (over) { if (threadIdx.x == 0) ucount[tile] = INT_MAX; return; }
-   // compact, pad to a power of two, bitonic sort (ascending: a staged tile is read in address order)
+   // compact, pad to a power of two, bitonic sort of (key, slot) pairs by key
    const int cnt = nuniq;
    int np2 = 32;
    while (np2 < cnt) np2 <<= 1;
    for (int q = threadIdx.x; q < TILE_HASH; q += TILE) {
       const int v = tab[q];
-      if (v >= 0) lst[atomicAdd(&nfill, 1)] = v;
+      if (v >= 0) { const int at = atomicAdd(&nfill, 1); lst[at] = v; keys[at] = tile_key(ham, orig, v); }
    }
-   for (int q = cnt + threadIdx.x; q < np2; q += TILE) lst[q] = INT_MAX;
+   for (int q = cnt + threadIdx.x; q < np2; q += TILE) { lst[q] = INT_MAX; keys[q] = ~0ull; }
    __syncthreads();
    for (int kk = 2; kk <= np2; kk <<= 1)
       for (int jj = kk >> 1; jj > 0; jj >>= 1) {
          for (int idx = threadIdx.x; idx < np2; idx += TILE) {
             const int ixj = idx ^ jj;
             if (ixj > idx) {
-               const int a = lst[idx], b = lst[ixj];
+               const unsigned long long a = keys[idx], b = keys[ixj];
                const bool asc = (idx & kk) == 0;
-               if ((a > b) == asc) { lst[idx] = b; lst[ixj] = a; }
+               if ((a > b) == asc) {
+                  keys[idx] = b; keys[ixj] = a;
+                  const int t0 = lst[idx]; lst[idx] = lst[ixj]; lst[ixj] = t0;
+               }
             }
          }
          __syncthreads();
       }
    for (int q = threadIdx.x; q < ucap; q += TILE) ulist[(size_t)tile * ucap + q] = (q < cnt) ? lst[q] : lst[0];
    if (threadIdx.x == 0) ucount[tile] = cnt;
-   if (s >= Npad) return;
-   auto find = [&](int key) -> unsigned {
+   if (s >= Nown) return;
+   auto find = [&](int slot) -> unsigned {
+      const unsigned long long key = tile_key(ham, orig, slot);
       int lo = 0, hi = cnt - 1;
       while (lo < hi) {
          const int mid = (lo + hi) >> 1;
-         if (lst[mid] < key) lo = mid + 1; else hi = mid;
+         if (keys[mid] < key) lo = mid + 1; else hi = mid;
       }
       return (unsigned)lo;
    };

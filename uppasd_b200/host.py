@@ -175,6 +175,30 @@ class Engine:
         self._chk(self.lib.asd_init_moments_tilted(self.h, amplitude, len(mb), _p(mb)))
 
 
+    # ---- multi-GPU -------------------------------------------------------------------------------------
+    def set_ensemble_offset(self, first_ensemble):
+        self._chk(self.lib.asd_set_ensemble_offset(self.h, first_ensemble))
+
+    def set_slab(self, nslabs, slab_index, halo_planes):
+        self._chk(self.lib.asd_set_slab(self.h, nslabs, slab_index, halo_planes))
+
+    def slab_export(self):
+        buf = C.create_string_buffer(self.lib.asd_slab_handle_bytes())
+        self._chk(self.lib.asd_slab_export(self.h, buf))
+        return buf.raw
+
+    def slab_connect_ipc(self, lower, upper):
+        self._chk(self.lib.asd_slab_connect_ipc(self.h, C.c_char_p(lower), C.c_char_p(upper)))
+
+    def slab_connect_local(self, lower, upper):
+        self._chk(self.lib.asd_slab_connect_local(self.h, lower.h, upper.h))
+
+    def slab_status(self):
+        ep, err = C.c_ulonglong(0), C.c_int(0)
+        self._chk(self.lib.asd_slab_status(self.h, C.byref(ep), C.byref(err)))
+        return ep.value, err.value
+
+
 def engine_from_system(S, consts, sdealgh=1, delta_t=1e-16, damping=0.05, temp=0.0, mompar=0, seed=20261017,
                        device=-1):
     """Feeds a system dict holding reference-shaped tables (nlist, ncoup, ... as the Fortran host has them) to a new Engine."""
