@@ -42,46 +42,94 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons of one GPU while the timed region runs (NVML, every ~5 ms; nvidia-smi as
+    a fallback)"""
+
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.sm, self.mx, self.reasons, self.stop_flag = index, [], [], set(), False
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[index]) if vis and vis.split(',')[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
 
     def run(self):
+        if self.nv is not None:
+            nv = self.nv
+            bits = {'hw_slowdown': nv.nvmlClocksThrottleReasonHwSlowdown,
+                    'hw_thermal_slowdown': nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    'sw_thermal_slowdown': nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    'sw_power_cap': nv.nvmlClocksThrottleReasonSwPowerCap}
+            try:
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            except Exception:
+                pass
+            while not self.stop_flag:
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for k, b in bits.items():
+                        if r & b:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+                time.sleep(0.005)
+            return
         q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         while not self.stop_flag:
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
                                       '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(',')])
+                r = [x.strip() for x in out.strip().split(',')]
+                if len(r) >= 6:
+                    self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+                    for i in range(4):
+                        if r[2 + i].lower().startswith('active'):
+                            self.reasons.add(names[i])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith('active')})
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+        return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': max(self.mx) if self.mx else None,
+                'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': 'nvml' if self.nv is not None else 'nvidia-smi'}
 
 
-def bcc_engine(ncell, solver, temp, damping, mensemble, ens_offset, device):
-    """bcc Fe supercell built entirely on the device (tables + tilted start), through the C ABI."""
+def bcc_engine(ncell, solver, temp, damping, mensemble, ens_offset, device, slab=None):
+    """bcc Fe supercell built entirely on the device (tables + tilted start), through the C ABI.
+    slab = (world, rank, dist): this engine holds one z-slab of the supercell and is connected to its ring neighbours."""
     from uppasd_b200 import host, lattice
+    from uppasd_b200 import slab as slabmod
     nn = np.array([4])
     red = BCC['shells'][None]                       # (NT=1, 4, 3)
     ns, ca, cs, sh = lattice.stencil(BCC['cell'], BCC['bas'], BCC['atype'], nn, red, 1, np.ones((1, 4), dtype=int))
     cp = lattice.couplings(ns, ca, sh, BCC['atype'], BCC['J'][None, None, :], BCC['mom'], CONST['mry'], CONST['mub'])
     e = host.Engine(device)
     e.set_constants(CONST['gama'], CONST['k_bolt'], CONST['mub'], CONST['mry'])
-    n = 2 * ncell[0] * ncell[1] * ncell[2]
+    nz = ncell[2]
+    if slab is not None:
+        world, rank, dist = slab
+        halo = slabmod.halo_depth(cs, ns)
+        _, nz = slabmod.slab_planes(ncell[2], world, rank, halo)
+    n = 2 * ncell[0] * ncell[1] * nz
     aham = (np.arange(n, dtype=np.int32) % 2) + 1
     e.set_system(n, mensemble, 2, aham)
+    if slab is not None:
+        e.set_slab(world, rank, halo)
     e.build_lattice_table(0, 2, ncell, ('P', 'P', 'P'), ns, ca, cs, cp)
-    e.set_llg(solver, 1e-16, landeg=1.0, lambda1=damping, temp=temp, seed=20261017 + 7919 * ens_offset)
+    e.set_llg(solver, 1e-16, landeg=1.0, lambda1=damping, temp=temp, seed=20261017)
+    e.set_ensemble_offset(ens_offset)
     e.commit()
+    if slab is not None:
+        slabmod.connect_ring(e, world, rank, dist)
     e.init_moments_tilted(0.1, BCC['mom'])
     return e, n
 
@@ -123,16 +171,30 @@ def cpu_leg(ncell, solver, temp, damping, steps, warmup):
     return n * steps / dt, dt / steps * 1e3, n
 
 
+def traffic_from_profiles(kernel_key):
+    """dram bytes per launch of the dominant kernel from the committed ncu summary (profiles/traffic.json), or None"""
+    p = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel_key)
+        except Exception:
+            return None
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=1000)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--ncell', type=int, nargs=3, default=[128, 128, 128])
     ap.add_argument('--solver', type=int, default=1, choices=[1, 5])
     ap.add_argument('--temp', type=float, default=300.0)
     ap.add_argument('--damping', type=float, default=0.5)
+    ap.add_argument('--decomp', default='ensemble', choices=['ensemble', 'slab'],
+                    help='N > 1: one ensemble of the supercell per GPU (weak scaling, no communication) or one z-slab '
+                         'of a single supercell per GPU with the fused NVLink halo push (strong scaling)')
     ap.add_argument('--cpu-ncell', type=int, nargs=3, default=[64, 64, 64])
     ap.add_argument('--no-cpu', action='store_true')
     a = ap.parse_args()
@@ -141,8 +203,8 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     steps, warmup = a.steps, max(a.warmup, 3)
     cores = os.cpu_count() or 1
-    workload = 'bccFe %dx%dx%d LLG midpoint (SDEalgh %d), T=%g K, damping %g, dt 1e-16, z=50, do_reduced Y' % (
-        a.ncell[0], a.ncell[1], a.ncell[2], a.solver, a.temp, a.damping)
+    workload = 'bccFe %dx%dx%d LLG %s (SDEalgh %d), T=%g K, damping %g, dt 1e-16, z=50, do_reduced Y' % (
+        a.ncell[0], a.ncell[1], a.ncell[2], 'midpoint' if a.solver == 1 else 'Depondt', a.solver, a.temp, a.damping)
 
     if a.impl == 'reference':
         if rank != 0:
@@ -166,7 +228,8 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.cuda.set_device(local)
-    e, n = bcc_engine(a.ncell, a.solver, a.temp, a.damping, 1, rank, local)
+    slab = (world, rank, dist) if a.decomp == 'slab' else None
+    e, n = bcc_engine(a.ncell, a.solver, a.temp, a.damping, 1, 0 if slab else rank, local, slab=slab)
     sync = torch.zeros(1, device='cuda')
 
     def barrier():
@@ -175,15 +238,15 @@ def main():
         torch.cuda.synchronize()
         e.synchronize()
 
-    l0 = e.launch_count()
     e.sd_steps(warmup, first_step=1)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    l0 = e.launch_count()
     ms = e.time_sd_steps(steps, first_step=warmup + 1)
-    launches = e.launch_count() - l0 - 2 * warmup
+    launches = e.launch_count() - l0
     barrier()
-    # per-kernel durations of the two stage kernels (CUDA events on the engine's stream), averaged
+    # per-kernel durations of the two stage kernels (CUDA events on the engine's stream), median of 8
     st1, st2 = [], []
     for r in range(8):
         _, (x, y) = e.time_sd_steps(0, first_step=warmup + steps + 1 + r, stages=True)
@@ -196,20 +259,27 @@ def main():
     ms = float(t.item())
     value = world * n * steps / (ms * 1e-3)
 
-    # ---- end to end through the host-buffer API: H2D of the moments, K steps with a D2H observable read every
-    #      step (what a measuring driver does), D2H of the final state
+    # ---- end to end through the C ABI with HOST buffers (what a driver that owns the moments does): H2D of the
+    #      state from pinned host memory, K steps each followed by the observable read-back a measuring driver
+    #      makes (asd_measure: D2H of sum M per ensemble), D2H of emom / emomM / mmom into pinned host memory
     emom, emomM, mmom = e.get_moments()
-    pin = lambda x: torch.from_numpy(np.ascontiguousarray(x.ravel(order='F'))).pin_memory()
-    p_e, p_m = pin(emom), pin(mmom)
-    from uppasd_b200 import host as _h
-    k2 = max(10, steps // 4)
+
+    def pinned(x):
+        tt = torch.empty(x.size, dtype=torch.float64).pin_memory()
+        v = tt.numpy().reshape(x.shape, order='F')
+        v[...] = x
+        return tt, v
+    keep, h_e = pinned(emom)
+    keep2, h_eM = pinned(emomM)
+    keep3, h_m = pinned(mmom)
+    k2 = steps
     barrier()
     t0 = time.perf_counter()
-    e._chk(e.lib.asd_set_moments(e.h, p_e.data_ptr(), p_m.data_ptr(), None))
+    e.set_moments(h_e, h_m)
     for s in range(k2):
         e.sd_steps(1, first_step=10_000 + s)
         e.measure()
-    e.get_moments()
+    e.get_moments(out=(h_e, h_eM, h_m))
     e.synchronize()
     dt = time.perf_counter() - t0
     te = torch.tensor([dt], device='cuda', dtype=torch.float64)
@@ -217,7 +287,8 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = world * n * k2 / float(te.item())
     h2d = 32.0 * n / k2
-    d2h = 56.0 * n / k2 + 32.0
+    d2h = 56.0 * n / k2 + 24.0
+    _, slab_err = e.slab_status()
 
     if rank == 0:
         peak, how = peaks()
@@ -225,24 +296,34 @@ def main():
         t2 = float(np.median(st2)) * 1e-3
         t1 = float(np.median(st1)) * 1e-3
         ach = b2 * n / t2 / 1e9
+        kname = 'llg_stage_kernel<solver=%d,stage=2,reduced,staged>' % a.solver
+        par = ('ensemble-sharded x%d (one %d-spin ensemble per GPU, no communication)' % (world, n)) if not slab else \
+              ('z-slabs x%d of one supercell, halo push fused into the boundary-tile launches (peer stores over NVLink)' % world)
         out = {
             'metric': 'atom-steps/sec', 'value': value, 'unit': 'atom-steps/s', 'n_gpus': world, 'steps': steps,
-            'warmup': warmup, 'ms_per_step': ms / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': workload, 'spins_per_gpu': n, 'ensembles': world, 'parallelism': 'ensemble-sharded x%d' % world,
-                       'l2_policy': 'inputs larger than L2 (neighbour table %.0f MB per GPU)' % (50 * 4 * n / 1e6)},
+            'warmup': warmup, 'ms_per_step': ms / steps, 'higher_is_better': True,
+            'scaling': 'strong' if slab else 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': workload, 'spins_per_gpu': n, 'ensembles': 1 if slab else world, 'parallelism': par,
+                       'l2_policy': 'inputs larger than L2 (index tables %.0f MB + spins %.0f MB per GPU vs 126 MB L2)'
+                                    % ((7 * 16 + 24) * n / 1e6, 64.0 * n / 1e6)},
             'clocks': sampler.summary(),
             'e2e': {'value': e2e, 'unit': 'atom-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'steps': k2, 'note': 'asd_set_moments from pinned host memory + K steps each followed by asd_measure '
-                                         '(D2H of sum M) + asd_get_moments of the final state; copies amortised over K'},
+                    'steps': k2, 'note': 'asd_set_moments from pinned host memory (H2D of emom+mmom) + K x [asd_sd_steps(1) + '
+                                         'asd_measure (sync + D2H of sum M)] + asd_get_moments into pinned host memory '
+                                         '(D2H of emom+emomM+mmom); state copies amortised over the K steps'},
             'gpu_launches': int(launches),
-            'roofline': {'bound': 'hbm', 'kernel': 'llg_stage_kernel<solver=%d,stage=2,reduced>' % a.solver,
-                         'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+            'roofline': {'bound': 'hbm', 'kernel': kname,
+                         'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                         'traffic': traffic_from_profiles(kname),
                          'peak_source': how, 'alg_bytes_per_atom': b2, 'kernel_ms': t2 * 1e3,
-                         'stage1': {'alg_bytes_per_atom': b1, 'kernel_ms': t1 * 1e3, 'achieved': b1 * n / t1 / 1e9},
+                         'stage1': {'alg_bytes_per_atom': b1, 'kernel_ms': t1 * 1e3, 'achieved': b1 * n / t1 / 1e9,
+                                    'frac': b1 * n / t1 / 1e9 / peak},
                          'step_alg_bytes_per_atom': b1 + b2,
-                         'step_frac_of_peak': (b1 + b2) * n * steps / (ms * 1e-3) / 1e9 / peak},
+                         'step_frac_of_peak': (b1 + b2) * world * n * steps / (ms * 1e-3) / 1e9 / (peak * world)},
         }
+        if slab:
+            out['config']['halo'] = {'planes': 2, 'bytes_per_exchange_per_side': 2 * a.ncell[0] * a.ncell[1] * 2 * 32,
+                                     'exchanges_per_step': 2, 'timeout_flag': slab_err}
         if world == 1 and not a.no_cpu:
             os.environ.setdefault('OMP_NUM_THREADS', str(cores))
             v, cms, cn = cpu_leg(a.cpu_ncell, a.solver, a.temp, a.damping, 5, 1)
@@ -251,6 +332,8 @@ def main():
                                              'all host cores, noise pre-generated' % (*a.cpu_ncell, cn)}
         print(json.dumps(out))
     if world > 1:
+        dist.barrier()
+        e.close()
         dist.destroy_process_group()
 
 

@@ -6,8 +6,11 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _bcc(ncell, solver, temp, nslabs=0, mens=1, damping=0.5, seed=77):
-    """list of engines: one undecomposed (nslabs = 0) or `nslabs` slabs living in this process on device 0"""
+def _bcc(ncell, solver, temp, nslabs=0, mens=1, damping=0.5, seed=77, spread=False):
+    """list of engines: one undecomposed (nslabs = 0) or `nslabs` slabs living in this process, on device 0 or
+    (spread) round-robin over all visible devices -> peer stores cross NVLink"""
+    from uppasd_b200 import capi
+    ndev = capi.load().asd_device_count() if spread else 1
     import bench
     from uppasd_b200 import host, lattice, slab
     B, CONST = bench.BCC, bench.CONST
@@ -17,7 +20,7 @@ def _bcc(ncell, solver, temp, nslabs=0, mens=1, damping=0.5, seed=77):
     assert H == 2
     out = []
     for g in range(max(nslabs, 1)):
-        e = host.Engine(0)
+        e = host.Engine(g % ndev)
         e.set_constants(CONST['gama'], CONST['k_bolt'], CONST['mub'], CONST['mry'])
         nz = ncell[2] // max(nslabs, 1)
         n = 2 * ncell[0] * ncell[1] * nz
@@ -92,3 +95,20 @@ def test_slab_errors_are_loud():
     cp = lattice.couplings(ns, ca, sh, B['atype'], B['J'][None, None, :], B['mom'], CONST['mry'], CONST['mub'])
     with pytest.raises(host.AsdError):
         e.build_lattice_table(0, 2, (32, 4, 7), ('P', 'P', 'P'), ns, ca, cs, cp)   # 7 planes do not split in two
+
+
+def test_slab_across_devices():
+    """the same check with the slabs on different GPUs of the box (skipped on a single-GPU box)"""
+    from uppasd_b200 import capi
+    ndev = capi.load().asd_device_count()
+    if ndev < 2:
+        pytest.skip('needs at least two GPUs')
+    ncell = (32, 8, 4 * ndev)
+    ref = _bcc(ncell, 1, 300.0)[0]
+    sl = _bcc(ncell, 1, 300.0, nslabs=ndev, spread=True)
+    for s in range(25):
+        ref.sd_steps(1, first_step=s + 1)
+        for e in sl:
+            e.sd_steps(1, first_step=s + 1)
+    assert np.array_equal(_gather(sl), ref.get_moments()[0])
+    assert all(e.slab_status()[1] == 0 for e in sl)

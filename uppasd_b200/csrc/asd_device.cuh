@@ -942,7 +942,7 @@ __global__ void vectorise_table_kernel(int Npad, int z, int zq, const int* __res
       v[a] = (j < z) ? nl[(size_t)j * Npad + s] : s;
       c[a] = (cp && j < z) ? cp[(size_t)j * Npad + s] : 0.0;
    }
-   nl4[(size_t)q * Npad + s] = make_int4(v[0], v[1], v[2], v[3]);
+   if (nl4) nl4[(size_t)q * Npad + s] = make_int4(v[0], v[1], v[2], v[3]);
    if (cp4) cp4[(size_t)q * Npad + s] = make_double4(c[0], c[1], c[2], c[3]);
 }
 

@@ -157,6 +157,7 @@ struct asd_engine {
    int state_layout = 0;  // 0 = none, 1 = sd, 2 = mc
    DevBuf<SpinVec> cur, pred;
    DevBuf<double> b2eff, esite, part, red;
+   DevBuf<double> io_e, io_eM, io_m;   // staging of asd_set_moments / asd_get_moments (kept between calls)
    DevBuf<unsigned int> acc;
    long launches = 0;
    bool committed = false;
@@ -236,15 +237,18 @@ static int finish_layout(asd_engine* e, Layout& L) {
       const int variant = var ? atoi(var) : 3;
       t.nl4 = nullptr; t.cp4 = nullptr; t.zq = (t.z + 3) / 4; t.pf_tiles = 0; t.cpl_param = 0;
       if ((r = build_tiles(e, L))) return r;
+      // staged layouts use nl16 in the LLG kernels; the field-only / MC kernels then read the plain nl table
       if (variant >= 3 && t.z > 0) {
-         // staged layouts need the int4 index copy only for the non-LLG kernels; keep it unless memory is tight
-         if ((r = L.d_nl4.alloc((size_t)t.zq * Npad))) return r;
+         L.d_nl4.release(); L.d_cp4.release();
+         if (!t.staged && (r = L.d_nl4.alloc((size_t)t.zq * Npad))) return r;
          if (!L.reduced && (r = L.d_cp4.alloc((size_t)t.zq * Npad))) return r;
-         vectorise_table_kernel<<<dim3((unsigned)((Npad + 255) / 256), t.zq), 256, 0, st>>>((int)Npad, t.z, t.zq, t.nl, L.reduced ? nullptr : t.cp,
-                                                                                 L.d_nl4.p, L.reduced ? nullptr : L.d_cp4.p);
-         e->launches++;
-         CU(cudaGetLastError());
-         CU(cudaStreamSynchronize(st));
+         if (L.d_nl4.p || L.d_cp4.p) {
+            vectorise_table_kernel<<<dim3((unsigned)((Npad + 255) / 256), t.zq), 256, 0, st>>>((int)Npad, t.z, t.zq, t.nl, L.reduced ? nullptr : t.cp,
+                                                                                    L.d_nl4.p, L.reduced ? nullptr : L.d_cp4.p);
+            e->launches++;
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(st));
+         }
          t.nl4 = L.d_nl4.p; t.cp4 = L.d_cp4.p;
          const char* pf = std::getenv("ASD_PF");
          int sms = 148;
@@ -488,51 +492,66 @@ static int fill_llg(asd_engine* e, Layout& L, LlgParams& p, unsigned long long s
 // ------------------------------------------------------------------------------------------------
 // state movement
 // ------------------------------------------------------------------------------------------------
-static int upload_state(asd_engine* e, Layout& L) {
+// host arrays (Fortran shapes, original atom order) -> packed device order.  emom / mmom may point at the caller's
+// buffers (pinned or pageable): they are copied with cudaMemcpyAsync on the engine's stream and packed on the device.
+static int upload_state_from(asd_engine* e, Layout& L, const double* emom, const double* mmom, const double* mmom0) {
    const size_t NM = (size_t)e->N * e->M;
-   DevBuf<double> d_e, d_m;
    int r;
-   if ((r = d_e.upload(e->h_emom, e->stream))) return r;
-   if ((r = d_m.upload(e->h_mmom, e->stream))) return r;
+   if ((r = e->io_e.alloc(3 * NM))) return r;
+   if ((r = e->io_m.alloc(NM))) return r;
+   CU(cudaMemcpyAsync(e->io_e.p, emom, 3 * NM * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+   CU(cudaMemcpyAsync(e->io_m.p, mmom, NM * sizeof(double), cudaMemcpyHostToDevice, e->stream));
    if ((r = e->cur.alloc((size_t)L.Npad * e->M))) return r;
    if ((r = e->pred.alloc((size_t)L.Npad * e->M))) return r;
    dim3 g, b;
    launch_cfg(L.Npad, e->M, g, b);
    // only the owned slots: the halo slots of a slab belong to the neighbours' pushes
-   pack_kernel<<<g, b, 0, e->stream>>>(e->N, L.t.Nown, L.Npad, e->M, L.d_orig.p, d_e.p, d_m.p, e->cur.p);
-   pack_kernel<<<g, b, 0, e->stream>>>(e->N, L.t.Nown, L.Npad, e->M, L.d_orig.p, d_e.p, d_m.p, e->pred.p);
+   pack_kernel<<<g, b, 0, e->stream>>>(e->N, L.t.Nown, L.Npad, e->M, L.d_orig.p, e->io_e.p, e->io_m.p, e->cur.p);
+   pack_kernel<<<g, b, 0, e->stream>>>(e->N, L.t.Nown, L.Npad, e->M, L.d_orig.p, e->io_e.p, e->io_m.p, e->pred.p);
    e->launches += 2;
    CU(cudaGetLastError());
    if (e->mompar != 0) {
       if ((r = host_orig(e, L))) return r;
       std::vector<double> h((size_t)e->M * L.Npad, 0.0);
-      const std::vector<double>& src = e->h_mmom0.empty() ? e->h_mmom : e->h_mmom0;
+      const double* src = mmom0 ? mmom0 : mmom;
       for (int k = 0; k < e->M; k++)
          for (int s = 0; s < L.Npad; s++) if (L.orig[s] >= 0) h[(size_t)k * L.Npad + s] = src[(size_t)L.orig[s] + (size_t)e->N * k];
       if ((r = L.d_mmom0.upload(h, e->stream))) return r;
    }
    CU(cudaStreamSynchronize(e->stream));
-   (void)NM;
    return slab_push_state(e);
+}
+
+static int upload_state(asd_engine* e, Layout& L) {
+   return upload_state_from(e, L, e->h_emom.data(), e->h_mmom.data(), e->h_mmom0.empty() ? nullptr : e->h_mmom0.data());
 }
 
 static int download_state(asd_engine* e, Layout& L, double* emom, double* emomM, double* mmom) {
    const size_t NM = (size_t)e->N * e->M;
-   DevBuf<double> d_e, d_eM, d_m;
    int r;
-   if (emom && (r = d_e.alloc(3 * NM))) return r;
-   if (emomM && (r = d_eM.alloc(3 * NM))) return r;
-   if (mmom && (r = d_m.alloc(NM))) return r;
+   if (emom && (r = e->io_e.alloc(3 * NM))) return r;
+   if (emomM && (r = e->io_eM.alloc(3 * NM))) return r;
+   if (mmom && (r = e->io_m.alloc(NM))) return r;
    dim3 g, b;
    launch_cfg(L.Npad, e->M, g, b);
-   unpack_kernel<<<g, b, 0, e->stream>>>(e->N, L.Npad, e->M, L.d_orig.p, e->cur.p, d_e.p, d_eM.p, d_m.p);
+   unpack_kernel<<<g, b, 0, e->stream>>>(e->N, L.Npad, e->M, L.d_orig.p, e->cur.p, emom ? e->io_e.p : nullptr,
+                                         emomM ? e->io_eM.p : nullptr, mmom ? e->io_m.p : nullptr);
    e->launches++;
    CU(cudaGetLastError());
-   if (emom) CU(cudaMemcpyAsync(emom, d_e.p, 3 * NM * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-   if (emomM) CU(cudaMemcpyAsync(emomM, d_eM.p, 3 * NM * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-   if (mmom) CU(cudaMemcpyAsync(mmom, d_m.p, NM * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   if (emom) CU(cudaMemcpyAsync(emom, e->io_e.p, 3 * NM * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   if (emomM) CU(cudaMemcpyAsync(emomM, e->io_eM.p, 3 * NM * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   if (mmom) CU(cudaMemcpyAsync(mmom, e->io_m.p, NM * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
    CU(cudaStreamSynchronize(e->stream));
    return 0;
+}
+
+// the device holds the only copy of the state (direct upload): bring it back before a layout is rebuilt
+static int stash_state_to_host(asd_engine* e) {
+   if (e->state_layout == 0 || !e->h_emom.empty()) return 0;
+   Layout& from = (e->state_layout == 1) ? e->sd : e->mc;
+   e->h_emom.resize(3 * (size_t)e->N * e->M);
+   e->h_mmom.resize((size_t)e->N * e->M);
+   return download_state(e, from, e->h_emom.data(), nullptr, e->h_mmom.data());
 }
 
 // make sure the spin buffers are in layout `want` (1 sd, 2 mc); converts through the host copy when switching
@@ -851,6 +870,8 @@ int asd_set_llg(asd_engine* e, int SDEalgh, double delta_t, const double* Landeg
    for (double x : e->temp) if (x > 0.0) e->llg_thermal = true;
    if (mompar != 0 && e->committed && e->state_layout == 1 && e->sd.d_mmom0.p == nullptr) {
       // moments were uploaded before mompar was switched on: re-stage through the host copy
+      int r = stash_state_to_host(e);
+      if (r) return r;
       e->state_layout = 0;
    }
    return 0;
@@ -859,6 +880,16 @@ int asd_set_llg(asd_engine* e, int SDEalgh, double delta_t, const double* Landeg
 int asd_set_moments(asd_engine* e, const double* emom, const double* mmom, const double* mmom0) {
    if (e->N == 0) return fail(-2, "asd_set_system must be called first");
    const size_t NM = (size_t)e->N * e->M;
+   if (e->committed && e->sd_built) {
+      // tables are frozen: go straight from the caller's buffers to the device layout (no host-side copy)
+      CU(cudaSetDevice(e->device));
+      if (mmom0) e->h_mmom0.assign(mmom0, mmom0 + NM); else e->h_mmom0.clear();
+      int r = upload_state_from(e, e->sd, emom, mmom, mmom0);
+      if (r) return r;
+      e->h_emom.clear(); e->h_mmom.clear();
+      e->state_layout = 1;
+      return 0;
+   }
    e->h_emom.assign(emom, emom + 3 * NM);
    e->h_mmom.assign(mmom, mmom + NM);
    if (mmom0) e->h_mmom0.assign(mmom0, mmom0 + NM); else e->h_mmom0.clear();
@@ -875,6 +906,7 @@ int asd_get_moments(asd_engine* e, double* emom, double* emomM, double* mmom) {
 int asd_commit(asd_engine* e) {
    if (e->N == 0) return fail(-2, "asd_set_system must be called first");
    CU(cudaSetDevice(e->device));
+   if (e->committed && !e->slab.on) { int r = stash_state_to_host(e); if (r) return r; }
    if (!e->lattice_built) {
       if (!e->ex.present()) return fail(-2, "no exchange table (asd_set_exchange / asd_build_lattice_table)");
       int r = build_layout(e, e->sd, false);

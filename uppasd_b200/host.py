@@ -105,10 +105,14 @@ class Engine:
         self._chk(self.lib.asd_commit(self.h))
 
     # ---- compute -----------------------------------------------------------------------------------
-    def get_moments(self):
-        emom = np.zeros((3, self.N, self.M), order='F')
-        emomM = np.zeros((3, self.N, self.M), order='F')
-        mmom = np.zeros((self.N, self.M), order='F')
+    def get_moments(self, out=None):
+        """out: optional (emom, emomM, mmom) Fortran-ordered arrays to fill (e.g. views of pinned host memory)"""
+        if out is None:
+            emom = np.zeros((3, self.N, self.M), order='F')
+            emomM = np.zeros((3, self.N, self.M), order='F')
+            mmom = np.zeros((self.N, self.M), order='F')
+        else:
+            emom, emomM, mmom = out
         self._chk(self.lib.asd_get_moments(self.h, _p(emom), _p(emomM), _p(mmom)))
         return emom, emomM, mmom
 
