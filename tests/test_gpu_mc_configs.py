@@ -1,0 +1,115 @@
+"""BASELINE.json configs 2 and 3 as parity cases: FeCo B2 two-sublattice Monte Carlo temperature points with 8
+ensembles (Metropolis), and the kagome Heisenberg + DMI lattice driven by heat-bath sweeps followed by an LLG
+relaxation.  Monte Carlo compares observables with the oracle's replay of mc_mphase (reference generators, random
+sequential visiting order) within statistical error bars; the LLG relaxation that follows starts from the GPU's own
+MC state and must match the oracle to 1e-12."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import inputs, orc
+from util import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def _system(name, mens, **over):
+    fx = json.load(open(os.path.join(GOLDEN, name + '.json')))
+    args = list(inputs.load_fixture(fx))
+    args[0] = dict(args[0], mensemble=mens, **over)
+    return args[0], orc.build_system(*args)
+
+
+@pytest.mark.parametrize('T', [300.0, 1100.0])
+def test_feco_metropolis_temperature_points(T):
+    """FeCo B2 (tests/FeCo tables: 2 sublattices, z up to 258), Mensemble = 8: <|M|> and <E> at a point well inside the
+    ordered phase and at one in the critical region."""
+    from uppasd_b200 import host
+    inp, S = _system('feco', 8)
+    e = host.engine_from_system(S, orc.CONST, temp=T, seed=21)
+    e.mc_sweeps('M', 400, T)
+    gm, ge = [], []
+    for r in range(80):
+        e.mc_sweeps('M', 5, T, first_sweep=401 + 5 * r)
+        m, en = e.measure(energy=True)
+        gm.append(np.sqrt(((m / S['Natom']) ** 2).sum(axis=0)))
+        ge.append(en / S['Natom'])
+    gm, ge = np.array(gm), np.array(ge)                # (samples, 8)
+    inp4, S4 = _system('feco', 4)
+    rm, re_, _ = orc.mc_run(S4, 'M', T, 800, seed=5, sample_every=5, burn=400)
+    g_m, r_m = gm.mean(axis=0), rm.mean(axis=0)
+    sig_m = np.sqrt(g_m.var() / len(g_m) + r_m.var() / len(r_m))
+    assert abs(g_m.mean() - r_m.mean()) < 5 * sig_m + 0.03, (T, g_m.mean(), r_m.mean(), sig_m)
+    g_e = ge.mean(axis=0)
+    sig_e = np.sqrt(g_e.var() / len(g_e)) + abs(re_.std()) / np.sqrt(len(re_) / 10.0)
+    assert abs(g_e.mean() - re_.mean()) < 5 * sig_e + 0.02 * abs(re_.mean()), (T, g_e.mean(), re_.mean(), sig_e)
+    # Tc ordering: the hot point must be less magnetised than the cold one would be (sanity of the scan direction)
+    emom, _, _ = e.get_moments()
+    assert np.abs(np.sqrt((emom ** 2).sum(axis=0)) - 1.0).max() < 1e-12
+
+
+def test_kagome_heatbath_then_llg_relaxation():
+    """tests/kagome tables (Heisenberg + DMI, reduced Hamiltonian, NA = 3): heat-bath sweeps at 5 K, observables against
+    the oracle; then the GPU state is relaxed with the midpoint LLG solver at T = 0 and must follow the oracle started
+    from that very state (MC layout -> SD layout hand-over inside the engine)."""
+    from uppasd_b200 import host
+    T = 5.0
+    inp, S = _system('kagome', 8)
+    e = host.engine_from_system(S, orc.CONST, sdealgh=1, delta_t=inp['timestep'], damping=inp['damping'], temp=0.0, seed=8)
+    e.mc_sweeps('H', 200, T)
+    gm, ge = [], []
+    for r in range(60):
+        e.mc_sweeps('H', 5, T, first_sweep=201 + 5 * r)
+        m, en = e.measure(energy=True)
+        gm.append(np.sqrt(((m / S['Natom']) ** 2).sum(axis=0)))
+        ge.append(en / S['Natom'])
+    gm, ge = np.array(gm), np.array(ge)
+    inp4, S4 = _system('kagome', 4)
+    rm, re_, _ = orc.mc_run(S4, 'H', T, 500, seed=2, sample_every=5, burn=200)
+    g_e = ge.mean(axis=0)
+    sig_e = np.sqrt(g_e.var() / len(g_e)) + abs(re_.std()) / np.sqrt(len(re_) / 10.0)
+    assert abs(g_e.mean() - re_.mean()) < 5 * sig_e + 0.02 * abs(re_.mean()), (g_e.mean(), re_.mean(), sig_e)
+    g_m, r_m = gm.mean(axis=0), rm.mean(axis=0)
+    sig_m = np.sqrt(g_m.var() / len(g_m) + r_m.var() / len(r_m))
+    assert abs(g_m.mean() - r_m.mean()) < 5 * sig_m + 0.03, (g_m.mean(), r_m.mean(), sig_m)
+    # ---- LLG relaxation from the Monte Carlo state ----
+    emom, emomM, mmom = e.get_moments()
+    S['emom'], S['emomM'], S['mmom'] = emom.copy(order='F'), emomM.copy(order='F'), mmom.copy(order='F')
+    st = orc.SdState(S, 1, inp['timestep'], inp['damping'])
+    e.sd_steps(300)
+    for _ in range(300):
+        st.step()
+    a, _, _ = e.get_moments()
+    assert np.abs(a - st.emom).max() <= 1e-12
+    _, en_after = e.measure(energy=True)
+    assert (en_after / S['Natom'] <= ge[-1] + 1e-9).all()      # damped T = 0 dynamics can only lower the energy
+
+
+def test_mc_on_device_built_tables_matches_host_tables():
+    """Monte Carlo on a lattice whose tables were built on the device (asd_build_lattice_table) = the same chain as on
+    tables handed over by the host: same colouring, noise keyed by the original atom index."""
+    import bench
+    from uppasd_b200 import host
+    e1, n = bench.bcc_engine((6, 6, 6), 1, 300.0, 0.5, 2, 0, 0)
+    lst, size, coup = e1.get_table(0)
+    emom, emomM, mmom = e1.get_moments()
+    e2 = host.Engine(0)
+    C = bench.CONST
+    e2.set_constants(C['gama'], C['k_bolt'], C['mub'], C['mry'])
+    e2.set_system(n, 2, 2, (np.arange(n, dtype=np.int32) % 2) + 1)
+    e2.set_exchange(lst, size, coup)
+    e2.set_llg(1, 1e-16, landeg=1.0, lambda1=0.5, temp=300.0, seed=20261017)
+    e2.set_moments(emom, mmom)
+    e2.commit()
+    for mode in ('M', 'H'):
+        e1.mc_sweeps(mode, 25, 600.0)
+        e2.mc_sweeps(mode, 25, 600.0)
+        a, _, _ = e1.get_moments()
+        b, _, _ = e2.get_moments()
+        assert np.array_equal(a, b), mode
+    # and back to spin dynamics on the lattice layout
+    e1.sd_steps(10)
+    e2.sd_steps(10)
+    assert np.abs(e1.get_moments()[0] - e2.get_moments()[0]).max() <= 1e-13

@@ -175,6 +175,7 @@ static void launch_cfg(int Npad, int M, dim3& grid, dim3& block) {
 // ------------------------------------------------------------------------------------------------
 static int host_orig(asd_engine* e, Layout& L);
 static int slab_commit(asd_engine* e);
+static int materialise_host_tables(asd_engine* e);
 static int slab_push_state(asd_engine* e);
 
 // staged tile path: gather lists + 16-bit neighbour table (asd_tiles.cuh).  Leaves t.staged = 0 when a tile would
@@ -299,33 +300,36 @@ static int finish_layout(asd_engine* e, Layout& L) {
    return 0;
 }
 
-// greedy colouring of the symmetrised union of the neighbour tables (host, O(N z))
+// greedy colouring of the symmetrised union of the neighbour tables (host, O(N z log z))
 static int colour_graph(const asd_engine* e, std::vector<int>& colour) {
    const int N = e->N;
-   std::vector<std::vector<int>> extra(0);
-   // adjacency = union of lists; lists are symmetric for every physical table, but symmetrise defensively
-   std::vector<int> deg(N, 0);
-   auto for_each_nb = [&](int i, auto&& f) {
-      const HostTable* T[3] = {&e->ex, &e->dm, &e->bq};
+   const HostTable* T[3] = {&e->ex, &e->dm, &e->bq};
+   int ztot = 0;
+   for (auto* t : T) if (t->present()) ztot += t->z;
+   // adj[i*ztot .. ) = sorted neighbours of i (0-based, self and empty entries removed), deg[i] of them
+   std::vector<int> adj((size_t)N * ztot), deg(N, 0);
+   for (int i = 0; i < N; i++) {
+      int* a = adj.data() + (size_t)i * ztot;
+      int n = 0;
       for (auto* t : T) {
          if (!t->present()) continue;
          for (int j = 0; j < t->z; j++) {
-            int nb = t->list[(size_t)j + (size_t)t->z * i];
-            if (nb > 0 && nb - 1 != i) f(nb - 1);
+            const int nb = t->list[(size_t)j + (size_t)t->z * i];
+            if (nb > 0 && nb - 1 != i) a[n++] = nb - 1;
          }
       }
-   };
-   // reverse edges that are not present forward
+      std::sort(a, a + n);
+      n = (int)(std::unique(a, a + n) - a);
+      deg[i] = n;
+   }
+   // lists are symmetric for every physical table; add the reverse of any edge that is not (e.g. DM maps, sym 0)
    std::vector<std::vector<int>> rev(N);
-   {
-      // cheap symmetry check via sorted forward lists
-      std::vector<int> fw;
-      for (int i = 0; i < N; i++) {
-         for_each_nb(i, [&](int nb) {
-            bool back = false;
-            for_each_nb(nb, [&](int x) { if (x == i) back = true; });
-            if (!back) rev[nb].push_back(i);
-         });
+   for (int i = 0; i < N; i++) {
+      const int* a = adj.data() + (size_t)i * ztot;
+      for (int q = 0; q < deg[i]; q++) {
+         const int nb = a[q];
+         const int* b = adj.data() + (size_t)nb * ztot;
+         if (!std::binary_search(b, b + deg[nb], i)) rev[nb].push_back(i);
       }
    }
    colour.assign(N, -1);
@@ -334,7 +338,8 @@ static int colour_graph(const asd_engine* e, std::vector<int>& colour) {
    for (int i = 0; i < N; i++) {
       mark.assign(ncol + 1, 0);
       auto see = [&](int nb) { int c = colour[nb]; if (c >= 0 && c <= ncol) mark[c] = 1; };
-      for_each_nb(i, see);
+      const int* a = adj.data() + (size_t)i * ztot;
+      for (int q = 0; q < deg[i]; q++) see(a[q]);
       for (int nb : rev[i]) see(nb);
       int c = 0;
       while (c < ncol && mark[c]) c++;
@@ -558,7 +563,13 @@ static int stash_state_to_host(asd_engine* e) {
 static int ensure_layout(asd_engine* e, int want) {
    if (!e->committed) return fail(-2, "asd_commit has not been called");
    if (want == 2 && !e->mc_built) {
-      if (e->lattice_built) return fail(-5, "Monte Carlo on device-built lattice tables needs asd_get_table + asd_set_exchange first");
+      if (e->slab.on) return fail(-5, "Monte Carlo sweeps are not decomposed into slabs yet");
+      if (e->lattice_built) {
+         // the colour-major layout is built on the host: bring the device-built tables back in the reference's shape
+         if ((long)e->N > 40000000L) return fail(-5, "Monte Carlo layout of a device-built lattice is limited to 4e7 atoms per engine");
+         int r = materialise_host_tables(e);
+         if (r) return r;
+      }
       int r = build_layout(e, e->mc, true);
       if (r) return r;
       e->mc_built = true;

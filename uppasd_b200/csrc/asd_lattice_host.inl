@@ -269,3 +269,21 @@ int asd_init_moments_tilted(asd_engine* e, double amplitude, int NA, const doubl
 }
 
 }  // extern "C"
+
+// device-built tables -> HostTable (reference shapes), for the host-side construction of the Monte Carlo layout
+static int materialise_host_tables(asd_engine* e) {
+   HostTable* T[3] = {&e->ex, &e->dm, &e->bq};
+   for (int kind = 0; kind < 3; kind++) {
+      const int z = e->sd.zs[kind];
+      if (z == 0 || T[kind]->present()) continue;
+      const int nc = (kind == 1) ? 3 : 1;
+      HostTable& H = *T[kind];
+      H.z = z; H.ncomp = nc;
+      H.list.assign((size_t)z * e->N, 0);
+      H.lsize.assign(e->NH, 0);
+      H.coup.assign((size_t)nc * z * e->NH, 0.0);
+      int r = asd_get_table(e, kind, H.list.data(), H.lsize.data(), H.coup.data());
+      if (r) { H = HostTable(); return r; }
+   }
+   return 0;
+}
