@@ -147,6 +147,13 @@ int asd_mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, doub
  * (NULL to skip). */
 int asd_measure(asd_engine* e, double* msum, double* energy);
 
+/* Term-resolved energy per atom in mRy (calc_energy, energy.f90:180-340, the columns of totenergy.*.out that
+ * exist on this path): terms(5,M) = exchange, anisotropy, DM, biquadratic, Zeeman; their sum is ene%energy. */
+int asd_energy_terms(asd_engine* e, double* terms);
+
+/* selected moments for trajectory output (prn_trajectories.f90:60-110): atoms[n] 1-based, out(4,n,M) = ex,ey,ez,|m| */
+int asd_get_atoms(asd_engine* e, int n, const int* atoms, double* out);
+
 /* Device-timing helper for bench.py: runs nsteps steps bracketed by CUDA events on the engine's stream
  * and returns the elapsed milliseconds; per-kernel time of the two stage kernels in stage_ms[2]. */
 int asd_time_sd_steps(asd_engine* e, long nsteps, long first_step, float* total_ms, float* stage_ms);

@@ -29,6 +29,12 @@ def fixture(dirname, inpname='inpsd.dat', extra_inp=None):
               'anisotropy': 'kfile'}
     for k, v in files.items():
         out[keymap[k]] = inputs._rows(v)
+    # the same files verbatim, so that the product's own readers (uppasd_b200/asdio.py) can be run on a copy of the
+    # reference's run directory materialised from this JSON
+    raw = {'inpsd.dat': open(os.path.join(d, inpname)).read()}
+    for k, v in files.items():
+        raw[os.path.relpath(v, d)] = open(v).read()
+    out['raw'] = raw
     inp['cell'] = [list(map(float, r)) for r in inp['cell']]
     out['inp'] = inp
     return out

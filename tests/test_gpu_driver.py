@@ -1,0 +1,122 @@
+"""The reference's own regression cases, run the way a user runs them: a copy of the reference run directory
+(materialised from tests/golden/*.json) -> `uppasd_b200.driver.Simulation(...).run()` -> the reference's measurement
+files, read back row by row like tests/bergtest.py does and compared with the values its YAML files pin
+(tests/regulartests.yaml, tests/regressionResaro.yaml, tests/cudatests.yaml; tolerances = bergtest's)."""
+import os
+
+import numpy as np
+import pytest
+
+from test_asdio_host import materialise
+from uppasd_b200 import asdio
+
+pytestmark = pytest.mark.gpu
+
+
+def _row(path, it):
+    for r in asdio.read_out(path):
+        if int(r[0]) == it:
+            return r
+    raise AssertionError('no row %d in %s' % (it, path))
+
+
+def _sloppy(a, b):
+    return abs(a - b) <= 2e-2 and abs(a - b) <= 2e-2 * max(abs(a), abs(b), 1e-300)
+
+
+def test_kagome_run_directory(tmp_path):
+    from uppasd_b200 import driver
+    fx, path = materialise('kagome', tmp_path)
+    sim = driver.Simulation(path).run()
+    d = str(tmp_path)
+    exp = fx['expected']
+    r = _row(os.path.join(d, 'averages.kagome_T.out'), 13000)
+    for a, b in zip(r[1:5], exp['averages']['13000']):
+        assert abs(a - b) <= 1e-8                                       # regulartests.yaml:132-143 ('similar')
+    t = _row(os.path.join(d, 'trajectory.kagome_T.002.1.out'), 2400)
+    assert int(t[1]) == 2
+    for a, b in zip(t[2:6], exp['trajectory']['2400']):
+        assert abs(a - b) <= 1e-8                                       # regulartests.yaml:145-156
+    # restart file written at the end (uppasd.f90:344-350), readable by initmag 4
+    rstep, emom, mmom = asdio.read_restart(os.path.join(d, 'restart.kagome_T.out'), sim.natom, 1)
+    assert rstep == 15001 and np.abs(emom - sim.moments()[0]).max() < 1e-8
+    assert os.path.exists(os.path.join(d, 'totenergy.kagome_T.out')) and os.path.exists(os.path.join(d, 'coord.kagome_T.out'))
+
+
+def test_megatest_run_directory(tmp_path):
+    from uppasd_b200 import driver
+    fx, path = materialise('megatest', tmp_path)
+    sim = driver.Simulation(path).run()
+    d = str(tmp_path)
+    exp = fx['expected']
+    r = _row(os.path.join(d, 'averages.megaTest.out'), 11000)
+    for a, b in zip(r[1:5], exp['averages']['11000']):
+        assert abs(a - b) <= 1e-8                                       # regressionResaro.yaml:18-27
+    emom, _, _ = sim.moments()
+    for a, b in zip(emom[:, exp['moment']['atom'] - 1, 0], exp['moment']['11000']):
+        assert abs(a - b) <= 1e-8                                       # regressionResaro.yaml:64-73
+    c = asdio.read_out(os.path.join(d, 'coord.megaTest.out'))[exp['coord']['atom'] - 1]
+    assert c[1:4] == exp['coord']['row'] and int(c[4]) == exp['coord']['type'] and int(c[5]) == exp['coord']['numb']
+    # totenergy row 10900 (regressionResaro.yaml:112-122): Tot, Exc, ..., Zeeman
+    e = _row(os.path.join(d, 'totenergy.megaTest.out'), 10900)
+    assert abs(e[1] - (-6.10005366)) <= 1e-8
+    assert abs(e[9] - (-5.36620122e-05)) <= 1e-8
+    assert abs(e[1] - (e[2] + e[9])) <= 3e-8                              # printed with es16.8
+
+
+@pytest.mark.parametrize('name,simid,sdealgh', [('feco', 'FeCo__B2', 1), ('feco_cuda', 'FeCo__B2', 5), ('bccfe_cuda', 'bcc_Fe_T', 5)])
+def test_cumulant_goldens(name, simid, sdealgh, tmp_path):
+    """tests/FeCo (regulartests.yaml:219-242) and the reference's CUDA cases (cudatests.yaml:24-70; its CUDA path always
+    integrates with Depondt, so SDEalgh 5 is requested explicitly here)"""
+    from uppasd_b200 import driver
+    fx, path = materialise(name, tmp_path)
+    inp = asdio.read_inpsd(path)
+    inp['sdealgh'] = sdealgh
+    driver.Simulation(inp, directory=str(tmp_path)).run()
+    exp = fx['expected']
+    (it, want), = exp['averages_M'].items()
+    assert _sloppy(_row(os.path.join(str(tmp_path), 'averages.%s.out' % simid), int(it))[4], want)
+    (it, want), = exp['cumulants'].items()
+    got = _row(os.path.join(str(tmp_path), 'cumulants.%s.out' % simid), int(it))
+    for a, b in zip(got[1:5], want):
+        assert _sloppy(a, b), (got, want)
+
+
+@pytest.mark.parametrize('mode', ['S', 'M', 'H'])
+def test_thermal_bccfe_modes_are_statistically_right(mode, tmp_path):
+    """tests/bccFe (6^3, 500 K, initial phase + measurement phase in modes S / M / H).  Its goldens pin the reference's
+    own random stream (tseed 5, one thread); with a different generator the same observables must agree within a
+    few per cent: <M> ~ 1.80 mu_B, U_Binder ~ 0.666 (regulartests.yaml:244-347)."""
+    from uppasd_b200 import driver
+    fx, path = materialise('bccfe', tmp_path, {'MODE': mode})
+    inp = asdio.read_inpsd(path)
+    inp['mcnstep'] = 3000 if mode != 'S' else 0
+    inp['mensemble'] = 4
+    driver.Simulation(inp, directory=str(tmp_path)).run()
+    rows = asdio.read_out(os.path.join(str(tmp_path), 'cumulants.bcc_Fe_T.out'))
+    last = rows[-1]
+    ref = fx['expected']['S_cumulants_41']
+    assert abs(last[1] - ref[0]) < 0.06, (mode, last, ref)               # <M>
+    assert abs(last[4] - ref[3]) < 5e-3                                  # Binder cumulant deep in the ordered phase
+    av = asdio.read_out(os.path.join(str(tmp_path), 'averages.bcc_Fe_T.out'))
+    assert abs(av[-1][4] - 1.80) < 0.08
+
+
+def test_restart_and_relax_api(tmp_path):
+    """initmag 4 continues a run from restart.<simid>.out (restart.f90:320-381); relax() is pyasd's relax_"""
+    from uppasd_b200 import driver
+    fx, path = materialise('kagome', tmp_path)
+    inp = asdio.read_inpsd(path)
+    inp['nstep'] = 400
+    a = driver.Simulation(dict(inp), directory=str(tmp_path)).run()
+    inp2 = dict(inp, initmag=4, restartfile=os.path.join(str(tmp_path), 'restart.kagome_T.out'), nstep=200)
+    b = driver.Simulation(inp2, directory=str(tmp_path))
+    assert b.rstep == 401
+    assert np.abs(b.moments()[0] - a.moments()[0]).max() < 1e-8           # es16.8 round trip
+    m = b.relax('S', 50, 0.0, 1e-16, 0.5)
+    # unit norm to the precision of the es16.8 restart file (the schemes conserve whatever norm they are given)
+    assert m.shape == (3, b.natom, 1) and np.abs(np.sqrt((m ** 2).sum(axis=0)) - 1).max() < 1e-8
+    e0 = b.energy()
+    b.relax('H', 20, 1.0)
+    b.relax('S', 200, 0.0, 1e-16, 0.5)
+    assert b.energy() <= e0 + 1e-6

@@ -1,0 +1,331 @@
+"""On-disk formats of the reference, for the slice of it this path serves.
+
+Readers (what the driver needs to set a simulation up from a reference run directory):
+  inpsd.dat            `keyword value` lines, case-insensitive, `d` exponents, block keywords (cell, ip_nphase,
+                       ip_mcanneal, ntraj) -- source/Input/inputhandler.f90:52 ff.; defaults inputdata.f90:300-530,
+                       prn_averages.f90:254-263, prn_trajectories.f90:112-125
+  posfile / momfile    source/Input/inputhandler_ext.f90:59-128, 228-330
+  jfile / dmfile / bqfile   :444-627, 1095-1190, 2023-2146 with getNeighVec :1007-1042 (maptype 1 / 2, posfiletype C / D)
+  kfile                :1069-1089
+  restart file         source/System/restart.f90:320-381 (new format written by prn_mag_conf_iter :186-246)
+Writers (what the reference's own regression YAMLs read back, tests/bergtest.py + extractoutput.py):
+  averages.<simid>.out, cumulants.<simid>.out, totenergy.<simid>.out, trajectory.<simid>.<atom>.<ens>.out,
+  restart.<simid>.out, coord.<simid>.out
+with the reference's Fortran edit descriptors (i8, es16.8, ...) reproduced digit for digit.
+
+Host-side product code (numpy only).
+"""
+import os
+
+import numpy as np
+
+
+class InputError(ValueError):
+    pass
+
+
+def _num(tok):
+    t = tok.strip().rstrip(',')
+    return float(t.replace('d', 'e').replace('D', 'e'))
+
+
+def _flag(tok):
+    t = tok.strip().strip('.').upper()
+    return t[0] if t else 'N'
+
+
+def _data_rows(path):
+    rows = []
+    with open(path) as fh:
+        for line in fh:
+            t = line.split()
+            if t and not t[0].startswith(('#', '!')):
+                rows.append(t)
+    return rows
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# inpsd.dat
+# ---------------------------------------------------------------------------------------------------------------
+def defaults():
+    return dict(
+        simid='_UppASD_', ncell=(1, 1, 1), bc=('0', '0', '0'), cell=np.eye(3), sym=0, alat=1.0, aunits='N',
+        posfile=None, momfile=None, exchange=None, dm=None, bq=None, anisotropy=None, restartfile=None,
+        posfiletype='C', maptype=1, do_ralloy=0, mensemble=1, tseed=1, sdealgh=1, ipsdealgh=-1, initmag=3, mode='S',
+        ip_mode='N', temp=0.0, nstep=1, mcnstep=0, damping=0.05, timestep=1.0e-16, hfield=(0.0, 0.0, 0.0),
+        ip_hfield=(0.0, 0.0, 0.0), ip_temp=0.0, ip_nphase=[], ip_mcanneal=[], ip_mcnstep=0, do_reduced='N', do_sortcoup='N',
+        mompar=0, landeg_glob=2.0, do_avrg='Y', avrg_step=100, avrg_buff=10, do_cumu='N', cumu_step=50, cumu_buff=10,
+        plotenergy=0, do_tottraj='N', tottraj_step=1000, tottraj_buff=10, trajectories=[], do_prnstruct=0,
+        gpu_mode=0, gpu_rng_seed=0, do_jtensor=0, map_multiple=False, relaxed_if=False)
+
+
+_SCALAR_INT = {'sym', 'maptype', 'do_ralloy', 'mensemble', 'tseed', 'sdealgh', 'ipsdealgh', 'initmag', 'nstep', 'mcnstep',
+               'mompar', 'avrg_step', 'avrg_buff', 'cumu_step', 'cumu_buff', 'plotenergy', 'tottraj_step', 'tottraj_buff',
+               'do_prnstruct', 'gpu_mode', 'gpu_rng_seed', 'do_jtensor', 'ip_mcnstep'}
+_SCALAR_REAL = {'alat', 'temp', 'damping', 'timestep', 'ip_temp'}
+_SCALAR_FLAG = {'aunits', 'posfiletype', 'do_reduced', 'do_sortcoup', 'do_avrg', 'do_cumu', 'do_tottraj', 'mode', 'ip_mode'}
+_FILES = {'posfile', 'momfile', 'exchange', 'dm', 'bq', 'anisotropy', 'restartfile'}
+
+
+def read_inpsd(path):
+    """Keywords of the hot-path slice; anything else is ignored, as the reference's per-module `select case`
+    passes ignore keywords of other modules."""
+    d = defaults()
+    base = os.path.dirname(os.path.abspath(path))
+    with open(path) as fh:
+        lines = fh.read().splitlines()
+    i = 0
+
+    def next_row():
+        nonlocal i
+        while i < len(lines):
+            t = lines[i].split()
+            i += 1
+            if t:
+                return t
+        raise InputError('unexpected end of %s' % path)
+
+    while i < len(lines):
+        t = lines[i].split()
+        i += 1
+        if not t or t[0].startswith(('#', '!', '%', '*')):
+            continue
+        key, v = t[0].lower(), t[1:]
+        try:
+            if key == 'simid':
+                d['simid'] = v[0][:8]
+            elif key == 'ncell':
+                d['ncell'] = tuple(int(_num(x)) for x in v[:3])
+            elif key == 'bc':
+                d['bc'] = tuple(x.upper()[0] for x in v[:3])
+            elif key == 'cell':
+                rows = [v[:3]]
+                while len(rows) < 3:
+                    rows.append(next_row()[:3])
+                d['cell'] = np.array([[_num(x) for x in r] for r in rows])
+            elif key in _FILES:
+                d[key] = os.path.normpath(os.path.join(base, v[0]))
+            elif key in _SCALAR_INT:
+                d[key] = int(_num(v[0]))
+            elif key in _SCALAR_REAL:
+                d[key] = _num(v[0])
+            elif key in _SCALAR_FLAG:
+                d[key] = _flag(v[0])
+            elif key in ('hfield', 'ip_hfield'):
+                d[key] = tuple(_num(x) for x in v[:3])
+            elif key == 'ip_nphase':          # rows: nstep  Temp  timestep  damping   (inputhandler.f90:788-850)
+                n = int(_num(v[0]))
+                d['ip_nphase'] = []
+                for _ in range(n):
+                    r = next_row()
+                    d['ip_nphase'].append((int(_num(r[0])), _num(r[1]), _num(r[2]), _num(r[3])))
+            elif key == 'ip_mcanneal':        # rows: nsweeps  Temp                      (inputhandler.f90:887-915)
+                n = int(_num(v[0]))
+                d['ip_mcanneal'] = []
+                for _ in range(n):
+                    r = next_row()
+                    d['ip_mcanneal'].append((int(_num(r[0])), _num(r[1])))
+            elif key == 'ntraj':              # rows: atom  step  buffer                 (prn_trajectories.f90:476-495)
+                n = int(_num(v[0]))
+                d['trajectories'] = []
+                for _ in range(n):
+                    r = next_row()
+                    d['trajectories'].append((int(_num(r[0])), int(_num(r[1])), int(_num(r[2]))))
+            elif key == 'map_multiple':
+                d['map_multiple'] = _flag(v[0]) in ('T', 'Y')
+        except (IndexError, ValueError) as exc:
+            raise InputError('cannot read keyword %s in %s: %s' % (key, path, exc))
+    if d['ipsdealgh'] == -1:
+        d['ipsdealgh'] = d['sdealgh']             # uppasd.f90:885
+    return d
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# structure files
+# ---------------------------------------------------------------------------------------------------------------
+def read_posfile(path, cell, posfiletype='C'):
+    """bas(3,NA) in Cartesian units of the lattice constant, atype(NA)."""
+    rows = _data_rows(path)
+    na = max(int(r[0]) for r in rows)
+    bas = np.zeros((3, na))
+    atype = np.zeros(na, dtype=np.int32)
+    for r in rows:
+        i = int(r[0]) - 1
+        p = np.array([_num(x) for x in r[2:5]])
+        bas[:, i] = p[0] * cell[0] + p[1] * cell[1] + p[2] * cell[2] if posfiletype == 'D' else p
+        atype[i] = int(r[1])
+    return bas, atype
+
+
+def read_momfile(path, na, landeg_glob=2.0):
+    """ammom(NA), aemom(3,NA) normalised like read_moments does, Landeg(NA)."""
+    ammom = np.zeros(na)
+    aemom = np.zeros((3, na))
+    for r in _data_rows(path):
+        i = int(r[0]) - 1
+        ammom[i] = _num(r[2])
+        e = np.array([_num(x) for x in r[3:6]])
+        aemom[:, i] = e / np.sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2])
+    return ammom, aemom, np.full(na, landeg_glob)
+
+
+def read_pairfile(path, atype, bas, cell, maptype, posfiletype, ncomp):
+    """Shell table of a pair interaction file: nn(NT), redcoord(NT,maxshell,3), xc(ncomp,NT,maxshell),
+    nntype(NT,maxshell).  A later line that repeats a shell vector (within 1e-5 squared) overwrites its value."""
+    nt = int(atype.max())
+    shells = [[] for _ in range(nt)]
+    for r in _data_rows(path):
+        isite, jsite = int(r[0]), int(r[1])
+        rt = [_num(x) for x in r[2:5]]
+        val = [_num(x) for x in r[5:5 + ncomp]]
+        if maptype == 2:      # bgfm style: vector between the two sites + cell translation (getNeighVec)
+            vec = np.array([bas[a, jsite - 1] - bas[a, isite - 1] + cell[0][a] * rt[0] + cell[1][a] * rt[1] + cell[2][a] * rt[2]
+                            for a in range(3)])
+        elif posfiletype == 'D':
+            vec = np.array([rt[0] * cell[0][a] + rt[1] * cell[1][a] + rt[2] * cell[2][a] for a in range(3)])
+        else:
+            vec = np.array(rt)
+        lst = shells[int(atype[isite - 1]) - 1]
+        for ent in lst:
+            if ((vec - ent[0]) ** 2).sum() < 1.0e-5:
+                ent[1] = val
+                break
+        else:
+            lst.append([vec, val, int(atype[jsite - 1])])
+    nn = np.array([len(s) for s in shells], dtype=np.int32)
+    ms = max(1, int(nn.max()))
+    red = np.zeros((nt, ms, 3))
+    xc = np.zeros((ncomp, nt, ms))
+    nntype = np.zeros((nt, ms), dtype=np.int32)
+    for t, lst in enumerate(shells):
+        for s, (vec, val, jt) in enumerate(lst):
+            red[t, s] = vec
+            xc[:, t, s] = val
+            nntype[t, s] = jt
+    return nn, red, xc, nntype
+
+
+def read_kfile(path, na):
+    """anisotropytype(NA), anisotropy(NA,6) = K1, K2, ex, ey, ez, ratio."""
+    atyp = np.zeros(na, dtype=np.int32)
+    an = np.zeros((na, 6))
+    for r in _data_rows(path)[:na]:
+        i = int(r[0]) - 1
+        atyp[i] = int(r[1])
+        an[i] = [_num(x) for x in r[2:8]]
+    return atyp, an
+
+
+def read_restart(path, natom, mensemble):
+    """restart.<simid>.out -> rstep, emom(3,N,M), mmom(N,M)."""
+    emom = np.zeros((3, natom, mensemble), order='F')
+    mmom = np.zeros((natom, mensemble), order='F')
+    rstep = 0
+    for r in _data_rows(path):
+        it, k, i = int(r[0]), int(r[1]) - 1, int(r[2]) - 1
+        rstep = it
+        mmom[i, k] = _num(r[3])
+        emom[:, i, k] = [_num(x) for x in r[4:7]]
+    return rstep, emom, mmom
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Fortran edit descriptors
+# ---------------------------------------------------------------------------------------------------------------
+def es16_8(x):
+    """ES16.8 like gfortran prints it (three-digit exponents drop the E)."""
+    s = '%16.8E' % x
+    mant, exp = s.split('E')
+    e = int(exp)
+    if abs(e) > 99:
+        return ('%s%+04d' % (mant, e)).rjust(16)
+    return s
+
+
+def _row(first, vals):
+    return first + ''.join(es16_8(v) for v in vals) + '\n'
+
+
+class OutputFiles:
+    """The measurement files of one run directory (append mode like the reference; truncated when the run starts)."""
+
+    def __init__(self, directory, simid):
+        self.dir, self.simid = directory, simid.strip()
+        self._started = set()
+
+    def _open(self, name):
+        path = os.path.join(self.dir, name)
+        mode = 'a' if name in self._started else 'w'
+        self._started.add(name)
+        return open(path, mode)
+
+    def averages(self, rows):
+        """rows: (iter, mx, my, mz, m, mstdv) -- prn_avrg, format 10004 = (i8,6es16.8)"""
+        name = 'averages.%s.out' % self.simid
+        new = name not in self._started
+        with self._open(name) as fh:
+            if new:
+                fh.write('%8s%16s%16s%16s%16s%16s\n' % ('#Iter', '<M>_x', '<M>_y', '<M>_z', '<M>', 'M_{stdv}'))
+            for r in rows:
+                fh.write(_row('%8d' % r[0], r[1:]))
+
+    def cumulants(self, row):
+        """(count, <M>, <M^2>, <M^4>, U, chi, Cv, <E>, <E_exc>, <E_lsf>) -- calc_and_print_cumulant, (i8,10es16.8)"""
+        name = 'cumulants.%s.out' % self.simid
+        new = name not in self._started
+        with self._open(name) as fh:
+            if new:
+                fh.write('%8s%16s%16s%16s%16s%16s%16s%16s%16s%16s\n' % ('#Iter', '<M>', '<M^2>', '<M^4>', 'U_{Binder}', '\\chi',
+                                                                        'C_v(tot)', '<E>', '<E_{exc}>', '<E_{lsf}>'))
+            fh.write(_row('%8d' % row[0], row[1:]))
+
+    def totenergy(self, it, terms):
+        """terms: dict with tot, exc, ani, dm, bq, ext (mRy per atom, ensemble means) -- energy.f90:404-430, (i8,13es16.8)"""
+        name = 'totenergy.%s.out' % self.simid
+        new = name not in self._started
+        with self._open(name) as fh:
+            if new:
+                fh.write('%8s' % '#Iter' + ''.join('%16s' % h for h in ('Tot', 'Exc', 'Ani', 'DM', 'PD', 'BiqDM', 'BQ', 'Dip',
+                                                                           'Zeeman', 'LSF', 'Chir', 'Ring', 'SA')) + '\n')
+            z = 0.0
+            fh.write(_row('%8d' % it, [terms['tot'], terms['exc'], terms['ani'], terms['dm'], z, z, terms['bq'], z,
+                                       terms['ext'], z, z, z, z]))
+
+    def trajectory(self, atom, ens, rows):
+        """rows: (iter, ex, ey, ez, m) -- prn_traj, format 10002 = (i8,2x,i8,2x,2x,4es16.8)"""
+        name = 'trajectory.%s.%03d.%1d.out' % (self.simid, atom, ens)
+        with self._open(name) as fh:
+            for r in rows:
+                fh.write('%8d  %8d    ' % (r[0], atom) + ''.join(es16_8(v) for v in r[1:]) + '\n')
+
+    def restart(self, mstep, mode, emom, mmom):
+        """restart.<simid>.out -- prn_mag_conf_iter type 'R' (restart.f90:186-246), rewritten every time"""
+        n, m = mmom.shape
+        with open(os.path.join(self.dir, 'restart.%s.out' % self.simid), 'w') as fh:
+            fh.write('#' * 80 + '\n')
+            fh.write('# File type: R\n# Simulation type: %s\n' % mode)
+            fh.write('# Number of atoms:  %8d\n# Number of ensembles:  %8d\n' % (n, m))
+            fh.write('#' * 80 + '\n')
+            fh.write('%8s%8s%8s%16s%16s%16s%16s\n' % ('# iter', 'ens', 'iatom', '|Mom|', 'M_x', 'M_y', 'M_z'))
+            for k in range(m):
+                for i in range(n):
+                    fh.write('%8d%8d%8d  ' % (mstep, k + 1, i + 1) + es16_8(mmom[i, k]) + es16_8(emom[0, i, k])
+                             + es16_8(emom[1, i, k]) + es16_8(emom[2, i, k]) + '\n')
+
+    def coord(self, coord, atype, anumb):
+        """coord.<simid>.out -- printhamiltonian / geometry output: index, x, y, z, type, number in cell"""
+        with open(os.path.join(self.dir, 'coord.%s.out' % self.simid), 'w') as fh:
+            for i in range(coord.shape[1]):
+                fh.write('%7d%12.6f%12.6f%12.6f%6d%6d\n' % (i + 1, coord[0, i], coord[1, i], coord[2, i], atype[i], anumb[i]))
+
+
+def read_out(path):
+    """rows of a .out file as lists of floats, comment lines skipped (what tests/extractoutput.py does)"""
+    out = []
+    with open(path) as fh:
+        for line in fh:
+            t = line.split()
+            if not t or t[0].startswith('#'):
+                continue
+            out.append([float(x) for x in t])
+    return out

@@ -48,6 +48,8 @@ SYMBOLS = {
     'asd_sd_steps': (C.c_int, [vp, C.c_long, C.c_long]),
     'asd_mc_sweeps': (C.c_int, [vp, C.c_char, C.c_long, C.c_long, C.c_double, C.c_double, vp]),
     'asd_measure': (C.c_int, [vp, vp, vp]),
+    'asd_energy_terms': (C.c_int, [vp, vp]),
+    'asd_get_atoms': (C.c_int, [vp, C.c_int, vp, vp]),
     'asd_time_sd_steps': (C.c_int, [vp, C.c_long, C.c_long, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     'asd_time_mc_sweeps': (C.c_int, [vp, C.c_char, C.c_long, C.c_double, C.POINTER(C.c_float)]),
     'asd_launch_count': (C.c_long, [vp]),

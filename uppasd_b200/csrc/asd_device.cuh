@@ -896,6 +896,133 @@ moment_final_kernel(int nblk, const double* __restrict__ part, double* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// Term-resolved energy (calc_energy, source/Hamiltonian/energy.f90:180-340): per site
+//   exc = -1/2 m.B_xc, dm = -1/2 m.B_dm, bq = -1/4 m.B_bq, ani = -1/2 m.B_ani, ext = -m.B_ext   (update_ene factors)
+// written as rows [k][5][Npad] (order: exc, ani, dm, bq, ext = the columns of totenergy.*.out that this path has);
+// reduced per ensemble by reduce_rows_*.  Measurement-only kernel: plain gathers.
+// ------------------------------------------------------------------------------------------------
+template <bool REDUCED>
+__global__ void __launch_bounds__(256)
+energy_terms_kernel(const __grid_constant__ Tables t, const SpinVec* __restrict__ cur, double* __restrict__ rows) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   const int k = blockIdx.y;
+   if (i >= t.Npad) return;
+   double* __restrict__ out = rows + (size_t)k * 5 * t.Npad + i;
+   const int o = __ldg(t.orig + i);
+   if (o < 0) { for (int a = 0; a < 5; a++) out[(size_t)a * t.Npad] = 0.0; return; }
+   const int ih = REDUCED ? __ldg(t.ham + i) : 0;
+   const int Npad = t.Npad;
+   const SpinVec* __restrict__ S = cur + (size_t)k * t.Npad;
+   const SpinVec own = S[i];
+   const double ox = own.x * own.m, oy = own.y * own.m, oz = own.z * own.m;
+   double f[3] = {0.0, 0.0, 0.0};
+   {  // Heisenberg
+      const int n = REDUCED ? __ldg(t.lsize + ih) : t.z;
+      for (int j = 0; j < n; j++) {
+         const SpinVec v = S[__ldg(t.nl + (size_t)j * Npad + i)];
+         const double cj = REDUCED ? __ldg(t.cp + (size_t)ih * t.z + j) : __ldg(t.cp + (size_t)j * Npad + i);
+         f[0] = fma(cj, v.x * v.m, f[0]); f[1] = fma(cj, v.y * v.m, f[1]); f[2] = fma(cj, v.z * v.m, f[2]);
+      }
+   }
+   out[0] = -0.5 * (ox * f[0] + oy * f[1] + oz * f[2]);
+   f[0] = f[1] = f[2] = 0.0;
+   if (t.zdm > 0) {
+      const int n = REDUCED ? __ldg(t.dmsize + ih) : t.zdm;
+      for (int j = 0; j < n; j++) {
+         const SpinVec v = S[__ldg(t.dml + (size_t)j * Npad + i)];
+         double Dx, Dy, Dz;
+         if (REDUCED) { const double* __restrict__ d = t.dmv + ((size_t)ih * t.zdm + j) * 3; Dx = d[0]; Dy = d[1]; Dz = d[2]; }
+         else { const size_t q = (size_t)j * Npad + i, s = (size_t)t.zdm * Npad; Dx = __ldg(t.dmv + q); Dy = __ldg(t.dmv + s + q); Dz = __ldg(t.dmv + 2 * s + q); }
+         const double mx = v.x * v.m, my = v.y * v.m, mz = v.z * v.m;
+         f[0] = f[0] + Dz * my - Dy * mz; f[1] = f[1] + Dx * mz - Dz * mx; f[2] = f[2] + Dy * mx - Dx * my;
+      }
+   }
+   out[(size_t)2 * Npad] = -0.5 * (ox * f[0] + oy * f[1] + oz * f[2]);
+   f[0] = f[1] = f[2] = 0.0;
+   if (t.zbq > 0) {
+      const int n = REDUCED ? __ldg(t.bqsize + ih) : t.zbq;
+      for (int j = 0; j < n; j++) {
+         const SpinVec v = S[__ldg(t.bql + (size_t)j * Npad + i)];
+         const double jb = REDUCED ? __ldg(t.jbq + (size_t)ih * t.zbq + j) : __ldg(t.jbq + (size_t)j * Npad + i);
+         const double mx = v.x * v.m, my = v.y * v.m, mz = v.z * v.m;
+         const double c = 2.0 * jb * (mx * ox + my * oy + mz * oz);
+         f[0] = fma(c, mx, f[0]); f[1] = fma(c, my, f[1]); f[2] = fma(c, mz, f[2]);
+      }
+   }
+   out[(size_t)3 * Npad] = -0.25 * (ox * f[0] + oy * f[1] + oz * f[2]);
+   f[0] = f[1] = f[2] = 0.0;
+   if (t.do_aniso) {
+      const int ta = __ldg(t.taniso + i);
+      if (ta == 1 || ta == 2 || ta == 7) {
+         const double k1 = __ldg(t.kaniso + i), k2 = __ldg(t.kaniso + Npad + i);
+         if (ta == 1 || ta == 7) {
+            const double ex = __ldg(t.eaniso + i), ey = __ldg(t.eaniso + Npad + i), ez = __ldg(t.eaniso + 2 * (size_t)Npad + i);
+            const double tt1 = ox * ex + oy * ey + oz * ez;
+            const double tt3 = 2.0 * tt1 * (k1 + 2.0 * k2 * (1.0 - tt1 * tt1));
+            f[0] -= tt3 * ex; f[1] -= tt3 * ey; f[2] -= tt3 * ez;
+         }
+         if (ta == 2 || ta == 7) {
+            const double x2 = ox * ox, y2 = oy * oy, z2 = oz * oz;
+            const double s = (ta == 7) ? __ldg(t.sb + i) : 1.0;
+            f[0] += s * (2.0 * k1 * ox * (y2 + z2) + 2.0 * k2 * ox * (y2 * z2));
+            f[1] += s * (2.0 * k1 * oy * (z2 + x2) + 2.0 * k2 * oy * (z2 * x2));
+            f[2] += s * (2.0 * k1 * oz * (x2 + y2) + 2.0 * k2 * oz * (x2 * y2));
+         }
+      }
+   }
+   out[(size_t)1 * Npad] = -0.5 * (ox * f[0] + oy * f[1] + oz * f[2]);
+   double h[3];
+   ext_field(t, i, k, h);
+   out[(size_t)4 * Npad] = -(ox * h[0] + oy * h[1] + oz * h[2]);
+}
+
+// per-ensemble sums of R rows of length Npad: rows[k][R][Npad] -> part[k][R][gridDim.x] -> out[k][R] (fixed tree)
+__global__ void __launch_bounds__(256)
+reduce_rows_partial_kernel(int Npad, int R, const double* __restrict__ rows, double* __restrict__ part) {
+   __shared__ double red[8];
+   const int r = blockIdx.y, k = blockIdx.z;
+   const double* __restrict__ src = rows + ((size_t)k * R + r) * Npad;
+   double s = 0.0;
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Npad; i += gridDim.x * blockDim.x) s += src[i];
+   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+   s = warp_sum(s);
+   if (l == 0) red[w] = s;
+   __syncthreads();
+   if (w == 0) {
+      double v = (l < 8) ? red[l] : 0.0;
+      v = warp_sum(v);
+      if (l == 0) part[((size_t)k * R + r) * gridDim.x + blockIdx.x] = v;
+   }
+}
+
+__global__ void __launch_bounds__(256)
+reduce_rows_final_kernel(int nblk, const double* __restrict__ part, double* __restrict__ out) {
+   __shared__ double red[8];
+   const double* __restrict__ src = part + (size_t)blockIdx.x * nblk;
+   double s = 0.0;
+   for (int b = threadIdx.x; b < nblk; b += blockDim.x) s += src[b];
+   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+   s = warp_sum(s);
+   if (l == 0) red[w] = s;
+   __syncthreads();
+   if (w == 0) {
+      double v = (l < 8) ? red[l] : 0.0;
+      v = warp_sum(v);
+      if (l == 0) out[blockIdx.x] = v;
+   }
+}
+
+// selected atoms (trajectory measurements, prn_trajectories.f90): out[k][n][4] = {ex, ey, ez, m} of atom slots sl[n]
+__global__ void gather_atoms_kernel(int n, int M, size_t Npad, const int* __restrict__ sl, const SpinVec* __restrict__ cur,
+                                    double* __restrict__ out) {
+   const int q = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+   if (q >= n) return;
+   const SpinVec v = cur[(size_t)k * Npad + sl[q]];
+   double* o = out + ((size_t)k * n + q) * 4;
+   o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.m;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Layout conversion between the host's Fortran arrays and the packed device order.
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_kernel(int N, int Nown, int Npad, int M, const int* __restrict__ orig, const double* __restrict__ emom,

@@ -219,6 +219,33 @@ static int build_tiles(asd_engine* e, Layout& L) {
    return 0;
 }
 
+// external_field(3,N,M) of the engine -> layout: a uniform field rides in the kernel parameters, anything else
+// is permuted into device order.  Callable on a committed layout (the drivers switch between the initial-phase and
+// the measurement-phase field, sd_driver.f90:122 / :406).
+static int apply_external_field(asd_engine* e, Layout& L) {
+   const int N = e->N, M = e->M;
+   Tables& t = L.t;
+   t.ext_uniform = 1; t.hext[0] = t.hext[1] = t.hext[2] = 0.0; t.ext = nullptr;
+   if (e->ext.empty()) return 0;
+   bool uni = true;
+   for (size_t q = 0; q < (size_t)N * M && uni; q++)
+      for (int a = 0; a < 3; a++) if (e->ext[3 * q + a] != e->ext[a]) { uni = false; break; }
+   if (uni) { for (int a = 0; a < 3; a++) t.hext[a] = e->ext[a]; return 0; }
+   int r = host_orig(e, L);
+   if (r) return r;
+   const long Npad = L.Npad;
+   std::vector<double> h((size_t)M * 3 * Npad, 0.0);
+   for (int k = 0; k < M; k++)
+      for (long s = 0; s < Npad; s++) {
+         const int o = L.orig[s];
+         if (o < 0) continue;
+         for (int a = 0; a < 3; a++) h[((size_t)k * 3 + a) * Npad + s] = e->ext[a + 3 * ((size_t)o + (size_t)N * k)];
+      }
+   if ((r = L.d_ext.upload(h, e->stream))) return r;
+   t.ext_uniform = 0; t.ext = L.d_ext.p;
+   return 0;
+}
+
 // shared tail of layout construction: shared-memory plan, per-atom arrays (anisotropy, fields) in device order
 static int finish_layout(asd_engine* e, Layout& L) {
    const int N = e->N, NH = e->NH, M = e->M;
@@ -287,15 +314,7 @@ static int finish_layout(asd_engine* e, Layout& L) {
       if ((r = permute(e->sb, 1, false, L.d_sb))) return r;
       t.do_aniso = 1; t.taniso = L.d_taniso.p; t.eaniso = L.d_eaniso.p; t.kaniso = L.d_kaniso.p; t.sb = L.d_sb.p;
    }
-   // external field: uniform?
-   t.ext_uniform = 1; t.hext[0] = t.hext[1] = t.hext[2] = 0.0;
-   if (!e->ext.empty()) {
-      bool uni = true;
-      for (size_t q = 0; q < (size_t)N * M && uni; q++)
-         for (int a = 0; a < 3; a++) if (e->ext[3 * q + a] != e->ext[a]) { uni = false; break; }
-      if (uni) { for (int a = 0; a < 3; a++) t.hext[a] = e->ext[a]; }
-      else { t.ext_uniform = 0; if ((r = permute(e->ext, 3, true, L.d_ext))) return r; t.ext = L.d_ext.p; }
-   }
+   if ((r = apply_external_field(e, L))) return r;
    if (!e->btorque.empty()) { if ((r = permute(e->btorque, 3, true, L.d_btorque))) return r; t.btorque = L.d_btorque.p; }
    return 0;
 }
@@ -692,7 +711,7 @@ static int sd_steps(asd_engine* e, long nsteps, long first_step, cudaEvent_t* ev
 
 static int measure(asd_engine* e, Layout& L, double* msum, double* energy) {
    int r;
-   const int nblk = std::min(296, (L.Npad + 255) / 256);
+   const int nblk = std::min(1184, (L.Npad + 255) / 256);
    if ((r = e->part.alloc((size_t)e->M * nblk * 4))) return r;
    if ((r = e->red.alloc((size_t)e->M * 4))) return r;
    dim3 g, b;
@@ -856,7 +875,13 @@ int asd_set_anisotropy(asd_engine* e, const int* taniso, const double* eaniso, c
 int asd_set_external_field(asd_engine* e, const double* f) {
    if (e->N == 0) return fail(-2, "asd_set_system must be called first");
    if (f) e->ext.assign(f, f + 3 * (size_t)e->N * e->M); else e->ext.clear();
-   e->committed = false;
+   if (e->committed) {
+      CU(cudaSetDevice(e->device));
+      CU(cudaStreamSynchronize(e->stream));
+      int r = apply_external_field(e, e->sd);
+      if (r) return r;
+      if (e->mc_built && (r = apply_external_field(e, e->mc))) return r;
+   }
    return 0;
 }
 int asd_set_torque(asd_engine* e, const double* f) {
@@ -961,7 +986,7 @@ int asd_effective_field(asd_engine* e, double* beff, double* beff1, double* beff
    CU(cudaStreamSynchronize(e->stream));
    if (energy) {
       // reuse the reduction path without recomputing the field
-      const int nblk = std::min(296, (L.Npad + 255) / 256);
+      const int nblk = std::min(1184, (L.Npad + 255) / 256);
       if ((r = e->part.alloc((size_t)e->M * nblk * 4))) return r;
       if ((r = e->red.alloc((size_t)e->M * 4))) return r;
       moment_partial_kernel<<<dim3(nblk, e->M), 256, 0, e->stream>>>(L.Npad, L.d_orig.p, e->cur.p, e->esite.p, e->part.p);
@@ -1040,6 +1065,56 @@ int asd_time_mc_sweeps(asd_engine* e, char mode, long nsweeps, double temperatur
    if (total_ms) CU(cudaEventElapsedTime(total_ms, a, b));
    cudaEventDestroy(a); cudaEventDestroy(b);
    return r;
+}
+
+int asd_energy_terms(asd_engine* e, double* terms) {
+   CU(cudaSetDevice(e->device));
+   int r = ensure_layout(e, e->state_layout == 2 ? 2 : 1);
+   if (r) return r;
+   Layout& L = (e->state_layout == 2) ? e->mc : e->sd;
+   const int R = 5, nblk = std::min(592, (L.Npad + 255) / 256);
+   DevBuf<double> rows, part, out;
+   if ((r = rows.alloc((size_t)e->M * R * L.Npad))) return r;
+   if ((r = part.alloc((size_t)e->M * R * nblk))) return r;
+   if ((r = out.alloc((size_t)e->M * R))) return r;
+   dim3 g, b;
+   launch_cfg(L.Npad, e->M, g, b);
+   if (L.reduced) energy_terms_kernel<true><<<g, b, 0, e->stream>>>(L.t, e->cur.p, rows.p);
+   else energy_terms_kernel<false><<<g, b, 0, e->stream>>>(L.t, e->cur.p, rows.p);
+   reduce_rows_partial_kernel<<<dim3(nblk, R, e->M), 256, 0, e->stream>>>(L.Npad, R, rows.p, part.p);
+   reduce_rows_final_kernel<<<e->M * R, 256, 0, e->stream>>>(nblk, part.p, out.p);
+   e->launches += 3;
+   CU(cudaGetLastError());
+   std::vector<double> h((size_t)e->M * R);
+   CU(cudaMemcpyAsync(h.data(), out.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   CU(cudaStreamSynchronize(e->stream));
+   const double fcinv = e->mub / e->mry;   // energy.f90: energies printed in mRy per atom
+   for (size_t q = 0; q < h.size(); q++) terms[q] = h[q] * fcinv / e->N;
+   return 0;
+}
+
+int asd_get_atoms(asd_engine* e, int n, const int* atoms, double* out) {
+   CU(cudaSetDevice(e->device));
+   if (n <= 0) return 0;
+   int r = ensure_layout(e, e->state_layout == 2 ? 2 : 1);
+   if (r) return r;
+   Layout& L = (e->state_layout == 2) ? e->mc : e->sd;
+   if ((r = host_orig(e, L))) return r;
+   std::vector<int> sl(n);
+   for (int q = 0; q < n; q++) {
+      if (atoms[q] < 1 || atoms[q] > e->N) return fail(-1, "atom %d outside 1..Natom", atoms[q]);
+      sl[q] = L.slot_of[atoms[q] - 1];
+   }
+   DevBuf<int> d_sl;
+   DevBuf<double> d_out;
+   if ((r = d_sl.upload(sl, e->stream))) return r;
+   if ((r = d_out.alloc((size_t)4 * n * e->M))) return r;
+   gather_atoms_kernel<<<dim3((n + 127) / 128, e->M), 128, 0, e->stream>>>(n, e->M, (size_t)L.Npad, d_sl.p, e->cur.p, d_out.p);
+   e->launches++;
+   CU(cudaGetLastError());
+   CU(cudaMemcpyAsync(out, d_out.p, (size_t)4 * n * e->M * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   CU(cudaStreamSynchronize(e->stream));
+   return 0;
 }
 
 int asd_set_ensemble_offset(asd_engine* e, unsigned int first_ensemble) {

@@ -137,6 +137,19 @@ class Engine:
         self._chk(self.lib.asd_measure(self.h, _p(msum), _p(en)))
         return (msum, en) if energy else msum
 
+    def energy_terms(self):
+        """(5, M): exchange, anisotropy, DM, biquadratic, Zeeman energy per atom in mRy (energy.f90 estimators)"""
+        out = np.zeros((5, self.M), order='F')
+        self._chk(self.lib.asd_energy_terms(self.h, _p(out)))
+        return out
+
+    def get_atoms(self, atoms):
+        """(4, n, M): ex, ey, ez, |m| of the 1-based atoms"""
+        a = np.ascontiguousarray(atoms, dtype=np.int32)
+        out = np.zeros((4, len(a), self.M), order='F')
+        self._chk(self.lib.asd_get_atoms(self.h, len(a), _p(a), _p(out)))
+        return out
+
     def time_sd_steps(self, nsteps, first_step=1, stages=False):
         tot = C.c_float(0)
         st = (C.c_float * 2)(0, 0)

@@ -1,0 +1,82 @@
+"""Observables of the measurement phases, accumulated on the host from the per-ensemble sums the device returns
+(asd_measure / asd_energy_terms) -- SURVEY 8 f-2.  The estimators are the reference's, not textbook ones:
+
+  averages   buffer_avrg / prn_avrg      source/Measurement/prn_averages.f90:414-456, 569-656
+  cumulants  calc_and_print_cumulant     source/Measurement/prn_averages.f90:919-1095 -- WEIGHTED running means with a
+             linearly growing weight (cumuw += 1 per sample per ensemble), U = 1 - <m^4>/(3 <m^2>^2),
+             chi = (<m^2> - <m>^2) mu_B^2 N / (k_B^2 T), C_v from the energy variance in mRy
+"""
+import numpy as np
+
+
+class Averages:
+    """Buffered <M> rows of averages.<simid>.out."""
+
+    def __init__(self, natom, buff=10):
+        self.natom, self.buff, self.rows = natom, buff, []
+
+    def sample(self, it, msum):
+        """msum(3, M) = sum_i emomM(:, i, k); returns the rows to print when the buffer is full, else None"""
+        av = np.asarray(msum, dtype=np.float64) / self.natom          # (3, M)
+        m = np.sqrt((av ** 2).sum(axis=0))                           # |<M>| per ensemble
+        mm = m.mean()
+        var = (m ** 2).mean() - mm ** 2
+        sd = 0.0 if var < 1.0e-14 else float(np.sqrt(var))           # dbl_tolerance filter (prn_averages.f90:632-636)
+        self.rows.append((it, av[0].mean(), av[1].mean(), av[2].mean(), mm, sd))
+        if len(self.rows) == self.buff:
+            return self.flush()
+        return None
+
+    def flush(self):
+        out, self.rows = self.rows, []
+        return out
+
+
+class Cumulants:
+    """Binder cumulant, susceptibility, specific heat with the reference's weighted running means."""
+
+    def __init__(self, natom, mensemble, temp, k_bolt, mub, mry, buff=10, plotenergy=0):
+        self.n, self.m, self.temp, self.kb, self.mub, self.mry = natom, mensemble, temp, k_bolt, mub, mry
+        self.buff, self.plotenergy = buff, plotenergy
+        self.cumuw = self.cumutotw = 0.0
+        self.navrg = 0
+        self.avm = self.avm2 = self.avm4 = 0.0
+        self.ave = self.ave2 = self.avexc = 0.0
+        self.binder = self.chi = self.cv = 0.0
+
+    def sample(self, msum, energy=None, exc=None):
+        """msum(3, M); energy / exc: per-ensemble total / exchange energy per atom in mRy (the values of the LAST
+        energy evaluation, as in the reference where calc_energy runs on its own cadence).  Returns the row to print
+        (count, <M>, <M^2>, <M^4>, U, chi, Cv, <E>, <E_exc>, <E_lsf>) or None."""
+        msum = np.asarray(msum, dtype=np.float64)
+        avm = avm2 = avm4 = ave = ave2 = avexc = 0.0
+        for k in range(self.m):
+            me = float(np.sqrt((msum[:, k] ** 2).sum())) / self.n
+            m2 = me * me
+            m4 = m2 * m2
+            self.cumuw += 1.0
+            w, tw = self.cumuw, self.cumutotw
+            avm = (self.avm * tw + me * w) / (tw + w)
+            avm2 = (self.avm2 * tw + m2 * w) / (tw + w)
+            avm4 = (self.avm4 * tw + m4 * w) / (tw + w)
+            self.binder = 1.0 - (avm4 / 3.0 / avm2 ** 2)
+            self.avm, self.avm2, self.avm4 = avm, avm2, avm4
+            if self.temp > 0.0:
+                self.chi = (avm2 - avm ** 2) * self.mub ** 2 * self.n / (self.kb ** 2) / self.temp
+            else:
+                self.chi = (avm2 - avm ** 2) * self.n * self.mub ** 2 / self.kb
+            if self.plotenergy > 0 and energy is not None:
+                ek = float(energy[k])
+                ave = (self.ave * tw + ek * w) / (tw + w)
+                ave2 = (self.ave2 * tw + ek * ek * w) / (tw + w)
+                avexc = (self.avexc * tw + (float(exc[k]) if exc is not None else 0.0) * w) / (tw + w)
+                self.cv = ((ave2 - ave ** 2) * self.mry ** 2 * self.n / (self.kb ** 2) / self.temp ** 2) if self.temp > 0.0 else 0.0
+                self.ave, self.ave2, self.avexc = ave, ave2, avexc
+            else:
+                self.cv = 0.0
+            self.navrg += 1
+            self.cumutotw += w
+        count = self.navrg // self.m
+        if (count - 1) % self.buff == 0:
+            return (count, self.avm, self.avm2, self.avm4, self.binder, self.chi, self.cv, self.ave, self.avexc, 0.0)
+        return None
