@@ -65,6 +65,18 @@ void cmdsim_initiateconstants_(void);
 void cmdsim_initiatefortran_(void);
 void cmdsim_measurementphase_(void);
 
+/* New sibling entries, same calling convention (every argument by reference), for the two driver loops the
+ * reference never moved behind its native boundary.  Both act on the engine that cudamdsim_initiatematrices_
+ * built from the fortrandata_* pointers and write emom / emomM / mmom back to the Fortran arrays on return.
+ *   cudamdsim_initialphase_  one phase of sd_iphase (sd_driver.f90:144-289): ipnstep(i), ipTemp(i), ipdelta_t(i),
+ *                            iplambda1(i), ipSDEalgh; first_step keys the noise.
+ *   cudamcsim_evolve_        nsweeps x mc_evolve (montecarlo.f90:44; call sites mc_driver.f90:126-132, 365-371, 518-524):
+ *                            mode 'M' / 'H', Temp, temprescale, extfield(3); *upload != 0 re-reads emom / mmom first. */
+void cudamdsim_initialphase_(unsigned int* ipnstep, double* ipTemp, double* ipdelta_t, double* iplambda1,
+                             int* ipSDEalgh, unsigned int* first_step);
+void cudamcsim_evolve_(char* mode, unsigned int* nsweeps, unsigned int* first_sweep, double* Temp,
+                       double* temprescale, double* extfield, int* upload);
+
 /* Extra inputs the reference never passes through fortrandata_* but whose Fortran semantics the engine
  * honours when given (all optional; NULL keeps the legacy behaviour of one global damping, g=2):
  *   Landeg(N), lambda1_array(N) (evolution.f90:38-44), bqlist/j_bq/bqlistsize (hamiltoniandatatype.f90:58-61). */

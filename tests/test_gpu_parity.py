@@ -184,3 +184,43 @@ def test_errors_are_loud():
     e.set_exchange(bad, S['exchange']['listsize'], S['exchange']['coup'])
     with pytest.raises(host.AsdError):
         e.commit()                     # reduced Hamiltonian with a missing neighbour
+
+
+def test_legacy_style_mc_and_initial_phase_entries():
+    """cudamcsim_evolve_ / cudamdsim_initialphase_ (new F77-style siblings of the legacy symbols) drive the same engine
+    as the explicit API: same seed -> identical states, written back into the host's Fortran arrays."""
+    from uppasd_b200 import host
+    fx, inp, S = load_golden('bccfe_cuda')
+    fh = host.FortranHost(S, orc.CONST, sdealgh=1, nstep=10, delta_t=1e-16, damping=0.5, gpu_rng_seed=77).initiate()
+    e = host.engine_from_system(S, orc.CONST, sdealgh=1, delta_t=1e-16, damping=0.5, temp=0.0, seed=77)
+    for mode in ('M', 'H'):
+        fh.mc_evolve(mode, 30, 400.0, first_sweep=1)
+        e.mc_sweeps(mode, 30, 400.0, first_sweep=1)
+        emom, emomM, mmom = e.get_moments()
+        assert np.array_equal(fh.arr['emom'], emom) and np.array_equal(fh.arr['emomM'], emomM)
+    # a thermal SD initial phase with its own step, temperature and damping, then back to the measurement parameters
+    fh.initial_phase(40, 300.0, 5e-16, 0.3, 5, first_step=1)
+    e.set_llg(5, 5e-16, landeg=S['Landeg'], lambda1=0.3, temp=300.0, seed=77)
+    e.sd_steps(40, first_step=1)
+    assert np.array_equal(fh.arr['emom'], e.get_moments()[0])
+    assert np.allclose(fh.arr['mmomi'], 1.0 / fh.arr['mmom'])
+
+
+def test_per_site_damping_temperature_and_lande_arrays():
+    """lambda1_array(N), Temp_array(N), Landeg(N) that differ from site to site (evolution.f90:38-44) take the in-kernel
+    per-site branch; T = 0 so that the comparison with the oracle is deterministic."""
+    fx, inp, S = load_golden('megatest')
+    N = S['Natom']
+    rng = np.random.default_rng(5)
+    lam = rng.uniform(0.05, 0.9, size=N)
+    lg = rng.uniform(0.8, 1.2, size=N)
+    from uppasd_b200 import host
+    for alg in (1, 5):
+        e = host.engine_from_system(S, orc.CONST, sdealgh=alg, delta_t=inp['timestep'], damping=0.1, temp=0.0)
+        e.set_llg(alg, inp['timestep'], landeg=lg, lambda1=lam, temp=np.zeros(N))
+        S2 = dict(S, Landeg=lg)
+        st = orc.SdState(S2, alg, inp['timestep'], lam)
+        e.sd_steps(60)
+        for _ in range(60):
+            st.step()
+        assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12, alg

@@ -24,6 +24,8 @@ SYMBOLS = {
     'cudamdsim_initiateconstants_': (None, []),
     'cudamdsim_initiatematrices_': (None, []),
     'cudamdsim_measurementphase_': (None, []),
+    'cudamdsim_initialphase_': (None, [vp] * 6),
+    'cudamcsim_evolve_': (None, [vp] * 7),
     'cmdsim_initiateconstants_': (None, []),
     'cmdsim_initiatefortran_': (None, []),
     'cmdsim_measurementphase_': (None, []),

@@ -199,6 +199,39 @@ void cudamdsim_measurementphase_(void) {
    if (asd_synchronize(eng)) die("synchronize");
 }
 
+// ---- new sibling entries in the same F77 style (boundaries the reference never had) ----------------
+// SD initial phase: one phase of sd_iphase (sd_driver.f90:144-289) on the engine initiated by
+// cudamdsim_initiatematrices_: nstep steps at temperature Temp with time step delta_t and damping lambda1,
+// solver ipSDEalgh (1 or 5).  The state stays on the device; emom/emomM/mmom are written back on return.
+void cudamdsim_initialphase_(unsigned int* ipnstep, double* ipTemp, double* ipdelta_t, double* iplambda1, int* ipSDEalgh,
+                             unsigned int* first_step) {
+   using namespace legacy;
+   if (!matrices_ok) { std::fprintf(stderr, "uppasd_b200: not initiated!\n"); return; }
+   const int N = eng->N;
+   std::vector<double> lam(N, *iplambda1), temp(N, *ipTemp);
+   if (asd_set_llg(eng, *ipSDEalgh, *ipdelta_t, fd.Landeg, lam.data(), temp.data(), fd.temprescale ? *fd.temprescale : 1.0,
+                   *fd.mompar, eng->seed)) die("cudamdsim_initialphase_");
+   if (asd_sd_steps(eng, (long)*ipnstep, (long)(first_step ? *first_step : 1))) die("cudamdsim_initialphase_");
+   copy_to_fortran(true);
+   // restore the measurement-phase parameters
+   std::vector<double> lam0(N, *fd.damping);
+   if (asd_set_llg(eng, eng->SDEalgh, *fd.delta_t, fd.Landeg, fd.lambda1_array ? fd.lambda1_array : lam0.data(), fd.temperature,
+                   fd.temprescale ? *fd.temprescale : 1.0, *fd.mompar, eng->seed)) die("cudamdsim_initialphase_");
+}
+
+// Monte Carlo: the body of the sweep loops of mc_iphase / mc_mphase / mc_minimal (mc_driver.f90:117-201, 310-430,
+// 516-525): nsweeps calls of mc_evolve(..., Temp, temprescale, mode, ..., emomM, emom, mmom, ..., extfield, ...) on the
+// tables handed over by fortrandata_setmatrices_.  emom / mmom are read from the host arrays when *upload != 0 (the
+// host changed them since the last call) and emom / emomM / mmom are written back on return (mc_driver.f90:215-216).
+void cudamcsim_evolve_(char* mode, unsigned int* nsweeps, unsigned int* first_sweep, double* Temp, double* temprescale,
+                       double* extfield, int* upload) {
+   using namespace legacy;
+   if (!matrices_ok) { std::fprintf(stderr, "uppasd_b200: not initiated!\n"); return; }
+   if (upload && *upload) { if (asd_set_moments(eng, fd.emom, fd.mmom, fd.mmom0)) die("cudamcsim_evolve_"); }
+   if (asd_mc_sweeps(eng, *mode, (long)*nsweeps, (long)*first_sweep, *Temp, temprescale ? *temprescale : 1.0, extfield)) die("cudamcsim_evolve_");
+   copy_to_fortran(true);
+}
+
 void cmdsim_initiateconstants_(void) { cudamdsim_initiateconstants_(); }
 void cmdsim_initiatefortran_(void) { cudamdsim_initiatematrices_(); }
 void cmdsim_measurementphase_(void) { cudamdsim_measurementphase_(); }

@@ -311,7 +311,7 @@ class FortranHost:
         mavg[0] = float(np.sqrt((m ** 2).sum(axis=0)).mean())
 
     # --- the call sequence of FortranData_Initiate + sd_mphaseCUDA ---
-    def run(self):
+    def initiate(self):
         s, a, L = self.sc, self.arr, self.lib
         r = lambda k: C.cast(C.byref(s[k]), C.c_void_p)
         L.asd_set_callbacks(*self._cbs)
@@ -327,5 +327,21 @@ class FortranHost:
         L.fortrandata_setextras_(_p(a['Landeg']), None, None, None, None, None, None, None)
         L.cudamdsim_initiateconstants_()
         L.cudamdsim_initiatematrices_()
-        L.cudamdsim_measurementphase_()
         return self
+
+    def run(self):
+        self.initiate()
+        self.lib.cudamdsim_measurementphase_()
+        return self
+
+    # --- the new sibling entries, called the way sd_iphase / mc_mphase would ---
+    def initial_phase(self, nstep, temp, delta_t, damping, sdealgh, first_step=1):
+        b = C.byref
+        self.lib.cudamdsim_initialphase_(b(C.c_uint(nstep)), b(C.c_double(temp)), b(C.c_double(delta_t)), b(C.c_double(damping)),
+                                         b(C.c_int(sdealgh)), b(C.c_uint(first_step)))
+
+    def mc_evolve(self, mode, nsweeps, temp, first_sweep=1, extfield=(0.0, 0.0, 0.0), upload=False, temprescale=1.0):
+        b = C.byref
+        ef = (C.c_double * 3)(*extfield)
+        self.lib.cudamcsim_evolve_(b(C.c_char(mode.encode())), b(C.c_uint(nsweeps)), b(C.c_uint(first_sweep)), b(C.c_double(temp)),
+                                   b(C.c_double(temprescale)), ef, b(C.c_int(1 if upload else 0)))
