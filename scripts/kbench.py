@@ -12,7 +12,7 @@ import bench  # noqa: E402
 
 def main():
     ncell = [int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (128, 128, 128))]
-    tag = ' '.join('%s=%s' % (k, os.environ.get(k, '-')) for k in ('ASD_STAGED', 'ASD_PF', 'ASD_MINB_STAGED', 'ASD_NPF'))
+    tag = ' '.join('%s=%s' % (k, os.environ.get(k, '-')) for k in ('ASD_STAGED', 'ASD_PF', 'ASD_PRELOAD', 'ASD_KEYWRAP'))
     for solver in (1, 5):
         for temp in (0.0, 300.0):
             e, n = bench.bcc_engine(ncell, solver, temp, 0.5, 1, 0, 0)

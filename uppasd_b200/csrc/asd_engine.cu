@@ -189,12 +189,15 @@ static int build_tiles(asd_engine* e, Layout& L) {
    if (t.Nown <= 0) t.Nown = L.Npad;
    const int ntile = (t.Nown + TILE - 1) / TILE;
    const int* key = L.d_okey.p ? L.d_okey.p : t.orig;
+   // lattice layouts: rotate x in the sort key so that periodic images stay next to the tile (asd_tiles.cuh)
+   const bool wrap = L.d_okey.p && e->lattice_built && e->lat.periodic[0] && e->lat.N1 >= 64 && !(std::getenv("ASD_KEYWRAP") && atoi(std::getenv("ASD_KEYWRAP")) == 0);
+   const int kna = wrap ? e->lat.NA : 0, kn1 = wrap ? e->lat.N1 : 0;
    cudaStream_t st = e->stream;
    int r;
    if ((r = L.d_ucount.alloc(ntile))) return r;
    const size_t smem = TILE_BUILD_SMEM;
    CU(cudaFuncSetAttribute(tile_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 0, 0, L.d_ucount.p, nullptr, nullptr, t.zq8);
+   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 0, 0, L.d_ucount.p, nullptr, nullptr, t.zq8, kna, kn1);
    e->launches++;
    CU(cudaGetLastError());
    std::vector<int> cnt(ntile);
@@ -205,7 +208,7 @@ static int build_tiles(asd_engine* e, Layout& L) {
    const int ucap = ((mx + 31) / 32) * 32;
    if ((r = L.d_ulist.alloc((size_t)ntile * ucap))) return r;
    if ((r = L.d_nl16.alloc((size_t)t.zq8 * Npad))) return r;
-   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 1, ucap, L.d_ucount.p, L.d_ulist.p, L.d_nl16.p, t.zq8);
+   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 1, ucap, L.d_ucount.p, L.d_ulist.p, L.d_nl16.p, t.zq8, kna, kn1);
    e->launches++;
    CU(cudaGetLastError());
    CU(cudaStreamSynchronize(st));

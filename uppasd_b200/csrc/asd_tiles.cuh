@@ -23,15 +23,27 @@ constexpr size_t TILE_BUILD_SMEM = (size_t)TILE_HASH * 4 + (size_t)TILE_UMAX * (
 // reference's own atom order (x fastest).  For a lattice this makes the neighbours that the 32 lanes of a warp
 // (one x-run of cells) read for a given shell a CONTIGUOUS run of the list -- including the part that lies in the
 // next brick -- so the shared-memory reads of the stage kernels are bank-conflict free.
-__device__ __forceinline__ unsigned long long tile_key(const int* __restrict__ ham, const int* __restrict__ orig, int slot) {
-   const int o = orig[slot];
+// Periodic wrap along x: a tile at the x-edge of the supercell reads the cells x = N1-2, N1-1 as the left neighbours
+// of x = 0 -- far away in index order, which would split the warp's run.  For lattice layouts (kna, kn1 > 0: key =
+// i0 + kna*(ix + kn1*...)) the x index is therefore rotated so that the tile's own first cell sits at kn1/2.
+struct TileKeyWrap { int kna, kn1, xref; };
+
+__device__ __forceinline__ unsigned long long tile_key(const int* __restrict__ ham, const int* __restrict__ orig, int slot,
+                                                       const TileKeyWrap& kw) {
+   int o = orig[slot];
    if (o < 0) return (0x7fffffull << 40) | (unsigned long long)(unsigned)slot;   // padding slots last
+   if (kw.kn1 > 0) {
+      const int c = o / kw.kna, kx = c % kw.kn1;
+      const int rx = (kx - kw.xref + kw.kn1 / 2 + kw.kn1) % kw.kn1;
+      o += kw.kna * (rx - kx);
+   }
    return ((unsigned long long)(unsigned)ham[slot] << 40) | (unsigned long long)(unsigned)o;
 }
 
 __global__ void __launch_bounds__(TILE)
 tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const int* __restrict__ ham, const int* __restrict__ orig,
-                   int pass, int ucap, int* __restrict__ ucount, int* __restrict__ ulist, uint4* __restrict__ nl16, int zq8) {
+                   int pass, int ucap, int* __restrict__ ucount, int* __restrict__ ulist, uint4* __restrict__ nl16, int zq8,
+                   int kna, int kn1) {
    extern __shared__ unsigned long long tsm64[];
    unsigned long long* keys = tsm64;                       // [TILE_UMAX] (pass 1)
    int* lst = (int*)(tsm64 + TILE_UMAX);                   // [TILE_UMAX] slot of each key (pass 1)
@@ -39,6 +51,8 @@ tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const 
    __shared__ int nuniq, over, nfill;
    const int tile = blockIdx.x;
    const int s = tile * TILE + threadIdx.x;
+   TileKeyWrap kw{kna, kn1, 0};
+   if (kn1 > 0) { const int o0 = orig[tile * TILE]; kw.xref = o0 >= 0 ? (o0 / kna) % kn1 : 0; }
    for (int q = threadIdx.x; q < TILE_HASH; q += TILE) tab[q] = -1;
    if (threadIdx.x == 0) { nuniq = 0; over = 0; nfill = 0; }
    __syncthreads();
@@ -68,7 +82,7 @@ tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const 
    while (np2 < cnt) np2 <<= 1;
    for (int q = threadIdx.x; q < TILE_HASH; q += TILE) {
       const int v = tab[q];
-      if (v >= 0) { const int at = atomicAdd(&nfill, 1); lst[at] = v; keys[at] = tile_key(ham, orig, v); }
+      if (v >= 0) { const int at = atomicAdd(&nfill, 1); lst[at] = v; keys[at] = tile_key(ham, orig, v, kw); }
    }
    for (int q = cnt + threadIdx.x; q < np2; q += TILE) { lst[q] = INT_MAX; keys[q] = ~0ull; }
    __syncthreads();
@@ -91,7 +105,7 @@ tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const 
    if (threadIdx.x == 0) ucount[tile] = cnt;
    if (s >= Nown) return;
    auto find = [&](int slot) -> unsigned {
-      const unsigned long long key = tile_key(ham, orig, slot);
+      const unsigned long long key = tile_key(ham, orig, slot, kw);
       int lo = 0, hi = cnt - 1;
       while (lo < hi) {
          const int mid = (lo + hi) >> 1;
