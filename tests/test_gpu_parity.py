@@ -224,3 +224,29 @@ def test_per_site_damping_temperature_and_lande_arrays():
         for _ in range(60):
             st.step()
         assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12, alg
+
+
+def test_fused_moment_sum_equals_the_standalone_reduction():
+    """asd_measure right after asd_sd_steps adds the per-tile partial sums that the corrector launch left behind;
+    asking for the energy as well takes the stand-alone reduction over the spins.  Same numbers, and both equal the
+    host-side sum of emomM."""
+    from uppasd_b200 import host
+    _, inp, S = load_golden('megatest')
+    from oracle import inputs
+    import json, os
+    from util import GOLDEN
+    fx = json.load(open(os.path.join(GOLDEN, 'megatest.json')))
+    args = list(inputs.load_fixture(fx))
+    args[0] = dict(args[0], mensemble=3)
+    S = orc.build_system(*args)
+    e = host.engine_from_system(S, orc.CONST, sdealgh=1, delta_t=inp['timestep'], damping=0.3, temp=200.0, seed=4)
+    for n in (1, 7):
+        e.sd_steps(n)
+        fused = e.measure()
+        alone, _ = e.measure(energy=True)
+        _, emomM, _ = e.get_moments()
+        assert np.allclose(fused, alone, rtol=1e-13, atol=1e-10)
+        assert np.allclose(fused, emomM.sum(axis=1), rtol=1e-13, atol=1e-10)
+    e.mc_sweeps('M', 2, 200.0)
+    after_mc = e.measure()
+    assert np.allclose(after_mc, e.get_moments()[1].sum(axis=1), rtol=1e-13, atol=1e-10)   # stale partials are not reused

@@ -113,6 +113,10 @@ struct LlgParams {
    // uniform case (per_site == 0): site-independent factors evaluated once on the host with the same IEEE
    // operations the kernel would use (division and square root are correctly rounded on both sides)
    double u_lldamp, u_dt, u_sqrtdt, u_Dk, u_Dp;
+   // fused observable: when non-null, the corrector launch also leaves sum_i emomM of every tile in
+   // msum_part[k][ntile][4] (asd_measure then only adds the per-tile partials: no second pass over the spins)
+   double* msum_part;
+   int msum_ntile;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -698,8 +702,9 @@ __device__ __forceinline__ SpinVec integrate_site(const Tables& t, const LlgPara
 //   STAGE 2: gathers from `pred`, reads own `cur`, writes the new spin to `cur` (own slot only).
 //   b2eff (Depondt only): [M][3][Npad] predictor field kept for the Heun average.
 //   STAGED: tile path (shared-memory gather list).  EDGE: boundary tiles of a slab, see EdgeParams.
+//   MSUM: the launch also leaves the per-tile sums of the new emomM in p.msum_part (corrector launches only).
 // ------------------------------------------------------------------------------------------------
-template <int SOLVER, int STAGE, bool REDUCED, bool STAGED, bool EDGE>
+template <int SOLVER, int STAGE, bool REDUCED, bool STAGED, bool EDGE, bool MSUM>
 __global__ void __launch_bounds__(256, STAGED ? ASD_MINB_STAGED : ASD_MINB)
 llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgParams p, const __grid_constant__ EdgeParams ep,
                  const TileRange tr, SpinVec* __restrict__ cur, SpinVec* __restrict__ pred, double* __restrict__ b2eff) {
@@ -715,6 +720,7 @@ llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPa
    int ih = 0, io = -1;
    bool active = i < t.Nown;
    double bs[3] = {0.0, 0.0, 0.0}, bq[3] = {0.0, 0.0, 0.0};
+   double mnew[3] = {0.0, 0.0, 0.0};   // emomM written by this thread (fused observable)
    SpinVec own;
    uint4 w[ASD_NPF];
    double* __restrict__ s3 = nullptr;
@@ -777,10 +783,30 @@ llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPa
       if (STAGE == 2) old = curk[i];
       const SpinVec o = integrate_site<SOLVER, STAGE>(t, p, i, k, io, b, own, (STAGE == 1) ? own : old, b2eff);
       if (STAGE == 1) predk[i] = o; else curk[i] = o;
+      if (MSUM) { mnew[0] = o.x * o.m; mnew[1] = o.y * o.m; mnew[2] = o.z * o.m; }
       if (EDGE) {
          const int lo = __ldg(ep.hdst_lo + i), hi = __ldg(ep.hdst_hi + i);
          if (lo >= 0) ep.peer_lo[(size_t)k * t.Npad + lo] = o;
          if (hi >= 0) ep.peer_hi[(size_t)k * t.Npad + hi] = o;
+      }
+   }
+   if (MSUM) {
+      // per-tile sum of the new emomM (fixed tree: lanes -> warps -> CTA), prn_averages.f90:437-447
+      __shared__ double red[3][8];
+      const int wp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+         double v = mnew[a];
+#pragma unroll
+         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+         if (ln == 0) red[a][wp] = v;
+      }
+      __syncthreads();
+      if (threadIdx.x < 4) {
+         double v = 0.0;
+         if (threadIdx.x < 3)
+            for (int q = 0; q < 8; q++) v += red[threadIdx.x][q];
+         p.msum_part[((size_t)k * p.msum_ntile + tile) * 4 + threadIdx.x] = v;
       }
    }
    if (EDGE) {

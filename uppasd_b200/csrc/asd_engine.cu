@@ -157,6 +157,9 @@ struct asd_engine {
    int state_layout = 0;  // 0 = none, 1 = sd, 2 = mc
    DevBuf<SpinVec> cur, pred;
    DevBuf<double> b2eff, esite, part, red;
+   DevBuf<double> msum_part;            // per-tile sums of emomM left by the last corrector launch of asd_sd_steps
+   bool msum_fresh = false;
+   int msum_ntile = 0;
    DevBuf<double> io_e, io_eM, io_m;   // staging of asd_set_moments / asd_get_moments (kept between calls)
    DevBuf<unsigned int> acc;
    long launches = 0;
@@ -523,6 +526,7 @@ static int fill_llg(asd_engine* e, Layout& L, LlgParams& p, unsigned long long s
 // buffers (pinned or pageable): they are copied with cudaMemcpyAsync on the engine's stream and packed on the device.
 static int upload_state_from(asd_engine* e, Layout& L, const double* emom, const double* mmom, const double* mmom0) {
    const size_t NM = (size_t)e->N * e->M;
+   e->msum_fresh = false;
    int r;
    if ((r = e->io_e.alloc(3 * NM))) return r;
    if ((r = e->io_m.alloc(NM))) return r;
@@ -625,22 +629,29 @@ static void allow_smem(K kernel, size_t bytes) {
    }
 }
 
-template <int SOLVER, int STAGE, bool EDGE>
-static void launch_stage_range(asd_engine* e, Layout& L, const LlgParams& p, const EdgeParams& ep, const TileRange& tr, int ntiles) {
-   if (ntiles <= 0) return;
+template <int SOLVER, int STAGE, bool EDGE, bool MSUM>
+static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, const EdgeParams& ep, const TileRange& tr, int ntiles) {
    const dim3 g(ntiles, e->M, 1), b(256, 1, 1);
    if (L.t.staged) {
       const size_t smem = L.smem_bytes + (size_t)3 * L.t.ucap * sizeof(double);
       if (L.reduced) {
-         allow_smem(llg_stage_kernel<SOLVER, STAGE, true, true, EDGE>, smem);
-         llg_stage_kernel<SOLVER, STAGE, true, true, EDGE><<<g, b, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
+         allow_smem(llg_stage_kernel<SOLVER, STAGE, true, true, EDGE, MSUM>, smem);
+         llg_stage_kernel<SOLVER, STAGE, true, true, EDGE, MSUM><<<g, b, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
       } else {
-         allow_smem(llg_stage_kernel<SOLVER, STAGE, false, true, EDGE>, smem);
-         llg_stage_kernel<SOLVER, STAGE, false, true, EDGE><<<g, b, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
+         allow_smem(llg_stage_kernel<SOLVER, STAGE, false, true, EDGE, MSUM>, smem);
+         llg_stage_kernel<SOLVER, STAGE, false, true, EDGE, MSUM><<<g, b, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
       }
-   } else if (L.reduced) llg_stage_kernel<SOLVER, STAGE, true, false, EDGE><<<g, b, L.smem_bytes, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
-   else llg_stage_kernel<SOLVER, STAGE, false, false, EDGE><<<g, b, 0, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
+   } else if (L.reduced) llg_stage_kernel<SOLVER, STAGE, true, false, EDGE, MSUM><<<g, b, L.smem_bytes, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
+   else llg_stage_kernel<SOLVER, STAGE, false, false, EDGE, MSUM><<<g, b, 0, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
    e->launches++;
+}
+
+template <int SOLVER, int STAGE, bool EDGE>
+static void launch_stage_range(asd_engine* e, Layout& L, const LlgParams& p, const EdgeParams& ep, const TileRange& tr, int ntiles) {
+   if (ntiles <= 0) return;
+   // the per-tile moment sums ride on corrector launches only
+   if (STAGE == 2 && p.msum_part != nullptr) launch_stage_range2<SOLVER, STAGE, EDGE, STAGE == 2>(e, L, p, ep, tr, ntiles);
+   else launch_stage_range2<SOLVER, STAGE, EDGE, false>(e, L, p, ep, tr, ntiles);
 }
 
 static EdgeParams edge_params(asd_engine* e, int stage, unsigned long long epoch) {
@@ -702,11 +713,20 @@ static int sd_steps(asd_engine* e, long nsteps, long first_step, cudaEvent_t* ev
    LlgParams p;
    if ((r = fill_llg(e, L, p, 0))) return r;
    if (e->slab.on && !e->slab.connected) return fail(-11, "slab: not connected to the ring neighbours");
+   const int ntile = (L.t.Nown + 255) / 256;
+   if (nsteps > 0) {
+      if ((r = e->msum_part.alloc((size_t)e->M * ntile * 4))) return r;
+      e->msum_fresh = false;
+   }
    for (long s = 0; s < nsteps; s++) {
       p.step = (unsigned long long)(first_step + s);
+      const bool last = (s == nsteps - 1);
+      p.msum_part = last ? e->msum_part.p : nullptr;   // the last corrector launch also leaves the per-tile sums of emomM
+      p.msum_ntile = ntile;
       if (e->SDEalgh == 1) { launch_stage<1, 1>(e, L, p); launch_stage<1, 2>(e, L, p); }
       else { launch_stage<5, 1>(e, L, p); launch_stage<5, 2>(e, L, p); }
    }
+   if (nsteps > 0) { e->msum_fresh = true; e->msum_ntile = ntile; }
    (void)ev;
    CU(cudaGetLastError());
    return 0;
@@ -714,6 +734,18 @@ static int sd_steps(asd_engine* e, long nsteps, long first_step, cudaEvent_t* ev
 
 static int measure(asd_engine* e, Layout& L, double* msum, double* energy) {
    int r;
+   if (!energy && msum && e->msum_fresh && e->state_layout == 1 && &L == &e->sd) {
+      // the corrector launch of the last step already reduced every tile: add the partials
+      if ((r = e->red.alloc((size_t)e->M * 4))) return r;
+      moment_final_kernel<<<e->M, 256, 0, e->stream>>>(e->msum_ntile, e->msum_part.p, e->red.p);
+      e->launches++;
+      CU(cudaGetLastError());
+      std::vector<double> h((size_t)e->M * 4);
+      CU(cudaMemcpyAsync(h.data(), e->red.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+      CU(cudaStreamSynchronize(e->stream));
+      for (int k = 0; k < e->M; k++) for (int a = 0; a < 3; a++) msum[3 * k + a] = h[4 * k + a];
+      return 0;
+   }
    const int nblk = std::min(1184, (L.Npad + 255) / 256);
    if ((r = e->part.alloc((size_t)e->M * nblk * 4))) return r;
    if ((r = e->red.alloc((size_t)e->M * 4))) return r;
@@ -746,6 +778,7 @@ static int mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, d
    if (mode != 'M' && mode != 'H') return fail(-8, "MC mode '%c' is not on this path ('M' Metropolis, 'H' heat bath)", mode);
    int r = ensure_layout(e, 2);
    if (r) return r;
+   e->msum_fresh = false;
    Layout& L = e->mc;
    McParams p;
    memset(&p, 0, sizeof p);
@@ -1038,6 +1071,7 @@ int asd_time_sd_steps(asd_engine* e, long nsteps, long first_step, float* total_
       Layout& L = e->sd;
       LlgParams p;
       if ((r = fill_llg(e, L, p, (unsigned long long)(first_step + nsteps)))) return r;
+      e->msum_fresh = false;
       cudaEvent_t c;
       CU(cudaEventCreate(&c));
       CU(cudaEventRecord(a, e->stream));
