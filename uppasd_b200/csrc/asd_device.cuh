@@ -216,10 +216,10 @@ __device__ __forceinline__ double4 ld_nc_d4(const double4* p) {
 // Heisenberg sum with explicit memory-level parallelism (hamiltonianactions.f90:461-464, same j order):
 // neighbour indices arrive as 16-byte vectors, one chunk (ASD_CHUNK slots) ahead of the gathers that use
 // them; the ASD_CHUNK 256-bit gathers of a chunk are all issued before the first FMA consumes one.
-template <bool REDUCED>
+template <bool REDUCED, int CH = ASD_CHUNK>
 __device__ __forceinline__ void exchange_chunked(const Tables& t, const SpinVec* __restrict__ S, int i, int ih,
                                                  const double* smc, double& fx, double& fy, double& fz) {
-   constexpr int CH = ASD_CHUNK, CQ = CH / 4;
+   constexpr int CQ = CH / 4;
    const size_t Npad = t.Npad;
    const int n = REDUCED ? __ldg(t.lsize + ih) : t.z;
    const int nq = (n + 3) >> 2;
@@ -379,7 +379,7 @@ __device__ __forceinline__ void prefetch_tile(const Tables& t, const SpinVec* S,
 }
 
 // EXCH = false: the Heisenberg sum was already accumulated into bs[] by the caller (staged tile path).
-template <bool REDUCED, bool EXCH = true>
+template <bool REDUCED, bool EXCH = true, int CH = ASD_CHUNK>
 __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __restrict__ S, int i, int ih,
                                            const SpinVec& own, const double* smc, const double* smd,
                                            const double* smb, double bs[3], double bq[3]) {
@@ -387,7 +387,7 @@ __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __res
    const int Npad = t.Npad;
    // ---- Heisenberg (hamiltonianactions.f90:461-464) ----
    if (!EXCH) {}
-   else if (t.nl4) exchange_chunked<REDUCED>(t, S, i, ih, smc, fx, fy, fz);
+   else if (t.nl4) exchange_chunked<REDUCED, CH>(t, S, i, ih, smc, fx, fy, fz);
    else {
       const int* __restrict__ nl = t.nl + i;
       if (REDUCED) {

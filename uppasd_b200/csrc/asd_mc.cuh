@@ -26,8 +26,15 @@ struct McParams {
    int first, count;  // device-slot range [first, first+count) of this colour class
 };
 
+#ifndef ASD_MC_MINB
+#define ASD_MC_MINB 4     // CTAs per SM the colour kernel is compiled for
+#endif
+#ifndef ASD_MC_CHUNK
+#define ASD_MC_CHUNK 4    // 256-bit gathers in flight per thread
+#endif
+
 template <bool REDUCED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, ASD_MC_MINB)
 mc_colour_kernel(const __grid_constant__ Tables t, const __grid_constant__ McParams p, SpinVec* __restrict__ cur, unsigned int* __restrict__ accepted) {
    extern __shared__ double sm[];
    const double *smc, *smd, *smb;
@@ -44,9 +51,9 @@ mc_colour_kernel(const __grid_constant__ Tables t, const __grid_constant__ McPar
    const double m = own.m;
    double bs[3], bq[3];
    // bilinear field from frozen neighbours (exchange + DM [+ uniaxial]); bq = BQ/cubic field at the CURRENT spin
-   site_field<REDUCED>(t, S, i, ih, own, smc, smd, smb, bs, bq);
+   site_field<REDUCED, true, ASD_MC_CHUNK>(t, S, i, ih, own, smc, smd, smb, bs, bq);
    double u[4];
-   uniform4(p.seed, (uint32_t)o, (uint32_t)k, p.sweep, 1u, u);
+   uniform4(p.seed, (uint32_t)o, (uint32_t)k + t.ens_offset, p.sweep, 1u, u);
    const double pi = 3.141592653589793;
    SpinVec out = own;
    if (p.mode == 'H') {
@@ -88,7 +95,7 @@ mc_colour_kernel(const __grid_constant__ Tables t, const __grid_constant__ McPar
       nx = st * cphi; ny = st * sphi; nz = ct;
    } else if (ftype == 1) {
       double g0, g1, g2;
-      gauss3(p.seed, (uint32_t)o, (uint32_t)k, p.sweep, 2u, g0, g1, g2);
+      gauss3f(p.seed, (uint32_t)o, (uint32_t)k + t.ens_offset, p.sweep, 2u, g0, g1, g2);
       // delta = (2/25) (k_B T / mu_B)^(1/5)  (montecarlo.f90:142; ignores temprescale like the reference)
       const double delta = (2.0 / 25.0) * pow(p.k_bolt * p.temperature / p.mub, 0.20);
       const double ax = own.x + g0 * delta, ay = own.y + g1 * delta, az = own.z + g2 * delta;
