@@ -899,22 +899,28 @@ moment_partial_kernel(int Npad, const int* __restrict__ orig, const SpinVec* __r
    }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 moment_final_kernel(int nblk, const double* __restrict__ part, double* __restrict__ out /*[M][4]*/) {
-   __shared__ double red[4][8];
+   // one CTA per ensemble; every thread keeps several independent 32-byte loads in flight (the partials of up to a
+   // few 10^4 tiles are summed in a fixed order: thread-strided, then lanes -> warps -> CTA)
+   __shared__ double red[4][32];
    const int k = blockIdx.x;
+   const double4* __restrict__ src = reinterpret_cast<const double4*>(part) + (size_t)k * nblk;
    double s[4] = {0, 0, 0, 0};
-   for (int b = threadIdx.x; b < nblk; b += blockDim.x)
-#pragma unroll
-      for (int a = 0; a < 4; a++) s[a] += part[((size_t)k * nblk + b) * 4 + a];
+#pragma unroll 8
+   for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+      const double4 v = src[b];
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+   }
    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
    for (int a = 0; a < 4; a++) { s[a] = warp_sum(s[a]); if (l == 0) red[a][w] = s[a]; }
    __syncthreads();
    if (w == 0) {
+      const int nw = blockDim.x >> 5;
 #pragma unroll
       for (int a = 0; a < 4; a++) {
-         double v = (l < 8) ? red[a][l] : 0.0;
+         double v = (l < nw) ? red[a][l] : 0.0;
          v = warp_sum(v);
          if (l == 0) out[k * 4 + a] = v;
       }

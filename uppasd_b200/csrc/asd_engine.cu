@@ -157,6 +157,8 @@ struct asd_engine {
    int state_layout = 0;  // 0 = none, 1 = sd, 2 = mc
    DevBuf<SpinVec> cur, pred;
    DevBuf<double> b2eff, esite, part, red;
+   double* h_red = nullptr;             // pinned host landing zone of the per-ensemble sums (4 doubles each)
+   size_t h_red_n = 0;
    DevBuf<double> msum_part;            // per-tile sums of emomM left by the last corrector launch of asd_sd_steps
    bool msum_fresh = false;
    int msum_ntile = 0;
@@ -732,16 +734,26 @@ static int sd_steps(asd_engine* e, long nsteps, long first_step, cudaEvent_t* ev
    return 0;
 }
 
+static int pinned_red(asd_engine* e, size_t n) {
+   if (e->h_red && e->h_red_n >= n) return 0;
+   if (e->h_red) cudaFreeHost(e->h_red);
+   e->h_red = nullptr; e->h_red_n = 0;
+   CU(cudaMallocHost((void**)&e->h_red, n * sizeof(double)));
+   e->h_red_n = n;
+   return 0;
+}
+
 static int measure(asd_engine* e, Layout& L, double* msum, double* energy) {
    int r;
+   if ((r = pinned_red(e, (size_t)e->M * 4))) return r;
    if (!energy && msum && e->msum_fresh && e->state_layout == 1 && &L == &e->sd) {
       // the corrector launch of the last step already reduced every tile: add the partials
       if ((r = e->red.alloc((size_t)e->M * 4))) return r;
-      moment_final_kernel<<<e->M, 256, 0, e->stream>>>(e->msum_ntile, e->msum_part.p, e->red.p);
+      moment_final_kernel<<<e->M, 1024, 0, e->stream>>>(e->msum_ntile, e->msum_part.p, e->red.p);
       e->launches++;
       CU(cudaGetLastError());
-      std::vector<double> h((size_t)e->M * 4);
-      CU(cudaMemcpyAsync(h.data(), e->red.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+      double* h = e->h_red;
+      CU(cudaMemcpyAsync(h, e->red.p, (size_t)e->M * 4 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
       CU(cudaStreamSynchronize(e->stream));
       for (int k = 0; k < e->M; k++) for (int a = 0; a < 3; a++) msum[3 * k + a] = h[4 * k + a];
       return 0;
@@ -760,11 +772,11 @@ static int measure(asd_engine* e, Layout& L, double* msum, double* energy) {
       es = e->esite.p;
    }
    moment_partial_kernel<<<dim3(nblk, e->M), 256, 0, e->stream>>>(L.Npad, L.d_orig.p, e->cur.p, es, e->part.p);
-   moment_final_kernel<<<e->M, 256, 0, e->stream>>>(nblk, e->part.p, e->red.p);
+   moment_final_kernel<<<e->M, 1024, 0, e->stream>>>(nblk, e->part.p, e->red.p);
    e->launches += 2;
    CU(cudaGetLastError());
-   std::vector<double> h((size_t)e->M * 4);
-   CU(cudaMemcpyAsync(h.data(), e->red.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   double* h = e->h_red;
+   CU(cudaMemcpyAsync(h, e->red.p, (size_t)e->M * 4 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
    CU(cudaStreamSynchronize(e->stream));
    for (int k = 0; k < e->M; k++) {
       if (msum) for (int a = 0; a < 3; a++) msum[3 * k + a] = h[4 * k + a];
@@ -859,6 +871,7 @@ void asd_destroy(asd_engine* e) {
    cudaSetDevice(e->device);
    if (e->stream) { cudaStreamSynchronize(e->stream); }
    for (int q = 0; q < e->slab.n_opened; q++) cudaIpcCloseMemHandle(e->slab.opened[q]);
+   if (e->h_red) cudaFreeHost(e->h_red);
    cudaStream_t s = e->stream;
    delete e;
    if (s) cudaStreamDestroy(s);
@@ -1026,7 +1039,7 @@ int asd_effective_field(asd_engine* e, double* beff, double* beff1, double* beff
       if ((r = e->part.alloc((size_t)e->M * nblk * 4))) return r;
       if ((r = e->red.alloc((size_t)e->M * 4))) return r;
       moment_partial_kernel<<<dim3(nblk, e->M), 256, 0, e->stream>>>(L.Npad, L.d_orig.p, e->cur.p, e->esite.p, e->part.p);
-      moment_final_kernel<<<e->M, 256, 0, e->stream>>>(nblk, e->part.p, e->red.p);
+      moment_final_kernel<<<e->M, 1024, 0, e->stream>>>(nblk, e->part.p, e->red.p);
       e->launches += 2;
       std::vector<double> h((size_t)e->M * 4);
       CU(cudaMemcpyAsync(h.data(), e->red.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
