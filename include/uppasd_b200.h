@@ -155,6 +155,16 @@ int asd_sd_steps(asd_engine* e, long nsteps, long first_step);
 int asd_mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, double temperature,
                   double temprescale, const double* extfield);
 
+/* Colouring used by asd_mc_sweeps.  layout 0: colour-major re-ordering of the atoms (greedy colouring of the actual
+ * neighbour graph; default for undecomposed engines), layout 1: lattice (brick) order with a PERIODIC colouring
+ * (colour = f(basis atom, global cell coordinates mod period)) -- always used by a slab, where it gives one halo
+ * exchange per colour and the same Markov chain for every decomposition; selectable on any device-built lattice.
+ * asd_mc_colouring reports what the next sweep uses: number of colours and (layout 1) the period in cells. */
+int asd_set_mc_layout(asd_engine* e, int layout);
+int asd_mc_colouring(asd_engine* e, int* layout, int* ncolours, int* period3);
+/* colour (0-based) of every atom of this engine, original atom order [Natom] */
+int asd_get_mc_colours(asd_engine* e, int* colour);
+
 /* On-device observables: msum(3,M) = sum_i emomM(:,i,k) (prn_averages.f90:437-447); energy[M] as above
  * (NULL to skip). */
 int asd_measure(asd_engine* e, double* msum, double* energy);
@@ -207,6 +217,8 @@ int asd_set_ensemble_offset(asd_engine* e, unsigned int first_ensemble);
  * Neighbour entries that leave the slab point at halo slots; the stage kernels of the boundary tiles store
  * their new spins directly into the ring neighbours' halo slots (peer memory over NVLink) and publish an epoch
  * flag; the next stage waits on the flags.  Noise and tilted initial moments are keyed by the global atom index.
+ * Monte Carlo sweeps on a slab visit the atoms by a periodic colouring that every slab derives from the global cell
+ * coordinates: one halo exchange per colour, fused into the boundary-tile launches in the same way.
  * Arrays passed to / returned by asd_set_moments / asd_get_moments / asd_measure are those of the local slab. */
 int asd_set_slab(asd_engine* e, int nslabs, int slab_index, int halo_planes);
 /* after asd_commit: IPC handles (asd_slab_handle_bytes() bytes) of this slab's cur / pred / flag buffers ... */

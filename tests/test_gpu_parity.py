@@ -250,3 +250,45 @@ def test_fused_moment_sum_equals_the_standalone_reduction():
     e.mc_sweeps('M', 2, 200.0)
     after_mc = e.measure()
     assert np.allclose(after_mc, e.get_moments()[1].sum(axis=1), rtol=1e-13, atol=1e-10)   # stale partials are not reused
+
+
+def test_ragged_lists_isolated_atoms_and_odd_sizes():
+    """Per-atom Hamiltonian (do_reduced N) whose neighbour lists have every length from 0 (an isolated moment that only
+    feels the external field) to z, on a system whose size is not a multiple of the warp or tile size; three
+    ensembles.  Field and both integrators against the oracle."""
+    from oracle import inputs
+    from uppasd_b200 import host
+    import json, os
+    from util import GOLDEN
+    fx = json.load(open(os.path.join(GOLDEN, 'megatest.json')))
+    args = list(inputs.load_fixture(fx))
+    args[0] = dict(args[0], do_reduced='N', ncell=(3, 3, 5), mensemble=3, hfield=(0.3, -0.2, 0.5))
+    S = orc.build_system(*args)
+    N = S['Natom']
+    assert N % 32 != 0 and S['nHam'] == N
+    rng = np.random.default_rng(12)
+    ex = S['exchange']
+    size = ex['listsize'].copy()
+    for i in range(N):
+        size[i] = rng.integers(0, size[i] + 1)
+    size[5] = 0
+    lst = ex['list'].copy(order='F')
+    coup = ex['coup'].copy(order='F')
+    for i in range(N):
+        lst[size[i]:, i] = 0
+        coup[size[i]:, i] = 0.0
+    S['exchange'] = dict(ex, list=lst, listsize=size, coup=coup)
+    e0 = rng.normal(size=(3, N, 3)); e0 /= np.sqrt((e0 ** 2).sum(axis=0))
+    S['emom'] = np.asfortranarray(e0)
+    S['emomM'] = np.asfortranarray(e0 * S['mmom'][None])
+    for alg in (1, 5):
+        e = host.engine_from_system(S, orc.CONST, sdealgh=alg, delta_t=1e-16, damping=0.4, temp=0.0)
+        beff, en = e.effective_field()
+        rb, ren = orc.effective_field(S)
+        assert np.abs(beff - rb).max() <= 1e-12 * np.abs(rb).max()
+        assert np.abs(beff[:, 5, :] - np.array([0.3, -0.2, 0.5])[:, None]).max() == 0.0      # the isolated moment
+        st = orc.SdState(S, alg, 1e-16, 0.4)
+        e.sd_steps(80)
+        for _ in range(80):
+            st.step()
+        assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12, alg

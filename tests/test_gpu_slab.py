@@ -84,7 +84,7 @@ def test_slab_errors_are_loud():
     from uppasd_b200 import host
     sl = _bcc((32, 4, 8), 1, 0.0, nslabs=2)
     with pytest.raises(host.AsdError):
-        sl[0].mc_sweeps('M', 1, 300.0)          # Monte Carlo is not decomposed yet
+        sl[0].set_mc_layout(0)                  # a slab cannot re-order its atoms colour by colour
     e = host.Engine(0)
     e.set_system(2 * 32 * 4 * 3, 1, 2, (np.arange(2 * 32 * 4 * 3, dtype=np.int32) % 2) + 1)
     e.set_slab(2, 0, 2)
@@ -112,3 +112,84 @@ def test_slab_across_devices():
             e.sd_steps(1, first_step=s + 1)
     assert np.array_equal(_gather(sl), ref.get_moments()[0])
     assert all(e.slab_status()[1] == 0 for e in sl)
+
+
+def _proper(e, col):
+    """no atom shares its colour with any atom of its neighbour list"""
+    nlist, nsize, _ = e.get_table(0)
+    for i in range(e.N):
+        nb = nlist[:nsize[i % len(nsize)] if len(nsize) < e.N else nsize[i], i] - 1
+        nb = nb[nb != i]
+        if (col[nb] == col[i]).any():
+            return False
+    return True
+
+
+@pytest.mark.parametrize('ncell', [(32, 6, 16), (12, 5, 8), (33, 4, 6)])
+def test_periodic_colouring_is_proper(ncell):
+    e = _bcc(ncell, 1, 0.0)[0]
+    e.set_mc_layout(1)
+    lay, ncol, per = e.mc_colouring()
+    assert lay == 1 and 2 <= ncol < 64
+    for a in range(3):
+        assert ncell[a] % per[a] == 0 and per[a] >= 3      # periodic directions: the period divides the extent
+    col = e.get_mc_colours()
+    assert col.min() == 0 and col.max() == ncol - 1
+    assert _proper(e, col)
+    # the colour-major layout colours the same graph (greedy on the actual lists)
+    e2 = _bcc(ncell, 1, 0.0)[0]
+    assert _proper(e2, e2.get_mc_colours())
+
+
+@pytest.mark.parametrize('mode', ['M', 'H'])
+@pytest.mark.parametrize('nslabs', [1, 2, 4])
+def test_slab_mc_matches_undecomposed(mode, nslabs):
+    """Monte Carlo on slabs: one fused halo exchange per colour; the chain is the one of the undecomposed lattice layout
+    bit for bit (global colouring, draws keyed by the global atom index)."""
+    ncell = (32, 6, 16)
+    ref = _bcc(ncell, 1, 0.0, mens=2)[0]
+    ref.set_mc_layout(1)
+    sl = _bcc(ncell, 1, 0.0, nslabs=nslabs, mens=2)
+    lay, ncol, per = ref.mc_colouring()
+    for e in sl:
+        assert e.mc_colouring() == (1, ncol, per)
+    gcol = ref.get_mc_colours()
+    assert np.array_equal(np.concatenate([e.get_mc_colours() for e in sl]), gcol)
+    done = 0
+    for n in (1, 2, 5):
+        ref.mc_sweeps(mode, n, 600.0, first_sweep=done + 1)
+        for s in range(n):
+            for e in sl:
+                e.mc_sweeps(mode, 1, 600.0, first_sweep=done + 1 + s)
+        done += n
+        a, b = _gather(sl), ref.get_moments()[0]
+        assert np.array_equal(a, b), (mode, nslabs, done, np.abs(a - b).max())
+    assert np.abs(np.linalg.norm(ref.get_moments()[0], axis=0) - 1.0).max() < 1e-12
+    for e in sl:
+        ep, err = e.slab_status()
+        assert err == 0 and ep == 1 + ncol * done
+    # SD steps continue on the same buffers after the sweeps (halos of `cur` are current)
+    ref.sd_steps(3, first_step=1)
+    for s in range(3):
+        for e in sl:
+            e.sd_steps(1, first_step=1 + s)
+    assert np.array_equal(_gather(sl), ref.get_moments()[0])
+
+
+def test_lattice_mc_layout_agrees_with_colour_major_on_observables():
+    """two different proper colourings = two Markov chains with the same stationary distribution: <|m|> at 600 K agrees
+    within the statistical error (bcc Fe, T well below Tc)."""
+    ncell = (32, 8, 8)
+    res = []
+    for layout in (0, 1):
+        e = _bcc(ncell, 1, 0.0, mens=4, seed=5 + layout)[0]
+        e.set_mc_layout(layout)
+        e.mc_sweeps('H', 300, 600.0)
+        ms = []
+        for b in range(40):
+            e.mc_sweeps('H', 10, 600.0, first_sweep=301 + 10 * b)
+            ms.append(np.linalg.norm(e.measure(), axis=0) / e.N)
+        ms = np.array(ms)                      # (40, M)
+        res.append((ms.mean(), ms.mean(axis=0).std() / np.sqrt(ms.shape[1]) + ms.std() / np.sqrt(ms.size)))
+    (m0, s0), (m1, s1) = res
+    assert abs(m0 - m1) < 5 * (s0 + s1) + 2e-3, res

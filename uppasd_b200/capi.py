@@ -49,6 +49,9 @@ SYMBOLS = {
     'asd_effective_field': (C.c_int, [vp, vp, vp, vp, vp]),
     'asd_sd_steps': (C.c_int, [vp, C.c_long, C.c_long]),
     'asd_mc_sweeps': (C.c_int, [vp, C.c_char, C.c_long, C.c_long, C.c_double, C.c_double, vp]),
+    'asd_set_mc_layout': (C.c_int, [vp, C.c_int]),
+    'asd_mc_colouring': (C.c_int, [vp, c_int_p, c_int_p, c_int_p]),
+    'asd_get_mc_colours': (C.c_int, [vp, vp]),
     'asd_measure': (C.c_int, [vp, vp, vp]),
     'asd_energy_terms': (C.c_int, [vp, vp]),
     'asd_get_atoms': (C.c_int, [vp, C.c_int, vp, vp]),

@@ -126,6 +126,13 @@ struct Slab {
    long long timeout_ticks = 8000000000LL;  // ~4 s at 1.9 GHz
 };
 
+// unit-cell stencil of a device-built table (asd_build_lattice_table), kept for the periodic colouring
+struct Stencil {
+   int maxslot = 0;
+   std::vector<int> nslot, cell_atom, cell_shift;
+   bool present() const { return maxslot > 0; }
+};
+
 struct asd_engine {
    int device = 0;
    Slab slab;
@@ -168,6 +175,10 @@ struct asd_engine {
    bool committed = false;
    // lattice description (when built on device)
    LatticeDesc lat{};
+   Stencil stencil[3];                  // exchange, DM, BQ
+   DevBuf<unsigned char> lat_col;       // [Nown] colour of every owned slot (periodic colouring, mc_tile_kernel)
+   int lat_ncol = 0, lat_period[3] = {1, 1, 1};
+   int mc_layout = -1;                  // -1: default (env ASD_MC_TILES), 0 colour-major, 1 lattice tiles
 };
 
 static void launch_cfg(int Npad, int M, dim3& grid, dim3& block) {
@@ -182,6 +193,7 @@ static int host_orig(asd_engine* e, Layout& L);
 static int slab_commit(asd_engine* e);
 static int materialise_host_tables(asd_engine* e);
 static int slab_push_state(asd_engine* e);
+static int lattice_colours(asd_engine* e);
 
 // staged tile path: gather lists + 16-bit neighbour table (asd_tiles.cuh).  Leaves t.staged = 0 when a tile would
 // need more than TILE_UMAX unique slots (layout without locality) or when switched off (ASD_STAGED=0).
@@ -591,7 +603,7 @@ static int stash_state_to_host(asd_engine* e) {
 static int ensure_layout(asd_engine* e, int want) {
    if (!e->committed) return fail(-2, "asd_commit has not been called");
    if (want == 2 && !e->mc_built) {
-      if (e->slab.on) return fail(-5, "Monte Carlo sweeps are not decomposed into slabs yet");
+      if (e->slab.on) return fail(-5, "internal: a slab runs Monte Carlo on the lattice layout");
       if (e->lattice_built) {
          // the colour-major layout is built on the host: bring the device-built tables back in the reference's shape
          if ((long)e->N > 40000000L) return fail(-5, "Monte Carlo layout of a device-built lattice is limited to 4e7 atoms per engine");
@@ -785,18 +797,69 @@ static int measure(asd_engine* e, Layout& L, double* msum, double* energy) {
    return 0;
 }
 
+// Monte Carlo on the lattice (brick) layout with a periodic colouring: the path of a slab-decomposed supercell
+// (colours are global, one halo exchange per colour).  Per colour: wait for the halos -> boundary tiles
+// with the fused halo push -> interior tiles.  Also selectable on an undecomposed device-built lattice
+// (ASD_MC_TILES=1), where it runs the very same Markov chain as any slab decomposition of that supercell.
+static int mc_sweeps_tiles(asd_engine* e, McParams& p, long nsweeps, long first_sweep) {
+   int r = ensure_layout(e, 1);
+   if (r) return r;
+   if (e->lat_ncol == 0 && (r = lattice_colours(e))) return r;
+   Layout& L = e->sd;
+   Slab& sb = e->slab;
+   if (sb.on && !sb.connected) return fail(-11, "slab: not connected to the ring neighbours");
+   const int ntile = (L.t.Nown + 255) / 256;
+   EdgeParams none;
+   memset(&none, 0, sizeof none);
+   auto launch = [&](bool edge, const EdgeParams& ep, const TileRange& tr, int ntiles) {
+      if (ntiles <= 0) return;
+      const dim3 g(ntiles, e->M), b(256);
+      if (L.reduced) {
+         if (edge) mc_tile_kernel<true, true><<<g, b, L.smem_bytes, e->stream>>>(L.t, p, ep, tr, e->lat_col.p, e->cur.p);
+         else mc_tile_kernel<true, false><<<g, b, L.smem_bytes, e->stream>>>(L.t, p, ep, tr, e->lat_col.p, e->cur.p);
+      } else {
+         if (edge) mc_tile_kernel<false, true><<<g, b, 0, e->stream>>>(L.t, p, ep, tr, e->lat_col.p, e->cur.p);
+         else mc_tile_kernel<false, false><<<g, b, 0, e->stream>>>(L.t, p, ep, tr, e->lat_col.p, e->cur.p);
+      }
+      e->launches++;
+   };
+   for (long s = 0; s < nsweeps; s++)
+      for (int c = 0; c < e->lat_ncol; c++) {
+         p.sweep = (unsigned long long)(first_sweep + s);
+         p.colour = c;
+         if (!sb.on) { launch(false, none, TileRange{0, ntile, 0}, ntile); continue; }
+         halo_wait_kernel<<<1, 1, 0, e->stream>>>(sb.flags.p, e->lat.has_lo, e->lat.has_hi, sb.epoch, sb.timeout_ticks, sb.err.p);
+         e->launches++;
+         const EdgeParams ep = edge_params(e, 2, sb.epoch + 1);
+         launch(true, ep, TileRange{0, sb.tile_a, sb.tile_b}, sb.tile_a + (ntile - sb.tile_b));
+         launch(false, none, TileRange{sb.tile_a, sb.tile_b - sb.tile_a, 0}, sb.tile_b - sb.tile_a);
+         sb.epoch += 1;
+      }
+   CU(cudaGetLastError());
+   return 0;
+}
+
+static bool mc_on_tiles(const asd_engine* e) {
+   if (!e->lattice_built) return false;
+   if (e->slab.on) return true;
+   if (e->mc_layout >= 0) return e->mc_layout == 1;
+   const char* env = std::getenv("ASD_MC_TILES");
+   return env && atoi(env) != 0;
+}
+
 static int mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, double temperature, double temprescale,
                      const double* extfield) {
    if (mode != 'M' && mode != 'H') return fail(-8, "MC mode '%c' is not on this path ('M' Metropolis, 'H' heat bath)", mode);
-   int r = ensure_layout(e, 2);
-   if (r) return r;
-   e->msum_fresh = false;
-   Layout& L = e->mc;
    McParams p;
    memset(&p, 0, sizeof p);
    p.mode = mode; p.temperature = temperature; p.temprescale = temprescale; p.k_bolt = e->k_bolt; p.mub = e->mub;
    for (int a = 0; a < 3; a++) p.extfield[a] = extfield ? extfield[a] : 0.0;
    p.seed = e->seed ^ 0x5bd1e995u;
+   e->msum_fresh = false;
+   if (mc_on_tiles(e)) return mc_sweeps_tiles(e, p, nsweeps, first_sweep);
+   int r = ensure_layout(e, 2);
+   if (r) return r;
+   Layout& L = e->mc;
    const int ncol = (int)L.colour_first.size();
    for (long s = 0; s < nsweeps; s++)
       for (int c = 0; c < ncol; c++) {
@@ -1060,6 +1123,44 @@ int asd_mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, doub
    return mc_sweeps(e, mode, nsweeps, first_sweep, temperature, temprescale, extfield);
 }
 
+int asd_set_mc_layout(asd_engine* e, int layout) {
+   if (layout != 0 && layout != 1) return fail(-1, "MC layout must be 0 (colour-major) or 1 (lattice tiles)");
+   if (layout == 1 && !e->lattice_built) return fail(-2, "the lattice MC layout needs a device-built lattice (asd_build_lattice_table)");
+   if (layout == 0 && e->slab.on) return fail(-5, "a slab runs Monte Carlo on the lattice layout only");
+   e->mc_layout = layout;
+   return 0;
+}
+
+int asd_mc_colouring(asd_engine* e, int* layout, int* ncolours, int* period3) {
+   CU(cudaSetDevice(e->device));
+   int r = mc_sweeps(e, 'M', 0, 1, 1.0, 1.0, nullptr);   // builds the layout / colouring, runs nothing
+   if (r) return r;
+   const bool tiles = mc_on_tiles(e);
+   if (layout) *layout = tiles ? 1 : 0;
+   if (ncolours) *ncolours = tiles ? e->lat_ncol : (int)e->mc.colour_first.size();
+   if (period3) for (int a = 0; a < 3; a++) period3[a] = tiles ? e->lat_period[a] : 0;
+   return 0;
+}
+
+int asd_get_mc_colours(asd_engine* e, int* colour) {
+   CU(cudaSetDevice(e->device));
+   int r = mc_sweeps(e, 'M', 0, 1, 1.0, 1.0, nullptr);
+   if (r) return r;
+   if (mc_on_tiles(e)) {
+      Layout& L = e->sd;
+      if ((r = host_orig(e, L))) return r;
+      std::vector<unsigned char> c(L.t.Nown);
+      CU(cudaMemcpy(c.data(), e->lat_col.p, c.size(), cudaMemcpyDeviceToHost));
+      for (int s = 0; s < L.t.Nown; s++) if (L.orig[s] >= 0) colour[L.orig[s]] = c[s];
+   } else {
+      Layout& L = e->mc;
+      for (size_t c = 0; c < L.colour_first.size(); c++)
+         for (int s = L.colour_first[c]; s < L.colour_first[c] + L.colour_count[c]; s++)
+            if (L.orig[s] >= 0) colour[L.orig[s]] = (int)c;
+   }
+   return 0;
+}
+
 int asd_measure(asd_engine* e, double* msum, double* energy) {
    CU(cudaSetDevice(e->device));
    int r = ensure_layout(e, e->state_layout == 2 ? 2 : 1);
@@ -1103,7 +1204,7 @@ int asd_time_sd_steps(asd_engine* e, long nsteps, long first_step, float* total_
 
 int asd_time_mc_sweeps(asd_engine* e, char mode, long nsweeps, double temperature, float* total_ms) {
    CU(cudaSetDevice(e->device));
-   int r = ensure_layout(e, 2);
+   int r = mc_sweeps(e, mode, 0, 1, temperature, 1.0, nullptr);   // builds the layout / colouring outside the timed region
    if (r) return r;
    cudaEvent_t a, b;
    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));

@@ -116,6 +116,14 @@ int asd_build_lattice_table(asd_engine* e, int kind, int NA, int N1, int N2, int
             if (same) { dedup = 1; break; }
          }
    if (dedup && sb.on) return fail(-1, "slab: supercell too small along some direction (a neighbour appears twice through the periodic wrap)");
+   {
+      Stencil& S = e->stencil[kind];
+      S.maxslot = maxslot;
+      S.nslot.assign(nslot, nslot + NA);
+      S.cell_atom.assign(cell_atom, cell_atom + (size_t)NA * maxslot);
+      S.cell_shift.assign(cell_shift, cell_shift + (size_t)3 * NA * maxslot);
+      e->lat_ncol = 0;
+   }
    DevBuf<int> d_nslot, d_catom, d_cshift;
    DevBuf<double> d_coupl;
    int r;
@@ -286,5 +294,98 @@ static int materialise_host_tables(asd_engine* e) {
       int r = asd_get_table(e, kind, H.list.data(), H.lsize.data(), H.coup.data());
       if (r) { H = HostTable(); return r; }
    }
+   return 0;
+}
+
+// Periodic colouring of a device-built lattice.  The colour of an atom depends only on its basis atom and on its
+// GLOBAL cell coordinates modulo a small period (p1, p2, p3), so every slab of a decomposed supercell derives the
+// same colouring without communication.  The quotient graph (p1*p2*p3*NA sites, edges = the union of the stencils of
+// all tables, symmetrised) is coloured greedily on the host; a proper colouring of the quotient lifts to a proper
+// colouring of the supercell as long as no stencil shift is a multiple of the period in every direction, which
+// p_a > max |shift_a| guarantees.  Periods must divide the extent of periodic directions.  Among the admissible
+// periods the one with the fewest colours wins.
+static int lattice_colours(asd_engine* e) {
+   const LatticeDesc& d = e->lat;
+   const int NA = d.NA;
+   const int Ng[3] = {d.N1, d.N2, d.slab ? d.N3g : d.N3};
+   int reach[3] = {0, 0, 0};
+   for (const Stencil& S : e->stencil) {
+      if (!S.present()) continue;
+      for (int i0 = 0; i0 < NA; i0++)
+         for (int q = 0; q < S.nslot[i0]; q++)
+            for (int a = 0; a < 3; a++) reach[a] = std::max(reach[a], std::abs(S.cell_shift[3 * (i0 * S.maxslot + q) + a]));
+   }
+   std::vector<int> cand[3];
+   for (int a = 0; a < 3; a++) {
+      if (Ng[a] == 1 || reach[a] == 0) { cand[a].push_back(1); continue; }
+      for (int p = reach[a] + 1; p <= std::min(Ng[a], 2 * reach[a] + 4); p++)
+         if (!d.periodic[a] || Ng[a] % p == 0) cand[a].push_back(p);
+      if (cand[a].empty()) {
+         // no small divisor: the whole extent is always a valid period (small supercells may alias neighbours, which
+         // only merges edges of the quotient graph)
+         if (Ng[a] > 4096) return fail(-5, "no colouring period found along direction %d (extent %d, stencil reach %d)", a + 1, Ng[a], reach[a]);
+         cand[a].push_back(Ng[a]);
+      }
+   }
+   int best_ncol = 1 << 30, best_p[3] = {1, 1, 1};
+   std::vector<unsigned char> best_col;
+   for (int p1 : cand[0]) for (int p2 : cand[1]) for (int p3 : cand[2]) {
+      const int P[3] = {p1, p2, p3};
+      const int ns = p1 * p2 * p3 * NA;
+      auto site = [&](int i0, int c1, int c2, int c3) { return ((c3 * p2 + c2) * p1 + c1) * NA + i0; };
+      std::vector<std::vector<int>> adj(ns);
+      bool ok = true;
+      for (int c3 = 0; c3 < p3 && ok; c3++) for (int c2 = 0; c2 < p2 && ok; c2++) for (int c1 = 0; c1 < p1 && ok; c1++)
+         for (int i0 = 0; i0 < NA && ok; i0++) {
+            const int u = site(i0, c1, c2, c3);
+            for (const Stencil& S : e->stencil) {
+               if (!S.present()) continue;
+               for (int q = 0; q < S.nslot[i0]; q++) {
+                  const int* sh = S.cell_shift.data() + 3 * (i0 * S.maxslot + q);
+                  const int j0 = S.cell_atom[i0 * S.maxslot + q] - 1;
+                  const int c[3] = {c1, c2, c3};
+                  int n[3];
+                  for (int a = 0; a < 3; a++) n[a] = ((c[a] + sh[a]) % P[a] + P[a]) % P[a];
+                  const int v = site(j0, n[0], n[1], n[2]);
+                  if (v == u) {
+                     // a true self-neighbour (periodic image of the atom itself in a tiny supercell) is harmless;
+                     // an alias of a different atom is not
+                     bool self = true;
+                     for (int a = 0; a < 3; a++) if (sh[a] != 0 && !(d.periodic[a] && sh[a] % Ng[a] == 0)) self = false;
+                     if (!self) ok = false;
+                     continue;
+                  }
+                  adj[u].push_back(v);
+                  adj[v].push_back(u);
+               }
+            }
+         }
+      if (!ok) continue;
+      std::vector<int> colour(ns, -1), mark;
+      int ncol = 0;
+      for (int u = 0; u < ns; u++) {
+         mark.assign(ncol + 1, 0);
+         for (int v : adj[u]) if (colour[v] >= 0) mark[colour[v]] = 1;
+         int c = 0;
+         while (c < ncol && mark[c]) c++;
+         colour[u] = c;
+         if (c == ncol) ncol++;
+      }
+      if (ncol < best_ncol && ncol < 255) {
+         best_ncol = ncol; best_p[0] = p1; best_p[1] = p2; best_p[2] = p3;
+         best_col.assign(colour.begin(), colour.end());
+      }
+   }
+   if (best_col.empty()) return fail(-5, "no periodic colouring of the lattice found");
+   DevBuf<unsigned char> cellcol;
+   int r;
+   if ((r = cellcol.upload(best_col, e->stream))) return r;
+   if ((r = e->lat_col.alloc(d.Nown))) return r;
+   lattice_colour_kernel<<<(d.Nown + 255) / 256, 256, 0, e->stream>>>(d, best_p[0], best_p[1], best_p[2], cellcol.p, e->lat_col.p);
+   e->launches++;
+   CU(cudaGetLastError());
+   CU(cudaStreamSynchronize(e->stream));
+   e->lat_ncol = best_ncol;
+   for (int a = 0; a < 3; a++) e->lat_period[a] = best_p[a];
    return 0;
 }

@@ -15,6 +15,7 @@
 // (-m_i . (m_j x D)); the reference mixes emom/emomM there (:611-616), identical for |m| = 1.
 #pragma once
 #include "asd_device.cuh"
+#include "asd_lattice.cuh"
 
 namespace asd {
 
@@ -23,7 +24,8 @@ struct McParams {
    double temperature, temprescale, k_bolt, mub;
    double extfield[3];  // mc_evolve's uniform field argument (Metropolis Zeeman term)
    unsigned long long seed, sweep;
-   int first, count;  // device-slot range [first, first+count) of this colour class
+   int first, count;  // device-slot range [first, first+count) of this colour class (colour-major layout)
+   int colour;        // colour updated by this launch (lattice layout, mc_tile_kernel)
 };
 
 #ifndef ASD_MC_MINB
@@ -33,29 +35,20 @@ struct McParams {
 #define ASD_MC_CHUNK 4    // 256-bit gathers in flight per thread
 #endif
 
+// One single-spin update of site i (device slot) of ensemble k with every neighbour frozen: returns true and the new
+// spin in `out` when the spin changes (heat bath: always; Metropolis: when the trial move is accepted).
 template <bool REDUCED>
-__global__ void __launch_bounds__(256, ASD_MC_MINB)
-mc_colour_kernel(const __grid_constant__ Tables t, const __grid_constant__ McParams p, SpinVec* __restrict__ cur, unsigned int* __restrict__ accepted) {
-   extern __shared__ double sm[];
-   const double *smc, *smd, *smb;
-   stage_couplings(t, sm, smc, smd, smb);
-   const int li = blockIdx.x * blockDim.x + threadIdx.x;
-   const int k = blockIdx.y;
-   if (li >= p.count) return;
-   const int i = p.first + li;
-   const int o = __ldg(t.orig + i);
-   if (o < 0) return;
-   const int ih = REDUCED ? __ldg(t.ham + i) : 0;
-   SpinVec* __restrict__ S = cur + (size_t)k * t.Npad;
+__device__ __forceinline__ bool mc_update_site(const Tables& t, const McParams& p, const SpinVec* __restrict__ S, int i, int k, int o,
+                                               int ih, const double* smc, const double* smd, const double* smb, SpinVec& out) {
    const SpinVec own = S[i];
    const double m = own.m;
    double bs[3], bq[3];
    // bilinear field from frozen neighbours (exchange + DM [+ uniaxial]); bq = BQ/cubic field at the CURRENT spin
    site_field<REDUCED, true, ASD_MC_CHUNK>(t, S, i, ih, own, smc, smd, smb, bs, bq);
+   out = own;
    double u[4];
-   uniform4(p.seed, (uint32_t)o, (uint32_t)k + t.ens_offset, p.sweep, 1u, u);
+   uniform4(p.seed, (uint32_t)o + t.atom_offset, (uint32_t)k + t.ens_offset, p.sweep, 1u, u);
    const double pi = 3.141592653589793;
-   SpinVec out = own;
    if (p.mode == 'H') {
       // ---- heat bath (flip_h): field = beff1 + beff2 from effective_field_single, external field from the
       //      external_field array / uniform vector of the tables (reference quirk, montecarlo.f90:231-237)
@@ -81,8 +74,7 @@ mc_colour_kernel(const __grid_constant__ Tables t, const __grid_constant__ McPar
       out.x = zcphi * zctheta * s0 - zsphi * s1 + zcphi * zstheta * s2;
       out.y = zsphi * zctheta * s0 + zcphi * s1 + zsphi * zstheta * s2;
       out.z = -zstheta * s0 + zctheta * s2;
-      S[i] = out;
-      return;
+      return true;
    }
    // ---- Metropolis: trial move (choose_random_flip) ----
    double nx, ny, nz;
@@ -95,7 +87,7 @@ mc_colour_kernel(const __grid_constant__ Tables t, const __grid_constant__ McPar
       nx = st * cphi; ny = st * sphi; nz = ct;
    } else if (ftype == 1) {
       double g0, g1, g2;
-      gauss3f(p.seed, (uint32_t)o, (uint32_t)k + t.ens_offset, p.sweep, 2u, g0, g1, g2);
+      gauss3f(p.seed, (uint32_t)o + t.atom_offset, (uint32_t)k + t.ens_offset, p.sweep, 2u, g0, g1, g2);
       // delta = (2/25) (k_B T / mu_B)^(1/5)  (montecarlo.f90:142; ignores temprescale like the reference)
       const double delta = (2.0 / 25.0) * pow(p.k_bolt * p.temperature / p.mub, 0.20);
       const double ax = own.x + g0 * delta, ay = own.y + g1 * delta, az = own.z + g2 * delta;
@@ -168,9 +160,88 @@ mc_colour_kernel(const __grid_constant__ Tables t, const __grid_constant__ McPar
    const double beta = 1.0 / p.k_bolt / (p.temprescale * p.temperature + 1.0e-15);
    if (de <= 0.0 || u[3] < exp(-beta * de)) {
       out.x = nx; out.y = ny; out.z = nz;
+      return true;
+   }
+   return false;
+}
+
+// colour-major layout: the slots [first, first+count) are one colour class
+template <bool REDUCED>
+__global__ void __launch_bounds__(256, ASD_MC_MINB)
+mc_colour_kernel(const __grid_constant__ Tables t, const __grid_constant__ McParams p, SpinVec* __restrict__ cur, unsigned int* __restrict__ accepted) {
+   extern __shared__ double sm[];
+   const double *smc, *smd, *smb;
+   stage_couplings(t, sm, smc, smd, smb);
+   const int li = blockIdx.x * blockDim.x + threadIdx.x;
+   const int k = blockIdx.y;
+   if (li >= p.count) return;
+   const int i = p.first + li;
+   const int o = __ldg(t.orig + i);
+   if (o < 0) return;
+   const int ih = REDUCED ? __ldg(t.ham + i) : 0;
+   SpinVec* __restrict__ S = cur + (size_t)k * t.Npad;
+   SpinVec out;
+   if (mc_update_site<REDUCED>(t, p, S, i, k, o, ih, smc, smd, smb, out)) {
       S[i] = out;
       if (accepted) atomicAdd(accepted, 1u);
    }
+}
+
+// Lattice (brick) layout with a periodic colouring: `col[slot]` is the colour of the atom (255 = padding); a launch
+// updates the atoms of colour p.colour of the tiles in `tr`.  This is the Monte Carlo path of a slab-decomposed
+// supercell: EDGE launches cover the boundary tiles, store every changed boundary spin into the ring neighbours'
+// halo slots as well and publish the exchange epoch -- one halo exchange per colour.
+template <bool REDUCED, bool EDGE>
+__global__ void __launch_bounds__(256, ASD_MC_MINB)
+mc_tile_kernel(const __grid_constant__ Tables t, const __grid_constant__ McParams p, const __grid_constant__ EdgeParams ep,
+               const TileRange tr, const unsigned char* __restrict__ col, SpinVec* __restrict__ cur) {
+   extern __shared__ double sm[];
+   const double *smc, *smd, *smb;
+   stage_couplings(t, sm, smc, smd, smb);
+   const int tile = ((int)blockIdx.x < tr.split) ? tr.first + (int)blockIdx.x : tr.second + ((int)blockIdx.x - tr.split);
+   const int i = tile * 256 + threadIdx.x;
+   const int k = blockIdx.y;
+   if (i < t.Nown && __ldg(col + i) == (unsigned char)p.colour) {
+      const int o = __ldg(t.orig + i);
+      const int ih = REDUCED ? __ldg(t.ham + i) : 0;
+      SpinVec* __restrict__ S = cur + (size_t)k * t.Npad;
+      SpinVec out;
+      if (mc_update_site<REDUCED>(t, p, S, i, k, o, ih, smc, smd, smb, out)) {
+         S[i] = out;
+         if (EDGE) {
+            const int lo = __ldg(ep.hdst_lo + i), hi = __ldg(ep.hdst_hi + i);
+            if (lo >= 0) ep.peer_lo[(size_t)k * t.Npad + lo] = out;
+            if (hi >= 0) ep.peer_hi[(size_t)k * t.Npad + hi] = out;
+         }
+      }
+   }
+   if (EDGE) {
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+         const unsigned int total = gridDim.x * gridDim.y;
+         if (atomicAdd(ep.ctr, 1u) == total - 1) {
+            *ep.ctr = 0;
+            __threadfence_system();
+            if (ep.flag_lo) st_release_sys(ep.flag_lo, ep.epoch);
+            if (ep.flag_hi) st_release_sys(ep.flag_hi, ep.epoch);
+         }
+      }
+   }
+}
+
+// colour of every owned slot of a lattice layout from the colouring of a small periodic cell (p1 x p2 x p3 cells)
+__global__ void lattice_colour_kernel(const LatticeDesc d, int p1, int p2, int p3, const unsigned char* __restrict__ cellcol,
+                                      unsigned char* __restrict__ col) {
+   const int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= d.Nown) return;
+   int i0, ix, iy, iz;
+   unsigned char c = 255;
+   if (lattice_unslot(d, s, i0, ix, iy, iz)) {
+      const int gz = d.z0 + iz;
+      c = cellcol[(((gz % p3) * p2 + iy % p2) * p1 + ix % p1) * d.NA + i0];
+   }
+   col[s] = c;
 }
 
 }  // namespace asd

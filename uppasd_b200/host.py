@@ -131,6 +131,21 @@ class Engine:
         ef = np.ascontiguousarray(extfield, dtype=np.float64) if extfield is not None else None
         self._chk(self.lib.asd_mc_sweeps(self.h, mode.encode(), nsweeps, first_sweep, temperature, temprescale, _p(ef)))
 
+    def set_mc_layout(self, layout):
+        self._chk(self.lib.asd_set_mc_layout(self.h, layout))
+
+    def mc_colouring(self):
+        """(layout, ncolours, period): what the next MC sweep uses"""
+        lay, nc = C.c_int(), C.c_int()
+        per = (C.c_int * 3)()
+        self._chk(self.lib.asd_mc_colouring(self.h, C.byref(lay), C.byref(nc), per))
+        return lay.value, nc.value, tuple(per)
+
+    def get_mc_colours(self):
+        col = np.full(self.N, -1, dtype=np.int32)
+        self._chk(self.lib.asd_get_mc_colours(self.h, _p(col)))
+        return col
+
     def measure(self, energy=False):
         msum = np.zeros((3, self.M), order='F')
         en = np.zeros(self.M) if energy else None
