@@ -12,11 +12,13 @@ import bench  # noqa: E402
 
 def main():
     ncell = [int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (128, 128, 128))]
-    tag = ' '.join('%s=%s' % (k, os.environ.get(k, '-')) for k in ('ASD_STAGED', 'ASD_PF', 'ASD_PRELOAD', 'ASD_KEYWRAP'))
+    tag = ' '.join('%s=%s' % (k, os.environ.get(k, '-')) for k in ('ASD_STAGED', 'ASD_RUNS', 'ASD_PF', 'ASD_KEYWRAP'))
     for solver in (1, 5):
         for temp in (0.0, 300.0):
             e, n = bench.bcc_engine(ncell, solver, temp, 0.5, 1, 0, 0)
             e.sd_steps(5)
+            if solver == 1 and temp == 0.0:
+                print('KB layout', e.layout_info(), flush=True)
             ms = e.time_sd_steps(40, first_step=6)
             s1, s2 = [], []
             for r in range(5):

@@ -57,6 +57,7 @@ SYMBOLS = {
     'asd_get_atoms': (C.c_int, [vp, C.c_int, vp, vp]),
     'asd_time_sd_steps': (C.c_int, [vp, C.c_long, C.c_long, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     'asd_time_mc_sweeps': (C.c_int, [vp, C.c_char, C.c_long, C.c_double, C.POINTER(C.c_float)]),
+    'asd_layout_info': (C.c_int, [vp, c_int_p]),
     'asd_launch_count': (C.c_long, [vp]),
     'asd_synchronize': (C.c_int, [vp]),
     'asd_build_lattice_table': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, vp, vp, vp, vp]),

@@ -83,6 +83,11 @@ struct Tables {
    const int* __restrict__ ucount;    // [ntile]
    const uint4* __restrict__ nl16;    // [zq8][Npad]
    int zq8;               // ceil(z / 8)
+   // run-compressed table of lattice layouts (asd_runs.cuh): groups of `runs` x-runs share one union row
+   int tile_slots;        // slots per tile of ulist / ucount (256; 512 or 1024 with the run kernel on super-bricks)
+   int runs;              // 0: off, else 4: the LLG stage kernels use llg_runs_kernel (4 x-runs per warp)
+   int urow;              // row stride of utab in uint2
+   const uint2* __restrict__ utab;    // [ntile * 8/R][urow]
    int pf_tiles;    // L2 bulk-prefetch distance in 256-atom tiles (0 = off)
    int cpl_param;   // 1: reduced exchange couplings live in cpl_small (kernel parameter = constant bank)
    double cpl_small[256];
@@ -167,8 +172,8 @@ __device__ __forceinline__ void gauss3(unsigned long long seed, uint32_t atom, u
 // is the single-precision-resolution Ziggurat r4_nor (source/RNG/randomnumbers.f90:330-438: a 32-bit integer hz
 // times a table entry), so 32-bit-resolution variates are what the Fortran path feeds into the same formulas.
 // Uniforms use all 32 bits (u = r 2^-32 + 2^-33, tail to 6.7 sigma).  ~5x fewer instructions than the FP64 form.
-__device__ __forceinline__ void gauss3f(unsigned long long seed, uint32_t atom, uint32_t ens, unsigned long long step,
-                                        uint32_t stream, double& g0, double& g1, double& g2) {
+__device__ __forceinline__ void gauss3f_raw(unsigned long long seed, uint32_t atom, uint32_t ens, unsigned long long step,
+                                            uint32_t stream, float& g0, float& g1, float& g2) {
    uint32_t r[4];
    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
    const uint32_t s_lo = (uint32_t)step, s_hi = (uint32_t)(step >> 32) ^ (stream << 24);
@@ -182,9 +187,15 @@ __device__ __forceinline__ void gauss3f(unsigned long long seed, uint32_t atom, 
    __sincosf(a1, &s1, &c1);
    __sincosf(a2, &s2, &c2);
    (void)s2;
-   g0 = (double)(rad1 * c1);
-   g1 = (double)(rad1 * s1);
-   g2 = (double)(rad2 * c2);
+   g0 = rad1 * c1;
+   g1 = rad1 * s1;
+   g2 = rad2 * c2;
+}
+__device__ __forceinline__ void gauss3f(unsigned long long seed, uint32_t atom, uint32_t ens, unsigned long long step,
+                                        uint32_t stream, double& g0, double& g1, double& g2) {
+   float a, b, c;
+   gauss3f_raw(seed, atom, ens, step, stream, a, b, c);
+   g0 = (double)a; g1 = (double)b; g2 = (double)c;
 }
 
 // four U[0,1) numbers (53-bit) for Monte Carlo draws
@@ -613,16 +624,20 @@ __global__ void halo_push_kernel(int Nown, int M, size_t Npad, const SpinVec* __
 // moment update (STAGE 2).  b = effective field at the spin `own` the field was evaluated with; c0 = spin at
 // time t.  Returns the spin to store (pred in stage 1, cur in stage 2).
 // ------------------------------------------------------------------------------------------------
+// gpre: the three N(0,1) numbers of this (atom, ensemble, step) when the caller already drew them (asd_runs.cuh
+// draws them while the gather list is in flight), else null.
 template <int SOLVER, int STAGE>
 __device__ __forceinline__ SpinVec integrate_site(const Tables& t, const LlgParams& p, int i, int k, int io, const double b[3],
-                                                  const SpinVec& own, const SpinVec& c0, double* __restrict__ b2eff) {
+                                                  const SpinVec& own, const SpinVec& c0, double* __restrict__ b2eff,
+                                                  const float* gpre = nullptr) {
    double lam, lg, temp;
    if (p.per_site) { lam = __ldg(p.lambda_a + i); lg = __ldg(p.landeg_a + i); temp = __ldg(p.temp_a + i); }
    else { lam = p.lambda; lg = p.landeg; temp = p.temp; }
    const double e[3] = {c0.x, c0.y, c0.z};
    const double m = c0.m;
    double g[3] = {0.0, 0.0, 0.0};
-   if (p.thermal) gauss3f(p.seed, (uint32_t)io + t.atom_offset, (uint32_t)k + t.ens_offset, p.step, 0u, g[0], g[1], g[2]);
+   if (gpre) { g[0] = (double)gpre[0]; g[1] = (double)gpre[1]; g[2] = (double)gpre[2]; }
+   else if (p.thermal) gauss3f(p.seed, (uint32_t)io + t.atom_offset, (uint32_t)k + t.ens_offset, p.step, 0u, g[0], g[1], g[2]);
    double bt[3] = {0.0, 0.0, 0.0};
    if (t.btorque) {
       const double* __restrict__ q = t.btorque + (size_t)k * 3 * t.Npad + i;

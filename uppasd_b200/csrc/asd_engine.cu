@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -23,6 +24,7 @@
 #include "asd_device.cuh"
 #include "asd_mc.cuh"
 #include "asd_tiles.cuh"
+#include "asd_runs.cuh"
 #include "asd_lattice.cuh"
 
 using namespace asd;
@@ -96,6 +98,8 @@ struct Layout {
    DevBuf<int> d_ucount, d_ulist;   // staged tile path (asd_tiles.cuh)
    DevBuf<uint4> d_nl16;
    DevBuf<int2> d_meta;
+   DevBuf<uint2> d_utab;            // run-compressed table (asd_runs.cuh)
+   DevBuf<int> d_gcount;
    DevBuf<int> d_okey;              // sort key of the gather lists when it differs from orig (lattice builder)
    bool is_mc = false;
    DevBuf<double4> d_cp4;
@@ -122,7 +126,6 @@ struct Slab {
    int n_opened = 0;
    unsigned long long epoch = 0;       // exchanges completed (identical on every rank)
    bool connected = false;
-   int tile_a = 0, tile_b = 0, ntile = 0;   // tiles [0,a) and [b,ntile) hold the boundary planes
    long long timeout_ticks = 8000000000LL;  // ~4 s at 1.9 GHz
 };
 
@@ -197,14 +200,15 @@ static int lattice_colours(asd_engine* e);
 
 // staged tile path: gather lists + 16-bit neighbour table (asd_tiles.cuh).  Leaves t.staged = 0 when a tile would
 // need more than TILE_UMAX unique slots (layout without locality) or when switched off (ASD_STAGED=0).
-static int build_tiles(asd_engine* e, Layout& L) {
+static int build_tiles(asd_engine* e, Layout& L, int ts) {
    Tables& t = L.t;
    t.staged = 0; t.ucap = 0; t.ulist = nullptr; t.ucount = nullptr; t.nl16 = nullptr; t.zq8 = (t.z + 7) / 8;
+   t.tile_slots = ts;
    const char* env = std::getenv("ASD_STAGED");
    if ((env && atoi(env) == 0) || L.is_mc || t.z <= 0) return 0;
    const long Npad = L.Npad;
    if (t.Nown <= 0) t.Nown = L.Npad;
-   const int ntile = (t.Nown + TILE - 1) / TILE;
+   const int ntile = (t.Nown + ts - 1) / ts;
    const int* key = L.d_okey.p ? L.d_okey.p : t.orig;
    // lattice layouts: rotate x in the sort key so that periodic images stay next to the tile (asd_tiles.cuh)
    const bool wrap = L.d_okey.p && e->lattice_built && e->lat.periodic[0] && e->lat.N1 >= 64 && !(std::getenv("ASD_KEYWRAP") && atoi(std::getenv("ASD_KEYWRAP")) == 0);
@@ -214,7 +218,7 @@ static int build_tiles(asd_engine* e, Layout& L) {
    if ((r = L.d_ucount.alloc(ntile))) return r;
    const size_t smem = TILE_BUILD_SMEM;
    CU(cudaFuncSetAttribute(tile_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 0, 0, L.d_ucount.p, nullptr, nullptr, t.zq8, kna, kn1);
+   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 0, 0, L.d_ucount.p, nullptr, nullptr, t.zq8, kna, kn1, ts);
    e->launches++;
    CU(cudaGetLastError());
    std::vector<int> cnt(ntile);
@@ -225,7 +229,7 @@ static int build_tiles(asd_engine* e, Layout& L) {
    const int ucap = ((mx + 31) / 32) * 32;
    if ((r = L.d_ulist.alloc((size_t)ntile * ucap))) return r;
    if ((r = L.d_nl16.alloc((size_t)t.zq8 * Npad))) return r;
-   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 1, ucap, L.d_ucount.p, L.d_ulist.p, L.d_nl16.p, t.zq8, kna, kn1);
+   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 1, ucap, L.d_ucount.p, L.d_ulist.p, L.d_nl16.p, t.zq8, kna, kn1, ts);
    e->launches++;
    CU(cudaGetLastError());
    CU(cudaStreamSynchronize(st));
@@ -236,6 +240,40 @@ static int build_tiles(asd_engine* e, Layout& L) {
    CU(cudaStreamSynchronize(st));
    t.meta = L.d_meta.p;
    t.staged = 1; t.ucap = ucap; t.ulist = L.d_ulist.p; t.ucount = L.d_ucount.p; t.nl16 = L.d_nl16.p;
+   return 0;
+}
+
+// run-compressed table (asd_runs.cuh): groups of 4 x-runs -> union rows.  Leaves t.runs = 0 unless every group of the
+// layout is regular.
+static int build_runs(asd_engine* e, Layout& L) {
+   constexpr int R = 4;
+   Tables& t = L.t;
+   t.runs = 0; t.urow = 0; t.utab = nullptr;
+   if (!t.staged || !L.reduced || !t.cpl_param || L.is_mc || !e->lattice_built) return 0;
+   if (t.z * R >= RUN_MAXPAIR) return 0;
+   const int ngroup = (t.Nown + R * 32 - 1) / (R * 32);
+   const int ntile = (t.Nown + t.tile_slots - 1) / t.tile_slots;
+   const int galloc = ntile * (t.tile_slots / (R * 32));      // whole tiles: the stage kernel copies NW rows per tile
+   cudaStream_t st = e->stream;
+   int r;
+   if ((r = L.d_gcount.alloc(ngroup))) return r;
+   run_union_kernel<R><<<ngroup, 32, 0, st>>>(t.Nown, L.Npad, t.nl16, t.meta, t.lsize, 0, 0, L.d_gcount.p, nullptr);
+   e->launches++;
+   CU(cudaGetLastError());
+   std::vector<int> cnt(ngroup);
+   CU(cudaMemcpyAsync(cnt.data(), L.d_gcount.p, (size_t)ngroup * sizeof(int), cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   int mx = 0;
+   for (int c : cnt) { if (c < 0) return 0; mx = std::max(mx, c); }
+   if (mx == 0 || mx > 255) return 0;
+   const int urow = 2 + ((mx + 2) / 2) * 2;   // header + entries + at least one spare (zero) entry
+   if ((r = L.d_utab.alloc((size_t)galloc * urow))) return r;
+   CU(cudaMemsetAsync(L.d_utab.p, 0, (size_t)galloc * urow * sizeof(uint2), st));
+   run_union_kernel<R><<<ngroup, 32, 0, st>>>(t.Nown, L.Npad, t.nl16, t.meta, t.lsize, 1, urow, L.d_gcount.p, L.d_utab.p);
+   e->launches++;
+   CU(cudaGetLastError());
+   CU(cudaStreamSynchronize(st));
+   t.runs = R; t.urow = urow; t.utab = L.d_utab.p;
    return 0;
 }
 
@@ -279,13 +317,31 @@ static int finish_layout(asd_engine* e, Layout& L) {
       size_t n0 = (size_t)NH * t.z, n1 = (size_t)NH * t.zdm * 3, n2 = (size_t)NH * t.zbq;
       if ((n0 + n1 + n2) * 8 <= 40 * 1024) { t.sm_cp = (int)n0; t.sm_dm = (int)n1; t.sm_bq = (int)n2; L.smem_bytes = (n0 + n1 + n2) * 8; }
    }
-   // ---- vectorised exchange table + coupling placement (experiment knobs: ASD_VARIANT, ASD_PF) ----
+   // ---- field path of the stage kernels: run kernel on big tiles > staged tiles > direct gathers
+   //      (experiment knobs: ASD_VARIANT, ASD_PF, ASD_STAGED, ASD_RUNS = 0 | 256 | 512 | 1024) ----
    {
       const char* var = std::getenv("ASD_VARIANT");
       const int variant = var ? atoi(var) : 3;
       t.nl4 = nullptr; t.cp4 = nullptr; t.zq = (t.z + 3) / 4; t.pf_tiles = 0; t.cpl_param = 0;
-      if ((r = build_tiles(e, L))) return r;
-      // staged layouts use nl16 in the LLG kernels; the field-only / MC kernels then read the plain nl table
+      t.runs = 0; t.urow = 0; t.utab = nullptr;
+      if (variant >= 3 && L.reduced && t.z > 0 && (size_t)NH * t.z <= 256) {
+         std::vector<double> rows((size_t)NH * t.z);
+         CU(cudaMemcpy(rows.data(), t.cp, rows.size() * sizeof(double), cudaMemcpyDeviceToHost));
+         for (size_t q = 0; q < rows.size(); q++) t.cpl_small[q] = rows[q];
+         t.cpl_param = 1;
+      }
+      // tile size of the run kernel: the whole super-brick by default
+      int big = (e->lattice_built && !L.is_mc) ? 256 * e->lat.SY * e->lat.SZ : 256;
+      const char* renv = std::getenv("ASD_RUNS");
+      if (renv) big = atoi(renv);
+      if (big != 0 && big != 256 && big != 512 && big != 1024) return fail(-1, "ASD_RUNS must be 0, 256, 512 or 1024");
+      if (big > 256 && (!e->lattice_built || 256 * e->lat.SY * e->lat.SZ % big != 0)) big = 256;
+      if (big >= 256 && (renv || big > 256)) {
+         if ((r = build_tiles(e, L, big))) return r;
+         if ((r = build_runs(e, L))) return r;
+      }
+      if (!t.runs && (r = build_tiles(e, L, 256))) return r;
+      // staged layouts use nl16 / the union rows in the LLG kernels; the field-only / MC kernels read the plain nl table
       if (variant >= 3 && t.z > 0) {
          L.d_nl4.release(); L.d_cp4.release();
          if (!t.staged && (r = L.d_nl4.alloc((size_t)t.zq * Npad))) return r;
@@ -302,12 +358,6 @@ static int finish_layout(asd_engine* e, Layout& L) {
          int sms = 148;
          cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
          t.pf_tiles = pf ? atoi(pf) : sms * 3;
-         if (L.reduced && (size_t)NH * t.z <= 256) {
-            std::vector<double> rows((size_t)NH * t.z);
-            CU(cudaMemcpy(rows.data(), t.cp, rows.size() * sizeof(double), cudaMemcpyDeviceToHost));
-            for (size_t q = 0; q < rows.size(); q++) t.cpl_small[q] = rows[q];
-            t.cpl_param = 1;
-         }
       }
    }
    // ---- per-atom arrays in device order ----
@@ -635,18 +685,34 @@ static int ensure_layout(asd_engine* e, int want) {
 // ------------------------------------------------------------------------------------------------
 template <class K>
 static void allow_smem(K kernel, size_t bytes) {
-   // opt in to > 48 KB of dynamic shared memory (once per kernel instantiation and size)
-   static size_t granted = 0;
-   if (bytes > 48 * 1024 && bytes > granted) {
+   // opt in to > 48 KB of dynamic shared memory (once per kernel and size; kernels of one signature share K)
+   static std::map<const void*, size_t> granted;
+   if (bytes <= 48 * 1024) return;
+   size_t& g = granted[(const void*)kernel];
+   if (bytes > g) {
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-      granted = bytes;
+      g = bytes;
    }
 }
 
 template <int SOLVER, int STAGE, bool EDGE, bool MSUM>
 static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, const EdgeParams& ep, const TileRange& tr, int ntiles) {
    const dim3 g(ntiles, e->M, 1), b(256, 1, 1);
-   if (L.t.staged) {
+   if (L.t.runs) {
+      const int NW = L.t.tile_slots / 128;
+      const size_t smem = (size_t)(L.t.sm_dm + L.t.sm_bq) * sizeof(double) + (size_t)3 * (L.t.ucap + 32) * sizeof(double) +
+                          (size_t)NW * L.t.urow * sizeof(uint2);
+      if (NW == 8) {
+         allow_smem(llg_runs_kernel<SOLVER, STAGE, 8, EDGE, MSUM>, smem);
+         llg_runs_kernel<SOLVER, STAGE, 8, EDGE, MSUM><<<g, 256, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
+      } else if (NW == 4) {
+         allow_smem(llg_runs_kernel<SOLVER, STAGE, 4, EDGE, MSUM>, smem);
+         llg_runs_kernel<SOLVER, STAGE, 4, EDGE, MSUM><<<g, 128, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
+      } else {
+         allow_smem(llg_runs_kernel<SOLVER, STAGE, 2, EDGE, MSUM>, smem);
+         llg_runs_kernel<SOLVER, STAGE, 2, EDGE, MSUM><<<g, 64, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
+      }
+   } else if (L.t.staged) {
       const size_t smem = L.smem_bytes + (size_t)3 * L.t.ucap * sizeof(double);
       if (L.reduced) {
          allow_smem(llg_stage_kernel<SOLVER, STAGE, true, true, EDGE, MSUM>, smem);
@@ -666,6 +732,17 @@ static void launch_stage_range(asd_engine* e, Layout& L, const LlgParams& p, con
    // the per-tile moment sums ride on corrector launches only
    if (STAGE == 2 && p.msum_part != nullptr) launch_stage_range2<SOLVER, STAGE, EDGE, STAGE == 2>(e, L, p, ep, tr, ntiles);
    else launch_stage_range2<SOLVER, STAGE, EDGE, false>(e, L, p, ep, tr, ntiles);
+}
+
+// boundary / interior split of a slab in tiles of `ts` slots: tiles [0,a) and [b,ntile) hold the H boundary planes
+static void slab_split(const asd_engine* e, int ts, int& a, int& b, int& ntile) {
+   const LatticeDesc& d = e->lat;
+   ntile = (d.Nown + ts - 1) / ts;
+   const long layer = (long)d.NTX * d.NSY * d.SY * d.SZ * d.NA * d.P;   // slots per layer of super-bricks
+   const long nl = (d.H + d.SZ * d.BZ - 1) / (d.SZ * d.BZ);             // layers that hold the H boundary planes
+   long aa = (layer * nl + ts - 1) / ts, bb = (d.Nown - layer * nl) / ts;
+   if (bb < aa) { aa = ntile; bb = ntile; }                             // thin slab: every tile is a boundary tile
+   a = (int)aa; b = (int)bb;
 }
 
 static EdgeParams edge_params(asd_engine* e, int stage, unsigned long long epoch) {
@@ -688,7 +765,7 @@ static EdgeParams edge_params(asd_engine* e, int stage, unsigned long long epoch
 template <int SOLVER, int STAGE>
 static void launch_stage(asd_engine* e, Layout& L, const LlgParams& p) {
    Slab& sb = e->slab;
-   const int ntile = (L.t.Nown + 255) / 256;
+   const int ntile = (L.t.Nown + L.t.tile_slots - 1) / L.t.tile_slots;
    EdgeParams none;
    memset(&none, 0, sizeof none);
    if (!sb.on) {
@@ -698,9 +775,10 @@ static void launch_stage(asd_engine* e, Layout& L, const LlgParams& p) {
    halo_wait_kernel<<<1, 1, 0, e->stream>>>(sb.flags.p, e->lat.has_lo, e->lat.has_hi, sb.epoch, sb.timeout_ticks, sb.err.p);
    e->launches++;
    const EdgeParams ep = edge_params(e, STAGE, sb.epoch + 1);
-   const int nedge = sb.tile_a + (ntile - sb.tile_b);
-   launch_stage_range<SOLVER, STAGE, true>(e, L, p, ep, TileRange{0, sb.tile_a, sb.tile_b}, nedge);
-   launch_stage_range<SOLVER, STAGE, false>(e, L, p, none, TileRange{sb.tile_a, sb.tile_b - sb.tile_a, 0}, sb.tile_b - sb.tile_a);
+   int ta, tb, nt;
+   slab_split(e, L.t.tile_slots, ta, tb, nt);
+   launch_stage_range<SOLVER, STAGE, true>(e, L, p, ep, TileRange{0, ta, tb}, ta + (nt - tb));
+   launch_stage_range<SOLVER, STAGE, false>(e, L, p, none, TileRange{ta, tb - ta, 0}, tb - ta);
    sb.epoch += 1;
 }
 
@@ -727,7 +805,7 @@ static int sd_steps(asd_engine* e, long nsteps, long first_step, cudaEvent_t* ev
    LlgParams p;
    if ((r = fill_llg(e, L, p, 0))) return r;
    if (e->slab.on && !e->slab.connected) return fail(-11, "slab: not connected to the ring neighbours");
-   const int ntile = (L.t.Nown + 255) / 256;
+   const int ntile = (L.t.Nown + L.t.tile_slots - 1) / L.t.tile_slots;
    if (nsteps > 0) {
       if ((r = e->msum_part.alloc((size_t)e->M * ntile * 4))) return r;
       e->msum_fresh = false;
@@ -831,8 +909,10 @@ static int mc_sweeps_tiles(asd_engine* e, McParams& p, long nsweeps, long first_
          halo_wait_kernel<<<1, 1, 0, e->stream>>>(sb.flags.p, e->lat.has_lo, e->lat.has_hi, sb.epoch, sb.timeout_ticks, sb.err.p);
          e->launches++;
          const EdgeParams ep = edge_params(e, 2, sb.epoch + 1);
-         launch(true, ep, TileRange{0, sb.tile_a, sb.tile_b}, sb.tile_a + (ntile - sb.tile_b));
-         launch(false, none, TileRange{sb.tile_a, sb.tile_b - sb.tile_a, 0}, sb.tile_b - sb.tile_a);
+         int ta, tb, nt;
+         slab_split(e, 256, ta, tb, nt);
+         launch(true, ep, TileRange{0, ta, tb}, ta + (nt - tb));
+         launch(false, none, TileRange{ta, tb - ta, 0}, tb - ta);
          sb.epoch += 1;
       }
    CU(cudaGetLastError());
@@ -892,12 +972,7 @@ static int slab_commit(asd_engine* e) {
    CU(cudaMemset(sb.ctr.p, 0, sizeof(unsigned int)));
    CU(cudaMemset(sb.err.p, 0, sizeof(int)));
    sb.epoch = 0;
-   sb.ntile = (d.Nown + 255) / 256;
-   const long layer = (long)d.NTX * d.NTY * d.NA * d.P;     // slots per brick layer
-   const long nl = (d.H + d.BZ - 1) / d.BZ;                 // brick layers that hold the H boundary planes
-   long a = (layer * nl + 255) / 256, b = (d.Nown - layer * nl) / 256;
-   if (b < a) { a = sb.ntile; b = sb.ntile; }               // thin slab: every tile is a boundary tile
-   sb.tile_a = (int)a; sb.tile_b = (int)b;
+   (void)d;
    return 0;
 }
 
@@ -1346,6 +1421,13 @@ int asd_slab_status(asd_engine* e, unsigned long long* epoch, int* error_flag) {
          if (*error_flag) return fail(-12, "slab: timed out waiting for the halo of the %s neighbour", *error_flag == 1 ? "lower" : "upper");
       }
    }
+   return 0;
+}
+
+int asd_layout_info(asd_engine* e, int* info4) {
+   if (!e->committed) return fail(-2, "asd_commit has not been called");
+   const Tables& t = e->sd.t;
+   info4[0] = t.staged; info4[1] = t.runs; info4[2] = t.ucap; info4[3] = t.runs ? t.urow - 2 : 0;
    return 0;
 }
 

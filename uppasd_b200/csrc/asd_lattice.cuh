@@ -25,6 +25,10 @@ struct LatticeDesc {
    // staged in shared memory (asd_tiles.cuh) instead of being gathered from L2 fifty times.
    int BX, BY, BZ, P;
    int NTX, NTY, NTZ;   // bricks per direction (the last one may be partly empty -> padding slots)
+   // SUPER-BRICKS: SY x SZ bricks that are adjacent in y / z are numbered consecutively, so that SY*SZ consecutive
+   // 256-slot tiles form one compact block (e.g. 32 x 4 x 4 cells): the big tiles of the run kernel (asd_runs.cuh)
+   // stage ~40 % fewer spins per atom than four separate bricks.  NSY, NSZ = super-bricks per direction.
+   int SY, SZ, NSY, NSZ;
    // Slab decomposition along z, one slab per GPU: this engine owns the global planes
    // [z0, z0 + N3) of N3g; N1, N2, N3, Ncell, N describe the LOCAL slab.  Slots [0, Nown) are the owned bricks;
    // the H halo planes of the lower ring neighbour and then of the upper one follow.  Halo slots hold copies of
@@ -42,7 +46,8 @@ __device__ __host__ __forceinline__ int halo_slot(const LatticeDesc& d, int side
 __device__ __host__ __forceinline__ int lattice_slot(const LatticeDesc& d, int i0, int ix, int iy, int iz) {
    const int tx = ix / d.BX, ty = iy / d.BY, tz = iz / d.BZ;
    const int lx = ix - tx * d.BX, ly = iy - ty * d.BY, lz = iz - tz * d.BZ;
-   const int brick = tx + d.NTX * (ty + d.NTY * tz);
+   const int sbk = tx + d.NTX * (ty / d.SY + d.NSY * (tz / d.SZ));
+   const int brick = sbk * (d.SY * d.SZ) + (ty % d.SY) + d.SY * (tz % d.SZ);
    return (brick * d.NA + i0) * d.P + lx + d.BX * (ly + d.BY * lz);
 }
 
@@ -51,7 +56,8 @@ __device__ __host__ __forceinline__ bool lattice_unslot(const LatticeDesc& d, in
    const int run = s / d.P, c = s - run * d.P;
    const int brick = run / d.NA;
    i0 = run - brick * d.NA;
-   const int tx = brick % d.NTX, ty = (brick / d.NTX) % d.NTY, tz = brick / (d.NTX * d.NTY);
+   const int sbk = brick / (d.SY * d.SZ), q = brick - sbk * (d.SY * d.SZ);
+   const int tx = sbk % d.NTX, ty = ((sbk / d.NTX) % d.NSY) * d.SY + q % d.SY, tz = (sbk / (d.NTX * d.NSY)) * d.SZ + q / d.SY;
    const int lx = c % d.BX, ly = (c / d.BX) % d.BY, lz = c / (d.BX * d.BY);
    ix = tx * d.BX + lx; iy = ty * d.BY + ly; iz = tz * d.BZ + lz;
    return ix < d.N1 && iy < d.N2 && iz < d.N3;

@@ -41,6 +41,18 @@ static void choose_brick(LatticeDesc& d) {
          }
    d.BX = bb[0]; d.BY = bb[1]; d.BZ = bb[2]; d.P = bb[0] * bb[1] * bb[2];
    d.NTX = (d.N1 + d.BX - 1) / d.BX; d.NTY = (d.N2 + d.BY - 1) / d.BY; d.NTZ = (d.N3 + d.BZ - 1) / d.BZ;
+   // super-bricks (big tiles of the run kernel): only when a brick is exactly one 256-slot tile and the Hamiltonian is
+   // reduced (the run kernel's precondition).  ASD_SUPER = "sy,sz" overrides (1,1 switches them off).
+   d.SY = d.SZ = 1;
+   if (d.reduced && d.NA * d.P == 256) {
+      if (d.NTZ >= 2 && d.NTY >= 2) { d.SY = 2; d.SZ = 2; }
+      else if (d.NTY >= 4) { d.SY = 4; d.SZ = 1; }
+      else if (d.NTZ >= 4) { d.SY = 1; d.SZ = 4; }
+      const char* env = std::getenv("ASD_SUPER");
+      int sy, sz;
+      if (env && sscanf(env, "%d,%d", &sy, &sz) == 2 && sy >= 1 && sz >= 1 && sy * sz <= 4) { d.SY = sy; d.SZ = sz; }
+   }
+   d.NSY = (d.NTY + d.SY - 1) / d.SY; d.NSZ = (d.NTZ + d.SZ - 1) / d.SZ;
 }
 
 extern "C" {
@@ -70,7 +82,7 @@ int asd_build_lattice_table(asd_engine* e, int kind, int NA, int N1, int N2, int
       d.has_hi = sb.on && (d.periodic[2] || sb.g < sb.G - 1);
       choose_brick(d);
       {
-         const long nown = (long)d.NTX * d.NTY * d.NTZ * d.NA * d.P;
+         const long nown = (long)d.NTX * d.NSY * d.NSZ * d.SY * d.SZ * d.NA * d.P;
          const long np = ((nown + 2L * d.H * NA * N1 * N2 + 31) / 32) * 32;
          if (np > 2000000000L) return fail(-3, "too many atoms for 32-bit device indices");
          d.Nown = (int)nown; d.Npad = (int)np;

@@ -1,0 +1,310 @@
+// Run-compressed neighbour table + register-blocked stage kernel (the fast path of lattice layouts).
+//
+// What the table means is unchanged -- entry j of atom i is nlist(j,i) of the reference
+// (source/Hamiltonian/hamiltoniandatatype.f90:30-33), summed with ncoup(j,aHam(i)) as in heisenberg_field
+// (source/Hamiltonian/hamiltonianactions.f90:461-464) -- but two regularities of a lattice in brick order are
+// used to store and to read it (both VERIFIED on the device when the table is built; a layout that lacks them keeps
+// the plain staged kernel of asd_device.cuh):
+//
+//  (1) a warp is one 32-cell x-run of one sublattice, and the gather list of its tile is sorted by (sublattice,
+//      atom index): the 32 lanes' j-th neighbours are 32 CONSECUTIVE positions of the list.  One 16-bit base per
+//      (run, j) replaces 32 per-atom indices: the index stream (4z bytes per atom and stage in the reference's
+//      layout, 2z in nl16) disappears from HBM traffic.
+//  (2) R runs that are adjacent in y / z share most of their neighbours: for the 4-shell bcc table the 4 x 50
+//      neighbour runs of a 2 x 2 block of x-runs are only 100 distinct runs.  A thread therefore owns R atoms (one
+//      per run of its group), reads every distinct neighbour ONCE from shared memory and feeds it to the 1..R
+//      accumulators that use it.  Shared-memory traffic -- the bound of the one-atom-per-thread kernel (ncu: L1 data
+//      pipe 86 %, profiles/) -- halves; FP64 FMA count is unchanged.
+//
+// Per group of R runs the build kernel emits the union as entries {position base, mask of runs that use it, the
+// neighbour number j of each such run}, sorted by (mask, j of the lowest run) -- a key that does not depend on how
+// the supercell is decomposed, so slabs reproduce the undecomposed summation order bit for bit.  The stage kernel
+// walks the entries mask by mask (15 compile-time variants of the inner loop for R = 4): no predicates, no wasted
+// FMAs.  The order of summation inside one atom differs from j = 1..z (parity bar: 1e-12 relative, tests).
+#pragma once
+#include "asd_device.cuh"
+
+namespace asd {
+
+#ifndef ASD_RUN_UNROLL
+#define ASD_RUN_UNROLL 4
+#endif
+
+constexpr int RUN_UNROLL = ASD_RUN_UNROLL;   // entries of the union walk in flight per mask loop
+constexpr int RUN_MAXPAIR = 256;   // R * z must stay below this (j and the entry counts are bytes)
+
+// One warp per group of R runs.  pass 0: gcount[g] = number of union entries, or -1 if the group is not regular;
+// pass 1: writes the row  utab[g][rowlen]:  bytes 0..15 = end[m] (one past the last entry whose mask is <= m),
+// then entries {x = 24 * base (byte offset of the record in the staged list), y = j of run 0 | j of run 1 << 8 | ...}
+// from uint2 index 2 on; at least one spare (zero) entry ends the row.
+template <int R>
+__global__ void __launch_bounds__(32)
+run_union_kernel(int Nown, int Npad, const uint4* __restrict__ nl16, const int2* __restrict__ meta, const int* __restrict__ lsize,
+                 int pass, int rowlen, int* __restrict__ gcount, uint2* __restrict__ utab) {
+   __shared__ unsigned short base[RUN_MAXPAIR], rj[RUN_MAXPAIR];
+   __shared__ unsigned int lkey[RUN_MAXPAIR];
+   __shared__ uint2 lent[RUN_MAXPAIR];
+   __shared__ int nlead, dup;
+   const int g = blockIdx.x, lane = threadIdx.x;
+   int npair = 0, ham0 = -1;
+   bool ok = true;
+   for (int r = 0; r < R; r++) {
+      const int s = (g * R + r) * 32 + lane;
+      int2 mt = make_int2(-1, -1);
+      if (s < Nown) mt = meta[s];
+      const bool act = mt.y >= 0;
+      const unsigned am = __ballot_sync(0xffffffffu, act);
+      if (am == 0) continue;                              // a run of padding slots
+      if (am & (am + 1)) { ok = false; continue; }        // the real cells must be lanes 0..n-1
+      const int hr = __shfl_sync(0xffffffffu, mt.x, 0);
+      if (ham0 < 0) ham0 = hr; else if (hr != ham0) ok = false;
+      if (__any_sync(0xffffffffu, act && mt.x != hr)) ok = false;
+      const int n = lsize[hr];
+      if (npair + n >= RUN_MAXPAIR) { ok = false; continue; }
+      for (int q = 0; 8 * q < n; q++) {
+         const uint4 w = nl16[(size_t)q * Npad + s];
+         const unsigned li[8] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16, w.z & 0xffffu, w.z >> 16, w.w & 0xffffu, w.w >> 16};
+#pragma unroll
+         for (int u = 0; u < 8; u++) {
+            const int j = 8 * q + u;
+            if (j < n) {
+               const unsigned b = __shfl_sync(0xffffffffu, li[u], 0);
+               if (__any_sync(0xffffffffu, act && li[u] != b + lane)) ok = false;
+               if (lane == 0) { base[npair] = (unsigned short)b; rj[npair] = (unsigned short)((r << 8) | j); }
+               npair++;
+            }
+         }
+      }
+   }
+   if (lane == 0) { nlead = 0; dup = 0; }
+   __syncwarp();
+   for (int p0 = 0; p0 < npair; p0 += 32) {
+      const int p = p0 + lane;
+      if (p < npair) {
+         bool leader = true;
+         for (int q = 0; q < p; q++) if (base[q] == base[p]) { leader = false; break; }
+         if (leader) {
+            unsigned mask = 0, jb = 0;
+            for (int q = p; q < npair; q++)
+               if (base[q] == base[p]) {
+                  const unsigned r = rj[q] >> 8, j = rj[q] & 255u;
+                  if (mask & (1u << r)) dup = 1;      // one atom lists the same neighbour twice: not handled here
+                  mask |= 1u << r;
+                  jb |= j << (8 * r);
+               }
+            const int at = atomicAdd(&nlead, 1);
+            lkey[at] = (mask << 8) | (rj[p] & 255u);   // pair p is the first use: lowest run, its j
+            lent[at] = make_uint2((unsigned)base[p] * 24u, jb);
+         }
+      }
+   }
+   __syncwarp();
+   const int nl = nlead;
+   if (dup) ok = false;
+   if (pass == 0) {
+      if (lane == 0) gcount[g] = ok ? nl : -1;
+      return;
+   }
+   if (!ok) return;
+   uint2* __restrict__ row = utab + (size_t)g * rowlen;
+   for (int l = lane; l < nl; l += 32) {
+      int rank = 0;
+      for (int q = 0; q < nl; q++) rank += lkey[q] < lkey[l];
+      row[2 + rank] = lent[l];
+   }
+   if (lane < 16) {
+      int c = 0;
+      for (int q = 0; q < nl; q++) c += (int)(lkey[q] >> 8) <= lane;
+      reinterpret_cast<unsigned char*>(row)[lane] = (unsigned char)c;
+   }
+}
+
+// inner loops of the union walk, one per mask value (ascending, like the entries)
+template <int R, int MASK>
+struct RunLoop {
+   static __device__ __forceinline__ void run(const Tables& t, int cbase, const uint2* __restrict__ ent, const unsigned char* __restrict__ endb,
+                                              const double* __restrict__ srec, double (&f)[R][3]) {
+      RunLoop<R, MASK - 1>::run(t, cbase, ent, endb, srec, f);
+      const int e0 = endb[MASK - 1], e1 = endb[MASK];
+      uint2 nx = ent[e0];                   // one entry ahead: its decode overlaps the loads of the current one
+#pragma unroll (RUN_UNROLL)
+      for (int e = e0; e < e1; e++) {
+         const uint2 en = nx;
+         nx = ent[e + 1];                   // rows carry one spare entry
+         const double* __restrict__ m = reinterpret_cast<const double*>(reinterpret_cast<const char*>(srec) + en.x);
+         const double mx = m[0], my = m[1], mz = m[2];
+#pragma unroll
+         for (int r = 0; r < R; r++)
+            if (MASK & (1 << r)) {
+               const double c = t.cpl_small[cbase + ((en.y >> (8 * r)) & 0xffu)];
+               f[r][0] = fma(c, mx, f[r][0]);
+               f[r][1] = fma(c, my, f[r][1]);
+               f[r][2] = fma(c, mz, f[r][2]);
+            }
+      }
+   }
+};
+template <int R>
+struct RunLoop<R, 0> {
+   static __device__ __forceinline__ void run(const Tables&, int, const uint2*, const unsigned char*, const double*, double (&)[R][3]) {}
+};
+
+// One stage of one LLG step on a tile of NW*128 slots = NW groups of R = 4 x-runs (NW = 2, 4, 8: tiles of 256, 512,
+// 1024 slots = 1, 2, 4 bricks of a super-brick): NW warps, thread (warp w, lane l) owns the atoms
+// tile*TS + (w*4 + r)*32 + l, r = 0..3.  Same contract as llg_stage_kernel (asd_device.cuh).
+template <int SOLVER, int STAGE, int NW, bool EDGE, bool MSUM>
+__global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : (NW == 4) ? 4 : 6)
+llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgParams p, const __grid_constant__ EdgeParams ep,
+                const TileRange tr, SpinVec* __restrict__ cur, SpinVec* __restrict__ pred, double* __restrict__ b2eff) {
+   constexpr int R = 4, NT = NW * 32, TS = NW * R * 32;
+   constexpr int SB = (NW == 8) ? 7 : 8;   // spins in flight per thread while the gather list is staged
+   extern __shared__ double sm[];
+   const double *smc, *smd, *smb;
+   const int tile = ((int)blockIdx.x < tr.split) ? tr.first + (int)blockIdx.x : tr.second + ((int)blockIdx.x - tr.split);
+   const int k = blockIdx.y;
+   const int wp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+   SpinVec* __restrict__ curk = cur + (size_t)k * t.Npad;
+   SpinVec* __restrict__ predk = pred + (size_t)k * t.Npad;
+   const SpinVec* __restrict__ S = (STAGE == 1) ? curk : predk;
+   const int i0 = tile * TS + wp * (R * 32) + ln;      // atom of run r: i0 + 32 r
+   // ---- every independent global load first: {ham, orig}, own spins, union rows, first batch of the gather list ----
+   int2 mt[R];
+#pragma unroll
+   for (int r = 0; r < R; r++) {
+      const int i = i0 + 32 * r;
+      const int ii = (i < t.Nown) ? i : 0;
+      mt[r] = __ldg(t.meta + ii);
+      if (i >= t.Nown) mt[r].y = -1;
+   }
+   const int cnt = __ldg(t.ucount + tile);
+   const int* __restrict__ ul = t.ulist + (size_t)tile * t.ucap;
+   const int ncpl = t.sm_dm + t.sm_bq;                       // exchange couplings ride in the constant bank
+   double* __restrict__ s3 = sm + ncpl;
+   uint2* __restrict__ rows = reinterpret_cast<uint2*>(s3 + 3 * (t.ucap + 32));
+   constexpr int RB = 4;                                     // union-row words per thread and round
+   const int nrow = NW * t.urow;
+   const uint2* __restrict__ rsrc = t.utab + (size_t)tile * nrow;
+   uint2 rw[RB];
+#pragma unroll
+   for (int a = 0; a < RB; a++) rw[a] = (threadIdx.x + a * NT < nrow) ? __ldg(rsrc + threadIdx.x + a * NT) : make_uint2(0u, 0u);
+   // L2 prefetch of what the CTA one wave later needs first: its own spins, gather list and union rows
+   if (t.pf_tiles > 0 && threadIdx.x < 3) {
+      const size_t nt = (size_t)tile + t.pf_tiles;
+      if (nt * TS < (size_t)t.Nown) {
+         if (threadIdx.x == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(S + nt * TS), "r"((unsigned)(TS * 32)) : "memory");
+         if (threadIdx.x == 1) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(t.ulist + nt * t.ucap), "r"((unsigned)t.ucap * 4u) : "memory");
+         if (threadIdx.x == 2) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(t.utab + nt * nrow), "r"((unsigned)nrow * 8u) : "memory");
+      }
+   }
+   float gn[R][3];
+#pragma unroll
+   for (int r = 0; r < R; r++) { gn[r][0] = 0.f; gn[r][1] = 0.f; gn[r][2] = 0.f; }
+   for (int u0 = threadIdx.x; u0 < cnt; u0 += SB * NT) {
+      int sl[SB];
+#pragma unroll
+      for (int a = 0; a < SB; a++) sl[a] = (u0 + a * NT < cnt) ? __ldg(ul + u0 + a * NT) : 0;
+      SpinVec v[SB];
+#pragma unroll
+      for (int a = 0; a < SB; a++) v[a] = S[sl[a]];
+      if (u0 == (int)threadIdx.x) {
+         // while the first batch is in flight: the Langevin noise of the 4 atoms (pure ALU work, independent of the field)
+         if (p.thermal) {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+               gauss3f_raw(p.seed, (uint32_t)mt[r].y + t.atom_offset, (uint32_t)k + t.ens_offset, p.step, 0u, gn[r][0], gn[r][1], gn[r][2]);
+         }
+#pragma unroll
+         for (int a = 0; a < RB; a++) if (threadIdx.x + a * NT < nrow) rows[threadIdx.x + a * NT] = rw[a];
+         for (int q = threadIdx.x + RB * NT; q < nrow; q += NT) rows[q] = __ldg(rsrc + q);
+      }
+#pragma unroll
+      for (int a = 0; a < SB; a++)
+         if (u0 + a * NT < cnt) {
+            double* __restrict__ m = s3 + 3 * (u0 + a * NT);
+            m[0] = v[a].x * v[a].m; m[1] = v[a].y * v[a].m; m[2] = v[a].z * v[a].m;
+         }
+   }
+   stage_couplings(t, sm, smc, smd, smb);   // ends with __syncthreads() when it stages anything
+   if (ncpl == 0) __syncthreads();
+   // ---- Heisenberg sums of the 4 atoms of this thread: every distinct neighbour run read once ----
+   double f[R][3];
+#pragma unroll
+   for (int r = 0; r < R; r++) { f[r][0] = 0.0; f[r][1] = 0.0; f[r][2] = 0.0; }
+   int ih = -1;
+#pragma unroll
+   for (int r = 0; r < R; r++) ih = max(ih, __shfl_sync(0xffffffffu, mt[r].y >= 0 ? mt[r].x : -1, 0));
+   if (ih >= 0) {
+      const uint2* __restrict__ row = rows + wp * t.urow;
+      RunLoop<R, (1 << R) - 1>::run(t, ih * t.z, row + 2, reinterpret_cast<const unsigned char*>(row), s3 + 3 * ln, f);
+   }
+   // ---- integrators: one rolled loop over the 4 atoms (the register arrays rotate, so the body exists once); the
+   //      own spin (and the old spin of a corrector) of the next atom is loaded one iteration ahead ----
+   double mnew[3] = {0.0, 0.0, 0.0};
+   const int ilast = t.Nown - 1;
+   SpinVec own = S[min(i0, ilast)], old;
+   if (STAGE == 2) old = curk[min(i0, ilast)];
+#pragma unroll 1
+   for (int r = 0; r < R; r++) {
+      const int i = i0 + 32 * r;
+      const int io = mt[0].y;
+      const int inext = min(i + 32, ilast);
+      const SpinVec own_n = S[inext];
+      SpinVec old_n;
+      if (STAGE == 2) old_n = curk[inext];
+      if (io >= 0) {
+         double bs[3] = {f[0][0], f[0][1], f[0][2]}, bq[3];
+         site_field<true, false>(t, S, i, ih, own, smc, smd, smb, bs, bq);
+         double h[3];
+         ext_field(t, i, k, h);
+         const double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
+         const SpinVec o = integrate_site<SOLVER, STAGE>(t, p, i, k, io, b, own, (STAGE == 1) ? own : old, b2eff, gn[0]);
+         if (STAGE == 1) predk[i] = o; else curk[i] = o;
+         if (MSUM) { mnew[0] += o.x * o.m; mnew[1] += o.y * o.m; mnew[2] += o.z * o.m; }
+         if (EDGE) {
+            const int lo = __ldg(ep.hdst_lo + i), hi = __ldg(ep.hdst_hi + i);
+            if (lo >= 0) ep.peer_lo[(size_t)k * t.Npad + lo] = o;
+            if (hi >= 0) ep.peer_hi[(size_t)k * t.Npad + hi] = o;
+         }
+      }
+      own = own_n;
+      if (STAGE == 2) old = old_n;
+#pragma unroll
+      for (int q = 0; q + 1 < R; q++) {
+         f[q][0] = f[q + 1][0]; f[q][1] = f[q + 1][1]; f[q][2] = f[q + 1][2];
+         mt[q] = mt[q + 1];
+         gn[q][0] = gn[q + 1][0]; gn[q][1] = gn[q + 1][1]; gn[q][2] = gn[q + 1][2];
+      }
+   }
+   if (MSUM) {
+      __shared__ double red[3][NW];
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+         double v = mnew[a];
+#pragma unroll
+         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+         if (ln == 0) red[a][wp] = v;
+      }
+      __syncthreads();
+      if (threadIdx.x < 4) {
+         double v = 0.0;
+         if (threadIdx.x < 3)
+            for (int q = 0; q < NW; q++) v += red[threadIdx.x][q];
+         p.msum_part[((size_t)k * p.msum_ntile + tile) * 4 + threadIdx.x] = v;
+      }
+   }
+   if (EDGE) {
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+         const unsigned int total = gridDim.x * gridDim.y;
+         if (atomicAdd(ep.ctr, 1u) == total - 1) {
+            *ep.ctr = 0;
+            __threadfence_system();
+            if (ep.flag_lo) st_release_sys(ep.flag_lo, ep.epoch);
+            if (ep.flag_hi) st_release_sys(ep.flag_hi, ep.epoch);
+         }
+      }
+   }
+}
+
+}  // namespace asd

@@ -12,7 +12,8 @@
 
 namespace asd {
 
-constexpr int TILE = 256;          // slots per tile = threads per CTA of the stage kernels
+constexpr int TILE = 256;          // threads per CTA of the build kernel = slots per tile of the one-atom-per-thread stage kernel
+                                   // (the run kernel uses tiles of ts = 256, 512 or 1024 slots: whole super-bricks)
 constexpr int TILE_HASH = 8192;    // open-addressing table (ints) used to find the unique slots
 constexpr int TILE_UMAX = 4096;    // beyond this many unique slots per tile the staged path is not used
 constexpr size_t TILE_BUILD_SMEM = (size_t)TILE_HASH * 4 + (size_t)TILE_UMAX * (8 + 4);
@@ -43,16 +44,16 @@ __device__ __forceinline__ unsigned long long tile_key(const int* __restrict__ h
 __global__ void __launch_bounds__(TILE)
 tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const int* __restrict__ ham, const int* __restrict__ orig,
                    int pass, int ucap, int* __restrict__ ucount, int* __restrict__ ulist, uint4* __restrict__ nl16, int zq8,
-                   int kna, int kn1) {
+                   int kna, int kn1, int ts) {
    extern __shared__ unsigned long long tsm64[];
    unsigned long long* keys = tsm64;                       // [TILE_UMAX] (pass 1)
    int* lst = (int*)(tsm64 + TILE_UMAX);                   // [TILE_UMAX] slot of each key (pass 1)
    int* tab = lst + TILE_UMAX;                             // [TILE_HASH]
    __shared__ int nuniq, over, nfill;
    const int tile = blockIdx.x;
-   const int s = tile * TILE + threadIdx.x;
+   const int s0 = tile * ts + threadIdx.x, send = min((tile + 1) * ts, Nown);
    TileKeyWrap kw{kna, kn1, 0};
-   if (kn1 > 0) { const int o0 = orig[tile * TILE]; kw.xref = o0 >= 0 ? (o0 / kna) % kn1 : 0; }
+   if (kn1 > 0) { const int o0 = orig[tile * ts]; kw.xref = o0 >= 0 ? (o0 / kna) % kn1 : 0; }
    for (int q = threadIdx.x; q < TILE_HASH; q += TILE) tab[q] = -1;
    if (threadIdx.x == 0) { nuniq = 0; over = 0; nfill = 0; }
    __syncthreads();
@@ -66,7 +67,7 @@ tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const 
          hsh = (hsh + 1) & (TILE_HASH - 1);
       }
    };
-   if (s < Nown) {
+   for (int s = s0; s < send; s += TILE) {
       insert(s);
       for (int j = 0; j < z; j++) insert(nl[(size_t)j * Npad + s]);
    }
@@ -103,7 +104,6 @@ tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const 
       }
    for (int q = threadIdx.x; q < ucap; q += TILE) ulist[(size_t)tile * ucap + q] = (q < cnt) ? lst[q] : lst[0];
    if (threadIdx.x == 0) ucount[tile] = cnt;
-   if (s >= Nown) return;
    auto find = [&](int slot) -> unsigned {
       const unsigned long long key = tile_key(ham, orig, slot, kw);
       int lo = 0, hi = cnt - 1;
@@ -113,15 +113,17 @@ tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const 
       }
       return (unsigned)lo;
    };
-   const unsigned self = find(s);
-   for (int q = 0; q < zq8; q++) {
-      unsigned v[8];
+   for (int s = s0; s < send; s += TILE) {
+      const unsigned self = find(s);
+      for (int q = 0; q < zq8; q++) {
+         unsigned v[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
-         const int j = 8 * q + u;
-         v[u] = (j < z) ? find(nl[(size_t)j * Npad + s]) : self;
+         for (int u = 0; u < 8; u++) {
+            const int j = 8 * q + u;
+            v[u] = (j < z) ? find(nl[(size_t)j * Npad + s]) : self;
+         }
+         nl16[(size_t)q * Npad + s] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
       }
-      nl16[(size_t)q * Npad + s] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
    }
 }
 

@@ -176,6 +176,12 @@ class Engine:
         self._chk(self.lib.asd_time_mc_sweeps(self.h, mode.encode(), nsweeps, temperature, C.byref(tot)))
         return tot.value
 
+    def layout_info(self):
+        """dict(staged, runs, ucap, union): the field path of the LLG stage kernels"""
+        info = (C.c_int * 4)()
+        self._chk(self.lib.asd_layout_info(self.h, info))
+        return dict(staged=info[0], runs=info[1], ucap=info[2], union=info[3])
+
     def launch_count(self):
         return self.lib.asd_launch_count(self.h)
 
