@@ -86,8 +86,8 @@ struct Tables {
    // run-compressed table of lattice layouts (asd_runs.cuh): groups of `runs` x-runs share one union row
    int tile_slots;        // slots per tile of ulist / ucount (256; 512 or 1024 with the run kernel on super-bricks)
    int runs;              // 0: off, else 4: the LLG stage kernels use llg_runs_kernel (4 x-runs per warp)
-   int urow;              // row stride of utab in uint2
-   const uint2* __restrict__ utab;    // [ntile * 8/R][urow]
+   int urow;              // row stride of utab in 16-byte words
+   const uint4* __restrict__ utab;    // [groups][urow]
    int pf_tiles;    // L2 bulk-prefetch distance in 256-atom tiles (0 = off)
    int cpl_param;   // 1: reduced exchange couplings live in cpl_small (kernel parameter = constant bank)
    double cpl_small[256];

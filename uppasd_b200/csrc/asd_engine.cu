@@ -98,7 +98,7 @@ struct Layout {
    DevBuf<int> d_ucount, d_ulist;   // staged tile path (asd_tiles.cuh)
    DevBuf<uint4> d_nl16;
    DevBuf<int2> d_meta;
-   DevBuf<uint2> d_utab;            // run-compressed table (asd_runs.cuh)
+   DevBuf<uint4> d_utab;            // run-compressed table (asd_runs.cuh)
    DevBuf<int> d_gcount;
    DevBuf<int> d_okey;              // sort key of the gather lists when it differs from orig (lattice builder)
    bool is_mc = false;
@@ -257,7 +257,7 @@ static int build_runs(asd_engine* e, Layout& L) {
    cudaStream_t st = e->stream;
    int r;
    if ((r = L.d_gcount.alloc(ngroup))) return r;
-   run_union_kernel<R><<<ngroup, 32, 0, st>>>(t.Nown, L.Npad, t.nl16, t.meta, t.lsize, 0, 0, L.d_gcount.p, nullptr);
+   run_union_kernel<R><<<ngroup, 32, 0, st>>>(t.Nown, L.Npad, t.z, t.nl16, t.meta, t.lsize, 0, 0, L.d_gcount.p, nullptr);
    e->launches++;
    CU(cudaGetLastError());
    std::vector<int> cnt(ngroup);
@@ -266,10 +266,10 @@ static int build_runs(asd_engine* e, Layout& L) {
    int mx = 0;
    for (int c : cnt) { if (c < 0) return 0; mx = std::max(mx, c); }
    if (mx == 0 || mx > 255) return 0;
-   const int urow = 2 + ((mx + 2) / 2) * 2;   // header + entries + at least one spare (zero) entry
+   const int urow = 1 + mx + 1;   // header word + entries + one spare (zero) entry
    if ((r = L.d_utab.alloc((size_t)galloc * urow))) return r;
-   CU(cudaMemsetAsync(L.d_utab.p, 0, (size_t)galloc * urow * sizeof(uint2), st));
-   run_union_kernel<R><<<ngroup, 32, 0, st>>>(t.Nown, L.Npad, t.nl16, t.meta, t.lsize, 1, urow, L.d_gcount.p, L.d_utab.p);
+   CU(cudaMemsetAsync(L.d_utab.p, 0, (size_t)galloc * urow * sizeof(uint4), st));
+   run_union_kernel<R><<<ngroup, 32, 0, st>>>(t.Nown, L.Npad, t.z, t.nl16, t.meta, t.lsize, 1, urow, L.d_gcount.p, L.d_utab.p);
    e->launches++;
    CU(cudaGetLastError());
    CU(cudaStreamSynchronize(st));
@@ -357,7 +357,7 @@ static int finish_layout(asd_engine* e, Layout& L) {
          const char* pf = std::getenv("ASD_PF");
          int sms = 148;
          cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
-         t.pf_tiles = pf ? atoi(pf) : sms * 3;
+         t.pf_tiles = pf ? atoi(pf) : (t.runs ? sms : sms * 3);   // prefetch distance in tiles (measured optimum)
       }
    }
    // ---- per-atom arrays in device order ----
@@ -700,8 +700,8 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
    const dim3 g(ntiles, e->M, 1), b(256, 1, 1);
    if (L.t.runs) {
       const int NW = L.t.tile_slots / 128;
-      const size_t smem = (size_t)(L.t.sm_dm + L.t.sm_bq) * sizeof(double) + (size_t)3 * (L.t.ucap + 32) * sizeof(double) +
-                          (size_t)NW * L.t.urow * sizeof(uint2);
+      const size_t smem = (size_t)((L.t.sm_dm + L.t.sm_bq + 1) & ~1) * sizeof(double) + (size_t)3 * (L.t.ucap + 32) * sizeof(double) +
+                          (size_t)NW * L.t.urow * sizeof(uint4);
       if (NW == 8) {
          allow_smem(llg_runs_kernel<SOLVER, STAGE, 8, EDGE, MSUM>, smem);
          llg_runs_kernel<SOLVER, STAGE, 8, EDGE, MSUM><<<g, 256, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
@@ -1427,7 +1427,7 @@ int asd_slab_status(asd_engine* e, unsigned long long* epoch, int* error_flag) {
 int asd_layout_info(asd_engine* e, int* info4) {
    if (!e->committed) return fail(-2, "asd_commit has not been called");
    const Tables& t = e->sd.t;
-   info4[0] = t.staged; info4[1] = t.runs; info4[2] = t.ucap; info4[3] = t.runs ? t.urow - 2 : 0;
+   info4[0] = t.staged; info4[1] = t.runs; info4[2] = t.ucap; info4[3] = t.runs ? t.urow - 2 : 0;   // urow = header + entries + spare
    return 0;
 }
 

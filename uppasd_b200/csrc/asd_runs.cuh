@@ -34,16 +34,16 @@ constexpr int RUN_UNROLL = ASD_RUN_UNROLL;   // entries of the union walk in fli
 constexpr int RUN_MAXPAIR = 256;   // R * z must stay below this (j and the entry counts are bytes)
 
 // One warp per group of R runs.  pass 0: gcount[g] = number of union entries, or -1 if the group is not regular;
-// pass 1: writes the row  utab[g][rowlen]:  bytes 0..15 = end[m] (one past the last entry whose mask is <= m),
-// then entries {x = 24 * base (byte offset of the record in the staged list), y = j of run 0 | j of run 1 << 8 | ...}
-// from uint2 index 2 on; at least one spare (zero) entry ends the row.
+// pass 1: writes the row  utab[g][rowlen] (16-byte words):  word 0 = end[m], m = 0..15, as bytes (one past the last entry
+// whose mask is <= m), then entries {x = 24 * base (byte offset of the record in the staged list), y / z = byte offsets
+// of the couplings of runs 0..3 in Tables::cpl_small, 16 bits each}; at least one spare (zero) entry ends the row.
 template <int R>
 __global__ void __launch_bounds__(32)
-run_union_kernel(int Nown, int Npad, const uint4* __restrict__ nl16, const int2* __restrict__ meta, const int* __restrict__ lsize,
-                 int pass, int rowlen, int* __restrict__ gcount, uint2* __restrict__ utab) {
+run_union_kernel(int Nown, int Npad, int z, const uint4* __restrict__ nl16, const int2* __restrict__ meta, const int* __restrict__ lsize,
+                 int pass, int rowlen, int* __restrict__ gcount, uint4* __restrict__ utab) {
    __shared__ unsigned short base[RUN_MAXPAIR], rj[RUN_MAXPAIR];
    __shared__ unsigned int lkey[RUN_MAXPAIR];
-   __shared__ uint2 lent[RUN_MAXPAIR];
+   __shared__ uint4 lent[RUN_MAXPAIR];
    __shared__ int nlead, dup;
    const int g = blockIdx.x, lane = threadIdx.x;
    int npair = 0, ham0 = -1;
@@ -84,17 +84,17 @@ run_union_kernel(int Nown, int Npad, const uint4* __restrict__ nl16, const int2*
          bool leader = true;
          for (int q = 0; q < p; q++) if (base[q] == base[p]) { leader = false; break; }
          if (leader) {
-            unsigned mask = 0, jb = 0;
+            unsigned mask = 0, off[4] = {0u, 0u, 0u, 0u};
             for (int q = p; q < npair; q++)
                if (base[q] == base[p]) {
                   const unsigned r = rj[q] >> 8, j = rj[q] & 255u;
                   if (mask & (1u << r)) dup = 1;      // one atom lists the same neighbour twice: not handled here
                   mask |= 1u << r;
-                  jb |= j << (8 * r);
+                  off[r] = (unsigned)(ham0 * z + (int)j) * 8u;   // byte offset of ncoup(j, aHam) in Tables::cpl_small
                }
             const int at = atomicAdd(&nlead, 1);
             lkey[at] = (mask << 8) | (rj[p] & 255u);   // pair p is the first use: lowest run, its j
-            lent[at] = make_uint2((unsigned)base[p] * 24u, jb);
+            lent[at] = make_uint4((unsigned)base[p] * 24u, off[0] | (off[1] << 16), off[2] | (off[3] << 16), 0u);
          }
       }
    }
@@ -106,11 +106,11 @@ run_union_kernel(int Nown, int Npad, const uint4* __restrict__ nl16, const int2*
       return;
    }
    if (!ok) return;
-   uint2* __restrict__ row = utab + (size_t)g * rowlen;
+   uint4* __restrict__ row = utab + (size_t)g * rowlen;
    for (int l = lane; l < nl; l += 32) {
       int rank = 0;
       for (int q = 0; q < nl; q++) rank += lkey[q] < lkey[l];
-      row[2 + rank] = lent[l];
+      row[1 + rank] = lent[l];
    }
    if (lane < 16) {
       int c = 0;
@@ -122,21 +122,24 @@ run_union_kernel(int Nown, int Npad, const uint4* __restrict__ nl16, const int2*
 // inner loops of the union walk, one per mask value (ascending, like the entries)
 template <int R, int MASK>
 struct RunLoop {
-   static __device__ __forceinline__ void run(const Tables& t, int cbase, const uint2* __restrict__ ent, const unsigned char* __restrict__ endb,
+   static __device__ __forceinline__ void run(const Tables& t, const uint4* __restrict__ ent, const unsigned char* __restrict__ endb,
                                               const double* __restrict__ srec, double (&f)[R][3]) {
-      RunLoop<R, MASK - 1>::run(t, cbase, ent, endb, srec, f);
+      RunLoop<R, MASK - 1>::run(t, ent, endb, srec, f);
       const int e0 = endb[MASK - 1], e1 = endb[MASK];
-      uint2 nx = ent[e0];                   // one entry ahead: its decode overlaps the loads of the current one
+      uint4 nx = ent[e0];                   // one entry ahead: its decode overlaps the loads of the current one
 #pragma unroll (RUN_UNROLL)
       for (int e = e0; e < e1; e++) {
-         const uint2 en = nx;
+         const uint4 en = nx;
          nx = ent[e + 1];                   // rows carry one spare entry
          const double* __restrict__ m = reinterpret_cast<const double*>(reinterpret_cast<const char*>(srec) + en.x);
          const double mx = m[0], my = m[1], mz = m[2];
+         const char* __restrict__ cb = reinterpret_cast<const char*>(t.cpl_small);
 #pragma unroll
          for (int r = 0; r < R; r++)
             if (MASK & (1 << r)) {
-               const double c = t.cpl_small[cbase + ((en.y >> (8 * r)) & 0xffu)];
+               const unsigned w = (r < 2) ? en.y : en.z;
+               const unsigned off = (r & 1) ? (w >> 16) : (w & 0xffffu);
+               const double c = *reinterpret_cast<const double*>(cb + off);
                f[r][0] = fma(c, mx, f[r][0]);
                f[r][1] = fma(c, my, f[r][1]);
                f[r][2] = fma(c, mz, f[r][2]);
@@ -146,7 +149,7 @@ struct RunLoop {
 };
 template <int R>
 struct RunLoop<R, 0> {
-   static __device__ __forceinline__ void run(const Tables&, int, const uint2*, const unsigned char*, const double*, double (&)[R][3]) {}
+   static __device__ __forceinline__ void run(const Tables&, const uint4*, const unsigned char*, const double*, double (&)[R][3]) {}
 };
 
 // One stage of one LLG step on a tile of NW*128 slots = NW groups of R = 4 x-runs (NW = 2, 4, 8: tiles of 256, 512,
@@ -179,21 +182,23 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
    const int cnt = __ldg(t.ucount + tile);
    const int* __restrict__ ul = t.ulist + (size_t)tile * t.ucap;
    const int ncpl = t.sm_dm + t.sm_bq;                       // exchange couplings ride in the constant bank
-   double* __restrict__ s3 = sm + ncpl;
-   uint2* __restrict__ rows = reinterpret_cast<uint2*>(s3 + 3 * (t.ucap + 32));
-   constexpr int RB = 4;                                     // union-row words per thread and round
+   double* __restrict__ s3 = sm + ((ncpl + 1) & ~1);          // keeps the union rows 16-byte aligned
+   uint4* __restrict__ rows = reinterpret_cast<uint4*>(s3 + 3 * (t.ucap + 32));
    const int nrow = NW * t.urow;
-   const uint2* __restrict__ rsrc = t.utab + (size_t)tile * nrow;
-   uint2 rw[RB];
-#pragma unroll
-   for (int a = 0; a < RB; a++) rw[a] = (threadIdx.x + a * NT < nrow) ? __ldg(rsrc + threadIdx.x + a * NT) : make_uint2(0u, 0u);
+   const uint4* __restrict__ rsrc = t.utab + (size_t)tile * nrow;
+   // union rows: asynchronous 16-byte copies straight into shared memory (no registers held while they fly)
+   for (int q = threadIdx.x; q < nrow; q += NT) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(rows + q);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rsrc + q) : "memory");
+   }
+   asm volatile("cp.async.commit_group;" ::: "memory");
    // L2 prefetch of what the CTA one wave later needs first: its own spins, gather list and union rows
    if (t.pf_tiles > 0 && threadIdx.x < 3) {
       const size_t nt = (size_t)tile + t.pf_tiles;
       if (nt * TS < (size_t)t.Nown) {
          if (threadIdx.x == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(S + nt * TS), "r"((unsigned)(TS * 32)) : "memory");
          if (threadIdx.x == 1) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(t.ulist + nt * t.ucap), "r"((unsigned)t.ucap * 4u) : "memory");
-         if (threadIdx.x == 2) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(t.utab + nt * nrow), "r"((unsigned)nrow * 8u) : "memory");
+         if (threadIdx.x == 2) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(t.utab + nt * nrow), "r"((unsigned)nrow * 16u) : "memory");
       }
    }
    float gn[R][3];
@@ -213,9 +218,6 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
             for (int r = 0; r < R; r++)
                gauss3f_raw(p.seed, (uint32_t)mt[r].y + t.atom_offset, (uint32_t)k + t.ens_offset, p.step, 0u, gn[r][0], gn[r][1], gn[r][2]);
          }
-#pragma unroll
-         for (int a = 0; a < RB; a++) if (threadIdx.x + a * NT < nrow) rows[threadIdx.x + a * NT] = rw[a];
-         for (int q = threadIdx.x + RB * NT; q < nrow; q += NT) rows[q] = __ldg(rsrc + q);
       }
 #pragma unroll
       for (int a = 0; a < SB; a++)
@@ -224,6 +226,7 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
             m[0] = v[a].x * v[a].m; m[1] = v[a].y * v[a].m; m[2] = v[a].z * v[a].m;
          }
    }
+   asm volatile("cp.async.wait_group 0;" ::: "memory");
    stage_couplings(t, sm, smc, smd, smb);   // ends with __syncthreads() when it stages anything
    if (ncpl == 0) __syncthreads();
    // ---- Heisenberg sums of the 4 atoms of this thread: every distinct neighbour run read once ----
@@ -234,8 +237,8 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
 #pragma unroll
    for (int r = 0; r < R; r++) ih = max(ih, __shfl_sync(0xffffffffu, mt[r].y >= 0 ? mt[r].x : -1, 0));
    if (ih >= 0) {
-      const uint2* __restrict__ row = rows + wp * t.urow;
-      RunLoop<R, (1 << R) - 1>::run(t, ih * t.z, row + 2, reinterpret_cast<const unsigned char*>(row), s3 + 3 * ln, f);
+      const uint4* __restrict__ row = rows + wp * t.urow;
+      RunLoop<R, (1 << R) - 1>::run(t, row + 1, reinterpret_cast<const unsigned char*>(row), s3 + 3 * ln, f);
    }
    // ---- integrators: one rolled loop over the 4 atoms (the register arrays rotate, so the body exists once); the
    //      own spin (and the old spin of a corrector) of the next atom is loaded one iteration ahead ----
