@@ -296,7 +296,13 @@ def main():
         t2 = float(np.median(st2)) * 1e-3
         t1 = float(np.median(st1)) * 1e-3
         ach = b2 * n / t2 / 1e9
-        kname = 'llg_stage_kernel<solver=%d,stage=2,reduced,staged>' % a.solver
+        lay = e.layout_info()
+        if lay['runs']:
+            kname = 'llg_runs_kernel<solver=%d,stage=2,tile=%d>' % (a.solver, lay['tile_slots'])
+            tables = '%.0f MB of gather lists + run-compressed tables' % ((4.0 * lay['ucap'] + 16.0 * (lay['union'] + 2) * lay['tile_slots'] / 128) / lay['tile_slots'] * n / 1e6 + 8.0 * n / 1e6)
+        else:
+            kname = 'llg_stage_kernel<solver=%d,stage=2,reduced,%s>' % (a.solver, 'staged' if lay['staged'] else 'direct')
+            tables = 'index tables %.0f MB' % ((7 * 16 + 24) * n / 1e6)
         par = ('ensemble-sharded x%d (one %d-spin ensemble per GPU, no communication)' % (world, n)) if not slab else \
               ('z-slabs x%d of one supercell, halo push fused into the boundary-tile launches (peer stores over NVLink)' % world)
         out = {
@@ -304,8 +310,8 @@ def main():
             'warmup': warmup, 'ms_per_step': ms / steps, 'higher_is_better': True,
             'scaling': 'strong' if slab else 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': workload, 'spins_per_gpu': n, 'ensembles': 1 if slab else world, 'parallelism': par,
-                       'l2_policy': 'inputs larger than L2 (index tables %.0f MB + spins %.0f MB per GPU vs 126 MB L2)'
-                                    % ((7 * 16 + 24) * n / 1e6, 64.0 * n / 1e6)},
+                       'field_path': lay,
+                       'l2_policy': 'inputs larger than L2 (%s + spins %.0f MB per GPU vs 126 MB L2)' % (tables, 64.0 * n / 1e6)},
             'clocks': sampler.summary(),
             'e2e': {'value': e2e, 'unit': 'atom-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'steps': k2, 'note': 'asd_set_moments from pinned host memory (H2D of emom+mmom) + K x [asd_sd_steps(1) + '

@@ -184,8 +184,9 @@ int asd_time_mc_sweeps(asd_engine* e, char mode, long nsweeps, double temperatur
 /* number of kernel launches issued by this engine so far (bench.py's gpu_launches). */
 /* which field path the LLG stage kernels of the committed layout use: info[0] = 1 if the tile's gather list is staged
  * in shared memory, info[1] = R of the run-compressed register-blocked kernel (0: one atom per thread), info[2] =
- * largest gather list of a tile, info[3] = largest number of distinct neighbour runs of a group of R runs */
-int asd_layout_info(asd_engine* e, int* info4);
+ * largest gather list of a tile, info[3] = largest number of distinct neighbour runs of a group of R runs,
+ * info[4] = slots per tile (256, 512 or 1024) */
+int asd_layout_info(asd_engine* e, int* info5);
 long asd_launch_count(asd_engine* e);
 int asd_synchronize(asd_engine* e);
 

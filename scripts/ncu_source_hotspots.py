@@ -29,4 +29,4 @@ print('--- executed warp-instr per warp by region')
 ex=[int(r[ie]) for r in out]
 import itertools
 for a in range(0,len(out),100):
-    print(a, '%.1f'%(sum(ex[a:a+100])/131072.0), 'samples %.1f%%'%(100*sum(int(r[si]) for r in out[a:a+100])/tot))
+    print(a, '%.1f'%(sum(ex[a:a+100])/32768.0), 'samples %.1f%%'%(100*sum(int(r[si]) for r in out[a:a+100])/tot))

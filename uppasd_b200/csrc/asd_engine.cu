@@ -1424,10 +1424,11 @@ int asd_slab_status(asd_engine* e, unsigned long long* epoch, int* error_flag) {
    return 0;
 }
 
-int asd_layout_info(asd_engine* e, int* info4) {
+int asd_layout_info(asd_engine* e, int* info5) {
    if (!e->committed) return fail(-2, "asd_commit has not been called");
    const Tables& t = e->sd.t;
-   info4[0] = t.staged; info4[1] = t.runs; info4[2] = t.ucap; info4[3] = t.runs ? t.urow - 2 : 0;   // urow = header + entries + spare
+   info5[0] = t.staged; info5[1] = t.runs; info5[2] = t.ucap; info5[3] = t.runs ? t.urow - 2 : 0;   // urow = header + entries + spare
+   info5[4] = t.tile_slots;
    return 0;
 }
 

@@ -204,27 +204,33 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
    float gn[R][3];
 #pragma unroll
    for (int r = 0; r < R; r++) { gn[r][0] = 0.f; gn[r][1] = 0.f; gn[r][2] = 0.f; }
-   for (int u0 = threadIdx.x; u0 < cnt; u0 += SB * NT) {
-      int sl[SB];
+   // gather list -> shared memory in rounds of 2 x SB spins per thread: the indices of both halves are fetched first
+   // (one round trip), the spins of the second half fly while the first half is converted and stored
+   for (int u0 = threadIdx.x; u0 < cnt; u0 += 2 * SB * NT) {
+      int sl[2 * SB];
 #pragma unroll
-      for (int a = 0; a < SB; a++) sl[a] = (u0 + a * NT < cnt) ? __ldg(ul + u0 + a * NT) : 0;
+      for (int a = 0; a < 2 * SB; a++) sl[a] = (u0 + a * NT < cnt) ? __ldg(ul + u0 + a * NT) : 0;
       SpinVec v[SB];
 #pragma unroll
       for (int a = 0; a < SB; a++) v[a] = S[sl[a]];
-      if (u0 == (int)threadIdx.x) {
+      if (u0 == (int)threadIdx.x && p.thermal) {
          // while the first batch is in flight: the Langevin noise of the 4 atoms (pure ALU work, independent of the field)
-         if (p.thermal) {
 #pragma unroll
-            for (int r = 0; r < R; r++)
-               gauss3f_raw(p.seed, (uint32_t)mt[r].y + t.atom_offset, (uint32_t)k + t.ens_offset, p.step, 0u, gn[r][0], gn[r][1], gn[r][2]);
-         }
+         for (int r = 0; r < R; r++)
+            gauss3f_raw(p.seed, (uint32_t)mt[r].y + t.atom_offset, (uint32_t)k + t.ens_offset, p.step, 0u, gn[r][0], gn[r][1], gn[r][2]);
       }
 #pragma unroll
-      for (int a = 0; a < SB; a++)
-         if (u0 + a * NT < cnt) {
-            double* __restrict__ m = s3 + 3 * (u0 + a * NT);
-            m[0] = v[a].x * v[a].m; m[1] = v[a].y * v[a].m; m[2] = v[a].z * v[a].m;
+      for (int h = 0; h < 2; h++) {
+#pragma unroll
+         for (int a = 0; a < SB; a++) {
+            const int u = u0 + (h * SB + a) * NT;
+            if (u < cnt) {
+               double* __restrict__ m = s3 + 3 * u;
+               m[0] = v[a].x * v[a].m; m[1] = v[a].y * v[a].m; m[2] = v[a].z * v[a].m;
+            }
+            if (h == 0) v[a] = S[sl[SB + a]];
          }
+      }
    }
    asm volatile("cp.async.wait_group 0;" ::: "memory");
    stage_couplings(t, sm, smc, smd, smb);   // ends with __syncthreads() when it stages anything
