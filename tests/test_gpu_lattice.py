@@ -71,3 +71,78 @@ def test_device_tables_drive_same_dynamics():
         st.step()
     emom, _, _ = e.get_moments()
     assert np.abs(emom - st.emom).max() <= 1e-12
+
+
+def _bcc_engine(S, inp, args, solver, temp, seed=11):
+    from uppasd_b200 import host, lattice
+    nn, red, xc, nntype = args[6](S)
+    ns, ca, cs, sh = lattice.stencil(inp['cell'], S['bas'], S['atype_inp'], nn, red, inp['sym'], nntype)
+    cp = lattice.couplings(ns, ca, sh, S['atype_inp'], xc, S['ammom_inp'], orc.CONST['mry'], orc.CONST['mub'])
+    e = host.Engine()
+    e.set_constants(*(orc.CONST[k] for k in ('gama', 'k_bolt', 'mub', 'mry')))
+    e.set_system(S['Natom'], S['emom'].shape[2], S['nHam'], S['aHam'])
+    e.build_lattice_table(0, S['NA'], inp['ncell'], inp['bc'], ns, ca, cs, cp)
+    e.set_llg(solver, inp['timestep'], landeg=S['Landeg'], lambda1=0.3, temp=temp, seed=seed)
+    e.set_moments(S['emom'], S['mmom'])
+    e.commit()
+    return e
+
+
+@pytest.mark.parametrize('ncell,tile', [((64, 4, 4), 1024), ((64, 6, 4), 1024), ((128, 8, 2), 1024)])
+def test_run_kernel_against_oracle_and_staged_kernel(ncell, tile, monkeypatch):
+    """The run-compressed register-blocked kernel (asd_runs.cuh) on lattices whose x extent is a multiple of 32 -- one,
+    several and partly empty super-bricks: field-level parity is implied by the trajectory (every step evaluates the
+    field twice); both solvers against the oracle at T = 0 to 1e-12, and against the one-atom-per-thread staged
+    kernel with the same noise stream at 300 K."""
+    fx, _, _ = load_golden('bccfe_cuda')
+    args = list(inputs.load_fixture(fx))
+    args[0] = dict(args[0], ncell=ncell, mensemble=2, do_reduced='Y')
+    S = orc.build_system(*args)
+    inp = args[0]
+    rng = np.random.default_rng(3)
+    e0 = rng.normal(size=(3, S['Natom'], 2)); e0 /= np.sqrt((e0 ** 2).sum(axis=0))
+    S['emom'] = np.asfortranarray(e0)
+    S['emomM'] = np.asfortranarray(e0 * S['mmom'][None])
+    for solver in (1, 5):
+        monkeypatch.delenv('ASD_RUNS', raising=False)
+        e = _bcc_engine(S, inp, args, solver, 0.0)
+        info = e.layout_info()
+        assert info['runs'] == 4 and info['tile_slots'] == tile and info['union'] <= 200, info
+        beff, _ = e.effective_field()
+        rb, _ = orc.effective_field(S)
+        assert np.abs(beff - rb).max() <= 1e-12 * np.abs(rb).max()
+        st = orc.SdState(S, solver, inp['timestep'], 0.3)
+        e.sd_steps(40)
+        for _ in range(40):
+            st.step()
+        assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12, (solver, ncell)
+        # thermal: same Philox stream in both kernels (the run kernel draws it while the gather list is in flight)
+        er = _bcc_engine(S, inp, args, solver, 300.0)
+        monkeypatch.setenv('ASD_RUNS', '0')
+        es = _bcc_engine(S, inp, args, solver, 300.0)
+        assert es.layout_info()['runs'] == 0 and es.layout_info()['staged'] == 1
+        er.sd_steps(25)
+        es.sd_steps(25)
+        a, b = er.get_moments()[0], es.get_moments()[0]
+        assert np.abs(a - b).max() <= 1e-11, (solver, ncell, np.abs(a - b).max())
+        assert np.abs(a - e0).max() > 1e-3          # the state did move
+        assert np.allclose(er.measure(), es.measure(), rtol=1e-10, atol=1e-8)   # fused per-tile moment sums
+
+
+def test_irregular_lattice_keeps_the_staged_kernel(monkeypatch):
+    """x extent not a multiple of 32 (or a single periodic 32-cell run, whose wrap splits the warp's neighbour run): the
+    regularity check of the run table fails on the device and the layout keeps the staged kernel -- same results as the
+    oracle."""
+    fx, _, _ = load_golden('bccfe_cuda')
+    args = list(inputs.load_fixture(fx))
+    args[0] = dict(args[0], ncell=(12, 6, 4), do_reduced='Y')
+    S = orc.build_system(*args)
+    monkeypatch.setenv('ASD_RUNS', '256')          # ask for the run kernel: the device-side check must refuse it
+    e = _bcc_engine(S, args[0], args, 1, 0.0)
+    info = e.layout_info()
+    assert info['runs'] == 0 and info['staged'] == 1 and info['tile_slots'] == 256, info
+    st = orc.SdState(S, 1, args[0]['timestep'], 0.3)
+    e.sd_steps(30)
+    for _ in range(30):
+        st.step()
+    assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12

@@ -46,10 +46,14 @@ def _gather(engines):
 @pytest.mark.parametrize('solver', [1, 5])
 @pytest.mark.parametrize('temp', [0.0, 300.0])
 @pytest.mark.parametrize('nslabs', [1, 2, 4])
-def test_slab_matches_undecomposed(solver, temp, nslabs):
-    ncell = (32, 6, 16)
+@pytest.mark.parametrize('ncell', [(32, 6, 16), (64, 6, 16)])
+def test_slab_matches_undecomposed(solver, temp, nslabs, ncell):
+    """(32, 6, 16): one periodic 32-cell x-run -> staged kernel; (64, 6, 16): run-compressed register-blocked kernel on
+    1024-slot super-brick tiles (boundary / interior split in those tiles)"""
     ref = _bcc(ncell, solver, temp)[0]
     sl = _bcc(ncell, solver, temp, nslabs=nslabs)
+    assert ref.layout_info()['runs'] == (4 if ncell[0] == 64 else 0)
+    assert all(e.layout_info()['runs'] == ref.layout_info()['runs'] for e in sl)
     assert np.array_equal(_gather(sl), ref.get_moments()[0])          # same tilted start (global index)
     done = 0
     for n in (1, 3, 20):
@@ -103,7 +107,7 @@ def test_slab_across_devices():
     ndev = capi.load().asd_device_count()
     if ndev < 2:
         pytest.skip('needs at least two GPUs')
-    ncell = (32, 8, 4 * ndev)
+    ncell = (64, 8, 4 * ndev)
     ref = _bcc(ncell, 1, 300.0)[0]
     sl = _bcc(ncell, 1, 300.0, nslabs=ndev, spread=True)
     for s in range(25):

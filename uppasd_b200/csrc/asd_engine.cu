@@ -211,14 +211,14 @@ static int build_tiles(asd_engine* e, Layout& L, int ts) {
    const int ntile = (t.Nown + ts - 1) / ts;
    const int* key = L.d_okey.p ? L.d_okey.p : t.orig;
    // lattice layouts: rotate x in the sort key so that periodic images stay next to the tile (asd_tiles.cuh)
-   const bool wrap = L.d_okey.p && e->lattice_built && e->lat.periodic[0] && e->lat.N1 >= 64 && !(std::getenv("ASD_KEYWRAP") && atoi(std::getenv("ASD_KEYWRAP")) == 0);
-   const int kna = wrap ? e->lat.NA : 0, kn1 = wrap ? e->lat.N1 : 0;
+   const bool wrap = L.d_okey.p && e->lattice_built && e->lat.periodic[0] && e->lat.N1 > e->lat.BX && !(std::getenv("ASD_KEYWRAP") && atoi(std::getenv("ASD_KEYWRAP")) == 0);
+   const int kna = wrap ? e->lat.NA : 0, kn1 = wrap ? e->lat.N1 : 0, koff = wrap ? (e->lat.N1 - e->lat.BX) / 2 : 0;
    cudaStream_t st = e->stream;
    int r;
    if ((r = L.d_ucount.alloc(ntile))) return r;
    const size_t smem = TILE_BUILD_SMEM;
    CU(cudaFuncSetAttribute(tile_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 0, 0, L.d_ucount.p, nullptr, nullptr, t.zq8, kna, kn1, ts);
+   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 0, 0, L.d_ucount.p, nullptr, nullptr, t.zq8, kna, kn1, koff, ts);
    e->launches++;
    CU(cudaGetLastError());
    std::vector<int> cnt(ntile);
@@ -229,7 +229,7 @@ static int build_tiles(asd_engine* e, Layout& L, int ts) {
    const int ucap = ((mx + 31) / 32) * 32;
    if ((r = L.d_ulist.alloc((size_t)ntile * ucap))) return r;
    if ((r = L.d_nl16.alloc((size_t)t.zq8 * Npad))) return r;
-   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 1, ucap, L.d_ucount.p, L.d_ulist.p, L.d_nl16.p, t.zq8, kna, kn1, ts);
+   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 1, ucap, L.d_ucount.p, L.d_ulist.p, L.d_nl16.p, t.zq8, kna, kn1, koff, ts);
    e->launches++;
    CU(cudaGetLastError());
    CU(cudaStreamSynchronize(st));
@@ -264,7 +264,18 @@ static int build_runs(asd_engine* e, Layout& L) {
    CU(cudaMemcpyAsync(cnt.data(), L.d_gcount.p, (size_t)ngroup * sizeof(int), cudaMemcpyDeviceToHost, st));
    CU(cudaStreamSynchronize(st));
    int mx = 0;
-   for (int c : cnt) { if (c < 0) return 0; mx = std::max(mx, c); }
+   for (int c : cnt) {
+      if (c < 0) {
+         if (std::getenv("ASD_DEBUG")) {
+            int hist[6] = {0, 0, 0, 0, 0, 0};
+            for (int q : cnt) if (q < 0 && q >= -5) hist[-q]++;
+            fprintf(stderr, "[asd] run table refused: %d groups; not a lane prefix %d, mixed rows %d, too many pairs %d, split neighbour run %d, duplicate neighbour %d\n",
+                    ngroup, hist[1], hist[2], hist[3], hist[4], hist[5]);
+         }
+         return 0;
+      }
+      mx = std::max(mx, c);
+   }
    if (mx == 0 || mx > 255) return 0;
    const int urow = 1 + mx + 1;   // header word + entries + one spare (zero) entry
    if ((r = L.d_utab.alloc((size_t)galloc * urow))) return r;

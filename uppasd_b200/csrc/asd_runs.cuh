@@ -47,6 +47,7 @@ run_union_kernel(int Nown, int Npad, int z, const uint4* __restrict__ nl16, cons
    __shared__ int nlead, dup;
    const int g = blockIdx.x, lane = threadIdx.x;
    int npair = 0, ham0 = -1;
+   int why = 0;   // first reason a group is not regular (negative code reported in gcount)
    bool ok = true;
    for (int r = 0; r < R; r++) {
       const int s = (g * R + r) * 32 + lane;
@@ -55,12 +56,12 @@ run_union_kernel(int Nown, int Npad, int z, const uint4* __restrict__ nl16, cons
       const bool act = mt.y >= 0;
       const unsigned am = __ballot_sync(0xffffffffu, act);
       if (am == 0) continue;                              // a run of padding slots
-      if (am & (am + 1)) { ok = false; continue; }        // the real cells must be lanes 0..n-1
+      if (am & (am + 1)) { ok = false; if (!why) why = -1; continue; }   // the real cells must be lanes 0..n-1
       const int hr = __shfl_sync(0xffffffffu, mt.x, 0);
-      if (ham0 < 0) ham0 = hr; else if (hr != ham0) ok = false;
-      if (__any_sync(0xffffffffu, act && mt.x != hr)) ok = false;
+      if (ham0 < 0) ham0 = hr; else if (hr != ham0) { ok = false; if (!why) why = -2; }
+      if (__any_sync(0xffffffffu, act && mt.x != hr)) { ok = false; if (!why) why = -2; }
       const int n = lsize[hr];
-      if (npair + n >= RUN_MAXPAIR) { ok = false; continue; }
+      if (npair + n >= RUN_MAXPAIR) { ok = false; if (!why) why = -3; continue; }
       for (int q = 0; 8 * q < n; q++) {
          const uint4 w = nl16[(size_t)q * Npad + s];
          const unsigned li[8] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16, w.z & 0xffffu, w.z >> 16, w.w & 0xffffu, w.w >> 16};
@@ -69,7 +70,7 @@ run_union_kernel(int Nown, int Npad, int z, const uint4* __restrict__ nl16, cons
             const int j = 8 * q + u;
             if (j < n) {
                const unsigned b = __shfl_sync(0xffffffffu, li[u], 0);
-               if (__any_sync(0xffffffffu, act && li[u] != b + lane)) ok = false;
+               if (__any_sync(0xffffffffu, act && li[u] != b + lane)) { ok = false; if (!why) why = -4; }
                if (lane == 0) { base[npair] = (unsigned short)b; rj[npair] = (unsigned short)((r << 8) | j); }
                npair++;
             }
@@ -100,9 +101,9 @@ run_union_kernel(int Nown, int Npad, int z, const uint4* __restrict__ nl16, cons
    }
    __syncwarp();
    const int nl = nlead;
-   if (dup) ok = false;
+   if (dup) { ok = false; if (!why) why = -5; }
    if (pass == 0) {
-      if (lane == 0) gcount[g] = ok ? nl : -1;
+      if (lane == 0) gcount[g] = ok ? nl : why;
       return;
    }
    if (!ok) return;

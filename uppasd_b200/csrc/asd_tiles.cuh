@@ -26,8 +26,9 @@ constexpr size_t TILE_BUILD_SMEM = (size_t)TILE_HASH * 4 + (size_t)TILE_UMAX * (
 // next brick -- so the shared-memory reads of the stage kernels are bank-conflict free.
 // Periodic wrap along x: a tile at the x-edge of the supercell reads the cells x = N1-2, N1-1 as the left neighbours
 // of x = 0 -- far away in index order, which would split the warp's run.  For lattice layouts (kna, kn1 > 0: key =
-// i0 + kna*(ix + kn1*...)) the x index is therefore rotated so that the tile's own first cell sits at kn1/2.
-struct TileKeyWrap { int kna, kn1, xref; };
+// i0 + kna*(ix + kn1*...)) the x index is therefore rotated so that the tile's own cells sit in the middle of the
+// rotated range (first cell at koff = (kn1 - BX) / 2): any N1 >= BX + 2 * reach keeps every neighbour run unsplit.
+struct TileKeyWrap { int kna, kn1, xref, koff; };
 
 __device__ __forceinline__ unsigned long long tile_key(const int* __restrict__ ham, const int* __restrict__ orig, int slot,
                                                        const TileKeyWrap& kw) {
@@ -35,7 +36,7 @@ __device__ __forceinline__ unsigned long long tile_key(const int* __restrict__ h
    if (o < 0) return (0x7fffffull << 40) | (unsigned long long)(unsigned)slot;   // padding slots last
    if (kw.kn1 > 0) {
       const int c = o / kw.kna, kx = c % kw.kn1;
-      const int rx = (kx - kw.xref + kw.kn1 / 2 + kw.kn1) % kw.kn1;
+      const int rx = (kx - kw.xref + kw.koff + kw.kn1) % kw.kn1;
       o += kw.kna * (rx - kx);
    }
    return ((unsigned long long)(unsigned)ham[slot] << 40) | (unsigned long long)(unsigned)o;
@@ -44,7 +45,7 @@ __device__ __forceinline__ unsigned long long tile_key(const int* __restrict__ h
 __global__ void __launch_bounds__(TILE)
 tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const int* __restrict__ ham, const int* __restrict__ orig,
                    int pass, int ucap, int* __restrict__ ucount, int* __restrict__ ulist, uint4* __restrict__ nl16, int zq8,
-                   int kna, int kn1, int ts) {
+                   int kna, int kn1, int koff, int ts) {
    extern __shared__ unsigned long long tsm64[];
    unsigned long long* keys = tsm64;                       // [TILE_UMAX] (pass 1)
    int* lst = (int*)(tsm64 + TILE_UMAX);                   // [TILE_UMAX] slot of each key (pass 1)
@@ -52,7 +53,7 @@ tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const 
    __shared__ int nuniq, over, nfill;
    const int tile = blockIdx.x;
    const int s0 = tile * ts + threadIdx.x, send = min((tile + 1) * ts, Nown);
-   TileKeyWrap kw{kna, kn1, 0};
+   TileKeyWrap kw{kna, kn1, 0, koff};
    if (kn1 > 0) { const int o0 = orig[tile * ts]; kw.xref = o0 >= 0 ? (o0 / kna) % kn1 : 0; }
    for (int q = threadIdx.x; q < TILE_HASH; q += TILE) tab[q] = -1;
    if (threadIdx.x == 0) { nuniq = 0; over = 0; nfill = 0; }
