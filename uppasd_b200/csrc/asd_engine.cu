@@ -696,10 +696,13 @@ static int ensure_layout(asd_engine* e, int want) {
 // ------------------------------------------------------------------------------------------------
 template <class K>
 static void allow_smem(K kernel, size_t bytes) {
-   // opt in to > 48 KB of dynamic shared memory (once per kernel and size; kernels of one signature share K)
-   static std::map<const void*, size_t> granted;
+   // opt in to > 48 KB of dynamic shared memory: the attribute is per device and per kernel (kernels of one signature
+   // share K, engines of one process may sit on different devices)
+   static std::map<std::pair<int, const void*>, size_t> granted;
    if (bytes <= 48 * 1024) return;
-   size_t& g = granted[(const void*)kernel];
+   int dev = 0;
+   cudaGetDevice(&dev);
+   size_t& g = granted[std::make_pair(dev, (const void*)kernel)];
    if (bytes > g) {
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
       g = bytes;
