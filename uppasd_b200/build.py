@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'asd_engine.cu')
 DEPS = [os.path.join(HERE, 'csrc', f) for f in os.listdir(os.path.join(HERE, 'csrc'))] + \
        [os.path.join(HERE, '..', 'include', 'uppasd_b200.h')]
-OUT = os.path.join(HERE, 'libuppasd_b200.so')
+OUT = os.environ.get('ASD_LIB_OUT') or os.path.join(HERE, 'libuppasd_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math=false',
          '-Xcompiler', '-fPIC', '-shared', '-ccbin', 'g++']

@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libuppasd_b200.so')
+LIB_PATH = os.environ.get('ASD_LIB') or os.path.join(_HERE, 'libuppasd_b200.so')   # ASD_LIB: development builds
 
 c_int_p = C.POINTER(C.c_int)
 c_uint_p = C.POINTER(C.c_uint)

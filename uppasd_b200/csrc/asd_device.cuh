@@ -61,6 +61,8 @@ struct Tables {
    const double* __restrict__ eaniso;  // [3][Npad]
    const double* __restrict__ kaniso;  // [2][Npad]
    const double* __restrict__ sb;      // [Npad]
+   int aniso_rows;                     // 1: anisotropy is the same for every atom of a Hamiltonian row -> aniso_small
+   double aniso_small[8][8];           // [row]{taniso, k1, k2, ex, ey, ez, sb, -} in the kernel-parameter constant bank
    // external field: uniform vector or per-slot array [M][3][Npad]
    int ext_uniform;
    double hext[3];
@@ -83,6 +85,8 @@ struct Tables {
    const int* __restrict__ ucount;    // [ntile]
    const uint4* __restrict__ nl16;    // [zq8][Npad]
    int zq8;               // ceil(z / 8)
+   const uint4* __restrict__ dm16;    // [ceil(zdm/8)][Npad] DM neighbours as positions in the tile's list (null: gather from global)
+   const uint4* __restrict__ bq16;    // [ceil(zbq/8)][Npad] same for the biquadratic table
    // run-compressed table of lattice layouts (asd_runs.cuh): groups of `runs` x-runs share one union row
    int tile_slots;        // slots per tile of ulist / ucount (256; 512 or 1024 with the run kernel on super-bricks)
    int runs;              // 0: off, else 4: the LLG stage kernels use llg_runs_kernel (4 x-runs per warp)
@@ -390,10 +394,20 @@ __device__ __forceinline__ void prefetch_tile(const Tables& t, const SpinVec* S,
 }
 
 // EXCH = false: the Heisenberg sum was already accumulated into bs[] by the caller (staged tile path).
-template <bool REDUCED, bool EXCH = true, int CH = ASD_CHUNK>
+// 16-bit position j of a neighbour word row (8 positions per 16-byte word)
+__device__ __forceinline__ unsigned pos16(const uint4* __restrict__ tab, size_t Npad, int i, int j) {
+   const uint4 w = __ldg(tab + (size_t)(j >> 3) * Npad + i);
+   const unsigned c = ((j >> 1) & 3) == 0 ? w.x : ((j >> 1) & 3) == 1 ? w.y : ((j >> 1) & 3) == 2 ? w.z : w.w;
+   return (j & 1) ? (c >> 16) : (c & 0xffffu);
+}
+
+// s3: the CTA's shared-memory copy of emomM of the tile's gather list (staged kernels), or null.  With s3 and the
+// 16-bit position tables dm16 / bq16 the DM and BQ neighbours are read from shared memory too.
+// XS (compile time: a kernel without DM / BQ work must not carry this code, it costs the plain Heisenberg kernel 15 %).
+template <bool REDUCED, bool EXCH = true, int CH = ASD_CHUNK, bool XS = false>
 __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __restrict__ S, int i, int ih,
                                            const SpinVec& own, const double* smc, const double* smd,
-                                           const double* smb, double bs[3], double bq[3]) {
+                                           const double* smb, double bs[3], double bq[3], const double* __restrict__ s3 = nullptr) {
    double fx = EXCH ? 0.0 : bs[0], fy = EXCH ? 0.0 : bs[1], fz = EXCH ? 0.0 : bs[2];
    const int Npad = t.Npad;
    // ---- Heisenberg (hamiltonianactions.f90:461-464) ----
@@ -430,8 +444,9 @@ __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __res
    if (t.zdm > 0) {
       const int* __restrict__ nl = t.dml + i;
       const int n = REDUCED ? __ldg(t.dmsize + ih) : t.zdm;
+      const bool smem_dm = XS && t.dm16 != nullptr;
+      uint4 wd = make_uint4(0u, 0u, 0u, 0u);
       for (int j = 0; j < n; j++) {
-         const int nb = __ldg(nl + (size_t)j * Npad);
          double Dx, Dy, Dz;
          if (REDUCED) {
             const double* __restrict__ d = (smd ? smd : t.dmv) + ((size_t)ih * t.zdm + j) * 3;
@@ -440,8 +455,16 @@ __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __res
             const size_t o = (size_t)j * Npad + i, s = (size_t)t.zdm * Npad;
             Dx = __ldg(t.dmv + o); Dy = __ldg(t.dmv + s + o); Dz = __ldg(t.dmv + 2 * s + o);
          }
-         const SpinVec v = S[nb];
-         const double mx = v.x * v.m, my = v.y * v.m, mz = v.z * v.m;
+         double mx, my, mz;
+         if (smem_dm) {
+            if ((j & 7) == 0) wd = __ldg(t.dm16 + (size_t)(j >> 3) * Npad + i);
+            const unsigned c = ((j >> 1) & 3) == 0 ? wd.x : ((j >> 1) & 3) == 1 ? wd.y : ((j >> 1) & 3) == 2 ? wd.z : wd.w;
+            const double* __restrict__ m = s3 + ((j & 1) ? (c >> 16) : (c & 0xffffu)) * 3u;
+            mx = m[0]; my = m[1]; mz = m[2];
+         } else {
+            const SpinVec v = S[__ldg(nl + (size_t)j * Npad)];
+            mx = v.x * v.m; my = v.y * v.m; mz = v.z * v.m;
+         }
          fx = fx + Dz * my - Dy * mz;
          fy = fy + Dx * mz - Dz * mx;
          fz = fz + Dy * mx - Dx * my;
@@ -453,11 +476,17 @@ __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __res
    if (t.zbq > 0) {
       const int* __restrict__ nl = t.bql + i;
       const int n = REDUCED ? __ldg(t.bqsize + ih) : t.zbq;
+      const bool smem_bq = XS && t.bq16 != nullptr;
       for (int j = 0; j < n; j++) {
-         const int nb = __ldg(nl + (size_t)j * Npad);
          const double jb = REDUCED ? (smb ? smb : t.jbq)[(size_t)ih * t.zbq + j] : __ldg(t.jbq + (size_t)j * Npad + i);
-         const SpinVec v = S[nb];
-         const double mx = v.x * v.m, my = v.y * v.m, mz = v.z * v.m;
+         double mx, my, mz;
+         if (smem_bq) {
+            const double* __restrict__ m = s3 + pos16(t.bq16, Npad, i, j) * 3u;
+            mx = m[0]; my = m[1]; mz = m[2];
+         } else {
+            const SpinVec v = S[__ldg(nl + (size_t)j * Npad)];
+            mx = v.x * v.m; my = v.y * v.m; mz = v.z * v.m;
+         }
          const double dot = mx * ox + my * oy + mz * oz;
          const double c = 2.0 * jb * dot;
          qx = fma(c, mx, qx);
@@ -467,11 +496,13 @@ __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __res
    }
    // ---- single-ion anisotropy (hamiltonianactions.f90:225-239, 842-919); uses the FULL moment ----
    if (t.do_aniso) {
-      const int ta = __ldg(t.taniso + i);
+      const bool rows = REDUCED && t.aniso_rows;
+      const int ta = rows ? (int)t.aniso_small[ih][0] : __ldg(t.taniso + i);
       if (ta == 1 || ta == 2 || ta == 7) {
-         const double k1 = __ldg(t.kaniso + i), k2 = __ldg(t.kaniso + Npad + i);
+         const double k1 = rows ? t.aniso_small[ih][1] : __ldg(t.kaniso + i), k2 = rows ? t.aniso_small[ih][2] : __ldg(t.kaniso + Npad + i);
          if (ta == 1 || ta == 7) {
-            const double ex = __ldg(t.eaniso + i), ey = __ldg(t.eaniso + Npad + i), ez = __ldg(t.eaniso + 2 * (size_t)Npad + i);
+            const double ex = rows ? t.aniso_small[ih][3] : __ldg(t.eaniso + i), ey = rows ? t.aniso_small[ih][4] : __ldg(t.eaniso + Npad + i),
+                         ez = rows ? t.aniso_small[ih][5] : __ldg(t.eaniso + 2 * (size_t)Npad + i);
             const double tt1 = ox * ex + oy * ey + oz * ez;
             const double tt2 = k1 + 2.0 * k2 * (1.0 - tt1 * tt1);
             const double tt3 = 2.0 * tt1 * tt2;
@@ -483,7 +514,7 @@ __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __res
             const double cy = 2.0 * k1 * oy * (z2 + x2) + 2.0 * k2 * oy * (z2 * x2);
             const double cz = 2.0 * k1 * oz * (x2 + y2) + 2.0 * k2 * oz * (x2 * y2);
             if (ta == 2) { fx += cx; fy += cy; fz += cz; }
-            else { const double s = __ldg(t.sb + i); qx += cx * s; qy += cy * s; qz += cz * s; }
+            else { const double s = rows ? t.aniso_small[ih][6] : __ldg(t.sb + i); qx += cx * s; qy += cy * s; qz += cz * s; }
          }
       }
    }

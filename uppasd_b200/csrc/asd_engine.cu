@@ -96,7 +96,7 @@ struct Layout {
    DevBuf<int> d_ham, d_orig, d_nl, d_lsize, d_dml, d_dmsize, d_bql, d_bqsize, d_taniso;
    DevBuf<int4> d_nl4;
    DevBuf<int> d_ucount, d_ulist;   // staged tile path (asd_tiles.cuh)
-   DevBuf<uint4> d_nl16;
+   DevBuf<uint4> d_nl16, d_dm16, d_bq16;
    DevBuf<int2> d_meta;
    DevBuf<uint4> d_utab;            // run-compressed table (asd_runs.cuh)
    DevBuf<int> d_gcount;
@@ -203,6 +203,7 @@ static int lattice_colours(asd_engine* e);
 static int build_tiles(asd_engine* e, Layout& L, int ts) {
    Tables& t = L.t;
    t.staged = 0; t.ucap = 0; t.ulist = nullptr; t.ucount = nullptr; t.nl16 = nullptr; t.zq8 = (t.z + 7) / 8;
+   t.dm16 = nullptr; t.bq16 = nullptr;
    t.tile_slots = ts;
    const char* env = std::getenv("ASD_STAGED");
    if ((env && atoi(env) == 0) || L.is_mc || t.z <= 0) return 0;
@@ -216,9 +217,14 @@ static int build_tiles(asd_engine* e, Layout& L, int ts) {
    cudaStream_t st = e->stream;
    int r;
    if ((r = L.d_ucount.alloc(ntile))) return r;
+   // DM / BQ neighbours join the gather lists (ASD_STAGE_DM=0: keep gathering them from global memory)
+   TileExtra x;
+   memset(&x, 0, sizeof x);
+   const char* sdm = std::getenv("ASD_STAGE_DM");
+   if (!(sdm && atoi(sdm) == 0) && ts == 1024) { x.zdm = t.zdm; x.dml = t.dml; x.zbq = t.zbq; x.bql = t.bql; }   // read by llg_runs_kernel<.., 8, .., XS>
    const size_t smem = TILE_BUILD_SMEM;
    CU(cudaFuncSetAttribute(tile_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 0, 0, L.d_ucount.p, nullptr, nullptr, t.zq8, kna, kn1, koff, ts);
+   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 0, 0, L.d_ucount.p, nullptr, nullptr, t.zq8, kna, kn1, koff, ts, x);
    e->launches++;
    CU(cudaGetLastError());
    std::vector<int> cnt(ntile);
@@ -229,7 +235,9 @@ static int build_tiles(asd_engine* e, Layout& L, int ts) {
    const int ucap = ((mx + 31) / 32) * 32;
    if ((r = L.d_ulist.alloc((size_t)ntile * ucap))) return r;
    if ((r = L.d_nl16.alloc((size_t)t.zq8 * Npad))) return r;
-   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 1, ucap, L.d_ucount.p, L.d_ulist.p, L.d_nl16.p, t.zq8, kna, kn1, koff, ts);
+   if (x.zdm > 0) { if ((r = L.d_dm16.alloc((size_t)((x.zdm + 7) / 8) * Npad))) return r; x.dm16 = L.d_dm16.p; }
+   if (x.zbq > 0) { if ((r = L.d_bq16.alloc((size_t)((x.zbq + 7) / 8) * Npad))) return r; x.bq16 = L.d_bq16.p; }
+   tile_gather_kernel<<<ntile, TILE, smem, st>>>(t.Nown, (int)Npad, t.z, t.nl, t.ham, key, 1, ucap, L.d_ucount.p, L.d_ulist.p, L.d_nl16.p, t.zq8, kna, kn1, koff, ts, x);
    e->launches++;
    CU(cudaGetLastError());
    CU(cudaStreamSynchronize(st));
@@ -240,6 +248,7 @@ static int build_tiles(asd_engine* e, Layout& L, int ts) {
    CU(cudaStreamSynchronize(st));
    t.meta = L.d_meta.p;
    t.staged = 1; t.ucap = ucap; t.ulist = L.d_ulist.p; t.ucount = L.d_ucount.p; t.nl16 = L.d_nl16.p;
+   t.dm16 = x.dm16; t.bq16 = x.bq16;
    return 0;
 }
 
@@ -394,6 +403,31 @@ static int finish_layout(asd_engine* e, Layout& L) {
       if ((r = permute(e->kaniso, 2, false, L.d_kaniso))) return r;
       if ((r = permute(e->sb, 1, false, L.d_sb))) return r;
       t.do_aniso = 1; t.taniso = L.d_taniso.p; t.eaniso = L.d_eaniso.p; t.kaniso = L.d_kaniso.p; t.sb = L.d_sb.p;
+      // same anisotropy on every atom of a Hamiltonian row (the usual case of do_reduced Y): constant bank, no loads
+      t.aniso_rows = 0;
+      if (L.reduced && NH <= 8) {
+         std::vector<int> first(NH, -1);
+         bool uni = true;
+         for (int i = 0; i < N && uni; i++) {
+            const int h = e->aHam[i] - 1;
+            if (first[h] < 0) { first[h] = i; continue; }
+            const int f = first[h];
+            uni = e->taniso[i] == e->taniso[f] && e->kaniso[2 * (size_t)i] == e->kaniso[2 * (size_t)f] &&
+                  e->kaniso[2 * (size_t)i + 1] == e->kaniso[2 * (size_t)f + 1] && e->sb[i] == e->sb[f] &&
+                  e->eaniso[3 * (size_t)i] == e->eaniso[3 * (size_t)f] && e->eaniso[3 * (size_t)i + 1] == e->eaniso[3 * (size_t)f + 1] &&
+                  e->eaniso[3 * (size_t)i + 2] == e->eaniso[3 * (size_t)f + 2];
+         }
+         if (uni) {
+            for (int h = 0; h < NH; h++) {
+               const int f = std::max(first[h], 0);
+               double* a = t.aniso_small[h];
+               a[0] = (double)e->taniso[f]; a[1] = e->kaniso[2 * (size_t)f]; a[2] = e->kaniso[2 * (size_t)f + 1];
+               a[3] = e->eaniso[3 * (size_t)f]; a[4] = e->eaniso[3 * (size_t)f + 1]; a[5] = e->eaniso[3 * (size_t)f + 2];
+               a[6] = e->sb[f]; a[7] = 0.0;
+            }
+            t.aniso_rows = 1;
+         }
+      }
    }
    if ((r = apply_external_field(e, L))) return r;
    if (!e->btorque.empty()) { if ((r = permute(e->btorque, 3, true, L.d_btorque))) return r; t.btorque = L.d_btorque.p; }
@@ -716,16 +750,16 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
       const int NW = L.t.tile_slots / 128;
       const size_t smem = (size_t)((L.t.sm_dm + L.t.sm_bq + 1) & ~1) * sizeof(double) + (size_t)3 * (L.t.ucap + 32) * sizeof(double) +
                           (size_t)NW * L.t.urow * sizeof(uint4);
-      if (NW == 8) {
-         allow_smem(llg_runs_kernel<SOLVER, STAGE, 8, EDGE, MSUM>, smem);
-         llg_runs_kernel<SOLVER, STAGE, 8, EDGE, MSUM><<<g, 256, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
-      } else if (NW == 4) {
-         allow_smem(llg_runs_kernel<SOLVER, STAGE, 4, EDGE, MSUM>, smem);
-         llg_runs_kernel<SOLVER, STAGE, 4, EDGE, MSUM><<<g, 128, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
-      } else {
-         allow_smem(llg_runs_kernel<SOLVER, STAGE, 2, EDGE, MSUM>, smem);
-         llg_runs_kernel<SOLVER, STAGE, 2, EDGE, MSUM><<<g, 64, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
-      }
+      const bool xs = L.t.dm16 != nullptr || L.t.bq16 != nullptr;
+#define ASD_LAUNCH_RUNS(NWV, XSV)                                                                                                  \
+      do {                                                                                                                         \
+         allow_smem(llg_runs_kernel<SOLVER, STAGE, NWV, EDGE, MSUM, XSV>, smem);                                                   \
+         llg_runs_kernel<SOLVER, STAGE, NWV, EDGE, MSUM, XSV><<<g, NWV * 32, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p); \
+      } while (0)
+      if (NW == 8) { if (xs) ASD_LAUNCH_RUNS(8, true); else ASD_LAUNCH_RUNS(8, false); }
+      else if (NW == 4) ASD_LAUNCH_RUNS(4, false);
+      else ASD_LAUNCH_RUNS(2, false);
+#undef ASD_LAUNCH_RUNS
    } else if (L.t.staged) {
       const size_t smem = L.smem_bytes + (size_t)3 * L.t.ucap * sizeof(double);
       if (L.reduced) {

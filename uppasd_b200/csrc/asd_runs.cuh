@@ -156,7 +156,8 @@ struct RunLoop<R, 0> {
 // One stage of one LLG step on a tile of NW*128 slots = NW groups of R = 4 x-runs (NW = 2, 4, 8: tiles of 256, 512,
 // 1024 slots = 1, 2, 4 bricks of a super-brick): NW warps, thread (warp w, lane l) owns the atoms
 // tile*TS + (w*4 + r)*32 + l, r = 0..3.  Same contract as llg_stage_kernel (asd_device.cuh).
-template <int SOLVER, int STAGE, int NW, bool EDGE, bool MSUM>
+// XS: the layout's DM / BQ neighbours are in the gather list too (dm16 / bq16) and are read from shared memory.
+template <int SOLVER, int STAGE, int NW, bool EDGE, bool MSUM, bool XS>
 __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : (NW == 4) ? 4 : 6)
 llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgParams p, const __grid_constant__ EdgeParams ep,
                 const TileRange tr, SpinVec* __restrict__ cur, SpinVec* __restrict__ pred, double* __restrict__ b2eff) {
@@ -263,7 +264,7 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
       if (STAGE == 2) old_n = curk[inext];
       if (io >= 0) {
          double bs[3] = {f[0][0], f[0][1], f[0][2]}, bq[3];
-         site_field<true, false>(t, S, i, ih, own, smc, smd, smb, bs, bq);
+         site_field<true, false, ASD_CHUNK, XS>(t, S, i, ih, own, smc, smd, smb, bs, bq, s3);
          double h[3];
          ext_field(t, i, k, h);
          const double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};

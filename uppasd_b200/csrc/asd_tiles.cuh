@@ -30,6 +30,16 @@ constexpr size_t TILE_BUILD_SMEM = (size_t)TILE_HASH * 4 + (size_t)TILE_UMAX * (
 // rotated range (first cell at koff = (kn1 - BX) / 2): any N1 >= BX + 2 * reach keeps every neighbour run unsplit.
 struct TileKeyWrap { int kna, kn1, xref, koff; };
 
+// the DM and BQ tables of the layout (z = 0: absent): their neighbours join the tile's gather list and get their own
+// 16-bit position tables, so that the stage kernels read them from shared memory as well
+struct TileExtra {
+   int zdm, zbq;
+   const int* __restrict__ dml;
+   const int* __restrict__ bql;
+   uint4* __restrict__ dm16;   // [ceil(zdm/8)][Npad]
+   uint4* __restrict__ bq16;   // [ceil(zbq/8)][Npad]
+};
+
 __device__ __forceinline__ unsigned long long tile_key(const int* __restrict__ ham, const int* __restrict__ orig, int slot,
                                                        const TileKeyWrap& kw) {
    int o = orig[slot];
@@ -45,7 +55,7 @@ __device__ __forceinline__ unsigned long long tile_key(const int* __restrict__ h
 __global__ void __launch_bounds__(TILE)
 tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const int* __restrict__ ham, const int* __restrict__ orig,
                    int pass, int ucap, int* __restrict__ ucount, int* __restrict__ ulist, uint4* __restrict__ nl16, int zq8,
-                   int kna, int kn1, int koff, int ts) {
+                   int kna, int kn1, int koff, int ts, const TileExtra x) {
    extern __shared__ unsigned long long tsm64[];
    unsigned long long* keys = tsm64;                       // [TILE_UMAX] (pass 1)
    int* lst = (int*)(tsm64 + TILE_UMAX);                   // [TILE_UMAX] slot of each key (pass 1)
@@ -71,6 +81,8 @@ tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const 
    for (int s = s0; s < send; s += TILE) {
       insert(s);
       for (int j = 0; j < z; j++) insert(nl[(size_t)j * Npad + s]);
+      for (int j = 0; j < x.zdm; j++) insert(x.dml[(size_t)j * Npad + s]);
+      for (int j = 0; j < x.zbq; j++) insert(x.bql[(size_t)j * Npad + s]);
    }
    __syncthreads();
    if (pass == 0) {
@@ -124,6 +136,20 @@ tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const 
             v[u] = (j < z) ? find(nl[(size_t)j * Npad + s]) : self;
          }
          nl16[(size_t)q * Npad + s] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+      }
+      for (int kind = 0; kind < 2; kind++) {
+         const int zz = kind ? x.zbq : x.zdm;
+         const int* __restrict__ tab = kind ? x.bql : x.dml;
+         uint4* __restrict__ out = kind ? x.bq16 : x.dm16;
+         for (int q = 0; 8 * q < zz; q++) {
+            unsigned v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+               const int j = 8 * q + u;
+               v[u] = (j < zz) ? find(tab[(size_t)j * Npad + s]) : self;
+            }
+            out[(size_t)q * Npad + s] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+         }
       }
    }
 }
