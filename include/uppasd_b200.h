@@ -84,6 +84,12 @@ void fortrandata_setextras_(double* Landeg, double* lambda1_array, double* tempr
                             unsigned int* nn_bq_tot, unsigned int* bqlist, unsigned int* bqlistsize,
                             double* j_bq);
 
+/* Shape of the supercell behind the tables of fortrandata_setmatrices_ (inputdata: NA, N1, N2, N3, BC1..BC3; the atom order
+ * is i0 + NA*(ix + N1*(iy + N2*iz)), geometry.f90:440-460).  Optional: with it the engine orders the atoms in bricks and
+ * the Fortran-built nlist runs on the fast path of device-built lattices (asd_set_lattice_hint); results do not change. */
+void fortrandata_setlattice_(unsigned int* NA, unsigned int* N1, unsigned int* N2, unsigned int* N3, char* BC1, char* BC2,
+                             char* BC3);
+
 /* Callbacks into the host (reference: source/gpu_files/c_helper.h:30-37, bodies in chelper.f90:73-160).
  * When the library is linked into the Fortran program the gfortran-mangled symbols
  * __chelper_MOD_fortran_* are picked up automatically (weak references).  A non-Fortran host registers
@@ -100,6 +106,10 @@ void asd_set_callbacks(asd_cb_do_measurements do_meas, asd_cb_measure_moment mea
  * (2) Explicit API
  * ---------------------------------------------------------------------------------------------- */
 typedef struct asd_engine asd_engine;
+
+/* the engine behind the legacy symbols (NULL before cudamdsim_initiateconstants_): lets a host use the explicit
+ * API (asd_measure, asd_layout_info, ...) on the state the legacy calls created */
+asd_engine* asd_legacy_engine(void);
 
 const char* asd_last_error(void);
 int asd_device_count(void);
@@ -123,6 +133,13 @@ int asd_set_dm(asd_engine* e, int max_no_dmneigh, const int* dmlist, const int* 
 /* biquadratic table: bqlist(zbq,N), bqlistsize(NH), j_bq(zbq,NH). */
 int asd_set_bq(asd_engine* e, int nn_bq_tot, const int* bqlist, const int* bqlistsize, const double* j_bq);
 /* single-ion anisotropy: taniso(N) in {0,1,2,7}, eaniso(3,N), kaniso(2,N), sb(N). */
+/* Optional: the tables describe a supercell of N1 x N2 x N3 cells with NA atoms each in the reference's atom order
+ * (i0 + NA*(ix + N1*(iy + N2*iz))); bc3 = "PP0"-style boundary conditions.  The engine then stores the atoms in brick
+ * order (like asd_build_lattice_table does) and checks ON THE DEVICE whether the host's tables have the regularity the
+ * run-compressed kernel needs; if not, or without this call, the one-atom-per-thread kernels run.  Results are
+ * independent of the hint (parity bar 1e-12). */
+int asd_set_lattice_hint(asd_engine* e, int NA, int N1, int N2, int N3, const char* bc3);
+
 int asd_set_anisotropy(asd_engine* e, const int* taniso, const double* eaniso, const double* kaniso,
                        const double* sb);
 /* external_field(3,N,M) (calculatefields.f90:23-82) and optional spin-transfer torque field btorque(3,N,M). */
@@ -185,8 +202,8 @@ int asd_time_mc_sweeps(asd_engine* e, char mode, long nsweeps, double temperatur
 /* which field path the LLG stage kernels of the committed layout use: info[0] = 1 if the tile's gather list is staged
  * in shared memory, info[1] = R of the run-compressed register-blocked kernel (0: one atom per thread), info[2] =
  * largest gather list of a tile, info[3] = largest number of distinct neighbour runs of a group of R runs,
- * info[4] = slots per tile (256, 512 or 1024) */
-int asd_layout_info(asd_engine* e, int* info5);
+ * info[4] = slots per tile (256, 512 or 1024), info[5] = 1 if the DM / BQ neighbours are read from shared memory too */
+int asd_layout_info(asd_engine* e, int* info6);
 long asd_launch_count(asd_engine* e);
 int asd_synchronize(asd_engine* e);
 

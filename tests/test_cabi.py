@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     src = open(os.path.join(ROOT, 'include', 'uppasd_b200.h')).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
-    names = re.findall(r'^\s*(?:const\s+)?(?:void|int|long|char\s*\*|const char\s*\*)\s*\*?\s*(\w+)\s*\(', src, flags=re.M)
+    names = re.findall(r'^\s*(?:const\s+)?(?:void|int|long|char\s*\*|const char\s*\*|asd_engine\s*\*)\s*\*?\s*(\w+)\s*\(', src, flags=re.M)
     return sorted(set(n for n in names if not n.startswith('asd_cb_')))
 
 

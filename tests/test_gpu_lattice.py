@@ -146,3 +146,71 @@ def test_irregular_lattice_keeps_the_staged_kernel(monkeypatch):
     for _ in range(30):
         st.step()
     assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12
+
+
+@pytest.mark.parametrize('reduced', ['Y', 'N'])
+def test_host_tables_with_lattice_hint_take_the_fast_path(reduced):
+    """The drop-in case: nlist / ncoup built by the (Fortran) host in the reference's atom order, plus the supercell shape
+    (asd_set_lattice_hint / fortrandata_setlattice_).  The engine stores the atoms in bricks; with do_reduced Y the
+    device-side check accepts the host's table for the run kernel, with do_reduced N the staged kernel runs on the
+    brick order.  Same trajectory as the oracle and as the same engine without the hint."""
+    from uppasd_b200 import host
+    fx, _, _ = load_golden('bccfe_cuda')
+    args = list(inputs.load_fixture(fx))
+    args[0] = dict(args[0], ncell=(64, 4, 6), mensemble=2, do_reduced=reduced, hfield=(0.1, 0.0, 0.2))
+    S = orc.build_system(*args)
+    inp = args[0]
+    rng = np.random.default_rng(5)
+    e0 = rng.normal(size=(3, S['Natom'], 2)); e0 /= np.sqrt((e0 ** 2).sum(axis=0))
+    S['emom'] = np.asfortranarray(e0)
+    S['emomM'] = np.asfortranarray(e0 * S['mmom'][None])
+    hint = (S['NA'], inp['ncell'], inp['bc'])
+    for solver in (1, 5):
+        eh = host.engine_from_system(S, orc.CONST, sdealgh=solver, delta_t=inp['timestep'], damping=0.2, lattice_hint=hint)
+        ep = host.engine_from_system(S, orc.CONST, sdealgh=solver, delta_t=inp['timestep'], damping=0.2)
+        ih, ip = eh.layout_info(), ep.layout_info()
+        assert ip['runs'] == 0 and ip['tile_slots'] == 256
+        if reduced == 'Y':
+            assert ih['runs'] == 4 and ih['tile_slots'] == 1024, ih
+        else:
+            assert ih['runs'] == 0 and ih['staged'] == 1, ih
+        rb, _ = orc.effective_field(S)
+        for e in (eh, ep):
+            beff, _ = e.effective_field()
+            assert np.abs(beff - rb).max() <= 1e-12 * np.abs(rb).max()
+        st = orc.SdState(S, solver, inp['timestep'], 0.2)
+        for _ in range(30):
+            st.step()
+        for e in (eh, ep):
+            e.sd_steps(30)
+            assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12, (solver, reduced)
+        # a shape that does not match the tables is ignored, not trusted
+        ew = host.engine_from_system(S, orc.CONST, sdealgh=solver, delta_t=inp['timestep'], damping=0.2,
+                                     lattice_hint=(S['NA'], (64, 4, 5), inp['bc']))
+        assert ew.layout_info()['runs'] == 0
+        ew.sd_steps(30)
+        assert np.abs(ew.get_moments()[0] - st.emom).max() <= 1e-12
+
+
+def test_legacy_boundary_with_lattice_shape():
+    """fortrandata_setlattice_ + the reference's own call sequence: the Fortran-built table of a bcc supercell runs on the
+    run-compressed kernel behind the legacy symbols; final state = oracle."""
+    from uppasd_b200 import host
+    fx, _, _ = load_golden('bccfe_cuda')
+    args = list(inputs.load_fixture(fx))
+    args[0] = dict(args[0], ncell=(64, 4, 4), do_reduced='Y')
+    S = orc.build_system(*args)
+    inp = args[0]
+    rng = np.random.default_rng(9)
+    e0 = rng.normal(size=(3, S['Natom'], 1)); e0 /= np.sqrt((e0 ** 2).sum(axis=0))
+    S['emom'] = np.asfortranarray(e0)
+    S['emomM'] = np.asfortranarray(e0 * S['mmom'][None])
+    fh = host.FortranHost(S, orc.CONST, sdealgh=1, nstep=60, delta_t=inp['timestep'], damping=0.3, avrg_step=20,
+                          lattice=(S['NA'], inp['ncell'], inp['bc'])).run()
+    info = fh.layout_info()
+    assert info['runs'] == 4 and info['tile_slots'] == 1024, info
+    st = orc.SdState(S, 1, inp['timestep'], 0.3)
+    for _ in range(60):
+        st.step()
+    assert np.abs(fh.arr['emom'] - st.emom).max() <= 1e-12
+    assert sorted(fh.averages) == [0, 20, 40, 60]

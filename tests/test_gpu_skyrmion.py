@@ -82,6 +82,10 @@ def test_triangular_dmi_field_relaxation(tmp_path):
     sim = driver.Simulation(path)
     inp, S = _oracle_system(path, 2)
     e = sim.engine
+    # 64 x 32 cells, one basis atom: 32 x 8 bricks, four of them (adjacent in y) per 1024-slot tile -> run kernel with the DM
+    # neighbours in the shared-memory gather list
+    info = e.layout_info()
+    assert info['runs'] == 4 and info['tile_slots'] == 1024 and info['extra_staged'] == 1, info
     # tables built on the device from the files = the oracle's, bit for bit (2-D bricks, open boundary along z)
     for kind, key in ((0, 'exchange'), (1, 'dm')):
         lst, size, coup = e.get_table(kind)

@@ -21,6 +21,7 @@ SYMBOLS = {
     'fortrandata_setmatrices_': (None, [vp] * 24),
     'fortrandata_setinputdata_': (None, [vp] * 3),
     'fortrandata_setextras_': (None, [vp] * 8),
+    'fortrandata_setlattice_': (None, [vp] * 7),
     'cudamdsim_initiateconstants_': (None, []),
     'cudamdsim_initiatematrices_': (None, []),
     'cudamdsim_measurementphase_': (None, []),
@@ -30,6 +31,7 @@ SYMBOLS = {
     'cmdsim_initiatefortran_': (None, []),
     'cmdsim_measurementphase_': (None, []),
     'asd_set_callbacks': (None, [CB_DO, CB_MEASURE, CB_FLUSH, CB_STATUS]),
+    'asd_legacy_engine': (vp, []),
     'asd_last_error': (C.c_char_p, []),
     'asd_device_count': (C.c_int, []),
     'asd_create': (C.c_int, [C.POINTER(vp), C.c_int]),
@@ -39,6 +41,7 @@ SYMBOLS = {
     'asd_set_exchange': (C.c_int, [vp, C.c_int, vp, vp, vp]),
     'asd_set_dm': (C.c_int, [vp, C.c_int, vp, vp, vp]),
     'asd_set_bq': (C.c_int, [vp, C.c_int, vp, vp, vp]),
+    'asd_set_lattice_hint': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]),
     'asd_set_anisotropy': (C.c_int, [vp, vp, vp, vp, vp]),
     'asd_set_external_field': (C.c_int, [vp, vp]),
     'asd_set_torque': (C.c_int, [vp, vp]),

@@ -164,6 +164,10 @@ struct asd_engine {
    Layout sd, mc;
    bool sd_built = false, mc_built = false;
    bool lattice_built = false;  // tables live on the device only (asd_build_lattice_table)
+   // host tables of a supercell in the reference's atom order (asd_set_lattice_hint): the SD layout is put in brick
+   // order like a device-built lattice, so that the same tile / run machinery applies to tables the Fortran host built
+   struct { int on = 0, NA = 0, N1 = 0, N2 = 0, N3 = 0, periodic[3] = {0, 0, 0}; } hint;
+   bool lat_ordered = false;    // the SD layout of host tables is in brick order (e->lat describes it)
    int state_layout = 0;  // 0 = none, 1 = sd, 2 = mc
    DevBuf<SpinVec> cur, pred;
    DevBuf<double> b2eff, esite, part, red;
@@ -197,6 +201,8 @@ static int slab_commit(asd_engine* e);
 static int materialise_host_tables(asd_engine* e);
 static int slab_push_state(asd_engine* e);
 static int lattice_colours(asd_engine* e);
+static int fill_lattice_desc(asd_engine* e, int NA, int N1, int N2, int N3l, int N3g, const int* periodic, bool reduced);
+static bool has_lattice(const asd_engine* e) { return e->lattice_built || e->lat_ordered; }
 
 // staged tile path: gather lists + 16-bit neighbour table (asd_tiles.cuh).  Leaves t.staged = 0 when a tile would
 // need more than TILE_UMAX unique slots (layout without locality) or when switched off (ASD_STAGED=0).
@@ -212,7 +218,7 @@ static int build_tiles(asd_engine* e, Layout& L, int ts) {
    const int ntile = (t.Nown + ts - 1) / ts;
    const int* key = L.d_okey.p ? L.d_okey.p : t.orig;
    // lattice layouts: rotate x in the sort key so that periodic images stay next to the tile (asd_tiles.cuh)
-   const bool wrap = L.d_okey.p && e->lattice_built && e->lat.periodic[0] && e->lat.N1 > e->lat.BX && !(std::getenv("ASD_KEYWRAP") && atoi(std::getenv("ASD_KEYWRAP")) == 0);
+   const bool wrap = L.d_okey.p && has_lattice(e) && e->lat.periodic[0] && e->lat.N1 > e->lat.BX && !(std::getenv("ASD_KEYWRAP") && atoi(std::getenv("ASD_KEYWRAP")) == 0);
    const int kna = wrap ? e->lat.NA : 0, kn1 = wrap ? e->lat.N1 : 0, koff = wrap ? (e->lat.N1 - e->lat.BX) / 2 : 0;
    cudaStream_t st = e->stream;
    int r;
@@ -258,7 +264,7 @@ static int build_runs(asd_engine* e, Layout& L) {
    constexpr int R = 4;
    Tables& t = L.t;
    t.runs = 0; t.urow = 0; t.utab = nullptr;
-   if (!t.staged || !L.reduced || !t.cpl_param || L.is_mc || !e->lattice_built) return 0;
+   if (!t.staged || !L.reduced || !t.cpl_param || L.is_mc || !has_lattice(e)) return 0;
    if (t.z * R >= RUN_MAXPAIR) return 0;
    const int ngroup = (t.Nown + R * 32 - 1) / (R * 32);
    const int ntile = (t.Nown + t.tile_slots - 1) / t.tile_slots;
@@ -351,11 +357,11 @@ static int finish_layout(asd_engine* e, Layout& L) {
          t.cpl_param = 1;
       }
       // tile size of the run kernel: the whole super-brick by default
-      int big = (e->lattice_built && !L.is_mc) ? 256 * e->lat.SY * e->lat.SZ : 256;
+      int big = (has_lattice(e) && !L.is_mc) ? 256 * e->lat.SY * e->lat.SZ : 256;
       const char* renv = std::getenv("ASD_RUNS");
       if (renv) big = atoi(renv);
       if (big != 0 && big != 256 && big != 512 && big != 1024) return fail(-1, "ASD_RUNS must be 0, 256, 512 or 1024");
-      if (big > 256 && (!e->lattice_built || 256 * e->lat.SY * e->lat.SZ % big != 0)) big = 256;
+      if (big > 256 && (!has_lattice(e) || L.is_mc || 256 * e->lat.SY * e->lat.SZ % big != 0)) big = 256;
       if (big >= 256 && (renv || big > 256)) {
          if ((r = build_tiles(e, L, big))) return r;
          if ((r = build_runs(e, L))) return r;
@@ -488,25 +494,52 @@ static int build_layout(asd_engine* e, Layout& L, bool colour_major) {
    L.N = N; L.NH = NH; L.M = M;
    L.reduced = NH < N;
    L.is_mc = colour_major;
-   // ---- ordering: groups = (colour, ham row) for MC, (ham row) for SD; stable within a group ----
+   // ---- ordering: groups = (colour, ham row) for MC, (ham row) for SD; stable within a group.  SD layout of a
+   //      supercell whose shape the host announced (asd_set_lattice_hint): brick order, like a device-built lattice ----
    std::vector<int> colour;
    int ncol = 1;
    if (colour_major) ncol = colour_graph(e, colour);
    const int nrow = L.reduced ? NH : 1;
-   std::vector<long> gcount((size_t)ncol * nrow, 0);
-   auto group_of = [&](int i) { return (size_t)(colour_major ? colour[i] : 0) * nrow + (L.reduced ? e->aHam[i] - 1 : 0); };
-   for (int i = 0; i < N; i++) gcount[group_of(i)]++;
-   std::vector<long> gstart(gcount.size() + 1, 0);
-   for (size_t g = 0; g < gcount.size(); g++) gstart[g + 1] = gstart[g] + ((gcount[g] + 31) / 32) * 32;
-   const long Npad = gstart.back();
-   if (Npad > 2000000000L) return fail(-3, "too many atoms for 32-bit device indices");
-   L.Npad = (int)Npad;
-   L.orig.assign(Npad, -1);
-   L.slot_of.assign(N, -1);
-   {
+   bool brick = false;
+   if (!colour_major) {
+      e->lat_ordered = false;
+      const auto& h = e->hint;
+      brick = h.on && !e->lattice_built && (long)h.NA * h.N1 * h.N2 * h.N3 == N && (!L.reduced || NH == h.NA);
+      if (brick && L.reduced)
+         for (int i = 0; i < N && brick; i++) if (e->aHam[i] != i % h.NA + 1) brick = false;
+      const char* env = std::getenv("ASD_HINT");
+      if (env && atoi(env) == 0) brick = false;
+   }
+   std::vector<long> gstart;
+   if (brick) {
+      const auto& h = e->hint;
+      int r = fill_lattice_desc(e, h.NA, h.N1, h.N2, h.N3, h.N3, h.periodic, L.reduced);
+      if (r) return r;
+      const LatticeDesc& d = e->lat;
+      L.Npad = d.Npad;
+      L.orig.assign(d.Npad, -1);
+      L.slot_of.assign(N, -1);
+      for (int i = 0; i < N; i++) {
+         const int i0 = i % h.NA, c = i / h.NA;
+         const int s = lattice_slot(d, i0, c % h.N1, (c / h.N1) % h.N2, c / (h.N1 * h.N2));
+         L.orig[s] = i; L.slot_of[i] = s;
+      }
+      e->lat_ordered = true;
+   } else {
+      std::vector<long> gcount((size_t)ncol * nrow, 0);
+      auto group_of = [&](int i) { return (size_t)(colour_major ? colour[i] : 0) * nrow + (L.reduced ? e->aHam[i] - 1 : 0); };
+      for (int i = 0; i < N; i++) gcount[group_of(i)]++;
+      gstart.assign(gcount.size() + 1, 0);
+      for (size_t g = 0; g < gcount.size(); g++) gstart[g + 1] = gstart[g] + ((gcount[g] + 31) / 32) * 32;
+      const long Npad = gstart.back();
+      if (Npad > 2000000000L) return fail(-3, "too many atoms for 32-bit device indices");
+      L.Npad = (int)Npad;
+      L.orig.assign(Npad, -1);
+      L.slot_of.assign(N, -1);
       std::vector<long> fill(gstart.begin(), gstart.end() - 1);
       for (int i = 0; i < N; i++) { long s = fill[group_of(i)]++; L.orig[s] = i; L.slot_of[i] = (int)s; }
    }
+   const long Npad = L.Npad;
    L.colour_first.clear(); L.colour_count.clear();
    if (colour_major)
       for (int c = 0; c < ncol; c++) {
@@ -519,6 +552,8 @@ static int build_layout(asd_engine* e, Layout& L, bool colour_major) {
    int r;
    if ((r = L.d_ham.upload(ham, st))) return r;
    if ((r = L.d_orig.upload(L.orig, st))) return r;
+   if (brick) { if ((r = L.d_okey.upload(L.orig, st))) return r; }   // sort key of the gather lists = atom index (x fastest)
+   else L.d_okey.release();
    Tables& t = L.t;
    memset(&t, 0, sizeof t);
    t.N = N; t.Npad = L.Npad; t.Nown = L.Npad; t.M = M; t.NH = NH; t.reduced = L.reduced ? 1 : 0;
@@ -1097,6 +1132,14 @@ int asd_set_exchange(asd_engine* e, int z, const int* nlist, const int* nlistsiz
 int asd_set_dm(asd_engine* e, int z, const int* dmlist, const int* dmlistsize, const double* dm_vect) { return set_table(e, e->dm, z, 3, dmlist, dmlistsize, dm_vect); }
 int asd_set_bq(asd_engine* e, int z, const int* bqlist, const int* bqlistsize, const double* j_bq) { return set_table(e, e->bq, z, 1, bqlist, bqlistsize, j_bq); }
 
+int asd_set_lattice_hint(asd_engine* e, int NA, int N1, int N2, int N3, const char* bc3) {
+   if (NA < 1 || N1 < 1 || N2 < 1 || N3 < 1 || !bc3) return fail(-1, "bad lattice hint");
+   e->hint.on = 1; e->hint.NA = NA; e->hint.N1 = N1; e->hint.N2 = N2; e->hint.N3 = N3;
+   for (int a = 0; a < 3; a++) e->hint.periodic[a] = (bc3[a] == 'P' || bc3[a] == 'p') ? 1 : 0;
+   e->committed = false;
+   return 0;
+}
+
 int asd_set_anisotropy(asd_engine* e, const int* taniso, const double* eaniso, const double* kaniso, const double* sb) {
    if (e->N == 0) return fail(-2, "asd_set_system must be called first");
    e->taniso.assign(taniso, taniso + e->N);
@@ -1472,11 +1515,12 @@ int asd_slab_status(asd_engine* e, unsigned long long* epoch, int* error_flag) {
    return 0;
 }
 
-int asd_layout_info(asd_engine* e, int* info5) {
+int asd_layout_info(asd_engine* e, int* info5 /* 6 ints */) {
    if (!e->committed) return fail(-2, "asd_commit has not been called");
    const Tables& t = e->sd.t;
    info5[0] = t.staged; info5[1] = t.runs; info5[2] = t.ucap; info5[3] = t.runs ? t.urow - 2 : 0;   // urow = header + entries + spare
    info5[4] = t.tile_slots;
+   info5[5] = (t.runs && (t.dm16 != nullptr || t.bq16 != nullptr)) ? 1 : 0;
    return 0;
 }
 

@@ -55,6 +55,27 @@ static void choose_brick(LatticeDesc& d) {
    d.NSY = (d.NTY + d.SY - 1) / d.SY; d.NSZ = (d.NTZ + d.SZ - 1) / d.SZ;
 }
 
+// shape, brick order and slot counts of a supercell (slab settings from e->slab)
+static int fill_lattice_desc(asd_engine* e, int NA, int N1, int N2, int N3l, int N3g, const int* periodic, bool reduced) {
+   LatticeDesc& d = e->lat;
+   const Slab& sb = e->slab;
+   memset(&d, 0, sizeof d);
+   d.NA = NA; d.N1 = N1; d.N2 = N2; d.N3 = N3l;
+   for (int a = 0; a < 3; a++) d.periodic[a] = periodic[a];
+   d.reduced = reduced ? 1 : 0;
+   d.Ncell = N1 * N2 * N3l;
+   d.N = e->N;
+   d.slab = sb.on; d.N3g = N3g; d.z0 = sb.on ? sb.g * N3l : 0; d.H = sb.on ? sb.H : 0;
+   d.has_lo = sb.on && (d.periodic[2] || sb.g > 0);
+   d.has_hi = sb.on && (d.periodic[2] || sb.g < sb.G - 1);
+   choose_brick(d);
+   const long nown = (long)d.NTX * d.NSY * d.NSZ * d.SY * d.SZ * d.NA * d.P;
+   const long np = ((nown + 2L * d.H * NA * N1 * N2 + 31) / 32) * 32;
+   if (np > 2000000000L) return fail(-3, "too many atoms for 32-bit device indices");
+   d.Nown = (int)nown; d.Npad = (int)np;
+   return 0;
+}
+
 extern "C" {
 
 int asd_build_lattice_table(asd_engine* e, int kind, int NA, int N1, int N2, int N3, const char* bc3, int maxslot,
@@ -72,20 +93,11 @@ int asd_build_lattice_table(asd_engine* e, int kind, int NA, int N1, int N2, int
    if (sb.on && (N3 % sb.G != 0 || N3l < sb.H)) return fail(-1, "slab: N3 = %d must be a multiple of the %d slabs and each slab at least %d planes thick", N3, sb.G, sb.H);
    if ((long)NA * N1 * N2 * N3l != e->N) return fail(-1, "NA*N1*N2*N3%s = %ld does not match Natom = %d", sb.on ? "/nslabs" : "", (long)NA * N1 * N2 * N3l, e->N);
    if (!e->lattice_built) {
-      d.NA = NA; d.N1 = N1; d.N2 = N2; d.N3 = N3l;
-      for (int a = 0; a < 3; a++) d.periodic[a] = (bc3[a] == 'P' || bc3[a] == 'p') ? 1 : 0;
-      d.reduced = (e->NH < e->N) ? 1 : 0;
-      d.Ncell = N1 * N2 * N3l;
-      d.N = e->N;
-      d.slab = sb.on; d.N3g = N3; d.z0 = sb.on ? sb.g * N3l : 0; d.H = sb.on ? sb.H : 0;
-      d.has_lo = sb.on && (d.periodic[2] || sb.g > 0);
-      d.has_hi = sb.on && (d.periodic[2] || sb.g < sb.G - 1);
-      choose_brick(d);
+      int per[3];
+      for (int a = 0; a < 3; a++) per[a] = (bc3[a] == 'P' || bc3[a] == 'p') ? 1 : 0;
       {
-         const long nown = (long)d.NTX * d.NSY * d.NSZ * d.SY * d.SZ * d.NA * d.P;
-         const long np = ((nown + 2L * d.H * NA * N1 * N2 + 31) / 32) * 32;
-         if (np > 2000000000L) return fail(-3, "too many atoms for 32-bit device indices");
-         d.Nown = (int)nown; d.Npad = (int)np;
+         int rr = fill_lattice_desc(e, NA, N1, N2, N3l, N3, per, e->NH < e->N);
+         if (rr) return rr;
       }
       if (d.reduced)
          for (int i = 0; i < e->N; i++) if (e->aHam[i] != i % NA + 1) return fail(-1, "aHam is not the basis-atom number; cannot use the lattice builder");

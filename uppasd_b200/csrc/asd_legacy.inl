@@ -41,6 +41,8 @@ struct FortranData {
    // extras (new)
    double *Landeg = nullptr, *lambda1_array = nullptr, *temprescale = nullptr;
    unsigned int *do_bq = nullptr, *nn_bq_tot = nullptr, *bqlist = nullptr, *bqlistsize = nullptr; double* j_bq = nullptr;
+   // supercell shape (new, optional)
+   unsigned int *NA = nullptr, *N1 = nullptr, *N2 = nullptr, *N3 = nullptr; char *BC1 = nullptr, *BC2 = nullptr, *BC3 = nullptr;
 };
 static FortranData fd;
 static asd_engine* eng = nullptr;
@@ -119,6 +121,13 @@ void fortrandata_setextras_(double* Landeg, double* lambda1_array, double* tempr
    f.do_bq = do_bq; f.nn_bq_tot = nn_bq_tot; f.bqlist = bqlist; f.bqlistsize = bqlistsize; f.j_bq = j_bq;
 }
 
+void fortrandata_setlattice_(unsigned int* NA, unsigned int* N1, unsigned int* N2, unsigned int* N3, char* BC1, char* BC2, char* BC3) {
+   auto& f = legacy::fd;
+   f.NA = NA; f.N1 = N1; f.N2 = N2; f.N3 = N3; f.BC1 = BC1; f.BC2 = BC2; f.BC3 = BC3;
+}
+
+asd_engine* asd_legacy_engine(void) { return legacy::eng; }
+
 void asd_set_callbacks(asd_cb_do_measurements a, asd_cb_measure_moment b, asd_cb_flush_measurements c, asd_cb_status d) {
    legacy::cb_do = a; legacy::cb_measure = b; legacy::cb_flush = c; legacy::cb_status = d;
 }
@@ -143,6 +152,10 @@ void cudamdsim_initiatematrices_(void) {
    if (!constants_ok) { std::fprintf(stderr, "uppasd_b200: constants not initiated!\n"); std::exit(EXIT_FAILURE); }
    const int N = (int)*fd.Natom, M = (int)*fd.Mensemble, NH = (int)*fd.nHam;
    if (asd_set_system(eng, N, M, NH, (const int*)fd.aHam)) die("set_system");
+   if (fd.NA && fd.N1 && fd.N2 && fd.N3 && fd.BC1 && fd.BC2 && fd.BC3) {
+      const char bc[4] = {*fd.BC1, *fd.BC2, *fd.BC3, 0};
+      if (asd_set_lattice_hint(eng, (int)*fd.NA, (int)*fd.N1, (int)*fd.N2, (int)*fd.N3, bc)) die("set_lattice_hint");
+   }
    if (asd_set_exchange(eng, (int)*fd.max_no_neigh, (const int*)fd.nlist, (const int*)fd.nlistsize, fd.ncoup)) die("set_exchange");
    if (fd.do_dm && *fd.do_dm == 1)
       if (asd_set_dm(eng, (int)*fd.max_no_dmneigh, (const int*)fd.dmlist, (const int*)fd.dmlistsize, fd.dmvect)) die("set_dm");

@@ -79,6 +79,9 @@ class Engine:
         bqlist = _i32(bqlist)
         self._chk(self.lib.asd_set_bq(self.h, bqlist.shape[0], _p(bqlist), _p(_i32(bqlistsize)), _p(_f64(j_bq))))
 
+    def set_lattice_hint(self, na, ncell, bc):
+        self._chk(self.lib.asd_set_lattice_hint(self.h, na, ncell[0], ncell[1], ncell[2], ''.join(bc).encode()))
+
     def set_anisotropy(self, taniso, eaniso, kaniso, sb):
         self._chk(self.lib.asd_set_anisotropy(self.h, _p(_i32(taniso)), _p(_f64(eaniso)), _p(_f64(kaniso)), _p(_f64(sb))))
 
@@ -178,9 +181,9 @@ class Engine:
 
     def layout_info(self):
         """dict(staged, runs, ucap, union, tile_slots): the field path of the LLG stage kernels"""
-        info = (C.c_int * 5)()
+        info = (C.c_int * 6)()
         self._chk(self.lib.asd_layout_info(self.h, info))
-        return dict(staged=info[0], runs=info[1], ucap=info[2], union=info[3], tile_slots=info[4])
+        return dict(staged=info[0], runs=info[1], ucap=info[2], union=info[3], tile_slots=info[4], extra_staged=info[5])
 
     def launch_count(self):
         return self.lib.asd_launch_count(self.h)
@@ -238,11 +241,14 @@ class Engine:
 
 
 def engine_from_system(S, consts, sdealgh=1, delta_t=1e-16, damping=0.05, temp=0.0, mompar=0, seed=20261017,
-                       device=-1):
-    """Feeds a system dict holding reference-shaped tables (nlist, ncoup, ... as the Fortran host has them) to a new Engine."""
+                       device=-1, lattice_hint=None):
+    """Feeds a system dict holding reference-shaped tables (nlist, ncoup, ... as the Fortran host has them) to a new Engine.
+    lattice_hint = (NA, ncell, bc): announce the supercell shape (asd_set_lattice_hint)."""
     e = Engine(device)
     e.set_constants(consts['gama'], consts['k_bolt'], consts['mub'], consts['mry'])
     e.set_system(S['Natom'], S['Mensemble'], S['nHam'], S['aHam'])
+    if lattice_hint is not None:
+        e.set_lattice_hint(*lattice_hint)
     ex = S['exchange']
     e.set_exchange(ex['list'], ex['listsize'], ex['coup'])
     if S.get('dm') is not None:
@@ -263,9 +269,14 @@ class FortranHost:
     """Plays the reference's Fortran program around the legacy boundary (sd_mphaseCUDA)."""
 
     def __init__(self, S, consts, sdealgh, nstep, delta_t, damping, temp=0.0, mompar=0, rstep=0, gpu_rng_seed=1,
-                 avrg_step=100, cumu_step=50, do_avrg='Y', do_cumu='N'):
+                 avrg_step=100, cumu_step=50, do_avrg='Y', do_cumu='N', lattice=None):
+        """lattice = (NA, (N1, N2, N3), 'PPP'): also announce the supercell shape (fortrandata_setlattice_)"""
         self.lib = capi.load()
         self.S = S
+        self.lattice = None
+        if lattice is not None:
+            na, nc, bc = lattice
+            self.lattice = [C.c_uint(na), C.c_uint(nc[0]), C.c_uint(nc[1]), C.c_uint(nc[2])] + [C.c_char(b.encode()) for b in bc]
         N, M = S['Natom'], S['Mensemble']
         self.N, self.M = N, M
         ci = lambda v: C.c_int(v)
@@ -346,6 +357,10 @@ class FortranHost:
                                                         'j_tens', 'kaniso', 'eaniso', 'taniso', 'sb', 'aHam')])
         L.fortrandata_setinputdata_(r('gpu_mode'), r('gpu_rng'), r('gpu_rng_seed'))
         L.fortrandata_setextras_(_p(a['Landeg']), None, None, None, None, None, None, None)
+        if self.lattice is not None:
+            L.fortrandata_setlattice_(*[C.cast(C.byref(x), C.c_void_p) for x in self.lattice])
+        else:
+            L.fortrandata_setlattice_(None, None, None, None, None, None, None)
         L.cudamdsim_initiateconstants_()
         L.cudamdsim_initiatematrices_()
         return self
@@ -354,6 +369,14 @@ class FortranHost:
         self.initiate()
         self.lib.cudamdsim_measurementphase_()
         return self
+
+    def layout_info(self):
+        """field path of the engine behind the legacy boundary (Engine.layout_info)"""
+        info = (C.c_int * 6)()
+        h = self.lib.asd_legacy_engine()
+        if not h or self.lib.asd_layout_info(h, info):
+            raise AsdError(self.lib.asd_last_error().decode())
+        return dict(staged=info[0], runs=info[1], ucap=info[2], union=info[3], tile_slots=info[4], extra_staged=info[5])
 
     # --- the new sibling entries, called the way sd_iphase / mc_mphase would ---
     def initial_phase(self, nstep, temp, delta_t, damping, sdealgh, first_step=1):
