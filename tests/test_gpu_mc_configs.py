@@ -113,3 +113,37 @@ def test_mc_on_device_built_tables_matches_host_tables():
     e1.sd_steps(10)
     e2.sd_steps(10)
     assert np.abs(e1.get_moments()[0] - e2.get_moments()[0]).max() <= 1e-13
+
+
+@pytest.mark.parametrize('mode', ['M', 'H'])
+def test_cooperative_and_persistent_sweeps_run_the_same_chain(mode, monkeypatch):
+    """FeCo B2 (z = 258, many small colour classes): the sub-warp cooperative update (warp-shuffle reduction of the
+    Heisenberg sum) and the single cooperative launch with grid barriers between colours make the same draws and the
+    same decisions as the one-thread-per-update colour launches; only the summation order of the field differs."""
+    from uppasd_b200 import host
+    inp, S = _system('feco', 3)
+    rng = np.random.default_rng(17)
+    e0 = rng.normal(size=(3, S['Natom'], 3)); e0 /= np.sqrt((e0 ** 2).sum(axis=0))
+    S['emom'] = np.asfortranarray(e0)
+    S['emomM'] = np.asfortranarray(e0 * S['mmom'][None])
+    out = {}
+    for name, env in (('thread', dict(ASD_MC_PERSISTENT='0', ASD_MC_LPA='1')), ('subwarp', dict(ASD_MC_PERSISTENT='0', ASD_MC_LPA='16')),
+                      ('persistent', dict())):
+        for k in ('ASD_MC_PERSISTENT', 'ASD_MC_LPA'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        e = host.engine_from_system(S, orc.CONST, temp=900.0, seed=33)
+        e.mc_sweeps(mode, 0, 900.0)             # builds the colour-major layout, runs nothing
+        n0 = e.launch_count()
+        e.mc_sweeps(mode, 4, 900.0)
+        e.mc_sweeps(mode, 3, 900.0, first_sweep=5)
+        nl = e.launch_count() - n0
+        out[name] = (e.get_moments()[0], nl)
+        assert np.abs(np.linalg.norm(out[name][0], axis=0) - 1.0).max() < 1e-12
+    lay, ncol, _ = e.mc_colouring()
+    assert lay == 0 and ncol >= 12
+    assert out['persistent'][1] == 2 and out['thread'][1] == 7 * ncol          # one launch per call vs one per colour
+    assert np.abs(out['thread'][0] - e0).max() > 0.1                            # the chain moved
+    for name in ('subwarp', 'persistent'):
+        assert np.abs(out[name][0] - out['thread'][0]).max() <= 1e-9, name

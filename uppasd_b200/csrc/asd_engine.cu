@@ -95,6 +95,8 @@ struct Layout {
    std::vector<int> colour_first, colour_count;
    DevBuf<int> d_ham, d_orig, d_nl, d_lsize, d_dml, d_dmsize, d_bql, d_bqsize, d_taniso;
    DevBuf<int4> d_nl4;
+   DevBuf<int> d_nlrow;             // atom-major exchange table of the MC layout (mc_colour_coop_kernel)
+   DevBuf<int2> d_classes;          // {first, count} of every colour class (mc_sweeps_persistent_kernel)
    DevBuf<int> d_ucount, d_ulist;   // staged tile path (asd_tiles.cuh)
    DevBuf<uint4> d_nl16, d_dm16, d_bq16;
    DevBuf<int2> d_meta;
@@ -609,7 +611,25 @@ static int build_layout(asd_engine* e, Layout& L, bool colour_major) {
    t.zdm = e->dm.z; t.dml = L.d_dml.p; t.dmv = L.d_dmv.p; t.dmsize = L.d_dmsize.p;
    t.zbq = e->bq.z; t.bql = L.d_bql.p; t.jbq = L.d_jbq.p; t.bqsize = L.d_bqsize.p;
    L.zs[0] = e->ex.z; L.zs[1] = e->dm.z; L.zs[2] = e->bq.z;
-   return finish_layout(e, L);
+   L.d_nlrow.release();
+   L.d_classes.release();
+   if (colour_major && L.reduced) {
+      // atom-major copy for the cooperative colour kernel (small colour classes / long lists)
+      const int z = e->ex.z;
+      std::vector<int> rowm((size_t)Npad * z);
+      for (long s = 0; s < Npad; s++) {
+         const int o = L.orig[s];
+         for (int j = 0; j < z; j++) {
+            int v = (int)s;
+            if (o >= 0 && j < e->ex.lsize[e->aHam[o] - 1]) v = L.slot_of[e->ex.list[(size_t)j + (size_t)z * o] - 1];
+            rowm[(size_t)s * z + j] = v;
+         }
+      }
+      if ((r = L.d_nlrow.upload(rowm, st))) return r;
+   }
+   r = finish_layout(e, L);
+   L.t.nlrow = L.d_nlrow.p;
+   return r;
 }
 
 // per-site LLG parameter arrays of a layout (uniform -> scalars)
@@ -1024,13 +1044,70 @@ static int mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, d
    if (r) return r;
    Layout& L = e->mc;
    const int ncol = (int)L.colour_first.size();
+   // launch-bound regime (many small colour classes): one cooperative launch for all colours of all sweeps
+   {
+      long mx = 0;
+      for (int c = 0; c < ncol; c++) mx = std::max(mx, (long)L.colour_count[c] * e->M);
+      const char* env = std::getenv("ASD_MC_PERSISTENT");
+      int sms = 148, coop = 0;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
+      bool use = L.reduced && L.t.nlrow && coop && ncol >= 12 && mx * 8 <= (long)sms * 2048 && L.t.z >= 32 && nsweeps > 0;
+      if (env) use = use && atoi(env) != 0;
+      if (use) {
+         int r;
+         if (L.d_classes.n != (size_t)ncol) {
+            std::vector<int2> cl(ncol);
+            for (int c = 0; c < ncol; c++) cl[c] = make_int2(L.colour_first[c], L.colour_count[c]);
+            if ((r = L.d_classes.upload(cl, e->stream))) return r;
+         }
+         int lpa = 8;
+         while (lpa < 32 && mx * lpa < (long)sms * 1024 && 4 * lpa <= L.t.z) lpa *= 2;
+         const char* le = std::getenv("ASD_MC_LPA");
+         if (le && (atoi(le) == 8 || atoi(le) == 16 || atoi(le) == 32)) lpa = atoi(le);
+         p.sweep = (unsigned long long)first_sweep;
+         const int2* cls = L.d_classes.p;
+         int nc = ncol, ns = (int)nsweeps;
+         SpinVec* curp = e->cur.p;
+         void* args[] = {(void*)&L.t, (void*)&p, (void*)&cls, (void*)&nc, (void*)&ns, (void*)&curp};
+         const void* fn = lpa == 8 ? (const void*)mc_sweeps_persistent_kernel<8> : lpa == 16 ? (const void*)mc_sweeps_persistent_kernel<16>
+                                                                                            : (const void*)mc_sweeps_persistent_kernel<32>;
+         int per_sm = 0;
+         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, L.smem_bytes));
+         if (per_sm > 0) {
+            const long want = (mx * lpa + 255) / 256;
+            const int grid = (int)std::max(1L, std::min((long)per_sm * sms, want));
+            CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, L.smem_bytes, e->stream));
+            e->launches++;
+            CU(cudaGetLastError());
+            return 0;
+         }
+      }
+   }
    for (long s = 0; s < nsweeps; s++)
       for (int c = 0; c < ncol; c++) {
          p.sweep = (unsigned long long)(first_sweep + s);
          p.first = L.colour_first[c]; p.count = L.colour_count[c];
          if (p.count == 0) continue;
          dim3 g((p.count + 255) / 256, e->M), b(256);
-         if (L.reduced) mc_colour_kernel<true><<<g, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p, nullptr);
+         // small classes: LPA lanes per update so that a launch still fills the GPU (ASD_MC_LPA forces a width)
+         int lpa = 1;
+         if (L.reduced && L.t.nlrow) {
+            const long attempts = (long)p.count * e->M;
+            while (lpa < 32 && attempts * lpa < 300000L && 4 * lpa <= L.t.z) lpa *= 2;
+            const char* env = std::getenv("ASD_MC_LPA");
+            if (env) lpa = atoi(env);
+         }
+         if (lpa > 1) {
+            const dim3 gc((unsigned)(((long)p.count * lpa + 255) / 256), e->M);
+            switch (lpa) {
+               case 2: mc_colour_coop_kernel<2><<<gc, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p); break;
+               case 4: mc_colour_coop_kernel<4><<<gc, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p); break;
+               case 8: mc_colour_coop_kernel<8><<<gc, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p); break;
+               case 16: mc_colour_coop_kernel<16><<<gc, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p); break;
+               default: mc_colour_coop_kernel<32><<<gc, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p); break;
+            }
+         } else if (L.reduced) mc_colour_kernel<true><<<g, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p, nullptr);
          else mc_colour_kernel<false><<<g, b, 0, e->stream>>>(L.t, p, e->cur.p, nullptr);
          e->launches++;
       }
