@@ -359,11 +359,14 @@ static int finish_layout(asd_engine* e, Layout& L) {
          t.cpl_param = 1;
       }
       // tile size of the run kernel: the whole super-brick by default
-      int big = (has_lattice(e) && !L.is_mc) ? 256 * e->lat.SY * e->lat.SZ : 256;
+      int big = (has_lattice(e) && !L.is_mc) ? e->lat.NA * e->lat.P * e->lat.SY * e->lat.SZ : 256;   // slots of a super-brick
+      if (big != 1024) big = 256;   // smaller tiles only on request (ASD_RUNS): measured slower than the staged kernel
+      // short lists without DM / BQ work (fcc, z = 18): the step is integrator-bound and the staged kernel's 32 warps/SM win
+      if (t.z < 24 && t.zdm == 0 && t.zbq == 0) big = 256;
       const char* renv = std::getenv("ASD_RUNS");
       if (renv) big = atoi(renv);
       if (big != 0 && big != 256 && big != 512 && big != 1024) return fail(-1, "ASD_RUNS must be 0, 256, 512 or 1024");
-      if (big > 256 && (!has_lattice(e) || L.is_mc || 256 * e->lat.SY * e->lat.SZ % big != 0)) big = 256;
+      if (big > 256 && (!has_lattice(e) || L.is_mc || (e->lat.NA * e->lat.P * e->lat.SY * e->lat.SZ) % big != 0)) big = 256;
       if (big >= 256 && (renv || big > 256)) {
          if ((r = build_tiles(e, L, big))) return r;
          if ((r = build_runs(e, L))) return r;

@@ -20,6 +20,9 @@ static void choose_brick(LatticeDesc& d) {
    int p2 = 32;
    while (p2 * 2 <= target) p2 *= 2;
    target = p2;
+   // reduced Hamiltonians with 4 or 8 basis atoms: 128 cells per brick, so that every 128-slot group (4 x-runs, the
+   // unit of the run kernel) is one sublattice and 2 bricks / 1 brick make a 1024-slot tile
+   if (d.reduced && (d.NA == 4 || d.NA == 8)) target = 128;
    double best = 1e300;
    int bb[3] = {32, 1, 1};
    for (int bx = 1; bx <= 256; bx *= 2)
@@ -41,16 +44,21 @@ static void choose_brick(LatticeDesc& d) {
          }
    d.BX = bb[0]; d.BY = bb[1]; d.BZ = bb[2]; d.P = bb[0] * bb[1] * bb[2];
    d.NTX = (d.N1 + d.BX - 1) / d.BX; d.NTY = (d.N2 + d.BY - 1) / d.BY; d.NTZ = (d.N3 + d.BZ - 1) / d.BZ;
-   // super-bricks (big tiles of the run kernel): only when a brick is exactly one 256-slot tile and the Hamiltonian is
-   // reduced (the run kernel's precondition).  ASD_SUPER = "sy,sz" overrides (1,1 switches them off).
+   // super-bricks (big tiles of the run kernel): 1024 slots = 4, 2 or 1 bricks, when the Hamiltonian is reduced (the run
+   // kernel's precondition) and every 128-slot group is one sublattice.  ASD_SUPER = "sy,sz" overrides (1,1 = off).
    d.SY = d.SZ = 1;
-   if (d.reduced && d.NA * d.P == 256) {
-      if (d.NTZ >= 2 && d.NTY >= 2) { d.SY = 2; d.SZ = 2; }
-      else if (d.NTY >= 4) { d.SY = 4; d.SZ = 1; }
-      else if (d.NTZ >= 4) { d.SY = 1; d.SZ = 4; }
+   if (d.reduced && (d.NA * d.P == 256 || (d.P % 128 == 0 && 1024 % (d.NA * d.P) == 0))) {
+      const int nb = 1024 / (d.NA * d.P);
+      if (nb == 4) {
+         if (d.NTZ >= 2 && d.NTY >= 2) { d.SY = 2; d.SZ = 2; }
+         else if (d.NTY >= 4) { d.SY = 4; d.SZ = 1; }
+         else if (d.NTZ >= 4) { d.SY = 1; d.SZ = 4; }
+      } else if (nb == 2) {
+         if (d.NTY >= 2) d.SY = 2; else if (d.NTZ >= 2) d.SZ = 2;
+      }
       const char* env = std::getenv("ASD_SUPER");
       int sy, sz;
-      if (env && sscanf(env, "%d,%d", &sy, &sz) == 2 && sy >= 1 && sz >= 1 && sy * sz <= 4) { d.SY = sy; d.SZ = sz; }
+      if (env && sscanf(env, "%d,%d", &sy, &sz) == 2 && sy >= 1 && sz >= 1 && sy * sz <= nb) { d.SY = sy; d.SZ = sz; }
    }
    d.NSY = (d.NTY + d.SY - 1) / d.SY; d.NSZ = (d.NTZ + d.SZ - 1) / d.SZ;
 }
