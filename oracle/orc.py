@@ -289,6 +289,15 @@ def rng_uniform(n):
     return out
 
 
+def initmag1(S, seed):
+    """Initmag 1 (magnetizationinit.f90:141-178): random directions from the reference's MT stream seeded with tseed
+    (uppasd.f90:903-910); fills S['emom'] / S['emomM'] in place."""
+    rng_init(seed)
+    n1, n2, n3 = S['ncell']
+    lib().orc_initmag1(S['Natom'], S['Mensemble'], S['NA'], n1, n2, n3, _p(S['mmom']), _p(S['emom']), _p(S['emomM']))
+    return S
+
+
 def zig_setup(seed):
     lib().orc_zig_setup(int(seed))
 

@@ -18,8 +18,21 @@ from oracle import inputs  # noqa: E402
 REF = '/root/reference/tests'
 
 
-def fixture(dirname, inpname='inpsd.dat', extra_inp=None):
+def fixture(dirname, inpname='inpsd.dat', extra_inp=None, subst=None):
     d = os.path.join(REF, dirname)
+    if subst:
+        # templated input (the reference's runtest.sh seds a placeholder): read a substituted copy placed next to the data files
+        import shutil
+        import tempfile
+        tmp = tempfile.mkdtemp()
+        for f in os.listdir(d):
+            shutil.copy(os.path.join(d, f), tmp)
+        txt = open(os.path.join(d, inpname)).read()
+        for a, b in subst.items():
+            txt = txt.replace(a, b)
+        inpname = 'inpsd.dat'
+        open(os.path.join(tmp, inpname), 'w').write(txt)
+        d = tmp
     inp = inputs.read_inpsd(os.path.join(d, inpname))
     if extra_inp:
         inp.update(extra_inp)
@@ -87,6 +100,15 @@ def main():
                      'S_averages_2700': [1.69336666, -0.0338763749, 0.61172735, 1.8007911],
                      'S_cumulants_41': [1.7980927, 3.23410613, 10.4720508, 0.666264851, 0.000377665603, 1.10522259]}
     fx['bccfe'] = f
+    # --- tests/Solvers: 100-spin chain, RANDOM start (Initmag 1, tseed 1: the reference's MT variant + rejection loop),
+    #     T=0, damping 1, dt 1e-15, midpoint and Depondt (regulartests.yaml:349-385), 1e-8 abs
+    f = fixture('Solvers', inpname='inpsd.dat.base', subst={'SOLVER': '1'})
+    f['source'] = 'tests/Solvers/inpsd.dat.base (SOLVER -> 1 | 5 as in runtest.sh)'
+    f['expected'] = {
+        'averages': {'1': {'8000': [-0.136652492, 0.0180191027, -0.260168482, 0.294425255]},
+                     '5': {'8000': [-0.13635776, 0.018097742, -0.260185475, 0.294308424]}},
+        'tol': 1e-8, 'yaml': 'tests/regulartests.yaml:349-385'}
+    fx['solvers'] = f
     for k, v in fx.items():
         with open(os.path.join(HERE, k + '.json'), 'w') as fh:
             json.dump(v, fh, indent=1, default=lambda o: list(o))

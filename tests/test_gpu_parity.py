@@ -292,3 +292,23 @@ def test_ragged_lists_isolated_atoms_and_odd_sizes():
         for _ in range(80):
             st.step()
         assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12, alg
+
+
+@pytest.mark.parametrize('solver', [1, 5])
+def test_solvers_golden_random_start(solver):
+    """tests/Solvers (regulartests.yaml:349-385): 100-spin chain from the reference's random start (Initmag 1), damping 1,
+    dt 1e-15, 8000 steps: the GPU path reproduces the reference's printed averages for the midpoint and the Depondt
+    solver at the reference's own tolerance (1e-8), and the oracle's final state to 1e-10."""
+    from uppasd_b200 import host
+    fx, inp, S = load_golden('solvers')
+    orc.initmag1(S, inp['tseed'])
+    e = host.engine_from_system(S, orc.CONST, sdealgh=solver, delta_t=inp['timestep'], damping=inp['damping'], temp=0.0)
+    e.sd_steps(8000)
+    m = e.measure()[:, 0] / S['Natom']
+    got = list(m) + [float(np.sqrt((m ** 2).sum()))]
+    for a, b in zip(got, fx['expected']['averages'][str(solver)]['8000']):
+        assert abs(a - b) <= 1e-8, (solver, got)
+    st = orc.SdState(S, solver, inp['timestep'], inp['damping'])
+    for _ in range(8000):
+        st.step()
+    assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-10

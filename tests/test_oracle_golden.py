@@ -58,6 +58,18 @@ def test_sloppy_goldens(name):
             assert abs(x - y) <= 5e-9 * max(1.0, abs(y)), (x, y)
 
 
+@pytest.mark.parametrize('solver', [1, 5])
+def test_solvers_random_start_chain(solver):
+    """tests/Solvers: pins Initmag 1 (the reference's MT variant, seed tseed = 1, and the rejection loop of
+    magnetizationinit.f90:148-160) and BOTH solvers on this path at the reference's tight tolerance."""
+    fx, inp, S = load_golden('solvers')
+    assert inp['initmag'] == 1 and S['Natom'] == 100
+    orc.initmag1(S, inp['tseed'])
+    r = orc.sd_run(S, dict(inp, sdealgh=solver), nstep=8001)
+    for a, b in zip(r['averages'][8000], fx['expected']['averages'][str(solver)]['8000']):
+        assert _similar(a, b), (solver, a, b)
+
+
 def test_reference_mt_variant_known_answers():
     # SURVEY.md facts table: emulating mtprng.f90 with 64-bit semantics, seed 5 -> these outputs
     # (the third differs from standard MT19937's 3739766767).
