@@ -109,6 +109,17 @@ def main():
                      '5': {'8000': [-0.13635776, 0.018097742, -0.260185475, 0.294308424]}},
         'tol': 1e-8, 'yaml': 'tests/regulartests.yaml:349-385'}
     fx['solvers'] = f
+    # --- tests/HeisChain: start from a restart file, THERMAL SD initial phase (20000 midpoint steps at 0.1 K, damping 4:
+    #     the reference's MT + Ziggurat stream through rannum), then T=0, damping 0 (regulartests.yaml:2-26), 1e-8 abs
+    f = fixture('HeisChain')
+    f['restart'] = inputs._rows(os.path.join(REF, 'HeisChain', 'startmom'))
+    f['ip_phase'] = {'nstep': 20000, 'temp': 0.1, 'timestep': 1e-16, 'damping': 4.0,
+                     'source': 'tests/HeisChain/inpsd.dat:18-20 (ip_mode S, ip_nphase 1)'}
+    f['expected'] = {
+        'averages': {'1000': [0.0125212146, 0.0243286358, 0.998725532, 0.999100271]},
+        'totenergy': {'1400': -4.99936339},
+        'tol': 1e-8, 'yaml': 'tests/regulartests.yaml:2-26'}
+    fx['heischain'] = f
     for k, v in fx.items():
         with open(os.path.join(HERE, k + '.json'), 'w') as fh:
             json.dump(v, fh, indent=1, default=lambda o: list(o))

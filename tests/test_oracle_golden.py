@@ -70,6 +70,34 @@ def test_solvers_random_start_chain(solver):
         assert _similar(a, b), (solver, a, b)
 
 
+def test_heischain_thermal_initial_phase():
+    """tests/HeisChain: restart-file start, 20000 THERMAL midpoint steps (0.1 K, damping 4) driven by the reference's own
+    noise source -- the MT variant feeding the Ziggurat r4_nor through rannum, 3*N normals per step in memory order,
+    sigma = sqrt(2 D) -- then 1400 undamped T = 0 steps.  The reference's printed averages @1000 and total energy @1400
+    come out digit for digit: this pins the oracle's RNG restatement, the noise amplitude and the thermal integrator, i.e.
+    the generator the GPU path's observables are compared with."""
+    fx, inp, S = load_golden('heischain')
+    N = S['Natom']
+    emom = np.zeros((3, N, 1), order='F')
+    mmom = np.zeros((N, 1), order='F')
+    for r in fx['restart']:
+        i = int(r[2]) - 1
+        mmom[i, 0] = float(r[3])
+        emom[:, i, 0] = [float(x) for x in r[4:7]]
+    S['emom'], S['mmom'] = emom, mmom
+    S['emomM'] = np.asfortranarray(emom * mmom[None])
+    S['mmom0'], S['mmomi'] = mmom.copy(order='F'), np.asfortranarray(1.0 / mmom)
+    ph = fx['ip_phase']
+    _, st = orc.sd_run_thermal(S, 1, ph['timestep'], ph['damping'], ph['temp'], ph['nstep'], seed=inp['tseed'], sample_every=1000)
+    S2 = dict(S, emom=st.emom.copy(order='F'), emomM=st.emomM.copy(order='F'), mmom=st.mmom.copy(order='F'))
+    r = orc.sd_run(S2, dict(inp, sdealgh=1, damping=0.0), nstep=1401)
+    exp = fx['expected']
+    for a, b in zip(r['averages'][1000], exp['averages']['1000']):
+        assert _similar(a, b), (a, b)
+    _, e = orc.effective_field(S2, emomM=r['state'].emomM)
+    assert _similar(e / N, exp['totenergy']['1400']), e / N
+
+
 def test_reference_mt_variant_known_answers():
     # SURVEY.md facts table: emulating mtprng.f90 with 64-bit semantics, seed 5 -> these outputs
     # (the third differs from standard MT19937's 3739766767).
