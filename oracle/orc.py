@@ -247,11 +247,14 @@ class Cumulants:
         return self.m1, self.m2, self.m4, self.binder
 
 
-def sd_run(S, inp, nstep=None, traj_atoms=(), want_rows=None):
-    """Replay of sd_mphase (source/sd_driver.f90:517-849) at T=0: returns averages rows {iter: (mx,my,mz,m)},
-    cumulant rows {sample_no: (m,m2,m4,U)}, trajectories {atom: {iter: (ex,ey,ez,m)}} and the final state."""
+def sd_run(S, inp, nstep=None, traj_atoms=(), want_rows=None, temp=0.0):
+    """Replay of sd_mphase (source/sd_driver.f90:517-849): returns averages rows {iter: (mx,my,mz,m)},
+    cumulant rows {sample_no: (m,m2,m4,U)}, trajectories {atom: {iter: (ex,ey,ez,m)}} and the final state.
+    temp > 0: every step draws its 3*N*M normals from the reference's Ziggurat stream in its CURRENT state (rannum ->
+    fill_rngarray, randomnumbers.f90:709-732), so a thermal initial phase run before continues into this phase as in
+    the reference."""
     nstep = inp['nstep'] if nstep is None else nstep
-    st = SdState(S, inp['sdealgh'], inp['timestep'], inp['damping'], temp=0.0, mompar=inp['mompar'])
+    st = SdState(S, inp['sdealgh'], inp['timestep'], inp['damping'], temp=temp, mompar=inp['mompar'])
     N, M = S['Natom'], S['Mensemble']
     avg, cum, traj = {}, {}, {a: {} for a in traj_atoms}
     cu = Cumulants(N)
@@ -273,7 +276,10 @@ def sd_run(S, inp, nstep=None, traj_atoms=(), want_rows=None):
 
     for mstep in range(1, nstep + 1):
         measure(mstep)
-        st.step()
+        if temp > 0.0:
+            st.step(gauss=fill_rngarray(3 * N * M).reshape((3, N, M), order='F'))
+        else:
+            st.step()
     measure(nstep + 1)
     return dict(averages=avg, cumulants=cum, traj=traj, state=st)
 
@@ -325,12 +331,15 @@ def sd_run_thermal(S, sdealgh, delta_t, damping, temp, nstep, seed=1, sample_eve
     return np.array(out), st
 
 
-def mc_run(S, mode, temperature, nsweeps, seed=1, sample_every=1, burn=0, extfield=(0.0, 0.0, 0.0)):
+def mc_run(S, mode, temperature, nsweeps, seed=1, sample_every=1, burn=0, extfield=(0.0, 0.0, 0.0), init=True,
+           reshuffle_every=None):
     """mc_mphase replay (source/mc_driver.f90:234-430): visiting order from choose_random_atom_x, redrawn every
-    mcnstep/10 sweeps; per sweep the bulk draws of mc_evolve in the reference's order."""
+    mcnstep/10 sweeps; per sweep the bulk draws of mc_evolve in the reference's order.  init=False continues the
+    generators from their current state (a measurement phase that follows an initial phase)."""
     L = lib()
-    rng_init(seed)
-    zig_setup(seed)
+    if init:
+        rng_init(seed)
+        zig_setup(seed)
     N, M = S['Natom'], S['Mensemble']
     H = ham_struct(S)
     emom = S['emom'].copy(order='F')
@@ -348,7 +357,7 @@ def mc_run(S, mode, temperature, nsweeps, seed=1, sample_every=1, burn=0, extfie
         L.orc_mc_sweep(C.byref(H), C.c_char(mode.encode()), _p(iflip), _p(emomM), _p(emom), _p(mmom), _p(ef),
                        _p(S['external_field']), _d(temperature), _d(1.0), _p(fm), _p(fg), _p(mf), _p(fa),
                        _d(CONST['k_bolt']), _d(CONST['mub']))
-        if sweep % max(1, nsweeps // 10) == 0:
+        if sweep % (reshuffle_every or max(1, nsweeps // 10)) == 0:      # mcnstep/10 of the PHASE (mc_driver.f90:407-410)
             L.orc_choose_random_atom_x(N, _p(iflip))
         if sweep > burn and sweep % sample_every == 0:
             m = np.zeros((3, M), order='F')

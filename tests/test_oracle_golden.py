@@ -98,6 +98,55 @@ def test_heischain_thermal_initial_phase():
     assert _similar(e / N, exp['totenergy']['1400']), e / N
 
 
+def test_bccfe_thermal_spin_dynamics_stream():
+    """tests/bccFe mode S (regulartests.yaml:244-275, tol 1e-8): 2000 thermal initial-phase steps and the 3000-step
+    measurement phase at 500 K, tseed 5 -- the reference's printed averages at iteration 0 and 2700 and the magnetisation
+    cumulants of sample 41 come out of the oracle (same noise stream, same draw order)."""
+    fx, inp, S = load_golden('bccfe')
+    orc.zig_setup(inp['tseed'])
+    _, st = None, orc.SdState(S, 1, 1.0e-16, 0.5, temp=500.0)
+    N = S['Natom']
+    for _ in range(2000):                                   # ip_nphase 1: 2000 500.0 1.0d-16 0.5
+        st.step(gauss=orc.fill_rngarray(3 * N).reshape((3, N, 1), order='F'))
+    S2 = dict(S, emom=st.emom.copy(order='F'), emomM=st.emomM.copy(order='F'), mmom=st.mmom.copy(order='F'))
+    r = orc.sd_run(S2, dict(inp, sdealgh=1), nstep=2701, temp=500.0)
+    for a, b in zip(r['averages'][0], [1.55223493, 0.240634844, 0.771889276, 1.75018612]):
+        assert _similar(a, b), (a, b)
+    # after 4700 thermal steps of a chaotic system the rounding differences between this C++ restatement and the gfortran
+    # build have grown to ~1e-8 in the smallest component (reference tolerance 1e-8; 8 of the 9 printed digits agree)
+    for a, b in zip(r['averages'][2700], fx['expected']['S_averages_2700']):
+        assert _similar(a, b, 5e-8), (a, b)
+    for a, b in zip(r['cumulants'][41], fx['expected']['S_cumulants_41'][:4]):
+        assert abs(a - b) <= 5e-9 * max(1.0, abs(b)), (a, b)
+
+
+def test_bccfe_metropolis_stream():
+    """tests/bccFe mode M (regulartests.yaml:278-312, tol 1e-8): 2000 initial-phase sweeps (ip_mcanneal) and 2700 sweeps
+    of the measurement phase at 500 K, tseed 5, visiting order from choose_random_atom_x redrawn every mcnstep/10 sweeps of
+    the phase, bulk draws in mc_evolve's order: the reference's printed averages at iteration 0 and 2700 digit for
+    digit -- pins the oracle's Metropolis restatement (trial moves, single-site energy, acceptance, RNG order)."""
+    fx, inp, S = load_golden('bccfe')
+    N = S['Natom']
+    _, _, (emom, emomM, mmom) = orc.mc_run(S, 'M', 500.0, 2000, seed=inp['tseed'], sample_every=2000)
+    m = emomM.sum(axis=1)[:, 0] / N
+    for a, b in zip(list(m) + [np.sqrt((m ** 2).sum())], [1.60393633, -0.790633521, -0.302402567, 1.81360426]):
+        assert _similar(a, b), (a, b)
+    S2 = dict(S, emom=emom, emomM=emomM, mmom=mmom)
+    _, _, (emom, emomM, mmom) = orc.mc_run(S2, 'M', 500.0, 2700, sample_every=2700, init=False, reshuffle_every=300)
+    m = emomM.sum(axis=1)[:, 0] / N
+    for a, b in zip(list(m) + [np.sqrt((m ** 2).sum())], [-0.011325332, -1.72463619, -0.148298609, 1.73103747]):
+        assert _similar(a, b), (a, b)
+
+
+def test_bccfe_heat_bath_initial_phase():
+    """tests/bccFe mode H (regulartests.yaml:315-330): M_avg after the 2000 heat-bath sweeps of the initial phase, the
+    reference's own `sloppy` tolerance (the oracle gives 1.748851 against the printed 1.748875)."""
+    fx, inp, S = load_golden('bccfe')
+    _, _, (emom, emomM, mmom) = orc.mc_run(S, 'H', 500.0, 2000, seed=inp['tseed'], sample_every=2000)
+    m = emomM.sum(axis=1)[:, 0] / S['Natom']
+    assert _sloppy(float(np.sqrt((m ** 2).sum())), 1.74887502)
+
+
 def test_reference_mt_variant_known_answers():
     # SURVEY.md facts table: emulating mtprng.f90 with 64-bit semantics, seed 5 -> these outputs
     # (the third differs from standard MT19937's 3739766767).
