@@ -128,6 +128,10 @@ int asd_set_system(asd_engine* e, int Natom, int Mensemble, int nHam, const int*
 int asd_set_exchange(asd_engine* e, int max_no_neigh, const int* nlist, const int* nlistsize,
                      const double* ncoup);
 /* DM table: dmlist(zdm,N), dmlistsize(NH), dm_vect(3,zdm,NH). */
+/* Tensorial exchange instead of the scalar table (do_jtensor 1): j_tens(3,3,max_no_neigh,nHam) as mounted by
+ * setup_neighbour_hamiltonian with hdim 9 (hamiltonianinit.f90:412-432); the field is tensor_field's
+ * f += J(:,1) m_x + J(:,2) m_y + J(:,3) m_z (hamiltonianactions.f90:499-542), indexed by the Hamiltonian row aHam(i). */
+int asd_set_jtensor(asd_engine* e, int max_no_neigh, const int* nlist, const int* nlistsize, const double* j_tens);
 int asd_set_dm(asd_engine* e, int max_no_dmneigh, const int* dmlist, const int* dmlistsize,
                const double* dm_vect);
 /* biquadratic table: bqlist(zbq,N), bqlistsize(NH), j_bq(zbq,NH). */

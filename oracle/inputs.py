@@ -36,7 +36,7 @@ def _rows(path):
 DEFAULTS = dict(
     simid='_UppASD_', ncell=(1, 1, 1), bc=('0', '0', '0'), cell=np.eye(3), sym=0, posfiletype='C', maptype=1,
     mensemble=1, tseed=1, sdealgh=1, initmag=3, mode='S', temp=0.0, nstep=1, damping=0.05, timestep=1.0e-16,
-    hfield=(0.0, 0.0, 0.0), do_reduced='N', do_sortcoup='N', mompar=0, landeg_glob=2.0, do_dm=0, do_bq=0,
+    hfield=(0.0, 0.0, 0.0), do_reduced='N', do_sortcoup='N', mompar=0, landeg_glob=2.0, do_dm=0, do_bq=0, do_jtensor=0,
     do_anisotropy=0, mcnstep=0, avrg_step=100, cumu_step=50, cumu_buff=10, do_avrg='N', do_cumu='N',
     plotenergy=0, map_multiple=False, gpu_mode=0, ip_mode='N',
 )
@@ -104,6 +104,8 @@ def read_inpsd(path):
             d['timestep'] = _f(v[0])
         elif key == 'hfield':
             d['hfield'] = tuple(_f(x) for x in v[:3])
+        elif key == 'do_jtensor':
+            d['do_jtensor'] = int(v[0])
         elif key == 'do_reduced':
             d['do_reduced'] = v[0].upper()
         elif key == 'do_sortcoup':
@@ -208,6 +210,19 @@ def read_pair_file(path, nt, atype_inp, bas, cell, maptype, posfiletype, ncomp, 
     return nn, redcoord, xc, (nntype if with_nntype else None)
 
 
+def read_tensor_file(path, nt, atype_inp, bas, cell, maptype, posfiletype):
+    """jfile in tensor format (do_jtensor 1; inputhandler_ext.f90:658-740, read_exchange_tensor_base): nine numbers per
+    line read into j_tmp(3,3) in Fortran order and then TRANSPOSED (:686-687), i.e. the file holds the tensor row by
+    row; neighbour type is not distinguished (jtype = 1, :704).  Returns nn, redcoord, xc(9, NT, shells) with xc the
+    column-major flattening of J(a,b), no nntype."""
+    nn, red, xc, _ = read_pair_file(path, nt, atype_inp, bas, cell, maptype, posfiletype, 9, False)
+    out = np.zeros_like(xc)
+    for a in range(3):
+        for b in range(3):
+            out[a + 3 * b] = xc[3 * a + b]          # J(a,b) = file[3a + b], stored at Fortran offset a + 3b
+    return nn, red, out, None
+
+
 def read_anisotropy(path, na):
     atyp = np.zeros(na, dtype=np.int32)
     an = np.zeros((na, 6), order='F')
@@ -237,4 +252,7 @@ def load_fixture(fx):
         return lambda S: read_pair_file(fx[key], nt, atype_inp, S['bas'], inp['cell'], inp['maptype'],
                                         inp['posfiletype'], ncomp, with_nntype)
     aniso = read_anisotropy(fx['kfile'], na) if fx.get('kfile') else None
-    return inp, bas, atype_inp, ammom, aemom, landeg, mk('jfile', 1, True), mk('dmfile', 3, False), mk('bqfile', 1, False), aniso
+    ex = mk('jfile', 1, True)
+    if inp.get('do_jtensor', 0) == 1:
+        ex = lambda S: read_tensor_file(fx['jfile'], nt, atype_inp, S['bas'], inp['cell'], inp['maptype'], inp['posfiletype'])
+    return inp, bas, atype_inp, ammom, aemom, landeg, ex, mk('dmfile', 3, False), mk('bqfile', 1, False), aniso

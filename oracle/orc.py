@@ -54,7 +54,7 @@ class OrcHam(C.Structure):
                 ('do_bq', C.c_int), ('nn_bq_tot', C.c_int), ('bqlist', C.c_void_p), ('bqlistsize', C.c_void_p),
                 ('j_bq', C.c_void_p),
                 ('do_anisotropy', C.c_int), ('taniso', C.c_void_p), ('eaniso', C.c_void_p),
-                ('kaniso', C.c_void_p), ('sb', C.c_void_p)]
+                ('kaniso', C.c_void_p), ('sb', C.c_void_p), ('do_jtensor', C.c_int)]
 
 
 def neighbour_table(S, nn, redcoord, xc, nntype, sym, hdim, lexp, do_sortcoup=False, map_multiple=False):
@@ -118,7 +118,12 @@ def build_system(inp, bas, atype_inp, ammom_inp, aemom_inp, landeg_ch, exchange,
     S['aHam'] = (S['anumb'].copy() if reduced else np.arange(1, N + 1, dtype=np.int32))
     sortc = inp['do_sortcoup'] == 'Y'
     ex = exchange(S) if callable(exchange) else exchange
-    S['exchange'] = neighbour_table(S, ex[0], ex[1], ex[2], ex[3], inp['sym'], 1, 1, sortc, inp['map_multiple'])
+    S['do_jtensor'] = int(inp.get('do_jtensor', 0))
+    if S['do_jtensor'] == 1:
+        # tensorial exchange: same neighbour map, nine couplings per pair, lexp = 1 (hamiltonianinit.f90:412-432)
+        S['exchange'] = neighbour_table(S, ex[0], ex[1], ex[2], None, inp['sym'], 9, 1, sortc, inp['map_multiple'])
+    else:
+        S['exchange'] = neighbour_table(S, ex[0], ex[1], ex[2], ex[3], inp['sym'], 1, 1, sortc, inp['map_multiple'])
     S['dm'] = None
     if dm is not None:
         t = dm(S) if callable(dm) else dm
@@ -159,6 +164,7 @@ def ham_struct(S):
     ex = S['exchange']
     H.max_no_neigh = ex['z']
     H.nlist, H.nlistsize, H.ncoup, H.aHam = _p(ex['list']), _p(ex['listsize']), _p(ex['coup']), _p(S['aHam'])
+    H.do_jtensor = int(S.get('do_jtensor', 0))          # ncoup then holds j_tens(3,3,z,nHam)
     if S.get('dm') is not None:
         t = S['dm']
         H.do_dm, H.max_no_dmneigh = 1, t['z']
@@ -337,6 +343,8 @@ def mc_run(S, mode, temperature, nsweeps, seed=1, sample_every=1, burn=0, extfie
     mcnstep/10 sweeps; per sweep the bulk draws of mc_evolve in the reference's order.  init=False continues the
     generators from their current state (a measurement phase that follows an initial phase)."""
     L = lib()
+    if S.get('do_jtensor', 0) == 1:
+        raise NotImplementedError('the Monte Carlo restatement covers scalar exchange only')
     if init:
         rng_init(seed)
         zig_setup(seed)

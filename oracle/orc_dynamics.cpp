@@ -50,6 +50,8 @@ struct OrcHam {
    const double* eaniso;   // (3, Natom)
    const double* kaniso;   // (2, Natom)
    const double* sb;       // (Natom)
+   // tensorial exchange: ncoup holds j_tens(3,3,max_no_neigh,nHam)
+   int do_jtensor;
 };
 
 // ---- field terms -----------------------------------------------------------------------------
@@ -63,6 +65,21 @@ static inline void heisenberg_field(const OrcHam& H, long i, long k, const doubl
       f[0] = f[0] + c * eM[3 * (nb - 1)];
       f[1] = f[1] + c * eM[3 * (nb - 1) + 1];
       f[2] = f[2] + c * eM[3 * (nb - 1) + 2];
+   }
+}
+
+// tensor_field (hamiltonianactions.f90:499-542): field += J(:,1) m_x + J(:,2) m_y + J(:,3) m_z.  The Fortran indexes
+// j_tens(:,:,j,i) with the ATOM number; this restatement uses the Hamiltonian row aHam(i), identical for do_reduced N
+// (the only mode the reference's own tensor tests use) and in-bounds for do_reduced Y.
+static inline void tensor_field(const OrcHam& H, long i, long k, const double* emomM, double* f) {
+   const int ih = H.aHam[i - 1];
+   const int z = H.max_no_neigh;
+   const double* eM = emomM + 3 * (size_t)H.Natom * (k - 1);
+   for (int j = 1; j <= H.nlistsize[ih - 1]; j++) {
+      const double* J = H.ncoup + 9 * ((j - 1) + (size_t)z * (ih - 1));   // J(a,b) at a + 3 b
+      const long nb = H.nlist[(j - 1) + (size_t)z * (i - 1)];
+      const double mx = eM[3 * (nb - 1)], my = eM[3 * (nb - 1) + 1], mz = eM[3 * (nb - 1) + 2];
+      for (int a = 0; a < 3; a++) f[a] = f[a] + J[a] * mx + J[a + 3] * my + J[a + 6] * mz;
    }
 }
 
@@ -119,7 +136,8 @@ static inline void cubic_field(const OrcHam& H, long i, const double* m, double*
 static inline void site_field(const OrcHam& H, long i, long k, const double* emomM, double* bs, double* bq) {
    bs[0] = bs[1] = bs[2] = 0.0;
    bq[0] = bq[1] = bq[2] = 0.0;
-   heisenberg_field(H, i, k, emomM, bs);
+   if (H.do_jtensor != 1) heisenberg_field(H, i, k, emomM, bs);
+   else tensor_field(H, i, k, emomM, bs);
    if (H.do_dm == 1) dm_field(H, i, k, emomM, bs);
    if (H.do_bq == 1) bq_field(H, i, k, emomM, bq);
    if (H.do_anisotropy == 1) {

@@ -100,6 +100,15 @@ def main():
                      'S_averages_2700': [1.69336666, -0.0338763749, 0.61172735, 1.8007911],
                      'S_cumulants_41': [1.7980927, 3.23410613, 10.4720508, 0.666264851, 0.000377665603, 1.10522259]}
     fx['bccfe'] = f
+    # --- tests/kagome_cuda: TENSORIAL exchange (do_jtensor 1, jfile.tensor), random start (Initmag 1), do_reduced N, on the
+    #     reference CUDA path => Depondt (cudatests.yaml:1-23), 1e-8 abs
+    f = fixture('kagome_cuda', extra_inp={'sdealgh': 5})
+    f['expected'] = {
+        'averages': {'1300': [0.000376432611, 0.00431880575, -0.00287422668, 0.00520143861]},
+        'cumulants': {'171': [0.00576048117, 3.39286723e-05, 1.28745915e-09, 0.627197795]},
+        'tol': 1e-8, 'yaml': 'tests/cudatests.yaml:1-23',
+        'note': 'gpu_mode 1: the reference CUDA path always integrates with Depondt (cudaMdSimulation.cu:319)'}
+    fx['kagome_cuda'] = f
     # --- tests/Solvers: 100-spin chain, RANDOM start (Initmag 1, tseed 1: the reference's MT variant + rejection loop),
     #     T=0, damping 1, dt 1e-15, midpoint and Depondt (regulartests.yaml:349-385), 1e-8 abs
     f = fixture('Solvers', inpname='inpsd.dat.base', subst={'SOLVER': '1'})

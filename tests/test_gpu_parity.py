@@ -312,3 +312,33 @@ def test_solvers_golden_random_start(solver):
     for _ in range(8000):
         st.step()
     assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-10
+
+
+def test_tensor_exchange_field_trajectory_and_golden():
+    """Tensorial exchange (do_jtensor 1; hamiltonianactions.f90:499-542) on tests/kagome_cuda: field and both solvers'
+    trajectories against the oracle to 1e-12, the reference's printed averages @1300 (cudatests.yaml:1-23, 1e-8), and the
+    same run through the legacy boundary (fd.j_tensor)."""
+    from uppasd_b200 import host
+    fx, inp, S = load_golden('kagome_cuda')
+    orc.initmag1(S, inp['tseed'])
+    e = _engine(S, inp)
+    beff, en = e.effective_field()
+    rb, ren = orc.effective_field(S)
+    assert np.abs(beff - rb).max() <= 1e-12 * np.abs(rb).max()
+    assert abs(en[0] - ren) <= 1e-12 * abs(ren)
+    for alg in (1, 5):
+        e = _engine(S, inp, sdealgh=alg)
+        st = orc.SdState(S, alg, inp['timestep'], inp['damping'])
+        e.sd_steps(100)
+        for _ in range(100):
+            st.step()
+        assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12, alg
+    e.sd_steps(1200, first_step=101)
+    m = e.measure()[:, 0] / S['Natom']
+    got = list(m) + [float(np.sqrt((m ** 2).sum()))]
+    for a, b in zip(got, fx['expected']['averages']['1300']):
+        assert abs(a - b) <= 1e-8, got
+    fh = host.FortranHost(S, orc.CONST, sdealgh=5, nstep=1301, delta_t=inp['timestep'], damping=inp['damping'],
+                          avrg_step=inp['avrg_step']).run()
+    for a, b in zip(fh.averages[1300], fx['expected']['averages']['1300']):
+        assert abs(a - b) <= 1e-8

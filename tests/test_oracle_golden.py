@@ -160,3 +160,19 @@ def test_ziggurat_moments():
     g = orc.fill_rngarray(400000)
     assert abs(g.mean()) < 5e-3 and abs(g.var() - 1.0) < 1e-2
     assert abs((g ** 4).mean() - 3.0) < 0.1
+
+
+def test_kagome_tensor_exchange_depondt():
+    """tests/kagome_cuda (cudatests.yaml:1-23, tol 1e-8): 13068-atom kagome lattice with TENSORIAL exchange (do_jtensor 1,
+    jfile.tensor read row by row and transposed), random start (Initmag 1), do_reduced N, integrated by the reference's CUDA
+    path, i.e. Depondt.  The printed averages @1300 and the cumulant row of sample 171 come out of the oracle digit for
+    digit: pins read_exchange_tensor, the hdim-9 mount and tensor_field."""
+    fx, inp, S = load_golden('kagome_cuda')
+    assert S['Natom'] == 13068 and S['exchange']['coup'].shape[0] == 9 and inp['sdealgh'] == 5
+    orc.initmag1(S, inp['tseed'])
+    r = orc.sd_run(S, inp, nstep=1711)
+    exp = fx['expected']
+    for a, b in zip(r['averages'][1300], exp['averages']['1300']):
+        assert _similar(a, b), (a, b)
+    for a, b in zip(r['cumulants'][171], exp['cumulants']['171']):
+        assert _similar(a, b), (a, b)

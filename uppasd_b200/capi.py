@@ -39,6 +39,7 @@ SYMBOLS = {
     'asd_set_constants': (C.c_int, [vp, C.c_double, C.c_double, C.c_double, C.c_double]),
     'asd_set_system': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
     'asd_set_exchange': (C.c_int, [vp, C.c_int, vp, vp, vp]),
+    'asd_set_jtensor': (C.c_int, [vp, C.c_int, vp, vp, vp]),
     'asd_set_dm': (C.c_int, [vp, C.c_int, vp, vp, vp]),
     'asd_set_bq': (C.c_int, [vp, C.c_int, vp, vp, vp]),
     'asd_set_lattice_hint': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]),

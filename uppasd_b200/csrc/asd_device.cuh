@@ -40,7 +40,8 @@ struct Tables {
    const int* __restrict__ ham;   // [Npad] 0-based ham row of the slot, -1 for padding slots
    const int* __restrict__ orig;  // [Npad] 0-based original atom index, -1 for padding slots
    const int2* __restrict__ meta; // [Npad] {ham, orig} zipped: one 8-byte load in the stage kernels
-   // Heisenberg
+   // Heisenberg (jtens = 1: tensorial exchange, nine couplings per pair, J(a,b) at component a + 3 b)
+   int jtens;
    int z;
    const int* __restrict__ nl;      // [z][Npad] device index of neighbour
    const double* __restrict__ cp;   // reduced: [NH][z]; else [z][Npad]
@@ -414,7 +415,27 @@ __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __res
    // ---- Heisenberg (hamiltonianactions.f90:461-464) ----
    if (!EXCH) {}
    else if (t.nl4) exchange_chunked<REDUCED, CH>(t, S, i, ih, smc, fx, fy, fz);
-   else {
+   else if (t.jtens) {
+      // tensor_field (hamiltonianactions.f90:499-542): f += J(:,1) m_x + J(:,2) m_y + J(:,3) m_z
+      const int* __restrict__ nl = t.nl + i;
+      const int n = REDUCED ? __ldg(t.lsize + ih) : t.z;
+      for (int j = 0; j < n; j++) {
+         const SpinVec v = S[__ldg(nl + (size_t)j * Npad)];
+         const double mx = v.x * v.m, my = v.y * v.m, mz = v.z * v.m;
+         double J[9];
+         if (REDUCED) {
+            const double* __restrict__ c = (smc ? smc : t.cp) + ((size_t)ih * t.z + j) * 9;
+#pragma unroll
+            for (int a = 0; a < 9; a++) J[a] = c[a];
+         } else {
+#pragma unroll
+            for (int a = 0; a < 9; a++) J[a] = __ldg(t.cp + ((size_t)a * t.z + j) * Npad + i);
+         }
+         fx = fx + J[0] * mx + J[3] * my + J[6] * mz;
+         fy = fy + J[1] * mx + J[4] * my + J[7] * mz;
+         fz = fz + J[2] * mx + J[5] * my + J[8] * mz;
+      }
+   } else {
       const int* __restrict__ nl = t.nl + i;
       if (REDUCED) {
          const int n = __ldg(t.lsize + ih);
@@ -999,6 +1020,16 @@ energy_terms_kernel(const __grid_constant__ Tables t, const SpinVec* __restrict_
       const int n = REDUCED ? __ldg(t.lsize + ih) : t.z;
       for (int j = 0; j < n; j++) {
          const SpinVec v = S[__ldg(t.nl + (size_t)j * Npad + i)];
+         if (t.jtens) {
+            const double mx = v.x * v.m, my = v.y * v.m, mz = v.z * v.m;
+            double J[9];
+            for (int a = 0; a < 9; a++)
+               J[a] = REDUCED ? __ldg(t.cp + ((size_t)ih * t.z + j) * 9 + a) : __ldg(t.cp + ((size_t)a * t.z + j) * Npad + i);
+            f[0] = f[0] + J[0] * mx + J[3] * my + J[6] * mz;
+            f[1] = f[1] + J[1] * mx + J[4] * my + J[7] * mz;
+            f[2] = f[2] + J[2] * mx + J[5] * my + J[8] * mz;
+            continue;
+         }
          const double cj = REDUCED ? __ldg(t.cp + (size_t)ih * t.z + j) : __ldg(t.cp + (size_t)j * Npad + i);
          f[0] = fma(cj, v.x * v.m, f[0]); f[1] = fma(cj, v.y * v.m, f[1]); f[2] = fma(cj, v.z * v.m, f[2]);
       }

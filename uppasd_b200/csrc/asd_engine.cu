@@ -148,6 +148,7 @@ struct asd_engine {
    int N = 0, M = 0, NH = 0;
    std::vector<int> aHam;  // 1-based ham row per atom
    HostTable ex, dm, bq;
+   bool jtensor = false;   // ex holds j_tens(3,3,z,NH): tensorial exchange (do_jtensor 1)
    bool have_aniso = false;
    std::vector<int> taniso;
    std::vector<double> eaniso, kaniso, sb;
@@ -214,7 +215,7 @@ static int build_tiles(asd_engine* e, Layout& L, int ts) {
    t.dm16 = nullptr; t.bq16 = nullptr;
    t.tile_slots = ts;
    const char* env = std::getenv("ASD_STAGED");
-   if ((env && atoi(env) == 0) || L.is_mc || t.z <= 0) return 0;
+   if ((env && atoi(env) == 0) || L.is_mc || t.z <= 0 || t.jtens) return 0;
    const long Npad = L.Npad;
    if (t.Nown <= 0) t.Nown = L.Npad;
    const int ntile = (t.Nown + ts - 1) / ts;
@@ -342,14 +343,15 @@ static int finish_layout(asd_engine* e, Layout& L) {
    // ---- shared-memory staging plan for reduced couplings ----
    L.smem_bytes = 0; t.sm_cp = t.sm_dm = t.sm_bq = 0;
    if (L.reduced) {
-      size_t n0 = (size_t)NH * t.z, n1 = (size_t)NH * t.zdm * 3, n2 = (size_t)NH * t.zbq;
+      size_t n0 = (size_t)NH * t.z * (t.jtens ? 9 : 1), n1 = (size_t)NH * t.zdm * 3, n2 = (size_t)NH * t.zbq;
       if ((n0 + n1 + n2) * 8 <= 40 * 1024) { t.sm_cp = (int)n0; t.sm_dm = (int)n1; t.sm_bq = (int)n2; L.smem_bytes = (n0 + n1 + n2) * 8; }
    }
    // ---- field path of the stage kernels: run kernel on big tiles > staged tiles > direct gathers
    //      (experiment knobs: ASD_VARIANT, ASD_PF, ASD_STAGED, ASD_RUNS = 0 | 256 | 512 | 1024) ----
    {
       const char* var = std::getenv("ASD_VARIANT");
-      const int variant = var ? atoi(var) : 3;
+      // tensorial exchange: direct gathers in site_field, none of the scalar-coupling fast paths
+      const int variant = t.jtens ? 0 : (var ? atoi(var) : 3);
       t.nl4 = nullptr; t.cp4 = nullptr; t.zq = (t.z + 3) / 4; t.pf_tiles = 0; t.cpl_param = 0;
       t.runs = 0; t.urow = 0; t.utab = nullptr;
       if (variant >= 3 && L.reduced && t.z > 0 && (size_t)NH * t.z <= 256) {
@@ -611,12 +613,13 @@ static int build_layout(asd_engine* e, Layout& L, bool colour_major) {
    if ((r = do_table(e->dm, L.d_dml, L.d_dmv, L.d_dmsize, "DM"))) return r;
    if ((r = do_table(e->bq, L.d_bql, L.d_jbq, L.d_bqsize, "BQ"))) return r;
    t.z = e->ex.z; t.nl = L.d_nl.p; t.cp = L.d_cp.p; t.lsize = L.d_lsize.p;
+   t.jtens = e->jtensor ? 1 : 0;
    t.zdm = e->dm.z; t.dml = L.d_dml.p; t.dmv = L.d_dmv.p; t.dmsize = L.d_dmsize.p;
    t.zbq = e->bq.z; t.bql = L.d_bql.p; t.jbq = L.d_jbq.p; t.bqsize = L.d_bqsize.p;
    L.zs[0] = e->ex.z; L.zs[1] = e->dm.z; L.zs[2] = e->bq.z;
    L.d_nlrow.release();
    L.d_classes.release();
-   if (colour_major && L.reduced) {
+   if (colour_major && L.reduced && !e->jtensor) {
       // atom-major copy for the cooperative colour kernel (small colour classes / long lists)
       const int z = e->ex.z;
       std::vector<int> rowm((size_t)Npad * z);
@@ -1208,7 +1211,14 @@ static int set_table(asd_engine* e, HostTable& T, int z, int ncomp, const int* l
    e->committed = false;
    return 0;
 }
-int asd_set_exchange(asd_engine* e, int z, const int* nlist, const int* nlistsize, const double* ncoup) { return set_table(e, e->ex, z, 1, nlist, nlistsize, ncoup); }
+int asd_set_exchange(asd_engine* e, int z, const int* nlist, const int* nlistsize, const double* ncoup) {
+   e->jtensor = false;
+   return set_table(e, e->ex, z, 1, nlist, nlistsize, ncoup);
+}
+int asd_set_jtensor(asd_engine* e, int z, const int* nlist, const int* nlistsize, const double* j_tens) {
+   e->jtensor = true;
+   return set_table(e, e->ex, z, 9, nlist, nlistsize, j_tens);
+}
 int asd_set_dm(asd_engine* e, int z, const int* dmlist, const int* dmlistsize, const double* dm_vect) { return set_table(e, e->dm, z, 3, dmlist, dmlistsize, dm_vect); }
 int asd_set_bq(asd_engine* e, int z, const int* bqlist, const int* bqlistsize, const double* j_bq) { return set_table(e, e->bq, z, 1, bqlist, bqlistsize, j_bq); }
 

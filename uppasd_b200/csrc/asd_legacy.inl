@@ -10,7 +10,7 @@
 //    a side effect of sampled measurements -- always writes the final emom/emomM/mmom/mmom2/mmomi/emom2 back
 //    to the Fortran arrays before returning (uppasd.f90:344-350 writes the restart file from them).
 // Deliberate differences: SDEalgh is honoured (1 = midpoint, 5 = Depondt; the reference CUDA path always ran
-// Depondt -- set ASD_LEGACY_FORCE_DEPONDT=1 to mimic that); do_jtensor=1 is refused loudly.
+// Depondt -- set ASD_LEGACY_FORCE_DEPONDT=1 to mimic that).
 
 #include <ctime>
 
@@ -140,7 +140,6 @@ void cudamdsim_initiateconstants_(void) {
    // this build honours the two solvers on its path and refuses the rest the same way the reference does
    if (!(alg == 1 || alg == 5)) { std::fprintf(stderr, "Invalid SDEalgh!\n"); std::exit(EXIT_FAILURE); }
    if (fd.gpu_rng && (*fd.gpu_rng < 0 || *fd.gpu_rng > 3)) { std::fprintf(stderr, "Unknown gpu_rng %d\n", *fd.gpu_rng); std::exit(EXIT_FAILURE); }
-   if (fd.do_jtensor && *fd.do_jtensor == 1) { std::fprintf(stderr, "uppasd_b200: do_jtensor=1 (tensor exchange) is outside this build's hot path\n"); std::exit(EXIT_FAILURE); }
    if (eng) { asd_destroy(eng); eng = nullptr; }
    if (asd_create(&eng, -1)) die("cudamdsim_initiateconstants_");
    asd_set_constants(eng, *fd.gamma, *fd.k_bolt, *fd.mub, eng->mry);
@@ -156,7 +155,10 @@ void cudamdsim_initiatematrices_(void) {
       const char bc[4] = {*fd.BC1, *fd.BC2, *fd.BC3, 0};
       if (asd_set_lattice_hint(eng, (int)*fd.NA, (int)*fd.N1, (int)*fd.N2, (int)*fd.N3, bc)) die("set_lattice_hint");
    }
-   if (asd_set_exchange(eng, (int)*fd.max_no_neigh, (const int*)fd.nlist, (const int*)fd.nlistsize, fd.ncoup)) die("set_exchange");
+   if (fd.do_jtensor && *fd.do_jtensor == 1) {
+      // tensorial exchange (cudaHamiltonianCalculations.cu:274-343 in the reference's native path): j_tens(3,3,z,nHam)
+      if (asd_set_jtensor(eng, (int)*fd.max_no_neigh, (const int*)fd.nlist, (const int*)fd.nlistsize, fd.j_tensor)) die("set_jtensor");
+   } else if (asd_set_exchange(eng, (int)*fd.max_no_neigh, (const int*)fd.nlist, (const int*)fd.nlistsize, fd.ncoup)) die("set_exchange");
    if (fd.do_dm && *fd.do_dm == 1)
       if (asd_set_dm(eng, (int)*fd.max_no_dmneigh, (const int*)fd.dmlist, (const int*)fd.dmlistsize, fd.dmvect)) die("set_dm");
    if (fd.do_bq && *fd.do_bq == 1)

@@ -71,6 +71,11 @@ class Engine:
         nlist = _i32(nlist)
         self._chk(self.lib.asd_set_exchange(self.h, nlist.shape[0], _p(nlist), _p(_i32(nlistsize)), _p(_f64(ncoup))))
 
+    def set_jtensor(self, nlist, nlistsize, j_tens):
+        """j_tens: (9, z, nHam) = the Fortran (3,3,z,nHam) array"""
+        nlist = _i32(nlist)
+        self._chk(self.lib.asd_set_jtensor(self.h, nlist.shape[0], _p(nlist), _p(_i32(nlistsize)), _p(_f64(j_tens))))
+
     def set_dm(self, dmlist, dmlistsize, dm_vect):
         dmlist = _i32(dmlist)
         self._chk(self.lib.asd_set_dm(self.h, dmlist.shape[0], _p(dmlist), _p(_i32(dmlistsize)), _p(_f64(dm_vect))))
@@ -250,7 +255,10 @@ def engine_from_system(S, consts, sdealgh=1, delta_t=1e-16, damping=0.05, temp=0
     if lattice_hint is not None:
         e.set_lattice_hint(*lattice_hint)
     ex = S['exchange']
-    e.set_exchange(ex['list'], ex['listsize'], ex['coup'])
+    if S.get('do_jtensor', 0) == 1:
+        e.set_jtensor(ex['list'], ex['listsize'], ex['coup'])
+    else:
+        e.set_exchange(ex['list'], ex['listsize'], ex['coup'])
     if S.get('dm') is not None:
         e.set_dm(S['dm']['list'], S['dm']['listsize'], S['dm']['coup'])
     if S.get('bq') is not None:
@@ -288,12 +296,14 @@ class FortranHost:
                        gamma=cd(consts['gama']), k_bolt=cd(consts['k_bolt']), mub=cd(consts['mub']),
                        damping=cd(damping), binderc=cd(0.0), mavg=cd(0.0), mompar=ci(mompar),
                        initexc=C.c_char(b'N'), do_dm=cu(1 if S.get('dm') is not None else 0),
-                       max_no_dmneigh=cu(S['dm']['z'] if S.get('dm') is not None else 1), do_jtensor=cu(0),
+                       max_no_dmneigh=cu(S['dm']['z'] if S.get('dm') is not None else 1), do_jtensor=cu(1 if S.get('do_jtensor', 0) == 1 else 0),
                        do_aniso=cu(1 if S.get('aniso') is not None else 0), nHam=cu(S['nHam']),
                        gpu_mode=ci(1), gpu_rng=ci(0), gpu_rng_seed=ci(gpu_rng_seed))
         z = np.zeros
+        jt = S.get('do_jtensor', 0) == 1
         self.arr = dict(
-            ncoup=_f64(S['exchange']['coup']), nlist=_i32(S['exchange']['list']), nlistsize=_i32(S['exchange']['listsize']),
+            ncoup=_f64(S['exchange']['coup']) if not jt else z((1, 1), order='F'), nlist=_i32(S['exchange']['list']),
+            nlistsize=_i32(S['exchange']['listsize']),
             beff=z((3, N, M), order='F'), b2eff=z((3, N, M), order='F'), emomM=S['emomM'].copy(order='F'),
             emom=S['emom'].copy(order='F'), emom2=z((3, N, M), order='F'), external_field=_f64(S['external_field']),
             mmom=S['mmom'].copy(order='F'), btorque=z((3, N, M), order='F'), Temp_array=np.full(N, float(temp)),
@@ -301,7 +311,7 @@ class FortranHost:
             dm_vect=_f64(S['dm']['coup']) if S.get('dm') is not None else z((3, 1, 1), order='F'),
             dmlist=_i32(S['dm']['list']) if S.get('dm') is not None else z((1, 1), dtype=np.int32),
             dmlistsize=_i32(S['dm']['listsize']) if S.get('dm') is not None else z(1, dtype=np.int32),
-            j_tens=z((3, 3, 1, 1), order='F'),
+            j_tens=_f64(S['exchange']['coup']) if jt else z((3, 3, 1, 1), order='F'),
             kaniso=_f64(S['aniso']['kaniso']) if S.get('aniso') is not None else z((2, 1), order='F'),
             eaniso=_f64(S['aniso']['eaniso']) if S.get('aniso') is not None else z((3, 1), order='F'),
             taniso=_i32(S['aniso']['taniso']) if S.get('aniso') is not None else z(1, dtype=np.int32),
