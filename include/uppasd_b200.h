@@ -194,6 +194,17 @@ int asd_measure(asd_engine* e, double* msum, double* energy);
  * exist on this path): terms(5,M) = exchange, anisotropy, DM, biquadratic, Zeeman; their sum is ene%energy. */
 int asd_energy_terms(asd_engine* e, double* terms);
 
+/* Sublattice-projected sums (buffer_proj_avrg, prn_averages.f90:462-512): msum_na(3,NA,M) = sum of emomM over the atoms
+ * with basis number mod(i-1,NA)+1 = i_na.  projavgs.*.out divides by N1*N2*N3 and, for do_proj_avrg Y, adds the basis
+ * atoms of one type (prn_proj_avrg, :662-760). */
+int asd_measure_sublattice(asd_engine* e, int NA, double* msum_na);
+
+/* Skyrmion number by triangulation (skyno T): simp(3,nsimp) = 1-based atom numbers of the triangle corners as
+ * delaunay_tri_tri builds them (topology.f90:307-380); q[M] = sum over triangles of the signed solid angle / 4 pi per
+ * ensemble (pontryagin_tri, topology.f90:78-116, before its division by Mensemble; buffer_skyno_tri divides by NA). */
+int asd_set_triangulation(asd_engine* e, int nsimp, const int* simp);
+int asd_skyrmion_number(asd_engine* e, double* q);
+
 /* selected moments for trajectory output (prn_trajectories.f90:60-110): atoms[n] 1-based, out(4,n,M) = ex,ey,ez,|m| */
 int asd_get_atoms(asd_engine* e, int n, const int* atoms, double* out);
 

@@ -38,7 +38,7 @@ DEFAULTS = dict(
     mensemble=1, tseed=1, sdealgh=1, initmag=3, mode='S', temp=0.0, nstep=1, damping=0.05, timestep=1.0e-16,
     hfield=(0.0, 0.0, 0.0), do_reduced='N', do_sortcoup='N', mompar=0, landeg_glob=2.0, do_dm=0, do_bq=0, do_jtensor=0,
     do_anisotropy=0, mcnstep=0, avrg_step=100, cumu_step=50, cumu_buff=10, do_avrg='N', do_cumu='N',
-    plotenergy=0, map_multiple=False, gpu_mode=0, ip_mode='N',
+    plotenergy=0, map_multiple=False, gpu_mode=0, ip_mode='N', aunits='N',
 )
 
 
@@ -57,7 +57,7 @@ def read_inpsd(path):
         key = t[0].lower()
         v = t[1:]
         if key == 'simid':
-            d['simid'] = v[0]
+            d['simid'] = v[0][:8]                      # character(len=8) :: simid
         elif key == 'ncell':
             d['ncell'] = tuple(int(x) for x in v[:3])
         elif key == 'bc':
@@ -128,6 +128,8 @@ def read_inpsd(path):
             d['gpu_mode'] = int(v[0])
         elif key == 'ip_mode':
             d['ip_mode'] = v[0].upper()
+        elif key == 'aunits':
+            d['aunits'] = v[0].upper()
     d['files'] = files
     return d
 

@@ -18,6 +18,14 @@ _LIB = None
 
 # source/Parameters/constants.f90:14-29
 CONST = dict(gama=1.760859644e11, k_bolt=1.38064852e-23, mub=9.274009994e-24, mry=2.179872325e-21)
+# aunits Y (uppasd.f90:794-797 -> change_constants, inputhandler.f90:1685-1704): model Hamiltonians in units where every
+# physical constant on this path is 1
+AUNITS = dict(gama=1.0, k_bolt=1.0, mub=1.0, mry=1.0)
+
+
+def consts(S):
+    """the constants a system was mounted with (S['const']; SI unless the input says aunits Y)"""
+    return S.get('const', CONST)
 
 
 def build(force=False):
@@ -79,7 +87,7 @@ def neighbour_table(S, nn, redcoord, xc, nntype, sym, hdim, lexp, do_sortcoup=Fa
     ncoup = np.zeros((hdim, z, NH), order='F')
     xc = np.asfortranarray(xc, dtype=np.float64)
     L.orc_mount(h, N, NT, NA, NH, _p(S['anumb']), _p(S['atype']), z, _p(nn), _p(xc), _p(S['ammom_inp']), hdim, lexp,
-                int(do_sortcoup), int(map_multiple), _d(CONST['mry']), _d(CONST['mub']), _p(nlistsize), _p(nlist),
+                int(do_sortcoup), int(map_multiple), _d(consts(S)['mry']), _d(consts(S)['mub']), _p(nlistsize), _p(nlist),
                 _p(ncoup))
     me, mnn = L.orc_nm_max_no_equiv(h), L.orc_nm_maxnn(h)
     nm_cell = np.zeros((me, ms, NA), dtype=np.int32, order='F')
@@ -103,6 +111,7 @@ def build_system(inp, bas, atype_inp, ammom_inp, aemom_inp, landeg_ch, exchange,
     M = inp['mensemble']
     cell = np.array(inp['cell'], dtype=np.float64)
     S = dict(Natom=N, NA=NA, NT=int(atype_inp.max()), ncell=(N1, N2, N3), cell=cell, bc=inp['bc'], Mensemble=M)
+    S['const'] = dict(AUNITS if inp.get('aunits', 'N') == 'Y' else CONST)
     S['bas'] = np.asfortranarray(bas, dtype=np.float64).copy(order='F')
     S['atype_inp'] = np.ascontiguousarray(atype_inp, dtype=np.int32)
     anumb_inp = np.arange(1, NA + 1, dtype=np.int32)
@@ -140,7 +149,7 @@ def build_system(inp, bas, atype_inp, ammom_inp, aemom_inp, landeg_ch, exchange,
         ka = np.zeros((2, N), order='F')
         sb = np.zeros(N)
         L.orc_setup_anisotropies(N, NA, _p(S['anumb']), _p(np.ascontiguousarray(atyp, dtype=np.int32)),
-                                 _p(np.asfortranarray(an)), _p(S['ammom_inp']), _d(CONST['mry']), _d(CONST['mub']),
+                                 _p(np.asfortranarray(an)), _p(S['ammom_inp']), _d(consts(S)['mry']), _d(consts(S)['mub']),
                                  _p(ta), _p(ea), _p(ka), _p(sb))
         S['aniso'] = dict(taniso=ta, eaniso=ea, kaniso=ka, sb=sb)
     for k in ('mmom', 'mmom0', 'mmomi'):
@@ -189,8 +198,19 @@ def effective_field(S, emomM=None, want_parts=False):
     b1 = np.zeros((3, N, M), order='F') if want_parts else None
     b2 = np.zeros((3, N, M), order='F') if want_parts else None
     e = L.orc_effective_field(C.byref(H), _p(emomM), _p(S['external_field']), _p(beff), _p(b1), _p(b2),
-                              _d(CONST['mub']), _d(CONST['mry']))
+                              _d(consts(S)['mub']), _d(consts(S)['mry']))
     return (beff, b1, b2, e) if want_parts else (beff, e)
+
+
+def energy_terms(S, emomM=None):
+    """calc_energy (energy.f90:181-398): terms(5, M) = exchange (pair energy for do_jtensor 1), anisotropy, DM, biquadratic,
+    Zeeman per atom in mRy, as the columns Exc, Ani, DM, BQ, Zeeman of totenergy.*.out (their sum is the column Tot)."""
+    H = ham_struct(S)
+    N, M = S['Natom'], S['Mensemble']
+    emomM = S['emomM'] if emomM is None else np.asfortranarray(emomM)
+    t = np.zeros((5, M), order='F')
+    lib().orc_energy_terms(C.byref(H), _p(emomM), _p(S['external_field']), _p(t))
+    return t * (consts(S)['mub'] / consts(S)['mry'])
 
 
 class SdState:
@@ -214,8 +234,8 @@ class SdState:
         g = np.asfortranarray(gauss) if gauss is not None else None
         L.orc_sd_step(C.byref(self.H), self.sdealgh, _p(self.emom), _p(self.emomM), _p(self.mmom), _p(self.mmom0),
                       _p(S['external_field']), _p(S['Landeg']), _p(self.lambda1), _p(self.temp),
-                      _d(self.temprescale), _d(self.delta_t), self.mompar, _p(g), _d(CONST['gama']),
-                      _d(CONST['k_bolt']), _d(CONST['mub']), _d(CONST['mry']), _p(self.work))
+                      _d(self.temprescale), _d(self.delta_t), self.mompar, _p(g), _d(consts(self.S)['gama']),
+                      _d(consts(self.S)['k_bolt']), _d(consts(self.S)['mub']), _d(consts(self.S)['mry']), _p(self.work))
 
     def sum_moments(self):
         N, M = self.S['Natom'], self.S['Mensemble']
@@ -364,7 +384,7 @@ def mc_run(S, mode, temperature, nsweeps, seed=1, sample_every=1, burn=0, extfie
         fa = rng_uniform(N * M)
         L.orc_mc_sweep(C.byref(H), C.c_char(mode.encode()), _p(iflip), _p(emomM), _p(emom), _p(mmom), _p(ef),
                        _p(S['external_field']), _d(temperature), _d(1.0), _p(fm), _p(fg), _p(mf), _p(fa),
-                       _d(CONST['k_bolt']), _d(CONST['mub']))
+                       _d(consts(S)['k_bolt']), _d(consts(S)['mub']))
         if sweep % (reshuffle_every or max(1, nsweeps // 10)) == 0:      # mcnstep/10 of the PHASE (mc_driver.f90:407-410)
             L.orc_choose_random_atom_x(N, _p(iflip))
         if sweep > burn and sweep % sample_every == 0:
@@ -373,6 +393,44 @@ def mc_run(S, mode, temperature, nsweeps, seed=1, sample_every=1, burn=0, extfie
             mags.append(np.sqrt(((m / N) ** 2).sum(axis=0)))
             beff = np.zeros((3, N, M), order='F')
             e = L.orc_effective_field(C.byref(H), _p(emomM), _p(S['external_field']), _p(beff), None, None,
-                                      _d(CONST['mub']), _d(CONST['mry']))
+                                      _d(consts(S)['mub']), _d(consts(S)['mry']))
             ens.append(e / (N * M))
     return np.array(mags), np.array(ens), (emom, emomM, mmom)
+
+
+# ---- topology (skyno T) ---------------------------------------------------------------------------
+def delaunay_tri_tri(nx, ny, nz, nt):
+    """delaunay_tri_tri (source/Measurement/topology.f90:307-380), loop for loop: simp(3, 2*nx*ny*nz*nt), 1-based."""
+    def wrap_idx(x, y, z):
+        return nx * ny * (z - 1) + nx * (y - 1) + x
+    simp = []
+    for z in range(1, nz + 1):
+        for y in range(1, ny + 1):
+            for x in range(1, nx + 1):
+                for it in range(1, nt + 1):
+                    simp.append((nt * wrap_idx(x, y, z) + it - nt,
+                                 nt * wrap_idx(x % nx + 1, y, z) + it - nt,
+                                 nt * wrap_idx(x, y % ny + 1, z) + it - nt))
+    for z in range(1, nz + 1):
+        for y in range(1, ny + 1):
+            for x in range(1, nx + 1):
+                for it in range(1, nt + 1):
+                    simp.append((nt * wrap_idx(x, y, z) + it - nt,
+                                 nt * wrap_idx(x, y % ny + 1, z) + it - nt,
+                                 nt * wrap_idx((x - 2) % nx + 1, y % ny + 1, z) + it - nt))
+    return np.asfortranarray(np.array(simp, dtype=np.int32).T)
+
+
+def pontryagin_tri(emom, simp):
+    """pontryagin_tri (topology.f90:78-116): sum over triangles and ensembles of 2 atan(m1.(m2 x m3) / (1 + m1.m2 + m1.m3 +
+    m2.m3)) / (4 pi) / Mensemble, with f_volume(a, b, c) = (a x b) . c (math_functions.f90:59-73).  Also returns the
+    per-ensemble sums / 4 pi."""
+    emom = np.asarray(emom)
+    M = emom.shape[2]
+    per = np.zeros(M)
+    for k in range(M):
+        m1, m2, m3 = (emom[:, simp[c] - 1, k] for c in range(3))
+        vol = (np.cross(m1.T, m2.T) * m3.T).sum(axis=1)
+        d = 1.0 + (m1 * m2).sum(axis=0) + (m1 * m3).sum(axis=0) + (m2 * m3).sum(axis=0)
+        per[k] = (2.0 * np.arctan(vol / d)).sum() / (4.0 * np.pi)
+    return per.sum() / M, per

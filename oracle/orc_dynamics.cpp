@@ -179,6 +179,55 @@ double orc_effective_field(const OrcHam* Hp, const double* emomM, const double* 
    return energy * mub / mry;
 }
 
+// calc_energy (source/Hamiltonian/energy.f90:181-342 with update_ene :559-571, do_lsf N): per ensemble the sums over
+// atoms of -factor * m_i . b_term(i), factor 1/2 for the bilinear terms and the anisotropy, 1/4 for the biquadratic
+// term, 1 for the external field, then divided by the number of atoms.  terms(5, M) = exchange (the "Heis-Tens" pair
+// energy when do_jtensor 1), anisotropy, DM, biquadratic, Zeeman -- in field units; totenergy.*.out prints the ensemble
+// means times fcinv = mub / mry (:170, :383-398), which is what the caller applies.
+void orc_energy_terms(const OrcHam* Hp, const double* emomM, const double* external_field, double* terms) {
+   const OrcHam& H = *Hp;
+   const long N = H.Natom, M = H.Mensemble;
+   for (long k = 1; k <= M; k++) {
+      double exc = 0.0, edm = 0.0, ebq = 0.0, eani = 0.0, eext = 0.0;
+      for (long i = 1; i <= N; i++) {
+         const double* m = emomM + 3 * ((i - 1) + (size_t)N * (k - 1));
+         auto upd = [&](const double* b, double factor) { return -factor * (m[0] * b[0] + m[1] * b[1] + m[2] * b[2]); };
+         double b[3] = {0.0, 0.0, 0.0};
+         if (H.do_jtensor != 1) heisenberg_field(H, i, k, emomM, b);
+         else tensor_field(H, i, k, emomM, b);
+         exc = exc + upd(b, 0.5);
+         if (H.do_jtensor != 1 && H.do_dm == 1) {
+            double d[3] = {0.0, 0.0, 0.0};
+            dm_field(H, i, k, emomM, d);
+            edm = edm + upd(d, 0.5);
+         }
+         if (H.do_bq == 1) {
+            double q[3] = {0.0, 0.0, 0.0};
+            bq_field(H, i, k, emomM, q);
+            ebq = ebq + upd(q, 0.25);
+         }
+         if (H.do_anisotropy == 1) {
+            const int t = H.taniso[i - 1];
+            double a[3] = {0.0, 0.0, 0.0};
+            if (t == 1) { uniaxial_field(H, i, m, a); eani = eani + upd(a, 0.5); }
+            else if (t == 2) { cubic_field(H, i, m, a); eani = eani + upd(a, 0.5); }
+            else if (t == 7) {
+               double c[3] = {0.0, 0.0, 0.0};
+               uniaxial_field(H, i, m, a);
+               cubic_field(H, i, m, c);
+               for (int x = 0; x < 3; x++) a[x] = a[x] + c[x] * H.sb[i - 1];
+               eani = eani + upd(a, 0.5);
+            }
+         }
+         const double* he = external_field + 3 * ((i - 1) + (size_t)N * (k - 1));
+         const double hb[3] = {0.0 + he[0], 0.0 + he[1], 0.0 + he[2]};
+         eext = eext + upd(hb, 1.0);
+      }
+      double* t = terms + 5 * (k - 1);
+      t[0] = exc / N; t[1] = eani / N; t[2] = edm / N; t[3] = ebq / N; t[4] = eext / N;
+   }
+}
+
 // ---- midpoint (SDEalgh 1) ---------------------------------------------------------------------
 // Cayley update shared by predictor and corrector (midpoint.f90:153-164 / :303-313): returns et*detAi.
 static inline void cayley(const double* e, const double* A, double* out) {

@@ -129,6 +129,42 @@ def main():
         'totenergy': {'1400': -4.99936339},
         'tol': 1e-8, 'yaml': 'tests/regulartests.yaml:2-26'}
     fx['heischain'] = f
+    # --- tests/Cluster: 43-atom finite cluster (BC 0 0 0), BIQUADRATIC exchange, anisotropy type 7 (uniaxial + cubic x ratio),
+    #     random start, Depondt through two T = 0 initial phases and 30000 undamped steps (regulartests.yaml:182-205), 1e-8 abs
+    f = fixture('Cluster')
+    f['ip_phases'] = [{'nstep': 1000, 'temp': 0.0, 'timestep': 2e-16, 'damping': 0.10},
+                      {'nstep': 4000, 'temp': 0.0, 'timestep': 1e-16, 'damping': 0.01}]
+    f['ip_source'] = 'tests/Cluster/inpsd.dat:18-21 (ip_mode S, ip_nphase 2; ipSDEalgh defaults to SDEalgh = 5)'
+    f['expected'] = {
+        'averages': {'25000': [0.0507836321, 0.00124796445, -0.0415898147, 0.0656524743]},
+        'totenergy': {'15000': {'tot': -4.04082234, 'exc': -3.39086666, 'ani': 0.00237801922, 'bq': -0.652333705}},
+        'tol': 1e-8, 'yaml': 'tests/regulartests.yaml:182-205'}
+    fx['cluster'] = f
+    # --- tests/HeisStripe: 10 x 1 x 100 stripe (BC 0 0 P), UNIAXIAL anisotropy (type 1), random start, midpoint, T = 0
+    #     (ip_mode N: no initial phase) (regulartests.yaml:105-129), 1e-8 abs
+    f = fixture('HeisStripe')
+    f['expected'] = {
+        'averages': {'1190': [0.0267646384, 0.034416429, -0.00313586401, 0.0437112125]},
+        'totenergy': {'1460': {'tot': -1.19366393, 'exc': -1.18719839, 'ani': -0.00646554288}},
+        'tol': 1e-8, 'yaml': 'tests/regulartests.yaml:105-129'}
+    fx['heisstripe'] = f
+    # --- tests/HeisChainAF: antiferromagnetic chain, 2 atom types, random start, midpoint, T = 0; sublattice-projected
+    #     averages (regulartests.yaml:54-103), 1e-8 abs
+    f = fixture('HeisChainAF')
+    f['expected'] = {
+        'averages': {'1000': [0.0538882967, 0.0142337295, 0.00361204926, 0.0558533301]},
+        'projavgs': {'5000': {'1': [0.47725269, -0.383636422, -0.225160187, -0.172904932],
+                              '2': [0.930466673, 0.750387815, 0.438670217, 0.332046379]}},
+        'totenergy': {'1500': {'tot': -1.53826977}},
+        'tol': 1e-8, 'yaml': 'tests/regulartests.yaml:54-103'}
+    fx['heischainaf'] = f
+    # --- tests/SCsurf: 16 x 16 monolayer, Heisenberg + DM + uniaxial anisotropy in ATOMIC UNITS (aunits Y: every constant 1),
+    #     maptype 2, random start, midpoint, T = 0 (regulartests.yaml:158-170), 1e-8 abs
+    f = fixture('SCsurf')
+    f['expected'] = {
+        'averages': {'800': [-8.05438058e-05, -6.4699084e-05, -6.60907331e-05, 0.000122642819]},
+        'tol': 1e-8, 'yaml': 'tests/regulartests.yaml:158-170'}
+    fx['scsurf'] = f
     for k, v in fx.items():
         with open(os.path.join(HERE, k + '.json'), 'w') as fh:
             json.dump(v, fh, indent=1, default=lambda o: list(o))

@@ -11,7 +11,7 @@ from oracle import orc
 from uppasd_b200 import asdio, observables
 from util import GOLDEN
 
-NAMES = ['kagome', 'megatest', 'feco', 'bccfe_cuda', 'bccfe']
+NAMES = ['kagome', 'megatest', 'feco', 'bccfe_cuda', 'bccfe', 'cluster', 'heisstripe', 'heischainaf', 'scsurf']
 
 
 def materialise(name, tmp_path, subst=None):
@@ -116,3 +116,78 @@ def test_averages_buffer():
     assert av.sample(0, np.array([[1.0, 3.0], [0.0, 0.0], [0.0, 4.0]])) is None
     rows = av.sample(100, np.array([[2.0, 2.0], [0.0, 0.0], [0.0, 0.0]]))
     assert len(rows) == 2 and rows[0][0] == 0 and abs(rows[0][4] - 0.5 * (0.1 + 0.5)) < 1e-15 and rows[1][5] == 0.0
+
+
+def test_reference_uniform_generator_and_random_start():
+    """uppasd_b200/refrng.py (product, Python integers) against the reference's known answers and
+    against the test-only C++ restatement: Initmag 1 starts are identical bit for bit."""
+    from uppasd_b200 import refrng
+    from util import load_golden
+    g = refrng.ReferenceUniform(5)
+    assert [g.word() for _ in range(3)] == [953453411, 236996814, 2970113047]
+    for name in ('solvers', 'cluster', 'heisstripe'):
+        fx, inp, S = load_golden(name)
+        orc.initmag1(S, inp['tseed'])
+        e = refrng.random_start(S['NA'], S['ncell'], inp['tseed'])
+        assert np.array_equal(e, S['emom'][:, :, 0]), name
+
+
+def test_triangulation_and_projected_estimators():
+    from uppasd_b200 import lattice
+    from util import load_golden
+    for dims in ((3, 2, 1, 1), (5, 4, 2, 3), (16, 16, 1, 1)):
+        assert np.array_equal(lattice.triangulation(*dims), orc.delaunay_tri_tri(*dims))
+    # projavgs rows from the oracle's state of tests/HeisChainAF at iteration 5000 (regulartests.yaml:69-92)
+    fx, inp, S = load_golden('heischainaf')
+    orc.initmag1(S, inp['tseed'])
+    st = orc.SdState(S, inp['sdealgh'], inp['timestep'], inp['damping'])
+    for _ in range(5000):
+        st.step()
+    na = S['NA']
+    msum_na = np.stack([st.emomM[:, c::na, :].sum(axis=1) for c in range(na)], axis=1)       # (3, NA, M)
+    rows = observables.projected_rows(5000, msum_na, S['Natom'] // na, S['atype_inp'], 'Y')
+    for r in rows:
+        want = fx['expected']['projavgs']['5000'][str(r[1])]
+        for a, b in zip((r[2], r[4], r[5], r[6]), want):
+            assert abs(a - b) <= 1e-8, (r, want)
+    # running mean / variance of the skyrmion number (prn_topology.f90:321-327)
+    sk = observables.SkyrmionNumber(1)
+    xs = [1.0, 0.5, 2.0, -1.0]
+    for i, x in enumerate(xs):
+        row = sk.sample(i, [x, x])
+    assert abs(row[2] - np.mean(xs)) < 1e-15 and abs(row[3] - np.var(xs)) < 1e-15
+
+
+def test_skyrmion_number_of_a_neel_skyrmion_is_an_integer():
+    n = 32
+    a1, a2 = np.array([1.0, 0.0]), np.array([-0.5, 0.866025403784])
+    ix, iy = np.meshgrid(np.arange(n), np.arange(n), indexing='xy')
+    pos = ix.ravel()[:, None] * a1 + iy.ravel()[:, None] * a2
+    d = pos - pos.mean(axis=0)
+    r, phi = np.hypot(d[:, 0], d[:, 1]), np.arctan2(d[:, 1], d[:, 0])
+    th = np.pi * np.exp(-r / 4.0)
+    e = np.stack([np.sin(th) * np.cos(phi), np.sin(th) * np.sin(phi), np.cos(th)])[:, :, None]
+    q, per = orc.pontryagin_tri(e, orc.delaunay_tri_tri(n, n, 1, 1))
+    assert abs(q + 1.0) < 1e-12 and abs(per[0] + 1.0) < 1e-12
+
+
+def test_single_cell_stencil_keeps_folded_neighbours():
+    """tests/Cluster is ONE cell with 43 basis atoms and BC 0 0 0; several basis positions are negative and get folded to the
+    far side of the 10 x 10 x 10 cell.  The reference keeps the neighbours found through the fold because a single cell
+    has no cell hops at all (neighbourmap.f90:226-230, 270-296).  The product's stencil must do the same: its entries,
+    de-duplicated in order (hamiltonianinit.f90:1055-1059), are the oracle's neighbour lists."""
+    from uppasd_b200 import lattice
+    from util import load_golden
+    fx, inp, S = load_golden('cluster')
+    args = oinputs.load_fixture(fx)
+    for key, mk, sym, typed in (('exchange', args[6], inp['sym'], True), ('bq', args[8], inp['sym'], False)):
+        nn, red, xc, nntype = mk(S)
+        ns, ca, cs, sh = lattice.stencil(inp['cell'], S['bas'], S['atype_inp'], nn, red, sym, nntype if typed else None, ncell=inp['ncell'])
+        assert not cs.any()
+        for i0 in range(S['NA']):
+            seen = []
+            for q in range(ns[i0]):
+                if ca[i0, q] not in seen:
+                    seen.append(int(ca[i0, q]))
+            n = S[key]['listsize'][i0]
+            assert seen == list(S[key]['list'][:n, i0]), (key, i0)

@@ -120,3 +120,61 @@ def test_restart_and_relax_api(tmp_path):
     b.relax('H', 20, 1.0)
     b.relax('S', 200, 0.0, 1e-16, 0.5)
     assert b.energy() <= e0 + 1e-6
+
+
+def test_cluster_run_directory(tmp_path):
+    """tests/Cluster through the driver (regulartests.yaml:182-205, tol 1e-8): random start from the reference's own
+    generator (uppasd_b200/refrng.py), two Depondt initial phases, BQ + type-7 anisotropy, energy columns."""
+    from uppasd_b200 import driver
+    fx, path = materialise('cluster', tmp_path)
+    driver.Simulation(path).run()
+    d, exp = str(tmp_path), fx['expected']
+    r = _row(os.path.join(d, 'averages.ClusterT.out'), 25000)
+    for a, b in zip(r[1:5], exp['averages']['25000']):
+        assert abs(a - b) <= 1e-8, (r, exp)
+    e = _row(os.path.join(d, 'totenergy.ClusterT.out'), 15000)
+    want = exp['totenergy']['15000']
+    for col, key in ((1, 'tot'), (2, 'exc'), (3, 'ani'), (7, 'bq')):
+        assert abs(e[col] - want[key]) <= 1e-8, (key, e, want)
+
+
+def test_heischainaf_run_directory_projected_averages(tmp_path):
+    """tests/HeisChainAF through the driver (regulartests.yaml:54-103): averages, total energy, and projavgs.*.out from the
+    device's sublattice sums (asd_measure_sublattice)."""
+    from uppasd_b200 import driver
+    fx, path = materialise('heischainaf', tmp_path)
+    inp = asdio.read_inpsd(path)
+    inp['nstep'] = 5100
+    driver.Simulation(inp, directory=str(tmp_path)).run()
+    d, exp = str(tmp_path), fx['expected']
+    r = _row(os.path.join(d, 'averages.AF_WireT.out'), 1000)
+    for a, b in zip(r[1:5], exp['averages']['1000']):
+        assert abs(a - b) <= 1e-8
+    assert abs(_row(os.path.join(d, 'totenergy.AF_WireT.out'), 1500)[1] - exp['totenergy']['1500']['tot']) <= 1e-8
+    rows = [x for x in asdio.read_out(os.path.join(d, 'projavgs.AF_WireT.out')) if int(x[0]) == 5000]
+    assert len(rows) == 2
+    for x in rows:
+        want = exp['projavgs']['5000'][str(int(x[1]))]
+        for a, b in zip((x[2], x[4], x[5], x[6]), want):
+            assert abs(a - b) <= 1e-8, (x, want)
+
+
+@pytest.mark.parametrize('name,simid', [('heisstripe', 'HeisStri'), ('scsurf', 'SCsurf_T')])
+def test_more_run_directories(name, simid, tmp_path):
+    """tests/HeisStripe (uniaxial anisotropy, open edges) and tests/SCsurf (aunits Y, DM, anisotropy; its `skyno Y` is not
+    on this path and only warns) through the driver, reference tolerances (regulartests.yaml:105-129, 158-170)."""
+    import warnings
+    from uppasd_b200 import driver
+    fx, path = materialise(name, tmp_path)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        driver.Simulation(path).run()
+    d, exp = str(tmp_path), fx['expected']
+    for it, want in exp['averages'].items():
+        r = _row(os.path.join(d, 'averages.%s.out' % simid), int(it))
+        for a, b in zip(r[1:5], want):
+            assert abs(a - b) <= 1e-8, (name, r, want)
+    for it, want in exp.get('totenergy', {}).items():
+        e = _row(os.path.join(d, 'totenergy.%s.out' % simid), int(it))
+        for col, key in ((1, 'tot'), (2, 'exc'), (3, 'ani')):
+            assert abs(e[col] - want[key]) <= 1e-8, (name, key, e, want)

@@ -24,6 +24,10 @@ CASES = [
     ('feco', dict(ncell=(3, 4, 2), do_reduced='N')),           # tiny periodic box: duplicate neighbours dropped
     ('bccfe_cuda', dict(ncell=(12, 10, 8))),
     ('bccfe_cuda', dict(ncell=(4, 4, 4), do_reduced='N', bc=('P', '0', 'P'))),
+    ('cluster', dict()),                                       # ONE cell, 43 basis atoms, BC 0 0 0: hops forced to zero; BQ table (lexp 2)
+    ('heisstripe', dict()),                                    # BC 0 0 P stripe
+    ('heischainaf', dict()),                                   # two atom types
+    ('scsurf', dict()),                                        # atomic units, maptype 2, DM
 ]
 
 
@@ -36,12 +40,15 @@ def test_device_tables_bit_exact(name, over):
     kinds = [(0, 'exchange', args[6], 1, 1, inp['sym'], True)]
     if args[7] is not None:
         kinds.append((1, 'dm', args[7], 3, 1, 0, False))
+    if args[8] is not None:
+        kinds.append((2, 'bq', args[8], 1, 2, inp['sym'], False))     # hamiltonianinit.f90:485-487: BQ map WITH the lattice symmetry
+    c = orc.consts(S)
     e = host.Engine()
     e.set_system(S['Natom'], 1, S['nHam'], S['aHam'])
     for kind, key, mk, ncomp, lexp, sym, typed in kinds:
         nn, red, xc, nntype = mk(S)
-        ns, ca, cs, sh = lattice.stencil(inp['cell'], S['bas'], S['atype_inp'], nn, red, sym, nntype if typed else None)
-        cp = lattice.couplings(ns, ca, sh, S['atype_inp'], xc, S['ammom_inp'], orc.CONST['mry'], orc.CONST['mub'], lexp)
+        ns, ca, cs, sh = lattice.stencil(inp['cell'], S['bas'], S['atype_inp'], nn, red, sym, nntype if typed else None, ncell=inp['ncell'])
+        cp = lattice.couplings(ns, ca, sh, S['atype_inp'], xc, S['ammom_inp'], c['mry'], c['mub'], lexp)
         e.build_lattice_table(kind, S['NA'], inp['ncell'], inp['bc'], ns, ca, cs, cp)
         lst, size, coup = e.get_table(kind)
         ref = S[key]

@@ -11,19 +11,21 @@ from util import load_golden
 
 pytestmark = pytest.mark.gpu
 
-FIX = ['kagome', 'megatest', 'feco', 'bccfe_cuda']
+FIX = ['kagome', 'megatest', 'feco', 'bccfe_cuda', 'cluster', 'heisstripe', 'heischainaf', 'scsurf']
 
 
 def _engine(S, inp, **kw):
     from uppasd_b200 import host
     args = dict(sdealgh=inp['sdealgh'], delta_t=inp['timestep'], damping=inp['damping'], temp=0.0, mompar=inp['mompar'])
     args.update(kw)
-    return host.engine_from_system(S, orc.CONST, **args)
+    return host.engine_from_system(S, orc.consts(S), **args)
 
 
 @pytest.mark.parametrize('name', FIX)
 def test_field_parity(name):
     fx, inp, S = load_golden(name)
+    if inp['initmag'] == 1:
+        orc.initmag1(S, inp['tseed'])
     e = _engine(S, inp)
     beff, b1, b2, en = e.effective_field(parts=True)
     rb, r1, r2, ren = orc.effective_field(S, want_parts=True)
@@ -38,6 +40,8 @@ def test_field_parity(name):
 @pytest.mark.parametrize('alg', [1, 5])
 def test_t0_trajectory(name, alg):
     fx, inp, S = load_golden(name)
+    if inp['initmag'] == 1:
+        orc.initmag1(S, inp['tseed'])
     e = _engine(S, inp, sdealgh=alg)
     st = orc.SdState(S, alg, inp['timestep'], inp['damping'])
     done = 0
@@ -342,3 +346,70 @@ def test_tensor_exchange_field_trajectory_and_golden():
                           avrg_step=inp['avrg_step']).run()
     for a, b in zip(fh.averages[1300], fx['expected']['averages']['1300']):
         assert abs(a - b) <= 1e-8
+
+
+@pytest.mark.parametrize('name', FIX + ['kagome_cuda'])
+def test_energy_terms_parity(name):
+    """asd_energy_terms against the oracle's calc_energy restatement (energy.f90:181-398) on every fixture: exchange / pair,
+    anisotropy, DM, biquadratic, Zeeman per atom in mRy, 1e-12 relative to the largest term."""
+    fx, inp, S = load_golden(name)
+    if inp['initmag'] == 1:
+        orc.initmag1(S, inp['tseed'])
+    e = _engine(S, inp)
+    e.sd_steps(25)
+    emomM = e.get_moments()[1]
+    got = e.energy_terms()
+    ref = orc.energy_terms(S, emomM)
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max(), (got, ref)
+    assert abs(ref[0, 0]) > 0
+
+
+def _gpu_rows(e, S, marks):
+    out, done = {}, 0
+    for it in sorted(marks):
+        if it > done:
+            e.sd_steps(it - done, first_step=done + 1)
+            done = it
+        m = e.measure()[:, 0] / S['Natom']
+        out[it] = (list(m) + [float(np.sqrt((m ** 2).sum()))], e.energy_terms()[:, 0])
+    return out
+
+
+def test_cluster_golden_on_gpu():
+    """tests/Cluster (regulartests.yaml:182-205, 1e-8): BQ + type-7 anisotropy + Depondt through the two initial phases
+    (set_llg between phases, as sd_iphase does) and the undamped measurement phase."""
+    fx, inp, S = load_golden('cluster')
+    orc.initmag1(S, inp['tseed'])
+    e = _engine(S, inp, sdealgh=5, delta_t=fx['ip_phases'][0]['timestep'], damping=fx['ip_phases'][0]['damping'])
+    e.sd_steps(fx['ip_phases'][0]['nstep'])
+    ph = fx['ip_phases'][1]
+    e.set_llg(5, ph['timestep'], landeg=S['Landeg'], lambda1=ph['damping'], temp=0.0)
+    e.sd_steps(ph['nstep'])
+    e.set_llg(5, inp['timestep'], landeg=S['Landeg'], lambda1=inp['damping'], temp=0.0)
+    r = _gpu_rows(e, S, {15000, 25000})
+    exp = fx['expected']
+    for a, b in zip(r[25000][0], exp['averages']['25000']):
+        assert abs(a - b) <= 1e-8, (a, b)
+    t, en = r[15000][1], exp['totenergy']['15000']
+    for a, b in ((t.sum(), en['tot']), (t[0], en['exc']), (t[1], en['ani']), (t[3], en['bq'])):
+        assert abs(a - b) <= 1e-8, (a, b)
+
+
+@pytest.mark.parametrize('name', ['heisstripe', 'heischainaf', 'scsurf'])
+def test_more_reference_goldens_on_gpu(name):
+    """tests/HeisStripe, tests/HeisChainAF, tests/SCsurf (regulartests.yaml:54-129,158-170, 1e-8): printed averages and
+    energy columns from the GPU path."""
+    fx, inp, S = load_golden(name)
+    orc.initmag1(S, inp['tseed'])
+    e = _engine(S, inp)
+    exp = fx['expected']
+    marks = {int(k) for k in exp['averages']} | {int(k) for k in exp.get('totenergy', {})}
+    r = _gpu_rows(e, S, marks)
+    for k, v in exp['averages'].items():
+        for a, b in zip(r[int(k)][0], v):
+            assert abs(a - b) <= 1e-8, (name, k, a, b)
+    for k, v in exp.get('totenergy', {}).items():
+        t = r[int(k)][1]
+        got = {'tot': t.sum(), 'exc': t[0], 'ani': t[1], 'dm': t[2], 'bq': t[3]}
+        for key, b in v.items():
+            assert abs(got[key] - b) <= 1e-8, (name, k, key, got[key], b)

@@ -133,3 +133,56 @@ def test_triangular_heat_bath_anneal_observables(tmp_path):
     rm, re_, (emom, emomM, mmom) = orc.mc_run(S, 'H', T, 350, seed=4, sample_every=5, burn=150)
     assert abs(ge.mean() - re_.mean()) < 0.03 * abs(re_.mean()) + 5 * ge.std() / np.sqrt(ge.size)
     assert abs(gm.mean() - emomM[2].mean()) < 0.05 * abs(emomM[2].mean()) + 0.02
+
+
+def test_skyrmion_number_and_sublattice_sums(tmp_path):
+    """asd_skyrmion_number against the oracle's pontryagin_tri on the triangulation delaunay_tri_tri builds (topology.f90),
+    for a Neel skyrmion written into the triangular lattice (Q = -1), a twisted texture, both device layouts (LLG tiles and
+    Monte Carlo colour order), and the sknumber.*.out the driver writes with skyno T; asd_measure_sublattice against numpy."""
+    from uppasd_b200 import asdio, driver, lattice
+    n1, n2 = 64, 32
+    path = _write(str(tmp_path), ncell=(n1, n2, 1), nstep=100, extra='skyno T\nskyno_step 50\nskyno_buff 2\ndo_proj_avrg A')
+    sim = driver.Simulation(path)
+    e = sim.engine
+    N = n1 * n2
+    simp = orc.delaunay_tri_tri(n1, n2, 1, 1)
+    assert np.array_equal(simp, lattice.triangulation(n1, n2, 1, 1))
+    idx = np.arange(N)
+    pos = np.outer(idx % n1, A1[:2]) + np.outer(idx // n1, A2[:2])
+    d = pos - pos.mean(axis=0)
+    r, phi = np.hypot(d[:, 0], d[:, 1]), np.arctan2(d[:, 1], d[:, 0])
+    th = np.pi * np.exp(-r / 5.0)
+    sk = np.stack([np.sin(th) * np.cos(phi), np.sin(th) * np.sin(phi), np.cos(th)])
+    ph = 2 * np.pi * np.modf(np.arange(1, N + 1) * 0.6180339887)[0]
+    tw = np.stack([0.6 * np.cos(ph), 0.6 * np.sin(ph), np.full(N, 0.8)])
+    tw /= np.sqrt((tw ** 2).sum(axis=0))
+    emom = np.asfortranarray(np.stack([sk, tw], axis=2))
+    mmom = np.full((N, 2), 1.5, order='F')
+    e.set_moments(emom, mmom)
+    q = e.skyrmion_number()
+    qref, per = orc.pontryagin_tri(emom, simp)
+    assert abs(per[0] + 1.0) < 1e-10
+    assert np.abs(q - per).max() <= 1e-12 * max(1.0, np.abs(per).max()), (q, per)
+    ms = e.measure_sublattice(1)
+    assert np.abs(ms[:, 0, :] - (emom * mmom[None]).sum(axis=1)).max() <= 1e-9
+    # the same state in the Monte Carlo (colour-major) layout: zero sweeps move the state there
+    e.mc_sweeps('H', 0, 1.0)
+    e.mc_sweeps('M', 1, 1e-9)
+    q2 = e.skyrmion_number()
+    em2 = e.get_moments()[0]
+    assert np.abs(q2 - orc.pontryagin_tri(em2, simp)[1]).max() <= 1e-12 * max(1.0, np.abs(q2).max())
+    # driver output: sknumber.<simid>.out rows at 0, 50, 100 with the running mean of prn_skyno
+    e.set_moments(emom, mmom)
+    sim.run()
+    rows = asdio.read_out(os.path.join(str(tmp_path), 'sknumber.skyrm_2D.out'))
+    assert [int(x[0]) for x in rows] == [0, 50, 100]
+    assert abs(rows[0][1] - qref) <= 1e-8                      # printed with f16.8; NA = 1
+    assert abs(rows[2][2] - np.mean([x[1] for x in rows])) <= 2e-8
+    pr = [x for x in asdio.read_out(os.path.join(str(tmp_path), 'projavgs.skyrm_2D.out')) if int(x[0]) == 0]
+    av = _first_averages(str(tmp_path))
+    assert len(pr) == 1 and abs(pr[0][2] - av[4]) <= 1e-8 and abs(pr[0][6] - av[3]) <= 1e-8
+
+
+def _first_averages(d):
+    from uppasd_b200 import asdio
+    return asdio.read_out(os.path.join(d, 'averages.skyrm_2D.out'))[0]

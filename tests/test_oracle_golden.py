@@ -176,3 +176,86 @@ def test_kagome_tensor_exchange_depondt():
         assert _similar(a, b), (a, b)
     for a, b in zip(r['cumulants'][171], exp['cumulants']['171']):
         assert _similar(a, b), (a, b)
+
+
+def _t0_run(S, inp, marks):
+    """T = 0 measurement phase from the current S: {iteration: (averages row, energy terms)} at the marked iterations"""
+    N = S['Natom']
+    st = orc.SdState(S, inp['sdealgh'], inp['timestep'], inp['damping'])
+    out = {}
+    for it in range(max(marks) + 1):
+        if it in marks:
+            m = st.sum_moments()[:, 0] / N
+            out[it] = (list(m) + [float(np.sqrt((m ** 2).sum()))], orc.energy_terms(S, st.emomM)[:, 0], st.emomM.copy(order='F'))
+        st.step()
+    return out
+
+
+def test_cluster_biquadratic_type7_anisotropy_depondt():
+    """tests/Cluster (regulartests.yaml:182-205, tol 1e-8): finite 43-atom cluster, Heisenberg + BIQUADRATIC exchange +
+    anisotropy type 7 (uniaxial into beff_s, cubic x ratio into beff_q), random start, Depondt through two T = 0 initial
+    phases (1000 steps dt 2e-16 damping 0.1, 4000 steps dt 1e-16 damping 0.01) and 25000 undamped steps.  Averages @25000
+    and the energy columns Tot / Exc / Ani / BQ @15000 come out digit for digit: pins biquadratic_field, the type-7 split,
+    the bq mount (lexp 2), Depondt, and calc_energy's factors (1/2, 1/4)."""
+    fx, inp, S = load_golden('cluster')
+    assert S['Natom'] == 43 and S['bq']['z'] == 12 and set(S['aniso']['taniso']) == {7}
+    orc.initmag1(S, inp['tseed'])
+    cur = S
+    for ph in fx['ip_phases']:
+        st = orc.SdState(cur, 5, ph['timestep'], ph['damping'])
+        for _ in range(ph['nstep']):
+            st.step()
+        cur = dict(cur, emom=st.emom.copy(order='F'), emomM=st.emomM.copy(order='F'), mmom=st.mmom.copy(order='F'))
+    r = _t0_run(cur, inp, {15000, 25000})
+    exp = fx['expected']
+    for a, b in zip(r[25000][0], exp['averages']['25000']):
+        assert _similar(a, b), (a, b)
+    t = r[15000][1]
+    e = exp['totenergy']['15000']
+    for a, b in ((t.sum(), e['tot']), (t[0], e['exc']), (t[1], e['ani']), (t[3], e['bq'])):
+        assert _similar(a, b), (a, b)
+
+
+def test_heisstripe_uniaxial_anisotropy():
+    """tests/HeisStripe (regulartests.yaml:105-129, tol 1e-8): 10 x 1 x 100 stripe with open edges, uniaxial anisotropy,
+    random start, midpoint at T = 0: averages @1190, energy columns Tot / Exc / Ani @1460 digit for digit."""
+    fx, inp, S = load_golden('heisstripe')
+    assert S['Natom'] == 1000 and set(S['aniso']['taniso']) == {1}
+    orc.initmag1(S, inp['tseed'])
+    r = _t0_run(S, inp, {1190, 1460})
+    exp = fx['expected']
+    for a, b in zip(r[1190][0], exp['averages']['1190']):
+        assert _similar(a, b), (a, b)
+    t, e = r[1460][1], exp['totenergy']['1460']
+    for a, b in ((t.sum(), e['tot']), (t[0], e['exc']), (t[1], e['ani'])):
+        assert _similar(a, b), (a, b)
+
+
+def test_heischainaf_sublattice_projections():
+    """tests/HeisChainAF (regulartests.yaml:54-103, tol 1e-8): antiferromagnetic chain with two atom types: averages @1000,
+    total energy @1500 and the type-projected averages (prn_averages.f90 projavgs: |<m>_type|, <m>_type) @5000."""
+    fx, inp, S = load_golden('heischainaf')
+    orc.initmag1(S, inp['tseed'])
+    r = _t0_run(S, inp, {1000, 1500, 5000})
+    exp = fx['expected']
+    for a, b in zip(r[1000][0], exp['averages']['1000']):
+        assert _similar(a, b), (a, b)
+    assert _similar(r[1500][1].sum(), exp['totenergy']['1500']['tot'])
+    emomM = r[5000][2]
+    for ty in (1, 2):
+        sel = S['atype'] == ty
+        m = emomM[:, sel, 0].sum(axis=1) / sel.sum()
+        got = [float(np.sqrt((m ** 2).sum()))] + list(m)
+        for a, b in zip(got, exp['projavgs']['5000'][str(ty)]):
+            assert _similar(a, b), (ty, a, b)
+
+
+def test_scsurf_dm_anisotropy_atomic_units():
+    """tests/SCsurf (regulartests.yaml:158-170, tol 1e-8): 16 x 16 monolayer, Heisenberg + DM + uniaxial anisotropy with
+    aunits Y (change_constants: gamma = k_B = mu_B = mRy = 1), maptype 2, random start, midpoint with dt 0.01."""
+    fx, inp, S = load_golden('scsurf')
+    assert inp['aunits'] == 'Y' and S['const']['gama'] == 1.0 and S['dm']['z'] == 4
+    orc.initmag1(S, inp['tseed'])
+    r = _t0_run(S, inp, {800})
+    for a, b in zip(r[800][0], fx['expected']['averages']['800']):
+        assert _similar(a, b), (a, b)

@@ -40,6 +40,9 @@ SYMBOLS = {
     'asd_set_system': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp]),
     'asd_set_exchange': (C.c_int, [vp, C.c_int, vp, vp, vp]),
     'asd_set_jtensor': (C.c_int, [vp, C.c_int, vp, vp, vp]),
+    'asd_measure_sublattice': (C.c_int, [vp, C.c_int, vp]),
+    'asd_set_triangulation': (C.c_int, [vp, C.c_int, vp]),
+    'asd_skyrmion_number': (C.c_int, [vp, vp]),
     'asd_set_dm': (C.c_int, [vp, C.c_int, vp, vp, vp]),
     'asd_set_bq': (C.c_int, [vp, C.c_int, vp, vp, vp]),
     'asd_set_lattice_hint': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]),

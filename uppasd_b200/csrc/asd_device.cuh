@@ -1132,6 +1132,53 @@ __global__ void gather_atoms_kernel(int n, int M, size_t Npad, const int* __rest
    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.m;
 }
 
+// Sublattice-projected moment sums (buffer_proj_avrg, prn_averages.f90:462-512): the partial sums of moment_partial_kernel
+// restricted to the atoms whose basis number mod(i-1, NA) equals cls; same fixed-shape tree, same final kernel.
+__global__ void __launch_bounds__(256)
+moment_class_partial_kernel(int Npad, const int* __restrict__ orig, const SpinVec* __restrict__ cur, int NA, int cls,
+                            double* __restrict__ part /*[M][gridDim.x][4]*/) {
+   __shared__ double red[4][8];
+   const int k = blockIdx.y;
+   double s[4] = {0, 0, 0, 0};
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Npad; i += gridDim.x * blockDim.x) {
+      const int o = __ldg(orig + i);
+      if (o < 0 || o % NA != cls) continue;
+      const SpinVec v = cur[(size_t)k * Npad + i];
+      s[0] += v.x * v.m; s[1] += v.y * v.m; s[2] += v.z * v.m;
+   }
+   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+   for (int a = 0; a < 4; a++) { s[a] = warp_sum(s[a]); if (l == 0) red[a][w] = s[a]; }
+   __syncthreads();
+   if (w == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+         double v = (l < 8) ? red[a][l] : 0.0;
+         v = warp_sum(v);
+         if (l == 0) part[((size_t)k * gridDim.x + blockIdx.x) * 4 + a] = v;
+      }
+   }
+}
+
+// Solid angle of every triangle of a triangulated lattice (pontryagin_tri, source/Measurement/topology.f90:78-116):
+// q = 2 atan( m1 . (m2 x m3) / (1 + m1.m2 + m1.m3 + m2.m3) ) with the UNIT moments of the three corners;
+// rows[k][t] = q of triangle t in ensemble k (summed by the reduce_rows kernels).  tri[c][t] = slot of corner c.
+__global__ void __launch_bounds__(256)
+skyrmion_tri_kernel(int nsimp, size_t Npad, const int* __restrict__ tri, const SpinVec* __restrict__ cur, double* __restrict__ rows) {
+   const int t = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+   if (t >= nsimp) return;
+   const SpinVec* __restrict__ S = cur + (size_t)k * Npad;
+   const SpinVec a = S[__ldg(tri + t)], b = S[__ldg(tri + nsimp + t)], c = S[__ldg(tri + 2 * (size_t)nsimp + t)];
+   // f_volume(m1, m2, m3) = (m1 x m2) . m3 (math_functions.f90:59-73)
+   const double cx = a.y * b.z - a.z * b.y, cy = a.z * b.x - a.x * b.z, cz = a.x * b.y - a.y * b.x;
+   const double vol = c.x * cx + c.y * cy + c.z * cz;
+   const double ab = a.x * b.x + a.y * b.y + a.z * b.z;
+   const double ac = a.x * c.x + a.y * c.y + a.z * c.z;
+   const double bc = b.x * c.x + b.y * c.y + b.z * c.z;
+   const double qq = vol / (1.0 + ab + ac + bc);
+   rows[(size_t)k * nsimp + t] = 2.0 * atan(qq);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Layout conversion between the host's Fortran arrays and the packed device order.
 // ------------------------------------------------------------------------------------------------

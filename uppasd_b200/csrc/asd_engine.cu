@@ -189,6 +189,11 @@ struct asd_engine {
    DevBuf<unsigned char> lat_col;       // [Nown] colour of every owned slot (periodic colouring, mc_tile_kernel)
    int lat_ncol = 0, lat_period[3] = {1, 1, 1};
    int mc_layout = -1;                  // -1: default (env ASD_MC_TILES), 0 colour-major, 1 lattice tiles
+   // triangulation for the skyrmion number (asd_set_triangulation): corners as 0-based ORIGINAL atom indices on the host,
+   // as slots of one layout on the device (rebuilt when the state moves to the other layout)
+   std::vector<int> simp;
+   int nsimp = 0, tri_layout = 0;
+   DevBuf<int> d_tri;
 };
 
 static void launch_cfg(int Npad, int M, dim3& grid, dim3& block) {
@@ -1497,6 +1502,79 @@ int asd_energy_terms(asd_engine* e, double* terms) {
    CU(cudaStreamSynchronize(e->stream));
    const double fcinv = e->mub / e->mry;   // energy.f90: energies printed in mRy per atom
    for (size_t q = 0; q < h.size(); q++) terms[q] = h[q] * fcinv / e->N;
+   return 0;
+}
+
+int asd_measure_sublattice(asd_engine* e, int NA, double* msum_na) {
+   CU(cudaSetDevice(e->device));
+   if (NA < 1 || e->N % NA) return fail(-1, "asd_measure_sublattice: NA = %d does not divide Natom", NA);
+   if (e->slab.on) return fail(-11, "asd_measure_sublattice: not available on a slab (sum the slabs' asd_get_moments instead)");
+   int r = ensure_layout(e, e->state_layout == 2 ? 2 : 1);
+   if (r) return r;
+   Layout& L = (e->state_layout == 2) ? e->mc : e->sd;
+   const int nblk = std::min(1184, (L.Npad + 255) / 256);
+   DevBuf<double> out;
+   if ((r = e->part.alloc((size_t)e->M * nblk * 4))) return r;
+   if ((r = out.alloc((size_t)NA * e->M * 4))) return r;
+   for (int c = 0; c < NA; c++) {
+      moment_class_partial_kernel<<<dim3(nblk, e->M), 256, 0, e->stream>>>(L.Npad, L.d_orig.p, e->cur.p, NA, c, e->part.p);
+      moment_final_kernel<<<e->M, 1024, 0, e->stream>>>(nblk, e->part.p, out.p + (size_t)c * e->M * 4);
+      e->launches += 2;
+   }
+   CU(cudaGetLastError());
+   std::vector<double> h((size_t)NA * e->M * 4);
+   CU(cudaMemcpyAsync(h.data(), out.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   CU(cudaStreamSynchronize(e->stream));
+   for (int k = 0; k < e->M; k++)
+      for (int c = 0; c < NA; c++)
+         for (int a = 0; a < 3; a++) msum_na[a + 3 * (c + (size_t)NA * k)] = h[((size_t)c * e->M + k) * 4 + a];
+   return 0;
+}
+
+int asd_set_triangulation(asd_engine* e, int nsimp, const int* simp) {
+   if (e->N == 0) return fail(-2, "asd_set_system must be called first");
+   if (nsimp < 0) return fail(-1, "asd_set_triangulation: nsimp < 0");
+   e->simp.resize((size_t)3 * nsimp);
+   for (size_t q = 0; q < (size_t)3 * nsimp; q++) {
+      if (simp[q] < 1 || simp[q] > e->N) return fail(-1, "asd_set_triangulation: atom %d outside 1..Natom", simp[q]);
+      e->simp[q] = simp[q] - 1;
+   }
+   e->nsimp = nsimp; e->tri_layout = 0;
+   return 0;
+}
+
+int asd_skyrmion_number(asd_engine* e, double* q) {
+   CU(cudaSetDevice(e->device));
+   if (e->nsimp <= 0) return fail(-2, "asd_skyrmion_number: asd_set_triangulation first");
+   if (e->slab.on) return fail(-11, "asd_skyrmion_number: not available on a slab");
+   int r = ensure_layout(e, e->state_layout == 2 ? 2 : 1);
+   if (r) return r;
+   const int lay = (e->state_layout == 2) ? 2 : 1;
+   Layout& L = (lay == 2) ? e->mc : e->sd;
+   const int ns = e->nsimp;
+   if (e->tri_layout != lay) {
+      if ((r = host_orig(e, L))) return r;
+      std::vector<int> tri((size_t)3 * ns);
+      for (int t = 0; t < ns; t++)
+         for (int c = 0; c < 3; c++) tri[(size_t)c * ns + t] = L.slot_of[e->simp[(size_t)3 * t + c]];   // simp(3, nsimp)
+      if ((r = e->d_tri.upload(tri, e->stream))) return r;
+      e->tri_layout = lay;
+   }
+   const int nblk = std::min(592, (ns + 255) / 256);
+   DevBuf<double> rows, part, out;
+   if ((r = rows.alloc((size_t)e->M * ns))) return r;
+   if ((r = part.alloc((size_t)e->M * nblk))) return r;
+   if ((r = out.alloc((size_t)e->M))) return r;
+   skyrmion_tri_kernel<<<dim3((ns + 255) / 256, e->M), 256, 0, e->stream>>>(ns, (size_t)L.Npad, e->d_tri.p, e->cur.p, rows.p);
+   reduce_rows_partial_kernel<<<dim3(nblk, 1, e->M), 256, 0, e->stream>>>(ns, 1, rows.p, part.p);
+   reduce_rows_final_kernel<<<e->M, 256, 0, e->stream>>>(nblk, part.p, out.p);
+   e->launches += 3;
+   CU(cudaGetLastError());
+   std::vector<double> h((size_t)e->M);
+   CU(cudaMemcpyAsync(h.data(), out.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   CU(cudaStreamSynchronize(e->stream));
+   const double four_pi = 4.0 * 3.14159265358979323846;
+   for (int k = 0; k < e->M; k++) q[k] = h[k] / four_pi;
    return 0;
 }
 

@@ -15,7 +15,7 @@ import os
 
 import numpy as np
 
-from . import asdio, host, lattice, observables
+from . import asdio, host, lattice, observables, refrng
 
 # source/Parameters/constants.f90:14-29
 CONSTANTS = dict(gama=1.760859644e11, k_bolt=1.38064852e-23, mub=9.274009994e-24, mry=2.179872325e-21)
@@ -73,7 +73,7 @@ class Simulation:
             if not inp.get(key):
                 continue
             nn, red, xc, nntype = asdio.read_pairfile(inp[key], atype_inp, bas, cell, inp['maptype'], inp['posfiletype'], ncomp)
-            ns, ca, cs, sh = lattice.stencil(cell, bas, atype_inp, nn, red, sym, nntype if typed else None)
+            ns, ca, cs, sh = lattice.stencil(cell, bas, atype_inp, nn, red, sym, nntype if typed else None, ncell=(n1, n2, n3))
             cp = lattice.couplings(ns, ca, sh, atype_inp, xc, ammom, c['mry'], c['mub'], lexp)
             e.build_lattice_table(kind, na, (n1, n2, n3), inp['bc'], ns, ca, cs, cp)
         if inp.get('anisotropy'):
@@ -99,14 +99,20 @@ class Simulation:
         elif inp['initmag'] == 4:
             self.rstep, emom, mmom = asdio.read_restart(inp['restartfile'], natom, mens)
         elif inp['initmag'] == 1:
-            # random start: the reference draws it from its own Mersenne-Twister variant (mtprng.f90); here a counter-based
-            # generator -- an equivalent ensemble, not the same numbers
-            g = np.random.Generator(np.random.Philox(self.seed)).normal(size=(3, natom, mens))
-            emom = np.asfortranarray(g / np.sqrt((g ** 2).sum(axis=0)))
+            # random start: drawn on the host, once, from the reference's own generator seeded with tseed -- the same numbers
+            # as the reference, so its Initmag 1 goldens apply to this path unchanged
+            e1 = refrng.random_start(na, (n1, n2, n3), inp['tseed'])
+            emom = np.asfortranarray(np.repeat(e1[:, :, None], mens, axis=2))
         else:
             raise Unsupported('initmag %d' % inp['initmag'])
         self.mmom0 = mmom.copy(order='F')
         e.set_moments(emom, mmom, self.mmom0)
+        self.atype_cell = atype_inp
+        if inp['skyno'] == 'T':
+            e.set_triangulation(lattice.triangulation(n1, n2, n3, na))          # uppasd.f90:1284-1286
+        elif inp['skyno'] == 'Y':
+            import warnings
+            warnings.warn('skyno Y (finite-difference Pontryagin density) is not on this path; use skyno T (triangulation)')
 
     def _set_field(self, h):
         f = np.zeros((3, self.natom, self.mens), order='F')
@@ -147,10 +153,18 @@ class Simulation:
         msum = None
         if inp['do_avrg'] == 'Y' and (mstep - 1) % inp['avrg_step'] == 0:
             msum = e.measure()
+            if inp['do_proj_avrg'] in ('Y', 'A'):
+                self.proj_rows += observables.projected_rows(mstep - 1, e.measure_sublattice(self.na), self.natom // self.na,
+                                                             self.atype_cell, inp['do_proj_avrg'])
             rows = self.avg.sample(mstep - 1, msum)
             if rows:
                 self.out.averages(rows)
+                self._flush_proj()
                 self._write_restart(mstep, mode)
+        if inp['skyno'] == 'T' and (mstep - 1) % inp['skyno_step'] == 0:
+            self.sky_rows.append(self.sky.sample(mstep - 1, e.skyrmion_number()))
+            if len(self.sky_rows) == inp['skyno_buff']:
+                self._flush_sky()
         for t, (atom, tstep, tbuff) in enumerate(inp['trajectories']):
             if (mstep - 1) % tstep == 0:
                 v = e.get_atoms([atom])                    # (4, 1, M)
@@ -171,6 +185,16 @@ class Simulation:
         self.last_energy, self.last_exc = tot, t[0]
         self.out.totenergy(mstep - 1, dict(tot=tot.mean(), exc=t[0].mean(), ani=t[1].mean(), dm=t[2].mean(), bq=t[3].mean(),
                                            ext=t[4].mean()))
+
+    def _flush_proj(self):
+        if self.proj_rows:
+            self.out.projavgs(self.proj_rows)
+            self.proj_rows = []
+
+    def _flush_sky(self):
+        if self.sky_rows:
+            self.out.sknumber(self.sky_rows)
+            self.sky_rows = []
 
     def _flush_traj(self, t):
         atom = self.inp['trajectories'][t][0]
@@ -193,6 +217,8 @@ class Simulation:
             periods.append((inp['avrg_step'], 1))          # (m - 1) % p == 0
         for _, tstep, _ in inp['trajectories']:
             periods.append((tstep, 1))
+        if inp['skyno'] == 'T':
+            periods.append((inp['skyno_step'], 1))
         if inp['do_cumu'] == 'Y':
             periods.append((inp['cumu_step'], 0))          # m % p == 0
         for p, off in periods:
@@ -207,6 +233,7 @@ class Simulation:
         self.cum = observables.Cumulants(self.natom, self.mens, inp['temp'], self.c['k_bolt'], self.c['mub'], self.c['mry'],
                                          inp['cumu_buff'], inp['plotenergy'])
         self.traj = [[[] for _ in range(self.mens)] for _ in inp['trajectories']]
+        self.proj_rows, self.sky_rows, self.sky = [], [], observables.SkyrmionNumber(self.na)
         self.last_energy = self.last_exc = None
         off = getattr(self, '_noise_offset', 1) - 1            # keeps the noise counters of the two phases apart
         if mode == 'S':
@@ -232,6 +259,8 @@ class Simulation:
         rows = self.avg.flush()
         if rows:
             self.out.averages(rows)
+        self._flush_proj()
+        self._flush_sky()
         for t in range(len(self.traj)):
             self._flush_traj(t)
         self._write_restart(mstep, mode)

@@ -166,6 +166,23 @@ class Engine:
         self._chk(self.lib.asd_energy_terms(self.h, _p(out)))
         return out
 
+    def measure_sublattice(self, na):
+        """(3, NA, M): sums of emomM per basis atom (buffer_proj_avrg)"""
+        out = np.zeros((3, na, self.M), order='F')
+        self._chk(self.lib.asd_measure_sublattice(self.h, na, _p(out)))
+        return out
+
+    def set_triangulation(self, simp):
+        """simp(3, nsimp): 1-based corner atoms of the triangles (delaunay_tri_tri)"""
+        simp = np.asfortranarray(simp, dtype=np.int32)
+        self._chk(self.lib.asd_set_triangulation(self.h, simp.shape[1], _p(simp)))
+
+    def skyrmion_number(self):
+        """per ensemble: sum of the triangles' solid angles / 4 pi (pontryagin_tri before the ensemble mean)"""
+        q = np.zeros(self.M)
+        self._chk(self.lib.asd_skyrmion_number(self.h, _p(q)))
+        return q
+
     def get_atoms(self, atoms):
         """(4, n, M): ex, ey, ez, |m| of the 1-based atoms"""
         a = np.ascontiguousarray(atoms, dtype=np.int32)

@@ -97,12 +97,15 @@ def fold_basis(cell, bas):
     return bas
 
 
-def stencil(cell, bas, atype, nn, redcoord, sym, nntype=None):
+def stencil(cell, bas, atype, nn, redcoord, sym, nntype=None, ncell=None):
     """Returns nslot[NA], cell_atom[NA][maxslot] (1-based), cell_shift[NA][maxslot][3], shell_of[NA][maxslot].
 
     cell: 3x3 (rows C1,C2,C3); bas: (3,NA) folded basis; atype[NA] 1-based types; nn[NT] shells per type;
     redcoord[NT][maxshell][3]; nntype[NT][maxshell] (type the shell connects to) or None.
     Entry order = shell-major, then image order, then basis atom order (neighbourmap.f90:170-241).
+    ncell = (N1, N2, N3): a SINGLE cell (N1*N2*N3 <= 1, e.g. a finite cluster given as one big cell) keeps no cell shifts at
+    all -- nm_trunk is only filled for more than one cell and the hop is forced to zero (neighbourmap.f90:226-230,
+    270-296) -- so a neighbour found through a folded basis position is kept whatever the boundary condition says.
     """
     cell = np.asarray(cell, dtype=float)
     det = np.linalg.det(cell)
@@ -137,6 +140,8 @@ def stencil(cell, bas, atype, nn, redcoord, sym, nntype=None):
                         continue
                     if ((r - bas[:, ia]) ** 2).sum() < TOL:
                         entries[i0].append((ia + 1, int(round(bsf[0])), int(round(bsf[1])), int(round(bsf[2])), ish))
+    if ncell is not None and int(ncell[0]) * int(ncell[1]) * int(ncell[2]) <= 1:
+        entries = [[(ja, 0, 0, 0, ish) for (ja, dx, dy, dz, ish) in x] for x in entries]
     maxslot = max(1, max(len(x) for x in entries))
     nslot = np.array([len(x) for x in entries], dtype=np.int32)
     cell_atom = np.ones((na, maxslot), dtype=np.int32)
@@ -169,3 +174,19 @@ def couplings(nslot, cell_atom, shell_of, atype, xc, ammom, mry, mub, lexp=1):
             for a in range(ncomp):
                 out[i0, q, a] = xc[a, atype[i0] - 1, shell_of[i0, q]] * fc2 / pi_ / pj_
     return out
+
+
+def triangulation(n1, n2, n3, na):
+    """The hard-coded triangulation of an a-priori triangular net (delaunay_tri_tri, source/Measurement/topology.f90:307-380):
+    per cell (x, y, z) and basis atom two triangles, first all [0, +x, +y] then all [0, +y, +y - x], periodic in x and y.
+    Returns simp(3, 2 * n1 * n2 * n3 * na), 1-based atom numbers in the reference's atom order."""
+    z, y, x, it = np.meshgrid(np.arange(n3), np.arange(n2), np.arange(n1), np.arange(na), indexing='ij')
+    z, y, x, it = z.ravel(), y.ravel(), x.ravel(), it.ravel()
+
+    def atom(xx, yy):
+        return na * (n1 * n2 * z + n1 * yy + xx) + it + 1
+
+    xp, yp, xm = (x + 1) % n1, (y + 1) % n2, (x - 1) % n1
+    first = np.stack([atom(x, y), atom(xp, y), atom(x, yp)])
+    second = np.stack([atom(x, y), atom(x, yp), atom(xm, yp)])
+    return np.asfortranarray(np.concatenate([first, second], axis=1), dtype=np.int32)

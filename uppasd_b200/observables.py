@@ -5,6 +5,8 @@
   cumulants  calc_and_print_cumulant     source/Measurement/prn_averages.f90:919-1095 -- WEIGHTED running means with a
              linearly growing weight (cumuw += 1 per sample per ensemble), U = 1 - <m^4>/(3 <m^2>^2),
              chi = (<m^2> - <m>^2) mu_B^2 N / (k_B^2 T), C_v from the energy variance in mRy
+  projavgs   buffer_proj_avrg / prn_proj_avrg  source/Measurement/prn_averages.f90:462-512, 662-802
+  sknumber   buffer_skyno_tri / prn_skyno      source/Measurement/prn_topology.f90:660-700, 296-345
 """
 import numpy as np
 
@@ -80,3 +82,44 @@ class Cumulants:
         if (count - 1) % self.buff == 0:
             return (count, self.avm, self.avm2, self.avm4, self.binder, self.chi, self.cv, self.ave, self.avexc, 0.0)
         return None
+
+
+def projected_rows(it, msum_na, ncells, atype_cell, mode='Y'):
+    """Rows of projavgs.<simid>.out for one sample: msum_na(3, NA, M) = sums of emomM per basis atom.  mode 'Y': one row per
+    atom TYPE, the sums of the basis atoms of that type divided by the number of CELLS (not by the number of atoms of the
+    type -- prn_averages.f90:713-722); mode 'A': one row per basis atom.  Row = (iter, proj, <M>, M_stdv, <M>_x, <M>_y, <M>_z)."""
+    msum_na = np.asarray(msum_na, dtype=np.float64)
+    na, mens = msum_na.shape[1], msum_na.shape[2]
+    atype_cell = np.asarray(atype_cell)
+    if mode == 'Y':
+        nproj = int(atype_cell.max())
+        v = np.zeros((3, nproj, mens))
+        for i_na in range(na):
+            v[:, atype_cell[i_na] - 1, :] += msum_na[:, i_na, :] / ncells
+    else:
+        nproj = na
+        v = msum_na / ncells
+    rows = []
+    for k in range(nproj):
+        m = np.sqrt((v[:, k, :] ** 2).sum(axis=0))             # per ensemble
+        mm = m.mean()
+        var = (m ** 2).mean() - mm ** 2
+        rows.append((it, k + 1, mm, 0.0 if var < 0 else float(np.sqrt(var)), v[0, k].mean(), v[1, k].mean(), v[2, k].mean()))
+    return rows
+
+
+class SkyrmionNumber:
+    """Running mean / variance of the skyrmion number as prn_skyno accumulates them (Welford update, prn_topology.f90:321-327)."""
+
+    def __init__(self, na):
+        self.na, self.count, self.avg, self.var = na, 0, 0.0, 0.0
+
+    def sample(self, it, q):
+        """q: per-ensemble sums of solid angles / 4 pi (asd_skyrmion_number); the printed number is their ensemble mean / NA
+        (pontryagin_tri divides by Mensemble, buffer_skyno_tri by NA).  Returns the row (iter, Skx num, Skx avg, Skx std)."""
+        x = float(np.mean(q)) / self.na
+        self.count += 1
+        prev = self.avg
+        self.avg = prev + (x - prev) / self.count
+        self.var += (x - prev) * (x - self.avg)
+        return (it, x, self.avg, self.var / self.count)
