@@ -38,7 +38,11 @@ def test_field_parity(name):
 
 @pytest.mark.parametrize('name', FIX)
 @pytest.mark.parametrize('alg', [1, 5])
-def test_t0_trajectory(name, alg):
+@pytest.mark.parametrize('resident', ['1', '0'])
+def test_t0_trajectory(name, alg, resident, monkeypatch):
+    """resident 1: the whole time loop in one launch with the state in shared memory (llg_resident_kernel, the default for
+    systems this small); resident 0: the two stage launches per step that large systems use."""
+    monkeypatch.setenv('ASD_RESIDENT', resident)
     fx, inp, S = load_golden(name)
     if inp['initmag'] == 1:
         orc.initmag1(S, inp['tseed'])
@@ -413,3 +417,32 @@ def test_more_reference_goldens_on_gpu(name):
         got = {'tot': t.sum(), 'exc': t[0], 'ani': t[1], 'dm': t[2], 'bq': t[3]}
         for key, b in v.items():
             assert abs(got[key] - b) <= 1e-8, (name, k, key, got[key], b)
+
+
+@pytest.mark.parametrize('alg', [1, 5])
+def test_resident_kernel_is_bit_identical_to_the_stage_launches(alg, monkeypatch):
+    """Thermal run (300 K, 3 ensembles, DM + anisotropy, external field) of the kagome fixture: one resident launch for 200
+    steps, the same 200 steps in uneven batches, and the two-launch-per-step path give the same bits (same summation order,
+    same noise counters), and the launch counts differ as designed."""
+    fx, inp, S0 = load_golden('kagome')
+    from uppasd_b200 import host
+    S = dict(S0, Mensemble=3)
+    for k in ('emom', 'emomM', 'external_field'):
+        S[k] = np.asfortranarray(np.repeat(S0[k], 3, axis=2))
+    for k in ('mmom', 'mmom0', 'mmomi'):
+        S[k] = np.asfortranarray(np.repeat(S0[k], 3, axis=1))
+    S['external_field'][1] += 3.0
+    out = {}
+    for tag, res, batches in (('resident', '1', (200,)), ('batched', '1', (1, 7, 192)), ('stages', '0', (200,))):
+        monkeypatch.setenv('ASD_RESIDENT', res)
+        e = host.engine_from_system(S, orc.CONST, sdealgh=alg, delta_t=inp['timestep'], damping=0.2, temp=300.0, seed=5)
+        n0, done = e.launch_count(), 0
+        for n in batches:
+            e.sd_steps(n, first_step=done + 1)
+            done += n
+        out[tag] = (e.get_moments()[0].copy(), e.launch_count() - n0)
+    assert np.array_equal(out['resident'][0], out['batched'][0])
+    assert np.array_equal(out['resident'][0], out['stages'][0])
+    # launch counts (get_moments adds a few conversion launches to each): 1 / 3 resident launches against 400 stage launches
+    assert out['batched'][1] - out['resident'][1] == 2 and out['stages'][1] - out['resident'][1] == 399, {k: v[1] for k, v in out.items()}
+    assert np.abs(out['resident'][0] - S['emom']).max() > 1e-3

@@ -18,6 +18,7 @@
 //   moment update     source/Evolution/updatemoments.f90:48-145
 //   noise amplitude   source/RNG/randomnumbers.f90:667-670,735-746 (midpoint), depondt.f90:143-145
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -406,7 +407,25 @@ __device__ __forceinline__ unsigned pos16(const uint4* __restrict__ tab, size_t 
 // s3: the CTA's shared-memory copy of emomM of the tile's gather list (staged kernels), or null.  With s3 and the
 // 16-bit position tables dm16 / bq16 the DM and BQ neighbours are read from shared memory too.
 // XS (compile time: a kernel without DM / BQ work must not carry this code, it costs the plain Heisenberg kernel 15 %).
-template <bool REDUCED, bool EXCH = true, int CH = ASD_CHUNK, bool XS = false>
+// one neighbour of the DM sum (hamiltonianactions.f90:566-571) and of the biquadratic sum (:791-794); shared by every
+// kernel that walks these lists so that the arithmetic is the same instruction sequence everywhere
+__device__ __forceinline__ void dm_term(double Dx, double Dy, double Dz, double mx, double my, double mz, double& fx, double& fy,
+                                        double& fz) {
+   fx = fx + Dz * my - Dy * mz;
+   fy = fy + Dx * mz - Dz * mx;
+   fz = fz + Dy * mx - Dx * my;
+}
+__device__ __forceinline__ void bq_term(double jb, double mx, double my, double mz, double ox, double oy, double oz, double& qx,
+                                        double& qy, double& qz) {
+   const double dot = mx * ox + my * oy + mz * oz;
+   const double c = 2.0 * jb * dot;
+   qx = fma(c, mx, qx);
+   qy = fma(c, my, qy);
+   qz = fma(c, mz, qz);
+}
+
+// PAIRS = false: every pair sum (Heisenberg, DM, BQ) was accumulated by the caller into bs[] / bq[] (resident kernel).
+template <bool REDUCED, bool EXCH = true, int CH = ASD_CHUNK, bool XS = false, bool PAIRS = true>
 __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __restrict__ S, int i, int ih,
                                            const SpinVec& own, const double* smc, const double* smd,
                                            const double* smb, double bs[3], double bq[3], const double* __restrict__ s3 = nullptr) {
@@ -463,7 +482,7 @@ __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __res
       }
    }
    // ---- Dzyaloshinskii-Moriya (hamiltonianactions.f90:565-571) ----
-   if (t.zdm > 0) {
+   if (PAIRS && t.zdm > 0) {
       const int* __restrict__ nl = t.dml + i;
       const int n = REDUCED ? __ldg(t.dmsize + ih) : t.zdm;
       const bool smem_dm = XS && t.dm16 != nullptr;
@@ -487,15 +506,13 @@ __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __res
             const SpinVec v = S[__ldg(nl + (size_t)j * Npad)];
             mx = v.x * v.m; my = v.y * v.m; mz = v.z * v.m;
          }
-         fx = fx + Dz * my - Dy * mz;
-         fy = fy + Dx * mz - Dz * mx;
-         fz = fz + Dy * mx - Dx * my;
+         dm_term(Dx, Dy, Dz, mx, my, mz, fx, fy, fz);
       }
    }
-   double qx = 0.0, qy = 0.0, qz = 0.0;
+   double qx = PAIRS ? 0.0 : bq[0], qy = PAIRS ? 0.0 : bq[1], qz = PAIRS ? 0.0 : bq[2];
    const double ox = own.x * own.m, oy = own.y * own.m, oz = own.z * own.m;  // emomM of this site
    // ---- biquadratic (hamiltonianactions.f90:790-795) ----
-   if (t.zbq > 0) {
+   if (PAIRS && t.zbq > 0) {
       const int* __restrict__ nl = t.bql + i;
       const int n = REDUCED ? __ldg(t.bqsize + ih) : t.zbq;
       const bool smem_bq = XS && t.bq16 != nullptr;
@@ -509,11 +526,7 @@ __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __res
             const SpinVec v = S[__ldg(nl + (size_t)j * Npad)];
             mx = v.x * v.m; my = v.y * v.m; mz = v.z * v.m;
          }
-         const double dot = mx * ox + my * oy + mz * oz;
-         const double c = 2.0 * jb * dot;
-         qx = fma(c, mx, qx);
-         qy = fma(c, my, qy);
-         qz = fma(c, mz, qz);
+         bq_term(jb, mx, my, mz, ox, oy, oz, qx, qy, qz);
       }
    }
    // ---- single-ion anisotropy (hamiltonianactions.f90:225-239, 842-919); uses the FULL moment ----
@@ -682,7 +695,9 @@ __global__ void halo_push_kernel(int Nown, int M, size_t Npad, const SpinVec* __
 template <int SOLVER, int STAGE>
 __device__ __forceinline__ SpinVec integrate_site(const Tables& t, const LlgParams& p, int i, int k, int io, const double b[3],
                                                   const SpinVec& own, const SpinVec& c0, double* __restrict__ b2eff,
-                                                  const float* gpre = nullptr) {
+                                                  const float* gpre = nullptr, unsigned long long step_arg = ~0ull) {
+   // step_arg: the noise key of a kernel that advances the step itself (llg_resident_kernel); default: p.step
+   const unsigned long long nstep = (step_arg != ~0ull) ? step_arg : p.step;
    double lam, lg, temp;
    if (p.per_site) { lam = __ldg(p.lambda_a + i); lg = __ldg(p.landeg_a + i); temp = __ldg(p.temp_a + i); }
    else { lam = p.lambda; lg = p.landeg; temp = p.temp; }
@@ -690,7 +705,7 @@ __device__ __forceinline__ SpinVec integrate_site(const Tables& t, const LlgPara
    const double m = c0.m;
    double g[3] = {0.0, 0.0, 0.0};
    if (gpre) { g[0] = (double)gpre[0]; g[1] = (double)gpre[1]; g[2] = (double)gpre[2]; }
-   else if (p.thermal) gauss3f(p.seed, (uint32_t)io + t.atom_offset, (uint32_t)k + t.ens_offset, p.step, 0u, g[0], g[1], g[2]);
+   else if (p.thermal) gauss3f(p.seed, (uint32_t)io + t.atom_offset, (uint32_t)k + t.ens_offset, nstep, 0u, g[0], g[1], g[2]);
    double bt[3] = {0.0, 0.0, 0.0};
    if (t.btorque) {
       const double* __restrict__ q = t.btorque + (size_t)k * 3 * t.Npad + i;
@@ -889,6 +904,152 @@ llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPa
             if (ep.flag_hi) st_release_sys(ep.flag_hi, ep.epoch);
          }
       }
+   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Resident kernel for SMALL systems (the reference's own regression cases: 43 ... a few thousand atoms).  Two launches
+// per step cost several microseconds of launch latency and start with cold L1 caches, while the arithmetic of such a
+// step is a short dependent chain per atom, so the whole time loop moves into ONE launch.  A thread-block CLUSTER of
+// C <= 8 CTAs owns one ensemble; every CTA keeps cur / pred of ALL atoms of the ensemble in its own shared memory
+// (2 x 32 bytes per slot) for the entire call and integrates the atoms i = rank * 256 + thread (+ C * 256 ...).  A new
+// spin is stored into the copies of all C CTAs through distributed shared memory, so every gather is a LOCAL
+// shared-memory read; predictor and corrector are separated by cluster barriers instead of kernel boundaries.  The
+// neighbour table stays in global memory and is served from L1 after the first step.  Same device functions, same
+// summation order (j = 1..nlistsize) and the same noise counters as llg_stage_kernel: a run is bit-identical whichever
+// way it is launched.  t.nl4 / t.cpl_param / t.staged must be cleared by the caller.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_spin_cluster(cooperative_groups::cluster_group& cl, SpinVec* __restrict__ local, int i,
+                                                   const SpinVec& v, unsigned nrank) {
+   if (nrank == 1) { local[i] = v; return; }
+   for (unsigned r = 0; r < nrank; r++) cl.map_shared_rank(local, r)[i] = v;
+}
+
+// cluster.sync() invalidates L1 (CCTL.IVALL): a single-CTA "cluster" takes the CTA barrier instead
+__device__ __forceinline__ void resident_barrier(cooperative_groups::cluster_group& cl, unsigned nrank) {
+   if (nrank == 1) __syncthreads(); else cl.sync();
+}
+
+// Pair sums of one atom with the neighbour slots read from the CTA's shared-memory copy of its atoms' lists
+// (idx[(j) * nt], 16-bit slots): same terms, same order, same helpers as site_field.
+template <bool REDUCED>
+__device__ __forceinline__ void resident_pairs(const Tables& t, const SpinVec* __restrict__ S, const unsigned short* __restrict__ idx,
+                                               int nt, int i, int ih, const SpinVec& own, const double* smc, const double* smd,
+                                               const double* smb, double bs[3], double bq[3]) {
+   const int Npad = t.Npad;
+   double fx = 0.0, fy = 0.0, fz = 0.0;
+   {
+      const int n = REDUCED ? __ldg(t.lsize + ih) : t.z;
+      const double* __restrict__ c = REDUCED ? (smc ? smc + (size_t)ih * t.z : t.cp + (size_t)ih * t.z) : t.cp + i;
+#pragma unroll 10
+      for (int j = 0; j < n; j++) {
+         const SpinVec v = S[idx[j * nt]];
+         const double cj = REDUCED ? c[j] : __ldg(c + (size_t)j * Npad);
+         fx = fma(cj, v.x * v.m, fx);
+         fy = fma(cj, v.y * v.m, fy);
+         fz = fma(cj, v.z * v.m, fz);
+      }
+   }
+   idx += t.z * nt;
+   if (t.zdm > 0) {
+      const int n = REDUCED ? __ldg(t.dmsize + ih) : t.zdm;
+      for (int j = 0; j < n; j++) {
+         double Dx, Dy, Dz;
+         if (REDUCED) {
+            const double* __restrict__ d = (smd ? smd : t.dmv) + ((size_t)ih * t.zdm + j) * 3;
+            Dx = d[0]; Dy = d[1]; Dz = d[2];
+         } else {
+            const size_t o = (size_t)j * Npad + i, s = (size_t)t.zdm * Npad;
+            Dx = __ldg(t.dmv + o); Dy = __ldg(t.dmv + s + o); Dz = __ldg(t.dmv + 2 * s + o);
+         }
+         const SpinVec v = S[idx[j * nt]];
+         dm_term(Dx, Dy, Dz, v.x * v.m, v.y * v.m, v.z * v.m, fx, fy, fz);
+      }
+   }
+   idx += t.zdm * nt;
+   double qx = 0.0, qy = 0.0, qz = 0.0;
+   if (t.zbq > 0) {
+      const double ox = own.x * own.m, oy = own.y * own.m, oz = own.z * own.m;
+      const int n = REDUCED ? __ldg(t.bqsize + ih) : t.zbq;
+      for (int j = 0; j < n; j++) {
+         const double jb = REDUCED ? (smb ? smb : t.jbq)[(size_t)ih * t.zbq + j] : __ldg(t.jbq + (size_t)j * Npad + i);
+         const SpinVec v = S[idx[j * nt]];
+         bq_term(jb, v.x * v.m, v.y * v.m, v.z * v.m, ox, oy, oz, qx, qy, qz);
+      }
+   }
+   bs[0] = fx; bs[1] = fy; bs[2] = fz;
+   bq[0] = qx; bq[1] = qy; bq[2] = qz;
+}
+
+// apt = atoms per thread (host: ceil(Nown / (nrank * blockDim.x))); shared memory = staged couplings | cur | pred |
+// 16-bit neighbour slots [apt][z + zdm + zbq][blockDim.x] of the atoms this CTA integrates
+template <int SOLVER, bool REDUCED>
+__global__ void __launch_bounds__(256, 1)
+llg_resident_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgParams p, SpinVec* __restrict__ cur,
+                    SpinVec* __restrict__ pred, double* __restrict__ b2eff, long nsteps, unsigned long long first_step, int apt) {
+   namespace cg = cooperative_groups;
+   cg::cluster_group cl = cg::this_cluster();
+   const unsigned nrank = cl.num_blocks(), rank = cl.block_rank();
+   extern __shared__ double sm[];
+   const double *smc, *smd, *smb;
+   stage_couplings(t, sm, smc, smd, smb);
+   const int ncpl = t.sm_cp + t.sm_dm + t.sm_bq;
+   SpinVec* __restrict__ shc = reinterpret_cast<SpinVec*>(sm + ((ncpl + 3) & ~3));   // 32-byte aligned
+   SpinVec* __restrict__ shp = shc + t.Npad;
+   unsigned short* __restrict__ idx = reinterpret_cast<unsigned short*>(shp + t.Npad);
+   const int nt = blockDim.x, zt = t.z + t.zdm + t.zbq;
+   const int k = blockIdx.x / nrank;
+   SpinVec* __restrict__ curk = cur + (size_t)k * t.Npad;
+   for (int i = threadIdx.x; i < t.Npad; i += nt) { const SpinVec v = curk[i]; shc[i] = v; shp[i] = v; }
+   const int first = rank * nt + threadIdx.x, stride = nrank * nt;
+   for (int a = 0; a < apt; a++) {
+      const int i = first + a * stride;
+      unsigned short* __restrict__ row = idx + (size_t)a * zt * nt + threadIdx.x;
+      if (i < t.Nown) {
+         for (int j = 0; j < t.z; j++) row[j * nt] = (unsigned short)__ldg(t.nl + (size_t)j * t.Npad + i);
+         for (int j = 0; j < t.zdm; j++) row[(t.z + j) * nt] = (unsigned short)__ldg(t.dml + (size_t)j * t.Npad + i);
+         for (int j = 0; j < t.zbq; j++) row[(t.z + t.zdm + j) * nt] = (unsigned short)__ldg(t.bql + (size_t)j * t.Npad + i);
+      }
+   }
+   resident_barrier(cl, nrank);
+   for (long s = 0; s < nsteps; s++) {
+      const unsigned long long step = first_step + (unsigned long long)s;
+      // ---- field(cur) + predictor ----
+      for (int a = 0; a < apt; a++) {
+         const int i = first + a * stride;
+         if (i >= t.Nown) break;
+         const int io = __ldg(t.orig + i);
+         if (io < 0) continue;
+         const int ih = REDUCED ? __ldg(t.ham + i) : 0;
+         const SpinVec own = shc[i];
+         double bs[3], bq[3], h[3];
+         resident_pairs<REDUCED>(t, shc, idx + (size_t)a * zt * nt + threadIdx.x, nt, i, ih, own, smc, smd, smb, bs, bq);
+         site_field<REDUCED, false, ASD_CHUNK, false, false>(t, shc, i, ih, own, smc, smd, smb, bs, bq);
+         ext_field(t, i, k, h);
+         const double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
+         store_spin_cluster(cl, shp, i, integrate_site<SOLVER, 1>(t, p, i, k, io, b, own, own, b2eff, nullptr, step), nrank);
+      }
+      resident_barrier(cl, nrank);
+      // ---- field(pred) + corrector + moment update: cur[i] is read by its owner only during this stage ----
+      for (int a = 0; a < apt; a++) {
+         const int i = first + a * stride;
+         if (i >= t.Nown) break;
+         const int io = __ldg(t.orig + i);
+         if (io < 0) continue;
+         const int ih = REDUCED ? __ldg(t.ham + i) : 0;
+         const SpinVec own = shp[i], old = shc[i];
+         double bs[3], bq[3], h[3];
+         resident_pairs<REDUCED>(t, shp, idx + (size_t)a * zt * nt + threadIdx.x, nt, i, ih, own, smc, smd, smb, bs, bq);
+         site_field<REDUCED, false, ASD_CHUNK, false, false>(t, shp, i, ih, own, smc, smd, smb, bs, bq);
+         ext_field(t, i, k, h);
+         const double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
+         store_spin_cluster(cl, shc, i, integrate_site<SOLVER, 2>(t, p, i, k, io, b, own, old, b2eff, nullptr, step), nrank);
+      }
+      resident_barrier(cl, nrank);
+   }
+   if (rank == 0) {
+      SpinVec* __restrict__ predk = pred + (size_t)k * t.Npad;
+      for (int i = threadIdx.x; i < t.Npad; i += nt) { curk[i] = shc[i]; predk[i] = shp[i]; }
    }
 }
 

@@ -910,6 +910,59 @@ static int slab_push_state(asd_engine* e) {
    return 0;
 }
 
+// Small systems: the whole time loop in one launch, state resident in shared memory, one thread-block cluster per
+// ensemble (llg_resident_kernel).  Applies when one ensemble's cur + pred (64 bytes per slot) and the staged couplings
+// fit the shared memory of one SM and the serial work per thread does not outweigh the launches it saves: with
+// apt = atoms per thread (1 up to 8 x 256 = 2048 atoms) and a dependent chain of ~(1.7 + 0.09 z) us per atom and stage
+// (measured, profiles/README.md), against ~3.3 us saved per stage.  ASD_RESIDENT=0 switches it off, =1 forces it
+// (A/B runs, tests of either path on small fixtures).
+struct ResidentPlan { size_t smem; int nrank, nt, apt; };
+
+static bool resident_applies(const asd_engine* e, const Layout& L, ResidentPlan& rp) {
+   const char* env = std::getenv("ASD_RESIDENT");
+   if (env && atoi(env) == 0) return false;
+   if (e->slab.on || L.t.runs || L.t.jtens) return false;   // run-compressed layouts are big-system layouts (tests build small ones on purpose)
+   const int nown = L.t.Nown > 0 ? L.t.Nown : L.Npad;
+   if (L.Npad > 65535) return false;                        // 16-bit neighbour slots
+   rp.nrank = std::min(8, std::max(1, (nown + 255) / 256));
+   rp.nt = std::min(256, std::max(64, (((nown + rp.nrank - 1) / rp.nrank + 31) / 32) * 32));
+   rp.apt = (nown + rp.nrank * rp.nt - 1) / (rp.nrank * rp.nt);
+   const int zt = L.t.z + L.t.zdm + L.t.zbq;
+   rp.smem = (size_t)(((L.t.sm_cp + L.t.sm_dm + L.t.sm_bq + 3) & ~3)) * sizeof(double) + (size_t)2 * L.Npad * sizeof(SpinVec) +
+             (size_t)rp.apt * zt * rp.nt * sizeof(unsigned short);
+   if (rp.smem > (size_t)220 * 1024) return false;
+   const double chain = 1.7 + 0.03 * zt;                     // us per atom and stage (measured, profiles/README.md)
+   return (env && atoi(env) == 1) || (rp.apt - 1) * chain < 3.3;
+}
+
+template <int SOLVER, bool REDUCED>
+static int launch_resident2(asd_engine* e, const Tables& t, const LlgParams& p, const ResidentPlan& rp, long nsteps, long first_step) {
+   allow_smem(llg_resident_kernel<SOLVER, REDUCED>, rp.smem);
+   cudaLaunchConfig_t cfg;
+   memset(&cfg, 0, sizeof cfg);
+   cfg.gridDim = dim3((unsigned)(e->M * rp.nrank), 1, 1);
+   cfg.blockDim = dim3((unsigned)rp.nt, 1, 1);
+   cfg.dynamicSmemBytes = rp.smem;
+   cfg.stream = e->stream;
+   cudaLaunchAttribute at[1];
+   at[0].id = cudaLaunchAttributeClusterDimension;
+   at[0].val.clusterDim.x = (unsigned)rp.nrank; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+   cfg.attrs = at; cfg.numAttrs = 1;
+   CU(cudaLaunchKernelEx(&cfg, llg_resident_kernel<SOLVER, REDUCED>, t, p, e->cur.p, e->pred.p, e->b2eff.p, nsteps,
+                         (unsigned long long)first_step, rp.apt));
+   e->launches++;
+   return 0;
+}
+
+template <int SOLVER>
+static int launch_resident(asd_engine* e, Layout& L, const LlgParams& p, const ResidentPlan& rp, long nsteps, long first_step) {
+   Tables t = L.t;
+   t.nl4 = nullptr; t.cp4 = nullptr; t.cpl_param = 0; t.staged = 0; t.runs = 0;   // the plain j = 1..n loop of site_field
+   if (t.Nown <= 0) t.Nown = L.Npad;
+   return L.reduced ? launch_resident2<SOLVER, true>(e, t, p, rp, nsteps, first_step)
+                    : launch_resident2<SOLVER, false>(e, t, p, rp, nsteps, first_step);
+}
+
 static int sd_steps(asd_engine* e, long nsteps, long first_step, cudaEvent_t* ev /*optional per-stage events*/) {
    int r = ensure_layout(e, 1);
    if (r) return r;
@@ -920,6 +973,11 @@ static int sd_steps(asd_engine* e, long nsteps, long first_step, cudaEvent_t* ev
    if ((r = fill_llg(e, L, p, 0))) return r;
    if (e->slab.on && !e->slab.connected) return fail(-11, "slab: not connected to the ring neighbours");
    const int ntile = (L.t.Nown + L.t.tile_slots - 1) / L.t.tile_slots;
+   ResidentPlan rp;
+   if (nsteps > 0 && resident_applies(e, L, rp)) {
+      e->msum_fresh = false;
+      return e->SDEalgh == 1 ? launch_resident<1>(e, L, p, rp, nsteps, first_step) : launch_resident<5>(e, L, p, rp, nsteps, first_step);
+   }
    if (nsteps > 0) {
       if ((r = e->msum_part.alloc((size_t)e->M * ntile * 4))) return r;
       e->msum_fresh = false;
