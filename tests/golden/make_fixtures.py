@@ -69,7 +69,13 @@ def main():
         'averages': {'11000': [0.145574347, 0.252312246, 1.87753739, 1.9]},
         'moment': {'atom': 128, '11000': [0.0766180766, 0.132795919, 0.988177572]},
         'coord': {'atom': 128, 'row': [3.5, 3.5, 3.51], 'type': 2, 'numb': 2},
-        'tol': 1e-8, 'yaml': 'tests/regressionResaro.yaml:18-27,64-73,145-154'}
+        # field-level golden: precession + damping torque e x B + e x (e x B) of atom 128, B = the field of the step's SECOND
+        # evaluation (prn_fields.f90:493-557 called from measure() before the next step); printed with es12.4
+        'torques': {'atom': 128, '11000': [-0.048638, -0.049279, 0.010393, 0.070015]},
+        'cumulants': {'211': [1.89999979, 3.6099992, 13.0320942, 0.666666666, 3.77522802e-31, 0.0, -6.10001753, -6.09996425]},
+        'projavgs': {'11000': {'2': [2.5, 0.0, 0.191531371, 0.331974475, 2.47044706]}},
+        'totenergy': {'10900': {'tot': -6.10005366, 'exc': -6.1, 'ext': -5.36620122e-05}},
+        'tol': 1e-8, 'yaml': 'tests/regressionResaro.yaml:18-27,64-73,112-122,145-154,168-179,231-252'}
     fx['megatest'] = f
     # --- tests/FeCo: B2 two sublattices, sym 0, maptype 2, alpha=0.001 (regulartests.yaml:219-242), sloppy 2e-2
     f = fixture('FeCo')

@@ -62,6 +62,15 @@ def test_megatest_run_directory(tmp_path):
     assert abs(e[1] - (-6.10005366)) <= 1e-8
     assert abs(e[9] - (-5.36620122e-05)) <= 1e-8
     assert abs(e[1] - (e[2] + e[9])) <= 3e-8                              # printed with es16.8
+    # cumulant row 211 with the energy running means (regressionResaro.yaml:112-122) and the per-site projected averages
+    # (:168-179, bergtest `almost` = 5e-4 in the reference's YAML)
+    cu = [x for x in asdio.read_out(os.path.join(d, 'cumulants.megaTest.out')) if int(x[0]) == 211][0]
+    for a, b in zip(cu[1:9], exp['cumulants']['211']):
+        assert abs(a - b) <= 5e-9 * max(1.0, abs(b)), (cu, exp['cumulants'])
+    pr = [x for x in asdio.read_out(os.path.join(d, 'projavgs.megaTest.out')) if int(x[0]) == 11000 and int(x[1]) == 2][0]
+    for a, b in zip(pr[2:7], exp['projavgs']['11000']['2']):
+        assert abs(a - b) <= 5e-4, (pr, exp['projavgs'])
+    assert abs(pr[4] - 2.5 * exp['moment']['11000'][0]) <= 1e-8
 
 
 @pytest.mark.parametrize('name,simid,sdealgh', [('feco', 'FeCo__B2', 1), ('feco_cuda', 'FeCo__B2', 5), ('bccfe_cuda', 'bcc_Fe_T', 5)])

@@ -259,3 +259,51 @@ def test_scsurf_dm_anisotropy_atomic_units():
     r = _t0_run(S, inp, {800})
     for a, b in zip(r[800][0], fx['expected']['averages']['800']):
         assert _similar(a, b), (a, b)
+
+
+def test_megatest_torque_energy_cumulant_and_projected_goldens():
+    """More rows of tests/Regression megaTest (regressionResaro.yaml:112-122, 168-179, 231-252): the FIELD-LEVEL golden
+    torques.megaTest.out (e x B + e x (e x B) of atom 128 at iteration 11000, B from the second field evaluation of the last
+    step, 5 printed digits), the energy columns at 10900, the cumulant row 211 including the running means of the total and
+    exchange energy (the product's estimator, uppasd_b200/observables.py, fed with oracle states), and the per-site projected
+    average of basis atom 2."""
+    from uppasd_b200 import observables
+    fx, inp, S = load_golden('megatest')
+    exp = fx['expected']
+    N, na = S['Natom'], S['NA']
+    c = orc.consts(S)
+    st = orc.SdState(S, 1, inp['timestep'], inp['damping'])
+    cum = observables.Cumulants(N, 1, inp['temp'], c['k_bolt'], c['mub'], c['mry'], inp['cumu_buff'], inp['plotenergy'])
+    rows, last_e, last_x, e10900 = {}, None, None, None
+    for mstep in range(1, 11001 + 1):
+        if (mstep - 1) % inp['avrg_step'] == 0:
+            t = orc.energy_terms(S, st.emomM)
+            last_e, last_x = t.sum(axis=0), t[0]
+            if mstep - 1 == 10900:
+                e10900 = t[:, 0]
+        if mstep % inp['cumu_step'] == 0:
+            r = cum.sample(st.sum_moments(), last_e, last_x)
+            if r:
+                rows[r[0]] = r
+        if mstep <= 11000:
+            st.step()
+    for a, b in zip(rows[211][1:9], exp['cumulants']['211']):
+        assert abs(a - b) <= 5e-9 * max(1.0, abs(b)), (rows[211], exp['cumulants'])      # nine printed digits
+    en = exp['totenergy']['10900']
+    for a, b in ((e10900.sum(), en['tot']), (e10900[0], en['exc']), (e10900[4], en['ext'])):
+        assert _similar(a, b), (a, b)
+    atom = exp['torques']['atom']
+    B = st.work[:3 * N].reshape((3, N, 1), order='F')[:, atom - 1, 0]      # beff of the last (second) evaluation
+    e = st.emom[:, atom - 1, 0]
+    prec = np.cross(e, B)
+    tq = prec + np.cross(e, prec)
+    for a, b in zip(list(tq) + [float(np.linalg.norm(tq))], exp['torques']['11000']):
+        assert abs(a - b) <= 5.1e-7, (tq, exp['torques'])                    # es12.4: half a unit of the last printed digit
+    msum_na = np.stack([st.emomM[:, q::na, :].sum(axis=1) for q in range(na)], axis=1)
+    prow = [r for r in observables.projected_rows(11000, msum_na, N // na, S['atype_inp'], 'A') if r[1] == 2][0]
+    # this row is compared with bergtest's `almost` (abs <= 5e-4) in the reference's own YAML: its printed value is not
+    # consistent with its own moment.megaTest.out (2.5 x 0.0766180766 = 0.19154519, what comes out here) beyond 1e-5
+    for a, b in zip(prow[2:], exp['projavgs']['11000']['2']):
+        assert abs(a - b) <= 5e-4, (prow, exp['projavgs'])
+    m = exp['moment']
+    assert abs(prow[4] - 2.5 * m['11000'][0]) <= 1e-8 and abs(prow[6] - 2.5 * m['11000'][2]) <= 1e-8
