@@ -191,3 +191,16 @@ def test_single_cell_stencil_keeps_folded_neighbours():
                     seen.append(int(ca[i0, q]))
             n = S[key]['listsize'][i0]
             assert seen == list(S[key]['list'][:n, i0]), (key, i0)
+
+
+def test_tensor_exchange_reader_agrees(tmp_path):
+    """jfile.tensor of tests/kagome_cuda: the product's reader (row-by-row tensor, transposed into Fortran storage order)
+    against the restated read_exchange_tensor_base."""
+    fx, path = materialise('kagome_cuda', tmp_path)
+    inp, ref = asdio.read_inpsd(path), oinputs.read_inpsd(path)
+    assert inp['do_jtensor'] == 1
+    bas, atype = asdio.read_posfile(inp['posfile'], inp['cell'], inp['posfiletype'])
+    a = asdio.read_tensorfile(inp['exchange'], atype, bas, inp['cell'], inp['maptype'], inp['posfiletype'])
+    b = oinputs.read_tensor_file(ref['files']['exchange'], int(atype.max()), atype, bas, ref['cell'], ref['maptype'], ref['posfiletype'])
+    assert all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3])) and a[3] is None
+    assert np.abs(a[2]).max() > 0 and not np.array_equal(a[2][1], a[2][3])      # an asymmetric tensor: the transpose matters

@@ -187,3 +187,21 @@ def test_more_run_directories(name, simid, tmp_path):
         e = _row(os.path.join(d, 'totenergy.%s.out' % simid), int(it))
         for col, key in ((1, 'tot'), (2, 'exc'), (3, 'ani')):
             assert abs(e[col] - want[key]) <= 1e-8, (name, key, e, want)
+
+
+def test_kagome_tensor_run_directory(tmp_path):
+    """tests/kagome_cuda through the driver (cudatests.yaml:1-23, tol 1e-8): jfile.tensor read by the product, the j_tens
+    table built on the device (builder kind 3), random start from the reference's generator, Depondt (what the reference's
+    CUDA path runs): averages @1300 and the cumulant row 171 from the written files."""
+    from uppasd_b200 import driver
+    fx, path = materialise('kagome_cuda', tmp_path)
+    inp = asdio.read_inpsd(path)
+    inp['sdealgh'] = 5
+    driver.Simulation(inp, directory=str(tmp_path)).run()
+    d, exp = str(tmp_path), fx['expected']
+    r = _row(os.path.join(d, 'averages.kagome_T.out'), 1300)
+    for a, b in zip(r[1:5], exp['averages']['1300']):
+        assert abs(a - b) <= 1e-8, (r, exp)
+    cu = [x for x in asdio.read_out(os.path.join(d, 'cumulants.kagome_T.out')) if int(x[0]) == 171][0]
+    for a, b in zip(cu[1:5], exp['cumulants']['171']):
+        assert abs(a - b) <= 1e-8, (cu, exp)

@@ -28,6 +28,8 @@ CASES = [
     ('heisstripe', dict()),                                    # BC 0 0 P stripe
     ('heischainaf', dict()),                                   # two atom types
     ('scsurf', dict()),                                        # atomic units, maptype 2, DM
+    ('kagome_cuda', dict(ncell=(12, 9, 1))),                   # tensorial exchange (nine couplings per pair), do_reduced N
+    ('kagome_cuda', dict(ncell=(7, 5, 1), do_reduced='Y')),
 ]
 
 
@@ -38,6 +40,8 @@ def test_device_tables_bit_exact(name, over):
     args, S = _build(fx, over)
     inp = args[0]
     kinds = [(0, 'exchange', args[6], 1, 1, inp['sym'], True)]
+    if inp.get('do_jtensor', 0) == 1:
+        kinds = [(3, 'exchange', args[6], 9, 1, inp['sym'], False)]   # builder kind 3 fills the exchange table with j_tens
     if args[7] is not None:
         kinds.append((1, 'dm', args[7], 3, 1, 0, False))
     if args[8] is not None:
@@ -50,7 +54,7 @@ def test_device_tables_bit_exact(name, over):
         ns, ca, cs, sh = lattice.stencil(inp['cell'], S['bas'], S['atype_inp'], nn, red, sym, nntype if typed else None, ncell=inp['ncell'])
         cp = lattice.couplings(ns, ca, sh, S['atype_inp'], xc, S['ammom_inp'], c['mry'], c['mub'], lexp)
         e.build_lattice_table(kind, S['NA'], inp['ncell'], inp['bc'], ns, ca, cs, cp)
-        lst, size, coup = e.get_table(kind)
+        lst, size, coup = e.get_table(0 if kind == 3 else kind)
         ref = S[key]
         assert lst.shape == ref['list'].shape, (lst.shape, ref['list'].shape)
         assert np.array_equal(size, ref['listsize'])

@@ -206,6 +206,19 @@ def read_pairfile(path, atype, bas, cell, maptype, posfiletype, ncomp):
     return nn, red, xc, nntype
 
 
+def read_tensorfile(path, atype, bas, cell, maptype, posfiletype):
+    """Exchange file in tensor format (do_jtensor 1; read_exchange_tensor_base, inputhandler_ext.f90:658-740): nine numbers
+    per line are read into j_tmp(3,3) in Fortran (column-major) order and then transposed, i.e. the file lists the tensor
+    row by row; the neighbour type is not distinguished.  Returns nn, redcoord, xc(9, NT, maxshell) with J(a,b) at component
+    a + 3 b (the Fortran storage order of j_tens(3,3,...)), and None for nntype."""
+    nn, red, xc, _ = read_pairfile(path, atype, bas, cell, maptype, posfiletype, 9)
+    out = np.zeros_like(xc)
+    for a in range(3):
+        for b in range(3):
+            out[a + 3 * b] = xc[3 * a + b]
+    return nn, red, out, None
+
+
 def read_kfile(path, na):
     """anisotropytype(NA), anisotropy(NA,6) = K1, K2, ex, ey, ez, ratio."""
     atyp = np.zeros(na, dtype=np.int32)

@@ -1102,6 +1102,7 @@ static bool mc_on_tiles(const asd_engine* e) {
 static int mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, double temperature, double temprescale,
                      const double* extfield) {
    if (mode != 'M' && mode != 'H') return fail(-8, "MC mode '%c' is not on this path ('M' Metropolis, 'H' heat bath)", mode);
+   if (e->jtensor) return fail(-8, "Monte Carlo with tensorial exchange (do_jtensor 1) is not on this path");
    McParams p;
    memset(&p, 0, sizeof p);
    p.mode = mode; p.temperature = temperature; p.temprescale = temprescale; p.k_bolt = e->k_bolt; p.mub = e->mub;

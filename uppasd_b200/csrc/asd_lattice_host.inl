@@ -91,8 +91,12 @@ int asd_build_lattice_table(asd_engine* e, int kind, int NA, int N1, int N2, int
    if (e->N == 0) return fail(-2, "asd_set_system must be called first");
    CU(cudaSetDevice(e->device));
    if (!(e->NH == NA || e->NH == e->N)) return fail(-1, "nHam must be NA (do_reduced Y) or Natom");
-   if (kind < 0 || kind > 2) return fail(-1, "kind must be 0 (exchange), 1 (DM) or 2 (BQ)");
-   const int ncomp = (kind == 1) ? 3 : 1;
+   if (kind < 0 || kind > 3) return fail(-1, "kind must be 0 (exchange), 1 (DM), 2 (BQ) or 3 (tensorial exchange)");
+   // kind 3: the exchange table with nine couplings per pair (do_jtensor 1, hamiltonianinit.f90:412-432): same map, same
+   // buffers as kind 0, J(a,b) at component a + 3 b
+   const bool tensor = (kind == 3);
+   if (tensor) kind = 0;
+   const int ncomp = tensor ? 9 : (kind == 1) ? 3 : 1;
    Layout& L = e->sd;
    LatticeDesc& d = e->lat;
    Slab& sb = e->slab;
@@ -210,7 +214,7 @@ int asd_build_lattice_table(asd_engine* e, int kind, int NA, int N1, int N2, int
    }
    CU(cudaStreamSynchronize(e->stream));
    Tables& t = L.t;
-   if (kind == 0) { t.z = z; t.nl = d_list.p; t.cp = d_cp.p; t.lsize = d_size.p; }
+   if (kind == 0) { t.z = z; t.nl = d_list.p; t.cp = d_cp.p; t.lsize = d_size.p; t.jtens = tensor ? 1 : 0; e->jtensor = tensor; }
    if (kind == 1) { t.zdm = z; t.dml = d_list.p; t.dmv = d_cp.p; t.dmsize = d_size.p; }
    if (kind == 2) { t.zbq = z; t.bql = d_list.p; t.jbq = d_cp.p; t.bqsize = d_size.p; }
    L.zs[kind] = z;
@@ -223,14 +227,14 @@ int asd_get_table_dims(asd_engine* e, int kind, int* z, int* ncomp) {
    const HostTable& T = (kind == 0) ? e->ex : (kind == 1) ? e->dm : e->bq;
    int zz = e->lattice_built ? e->sd.zs[kind] : T.z;
    if (z) *z = zz;
-   if (ncomp) *ncomp = (kind == 1) ? 3 : 1;
+   if (ncomp) *ncomp = (kind == 1) ? 3 : (kind == 0 && e->jtensor) ? 9 : 1;
    return 0;
 }
 
 int asd_get_table(asd_engine* e, int kind, int* list, int* listsize, double* coup) {
    if (kind < 0 || kind > 2) return fail(-1, "bad kind");
    CU(cudaSetDevice(e->device));
-   const int ncomp = (kind == 1) ? 3 : 1;
+   const int ncomp = (kind == 1) ? 3 : (kind == 0 && e->jtensor) ? 9 : 1;
    if (!e->lattice_built) {
       const HostTable& T = (kind == 0) ? e->ex : (kind == 1) ? e->dm : e->bq;
       if (!T.present()) return fail(-2, "table not set");

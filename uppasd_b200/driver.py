@@ -35,8 +35,10 @@ class Simulation:
         self.c = dict(consts or CONSTANTS)
         if inp['aunits'] == 'Y':                       # inputhandler.f90:1685-1704
             self.c = dict(gama=1.0, k_bolt=1.0, mub=1.0, mry=1.0)
-        if inp['do_jtensor'] == 1 or inp['do_ralloy'] != 0:
-            raise Unsupported('do_jtensor / do_ralloy are outside the hot path served here')
+        if inp['do_ralloy'] != 0:
+            raise Unsupported('do_ralloy is outside the hot path served here')
+        if inp['do_jtensor'] == 1 and (inp['mode'] != 'S' or inp['ip_mode'] not in ('N', 'S')):
+            raise Unsupported('do_jtensor 1 is served for spin dynamics only (mode / ip_mode S)')
         if inp['mode'] not in ('S', 'M', 'H') or inp['ip_mode'] not in ('N', 'S', 'M', 'H'):
             raise Unsupported('mode %s / ip_mode %s: only S (spin dynamics), M (Metropolis), H (heat bath)' % (inp['mode'], inp['ip_mode']))
         self.seed = int(seed if seed is not None else (inp['gpu_rng_seed'] or inp['tseed']))
@@ -72,7 +74,12 @@ class Simulation:
         for kind, key, ncomp, lexp, sym, typed in tables:
             if not inp.get(key):
                 continue
-            nn, red, xc, nntype = asdio.read_pairfile(inp[key], atype_inp, bas, cell, inp['maptype'], inp['posfiletype'], ncomp)
+            if kind == 0 and inp['do_jtensor'] == 1:
+                # tensorial exchange: same neighbour map, nine couplings per pair, no neighbour-type filter (kind 3)
+                nn, red, xc, nntype = asdio.read_tensorfile(inp[key], atype_inp, bas, cell, inp['maptype'], inp['posfiletype'])
+                kind, typed = 3, False
+            else:
+                nn, red, xc, nntype = asdio.read_pairfile(inp[key], atype_inp, bas, cell, inp['maptype'], inp['posfiletype'], ncomp)
             ns, ca, cs, sh = lattice.stencil(cell, bas, atype_inp, nn, red, sym, nntype if typed else None, ncell=(n1, n2, n3))
             cp = lattice.couplings(ns, ca, sh, atype_inp, xc, ammom, c['mry'], c['mub'], lexp)
             e.build_lattice_table(kind, na, (n1, n2, n3), inp['bc'], ns, ca, cs, cp)
