@@ -322,6 +322,15 @@ def test_solvers_golden_random_start(solver):
     assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-10
 
 
+def test_monte_carlo_refuses_tensor_exchange():
+    """do_jtensor 1 is served by the LLG path only; a Monte Carlo sweep must fail loudly, not run with the wrong couplings"""
+    from uppasd_b200 import host
+    fx, inp, S = load_golden('kagome_cuda')
+    e = _engine(S, inp)
+    with pytest.raises(host.AsdError):
+        e.mc_sweeps('M', 1, 10.0)
+
+
 def test_tensor_exchange_field_trajectory_and_golden():
     """Tensorial exchange (do_jtensor 1; hamiltonianactions.f90:499-542) on tests/kagome_cuda: field and both solvers'
     trajectories against the oracle to 1e-12, the reference's printed averages @1300 (cudatests.yaml:1-23, 1e-8), and the
