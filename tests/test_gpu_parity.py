@@ -455,3 +455,32 @@ def test_resident_kernel_is_bit_identical_to_the_stage_launches(alg, monkeypatch
     # launch counts (get_moments adds a few conversion launches to each): 1 / 3 resident launches against 400 stage launches
     assert out['batched'][1] - out['resident'][1] == 2 and out['stages'][1] - out['resident'][1] == 399, {k: v[1] for k, v in out.items()}
     assert np.abs(out['resident'][0] - S['emom']).max() > 1e-3
+
+
+def test_observables_on_host_table_layouts():
+    """asd_measure_sublattice and asd_skyrmion_number on layouts built from HOST tables (three sublattices of the kagome
+    fixture, two ensembles, after a few steps): against numpy / the oracle's pontryagin_tri, in the LLG layout and after
+    the state moved to the Monte Carlo (colour-major) layout."""
+    from uppasd_b200 import host
+    fx, inp, S0 = load_golden('kagome')
+    S = dict(S0, Mensemble=2)
+    for k in ('emom', 'emomM', 'external_field'):
+        S[k] = np.asfortranarray(np.repeat(S0[k], 2, axis=2))
+    for k in ('mmom', 'mmom0', 'mmomi'):
+        S[k] = np.asfortranarray(np.repeat(S0[k], 2, axis=1))
+    e = host.engine_from_system(S, orc.CONST, sdealgh=1, delta_t=inp['timestep'], damping=0.1, temp=50.0, seed=3)
+    e.sd_steps(60)
+    n1, n2, n3 = S['ncell']
+    simp = orc.delaunay_tri_tri(n1, n2, n3, S['NA'])
+    e.set_triangulation(simp)
+    for phase in ('llg', 'mc'):
+        if phase == 'mc':
+            e.mc_sweeps('H', 2, 20.0)
+        emom, emomM, _ = e.get_moments()
+        ms = e.measure_sublattice(S['NA'])
+        ref = np.stack([emomM[:, c::S['NA'], :].sum(axis=1) for c in range(S['NA'])], axis=1)
+        assert np.abs(ms - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max()), phase
+        q = e.skyrmion_number()
+        assert np.abs(q - orc.pontryagin_tri(emom, simp)[1]).max() <= 1e-12 * max(1.0, np.abs(q).max()), phase
+    with pytest.raises(host.AsdError):
+        e.measure_sublattice(5)                    # does not divide Natom
