@@ -216,7 +216,7 @@ def energy_terms(S, emomM=None):
 class SdState:
     """Mutable LLG state + work arrays for repeated orc_sd_step calls."""
 
-    def __init__(self, S, sdealgh, delta_t, damping, temp=0.0, mompar=0, temprescale=1.0):
+    def __init__(self, S, sdealgh, delta_t, damping, temp=0.0, mompar=0, temprescale=1.0, red_atom_list=None):
         N, M = S['Natom'], S['Mensemble']
         self.S, self.sdealgh, self.delta_t, self.mompar, self.temprescale = S, sdealgh, delta_t, mompar, temprescale
         self.H = ham_struct(S)
@@ -227,6 +227,11 @@ class SdState:
         self.lambda1 = np.full(N, damping) if np.isscalar(damping) else np.ascontiguousarray(damping, dtype=np.float64)
         self.temp = np.full(N, temp) if np.isscalar(temp) else np.ascontiguousarray(temp, dtype=np.float64)
         self.work = np.zeros(14 * N * M)
+        # fixed-moment run: red_atom_list = the 1-based atoms that evolve (evolution.f90:38-44)
+        self.frozen = None
+        if red_atom_list is not None:
+            self.frozen = np.ones(N, dtype=np.uint8)
+            self.frozen[np.asarray(red_atom_list, dtype=np.int64) - 1] = 0
 
     def step(self, gauss=None):
         L = lib()
@@ -235,7 +240,8 @@ class SdState:
         L.orc_sd_step(C.byref(self.H), self.sdealgh, _p(self.emom), _p(self.emomM), _p(self.mmom), _p(self.mmom0),
                       _p(S['external_field']), _p(S['Landeg']), _p(self.lambda1), _p(self.temp),
                       _d(self.temprescale), _d(self.delta_t), self.mompar, _p(g), _d(consts(self.S)['gama']),
-                      _d(consts(self.S)['k_bolt']), _d(consts(self.S)['mub']), _d(consts(self.S)['mry']), _p(self.work))
+                      _d(consts(self.S)['k_bolt']), _d(consts(self.S)['mub']), _d(consts(self.S)['mry']), _p(self.work),
+                      _p(self.frozen))
 
     def sum_moments(self):
         N, M = self.S['Natom'], self.S['Mensemble']

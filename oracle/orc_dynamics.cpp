@@ -438,8 +438,27 @@ void orc_moment_update(int Natom, int Mensemble, double* mmom, const double* mmo
 void orc_sd_step(const OrcHam* H, int SDEalgh, double* emom, double* emomM, double* mmom, const double* mmom0,
                  const double* external_field, const double* Landeg, const double* lambda1_array,
                  const double* Temp_array, double temprescale, double delta_t, int mompar, const double* gauss,
-                 double gama, double k_bolt, double mub, double mry, double* work) {
+                 double gama, double k_bolt, double mub, double mry, double* work, const unsigned char* frozen) {
+   // frozen (may be NULL): frozen[i-1] != 0 for atoms that are NOT in red_atom_list (Nred < Natom).  The reference's loops
+   // (midpoint.f90:123, depondt.f90:138 and their second halves) simply never visit such an atom: emom2 keeps the value
+   // magninit gave it (emom2 = emom, magnetizationinit.f90:538), copym writes that back.  Restated here by equivalence: the
+   // stage routines run over every atom and the rows of the frozen atoms are put back after each stage.
    const size_t NM = (size_t)H->Natom * H->Mensemble;
+   std::vector<double> keep;
+   if (frozen) keep.assign(emom, emom + 3 * NM);
+   auto put_back = [&](double* emom2_) {
+      if (!frozen) return;
+      for (long k = 0; k < H->Mensemble; k++)
+         for (long i = 0; i < H->Natom; i++)
+            if (frozen[i]) {
+               const size_t q = (size_t)i + (size_t)H->Natom * k;
+               for (int a = 0; a < 3; a++) {
+                  emom[3 * q + a] = keep[3 * q + a];
+                  emom2_[3 * q + a] = keep[3 * q + a];
+                  emomM[3 * q + a] = keep[3 * q + a] * mmom[q];
+               }
+            }
+   };
    double* beff = work;
    double* b2eff = work + 3 * NM;
    double* ranv = work + 6 * NM;
@@ -453,12 +472,16 @@ void orc_sd_step(const OrcHam* H, int SDEalgh, double* emom, double* emomM, doub
    if (SDEalgh == 1) {
       if (gauss) orc_rannum_scale(H->Natom, H->Mensemble, lambda1_array, bn, mmomi, Temp_array, temprescale, k_bolt, gama, mub, ranv);
       orc_midpoint_first(H->Natom, H->Mensemble, Landeg, bn, lambda1_array, beff, emom, emom2, emomM, mmom, delta_t, ranv, nullptr, gama);
+      put_back(emom2);
       orc_effective_field(H, emomM, external_field, beff, nullptr, nullptr, mub, mry);
       orc_midpoint_second(H->Natom, H->Mensemble, Landeg, bn, lambda1_array, beff, emom, emom2, delta_t, ranv, gama);
+      put_back(emom2);
    } else {
       orc_depondt_first(H->Natom, H->Mensemble, lambda1_array, beff, b2eff, emom, emom2, emomM, mmom, delta_t, Temp_array, temprescale, ranv, k_bolt, gama, mub);
+      put_back(emom2);
       orc_effective_field(H, emomM, external_field, beff, nullptr, nullptr, mub, mry);
       orc_depondt_second(H->Natom, H->Mensemble, lambda1_array, beff, b2eff, emom, emom2, delta_t, ranv, gama);
+      put_back(emom2);
    }
    orc_moment_update(H->Natom, H->Mensemble, mmom, mmom0, mmom2, emom, emom2, emomM, mmomi, mompar);
 }

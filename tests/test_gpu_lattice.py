@@ -8,6 +8,12 @@ from util import load_golden
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _stage_launch_path(monkeypatch):
+    """this module is about the kernels of LARGE systems, built small on purpose: keep the resident small-system kernel out"""
+    monkeypatch.setenv('ASD_RESIDENT', '0')
+
+
 def _build(fx, over):
     args = list(inputs.load_fixture(fx))
     args[0] = dict(args[0], **over)
@@ -225,3 +231,31 @@ def test_legacy_boundary_with_lattice_shape():
         st.step()
     assert np.abs(fh.arr['emom'] - st.emom).max() <= 1e-12
     assert sorted(fh.averages) == [0, 20, 40, 60]
+
+
+def test_fixed_moment_list_in_the_run_kernel():
+    """red_atom_list on a device-built lattice (run-compressed kernel, 4 atoms per thread): frozen atoms bit for bit, the rest
+    against the oracle to 1e-12, both solvers."""
+    fx, _, _ = load_golden('bccfe_cuda')
+    args = list(inputs.load_fixture(fx))
+    args[0] = dict(args[0], ncell=(64, 4, 4), mensemble=2, do_reduced='Y')
+    S = orc.build_system(*args)
+    inp = args[0]
+    rng = np.random.default_rng(5)
+    e0 = rng.normal(size=(3, S['Natom'], 2)); e0 /= np.sqrt((e0 ** 2).sum(axis=0))
+    S['emom'] = np.asfortranarray(e0)
+    S['emomM'] = np.asfortranarray(e0 * S['mmom'][None])
+    N = S['Natom']
+    fro = (np.arange(N) % 7 == 3)
+    red = np.arange(1, N + 1)[~fro]
+    for solver in (1, 5):
+        e = _bcc_engine(S, inp, args, solver, 0.0)
+        assert e.layout_info()['runs'] == 4
+        e.set_evolving_atoms(red)
+        st = orc.SdState(S, solver, inp['timestep'], 0.3, red_atom_list=red)
+        e.sd_steps(30)
+        for _ in range(30):
+            st.step()
+        emom = e.get_moments()[0]
+        assert np.array_equal(emom[:, fro, :], S['emom'][:, fro, :])
+        assert np.abs(emom - st.emom).max() <= 1e-12, solver

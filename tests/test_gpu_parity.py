@@ -484,3 +484,34 @@ def test_observables_on_host_table_layouts():
         assert np.abs(q - orc.pontryagin_tri(emom, simp)[1]).max() <= 1e-12 * max(1.0, np.abs(q).max()), phase
     with pytest.raises(host.AsdError):
         e.measure_sublattice(5)                    # does not divide Natom
+
+
+@pytest.mark.parametrize('alg', [1, 5])
+@pytest.mark.parametrize('resident', ['1', '0'])
+def test_fixed_moment_list(alg, resident, monkeypatch):
+    """Nred / red_atom_list of evolve_first (evolution.f90:38-44): every fifth atom of the kagome fixture is left out of the
+    list.  Frozen atoms keep their moment bit for bit, still act on their neighbours, and the trajectory equals the oracle's
+    (which restores the rows of the atoms the reference's loops never visit) to 1e-12; clearing the list restores the
+    ordinary run."""
+    monkeypatch.setenv('ASD_RESIDENT', resident)
+    fx, inp, S = load_golden('kagome')
+    N = S['Natom']
+    fro = np.arange(N) % 5 == 0
+    red = np.arange(1, N + 1)[~fro]
+    e = _engine(S, inp, sdealgh=alg)
+    e.set_evolving_atoms(red)
+    st = orc.SdState(S, alg, inp['timestep'], inp['damping'], red_atom_list=red)
+    e.sd_steps(150)
+    for _ in range(150):
+        st.step()
+    emom = e.get_moments()[0]
+    assert np.array_equal(emom[:, fro, 0], S['emom'][:, fro, 0])
+    assert np.abs(emom - st.emom).max() <= 1e-12
+    assert np.abs(emom[:, ~fro, 0] - S['emom'][:, ~fro, 0]).max() > 0.1
+    e.set_evolving_atoms(None)
+    e.set_moments(S['emom'], S['mmom'], S['mmom0'])
+    e.sd_steps(50)
+    st = orc.SdState(S, alg, inp['timestep'], inp['damping'])
+    for _ in range(50):
+        st.step()
+    assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12

@@ -43,6 +43,7 @@ SYMBOLS = {
     'asd_measure_sublattice': (C.c_int, [vp, C.c_int, vp]),
     'asd_set_triangulation': (C.c_int, [vp, C.c_int, vp]),
     'asd_skyrmion_number': (C.c_int, [vp, vp]),
+    'asd_set_evolving_atoms': (C.c_int, [vp, C.c_int, vp]),
     'asd_set_dm': (C.c_int, [vp, C.c_int, vp, vp, vp]),
     'asd_set_bq': (C.c_int, [vp, C.c_int, vp, vp, vp]),
     'asd_set_lattice_hint': (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]),

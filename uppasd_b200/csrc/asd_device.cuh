@@ -129,6 +129,9 @@ struct LlgParams {
    // msum_part[k][ntile][4] (asd_measure then only adds the per-tile partials: no second pass over the spins)
    double* msum_part;
    int msum_ntile;
+   // fixed-moment run (Nred < Natom, red_atom_list of evolve_first, evolution.f90:38-44): frozen[slot] != 0 marks an atom
+   // that is NOT in the list of evolving atoms -- the integrators skip it, every neighbour still sees its moment
+   const unsigned char* __restrict__ frozen;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -698,6 +701,13 @@ __device__ __forceinline__ SpinVec integrate_site(const Tables& t, const LlgPara
                                                   const float* gpre = nullptr, unsigned long long step_arg = ~0ull) {
    // step_arg: the noise key of a kernel that advances the step itself (llg_resident_kernel); default: p.step
    const unsigned long long nstep = (step_arg != ~0ull) ? step_arg : p.step;
+   if (p.frozen != nullptr && __ldg(p.frozen + i)) {
+      // not in red_atom_list: the loops of midpoint.f90:123 / depondt.f90:138 never visit this atom, emom2 keeps the value
+      // magninit gave it (emom2 = emom, magnetizationinit.f90:538) and copym writes that back every step
+      SpinVec o = c0;
+      if (STAGE == 2 && p.mompar) o.m = calcm(p.mompar, c0.m, __ldg(p.mmom0 + (size_t)k * t.Npad + i), c0.z);
+      return o;
+   }
    double lam, lg, temp;
    if (p.per_site) { lam = __ldg(p.lambda_a + i); lg = __ldg(p.landeg_a + i); temp = __ldg(p.temp_a + i); }
    else { lam = p.lambda; lg = p.landeg; temp = p.temp; }

@@ -87,6 +87,7 @@ struct HostTable {
 // Layout: one device ordering of the atoms + the tables permuted/transposed into it.
 // ------------------------------------------------------------------------------------------------
 struct Layout {
+   DevBuf<unsigned char> d_frozen;   // [Npad] device order, only for fixed-moment runs
    int N = 0, Npad = 0, NH = 0, M = 0;
    bool reduced = false;
    std::vector<int> orig;     // [Npad] original 0-based atom of slot, -1 padding
@@ -189,6 +190,8 @@ struct asd_engine {
    DevBuf<unsigned char> lat_col;       // [Nown] colour of every owned slot (periodic colouring, mc_tile_kernel)
    int lat_ncol = 0, lat_period[3] = {1, 1, 1};
    int mc_layout = -1;                  // -1: default (env ASD_MC_TILES), 0 colour-major, 1 lattice tiles
+   // fixed-moment run: frozen[i] != 0 for atoms outside red_atom_list (empty: every atom evolves)
+   std::vector<unsigned char> frozen;
    // triangulation for the skyrmion number (asd_set_triangulation): corners as 0-based ORIGINAL atom indices on the host,
    // as slots of one layout on the device (rebuilt when the state moves to the other layout)
    std::vector<int> simp;
@@ -665,6 +668,14 @@ static int fill_llg(asd_engine* e, Layout& L, LlgParams& p, unsigned long long s
       if ((r = perm(e->temp, L.d_temp))) return r;
    }
    p.landeg_a = L.d_landeg.p; p.lambda_a = L.d_lambda.p; p.temp_a = L.d_temp.p;
+   if (!e->frozen.empty() && L.d_frozen.p == nullptr) {
+      int rr = host_orig(e, L);
+      if (rr) return rr;
+      std::vector<unsigned char> h(L.Npad, 0);
+      for (int s = 0; s < L.Npad; s++) if (L.orig[s] >= 0) h[s] = e->frozen[L.orig[s]];
+      if ((rr = L.d_frozen.upload(h, e->stream))) return rr;
+   }
+   p.frozen = e->frozen.empty() ? nullptr : L.d_frozen.p;
    p.delta_t = e->delta_t; p.gamma = e->gamma; p.k_bolt = e->k_bolt; p.mub = e->mub; p.temprescale = e->temprescale;
    p.mompar = e->mompar; p.mmom0 = L.d_mmom0.p;
    p.seed = e->seed; p.step = step;
@@ -1342,6 +1353,27 @@ int asd_set_llg(asd_engine* e, int SDEalgh, double delta_t, const double* Landeg
       if (r) return r;
       e->state_layout = 0;
    }
+   return 0;
+}
+
+int asd_set_evolving_atoms(asd_engine* e, int Nred, const int* red_atom_list) {
+   if (e->N == 0) return fail(-2, "asd_set_system must be called first");
+   e->sd.d_frozen.release(); e->mc.d_frozen.release();
+   e->frozen.clear();
+   if (red_atom_list == nullptr || Nred <= 0 || Nred >= e->N) {
+      if (red_atom_list != nullptr && Nred > e->N) return fail(-1, "asd_set_evolving_atoms: Nred = %d exceeds Natom", Nred);
+      if (red_atom_list == nullptr || Nred <= 0) return 0;      // every atom evolves
+   }
+   if (e->slab.on) return fail(-11, "asd_set_evolving_atoms: not available on a slab");
+   e->frozen.assign(e->N, 1);
+   for (int q = 0; q < Nred; q++) {
+      const int a = red_atom_list[q];
+      if (a < 1 || a > e->N) { e->frozen.clear(); return fail(-1, "asd_set_evolving_atoms: atom %d outside 1..Natom", a); }
+      e->frozen[a - 1] = 0;
+   }
+   bool any = false;
+   for (unsigned char f : e->frozen) any = any || f;
+   if (!any) e->frozen.clear();
    return 0;
 }
 

@@ -104,6 +104,14 @@ class Engine:
         a, b, c = arr(landeg), arr(lambda1), arr(temp)
         self._chk(self.lib.asd_set_llg(self.h, sdealgh, delta_t, _p(a), _p(b), _p(c), temprescale, mompar, seed))
 
+    def set_evolving_atoms(self, red_atom_list=None):
+        """red_atom_list: 1-based atoms that evolve (fixed-moment runs); None: all"""
+        if red_atom_list is None:
+            self._chk(self.lib.asd_set_evolving_atoms(self.h, 0, None))
+        else:
+            r = _i32(red_atom_list)
+            self._chk(self.lib.asd_set_evolving_atoms(self.h, int(r.size), _p(r)))
+
     def set_moments(self, emom, mmom, mmom0=None):
         e, m = _f64(emom, (3, self.N, self.M)), _f64(mmom, (self.N, self.M))
         m0 = _f64(mmom0, (self.N, self.M)) if mmom0 is not None else None
