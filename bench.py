@@ -154,21 +154,28 @@ def oracle_bcc(ncell, mensemble=1):
     return S
 
 
-def cpu_leg(ncell, solver, temp, damping, steps, warmup):
+def cpu_leg(ncell, solver, temp, damping, steps, warmup, settle_s=0.0):
     """Times the restated reference CPU path (oracle, OpenMP over all host cores) on a bounded sample."""
     from oracle import orc
+    # all host cores, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for its workers)
+    threads = orc.set_num_threads(os.cpu_count() or 1)
     S = oracle_bcc(ncell)
     n = S['Natom']
     st = orc.SdState(S, solver, 1e-16, damping, temp=temp)
     rng = np.random.default_rng(1)
     g = np.asfortranarray(rng.normal(size=(3, n, 1))) if temp > 0 else None   # noise generation not timed (favours the CPU)
-    for _ in range(warmup):
+    tw = time.perf_counter()
+    w = 0
+    # settle_s: under a multi-rank launcher the other ranks are still starting their interpreters (and exit at once); keep
+    # warming up until they are gone so that the timed steps have the host cores to themselves
+    while w < warmup or time.perf_counter() - tw < settle_s:
         st.step(gauss=g)
+        w += 1
     t0 = time.perf_counter()
     for _ in range(steps):
         st.step(gauss=g)
     dt = time.perf_counter() - t0
-    return n * steps / dt, dt / steps * 1e3, n
+    return n * steps / dt, dt / steps * 1e3, n, threads
 
 
 def traffic_from_profiles(kernel_key):
@@ -209,9 +216,9 @@ def main():
     if a.impl == 'reference':
         if rank != 0:
             return
-        os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+        os.environ['OMP_NUM_THREADS'] = str(cores)
         k = max(1, min(steps, 10))
-        v, ms, n = cpu_leg(a.cpu_ncell, a.solver, a.temp, a.damping, k, min(warmup, 3))
+        v, ms, n, cores = cpu_leg(a.cpu_ncell, a.solver, a.temp, a.damping, k, min(warmup, 3), settle_s=6.0 if world > 1 else 0.0)
         sample = 'bcc %dx%dx%d (%d spins) x %d steps of the same lattice/solver; restated Fortran loops ' \
                  '(oracle/), OpenMP static schedule, noise array pre-generated' % (*a.cpu_ncell, n, k)
         print(json.dumps({
@@ -331,8 +338,8 @@ def main():
             out['config']['halo'] = {'planes': 2, 'bytes_per_exchange_per_side': 2 * a.ncell[0] * a.ncell[1] * 2 * 32,
                                      'exchanges_per_step': 2, 'timeout_flag': slab_err}
         if world == 1 and not a.no_cpu:
-            os.environ.setdefault('OMP_NUM_THREADS', str(cores))
-            v, cms, cn = cpu_leg(a.cpu_ncell, a.solver, a.temp, a.damping, 5, 1)
+            os.environ['OMP_NUM_THREADS'] = str(cores)
+            v, cms, cn, cores = cpu_leg(a.cpu_ncell, a.solver, a.temp, a.damping, 5, 1)
             out['cpu_baseline'] = {'value': v, 'unit': 'atom-steps/s', 'cores': cores, 'kind': 'port',
                                    'sample': 'bcc %dx%dx%d (%d spins) x 5 steps, restated Fortran loops (oracle/), OpenMP over '
                                              'all host cores, noise pre-generated' % (*a.cpu_ncell, cn)}

@@ -317,6 +317,11 @@ def sd_run(S, inp, nstep=None, traj_atoms=(), want_rows=None, temp=0.0):
 
 
 # ---- reference RNG access (MT variant + ziggurat) ---------------------------------------------
+def set_num_threads(n):
+    """OpenMP threads of the restated loops (overrides OMP_NUM_THREADS); returns the count in force"""
+    return int(lib().orc_set_num_threads(int(n)))
+
+
 def rng_init(seed):
     lib().orc_rng_init(int(seed))
 

@@ -24,7 +24,23 @@
 #include <vector>
 #include <cstdint>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 extern "C" {
+
+// thread count of the OpenMP loops (a launcher such as torchrun exports OMP_NUM_THREADS=1 to its workers; the timed CPU
+// baseline must use the host cores it reports): returns the count now in force
+int orc_set_num_threads(int n) {
+#ifdef _OPENMP
+   if (n > 0) omp_set_num_threads(n);
+   return omp_get_max_threads();
+#else
+   (void)n;
+   return 1;
+#endif
+}
 
 struct OrcHam {
    int Natom, Mensemble, nHam;
