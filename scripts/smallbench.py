@@ -28,12 +28,13 @@ for name in ('bccfe', 'kagome', 'cluster', 'heisstripe'):
 # Monte Carlo sweeps on the same small systems (colour classes of a few dozen atoms)
 for name in ('bccfe', 'kagome'):
     fx, inp, S = load_golden(name)
-    for mode in ('M', 'H'):
+    for mode, res in (('M', '1'), ('M', '0'), ('H', '1'), ('H', '0')):
+        os.environ['ASD_RESIDENT'] = res
         e = host.engine_from_system(S, orc.consts(S), sdealgh=1, delta_t=1e-16, damping=0.5, temp=300.0)
         e.mc_sweeps(mode, 50, 300.0)
         ms = e.time_mc_sweeps(mode, 5000, 300.0)
         lay, ncol, per = e.mc_colouring()
-        print('%-10s N=%5d MC %s: %8.3f us/sweep (%d colours)  %.3e attempts/s' % (name, S['Natom'], mode, 1e3 * ms / 5000, ncol,
+        print('%-10s N=%5d MC %s resident=%s: %8.3f us/sweep (%d colours)  %.3e attempts/s' % (name, S['Natom'], mode, res, 1e3 * ms / 5000, ncol,
                                                                                   S['Natom'] * 5000 / ms * 1e3), flush=True)
         e.close()
 # the restated CPU path on the same system, one thread

@@ -121,6 +121,7 @@ def test_cooperative_and_persistent_sweeps_run_the_same_chain(mode, monkeypatch)
     Heisenberg sum) and the single cooperative launch with grid barriers between colours make the same draws and the
     same decisions as the one-thread-per-update colour launches; only the summation order of the field differs."""
     from uppasd_b200 import host
+    monkeypatch.setenv('ASD_RESIDENT', '0')      # the launch-per-colour family is under test here, not the small-system kernel
     inp, S = _system('feco', 3)
     rng = np.random.default_rng(17)
     e0 = rng.normal(size=(3, S['Natom'], 3)); e0 /= np.sqrt((e0 ** 2).sum(axis=0))
@@ -147,3 +148,35 @@ def test_cooperative_and_persistent_sweeps_run_the_same_chain(mode, monkeypatch)
     assert np.abs(out['thread'][0] - e0).max() > 0.1                            # the chain moved
     for name in ('subwarp', 'persistent'):
         assert np.abs(out[name][0] - out['thread'][0]).max() <= 1e-9, name
+
+
+@pytest.mark.parametrize('name', ['bccfe', 'kagome', 'feco'])
+@pytest.mark.parametrize('mode', ['M', 'H'])
+def test_resident_monte_carlo_runs_the_same_chain(name, mode, monkeypatch):
+    """Small systems: all colours of all sweeps of a call in ONE launch with the ensemble's state in shared memory
+    (mc_resident_kernel, the default at this size) against one launch per colour with one thread per update: the same
+    draws, the same field summation order, hence the same chain bit for bit; one launch per call."""
+    from uppasd_b200 import host
+    inp, S = _system(name, 3)
+    rng = np.random.default_rng(23)
+    e0 = rng.normal(size=(3, S['Natom'], 3)); e0 /= np.sqrt((e0 ** 2).sum(axis=0))
+    S['emom'] = np.asfortranarray(e0)
+    S['emomM'] = np.asfortranarray(e0 * S['mmom'][None])
+    T = 400.0
+    out = {}
+    for tag, env in (('resident', dict()), ('launches', dict(ASD_RESIDENT='0', ASD_MC_PERSISTENT='0', ASD_MC_LPA='1'))):
+        for k in ('ASD_RESIDENT', 'ASD_MC_PERSISTENT', 'ASD_MC_LPA'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        e = host.engine_from_system(S, orc.CONST, temp=T, seed=9)
+        e.mc_sweeps(mode, 0, T)
+        n0 = e.launch_count()
+        e.mc_sweeps(mode, 5, T)
+        e.mc_sweeps(mode, 4, T, first_sweep=6)
+        out[tag] = (e.get_moments()[0], e.launch_count() - n0)
+    _, ncol, _ = e.mc_colouring()
+    # (each count includes the one conversion launch of get_moments)
+    assert out['resident'][1] == 2 + 1 and out['launches'][1] == 9 * ncol + 1, (out['resident'][1], out['launches'][1], ncol)
+    assert np.array_equal(out['resident'][0], out['launches'][0])
+    assert np.abs(out['resident'][0] - e0).max() > 0.1

@@ -1125,6 +1125,38 @@ static int mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, d
    if (r) return r;
    Layout& L = e->mc;
    const int ncol = (int)L.colour_first.size();
+   // small systems: all colours of all sweeps in one launch, one CTA per ensemble, state in shared memory
+   // (mc_resident_kernel; ASD_RESIDENT=0 keeps the colour launches)
+   {
+      const char* env = std::getenv("ASD_RESIDENT");
+      long mx = 0;
+      for (int c = 0; c < ncol; c++) mx = std::max(mx, (long)L.colour_count[c]);
+      const size_t smem = (size_t)(((L.t.sm_cp + L.t.sm_dm + L.t.sm_bq + 3) & ~3)) * sizeof(double) + (size_t)L.Npad * sizeof(SpinVec);
+      // a colour class of up to 512 atoms is one round of the CTA; more rounds only pay while they stay cheaper than launches
+      const bool fits = smem <= (size_t)200 * 1024 && mx <= 1024 && nsweeps > 0 && ncol > 0;
+      if (fits && !(env && atoi(env) == 0)) {
+         int r;
+         if (L.d_classes.n != (size_t)ncol) {
+            std::vector<int2> cl(ncol);
+            for (int c = 0; c < ncol; c++) cl[c] = make_int2(L.colour_first[c], L.colour_count[c]);
+            if ((r = L.d_classes.upload(cl, e->stream))) return r;
+         }
+         p.sweep = (unsigned long long)first_sweep;
+         Tables t = L.t;
+         t.nl4 = nullptr; t.cp4 = nullptr; t.cpl_param = 0;      // plain j = 1..n neighbour loop, couplings staged in shared memory
+         const int nt = (int)std::min(512L, std::max(64L, ((mx + 31) / 32) * 32));
+         if (L.reduced) {
+            allow_smem(mc_resident_kernel<true>, smem);
+            mc_resident_kernel<true><<<e->M, nt, smem, e->stream>>>(t, p, L.d_classes.p, ncol, (int)nsweeps, e->cur.p);
+         } else {
+            allow_smem(mc_resident_kernel<false>, smem);
+            mc_resident_kernel<false><<<e->M, nt, smem, e->stream>>>(t, p, L.d_classes.p, ncol, (int)nsweeps, e->cur.p);
+         }
+         e->launches++;
+         CU(cudaGetLastError());
+         return 0;
+      }
+   }
    // launch-bound regime (many small colour classes): one cooperative launch for all colours of all sweeps
    {
       long mx = 0;

@@ -280,6 +280,43 @@ mc_sweeps_persistent_kernel(const __grid_constant__ Tables t, const __grid_const
    }
 }
 
+// SMALL systems (the reference's own Monte Carlo regression cases: a few hundred atoms, colour classes of a few dozen):
+// every colour launch is latency-bound (~6-12 us each, 8 per sweep for bcc Fe).  One CTA per ensemble keeps the whole state
+// of its ensemble in shared memory and runs ALL colours of ALL requested sweeps, separated by __syncthreads(); a CTA
+// barrier does not touch L1, so the neighbour table stays there after the first sweep.  Same update function, same draws
+// (keyed by atom, ensemble, sweep) as the colour launches: the chain is bit-identical.
+template <bool REDUCED>
+__global__ void __launch_bounds__(512, 1)
+mc_resident_kernel(const __grid_constant__ Tables t, const __grid_constant__ McParams p0, const int2* __restrict__ classes, int ncol,
+                   int nsweeps, SpinVec* __restrict__ cur) {
+   extern __shared__ double sm[];
+   const double *smc, *smd, *smb;
+   stage_couplings(t, sm, smc, smd, smb);
+   const int ncpl = t.sm_cp + t.sm_dm + t.sm_bq;
+   SpinVec* __restrict__ sh = reinterpret_cast<SpinVec*>(sm + ((ncpl + 3) & ~3));
+   const int k = blockIdx.x;
+   SpinVec* __restrict__ curk = cur + (size_t)k * t.Npad;
+   for (int i = threadIdx.x; i < t.Npad; i += blockDim.x) sh[i] = curk[i];
+   __syncthreads();
+   McParams p = p0;
+   for (int s = 0; s < nsweeps; s++) {
+      p.sweep = p0.sweep + (unsigned long long)s;
+      for (int c = 0; c < ncol; c++) {
+         const int2 cl = classes[c];
+         for (int a = threadIdx.x; a < cl.y; a += blockDim.x) {
+            const int i = cl.x + a;
+            const int o = __ldg(t.orig + i);
+            if (o < 0) continue;
+            const int ih = REDUCED ? __ldg(t.ham + i) : 0;
+            SpinVec out;
+            if (mc_update_site<REDUCED>(t, p, sh, i, k, o, ih, smc, smd, smb, out)) sh[i] = out;
+         }
+         __syncthreads();
+      }
+   }
+   for (int i = threadIdx.x; i < t.Npad; i += blockDim.x) curk[i] = sh[i];
+}
+
 // Lattice (brick) layout with a periodic colouring: `col[slot]` is the colour of the atom (255 = padding); a launch
 // updates the atoms of colour p.colour of the tiles in `tr`.  This is the Monte Carlo path of a slab-decomposed
 // supercell: EDGE launches cover the boundary tiles, store every changed boundary spin into the ring neighbours'
