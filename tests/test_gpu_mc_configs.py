@@ -180,3 +180,51 @@ def test_resident_monte_carlo_runs_the_same_chain(name, mode, monkeypatch):
     assert out['resident'][1] == 2 + 1 and out['launches'][1] == 9 * ncol + 1, (out['resident'][1], out['launches'][1], ncol)
     assert np.array_equal(out['resident'][0], out['launches'][0])
     assert np.abs(out['resident'][0] - e0).max() > 0.1
+
+
+def test_bccfe_temperature_scan_magnetisation_binder_and_tc():
+    """BASELINE config 2 in miniature (Tc scan, ensembles in parallel): heat-bath sweeps of tests/bccFe (6^3 cells) at six
+    temperatures across the transition, 16 ensembles on the GPU (colour-parallel, resident kernel) against the oracle's
+    random-sequential chain (4 ensembles).  <|M|> and the Binder cumulant U4 = 1 - <m^4> / (3 <m^2>^2) agree within the
+    statistical error bars at every temperature, and the temperature at which <|M|> has dropped to half the moment (a
+    finite-size Tc estimate) agrees within 40 K."""
+    from uppasd_b200 import host
+    temps = [700.0, 800.0, 900.0, 1000.0, 1100.0, 1300.0]
+    inp, S = _system('bccfe', 16)
+    inp4, S4 = _system('bccfe', 4)
+    m0 = float(S['mmom'][0, 0])
+    e = host.engine_from_system(S, orc.CONST, temp=temps[0], seed=41)
+    gpu_m, ref_m = [], []
+    sweep = 1
+    for T in temps:
+        e.mc_sweeps('H', 400, T, first_sweep=sweep)
+        sweep += 400
+        gm = []
+        for r in range(300):
+            e.mc_sweeps('H', 5, T, first_sweep=sweep)
+            sweep += 5
+            gm.append(np.sqrt(((e.measure() / S['Natom']) ** 2).sum(axis=0)))
+        gm = np.array(gm)                                   # (samples, 16)
+        rm, _, _ = orc.mc_run(S4, 'H', T, 1200, seed=7, sample_every=5, burn=300)      # (samples, 4)
+
+        def stats(x):
+            m1, m2, m4 = x.mean(axis=0), (x ** 2).mean(axis=0), (x ** 4).mean(axis=0)
+            return m1, 1.0 - m4 / (3.0 * m2 ** 2)
+
+        (g1, gu), (r1, ru) = stats(gm), stats(rm)
+        sig_m = np.sqrt(g1.var() / len(g1) + r1.var() / len(r1))
+        sig_u = np.sqrt(gu.var() / len(gu) + ru.var() / len(ru))
+        assert abs(g1.mean() - r1.mean()) < 5 * sig_m + 0.03, (T, g1.mean(), r1.mean(), sig_m)
+        assert abs(gu.mean() - ru.mean()) < 5 * sig_u + 0.02, (T, gu.mean(), ru.mean(), sig_u)
+        gpu_m.append(g1.mean())
+        ref_m.append(r1.mean())
+
+    def t_half(ms):
+        ms = np.array(ms) / m0
+        for a in range(len(temps) - 1):
+            if ms[a] >= 0.5 > ms[a + 1]:
+                return temps[a] + (ms[a] - 0.5) / (ms[a] - ms[a + 1]) * (temps[a + 1] - temps[a])
+        raise AssertionError(('no crossing', list(ms)))
+
+    assert gpu_m[0] > 0.6 * m0 and gpu_m[-1] < 0.35 * m0, gpu_m
+    assert abs(t_half(gpu_m) - t_half(ref_m)) < 40.0, (t_half(gpu_m), t_half(ref_m), gpu_m, ref_m)
