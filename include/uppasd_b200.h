@@ -158,7 +158,8 @@ int asd_set_llg(asd_engine* e, int SDEalgh, double delta_t, const double* Landeg
 /* moments: emom(3,N,M) unit vectors, mmom(N,M) magnitudes, mmom0(N,M) (NULL => mmom). */
 /* Fixed-moment runs: red_atom_list(Nred) = the 1-based atoms that evolve, as evolve_first / evolve_second receive it
  * (evolution.f90:38-44, midpoint.f90:123, depondt.f90:138); every other atom keeps its moment and still acts on its
- * neighbours.  Nred <= 0 or a null list: every atom evolves.  Monte Carlo sweeps ignore the list, as mc_evolve does. */
+ * neighbours.  Nred <= 0 or a null list: every atom evolves.  Monte Carlo sweeps ignore the list, as mc_evolve does.
+ * Large systems step with the direct one-atom-per-thread kernel while a list is set (the tile kernels carry no mask). */
 int asd_set_evolving_atoms(asd_engine* e, int Nred, const int* red_atom_list);
 int asd_set_moments(asd_engine* e, const double* emom, const double* mmom, const double* mmom0);
 int asd_get_moments(asd_engine* e, double* emom, double* emomM, double* mmom);

@@ -234,8 +234,9 @@ def test_legacy_boundary_with_lattice_shape():
 
 
 def test_fixed_moment_list_in_the_run_kernel():
-    """red_atom_list on a device-built lattice (run-compressed kernel, 4 atoms per thread): frozen atoms bit for bit, the rest
-    against the oracle to 1e-12, both solvers."""
+    """red_atom_list on a device-built lattice whose layout carries the run-compressed table: the engine routes a fixed-moment
+    run to the direct one-atom-per-thread kernel (the only large-system kernel compiled with the frozen mask); frozen atoms bit
+    for bit, the rest against the oracle to 1e-12, both solvers; clearing the list returns to the run kernel."""
     fx, _, _ = load_golden('bccfe_cuda')
     args = list(inputs.load_fixture(fx))
     args[0] = dict(args[0], ncell=(64, 4, 4), mensemble=2, do_reduced='Y')

@@ -695,13 +695,16 @@ __global__ void halo_push_kernel(int Nown, int M, size_t Npad, const SpinVec* __
 // ------------------------------------------------------------------------------------------------
 // gpre: the three N(0,1) numbers of this (atom, ensemble, step) when the caller already drew them (asd_runs.cuh
 // draws them while the gather list is in flight), else null.
-template <int SOLVER, int STAGE>
+// FROZEN (compile time): the kernel honours LlgParams::frozen.  Only the one-atom-per-thread direct kernel and the resident
+// kernel are compiled with it (the check costs the register-blocked run kernel 1.5 %, measured); the engine routes
+// fixed-moment runs to them.
+template <int SOLVER, int STAGE, bool FROZEN = false>
 __device__ __forceinline__ SpinVec integrate_site(const Tables& t, const LlgParams& p, int i, int k, int io, const double b[3],
                                                   const SpinVec& own, const SpinVec& c0, double* __restrict__ b2eff,
                                                   const float* gpre = nullptr, unsigned long long step_arg = ~0ull) {
    // step_arg: the noise key of a kernel that advances the step itself (llg_resident_kernel); default: p.step
    const unsigned long long nstep = (step_arg != ~0ull) ? step_arg : p.step;
-   if (p.frozen != nullptr && __ldg(p.frozen + i)) {
+   if (FROZEN && p.frozen != nullptr && __ldg(p.frozen + i)) {
       // not in red_atom_list: the loops of midpoint.f90:123 / depondt.f90:138 never visit this atom, emom2 keeps the value
       // magninit gave it (emom2 = emom, magnetizationinit.f90:538) and copym writes that back every step
       SpinVec o = c0;
@@ -874,7 +877,7 @@ llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPa
       const double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
       SpinVec old;
       if (STAGE == 2) old = curk[i];
-      const SpinVec o = integrate_site<SOLVER, STAGE>(t, p, i, k, io, b, own, (STAGE == 1) ? own : old, b2eff);
+      const SpinVec o = integrate_site<SOLVER, STAGE, !STAGED>(t, p, i, k, io, b, own, (STAGE == 1) ? own : old, b2eff);
       if (STAGE == 1) predk[i] = o; else curk[i] = o;
       if (MSUM) { mnew[0] = o.x * o.m; mnew[1] = o.y * o.m; mnew[2] = o.z * o.m; }
       if (EDGE) {
@@ -1037,7 +1040,7 @@ llg_resident_kernel(const __grid_constant__ Tables t, const __grid_constant__ Ll
          site_field<REDUCED, false, ASD_CHUNK, false, false>(t, shc, i, ih, own, smc, smd, smb, bs, bq);
          ext_field(t, i, k, h);
          const double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
-         store_spin_cluster(cl, shp, i, integrate_site<SOLVER, 1>(t, p, i, k, io, b, own, own, b2eff, nullptr, step), nrank);
+         store_spin_cluster(cl, shp, i, integrate_site<SOLVER, 1, true>(t, p, i, k, io, b, own, own, b2eff, nullptr, step), nrank);
       }
       resident_barrier(cl, nrank);
       // ---- field(pred) + corrector + moment update: cur[i] is read by its owner only during this stage ----
@@ -1053,7 +1056,7 @@ llg_resident_kernel(const __grid_constant__ Tables t, const __grid_constant__ Ll
          site_field<REDUCED, false, ASD_CHUNK, false, false>(t, shp, i, ih, own, smc, smd, smb, bs, bq);
          ext_field(t, i, k, h);
          const double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
-         store_spin_cluster(cl, shc, i, integrate_site<SOLVER, 2>(t, p, i, k, io, b, own, old, b2eff, nullptr, step), nrank);
+         store_spin_cluster(cl, shc, i, integrate_site<SOLVER, 2, true>(t, p, i, k, io, b, own, old, b2eff, nullptr, step), nrank);
       }
       resident_barrier(cl, nrank);
    }

@@ -823,7 +823,9 @@ static void allow_smem(K kernel, size_t bytes) {
 template <int SOLVER, int STAGE, bool EDGE, bool MSUM>
 static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, const EdgeParams& ep, const TileRange& tr, int ntiles) {
    const dim3 g(ntiles, e->M, 1), b(256, 1, 1);
-   if (L.t.runs) {
+   // fixed-moment runs (asd_set_evolving_atoms): only the direct one-atom-per-thread kernel is compiled with the frozen mask
+   const bool fr = p.frozen != nullptr;
+   if (L.t.runs && !fr) {
       const int NW = L.t.tile_slots / 128;
       const size_t smem = (size_t)((L.t.sm_dm + L.t.sm_bq + 1) & ~1) * sizeof(double) + (size_t)3 * (L.t.ucap + 32) * sizeof(double) +
                           (size_t)NW * L.t.urow * sizeof(uint4);
@@ -837,7 +839,7 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
       else if (NW == 4) ASD_LAUNCH_RUNS(4, false);
       else ASD_LAUNCH_RUNS(2, false);
 #undef ASD_LAUNCH_RUNS
-   } else if (L.t.staged) {
+   } else if (L.t.staged && !fr) {
       const size_t smem = L.smem_bytes + (size_t)3 * L.t.ucap * sizeof(double);
       if (L.reduced) {
          allow_smem(llg_stage_kernel<SOLVER, STAGE, true, true, EDGE, MSUM>, smem);
