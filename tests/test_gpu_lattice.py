@@ -260,3 +260,12 @@ def test_fixed_moment_list_in_the_run_kernel():
         emom = e.get_moments()[0]
         assert np.array_equal(emom[:, fro, :], S['emom'][:, fro, :])
         assert np.abs(emom - st.emom).max() <= 1e-12, solver
+        # the per-tile moment sums are not fused on this path: asd_measure still returns the right sums
+        assert np.allclose(e.measure(), e.get_moments()[1].sum(axis=1), rtol=1e-12, atol=1e-9)
+        e.set_evolving_atoms(None)
+        e.set_moments(S['emom'], S['mmom'])
+        st = orc.SdState(S, solver, inp['timestep'], 0.3)
+        e.sd_steps(10)
+        for _ in range(10):
+            st.step()
+        assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12, solver

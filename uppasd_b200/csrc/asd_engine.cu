@@ -822,9 +822,17 @@ static void allow_smem(K kernel, size_t bytes) {
 
 template <int SOLVER, int STAGE, bool EDGE, bool MSUM>
 static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, const EdgeParams& ep, const TileRange& tr, int ntiles) {
-   const dim3 g(ntiles, e->M, 1), b(256, 1, 1);
-   // fixed-moment runs (asd_set_evolving_atoms): only the direct one-atom-per-thread kernel is compiled with the frozen mask
+   dim3 g(ntiles, e->M, 1);
+   const dim3 b(256, 1, 1);
+   // fixed-moment runs (asd_set_evolving_atoms): only the direct one-atom-per-thread kernel is compiled with the frozen mask;
+   // it works on 256-slot tiles whatever tile size the layout was built for (never on a slab: refused at the setter)
    const bool fr = p.frozen != nullptr;
+   TileRange trd = tr;
+   if (fr && L.t.tile_slots != 256) {
+      const int n256 = (L.t.Nown + 255) / 256;
+      g.x = (unsigned)n256;
+      trd = TileRange{0, n256, 0};
+   }
    if (L.t.runs && !fr) {
       const int NW = L.t.tile_slots / 128;
       const size_t smem = (size_t)((L.t.sm_dm + L.t.sm_bq + 1) & ~1) * sizeof(double) + (size_t)3 * (L.t.ucap + 32) * sizeof(double) +
@@ -848,8 +856,8 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
          allow_smem(llg_stage_kernel<SOLVER, STAGE, false, true, EDGE, MSUM>, smem);
          llg_stage_kernel<SOLVER, STAGE, false, true, EDGE, MSUM><<<g, b, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
       }
-   } else if (L.reduced) llg_stage_kernel<SOLVER, STAGE, true, false, EDGE, MSUM><<<g, b, L.smem_bytes, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
-   else llg_stage_kernel<SOLVER, STAGE, false, false, EDGE, MSUM><<<g, b, 0, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
+   } else if (L.reduced) llg_stage_kernel<SOLVER, STAGE, true, false, EDGE, MSUM><<<g, b, L.smem_bytes, e->stream>>>(L.t, p, ep, trd, e->cur.p, e->pred.p, e->b2eff.p);
+   else llg_stage_kernel<SOLVER, STAGE, false, false, EDGE, MSUM><<<g, b, 0, e->stream>>>(L.t, p, ep, trd, e->cur.p, e->pred.p, e->b2eff.p);
    e->launches++;
 }
 
@@ -998,12 +1006,13 @@ static int sd_steps(asd_engine* e, long nsteps, long first_step, cudaEvent_t* ev
    for (long s = 0; s < nsteps; s++) {
       p.step = (unsigned long long)(first_step + s);
       const bool last = (s == nsteps - 1);
-      p.msum_part = last ? e->msum_part.p : nullptr;   // the last corrector launch also leaves the per-tile sums of emomM
+      // the last corrector launch also leaves the per-tile sums of emomM (not on the fixed-moment path, whose tiles differ)
+      p.msum_part = (last && p.frozen == nullptr) ? e->msum_part.p : nullptr;
       p.msum_ntile = ntile;
       if (e->SDEalgh == 1) { launch_stage<1, 1>(e, L, p); launch_stage<1, 2>(e, L, p); }
       else { launch_stage<5, 1>(e, L, p); launch_stage<5, 2>(e, L, p); }
    }
-   if (nsteps > 0) { e->msum_fresh = true; e->msum_ntile = ntile; }
+   if (nsteps > 0) { e->msum_fresh = (p.frozen == nullptr); e->msum_ntile = ntile; }
    (void)ev;
    CU(cudaGetLastError());
    return 0;
