@@ -104,6 +104,7 @@ int asd_build_lattice_table(asd_engine* e, int kind, int NA, int N1, int N2, int
    const int N3l = sb.on ? N3 / sb.G : N3;
    if (sb.on && (N3 % sb.G != 0 || N3l < sb.H)) return fail(-1, "slab: N3 = %d must be a multiple of the %d slabs and each slab at least %d planes thick", N3, sb.G, sb.H);
    if ((long)NA * N1 * N2 * N3l != e->N) return fail(-1, "NA*N1*N2*N3%s = %ld does not match Natom = %d", sb.on ? "/nslabs" : "", (long)NA * N1 * N2 * N3l, e->N);
+   e->tri_layout = 0;
    if (!e->lattice_built) {
       int per[3];
       for (int a = 0; a < 3; a++) per[a] = (bc3[a] == 'P' || bc3[a] == 'p') ? 1 : 0;
