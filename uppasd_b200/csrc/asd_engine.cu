@@ -507,7 +507,8 @@ static int colour_graph(const asd_engine* e, std::vector<int>& colour) {
 static int build_layout(asd_engine* e, Layout& L, bool colour_major) {
    const int N = e->N, NH = e->NH, M = e->M;
    e->tri_layout = 0;          // slots change: the device copy of the triangulation is rebuilt on its next use
-   L.d_frozen.release();
+   L.d_frozen.release();       // ... and so are the per-site arrays kept in device order (fill_llg re-permutes them)
+   L.d_lambda.release(); L.d_landeg.release(); L.d_temp.release();
    L.N = N; L.NH = NH; L.M = M;
    L.reduced = NH < N;
    L.is_mc = colour_major;
