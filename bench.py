@@ -103,7 +103,7 @@ class ClockSampler(threading.Thread):
                 'reasons': sorted(self.reasons), 'samples': len(self.sm), 'source': 'nvml' if self.nv is not None else 'nvidia-smi'}
 
 
-def bcc_engine(ncell, solver, temp, damping, mensemble, ens_offset, device, slab=None):
+def bcc_engine(ncell, solver, temp, damping, mensemble, ens_offset, device, slab=None, reduced=True):
     """bcc Fe supercell built entirely on the device (tables + tilted start), through the C ABI.
     slab = (world, rank, dist): this engine holds one z-slab of the supercell and is connected to its ring neighbours."""
     from uppasd_b200 import host, lattice
@@ -121,7 +121,10 @@ def bcc_engine(ncell, solver, temp, damping, mensemble, ens_offset, device, slab
         _, nz = slabmod.slab_planes(ncell[2], world, rank, halo)
     n = 2 * ncell[0] * ncell[1] * nz
     aham = (np.arange(n, dtype=np.int32) % 2) + 1
-    e.set_system(n, mensemble, 2, aham)
+    if reduced:
+        e.set_system(n, mensemble, 2, aham)
+    else:
+        e.set_system(n, mensemble, n, None)          # do_reduced N: one coupling row per atom (ncoup(z, Natom))
     if slab is not None:
         e.set_slab(world, rank, halo)
     e.build_lattice_table(0, 2, ncell, ('P', 'P', 'P'), ns, ca, cs, cp)
@@ -197,6 +200,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--ncell', type=int, nargs=3, default=[128, 128, 128])
     ap.add_argument('--solver', type=int, default=1, choices=[1, 5])
+    ap.add_argument('--full-ham', action='store_true', help='do_reduced N: per-atom coupling rows (SURVEY 8d: +16 z bytes per atom-step)')
     ap.add_argument('--temp', type=float, default=300.0)
     ap.add_argument('--damping', type=float, default=0.5)
     ap.add_argument('--decomp', default='ensemble', choices=['ensemble', 'slab'],
@@ -210,8 +214,9 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     steps, warmup = a.steps, max(a.warmup, 3)
     cores = os.cpu_count() or 1
-    workload = 'bccFe %dx%dx%d LLG %s (SDEalgh %d), T=%g K, damping %g, dt 1e-16, z=50, do_reduced Y' % (
-        a.ncell[0], a.ncell[1], a.ncell[2], 'midpoint' if a.solver == 1 else 'Depondt', a.solver, a.temp, a.damping)
+    workload = 'bccFe %dx%dx%d LLG %s (SDEalgh %d), T=%g K, damping %g, dt 1e-16, z=50, do_reduced %s' % (
+        a.ncell[0], a.ncell[1], a.ncell[2], 'midpoint' if a.solver == 1 else 'Depondt', a.solver, a.temp, a.damping,
+        'N' if a.full_ham else 'Y')
 
     if a.impl == 'reference':
         if rank != 0:
@@ -236,7 +241,7 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.cuda.set_device(local)
     slab = (world, rank, dist) if a.decomp == 'slab' else None
-    e, n = bcc_engine(a.ncell, a.solver, a.temp, a.damping, 1, 0 if slab else rank, local, slab=slab)
+    e, n = bcc_engine(a.ncell, a.solver, a.temp, a.damping, 1, 0 if slab else rank, local, slab=slab, reduced=not a.full_ham)
     sync = torch.zeros(1, device='cuda')
 
     def barrier():
@@ -300,6 +305,8 @@ def main():
     if rank == 0:
         peak, how = peaks()
         b1, b2 = B_ALG[a.solver]
+        if a.full_ham:
+            b1, b2 = b1 + 8.0 * 50, b2 + 8.0 * 50        # per-atom couplings add 8 z bytes per stage
         t2 = float(np.median(st2)) * 1e-3
         t1 = float(np.median(st1)) * 1e-3
         ach = b2 * n / t2 / 1e9
@@ -308,7 +315,7 @@ def main():
             kname = 'llg_runs_kernel<solver=%d,stage=2,tile=%d>' % (a.solver, lay['tile_slots'])
             tables = '%.0f MB of gather lists + run-compressed tables' % ((4.0 * lay['ucap'] + 16.0 * (lay['union'] + 2) * lay['tile_slots'] / 128) / lay['tile_slots'] * n / 1e6 + 8.0 * n / 1e6)
         else:
-            kname = 'llg_stage_kernel<solver=%d,stage=2,reduced,%s>' % (a.solver, 'staged' if lay['staged'] else 'direct')
+            kname = 'llg_stage_kernel<solver=%d,stage=2,%s,%s>' % (a.solver, 'full' if a.full_ham else 'reduced', 'staged' if lay['staged'] else 'direct')
             tables = 'index tables %.0f MB' % ((7 * 16 + 24) * n / 1e6)
         par = ('ensemble-sharded x%d (one %d-spin ensemble per GPU, no communication)' % (world, n)) if not slab else \
               ('z-slabs x%d of one supercell, halo push fused into the boundary-tile launches (peer stores over NVLink)' % world)
