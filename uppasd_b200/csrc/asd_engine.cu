@@ -841,10 +841,25 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
       const size_t smem = (size_t)((L.t.sm_dm + L.t.sm_bq + 1) & ~1) * sizeof(double) + (size_t)3 * (L.t.ucap + 32) * sizeof(double) +
                           (size_t)NW * L.t.urow * sizeof(uint4);
       const bool xs = L.t.dm16 != nullptr || L.t.bq16 != nullptr;
+      static const bool pdl_env = !(std::getenv("ASD_PDL") && atoi(std::getenv("ASD_PDL")) == 0);
+      const bool pdl = pdl_env && !EDGE && !e->slab.on;
 #define ASD_LAUNCH_RUNS(NWV, XSV)                                                                                                  \
       do {                                                                                                                         \
          allow_smem(llg_runs_kernel<SOLVER, STAGE, NWV, EDGE, MSUM, XSV>, smem);                                                   \
-         llg_runs_kernel<SOLVER, STAGE, NWV, EDGE, MSUM, XSV><<<g, NWV * 32, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p); \
+         if (pdl) {                                                                                                                \
+            /* programmatic dependent launch: the CTAs of this stage become resident while the previous stage drains its last */  \
+            /* wave, run the prologue that only touches tables and wait (griddepcontrol.wait) before the first spin is read */    \
+            cudaLaunchConfig_t cfg;                                                                                                \
+            memset(&cfg, 0, sizeof cfg);                                                                                           \
+            cfg.gridDim = g; cfg.blockDim = dim3(NWV * 32, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = e->stream;             \
+            cudaLaunchAttribute at[1];                                                                                             \
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                         \
+            at[0].val.programmaticStreamSerializationAllowed = 1;                                                                  \
+            cfg.attrs = at; cfg.numAttrs = 1;                                                                                      \
+            cudaLaunchKernelEx(&cfg, llg_runs_kernel<SOLVER, STAGE, NWV, EDGE, MSUM, XSV>, L.t, p, ep, tr, e->cur.p, e->pred.p,    \
+                               e->b2eff.p);                                                                                        \
+         } else                                                                                                                    \
+            llg_runs_kernel<SOLVER, STAGE, NWV, EDGE, MSUM, XSV><<<g, NWV * 32, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p); \
       } while (0)
       if (NW == 8) { if (xs) ASD_LAUNCH_RUNS(8, true); else ASD_LAUNCH_RUNS(8, false); }
       else if (NW == 4) ASD_LAUNCH_RUNS(4, false);

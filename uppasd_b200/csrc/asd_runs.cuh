@@ -194,6 +194,11 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rsrc + q) : "memory");
    }
    asm volatile("cp.async.commit_group;" ::: "memory");
+   // Programmatic dependent launch: everything above reads tables only.  Let the next stage's CTAs be scheduled as soon as
+   // every CTA of this grid has started, and do not touch a spin before the previous stage has completed and flushed.
+   // (Both are no-ops for an ordinary launch.)
+   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+   asm volatile("griddepcontrol.wait;" ::: "memory");
    // L2 prefetch of what the CTA one wave later needs first: its own spins, gather list and union rows
    if (t.pf_tiles > 0 && threadIdx.x < 3) {
       const size_t nt = (size_t)tile + t.pf_tiles;
