@@ -804,6 +804,10 @@ template <int SOLVER, int STAGE, bool REDUCED, bool STAGED, bool EDGE, bool MSUM
 __global__ void __launch_bounds__(256, STAGED ? ASD_MINB_STAGED : ASD_MINB)
 llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgParams p, const __grid_constant__ EdgeParams ep,
                  const TileRange tr, SpinVec* __restrict__ cur, SpinVec* __restrict__ pred, double* __restrict__ b2eff) {
+   // programmatic dependent launch (asd_engine.cu, launch_dep): the next stage's CTAs may be scheduled once every CTA of this
+   // grid has started; nothing below runs before the previous kernel of the stream has completed (no-ops otherwise)
+   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+   asm volatile("griddepcontrol.wait;" ::: "memory");
    extern __shared__ double sm[];
    const double *smc, *smd, *smb;
    const int tile = ((int)blockIdx.x < tr.split) ? tr.first + (int)blockIdx.x : tr.second + ((int)blockIdx.x - tr.split);

@@ -823,6 +823,21 @@ static void allow_smem(K kernel, size_t bytes) {
    }
 }
 
+// launch with or without the programmatic-dependent-launch attribute (the kernel must issue griddepcontrol.wait before it
+// touches anything the previous kernel of the stream writes)
+template <class K, class... A>
+static void launch_dep(bool pdl, K kernel, dim3 g, dim3 b, size_t smem, cudaStream_t st, A... args) {
+   if (!pdl) { kernel<<<g, b, smem, st>>>(args...); return; }
+   cudaLaunchConfig_t cfg;
+   memset(&cfg, 0, sizeof cfg);
+   cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+   cudaLaunchAttribute at[1];
+   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+   at[0].val.programmaticStreamSerializationAllowed = 1;
+   cfg.attrs = at; cfg.numAttrs = 1;
+   cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <int SOLVER, int STAGE, bool EDGE, bool MSUM>
 static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, const EdgeParams& ep, const TileRange& tr, int ntiles) {
    dim3 g(ntiles, e->M, 1);
@@ -836,6 +851,8 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
       g.x = (unsigned)n256;
       trd = TileRange{0, n256, 0};
    }
+   static const bool pdl_all = !(std::getenv("ASD_PDL") && atoi(std::getenv("ASD_PDL")) == 0);
+   const bool pdl_s = pdl_all && !EDGE && !e->slab.on;
    if (L.t.runs && !fr) {
       const int NW = L.t.tile_slots / 128;
       const size_t smem = (size_t)((L.t.sm_dm + L.t.sm_bq + 1) & ~1) * sizeof(double) + (size_t)3 * (L.t.ucap + 32) * sizeof(double) +
@@ -869,13 +886,13 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
       const size_t smem = L.smem_bytes + (size_t)3 * L.t.ucap * sizeof(double);
       if (L.reduced) {
          allow_smem(llg_stage_kernel<SOLVER, STAGE, true, true, EDGE, MSUM>, smem);
-         llg_stage_kernel<SOLVER, STAGE, true, true, EDGE, MSUM><<<g, b, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
+         launch_dep(pdl_s, llg_stage_kernel<SOLVER, STAGE, true, true, EDGE, MSUM>, g, b, smem, e->stream, L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
       } else {
          allow_smem(llg_stage_kernel<SOLVER, STAGE, false, true, EDGE, MSUM>, smem);
-         llg_stage_kernel<SOLVER, STAGE, false, true, EDGE, MSUM><<<g, b, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
+         launch_dep(pdl_s, llg_stage_kernel<SOLVER, STAGE, false, true, EDGE, MSUM>, g, b, smem, e->stream, L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
       }
-   } else if (L.reduced) llg_stage_kernel<SOLVER, STAGE, true, false, EDGE, MSUM><<<g, b, L.smem_bytes, e->stream>>>(L.t, p, ep, trd, e->cur.p, e->pred.p, e->b2eff.p);
-   else llg_stage_kernel<SOLVER, STAGE, false, false, EDGE, MSUM><<<g, b, 0, e->stream>>>(L.t, p, ep, trd, e->cur.p, e->pred.p, e->b2eff.p);
+   } else if (L.reduced) launch_dep(pdl_s, llg_stage_kernel<SOLVER, STAGE, true, false, EDGE, MSUM>, g, b, L.smem_bytes, e->stream, L.t, p, ep, trd, e->cur.p, e->pred.p, e->b2eff.p);
+   else launch_dep(pdl_s, llg_stage_kernel<SOLVER, STAGE, false, false, EDGE, MSUM>, g, b, (size_t)0, e->stream, L.t, p, ep, trd, e->cur.p, e->pred.p, e->b2eff.p);
    e->launches++;
 }
 
