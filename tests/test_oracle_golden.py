@@ -145,6 +145,26 @@ def test_bccfe_heat_bath_initial_phase():
     _, _, (emom, emomM, mmom) = orc.mc_run(S, 'H', 500.0, 2000, seed=inp['tseed'], sample_every=2000)
     m = emomM.sum(axis=1)[:, 0] / S['Natom']
     assert _sloppy(float(np.sqrt((m ** 2).sum())), 1.74887502)
+    # measurement phase: M_avg @2700 and the cumulant row 41 (regulartests.yaml:325-347, all `sloppy` in the reference)
+    from uppasd_b200 import observables
+    c, N = orc.consts(S), S['Natom']
+    S2 = dict(S, emom=emom, emomM=emomM, mmom=mmom)
+    cum = observables.Cumulants(N, 1, 500.0, c['k_bolt'], c['mub'], c['mry'], inp['cumu_buff'], inp['plotenergy'])
+    rows, av = {}, {}
+
+    def before_sweep(mcmstep, eM):
+        if (mcmstep - 1) % inp['avrg_step'] == 0:
+            mm = eM.sum(axis=1)[:, 0] / N
+            av[mcmstep - 1] = float(np.sqrt((mm ** 2).sum()))
+        if mcmstep % inp['cumu_step'] == 0:
+            r = cum.sample(eM.sum(axis=1))
+            if r:
+                rows[r[0]] = r
+
+    orc.mc_run(S2, 'H', 500.0, 2701, sample_every=5000, init=False, reshuffle_every=300, before_sweep=before_sweep)
+    assert _sloppy(av[2700], 1.76487867)
+    for a, b in zip(rows[41][1:5], [1.76731228, 3.12449683, 9.77644188, 0.666189962]):
+        assert _sloppy(a, b), (a, b)
 
 
 def test_reference_mt_variant_known_answers():
