@@ -515,3 +515,23 @@ def test_fixed_moment_list(alg, resident, monkeypatch):
     for _ in range(50):
         st.step()
     assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12
+
+
+def test_cluster_golden_through_the_legacy_boundary():
+    """tests/Cluster the way a patched sd_iphase / sd_mphaseCUDA would run it: FortranData_Initiate with the biquadratic table
+    handed over through fortrandata_setextras_, the two initial phases through cudamdsim_initialphase_, the measurement phase
+    through cudamdsim_measurementphase_ with the measurement callbacks: the reference's printed averages @25000
+    (regulartests.yaml:186-194, 1e-8) and the final state written back to the host arrays."""
+    from uppasd_b200 import host
+    fx, inp, S = load_golden('cluster')
+    orc.initmag1(S, inp['tseed'])
+    fh = host.FortranHost(S, orc.consts(S), sdealgh=5, nstep=25001, delta_t=inp['timestep'], damping=inp['damping'],
+                          avrg_step=inp['avrg_step']).initiate()
+    step = 1
+    for ph in fx['ip_phases']:
+        fh.initial_phase(ph['nstep'], ph['temp'], ph['timestep'], ph['damping'], 5, first_step=step)
+        step += ph['nstep']
+    fh.lib.cudamdsim_measurementphase_()
+    for a, b in zip(fh.averages[25000], fx['expected']['averages']['25000']):
+        assert abs(a - b) <= 1e-8, (fh.averages[25000], fx['expected'])
+    assert np.abs(np.sqrt((fh.arr['emom'] ** 2).sum(axis=0)) - 1.0).max() < 1e-10

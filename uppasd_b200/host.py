@@ -391,7 +391,15 @@ class FortranHost:
                                                         'mmom0', 'mmom2', 'mmomi', 'dm_vect', 'dmlist', 'dmlistsize',
                                                         'j_tens', 'kaniso', 'eaniso', 'taniso', 'sb', 'aHam')])
         L.fortrandata_setinputdata_(r('gpu_mode'), r('gpu_rng'), r('gpu_rng_seed'))
-        L.fortrandata_setextras_(_p(a['Landeg']), None, None, None, None, None, None, None)
+        bq = self.S.get('bq')
+        if bq is not None:
+            # the extras a maintainer passes for the biquadratic table (ham%bqlist, ham%bqlistsize, ham%j_bq, nn_bq_tot)
+            self._bq = dict(do_bq=C.c_uint(1), nn=C.c_uint(bq['z']), lst=_i32(bq['list']), size=_i32(bq['listsize']), j=_f64(bq['coup']))
+            q = self._bq
+            L.fortrandata_setextras_(_p(a['Landeg']), None, None, C.cast(C.byref(q['do_bq']), C.c_void_p),
+                                     C.cast(C.byref(q['nn']), C.c_void_p), _p(q['lst']), _p(q['size']), _p(q['j']))
+        else:
+            L.fortrandata_setextras_(_p(a['Landeg']), None, None, None, None, None, None, None)
         if self.lattice is not None:
             L.fortrandata_setlattice_(*[C.cast(C.byref(x), C.c_void_p) for x in self.lattice])
         else:
