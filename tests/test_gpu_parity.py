@@ -535,3 +535,37 @@ def test_cluster_golden_through_the_legacy_boundary():
     for a, b in zip(fh.averages[25000], fx['expected']['averages']['25000']):
         assert abs(a - b) <= 1e-8, (fh.averages[25000], fx['expected'])
     assert np.abs(np.sqrt((fh.arr['emom'] ** 2).sum(axis=0)) - 1.0).max() < 1e-10
+
+
+def test_resident_kernel_with_the_largest_cluster(monkeypatch):
+    """2000 atoms (bcc 10^3, z = 50): eight CTAs per cluster, 155 KB of shared memory each -- the upper end of the resident
+    kernel's range.  Bit-identical to the stage launches at 300 K, and to the oracle to 1e-12 at T = 0.  (If the device could not
+    co-schedule such a cluster the engine falls back to the stage launches; the results are the same either way.)"""
+    import json
+    import os
+    from oracle import inputs
+    from util import GOLDEN
+    from uppasd_b200 import host
+    fx = json.load(open(os.path.join(GOLDEN, 'bccfe_cuda.json')))
+    args = list(inputs.load_fixture(fx))
+    args[0] = dict(args[0], ncell=(10, 10, 10), mensemble=2)
+    S = orc.build_system(*args)
+    inp = args[0]
+    rng = np.random.default_rng(8)
+    e0 = rng.normal(size=(3, S['Natom'], 2)); e0 /= np.sqrt((e0 ** 2).sum(axis=0))
+    S['emom'] = np.asfortranarray(e0)
+    S['emomM'] = np.asfortranarray(e0 * S['mmom'][None])
+    out = {}
+    for res in ('1', '0'):
+        monkeypatch.setenv('ASD_RESIDENT', res)
+        e = host.engine_from_system(S, orc.CONST, sdealgh=1, delta_t=inp['timestep'], damping=0.3, temp=300.0, seed=2)
+        e.sd_steps(25)
+        out[res] = e.get_moments()[0]
+    assert np.array_equal(out['1'], out['0'])
+    monkeypatch.setenv('ASD_RESIDENT', '1')
+    e = host.engine_from_system(S, orc.CONST, sdealgh=5, delta_t=inp['timestep'], damping=0.3, temp=0.0)
+    st = orc.SdState(S, 5, inp['timestep'], 0.3)
+    e.sd_steps(30)
+    for _ in range(30):
+        st.step()
+    assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12

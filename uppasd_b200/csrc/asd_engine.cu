@@ -979,6 +979,7 @@ static int slab_push_state(asd_engine* e) {
 // (measured, profiles/README.md), against ~3.3 us saved per stage.  ASD_RESIDENT=0 switches it off, =1 forces it
 // (A/B runs, tests of either path on small fixtures).
 struct ResidentPlan { size_t smem; int nrank, nt, apt; };
+static const int RESIDENT_UNAVAILABLE = 31415;   // launch_resident: the cluster cannot be scheduled, use the stage launches
 
 static bool resident_applies(const asd_engine* e, const Layout& L, ResidentPlan& rp) {
    const char* env = std::getenv("ASD_RESIDENT");
@@ -1010,6 +1011,13 @@ static int launch_resident2(asd_engine* e, const Tables& t, const LlgParams& p, 
    at[0].id = cudaLaunchAttributeClusterDimension;
    at[0].val.clusterDim.x = (unsigned)rp.nrank; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
    cfg.attrs = at; cfg.numAttrs = 1;
+   // can the device co-schedule one such cluster at all (shared memory per CTA x cluster size inside one GPC)?  If not,
+   // the caller falls back to the stage launches instead of failing.
+   int nclusters = 0;
+   if (cudaOccupancyMaxActiveClusters(&nclusters, llg_resident_kernel<SOLVER, REDUCED>, &cfg) != cudaSuccess || nclusters < 1) {
+      cudaGetLastError();
+      return RESIDENT_UNAVAILABLE;
+   }
    CU(cudaLaunchKernelEx(&cfg, llg_resident_kernel<SOLVER, REDUCED>, t, p, e->cur.p, e->pred.p, e->b2eff.p, nsteps,
                          (unsigned long long)first_step, rp.apt));
    e->launches++;
@@ -1038,7 +1046,8 @@ static int sd_steps(asd_engine* e, long nsteps, long first_step, cudaEvent_t* ev
    ResidentPlan rp;
    if (nsteps > 0 && resident_applies(e, L, rp)) {
       e->msum_fresh = false;
-      return e->SDEalgh == 1 ? launch_resident<1>(e, L, p, rp, nsteps, first_step) : launch_resident<5>(e, L, p, rp, nsteps, first_step);
+      const int rr = e->SDEalgh == 1 ? launch_resident<1>(e, L, p, rp, nsteps, first_step) : launch_resident<5>(e, L, p, rp, nsteps, first_step);
+      if (rr != RESIDENT_UNAVAILABLE) return rr;
    }
    if (nsteps > 0) {
       if ((r = e->msum_part.alloc((size_t)e->M * ntile * 4))) return r;
