@@ -93,3 +93,29 @@ def test_single_slab_connects_to_itself():
     e = _FakeEngine(0)
     slab.connect_ring(e, 1, 0)
     assert e.got == ('local', True, True)
+
+
+def test_reference_arm_under_a_two_rank_launcher_uses_all_host_cores():
+    """`bench.py --impl reference` launched the way the driver launches it for N > 1 (torch.distributed.run, which exports
+    OMP_NUM_THREADS=1 to its workers): rank 0 alone prints ONE JSON line, timed on every host core (explicit
+    omp_set_num_threads), the other rank exits 0 without work."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    env = dict(os.environ, OMP_NUM_THREADS='1')
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+                        '127.0.0.1', '--master-port', str(port), os.path.join(root, 'bench.py'), '--impl', 'reference', '--gpus', '2',
+                        '--steps', '3', '--warmup', '1', '--cpu-ncell', '16', '16', '16'],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['n_gpus'] == 2 and d['gpu_launches'] == 0
+    assert d['cpu_baseline']['cores'] == (os.cpu_count() or 1) and d['cpu_baseline']['kind'] == 'port'
+    assert d['e2e']['value'] == d['value'] > 0 and d['e2e']['h2d_bytes_per_step'] == 0
