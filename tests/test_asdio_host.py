@@ -204,3 +204,23 @@ def test_tensor_exchange_reader_agrees(tmp_path):
     b = oinputs.read_tensor_file(ref['files']['exchange'], int(atype.max()), atype, bas, ref['cell'], ref['maptype'], ref['posfiletype'])
     assert all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3])) and a[3] is None
     assert np.abs(a[2]).max() > 0 and not np.array_equal(a[2][1], a[2][3])      # an asymmetric tensor: the transpose matters
+
+
+def test_projected_cumulants_estimator_and_file(tmp_path):
+    """projcumulants.megaTest.out row 211 of type 2 (regressionResaro.yaml:181-190): the product's per-type estimator (plain
+    running means, calc_and_print_cumulant_proj) fed with oracle states, written and read back in the reference's format."""
+    from util import load_golden
+    fx, inp, S = load_golden('megatest')
+    N, na, c = S['Natom'], S['NA'], orc.consts(S)
+    st = orc.SdState(S, 1, inp['timestep'], inp['damping'])
+    pc = observables.ProjectedCumulants(S['atype_inp'], N // na, 1, inp['temp'], c['k_bolt'], c['mub'], inp['cumu_buff'])
+    out = asdio.OutputFiles(str(tmp_path), 'megaTest')
+    for mstep in range(1, 10551):
+        if mstep % inp['cumu_step'] == 0:
+            rows = pc.sample(np.stack([st.emomM[:, q::na, :].sum(axis=1) for q in range(na)], axis=1))
+            if rows:
+                out.projcumulants(rows)
+        st.step()
+    got = [r for r in asdio.read_out(os.path.join(str(tmp_path), 'projcumulants.megaTest.out')) if int(r[0]) == 211 and int(r[1]) == 2][0]
+    for a, b in zip(got[1:7], [2, 2.5, 6.25, 39.0625, 0.666666667, -7.08541485e-37]):
+        assert abs(a - b) <= 1e-8, got

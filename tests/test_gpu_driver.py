@@ -71,6 +71,10 @@ def test_megatest_run_directory(tmp_path):
     for a, b in zip(pr[2:7], exp['projavgs']['11000']['2']):
         assert abs(a - b) <= 5e-4, (pr, exp['projavgs'])
     assert abs(pr[4] - 2.5 * exp['moment']['11000'][0]) <= 1e-8
+    # projcumulants row 211 of type 2 (regressionResaro.yaml:181-190)
+    pc = [x for x in asdio.read_out(os.path.join(d, 'projcumulants.megaTest.out')) if int(x[0]) == 211 and int(x[1]) == 2][0]
+    for a, b in zip(pc[1:7], [2, 2.5, 6.25, 39.0625, 0.666666667, -7.08541485e-37]):
+        assert abs(a - b) <= 1e-8, pc
 
 
 @pytest.mark.parametrize('name,simid,sdealgh', [('feco', 'FeCo__B2', 1), ('feco_cuda', 'FeCo__B2', 5), ('bccfe_cuda', 'bcc_Fe_T', 5)])

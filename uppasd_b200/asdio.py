@@ -56,7 +56,7 @@ def defaults():
         ip_hfield=(0.0, 0.0, 0.0), ip_temp=0.0, ip_nphase=[], ip_mcanneal=[], ip_mcnstep=0, do_reduced='N', do_sortcoup='N',
         mompar=0, landeg_glob=2.0, do_avrg='Y', avrg_step=100, avrg_buff=10, do_cumu='N', cumu_step=50, cumu_buff=10,
         plotenergy=0, do_tottraj='N', tottraj_step=1000, tottraj_buff=10, trajectories=[], do_prnstruct=0,
-        gpu_mode=0, gpu_rng_seed=0, do_jtensor=0, map_multiple=False, relaxed_if=False, do_proj_avrg='N', skyno='N',
+        gpu_mode=0, gpu_rng_seed=0, do_jtensor=0, map_multiple=False, relaxed_if=False, do_proj_avrg='N', do_cumu_proj='N', skyno='N',
         skyno_step=100, skyno_buff=10)
 
 
@@ -64,7 +64,7 @@ _SCALAR_INT = {'sym', 'maptype', 'do_ralloy', 'mensemble', 'tseed', 'sdealgh', '
                'mompar', 'avrg_step', 'avrg_buff', 'cumu_step', 'cumu_buff', 'plotenergy', 'tottraj_step', 'tottraj_buff',
                'do_prnstruct', 'gpu_mode', 'gpu_rng_seed', 'do_jtensor', 'ip_mcnstep', 'skyno_step', 'skyno_buff'}
 _SCALAR_REAL = {'alat', 'temp', 'damping', 'timestep', 'ip_temp'}
-_SCALAR_FLAG = {'aunits', 'posfiletype', 'do_reduced', 'do_sortcoup', 'do_avrg', 'do_cumu', 'do_tottraj', 'mode', 'ip_mode', 'do_proj_avrg', 'skyno'}
+_SCALAR_FLAG = {'aunits', 'posfiletype', 'do_reduced', 'do_sortcoup', 'do_avrg', 'do_cumu', 'do_tottraj', 'mode', 'ip_mode', 'do_proj_avrg', 'do_cumu_proj', 'skyno'}
 _FILES = {'posfile', 'momfile', 'exchange', 'dm', 'bq', 'anisotropy', 'restartfile'}
 
 
@@ -314,6 +314,16 @@ class OutputFiles:
                 fh.write('%8s%s%16s%16s%16s%16s%16s\n' % ('#Iter', 'Proj', '<M>', 'M_{stdv}', '<M>_x', '<M>_y', '<M>_z'))
             for r in rows:
                 fh.write(_row('%8d%8d' % (r[0], r[1]), r[2:]))
+
+    def projcumulants(self, rows):
+        """rows: (count, type, <M>, <M^2>, <M^4>, U, chi) -- calc_and_print_cumulant_proj, format 10004 = (i8,i6,5es16.8)"""
+        name = 'projcumulants.%s.out' % self.simid
+        new = name not in self._started
+        with self._open(name) as fh:
+            if new:
+                fh.write('%8s%6s%16s%16s%16s%16s%16s\n' % ('# ter.', 'Type', '<M>', '<M^2>', '<M^4>', 'U_{Binder}', '\\chi'))
+            for r in rows:
+                fh.write(_row('%8d%6d' % (r[0], r[1]), r[2:]))
 
     def sknumber(self, rows):
         """rows: (iter, Skx num, Skx avg, Skx std) -- prn_skyno, format 240 = (i8,2x,5f16.8)"""

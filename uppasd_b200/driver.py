@@ -185,6 +185,10 @@ class Simulation:
             row = self.cum.sample(msum, self.last_energy, self.last_exc)
             if row:
                 self.out.cumulants(row)
+        if inp['do_cumu_proj'] == 'Y' and mstep % inp['cumu_step'] == 0:      # prn_averages.f90:186-189
+            rows = self.pcum.sample(e.measure_sublattice(self.na))
+            if rows:
+                self.out.projcumulants(rows)
 
     def _energy(self, mstep):
         t = self.engine.energy_terms()                     # (5, M): exc, ani, dm, bq, ext
@@ -226,7 +230,7 @@ class Simulation:
             periods.append((tstep, 1))
         if inp['skyno'] == 'T':
             periods.append((inp['skyno_step'], 1))
-        if inp['do_cumu'] == 'Y':
+        if inp['do_cumu'] == 'Y' or inp['do_cumu_proj'] == 'Y':
             periods.append((inp['cumu_step'], 0))          # m % p == 0
         for p, off in periods:
             m = ((mstep - off) // p + 1) * p + off
@@ -241,6 +245,8 @@ class Simulation:
                                          inp['cumu_buff'], inp['plotenergy'])
         self.traj = [[[] for _ in range(self.mens)] for _ in inp['trajectories']]
         self.proj_rows, self.sky_rows, self.sky = [], [], observables.SkyrmionNumber(self.na)
+        self.pcum = observables.ProjectedCumulants(self.atype_cell, self.natom // self.na, self.mens, inp['temp'], self.c['k_bolt'],
+                                                   self.c['mub'], inp['cumu_buff'])
         self.last_energy = self.last_exc = None
         off = getattr(self, '_noise_offset', 1) - 1            # keeps the noise counters of the two phases apart
         if mode == 'S':

@@ -7,6 +7,8 @@
              chi = (<m^2> - <m>^2) mu_B^2 N / (k_B^2 T), C_v from the energy variance in mRy
   projavgs   buffer_proj_avrg / prn_proj_avrg  source/Measurement/prn_averages.f90:462-512, 662-802
   sknumber   buffer_skyno_tri / prn_skyno      source/Measurement/prn_topology.f90:660-700, 296-345
+  projcumulants  calc_and_print_cumulant_proj  source/Measurement/prn_averages.f90:1239-1333 -- PLAIN running means per atom
+             type (unlike the weighted means of the total cumulants)
 """
 import numpy as np
 
@@ -123,3 +125,44 @@ class SkyrmionNumber:
         self.avg = prev + (x - prev) / self.count
         self.var += (x - prev) * (x - self.avg)
         return (it, x, self.avg, self.var / self.count)
+
+
+class ProjectedCumulants:
+    """Per-type Binder cumulant and susceptibility (do_cumu_proj Y): plain running means over all samples and ensembles."""
+
+    def __init__(self, atype_cell, ncells, mensemble, temp, k_bolt, mub, buff=10):
+        self.atype = np.asarray(atype_cell)
+        self.nt = int(self.atype.max())
+        self.ncount = np.array([int((self.atype == it + 1).sum()) * ncells for it in range(self.nt)], dtype=np.float64)
+        self.m, self.temp, self.kb, self.mub, self.buff = mensemble, temp, k_bolt, mub, buff
+        self.n = 0
+        self.c1 = np.zeros(self.nt)
+        self.c2 = np.zeros(self.nt)
+        self.c4 = np.zeros(self.nt)
+
+    def sample(self, msum_na):
+        """msum_na(3, NA, M): sums of emomM per basis atom (asd_measure_sublattice).  Returns the rows to print
+        (count, type, <M>, <M^2>, <M^4>, U, chi) when mod(count - 1, cumu_buff) == 0, else None."""
+        msum_na = np.asarray(msum_na, dtype=np.float64)
+        u = np.zeros(self.nt)
+        chi = np.zeros(self.nt)
+        for k in range(self.m):
+            for it in range(self.nt):
+                v = msum_na[:, self.atype == it + 1, k].sum(axis=1)
+                me = float(np.sqrt(v[0] ** 2 + v[1] ** 2 + v[2] ** 2)) / self.ncount[it]
+                m2 = me * me
+                m4 = m2 * m2
+                t1 = (self.n * self.c1[it] + me) / (self.n + 1)
+                t2 = (self.n * self.c2[it] + m2) / (self.n + 1)
+                t4 = (self.n * self.c4[it] + m4) / (self.n + 1)
+                u[it] = 1.0 - (t4 / 3.0 / t2 ** 2)
+                self.c1[it], self.c2[it], self.c4[it] = t1, t2, t4
+                if self.temp > 0.0:
+                    chi[it] = (t2 - t1 ** 2) * self.mub ** 2 * self.ncount[it] / (self.kb ** 2) / self.temp
+                else:
+                    chi[it] = (t2 - t1 ** 2) * self.ncount[it] * self.mub ** 2 / self.kb
+            self.n += 1
+        count = self.n // self.m
+        if (count - 1) % self.buff == 0:
+            return [(count, it + 1, self.c1[it], self.c2[it], self.c4[it], u[it], chi[it]) for it in range(self.nt)]
+        return None
