@@ -224,3 +224,39 @@ def test_projected_cumulants_estimator_and_file(tmp_path):
     got = [r for r in asdio.read_out(os.path.join(str(tmp_path), 'projcumulants.megaTest.out')) if int(r[0]) == 211 and int(r[1]) == 2][0]
     for a, b in zip(got[1:7], [2, 2.5, 6.25, 39.0625, 0.666666667, -7.08541485e-37]):
         assert abs(a - b) <= 1e-8, got
+
+
+def test_input_edge_cases(tmp_path):
+    """Fortran-style numbers (`1.0d-16`, `.5`), logical flags written `.true.` / `T`, comment characters, unknown keywords,
+    a truncated multi-row block, and empty / ragged data files."""
+    d = str(tmp_path)
+    with open(os.path.join(d, 'posfile'), 'w') as fh:
+        fh.write('# comment line\n1 1 0.0 0.0 0.0\n\n2 1 .5 .5 0.5d0   trailing words are ignored\n')
+    with open(os.path.join(d, 'momfile'), 'w') as fh:
+        fh.write('1 1 2.0d0 0 0 1\n2 1 1.5 0.0 3.0 4.0\n')
+    with open(os.path.join(d, 'jfile'), 'w') as fh:
+        fh.write('1 1 1.0 0.0 0.0 1.0d0\n1 1 1.0 0.0 0.0 2.0\n')          # the later line overwrites the shell's value
+    with open(os.path.join(d, 'inpsd.dat'), 'w') as fh:
+        fh.write('simid averylongname\n% a comment\nncell 2 3 4\nBC P 0 p\ncell 1 0 0\n 0 1.0d0 0\n\n 0 0 1\n'
+                 'posfile ./posfile\nmomfile ./momfile\nexchange ./jfile\nsome_unknown_keyword 1 2 3\n'
+                 'timestep 1.0d-16\ndamping .5\nmap_multiple .true.\ndo_cumu y\nTemp 3.0D2\nip_nphase 2\n100 1.0 1d-16 0.1\n\n200 2.0 2d-16 0.2\n')
+    inp = asdio.read_inpsd(os.path.join(d, 'inpsd.dat'))
+    assert inp['simid'] == 'averylon' and inp['ncell'] == (2, 3, 4) and inp['bc'] == ('P', '0', 'P')
+    assert inp['timestep'] == 1.0e-16 and inp['damping'] == 0.5 and inp['temp'] == 300.0 and inp['map_multiple'] is True
+    assert inp['do_cumu'] == 'Y' and inp['ip_nphase'] == [(100, 1.0, 1e-16, 0.1), (200, 2.0, 2e-16, 0.2)]
+    assert np.array_equal(inp['cell'], np.eye(3))
+    bas, atype = asdio.read_posfile(inp['posfile'], inp['cell'], 'C')
+    assert bas.shape == (3, 2) and np.array_equal(bas[:, 1], [0.5, 0.5, 0.5]) and list(atype) == [1, 1]
+    ammom, aemom, _ = asdio.read_momfile(inp['momfile'], 2)
+    assert list(ammom) == [2.0, 1.5] and np.allclose(aemom[:, 1], [0.0, 0.6, 0.8])
+    nn, red, xc, nnt = asdio.read_pairfile(inp['exchange'], atype, bas, inp['cell'], 1, 'C', 1)
+    assert list(nn) == [1] and xc[0, 0, 0] == 2.0
+    # a block that ends early is an input error, not a silent truncation
+    with open(os.path.join(d, 'bad.dat'), 'w') as fh:
+        fh.write('ip_nphase 2\n100 1.0 1d-16 0.1\n')
+    with pytest.raises(asdio.InputError):
+        asdio.read_inpsd(os.path.join(d, 'bad.dat'))
+    # empty data file: no shells
+    open(os.path.join(d, 'empty'), 'w').close()
+    nn, red, xc, nnt = asdio.read_pairfile(os.path.join(d, 'empty'), atype, bas, inp['cell'], 1, 'C', 1)
+    assert list(nn) == [0]
