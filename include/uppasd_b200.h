@@ -186,10 +186,19 @@ int asd_mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, doub
  * (colour = f(basis atom, global cell coordinates mod period)) -- always used by a slab, where it gives one halo
  * exchange per colour and the same Markov chain for every decomposition; selectable on any device-built lattice.
  * asd_mc_colouring reports what the next sweep uses: number of colours and (layout 1) the period in cells. */
-int asd_set_mc_layout(asd_engine* e, int layout);
+int asd_set_mc_layout(asd_engine* e, int layout);   /* -1 automatic, 0, 1, 2 (block sweep, below) */
 int asd_mc_colouring(asd_engine* e, int* layout, int* ncolours, int* period3);
 /* colour (0-based) of every atom of this engine, original atom order [Natom] */
 int asd_get_mc_colours(asd_engine* e, int* colour);
+/* Layout 2 (asd_set_mc_layout(e, 2); the default of large undecomposed device-built lattices): BLOCK SWEEP -- tiles of the
+ * brick order are coloured as well, one CTA sweeps all atom colours of its tile in shared memory (asd_mc_block.cuh).
+ * order[Natom]: the 1-based atoms in a sequential visiting order that reproduces the chain of the next sweep for every
+ * layout (mc_evolve's iflip_a, montecarlo.f90:165-173): colour-parallel updates commute inside a colour class. */
+int asd_get_mc_visit_order(asd_engine* e, int* order);
+/* Test hook: the random draws of Monte Carlo sweep `sweep` exactly as the update kernels compute them from the counter-based
+ * generator: u(4,Natom,Mensemble) uniforms (Metropolis: move type, azimuth, cos(theta), acceptance; heat bath: polar draw,
+ * azimuth), g(3,Natom,Mensemble) the Gaussian trial-move numbers.  Lets a CPU restatement of mc_evolve replay a sweep. */
+int asd_debug_mc_draws(asd_engine* e, long sweep, double* u, double* g);
 
 /* On-device observables: msum(3,M) = sum_i emomM(:,i,k) (prn_averages.f90:437-447); energy[M] as above
  * (NULL to skip). */

@@ -216,8 +216,10 @@ def energy_terms(S, emomM=None):
 class SdState:
     """Mutable LLG state + work arrays for repeated orc_sd_step calls."""
 
-    def __init__(self, S, sdealgh, delta_t, damping, temp=0.0, mompar=0, temprescale=1.0, red_atom_list=None):
+    def __init__(self, S, sdealgh, delta_t, damping, temp=0.0, mompar=0, temprescale=1.0, red_atom_list=None, btorque=None):
         N, M = S['Natom'], S['Mensemble']
+        # stt /= 'N': the spin-transfer-torque field btorque(3,N,M) the integrators add (midpoint.f90:86-97, depondt.f90:100-113)
+        self.btorque = np.asfortranarray(btorque, dtype=np.float64) if btorque is not None else None
         self.S, self.sdealgh, self.delta_t, self.mompar, self.temprescale = S, sdealgh, delta_t, mompar, temprescale
         self.H = ham_struct(S)
         self.emom = S['emom'].copy(order='F')
@@ -237,11 +239,13 @@ class SdState:
         L = lib()
         S = self.S
         g = np.asfortranarray(gauss) if gauss is not None else None
+        L.orc_set_btorque(_p(self.btorque))
         L.orc_sd_step(C.byref(self.H), self.sdealgh, _p(self.emom), _p(self.emomM), _p(self.mmom), _p(self.mmom0),
                       _p(S['external_field']), _p(S['Landeg']), _p(self.lambda1), _p(self.temp),
                       _d(self.temprescale), _d(self.delta_t), self.mompar, _p(g), _d(consts(self.S)['gama']),
                       _d(consts(self.S)['k_bolt']), _d(consts(self.S)['mub']), _d(consts(self.S)['mry']), _p(self.work),
                       _p(self.frozen))
+        L.orc_set_btorque(None)
 
     def sum_moments(self):
         N, M = self.S['Natom'], self.S['Mensemble']
@@ -409,6 +413,44 @@ def mc_run(S, mode, temperature, nsweeps, seed=1, sample_every=1, burn=0, extfie
                                       _d(consts(S)['mub']), _d(consts(S)['mry']))
             ens.append(e / (N * M))
     return np.array(mags), np.array(ens), (emom, emomM, mmom)
+
+
+class McState:
+    """Mutable Monte Carlo state for replaying sweeps with EXTERNALLY supplied draws and visiting order (orc_mc_sweep is
+    mc_evolve, montecarlo.f90:44-273, with the bulk draws as arguments).  Used by the deterministic chain-parity tests: the
+    GPU's draws (asd_debug_mc_draws) and its sequential-equivalent visiting order (asd_get_mc_visit_order) go in, the chain
+    must come out identical.  dm_quirk=False selects the consistent emomM form of the DM energy (see orc_set_dm_energy_quirk)."""
+
+    def __init__(self, S, dm_quirk=True):
+        self.S = S
+        self.H = ham_struct(S)
+        self.emom = S['emom'].copy(order='F')
+        self.emomM = S['emomM'].copy(order='F')
+        self.mmom = S['mmom'].copy(order='F')
+        self.dm_quirk = dm_quirk
+
+    def sweep(self, mode, temperature, order, u, g, extfield=(0.0, 0.0, 0.0), temprescale=1.0):
+        """order: 1-based atoms in visiting order; u(4,N,M), g(3,N,M): per-ATOM draws (Metropolis: u[0:3] = trial-move
+        uniforms, u[3] = acceptance; heat bath: u[0] = polar draw, u[1] = azimuth)."""
+        L = lib()
+        S = self.S
+        N, M = S['Natom'], S['Mensemble']
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        fm = np.asfortranarray(u[0:3])
+        fg = np.asfortranarray(g)
+        # mflip / flipprob_a are indexed by the POSITION in the sweep (montecarlo.f90:236,246), the GPU keys them by atom
+        if mode == 'H':
+            mf = np.asfortranarray(u[0][order - 1, :])
+            fa = np.asfortranarray(u[1][order - 1, :])
+        else:
+            mf = None
+            fa = np.asfortranarray(u[3][order - 1, :])
+        ef = np.ascontiguousarray(extfield, dtype=np.float64)
+        L.orc_set_dm_energy_quirk(1 if self.dm_quirk else 0)
+        L.orc_mc_sweep(C.byref(self.H), C.c_char(mode.encode()), _p(order), _p(self.emomM), _p(self.emom), _p(self.mmom), _p(ef),
+                       _p(S['external_field']), _d(temperature), _d(temprescale), _p(fm), _p(fg), _p(mf), _p(fa),
+                       _d(consts(S)['k_bolt']), _d(consts(S)['mub']))
+        L.orc_set_dm_energy_quirk(1)
 
 
 # ---- topology (skyno T) ---------------------------------------------------------------------------

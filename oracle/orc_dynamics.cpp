@@ -261,7 +261,13 @@ static inline void cayley(const double* e, const double* A, double* out) {
    out[2] = et[2] * detAi;
 }
 
-// smodeulermpt (midpoint.f90:34-181), no STT/SHE/SOT torques (btorque_full = 0), Nred = Natom.
+// btorque(3,N,M): the spin-transfer-torque field of the integrators (stt /= 'N': midpoint.f90:86-97 / :242-252 copy it into
+// btorque_full, depondt.f90:100-113 / :255-262 add stt_fac*btorque to bdup).  A module array in the reference; here a module
+// pointer set by orc_set_btorque (NULL = stt 'N': btorque_full = 0).  SHE / SOT torques are not on this path.
+static const double* g_btorque = nullptr;
+void orc_set_btorque(const double* bt) { g_btorque = bt; }
+
+// smodeulermpt (midpoint.f90:34-181), Nred = Natom.
 void orc_midpoint_first(int Natom, int Mensemble, const double* Landeg, double bn, const double* lambda1_array,
                         const double* beff, const double* emom, double* emom2, double* emomM, const double* mmom,
                         double deltat, const double* ranv, double* thermal_field, double gama) {
@@ -279,10 +285,12 @@ void orc_midpoint_first(int Natom, int Mensemble, const double* Landeg, double b
          const double* e = emom + o;
          const double* b = beff + o;
          const double* r = ranv + o;
+         const double zero3[3] = {0.0, 0.0, 0.0};
+         const double* bt = g_btorque ? g_btorque + o : zero3;      // btorque_full (midpoint.f90:86-97)
          double a1[3], s1[3], A[3];
-         a1[0] = -0.0 - b[0] - lam * (e[1] * b[2] - e[2] * b[1]);
-         a1[1] = -0.0 - b[1] - lam * (e[2] * b[0] - e[0] * b[2]);
-         a1[2] = -0.0 - b[2] - lam * (e[0] * b[1] - e[1] * b[0]);
+         a1[0] = -bt[0] - b[0] - lam * (e[1] * b[2] - e[2] * b[1]);
+         a1[1] = -bt[1] - b[1] - lam * (e[2] * b[0] - e[0] * b[2]);
+         a1[2] = -bt[2] - b[2] - lam * (e[0] * b[1] - e[1] * b[0]);
          s1[0] = -r[0] - lam * (e[1] * r[2] - e[2] * r[1]);
          s1[1] = -r[1] - lam * (e[2] * r[0] - e[0] * r[2]);
          s1[2] = -r[2] - lam * (e[0] * r[1] - e[1] * r[0]);
@@ -317,10 +325,12 @@ void orc_midpoint_second(int Natom, int Mensemble, const double* Landeg, double 
          double etp[3] = {emom2[o], emom2[o + 1], emom2[o + 2]};
          const double* b = beff + o;
          const double* r = ranv + o;
+         const double zero3[3] = {0.0, 0.0, 0.0};
+         const double* bt = g_btorque ? g_btorque + o : zero3;      // btorque_full (midpoint.f90:242-252)
          double a1[3], s1[3], A[3];
-         a1[0] = -0.0 - b[0] - lam * (etp[1] * b[2] - etp[2] * b[1]);
-         a1[1] = -0.0 - b[1] - lam * (etp[2] * b[0] - etp[0] * b[2]);
-         a1[2] = -0.0 - b[2] - lam * (etp[0] * b[1] - etp[1] * b[0]);
+         a1[0] = -bt[0] - b[0] - lam * (etp[1] * b[2] - etp[2] * b[1]);
+         a1[1] = -bt[1] - b[1] - lam * (etp[2] * b[0] - etp[0] * b[2]);
+         a1[2] = -bt[2] - b[2] - lam * (etp[0] * b[1] - etp[1] * b[0]);
          s1[0] = -r[0] - lam * (etp[1] * r[2] - etp[2] * r[1]);
          s1[1] = -r[1] - lam * (etp[2] * r[0] - etp[0] * r[2]);
          s1[2] = -r[2] - lam * (etp[0] * r[1] - etp[1] * r[0]);
@@ -378,6 +388,7 @@ void orc_depondt_first(int Natom, int Mensemble, const double* lambda1_array, co
          const double Dp = (2.0 * lam * k_bolt) / (delta_t * gama * mub);
          const double sigma = std::sqrt(Dp * temprescale * Temp_array[i - 1] / m);
          double bloc[3], bdup[3] = {0.0, 0.0, 0.0};
+         if (g_btorque) for (int a = 0; a < 3; a++) bdup[a] = bdup[a] + 1.0 * g_btorque[o + a];   // bdup = 0 + stt_fac*btorque (depondt.f90:100-113, :255-262)
          for (int a = 0; a < 3; a++) {
             btherm[o + a] = btherm[o + a] * sigma;
             bloc[a] = beff[o + a] + btherm[o + a];
@@ -411,6 +422,7 @@ void orc_depondt_second(int Natom, int Mensemble, const double* lambda1_array, c
          const size_t o = 3 * ((i - 1) + (size_t)N * (k - 1));
          const double lam = lambda1_array[i - 1];
          double bloc[3], bdup[3] = {0.0, 0.0, 0.0};
+         if (g_btorque) for (int a = 0; a < 3; a++) bdup[a] = bdup[a] + 1.0 * g_btorque[o + a];   // bdup = 0 + stt_fac*btorque (depondt.f90:100-113, :255-262)
          for (int a = 0; a < 3; a++) bloc[a] = beff[o + a] + btherm[o + a];
          double* e = emom + o;
          bdup[0] = bdup[0] + bloc[0] + lam * e[1] * bloc[2] - lam * e[2] * bloc[1];
@@ -512,6 +524,13 @@ void orc_sum_moments(int Natom, int Mensemble, const double* emomM, double* m /*
 }
 
 // ---- Monte Carlo -------------------------------------------------------------------------------
+// The current-state DM term of calculate_energy mixes emom and emomM (montecarlo_common.f90:611-616); identical to the
+// consistent form for |m| = 1.  orc_set_dm_energy_quirk(0) selects the consistent form -m_i . (m_j x D) with emomM only, which
+// is what the product computes (documented deviation): used by the deterministic chain-parity tests on systems
+// with |m| /= 1.  Default 1 = the reference as written.
+static int g_dm_quirk = 1;
+void orc_set_dm_energy_quirk(int on) { g_dm_quirk = on; }
+
 // calculate_energy (montecarlo_common.f90:431-865) for exchange(+DM+BQ+anisotropy+Zeeman), returns de.
 // Reference quirk kept: the DM current-state term mixes emom and emomM (:611-616).
 static double mc_delta_e(const OrcHam& H, const double* emomM, const double* emom, const double* mmom, long iflip,
@@ -559,7 +578,7 @@ static double mc_delta_e(const OrcHam& H, const double* emomM, const double* emo
       }
    }
    if (H.do_dm == 1) {
-      const double* ui = eU + 3 * (iflip - 1);
+      const double* ui = g_dm_quirk ? eU + 3 * (iflip - 1) : mi;
       for (int j = 1; j <= H.dmlistsize[ih - 1]; j++) {
          const double* D = H.dm_vect + 3 * ((j - 1) + (size_t)H.max_no_dmneigh * (ih - 1));
          const double* mj = eM + 3 * ((long)H.dmlist[(j - 1) + (size_t)H.max_no_dmneigh * (iflip - 1)] - 1);

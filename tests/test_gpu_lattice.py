@@ -269,3 +269,55 @@ def test_fixed_moment_list_in_the_run_kernel():
         for _ in range(10):
             st.step()
         assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12, solver
+
+
+@pytest.mark.parametrize('solver', [1, 5])
+def test_headline_launch_geometry_64_against_oracle(solver, monkeypatch):
+    """bcc Fe 64^3 (524 288 spins, 512 tiles of 1024 slots: several waves of CTAs, L2 look-ahead one wave ahead, dependent
+    launches) -- the launch geometry of the headline benchmark, T = 0, 10 steps, both solvers, against the oracle to 1e-12."""
+    import bench
+    monkeypatch.delenv('ASD_RESIDENT', raising=False)
+    nc = (64, 64, 64)
+    S = bench.oracle_bcc(nc)
+    e, n = bench.bcc_engine(nc, solver, 0.0, 0.5, 1, 0, 0)
+    info = e.layout_info()
+    assert info['runs'] == 4 and info['tile_slots'] == 1024, info
+    assert np.abs(e.get_moments()[0] - S['emom']).max() <= 1e-15
+    st = orc.SdState(S, solver, 1e-16, 0.5)
+    e.sd_steps(10)
+    for _ in range(10):
+        st.step()
+    err = float(np.abs(e.get_moments()[0] - st.emom).max())
+    assert err <= 1e-12, (solver, err)
+
+
+def test_headline_128_cubed_against_oracle_and_direct_kernel(monkeypatch):
+    """The benchmark configuration itself: bcc Fe 128^3 = 4 194 304 spins, 4096 tiles, 28 waves.  (1) T = 0, midpoint, 5 steps
+    against the oracle to 1e-12; (2) 300 K, both solvers: the run-compressed kernel against the direct-gather kernel
+    (ASD_STAGED=0: no tiles, no run table, plain 256-bit gathers) with the same counter-based noise -- 1e-12."""
+    import bench
+    nc = (128, 128, 128)
+    S = bench.oracle_bcc(nc)
+    e, n = bench.bcc_engine(nc, 1, 0.0, 0.5, 1, 0, 0)
+    assert e.layout_info()['runs'] == 4 and e.layout_info()['tile_slots'] == 1024
+    st = orc.SdState(S, 1, 1e-16, 0.5)
+    e.sd_steps(5)
+    for _ in range(5):
+        st.step()
+    err = float(np.abs(e.get_moments()[0] - st.emom).max())
+    assert err <= 1e-12, err
+    del S, st
+    e.close()
+    for solver in (1, 5):
+        monkeypatch.delenv('ASD_STAGED', raising=False)
+        er, _ = bench.bcc_engine(nc, solver, 300.0, 0.5, 1, 0, 0)
+        monkeypatch.setenv('ASD_STAGED', '0')
+        ed, _ = bench.bcc_engine(nc, solver, 300.0, 0.5, 1, 0, 0)
+        assert er.layout_info()['runs'] == 4 and ed.layout_info()['staged'] == 0
+        a0 = er.get_moments()[0]
+        er.sd_steps(8)
+        ed.sd_steps(8)
+        a, b = er.get_moments()[0], ed.get_moments()[0]
+        assert np.abs(a - b).max() <= 1e-12, (solver, np.abs(a - b).max())
+        assert np.abs(a - a0).max() > 1e-6                      # the spins did move
+        er.close(); ed.close()

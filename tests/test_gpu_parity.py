@@ -569,3 +569,61 @@ def test_resident_kernel_with_the_largest_cluster(monkeypatch):
     for _ in range(30):
         st.step()
     assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12
+
+
+@pytest.mark.parametrize('alg', [1, 5])
+@pytest.mark.parametrize('path', ['resident', 'stage', 'lattice'])
+def test_spin_transfer_torque_field(alg, path, monkeypatch):
+    """btorque /= 0 (stt /= 'N'): midpoint adds -btorque to a1 in both half steps (midpoint.f90:86-97,134-136, :242-252),
+    Depondt adds +btorque to bdup (depondt.f90:100-113,152-154, :255-262).  Every launch path: the resident small-system
+    kernel, the one-atom-per-thread stage launches, and the run kernel of a device-built lattice (per-slot arrays)."""
+    from util import fixture_args, lattice_engine
+    monkeypatch.setenv('ASD_RESIDENT', '1' if path == 'resident' else '0')
+    if path == 'lattice':
+        args = fixture_args('bccfe_cuda', mens=2, ncell=(64, 4, 4), do_reduced='Y')
+    else:
+        args = fixture_args('kagome', mens=2)
+    S = orc.build_system(*args)
+    inp = args[0]
+    rng = np.random.default_rng(12)
+    e0 = rng.normal(size=S['emom'].shape); e0 /= np.sqrt((e0 ** 2).sum(axis=0))
+    S['emom'] = np.asfortranarray(e0); S['emomM'] = np.asfortranarray(e0 * S['mmom'][None])
+    beff, _ = orc.effective_field(S)
+    bt = np.asfortranarray(rng.normal(size=S['emom'].shape) * 0.3 * np.abs(beff).max())     # a torque comparable with the field
+    from uppasd_b200 import host
+    if path == 'lattice':
+        # lattice_engine commits: the torque must be set before (asd_set_torque invalidates the commit)
+        from uppasd_b200 import lattice
+        e = host.Engine()
+        c = orc.consts(S)
+        e.set_constants(c['gama'], c['k_bolt'], c['mub'], c['mry'])
+        e.set_system(S['Natom'], 2, S['nHam'], S['aHam'])
+        nn, red, xc, nntype = args[6](S)
+        ns, ca, cs, sh = lattice.stencil(inp['cell'], S['bas'], S['atype_inp'], nn, red, inp['sym'], nntype)
+        cp = lattice.couplings(ns, ca, sh, S['atype_inp'], xc, S['ammom_inp'], c['mry'], c['mub'])
+        e.build_lattice_table(0, S['NA'], inp['ncell'], inp['bc'], ns, ca, cs, cp)
+        e.set_torque(bt)
+        e.set_llg(alg, inp['timestep'], landeg=S['Landeg'], lambda1=0.2, temp=0.0)
+        e.set_moments(S['emom'], S['mmom'])
+        e.commit()
+        assert e.layout_info()['runs'] == 4
+    else:
+        e = host.Engine()
+        c = orc.consts(S)
+        e.set_constants(c['gama'], c['k_bolt'], c['mub'], c['mry'])
+        e.set_system(S['Natom'], 2, S['nHam'], S['aHam'])
+        e.set_exchange(S['exchange']['list'], S['exchange']['listsize'], S['exchange']['coup'])
+        e.set_dm(S['dm']['list'], S['dm']['listsize'], S['dm']['coup'])
+        e.set_external_field(S['external_field'])
+        e.set_torque(bt)
+        e.set_llg(alg, inp['timestep'], landeg=S['Landeg'], lambda1=0.2, temp=0.0)
+        e.set_moments(S['emom'], S['mmom'], S['mmom0'])
+        e.commit()
+    st = orc.SdState(S, alg, inp['timestep'], 0.2, btorque=bt)
+    st0 = orc.SdState(S, alg, inp['timestep'], 0.2)
+    e.sd_steps(50)
+    for _ in range(50):
+        st.step(); st0.step()
+    emom = e.get_moments()[0]
+    assert np.abs(st.emom - st0.emom).max() > 1e-6          # the torque matters at this amplitude
+    assert np.abs(emom - st.emom).max() <= 1e-12, (alg, path, np.abs(emom - st.emom).max())

@@ -10,7 +10,7 @@ DEPS = [os.path.join(HERE, 'csrc', f) for f in os.listdir(os.path.join(HERE, 'cs
 OUT = os.environ.get('ASD_LIB_OUT') or os.path.join(HERE, 'libuppasd_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math=false',
-         '-Xcompiler', '-fPIC', '-shared', '-ccbin', 'g++']
+         '-Xcompiler', '-fPIC', '-shared', '-ccbin', 'g++', '-split-compile', '0']   # split-compile: kernels of the one TU in parallel
 
 
 def build(force=False, verbose=False):

@@ -60,6 +60,8 @@ SYMBOLS = {
     'asd_set_mc_layout': (C.c_int, [vp, C.c_int]),
     'asd_mc_colouring': (C.c_int, [vp, c_int_p, c_int_p, c_int_p]),
     'asd_get_mc_colours': (C.c_int, [vp, vp]),
+    'asd_get_mc_visit_order': (C.c_int, [vp, vp]),
+    'asd_debug_mc_draws': (C.c_int, [vp, C.c_long, vp, vp]),
     'asd_measure': (C.c_int, [vp, vp, vp]),
     'asd_energy_terms': (C.c_int, [vp, vp]),
     'asd_get_atoms': (C.c_int, [vp, C.c_int, vp, vp]),

@@ -427,6 +427,37 @@ __device__ __forceinline__ void bq_term(double jb, double mx, double my, double 
    qz = fma(c, mz, qz);
 }
 
+// single-ion anisotropy field of slot i at the moment (ox, oy, oz) (hamiltonianactions.f90:225-239, 842-919): the uniaxial
+// part and the cubic part of taniso 2 join the bilinear field f, the cubic part of taniso 7 (times sb) the "q" field
+template <bool REDUCED>
+__device__ __forceinline__ void aniso_field(const Tables& t, int i, int ih, double ox, double oy, double oz, double& fx, double& fy,
+                                            double& fz, double& qx, double& qy, double& qz) {
+   const int Npad = t.Npad;
+   if (t.do_aniso) {
+      const bool rows = REDUCED && t.aniso_rows;
+      const int ta = rows ? (int)t.aniso_small[ih][0] : __ldg(t.taniso + i);
+      if (ta == 1 || ta == 2 || ta == 7) {
+         const double k1 = rows ? t.aniso_small[ih][1] : __ldg(t.kaniso + i), k2 = rows ? t.aniso_small[ih][2] : __ldg(t.kaniso + Npad + i);
+         if (ta == 1 || ta == 7) {
+            const double ex = rows ? t.aniso_small[ih][3] : __ldg(t.eaniso + i), ey = rows ? t.aniso_small[ih][4] : __ldg(t.eaniso + Npad + i),
+                         ez = rows ? t.aniso_small[ih][5] : __ldg(t.eaniso + 2 * (size_t)Npad + i);
+            const double tt1 = ox * ex + oy * ey + oz * ez;
+            const double tt2 = k1 + 2.0 * k2 * (1.0 - tt1 * tt1);
+            const double tt3 = 2.0 * tt1 * tt2;
+            fx -= tt3 * ex; fy -= tt3 * ey; fz -= tt3 * ez;
+         }
+         if (ta == 2 || ta == 7) {
+            const double x2 = ox * ox, y2 = oy * oy, z2 = oz * oz;
+            const double cx = 2.0 * k1 * ox * (y2 + z2) + 2.0 * k2 * ox * (y2 * z2);
+            const double cy = 2.0 * k1 * oy * (z2 + x2) + 2.0 * k2 * oy * (z2 * x2);
+            const double cz = 2.0 * k1 * oz * (x2 + y2) + 2.0 * k2 * oz * (x2 * y2);
+            if (ta == 2) { fx += cx; fy += cy; fz += cz; }
+            else { const double s = rows ? t.aniso_small[ih][6] : __ldg(t.sb + i); qx += cx * s; qy += cy * s; qz += cz * s; }
+         }
+      }
+   }
+}
+
 // PAIRS = false: every pair sum (Heisenberg, DM, BQ) was accumulated by the caller into bs[] / bq[] (resident kernel).
 template <bool REDUCED, bool EXCH = true, int CH = ASD_CHUNK, bool XS = false, bool PAIRS = true>
 __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __restrict__ S, int i, int ih,
@@ -533,29 +564,7 @@ __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __res
       }
    }
    // ---- single-ion anisotropy (hamiltonianactions.f90:225-239, 842-919); uses the FULL moment ----
-   if (t.do_aniso) {
-      const bool rows = REDUCED && t.aniso_rows;
-      const int ta = rows ? (int)t.aniso_small[ih][0] : __ldg(t.taniso + i);
-      if (ta == 1 || ta == 2 || ta == 7) {
-         const double k1 = rows ? t.aniso_small[ih][1] : __ldg(t.kaniso + i), k2 = rows ? t.aniso_small[ih][2] : __ldg(t.kaniso + Npad + i);
-         if (ta == 1 || ta == 7) {
-            const double ex = rows ? t.aniso_small[ih][3] : __ldg(t.eaniso + i), ey = rows ? t.aniso_small[ih][4] : __ldg(t.eaniso + Npad + i),
-                         ez = rows ? t.aniso_small[ih][5] : __ldg(t.eaniso + 2 * (size_t)Npad + i);
-            const double tt1 = ox * ex + oy * ey + oz * ez;
-            const double tt2 = k1 + 2.0 * k2 * (1.0 - tt1 * tt1);
-            const double tt3 = 2.0 * tt1 * tt2;
-            fx -= tt3 * ex; fy -= tt3 * ey; fz -= tt3 * ez;
-         }
-         if (ta == 2 || ta == 7) {
-            const double x2 = ox * ox, y2 = oy * oy, z2 = oz * oz;
-            const double cx = 2.0 * k1 * ox * (y2 + z2) + 2.0 * k2 * ox * (y2 * z2);
-            const double cy = 2.0 * k1 * oy * (z2 + x2) + 2.0 * k2 * oy * (z2 * x2);
-            const double cz = 2.0 * k1 * oz * (x2 + y2) + 2.0 * k2 * oz * (x2 * y2);
-            if (ta == 2) { fx += cx; fy += cy; fz += cz; }
-            else { const double s = rows ? t.aniso_small[ih][6] : __ldg(t.sb + i); qx += cx * s; qy += cy * s; qz += cz * s; }
-         }
-      }
-   }
+   aniso_field<REDUCED>(t, i, ih, ox, oy, oz, fx, fy, fz, qx, qy, qz);
    bs[0] = fx; bs[1] = fy; bs[2] = fz;
    bq[0] = qx; bq[1] = qy; bq[2] = qz;
 }

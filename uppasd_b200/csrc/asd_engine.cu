@@ -23,6 +23,7 @@
 #include "../../include/uppasd_b200.h"
 #include "asd_device.cuh"
 #include "asd_mc.cuh"
+#include "asd_mc_block.cuh"
 #include "asd_tiles.cuh"
 #include "asd_runs.cuh"
 #include "asd_lattice.cuh"
@@ -139,8 +140,20 @@ struct Stencil {
    bool present() const { return maxslot > 0; }
 };
 
+// tables of the Monte Carlo block sweep (asd_mc_block.cuh), built lazily on the SD (brick) layout of a device-built lattice
+struct McBlockState {
+   bool tried = false, on = false;
+   int ts = 0, ucap = 0, ncol = 0, ntile = 0;
+   size_t smem = 0;
+   std::vector<int> class_first, class_count, h_tilelist;   // tile-colour classes: ranges of h_tilelist
+   DevBuf<int> ulist, ucount, cstart, tilelist;
+   DevBuf<uint4> nl16, dm16, bq16;
+   DevBuf<unsigned short> selfpos, corder;
+};
+
 struct asd_engine {
    int device = 0;
+   McBlockState mcb;
    Slab slab;
    cudaStream_t stream = nullptr;
    // constants
@@ -214,6 +227,11 @@ static int slab_push_state(asd_engine* e);
 static int lattice_colours(asd_engine* e);
 static int fill_lattice_desc(asd_engine* e, int NA, int N1, int N2, int N3l, int N3g, const int* periodic, bool reduced);
 static bool has_lattice(const asd_engine* e) { return e->lattice_built || e->lat_ordered; }
+static bool mc_block_candidate(const asd_engine* e);
+static int mc_block_prepare(asd_engine* e);
+static int mc_sweeps_block(asd_engine* e, McParams& p, long nsweeps, long first_sweep);
+static int mc_block_visit_order(asd_engine* e, int* order);
+template <class K> static void allow_smem(K kernel, size_t bytes);
 
 // staged tile path: gather lists + 16-bit neighbour table (asd_tiles.cuh).  Leaves t.staged = 0 when a tile would
 // need more than TILE_UMAX unique slots (layout without locality) or when switched off (ASD_STAGED=0).
@@ -746,6 +764,18 @@ static int upload_state(asd_engine* e, Layout& L) {
    return upload_state_from(e, L, e->h_emom.data(), e->h_mmom.data(), e->h_mmom0.empty() ? nullptr : e->h_mmom0.data());
 }
 
+// A halo wait that timed out (halo_wait_kernel) leaves the device flag sb.err set: every entry point that synchronises the
+// stream reads it, so that a lost or slow peer surfaces as an error code instead of silently stale halos.
+static int slab_check(asd_engine* e) {
+   Slab& sb = e->slab;
+   if (!sb.on || !sb.err.p) return 0;
+   int flag = 0;
+   CU(cudaMemcpyAsync(&flag, sb.err.p, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+   CU(cudaStreamSynchronize(e->stream));
+   if (flag) return fail(-12, "slab: timed out waiting for the halo of the %s neighbour; the state is not valid", flag == 1 ? "lower" : "upper");
+   return 0;
+}
+
 static int download_state(asd_engine* e, Layout& L, double* emom, double* emomM, double* mmom) {
    const size_t NM = (size_t)e->N * e->M;
    int r;
@@ -762,7 +792,7 @@ static int download_state(asd_engine* e, Layout& L, double* emom, double* emomM,
    if (emomM) CU(cudaMemcpyAsync(emomM, e->io_eM.p, 3 * NM * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
    if (mmom) CU(cudaMemcpyAsync(mmom, e->io_m.p, NM * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
    CU(cudaStreamSynchronize(e->stream));
-   return 0;
+   return slab_check(e);
 }
 
 // the device holds the only copy of the state (direct upload): bring it back before a layout is rebuilt
@@ -1033,7 +1063,7 @@ static int launch_resident(asd_engine* e, Layout& L, const LlgParams& p, const R
                     : launch_resident2<SOLVER, false>(e, t, p, rp, nsteps, first_step);
 }
 
-static int sd_steps(asd_engine* e, long nsteps, long first_step, cudaEvent_t* ev /*optional per-stage events*/) {
+static int sd_steps(asd_engine* e, long nsteps, long first_step) {
    int r = ensure_layout(e, 1);
    if (r) return r;
    Layout& L = e->sd;
@@ -1063,7 +1093,6 @@ static int sd_steps(asd_engine* e, long nsteps, long first_step, cudaEvent_t* ev
       else { launch_stage<5, 1>(e, L, p); launch_stage<5, 2>(e, L, p); }
    }
    if (nsteps > 0) { e->msum_fresh = (p.frozen == nullptr); e->msum_ntile = ntile; }
-   (void)ev;
    CU(cudaGetLastError());
    return 0;
 }
@@ -1090,7 +1119,7 @@ static int measure(asd_engine* e, Layout& L, double* msum, double* energy) {
       CU(cudaMemcpyAsync(h, e->red.p, (size_t)e->M * 4 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
       CU(cudaStreamSynchronize(e->stream));
       for (int k = 0; k < e->M; k++) for (int a = 0; a < 3; a++) msum[3 * k + a] = h[4 * k + a];
-      return 0;
+      return slab_check(e);
    }
    const int nblk = std::min(1184, (L.Npad + 255) / 256);
    if ((r = e->part.alloc((size_t)e->M * nblk * 4))) return r;
@@ -1116,7 +1145,7 @@ static int measure(asd_engine* e, Layout& L, double* msum, double* energy) {
       if (msum) for (int a = 0; a < 3; a++) msum[3 * k + a] = h[4 * k + a];
       if (energy) energy[k] = h[4 * k + 3] * e->mub / e->mry;
    }
-   return 0;
+   return slab_check(e);
 }
 
 // Monte Carlo on the lattice (brick) layout with a periodic colouring: the path of a slab-decomposed supercell
@@ -1166,6 +1195,7 @@ static int mc_sweeps_tiles(asd_engine* e, McParams& p, long nsweeps, long first_
 static bool mc_on_tiles(const asd_engine* e) {
    if (!e->lattice_built) return false;
    if (e->slab.on) return true;
+   if (e->mc_layout == 2) return false;      // block sweep requested but not applicable: colour-major layout
    if (e->mc_layout >= 0) return e->mc_layout == 1;
    const char* env = std::getenv("ASD_MC_TILES");
    return env && atoi(env) != 0;
@@ -1180,7 +1210,15 @@ static int mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, d
    p.mode = mode; p.temperature = temperature; p.temprescale = temprescale; p.k_bolt = e->k_bolt; p.mub = e->mub;
    for (int a = 0; a < 3; a++) p.extfield[a] = extfield ? extfield[a] : 0.0;
    p.seed = e->seed ^ 0x5bd1e995u;
+   // delta=(2.0/25.0)*(k_bolt*temperature/mub)**(0.20_dblprec) (montecarlo.f90:142): 2.0/25.0 is a default-real constant
+   // expression in the Fortran, i.e. the single-precision 0.08; ignores temprescale like the reference
+   p.delta = (double)(2.0f / 25.0f) * std::pow(e->k_bolt * temperature / e->mub, 0.20);
    e->msum_fresh = false;
+   if (mc_block_candidate(e)) {
+      int rb = mc_block_prepare(e);
+      if (rb) return rb;
+      if (e->mcb.on) return mc_sweeps_block(e, p, nsweeps, first_sweep);
+   }
    if (mc_on_tiles(e)) return mc_sweeps_tiles(e, p, nsweeps, first_sweep);
    int r = ensure_layout(e, 2);
    if (r) return r;
@@ -1515,6 +1553,7 @@ int asd_commit(asd_engine* e) {
       if (r) return r;
    }
    e->sd_built = true; e->mc_built = false;
+   e->mcb.tried = false; e->mcb.on = false;
    e->committed = true;
    if (e->state_layout != 0) e->state_layout = 0;
    return 0;
@@ -1559,7 +1598,7 @@ int asd_effective_field(asd_engine* e, double* beff, double* beff1, double* beff
 
 int asd_sd_steps(asd_engine* e, long nsteps, long first_step) {
    CU(cudaSetDevice(e->device));
-   return sd_steps(e, nsteps, first_step, nullptr);
+   return sd_steps(e, nsteps, first_step);
 }
 
 int asd_mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, double temperature, double temprescale,
@@ -1569,7 +1608,8 @@ int asd_mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, doub
 }
 
 int asd_set_mc_layout(asd_engine* e, int layout) {
-   if (layout != 0 && layout != 1) return fail(-1, "MC layout must be 0 (colour-major) or 1 (lattice tiles)");
+   if (layout < -1 || layout > 2) return fail(-1, "MC layout must be -1 (automatic), 0 (colour-major), 1 (lattice tiles) or 2 (block sweep)");
+   if (layout == 2 && (!e->lattice_built || e->slab.on)) return fail(-2, "the block sweep needs an undecomposed device-built lattice (asd_build_lattice_table)");
    if (layout == 1 && !e->lattice_built) return fail(-2, "the lattice MC layout needs a device-built lattice (asd_build_lattice_table)");
    if (layout == 0 && e->slab.on) return fail(-5, "a slab runs Monte Carlo on the lattice layout only");
    e->mc_layout = layout;
@@ -1580,8 +1620,9 @@ int asd_mc_colouring(asd_engine* e, int* layout, int* ncolours, int* period3) {
    CU(cudaSetDevice(e->device));
    int r = mc_sweeps(e, 'M', 0, 1, 1.0, 1.0, nullptr);   // builds the layout / colouring, runs nothing
    if (r) return r;
-   const bool tiles = mc_on_tiles(e);
-   if (layout) *layout = tiles ? 1 : 0;
+   const bool block = mc_block_candidate(e) && e->mcb.on;
+   const bool tiles = block || mc_on_tiles(e);
+   if (layout) *layout = block ? 2 : tiles ? 1 : 0;
    if (ncolours) *ncolours = tiles ? e->lat_ncol : (int)e->mc.colour_first.size();
    if (period3) for (int a = 0; a < 3; a++) period3[a] = tiles ? e->lat_period[a] : 0;
    return 0;
@@ -1591,7 +1632,7 @@ int asd_get_mc_colours(asd_engine* e, int* colour) {
    CU(cudaSetDevice(e->device));
    int r = mc_sweeps(e, 'M', 0, 1, 1.0, 1.0, nullptr);
    if (r) return r;
-   if (mc_on_tiles(e)) {
+   if ((mc_block_candidate(e) && e->mcb.on) || mc_on_tiles(e)) {
       Layout& L = e->sd;
       if ((r = host_orig(e, L))) return r;
       std::vector<unsigned char> c(L.t.Nown);
@@ -1603,6 +1644,60 @@ int asd_get_mc_colours(asd_engine* e, int* colour) {
          for (int s = L.colour_first[c]; s < L.colour_first[c] + L.colour_count[c]; s++)
             if (L.orig[s] >= 0) colour[L.orig[s]] = (int)c;
    }
+   return 0;
+}
+
+int asd_get_mc_visit_order(asd_engine* e, int* order) {
+   CU(cudaSetDevice(e->device));
+   int r = mc_sweeps(e, 'M', 0, 1, 1.0, 1.0, nullptr);   // builds the layout / colouring, runs nothing
+   if (r) return r;
+   if (mc_block_candidate(e) && e->mcb.on) return mc_block_visit_order(e, order);
+   size_t n = 0;
+   if (mc_on_tiles(e)) {
+      // one launch per colour over the lattice order: colour by colour, slots ascending
+      Layout& L = e->sd;
+      if ((r = host_orig(e, L))) return r;
+      std::vector<unsigned char> c(L.t.Nown);
+      CU(cudaMemcpy(c.data(), e->lat_col.p, c.size(), cudaMemcpyDeviceToHost));
+      for (int col = 0; col < e->lat_ncol; col++)
+         for (int s = 0; s < L.t.Nown; s++) if (L.orig[s] >= 0 && c[s] == col) order[n++] = L.orig[s] + 1;
+   } else {
+      Layout& L = e->mc;
+      for (int s = 0; s < L.Npad; s++) if (L.orig[s] >= 0) order[n++] = L.orig[s] + 1;   // colour classes are slot ranges
+   }
+   if (n != (size_t)e->N) return fail(-5, "internal: visiting order covers %zu of %d atoms", n, e->N);
+   return 0;
+}
+
+// the draws of one sweep, exactly as the update kernels compute them (test hook: a CPU restatement of mc_evolve replays a sweep with them)
+__global__ void mc_draws_kernel(int N, int M, unsigned long long seed, unsigned long long sweep, unsigned int atom_offset,
+                                unsigned int ens_offset, double* __restrict__ u, double* __restrict__ g) {
+   const int o = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+   if (o >= N) return;
+   double uu[4], g0, g1, g2;
+   uniform4(seed, (uint32_t)o + atom_offset, (uint32_t)k + ens_offset, sweep, 1u, uu);
+   gauss3f(seed, (uint32_t)o + atom_offset, (uint32_t)k + ens_offset, sweep, 2u, g0, g1, g2);
+   const size_t q = (size_t)o + (size_t)N * k;
+   for (int a = 0; a < 4; a++) u[4 * q + a] = uu[a];
+   g[3 * q] = g0; g[3 * q + 1] = g1; g[3 * q + 2] = g2;
+}
+
+int asd_debug_mc_draws(asd_engine* e, long sweep, double* u, double* g) {
+   if (e->N == 0) return fail(-2, "asd_set_system must be called first");
+   CU(cudaSetDevice(e->device));
+   const size_t NM = (size_t)e->N * e->M;
+   DevBuf<double> du, dg;
+   int r;
+   if ((r = du.alloc(4 * NM))) return r;
+   if ((r = dg.alloc(3 * NM))) return r;
+   const unsigned int aoff = e->lattice_built ? e->sd.t.atom_offset : 0u;
+   mc_draws_kernel<<<dim3((e->N + 255) / 256, e->M), 256, 0, e->stream>>>(e->N, e->M, e->seed ^ 0x5bd1e995u, (unsigned long long)sweep, aoff,
+                                                                        e->ens_offset, du.p, dg.p);
+   e->launches++;
+   CU(cudaGetLastError());
+   CU(cudaMemcpyAsync(u, du.p, 4 * NM * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   CU(cudaMemcpyAsync(g, dg.p, 3 * NM * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+   CU(cudaStreamSynchronize(e->stream));
    return 0;
 }
 
@@ -1621,7 +1716,7 @@ int asd_time_sd_steps(asd_engine* e, long nsteps, long first_step, float* total_
    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
    CU(cudaStreamSynchronize(e->stream));
    CU(cudaEventRecord(a, e->stream));
-   r = sd_steps(e, nsteps, first_step, nullptr);
+   r = sd_steps(e, nsteps, first_step);
    CU(cudaEventRecord(b, e->stream));
    CU(cudaEventSynchronize(b));
    if (total_ms) CU(cudaEventElapsedTime(total_ms, a, b));
@@ -1818,13 +1913,17 @@ int asd_slab_connect_ipc(asd_engine* e, const void* lower, const void* upper) {
    if (!sb.on || !e->committed) return fail(-11, "slab: asd_set_slab + asd_commit first");
    CU(cudaSetDevice(e->device));
    const cudaIpcMemHandle_t* hs[2] = {(const cudaIpcMemHandle_t*)lower, (const cudaIpcMemHandle_t*)upper};
+   // a reconnect (e.g. after a second asd_commit) closes the mappings of the previous connection first
+   for (int q = 0; q < sb.n_opened; q++) cudaIpcCloseMemHandle(sb.opened[q]);
+   sb.n_opened = 0;
+   sb.connected = false;
    const bool same = memcmp(lower, upper, 3 * sizeof(cudaIpcMemHandle_t)) == 0;   // two slabs: one neighbour on both sides
    for (int side = 0; side < 2; side++) {
       if (side == 1 && same) { sb.peer_cur[1] = sb.peer_cur[0]; sb.peer_pred[1] = sb.peer_pred[0]; sb.peer_flags[1] = sb.peer_flags[0]; break; }
       void* p[3];
       for (int q = 0; q < 3; q++) {
          CU(cudaIpcOpenMemHandle(&p[q], hs[side][q], cudaIpcMemLazyEnablePeerAccess));
-         sb.opened[sb.n_opened++] = p[q];
+         if (sb.n_opened < 6) sb.opened[sb.n_opened++] = p[q];
       }
       sb.peer_cur[side] = (SpinVec*)p[0]; sb.peer_pred[side] = (SpinVec*)p[1]; sb.peer_flags[side] = (unsigned long long*)p[2];
    }
@@ -1877,9 +1976,10 @@ int asd_layout_info(asd_engine* e, int* info5 /* 6 ints */) {
 }
 
 long asd_launch_count(asd_engine* e) { return e->launches; }
-int asd_synchronize(asd_engine* e) { CU(cudaSetDevice(e->device)); CU(cudaStreamSynchronize(e->stream)); return 0; }
+int asd_synchronize(asd_engine* e) { CU(cudaSetDevice(e->device)); CU(cudaStreamSynchronize(e->stream)); return slab_check(e); }
 
 }  // extern "C"
 
 #include "asd_lattice_host.inl"
+#include "asd_mc_block_host.inl"
 #include "asd_legacy.inl"

@@ -160,6 +160,7 @@ int asd_build_lattice_table(asd_engine* e, int kind, int NA, int N1, int N2, int
       S.cell_atom.assign(cell_atom, cell_atom + (size_t)NA * maxslot);
       S.cell_shift.assign(cell_shift, cell_shift + (size_t)3 * NA * maxslot);
       e->lat_ncol = 0;
+      e->mcb.tried = false; e->mcb.on = false;
    }
    DevBuf<int> d_nslot, d_catom, d_cshift;
    DevBuf<double> d_coupl;
@@ -338,8 +339,8 @@ static int materialise_host_tables(asd_engine* e) {
 // GLOBAL cell coordinates modulo a small period (p1, p2, p3), so every slab of a decomposed supercell derives the
 // same colouring without communication.  The quotient graph (p1*p2*p3*NA sites, edges = the union of the stencils of
 // all tables, symmetrised) is coloured greedily on the host; a proper colouring of the quotient lifts to a proper
-// colouring of the supercell as long as no stencil shift is a multiple of the period in every direction, which
-// p_a > max |shift_a| guarantees.  Periods must divide the extent of periodic directions.  Among the admissible
+// colouring of the supercell as long as no edge becomes a self-loop of the quotient (checked for every candidate period;
+// p_a > max |shift_a| guarantees it).  Periods must divide the extent of periodic directions.  Among the admissible
 // periods the one with the fewest colours wins.
 static int lattice_colours(asd_engine* e) {
    const LatticeDesc& d = e->lat;
@@ -355,7 +356,10 @@ static int lattice_colours(asd_engine* e) {
    std::vector<int> cand[3];
    for (int a = 0; a < 3; a++) {
       if (Ng[a] == 1 || reach[a] == 0) { cand[a].push_back(1); continue; }
-      for (int p = reach[a] + 1; p <= std::min(Ng[a], 2 * reach[a] + 4); p++)
+      // periods not larger than the reach are admissible too when no shift aliases an atom with itself in the quotient (the
+      // check below rejects those that do): bcc Fe with 4 shells has reach 2 and the 8-colouring of period (2, 2, 2).  Ties
+      // keep the smallest x period (loops ascend): the block sweep lists an x-run residue class by residue class.
+      for (int p = 2; p <= std::min(Ng[a], 2 * reach[a] + 4); p++)
          if (!d.periodic[a] || Ng[a] % p == 0) cand[a].push_back(p);
       if (cand[a].empty()) {
          // no small divisor: the whole extent is always a valid period (small supercells may alias neighbours, which

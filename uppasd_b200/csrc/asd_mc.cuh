@@ -27,6 +27,7 @@ struct McParams {
    unsigned long long seed, sweep;
    int first, count;  // device-slot range [first, first+count) of this colour class (colour-major layout)
    int colour;        // colour updated by this launch (lattice layout, mc_tile_kernel)
+   double delta;      // cone width of the Gaussian trial move (montecarlo.f90:142), evaluated once on the host
 };
 
 #ifndef ASD_MC_MINB
@@ -92,9 +93,7 @@ __device__ __forceinline__ bool mc_update_site(const Tables& t, const McParams& 
    } else if (ftype == 1) {
       double g0, g1, g2;
       gauss3f(p.seed, (uint32_t)o + t.atom_offset, (uint32_t)k + t.ens_offset, p.sweep, 2u, g0, g1, g2);
-      // delta = (2/25) (k_B T / mu_B)^(1/5)  (montecarlo.f90:142; ignores temprescale like the reference)
-      const double delta = (2.0 / 25.0) * pow(p.k_bolt * p.temperature / p.mub, 0.20);
-      const double ax = own.x + g0 * delta, ay = own.y + g1 * delta, az = own.z + g2 * delta;
+      const double ax = own.x + g0 * p.delta, ay = own.y + g1 * p.delta, az = own.z + g2 * p.delta;
       const double l = sqrt(ax * ax + ay * ay + az * az);
       nx = ax / l; ny = ay / l; nz = az / l;
    } else {

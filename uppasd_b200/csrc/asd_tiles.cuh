@@ -28,7 +28,10 @@ constexpr size_t TILE_BUILD_SMEM = (size_t)TILE_HASH * 4 + (size_t)TILE_UMAX * (
 // of x = 0 -- far away in index order, which would split the warp's run.  For lattice layouts (kna, kn1 > 0: key =
 // i0 + kna*(ix + kn1*...)) the x index is therefore rotated so that the tile's own cells sit in the middle of the
 // rotated range (first cell at koff = (kn1 - BX) / 2): any N1 >= BX + 2 * reach keeps every neighbour run unsplit.
-struct TileKeyWrap { int kna, kn1, xref, koff; };
+// x-residue split (Monte Carlo block sweep, asd_mc_block.cuh): with split = px > 1 (sna = NA, sn1 = N1 of the lattice) the
+// cells of an x-run are listed residue class by residue class (x mod px), so that the cells of ONE colour of a periodic
+// colouring with x-period px -- the lanes that are active together in a colour phase -- are consecutive list positions.
+struct TileKeyWrap { int kna, kn1, xref, koff, split, sna, sn1; };
 
 // the DM and BQ tables of the layout (z = 0: absent): their neighbours join the tile's gather list and get their own
 // 16-bit position tables, so that the stage kernels read them from shared memory as well
@@ -49,13 +52,19 @@ __device__ __forceinline__ unsigned long long tile_key(const int* __restrict__ h
       const int rx = (kx - kw.xref + kw.koff + kw.kn1) % kw.kn1;
       o += kw.kna * (rx - kx);
    }
+   if (kw.split > 1) {
+      const int c = o / kw.sna, kx = c % kw.sn1;
+      const int sx = (kx % kw.split) * ((kw.sn1 + kw.split - 1) / kw.split) + kx / kw.split;
+      o += kw.sna * (sx - kx);
+   }
    return ((unsigned long long)(unsigned)ham[slot] << 40) | (unsigned long long)(unsigned)o;
 }
 
 __global__ void __launch_bounds__(TILE)
 tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const int* __restrict__ ham, const int* __restrict__ orig,
                    int pass, int ucap, int* __restrict__ ucount, int* __restrict__ ulist, uint4* __restrict__ nl16, int zq8,
-                   int kna, int kn1, int koff, int ts, const TileExtra x) {
+                   int kna, int kn1, int koff, int ts, const TileExtra x, int xsplit = 0, int sna = 0, int sn1 = 0,
+                   unsigned short* __restrict__ selfpos = nullptr) {
    extern __shared__ unsigned long long tsm64[];
    unsigned long long* keys = tsm64;                       // [TILE_UMAX] (pass 1)
    int* lst = (int*)(tsm64 + TILE_UMAX);                   // [TILE_UMAX] slot of each key (pass 1)
@@ -63,7 +72,7 @@ tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const 
    __shared__ int nuniq, over, nfill;
    const int tile = blockIdx.x;
    const int s0 = tile * ts + threadIdx.x, send = min((tile + 1) * ts, Nown);
-   TileKeyWrap kw{kna, kn1, 0, koff};
+   TileKeyWrap kw{kna, kn1, 0, koff, xsplit, sna, sn1};
    if (kn1 > 0) { const int o0 = orig[tile * ts]; kw.xref = o0 >= 0 ? (o0 / kna) % kn1 : 0; }
    for (int q = threadIdx.x; q < TILE_HASH; q += TILE) tab[q] = -1;
    if (threadIdx.x == 0) { nuniq = 0; over = 0; nfill = 0; }
@@ -128,6 +137,7 @@ tile_gather_kernel(int Nown, int Npad, int z, const int* __restrict__ nl, const 
    };
    for (int s = s0; s < send; s += TILE) {
       const unsigned self = find(s);
+      if (selfpos) selfpos[s] = (unsigned short)self;
       for (int q = 0; q < zq8; q++) {
          unsigned v[8];
 #pragma unroll

@@ -162,6 +162,19 @@ class Engine:
         self._chk(self.lib.asd_get_mc_colours(self.h, _p(col)))
         return col
 
+    def get_mc_visit_order(self):
+        """1-based atoms in a sequential visiting order that reproduces the chain of the next sweep"""
+        order = np.zeros(self.N, dtype=np.int32)
+        self._chk(self.lib.asd_get_mc_visit_order(self.h, _p(order)))
+        return order
+
+    def debug_mc_draws(self, sweep):
+        """(u(4,N,M), g(3,N,M)): the draws of one sweep as the update kernels compute them (test hook)"""
+        u = np.zeros((4, self.N, self.M), order='F')
+        g = np.zeros((3, self.N, self.M), order='F')
+        self._chk(self.lib.asd_debug_mc_draws(self.h, sweep, _p(u), _p(g)))
+        return u, g
+
     def measure(self, energy=False):
         msum = np.zeros((3, self.M), order='F')
         en = np.zeros(self.M) if energy else None
