@@ -175,6 +175,14 @@ int asd_effective_field(asd_engine* e, double* beff, double* beff1, double* beff
  * (sd_driver.f90:668-764).  first_step is the value of mstep for the first step (keys the noise). */
 int asd_sd_steps(asd_engine* e, long nsteps, long first_step);
 
+/* The measurement-phase loop (sd_mphase, sd_driver.f90:517-849) in one call: nsteps LLG steps, and after every
+ * `sample_every`-th step the per-ensemble sums of emomM that prn_averages buffers (prn_averages.f90:437-447) are reduced
+ * on the device and kept in a sample ring.  One device-to-host copy and one synchronisation end the call:
+ * msum(3, Mensemble, nsamples) with nsamples = nsteps / sample_every (also returned in *nsamples; msum may be NULL to
+ * leave the samples on the device).  Replaces the per-sample full-state copy of the reference's CUDA loop
+ * (gpu_files/cudaMdSimulation.cu:400-470, cudaMeasurement.cu:109-182).  sample_every <= 0: one sample after the last step. */
+int asd_sd_run(asd_engine* e, long nsteps, long first_step, long sample_every, double* msum, long* nsamples);
+
 /* nsweeps Monte Carlo sweeps (mc_evolve, montecarlo.f90:44-273): mode 'M' Metropolis / 'H' heat bath,
  * N*M single-spin trials per sweep visited colour by colour (graph colouring of the union of all
  * neighbour tables).  extfield[3] is mc_evolve's uniform field argument. */

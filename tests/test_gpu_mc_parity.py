@@ -6,7 +6,7 @@ colour class commute), and the draws of the counter-based generator are keyed by
 given that visiting order (mc_evolve's iflip_a) and those very draws (asd_debug_mc_draws: the uniforms are checked bit for
 bit against a numpy restatement of Philox4x32-10 here, the Gaussians to float accuracy) and must then produce the SAME
 chain -- every trial move, every delta-E branch (Heisenberg, DM, biquadratic, uniaxial / cubic / type-7 anisotropy, Zeeman),
-every acceptance, every heat-bath frame -- to 1e-12 after several sweeps."""
+every acceptance, every heat-bath frame -- to CHAIN_TOL after several sweeps."""
 import numpy as np
 import pytest
 
@@ -14,6 +14,15 @@ from oracle import orc
 from util import fixture_system, lattice_engine
 
 pytestmark = pytest.mark.gpu
+
+# The device contracts a*b+c into FMAs and sums the neighbours in its own order, the oracle rounds every operation
+# (-ffp-contract=off) in list order: each local field differs in the last bits.  A Metropolis chain does not accumulate that
+# (an accepted move IS the trial vector, which depends on the draws only), so it must agree to a few ulp.  A heat-bath
+# update is a continuous function of the local field whose frame rotation divides by sin(theta) of the field direction:
+# a field within 1e-3 of the z axis amplifies the last-bit difference by 1e6, and the chain carries it on (observed: up to
+# 6e-10 after 5 sweeps, depending on the summation order of the kernel).  A wrong branch, sign, draw or visiting order shows
+# up as O(1e-2 .. 1) in either mode.
+CHAIN_TOL = {'M': 5e-12, 'H': 5e-9}
 
 
 def philox4x32_10(c, k):
@@ -108,7 +117,7 @@ def test_chain_parity_host_tables(name, over, T, ext, quirk, resident, mode, mon
     e = _host_engine(S, 31)
     err, moved = _chain_parity(e, S, mode, T, 6, extfield=ext, dm_quirk=quirk or bool(np.all(S['mmom'] == 1.0)))
     assert moved > 0.1
-    assert err <= 1e-12, (name, mode, resident, err)
+    assert err <= CHAIN_TOL[mode], (name, mode, resident, err)
 
 
 def test_chain_parity_cubic_anisotropy():
@@ -125,7 +134,7 @@ def test_chain_parity_cubic_anisotropy():
     for mode in ('M', 'H'):
         e = _host_engine(S, 9)
         err, moved = _chain_parity(e, S, mode, 200.0, 6, extfield=(0.0, 2.0, 0.0))
-        assert moved > 0.1 and err <= 1e-12, (mode, err)
+        assert moved > 0.1 and err <= CHAIN_TOL[mode], (mode, err)
 
 
 def _with_bq(args):
@@ -186,10 +195,10 @@ def test_chain_parity_lattice_layouts(name, over, T, ext, quirk, ts, extra, layo
         assert lay == layout, (lay, layout)
         err, moved = _chain_parity(e, S, mode, T, 5, extfield=ext, dm_quirk=q)
         assert moved > 0.1
-        assert err <= 1e-12, (name, mode, layout, err)
+        assert err <= CHAIN_TOL[mode], (name, mode, layout, err)
         # a second batch continues the same chain (the sweep number keys the draws)
         err2, _ = _chain_parity(e, S, mode, T, 3, extfield=ext, dm_quirk=q, first=6)
-        assert err2 <= 1e-12, (name, mode, layout, err2)
+        assert err2 <= CHAIN_TOL[mode], (name, mode, layout, err2)
         e.close()
 
 

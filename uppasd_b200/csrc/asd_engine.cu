@@ -24,6 +24,7 @@
 #include "asd_device.cuh"
 #include "asd_mc.cuh"
 #include "asd_mc_block.cuh"
+#include "asd_mc_runs.cuh"
 #include "asd_tiles.cuh"
 #include "asd_runs.cuh"
 #include "asd_lattice.cuh"
@@ -146,6 +147,19 @@ struct McBlockState {
    int ts = 0, ucap = 0, ncol = 0, ntile = 0;
    size_t smem = 0;
    std::vector<int> class_first, class_count, h_tilelist;   // tile-colour classes: ranges of h_tilelist
+   std::vector<int> class_run;                              // leading tiles of every class that take the run form (asd_mc_runs.cuh)
+   McRuns mr{};
+   size_t smem_run = 0;
+   int nt = 256;                                            // threads per CTA of the run form
+   bool ticket = false;                                     // one launch per sweep with tile dependencies (McTicket)
+   int adjcap = 0;
+   unsigned long long tickets = 0;
+   unsigned int epoch = 0;
+   DevBuf<int> adj, nadj;
+   DevBuf<unsigned char> tclass;
+   DevBuf<unsigned int> done;
+   DevBuf<unsigned long long> counter;
+   DevBuf<unsigned short> gtab;
    DevBuf<int> ulist, ucount, cstart, tilelist;
    DevBuf<uint4> nl16, dm16, bq16;
    DevBuf<unsigned short> selfpos, corder;
@@ -187,7 +201,7 @@ struct asd_engine {
    bool lat_ordered = false;    // the SD layout of host tables is in brick order (e->lat describes it)
    int state_layout = 0;  // 0 = none, 1 = sd, 2 = mc
    DevBuf<SpinVec> cur, pred;
-   DevBuf<double> b2eff, esite, part, red;
+   DevBuf<double> b2eff, esite, part, red, ring;   // ring: per-sample sums of asd_sd_run
    double* h_red = nullptr;             // pinned host landing zone of the per-ensemble sums (4 doubles each)
    size_t h_red_n = 0;
    DevBuf<double> msum_part;            // per-tile sums of emomM left by the last corrector launch of asd_sd_steps
@@ -1708,6 +1722,58 @@ int asd_measure(asd_engine* e, double* msum, double* energy) {
    return measure(e, e->state_layout == 2 ? e->mc : e->sd, msum, energy);
 }
 
+// Sampled run: the measurement-phase loop of sd_mphase (sd_driver.f90:517-849) without a host round trip per sample.  Every
+// `sample_every` steps the per-ensemble sums of emomM (what prn_averages needs, prn_averages.f90:437-447) are reduced on the
+// device into a sample ring; ONE device-to-host copy and ONE stream synchronisation end the call.  The corrector launch of a
+// sampled step leaves the per-tile sums (no extra pass over the spins); small systems / fixed-moment runs use the stand-alone
+// reduction.  The reference's CUDA loop instead copies the whole state to the host at every sampled step
+// (cudaMdSimulation.cu:400-470, cudaMeasurement.cu:109-182).
+static int sd_run(asd_engine* e, long nsteps, long first_step, long sample_every, double* msum, long* nsamples) {
+   if (sample_every <= 0) sample_every = nsteps > 0 ? nsteps : 1;
+   const long ns = nsteps / sample_every;
+   int r = ensure_layout(e, 1);
+   if (r) return r;
+   Layout& L = e->sd;
+   if (nsamples) *nsamples = ns;
+   if (ns > 0) {
+      if ((r = e->ring.alloc((size_t)ns * e->M * 4))) return r;
+      if ((r = pinned_red(e, (size_t)ns * e->M * 4))) return r;
+   }
+   long done = 0;
+   for (long q = 0; q < ns; q++) {
+      if ((r = sd_steps(e, sample_every, first_step + done))) return r;
+      done += sample_every;
+      double* dst = e->ring.p + (size_t)q * e->M * 4;
+      if (e->msum_fresh) {
+         moment_final_kernel<<<e->M, 1024, 0, e->stream>>>(e->msum_ntile, e->msum_part.p, dst);
+         e->launches++;
+      } else {
+         const int nblk = std::min(1184, (L.Npad + 255) / 256);
+         if ((r = e->part.alloc((size_t)e->M * nblk * 4))) return r;
+         moment_partial_kernel<<<dim3(nblk, e->M), 256, 0, e->stream>>>(L.Npad, L.d_orig.p, e->cur.p, nullptr, e->part.p);
+         moment_final_kernel<<<e->M, 1024, 0, e->stream>>>(nblk, e->part.p, dst);
+         e->launches += 2;
+      }
+   }
+   if (done < nsteps && (r = sd_steps(e, nsteps - done, first_step + done))) return r;
+   CU(cudaGetLastError());
+   if (ns > 0 && msum) {
+      CU(cudaMemcpyAsync(e->h_red, e->ring.p, (size_t)ns * e->M * 4 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+      CU(cudaStreamSynchronize(e->stream));
+      for (long q = 0; q < ns; q++)
+         for (int k = 0; k < e->M; k++)
+            for (int a = 0; a < 3; a++) msum[(size_t)3 * (k + (size_t)e->M * q) + a] = e->h_red[(size_t)4 * (k + (size_t)e->M * q) + a];
+      return slab_check(e);
+   }
+   return 0;
+}
+
+int asd_sd_run(asd_engine* e, long nsteps, long first_step, long sample_every, double* msum, long* nsamples) {
+   CU(cudaSetDevice(e->device));
+   if (nsteps < 0) return fail(-1, "asd_sd_run: nsteps < 0");
+   return sd_run(e, nsteps, first_step, sample_every, msum, nsamples);
+}
+
 int asd_time_sd_steps(asd_engine* e, long nsteps, long first_step, float* total_ms, float* stage_ms) {
    CU(cudaSetDevice(e->device));
    int r = ensure_layout(e, 1);
@@ -1741,6 +1807,14 @@ int asd_time_sd_steps(asd_engine* e, long nsteps, long first_step, float* total_
    cudaEventDestroy(a); cudaEventDestroy(b);
    return r;
 }
+
+#ifdef ASD_MC_PROF
+extern "C" int asd_debug_mc_prof(unsigned long long* out8, int reset) {
+   if (out8) CU(cudaMemcpyFromSymbol(out8, asd::g_mc_prof, 8 * sizeof(unsigned long long)));
+   if (reset) { unsigned long long z[8] = {0}; CU(cudaMemcpyToSymbol(asd::g_mc_prof, z, sizeof z)); }
+   return 0;
+}
+#endif
 
 int asd_time_mc_sweeps(asd_engine* e, char mode, long nsweeps, double temperature, float* total_ms) {
    CU(cudaSetDevice(e->device));

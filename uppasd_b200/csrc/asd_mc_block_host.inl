@@ -14,6 +14,13 @@ static bool mc_block_candidate(const asd_engine* e) {
 }
 
 template <class K>
+static void mc_block_run_launch(K kernel, int nt, dim3 g, size_t smem, cudaStream_t st, const Tables& t, const McParams& p, const McBlock& mb,
+                                const McRuns& mr, const McTicket& tk, int first, SpinVec* cur) {
+   allow_smem(kernel, smem);
+   kernel<<<g, nt, smem, st>>>(t, p, mb, mr, tk, first, cur);
+}
+
+template <class K>
 static void mc_block_launch(K kernel, dim3 g, size_t smem, cudaStream_t st, const Tables& t, const McParams& p, const McBlock& mb,
                             int first, SpinVec* cur) {
    allow_smem(kernel, smem);
@@ -125,12 +132,108 @@ static int mc_block_prepare(asd_engine* e) {
       std::vector<int> fill(B.class_first);
       for (int a = 0; a < ntile; a++) B.h_tilelist[fill[tcol[a]]++] = a;
    }
+   // RUN form (asd_mc_runs.cuh): neighbour arrangement per Hamiltonian row, group table + per-tile verification; regular tiles
+   // come first in every class
+   B.class_run.assign(ntc, 0);
+   B.smem_run = 0;
+   {
+      const char* renv = std::getenv("ASD_MC_RUNS");
+      const char* nenv = std::getenv("ASD_MC_NT");
+      B.nt = (nenv && atoi(nenv) == 512) ? 512 : 256;
+      if (!xs && ts == 1024 && ncol <= 56 && t.z <= MCR_ZMAX && !(renv && atoi(renv) == 0)) {
+         McRuns& mr = B.mr;
+         memset(&mr, 0, sizeof mr);
+         mr.q = B.nt / 128;
+         const int spcap = MCR_ZMAX;
+         DevBuf<unsigned short> d_arr;
+         DevBuf<double> d_cseq;
+         DevBuf<int> d_steps, d_ok;
+         if ((r = d_arr.alloc((size_t)t.NH * mr.q * spcap))) return r;
+         if ((r = d_cseq.alloc((size_t)t.NH * spcap))) return r;
+         if ((r = d_steps.alloc(t.NH))) return r;
+         mc_runs_arrange_kernel<<<(t.NH + 31) / 32, 32, 0, st>>>(t.NH, t.z, mr.q, spcap, t.lsize, t.cp, d_arr.p, d_cseq.p, d_steps.p);
+         e->launches++;
+         CU(cudaGetLastError());
+         std::vector<int> steps(t.NH);
+         std::vector<double> cseq((size_t)t.NH * spcap);
+         CU(cudaMemcpyAsync(steps.data(), d_steps.p, steps.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+         CU(cudaMemcpyAsync(cseq.data(), d_cseq.p, cseq.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+         CU(cudaStreamSynchronize(st));
+         const int smin = *std::min_element(steps.begin(), steps.end()), smax = *std::max_element(steps.begin(), steps.end());
+         mr.sp = (std::max(smax, 1) + 3) & ~3;
+         // worth it only while the padding of the arrangement stays small: steps x lanes <= list length + 25 %
+         const bool fits = smin >= 0 && (long)t.NH * mr.sp <= MCR_CSEQ && (long)smax * mr.q <= (long)t.z + t.z / 4 + mr.q;
+         if (fits) {
+            for (int h = 0; h < t.NH; h++)
+               for (int q = 0; q < mr.sp; q++) mr.cseq[h * mr.sp + q] = cseq[(size_t)h * spcap + q];
+            mr.ncw = (MCR_PH0 + 4 * MCR_PHMAX + 7) & ~7;
+            mr.gstride = (mr.ncw + MCR_GMAX * (MCR_HDR + mr.q * mr.sp) + 7) & ~7;
+            mr.zero = ucap;
+            if ((r = B.gtab.alloc((size_t)ntile * mr.gstride))) return r;
+            if ((r = d_ok.alloc(ntile))) return r;
+            mc_block_groups_kernel<<<ntile, 256, 0, st>>>(ts, ncol, t.z, (size_t)Npad, t.ham, B.nl16.p, B.selfpos.p, B.corder.p, B.cstart.p,
+                                                           B.ucount.p, d_arr.p, d_steps.p, spcap, mr, B.gtab.p, d_ok.p);
+            e->launches++;
+            CU(cudaGetLastError());
+            std::vector<int> ok(ntile);
+            CU(cudaMemcpyAsync(ok.data(), d_ok.p, (size_t)ntile * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            const int gmax = *std::max_element(ok.begin(), ok.end());
+            mr.gwords = (mr.ncw + gmax * (MCR_HDR + mr.q * mr.sp) + 7) & ~7;
+            mr.gtab = B.gtab.p;
+            B.smem_run = (size_t)5 * MCR_BATCH * sizeof(double) + (B.nt == 512 ? (size_t)2 * 8 * 16 * 3 * sizeof(double) : 0) +
+                         (size_t)mr.gwords * 2 + (size_t)MCR_BATCH * 2 + (size_t)3 * (ucap + 16) * sizeof(double);
+            if (gmax > 0 && B.smem_run <= (size_t)113 * 1024) {
+               for (int c = 0; c < ntc; c++) {
+                  int* lst = B.h_tilelist.data() + B.class_first[c];
+                  B.class_run[c] = (int)(std::stable_partition(lst, lst + B.class_count[c], [&](int a) { return ok[a] > 0; }) - lst);
+               }
+            }
+         }
+      }
+   }
    if ((r = B.tilelist.upload(B.h_tilelist, st))) return r;
+   // whole-sweep scheduling (McTicket): every tile in the run form, symmetric tile adjacency of at most 64 neighbours
+   B.ticket = false;
+   {
+      int nrun = 0, deg = 0;
+      for (int c : B.class_run) nrun += c;
+      for (int a = 0; a < ntile; a++) {
+         std::sort(nb[a].begin(), nb[a].end());
+         nb[a].erase(std::unique(nb[a].begin(), nb[a].end()), nb[a].end());
+         deg = std::max(deg, (int)nb[a].size());
+      }
+      const char* tenv2 = std::getenv("ASD_MC_TICKET");
+      if (nrun == ntile && deg <= 64 && ntc <= 255 && !(tenv2 && atoi(tenv2) == 0)) {
+         B.adjcap = std::max(deg, 1);
+         std::vector<int> hadj((size_t)ntile * B.adjcap, 0), hn(ntile);
+         std::vector<unsigned char> hc(ntile);
+         for (int a = 0; a < ntile; a++) {
+            hn[a] = (int)nb[a].size();
+            hc[a] = (unsigned char)tcol[a];
+            std::copy(nb[a].begin(), nb[a].end(), hadj.begin() + (size_t)a * B.adjcap);
+         }
+         if ((r = B.adj.upload(hadj, st))) return r;
+         if ((r = B.nadj.upload(hn, st))) return r;
+         if ((r = B.tclass.upload(hc, st))) return r;
+         if ((r = B.done.alloc((size_t)ntile * e->M))) return r;
+         if ((r = B.counter.alloc(1))) return r;
+         CU(cudaMemsetAsync(B.done.p, 0, (size_t)ntile * e->M * sizeof(unsigned int), st));
+         CU(cudaMemsetAsync(B.counter.p, 0, sizeof(unsigned long long), st));
+         B.tickets = 0; B.epoch = 0;
+         B.ticket = true;
+      }
+   }
    B.ts = ts; B.ucap = ucap; B.ncol = ncol; B.ntile = ntile;
    B.on = true;
    if (std::getenv("ASD_DEBUG"))
-      fprintf(stderr, "[asd] MC block sweep: tiles of %d slots, %d tiles in %d classes, %d atom colours (period %d %d %d), gather list <= %d, %zu B smem\n",
-              ts, ntile, ntc, ncol, e->lat_period[0], e->lat_period[1], e->lat_period[2], ucap, B.smem);
+   {
+      int nrun = 0;
+      for (int c : B.class_run) nrun += c;
+      fprintf(stderr, "[asd] MC block sweep: tiles of %d slots, %d tiles in %d classes, %d atom colours (period %d %d %d), gather list <= %d, %zu B smem; "
+                      "run form on %d tiles (%d threads, %d steps x %d lanes, %zu B smem)%s\n",
+              ts, ntile, ntc, ncol, e->lat_period[0], e->lat_period[1], e->lat_period[2], ucap, B.smem, nrun, B.nt, B.mr.sp, B.mr.q, B.smem_run, B.ticket ? ", one launch per sweep (tickets)" : "");
+   }
    return 0;
 }
 
@@ -151,11 +254,36 @@ static int mc_sweeps_block(asd_engine* e, McParams& p, long nsweeps, long first_
    Layout& L = e->sd;
    const McBlock mb = mc_block_params(e);
    const bool xs = L.t.zdm > 0 || L.t.zbq > 0, hb = p.mode == 'H';
+   McTicket tk;
+   memset(&tk, 0, sizeof tk);
    for (long s = 0; s < nsweeps; s++) {
       p.sweep = (unsigned long long)(first_sweep + s);
+      if (B.ticket) {
+         // one launch for the whole sweep: tickets in class order, dependencies through done[] (asd_mc_runs.cuh)
+         tk.counter = B.counter.p; tk.base = B.tickets; tk.epoch = ++B.epoch; tk.done = B.done.p; tk.adj = B.adj.p; tk.nadj = B.nadj.p;
+         tk.tclass = B.tclass.p; tk.cap = B.adjcap; tk.ntile = B.ntile;
+         const dim3 gr((unsigned)((long)B.ntile * e->M));
+#define ASD_MCR(HB, NT) mc_block_run_launch(mc_block_run_kernel<HB, NT, true>, NT, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, 0, e->cur.p)
+         if (B.nt == 512) { if (hb) ASD_MCR(true, 512); else ASD_MCR(false, 512); }
+         else { if (hb) ASD_MCR(true, 256); else ASD_MCR(false, 256); }
+#undef ASD_MCR
+         B.tickets += (unsigned long long)B.ntile * e->M;
+         e->launches++;
+         continue;
+      }
       for (size_t c = 0; c < B.class_first.size(); c++) {
-         const dim3 g((unsigned)B.class_count[c], (unsigned)e->M);
-         const int first = B.class_first[c];
+         const int nrun = B.class_run[c];
+         if (nrun > 0) {
+            const dim3 gr((unsigned)nrun, (unsigned)e->M);
+#define ASD_MCR(HB, NT) mc_block_run_launch(mc_block_run_kernel<HB, NT, false>, NT, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, B.class_first[c], e->cur.p)
+            if (B.nt == 512) { if (hb) ASD_MCR(true, 512); else ASD_MCR(false, 512); }
+            else { if (hb) ASD_MCR(true, 256); else ASD_MCR(false, 256); }
+#undef ASD_MCR
+            e->launches++;
+         }
+         if (nrun == B.class_count[c]) continue;
+         const dim3 g((unsigned)(B.class_count[c] - nrun), (unsigned)e->M);
+         const int first = B.class_first[c] + nrun;
 #define ASD_MCB(APT, XS, HB) mc_block_launch(mc_block_kernel<APT, XS, HB>, g, B.smem, e->stream, L.t, p, mb, first, e->cur.p)
          if (B.ts == 1024) {
             if (xs) { if (hb) ASD_MCB(4, true, true); else ASD_MCB(4, true, false); }
