@@ -10,6 +10,10 @@ One "step" = one full LLG time step of every spin (field / predictor / field / c
 
 N > 1 shards independent ensembles (Mensemble = N, one per GPU, no data-path communication): weak scaling.
 All timing is on the device (CUDA events on the engine's stream), max over ranks, after a barrier.
+
+The one JSON line also carries `secondary`: the Monte Carlo sweep rate of the same supercell (Metropolis and heat bath,
+attempts/s against the 256 B/attempt figure of SURVEY 8d) and, for N > 1, the slab-decomposed single supercell with the
+fused NVLink halo push (BASELINE config 5: bcc 512 x 512 x 256 on 8 GPUs, 256^3 below), strong scaling.
 """
 import argparse
 import json
@@ -157,8 +161,9 @@ def oracle_bcc(ncell, mensemble=1):
     return S
 
 
-def cpu_leg(ncell, solver, temp, damping, steps, warmup, settle_s=0.0):
-    """Times the restated reference CPU path (oracle, OpenMP over all host cores) on a bounded sample."""
+def cpu_leg(ncell, solver, temp, damping, steps, warmup, settle_s=0.0, one_thread_steps=0):
+    """Times the restated reference CPU path (oracle, OpenMP over all host cores) on a bounded sample; optionally the same
+    system on ONE thread as well (SURVEY 8d asks for both).  Returns (rate, ms/step, atoms, threads, one-thread rate | None)."""
     from oracle import orc
     # all host cores, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for its workers)
     threads = orc.set_num_threads(os.cpu_count() or 1)
@@ -178,7 +183,15 @@ def cpu_leg(ncell, solver, temp, damping, steps, warmup, settle_s=0.0):
     for _ in range(steps):
         st.step(gauss=g)
     dt = time.perf_counter() - t0
-    return n * steps / dt, dt / steps * 1e3, n, threads
+    one = None
+    if one_thread_steps > 0:
+        orc.set_num_threads(1)
+        t1 = time.perf_counter()
+        for _ in range(one_thread_steps):
+            st.step(gauss=g)
+        one = n * one_thread_steps / (time.perf_counter() - t1)
+        orc.set_num_threads(threads)
+    return n * steps / dt, dt / steps * 1e3, n, threads, one
 
 
 def traffic_from_profiles(kernel_key):
@@ -190,6 +203,69 @@ def traffic_from_profiles(kernel_key):
         except Exception:
             return None
     return None
+
+
+def slab_block(a, world, rank, local, dist, torch, out, warmup, steps):
+    """BASELINE config 5 next to the headline line: one supercell (512 x 512 x 256 on 8 GPUs, 256^3 below) cut into z-slabs.
+    A watchdog prints the headline line without it if the ring does not come up (a hang must not cost the main number)."""
+    import signal
+    ncell = [512, 512, 256] if world >= 8 else [256, 256, 256]
+    state = {'done': False}
+
+    def bail():
+        if state['done']:
+            return
+        if rank == 0 and out is not None:
+            out.setdefault('secondary', {})['slab'] = {'error': 'timed out after 240 s'}
+            print(json.dumps(out), flush=True)
+        os._exit(0)
+    timer = threading.Timer(240.0, bail)
+    timer.daemon = True
+    timer.start()
+    blk = None
+    try:
+        e, n = bcc_engine(ncell, a.solver, a.temp, a.damping, 1, 0, local, slab=(world, rank, dist))
+        sync = torch.zeros(1, device='cuda')
+
+        def barrier():
+            dist.all_reduce(sync)
+            torch.cuda.synchronize()
+            e.synchronize()
+        e.sd_steps(warmup, first_step=1)
+        barrier()
+        ms = e.time_sd_steps(steps, first_step=warmup + 1)
+        barrier()
+        t = torch.tensor([ms], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        nt = torch.tensor([float(n)], device='cuda', dtype=torch.float64)
+        dist.all_reduce(nt)
+        ntot = float(nt.item())
+        _, err = e.slab_status()
+        ef = torch.tensor([float(err)], device='cuda', dtype=torch.float64)
+        dist.all_reduce(ef, op=dist.ReduceOp.MAX)
+        peak, _ = peaks()
+        b1, b2 = B_ALG[a.solver]
+        rate = ntot * steps / (ms * 1e-3)
+        blk = {'workload': 'bccFe %dx%dx%d (%d spins), ONE supercell in %d z-slabs, LLG solver %d, T=%g K' % (*ncell, int(ntot), world, a.solver, a.temp),
+               'value': rate, 'unit': 'atom-steps/s', 'scaling': 'strong', 'ms_per_step': ms / steps, 'steps': steps, 'warmup': warmup,
+               'halo': {'planes': 2, 'bytes_per_exchange_per_side': 2 * ncell[0] * ncell[1] * 2 * 32, 'exchanges_per_step': 2,
+                        'transport': 'peer stores over NVLink from the boundary-tile launches (CUDA IPC), epoch flags',
+                        'timeout_flag': int(ef.item())},
+               'step_frac_of_peak': (b1 + b2) * rate / 1e9 / (peak * world)}
+        e.close()
+    except Exception as ex:
+        blk = {'error': repr(ex)[:300]}
+    state['done'] = True
+    timer.cancel()
+    if rank == 0 and out is not None:
+        out.setdefault('secondary', {})['slab'] = blk
+        print(json.dumps(out), flush=True)
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 def main():
@@ -206,7 +282,8 @@ def main():
     ap.add_argument('--decomp', default='ensemble', choices=['ensemble', 'slab'],
                     help='N > 1: one ensemble of the supercell per GPU (weak scaling, no communication) or one z-slab '
                          'of a single supercell per GPU with the fused NVLink halo push (strong scaling)')
-    ap.add_argument('--cpu-ncell', type=int, nargs=3, default=[64, 64, 64])
+    ap.add_argument('--cpu-ncell', type=int, nargs=3, default=None, help='CPU legs on a smaller supercell (default: the same one)')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the Monte Carlo and slab blocks')
     ap.add_argument('--no-cpu', action='store_true')
     a = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -218,19 +295,26 @@ def main():
         a.ncell[0], a.ncell[1], a.ncell[2], 'midpoint' if a.solver == 1 else 'Depondt', a.solver, a.temp, a.damping,
         'N' if a.full_ham else 'Y')
 
+    cpu_ncell = a.cpu_ncell or a.ncell
     if a.impl == 'reference':
         if rank != 0:
             return
         os.environ['OMP_NUM_THREADS'] = str(cores)
-        k = max(1, min(steps, 10))
-        v, ms, n, cores = cpu_leg(a.cpu_ncell, a.solver, a.temp, a.damping, k, min(warmup, 3), settle_s=6.0 if world > 1 else 0.0)
-        sample = 'bcc %dx%dx%d (%d spins) x %d steps of the same lattice/solver; restated Fortran loops ' \
-                 '(oracle/), OpenMP static schedule, noise array pre-generated' % (*a.cpu_ncell, n, k)
+        # the configuration it names (default bcc 128^3): every step is a full step of that supercell; the step count is
+        # bounded (<= 20) so that the run ends within a few minutes on any host
+        k = max(1, min(steps, 20))
+        w = min(warmup, 2)
+        v, ms, n, cores, one = cpu_leg(cpu_ncell, a.solver, a.temp, a.damping, k, w, settle_s=6.0 if world > 1 else 0.0, one_thread_steps=1)
+        if a.cpu_ncell:
+            workload += ' [CPU sample: bcc %dx%dx%d]' % tuple(cpu_ncell)
+        sample = 'bcc %dx%dx%d (%d spins) x %d full steps of the same lattice / solver / temperature; restated Fortran loops ' \
+                 '(oracle/), OpenMP static schedule over %d threads, noise array pre-generated' % (*cpu_ncell, n, k, cores)
         print(json.dumps({
             'impl': 'reference', 'metric': 'atom-steps/sec', 'value': v, 'unit': 'atom-steps/s', 'n_gpus': a.gpus,
-            'steps': k, 'warmup': min(warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'steps': k, 'warmup': w, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': {'workload': workload},
-            'cpu_baseline': {'value': v, 'unit': 'atom-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'cpu_baseline': {'value': v, 'unit': 'atom-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample,
+                             'one_thread': {'value': one, 'unit': 'atom-steps/s', 'steps': 1}},
             'e2e': {'value': v, 'unit': 'atom-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}))
         return
@@ -271,9 +355,11 @@ def main():
     ms = float(t.item())
     value = world * n * steps / (ms * 1e-3)
 
-    # ---- end to end through the C ABI with HOST buffers (what a driver that owns the moments does): H2D of the
-    #      state from pinned host memory, K steps each followed by the observable read-back a measuring driver
-    #      makes (asd_measure: D2H of sum M per ensemble), D2H of emom / emomM / mmom into pinned host memory
+    # ---- end to end through the C ABI with HOST buffers (what a driver that owns the moments does, sd_mphase): H2D of the
+    #      state from pinned host memory (asd_set_moments: emom + mmom), the measurement-phase loop asd_sd_run with a sample
+    #      of sum M after EVERY step (reduced on the device into a sample ring, one D2H + one synchronisation at the end),
+    #      D2H of the final unit vectors into pinned host memory (asd_get_moments(emom); |m| does not change with mompar 0
+    #      and emomM = emom * mmom is the host's to form)
     emom, emomM, mmom = e.get_moments()
 
     def pinned(x):
@@ -282,28 +368,54 @@ def main():
         v[...] = x
         return tt, v
     keep, h_e = pinned(emom)
-    keep2, h_eM = pinned(emomM)
     keep3, h_m = pinned(mmom)
     k2 = steps
+    keep4, h_s = pinned(np.zeros((3, 1, k2), order='F'))
+    del emomM
+    e.sd_run(2, first_step=9_000, sample_every=1)          # sample ring + pinned landing zone allocated outside the timed region
     barrier()
     t0 = time.perf_counter()
     e.set_moments(h_e, h_m)
-    for s in range(k2):
-        e.sd_steps(1, first_step=10_000 + s)
-        e.measure()
-    e.get_moments(out=(h_e, h_eM, h_m))
+    samples = e.sd_run(k2, first_step=10_000, sample_every=1, out=h_s)
+    e.get_moments(out=(h_e, None, None))
     e.synchronize()
     dt = time.perf_counter() - t0
+    assert samples.shape[2] == k2 and np.isfinite(samples).all() and abs(np.sqrt((h_e[:, :8, 0] ** 2).sum(axis=0)) - 1.0).max() < 1e-9
     te = torch.tensor([dt], device='cuda', dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = world * n * k2 / float(te.item())
     h2d = 32.0 * n / k2
-    d2h = 56.0 * n / k2 + 24.0
+    d2h = 24.0 * n / k2 + 24.0
     _, slab_err = e.slab_status()
 
+    # ---- secondary: Monte Carlo on the same supercell (attempts/s, 256 B per attempt at z = 50) ----
+    secondary = {}
+    peak, how = peaks()
+    if not a.no_secondary and not slab and not a.full_ham:
+        try:
+            mc = {}
+            for mode, key in (('M', 'metropolis'), ('H', 'heat_bath')):
+                e.mc_sweeps(mode, 5, a.temp)
+                l0 = e.launch_count()
+                msw = e.time_mc_sweeps(mode, 20, a.temp)
+                tm = torch.tensor([msw], device='cuda', dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                rate = world * n * 20 / (float(tm.item()) * 1e-3)
+                mc[key] = {'value': rate, 'unit': 'attempts/s', 'ms_per_sweep': float(tm.item()) / 20, 'sweeps': 20,
+                           'launches_per_sweep': (e.launch_count() - l0) / 20.0,
+                           'roofline': {'bound': 'hbm', 'alg_bytes_per_attempt': 256.0, 'achieved': 256.0 * rate / world / 1e9,
+                                        'peak': peak, 'unit': 'GB/s', 'frac': 256.0 * rate / world / 1e9 / peak}}
+            lay_mc, ncol, per = e.mc_colouring()
+            mc['layout'] = {0: 'colour-major', 1: 'lattice tiles, one launch per colour', 2: 'block sweep'}[lay_mc]
+            mc['colours'] = ncol
+            mc['workload'] = 'bccFe %dx%dx%d, T=%g K, one ensemble per GPU' % (*a.ncell, a.temp)
+            secondary['mc'] = mc
+        except Exception as ex:                                   # the headline line must survive
+            secondary['mc'] = {'error': repr(ex)[:300]}
+
     if rank == 0:
-        peak, how = peaks()
         b1, b2 = B_ALG[a.solver]
         if a.full_ham:
             b1, b2 = b1 + 8.0 * 50, b2 + 8.0 * 50        # per-atom couplings add 8 z bytes per stage
@@ -328,9 +440,9 @@ def main():
                        'l2_policy': 'inputs larger than L2 (%s + spins %.0f MB per GPU vs 126 MB L2)' % (tables, 64.0 * n / 1e6)},
             'clocks': sampler.summary(),
             'e2e': {'value': e2e, 'unit': 'atom-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'steps': k2, 'note': 'asd_set_moments from pinned host memory (H2D of emom+mmom) + K x [asd_sd_steps(1) + '
-                                         'asd_measure (sync + D2H of sum M)] + asd_get_moments into pinned host memory '
-                                         '(D2H of emom+emomM+mmom); state copies amortised over the K steps'},
+                    'steps': k2, 'note': 'asd_set_moments from pinned host memory (H2D of emom + mmom) + asd_sd_run(K, sample sum M '
+                                         'after every step: device sample ring, one D2H + one sync) + asd_get_moments(emom) into '
+                                         'pinned host memory; state copies amortised over the K steps'},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'hbm', 'kernel': kname,
                          'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
@@ -344,12 +456,23 @@ def main():
         if slab:
             out['config']['halo'] = {'planes': 2, 'bytes_per_exchange_per_side': 2 * a.ncell[0] * a.ncell[1] * 2 * 32,
                                      'exchanges_per_step': 2, 'timeout_flag': slab_err}
+        if secondary:
+            out['secondary'] = secondary
         if world == 1 and not a.no_cpu:
             os.environ['OMP_NUM_THREADS'] = str(cores)
-            v, cms, cn, cores = cpu_leg(a.cpu_ncell, a.solver, a.temp, a.damping, 5, 1)
+            v, cms, cn, cores, one = cpu_leg(cpu_ncell, a.solver, a.temp, a.damping, 3, 1, one_thread_steps=1)
             out['cpu_baseline'] = {'value': v, 'unit': 'atom-steps/s', 'cores': cores, 'kind': 'port',
-                                   'sample': 'bcc %dx%dx%d (%d spins) x 5 steps, restated Fortran loops (oracle/), OpenMP over '
-                                             'all host cores, noise pre-generated' % (*a.cpu_ncell, cn)}
+                                   'sample': 'bcc %dx%dx%d (%d spins) x 3 full steps, restated Fortran loops (oracle/), OpenMP over '
+                                             'all host cores, noise pre-generated' % (*cpu_ncell, cn),
+                                   'one_thread': {'value': one, 'unit': 'atom-steps/s', 'steps': 1}}
+    else:
+        out = None
+    # ---- secondary: ONE supercell cut into z-slabs, halo push over NVLink fused into the boundary-tile launches (N > 1) ----
+    if world > 1 and not slab and not a.no_secondary and not a.full_ham:
+        e.close()
+        slab_block(a, world, rank, local, dist, torch, out, warmup, steps)
+        return
+    if rank == 0:
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

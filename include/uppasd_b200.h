@@ -77,6 +77,23 @@ void cudamdsim_initialphase_(unsigned int* ipnstep, double* ipTemp, double* ipde
 void cudamcsim_evolve_(char* mode, unsigned int* nsweeps, unsigned int* first_sweep, double* Temp,
                        double* temprescale, double* extfield, int* upload);
 
+/* pyasd, the reference's second caller (source/pyasd.f90; the Python package uppasd binds these names): the same bind(c)
+ * entry points, acting on the engine and the module arrays handed over by fortrandata_set*_ / cudamdsim_initiatematrices_.
+ *   relax_       pyasd.f90:255-298  imode 'M' / 'H': instep sweeps of mc_evolve at itemperature (mc_minimal); otherwise
+ *                                   instep midpoint steps at itemperature with damping idamping (sd_minimal, solver 1, the
+ *                                   module's delta_t; itimestep is accepted and unused, as in the reference).
+ *                                   moments(3,natom,mensemble) = emomM on return.
+ *   get_emom_    pyasd.f90:316-328  moments = emom
+ *   put_emom_    pyasd.f90:330-350  emom = moments; emom2 = emom; emomM = moments * mmom
+ *   get_beff_    pyasd.f90:356-369  effective_field(); fields = beff
+ *   get_energy_  pyasd.f90:505-517  effective_field(energy); energy / (Natom * Mensemble), in mRy */
+void relax_(double* moments, int* natom, int* mensemble, char* imode, int* instep, double* itemperature,
+            double* itimestep, double* idamping);
+void get_emom_(double* moments, int* natom, int* mensemble);
+void put_emom_(const double* moments, int* natom, int* mensemble);
+void get_beff_(double* fields, int* natom, int* mensemble);
+void get_energy_(double* energy);
+
 /* Extra inputs the reference never passes through fortrandata_* but whose Fortran semantics the engine
  * honours when given (all optional; NULL keeps the legacy behaviour of one global damping, g=2):
  *   Landeg(N), lambda1_array(N) (evolution.f90:38-44), bqlist/j_bq/bqlistsize (hamiltoniandatatype.f90:58-61). */

@@ -155,7 +155,8 @@ def test_cooperative_and_persistent_sweeps_run_the_same_chain(mode, monkeypatch)
 def test_resident_monte_carlo_runs_the_same_chain(name, mode, monkeypatch):
     """Small systems: all colours of all sweeps of a call in ONE launch with the ensemble's state in shared memory
     (mc_resident_kernel, the default at this size) against one launch per colour with one thread per update: the same
-    draws, the same field summation order, hence the same chain bit for bit; one launch per call."""
+    draws, the same field summation order, hence the same chain -- to the last bit or two: mc_update_site is inlined into both
+    kernels and the compiler contracts multiply-adds per copy (observed: 2.2e-16 on 7 % of the components); one launch per call."""
     from uppasd_b200 import host
     inp, S = _system(name, 3)
     rng = np.random.default_rng(23)
@@ -178,7 +179,7 @@ def test_resident_monte_carlo_runs_the_same_chain(name, mode, monkeypatch):
     _, ncol, _ = e.mc_colouring()
     # (each count includes the one conversion launch of get_moments)
     assert out['resident'][1] == 2 + 1 and out['launches'][1] == 9 * ncol + 1, (out['resident'][1], out['launches'][1], ncol)
-    assert np.array_equal(out['resident'][0], out['launches'][0])
+    assert np.abs(out['resident'][0] - out['launches'][0]).max() <= 1e-14
     assert np.abs(out['resident'][0] - e0).max() > 0.1
 
 

@@ -627,3 +627,44 @@ def test_spin_transfer_torque_field(alg, path, monkeypatch):
     emom = e.get_moments()[0]
     assert np.abs(st.emom - st0.emom).max() > 1e-6          # the torque matters at this amplitude
     assert np.abs(emom - st.emom).max() <= 1e-12, (alg, path, np.abs(emom - st.emom).max())
+
+
+def test_pyasd_entry_points():
+    """relax_ / get_emom_ / put_emom_ / get_beff_ / get_energy_ (source/pyasd.f90:255-384, 505-517), called by reference like
+    the Python package uppasd calls them, on the engine behind the legacy boundary: the field and the energy per atom against
+    the oracle's effective_field, a T = 0 relax_ against the oracle's sd_minimal loop (midpoint, the module's time step, the
+    damping of the call; itimestep unused as in the reference), put_emom_ -> get_emom_ round trip, Monte Carlo relax_ against
+    the explicit API with the same seed."""
+    from uppasd_b200 import host
+    fx, inp, S = load_golden('kagome')
+    N, M = S['Natom'], S['Mensemble']
+    fh = host.FortranHost(S, orc.consts(S), sdealgh=5, nstep=10, delta_t=inp['timestep'], damping=inp['damping'], gpu_rng_seed=5).initiate()
+    rb, ren = orc.effective_field(S)
+    beff = fh.get_beff()
+    assert np.abs(beff - rb).max() <= 1e-12 * np.abs(rb).max()
+    assert np.array_equal(fh.arr['beff'], beff)
+    assert abs(fh.get_energy() - ren.sum() / (N * M)) <= 1e-12 * abs(ren.sum() / (N * M))
+    # relax_ in SD mode: solver 1 whatever SDEalgh the run uses, damping of the call, the module's delta_t
+    mom = fh.relax('S', 25, 0.0, 123.0, 0.3)
+    st = orc.SdState(S, 1, inp['timestep'], 0.3)
+    for _ in range(25):
+        st.step()
+    assert np.abs(fh.arr['emom'] - st.emom).max() <= 1e-12
+    assert np.abs(mom - st.emom * S['mmom'][None]).max() <= 1e-12 * np.abs(S['mmom']).max()
+    assert np.array_equal(mom, fh.arr['emomM']) and np.array_equal(fh.get_emom(), fh.arr['emom'])
+    # put_emom_: new directions, emomM = moments * mmom, the device state follows
+    rng = np.random.default_rng(3)
+    e1 = rng.normal(size=(3, N, M)); e1 /= np.sqrt((e1 ** 2).sum(axis=0))
+    fh.put_emom(e1)
+    assert np.array_equal(fh.get_emom(), np.asfortranarray(e1))
+    assert np.array_equal(fh.arr['emomM'], e1 * fh.arr['mmom'][None]) and np.array_equal(fh.arr['emom2'], e1)
+    S2 = dict(S, emom=np.asfortranarray(e1), emomM=np.asfortranarray(e1 * S['mmom'][None]))
+    rb2, _ = orc.effective_field(S2)
+    assert np.abs(fh.get_beff() - rb2).max() <= 1e-12 * np.abs(rb2).max()
+    # relax_ in Monte Carlo mode = nsweeps of mc_evolve with the run's seed; the draw counter continues after the 25 SD steps
+    e = host.engine_from_system(S2, orc.consts(S), temp=0.0, seed=5)
+    for mode in ('M', 'H'):
+        first = 26 if mode == 'M' else 36
+        momc = fh.relax(mode, 10, 5.0, 0.0, 0.0)
+        e.mc_sweeps(mode, 10, 5.0, first_sweep=first, extfield=S['external_field'][:, 0, 0])
+        assert np.array_equal(momc, e.get_moments()[1]), mode

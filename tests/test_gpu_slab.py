@@ -136,7 +136,9 @@ def test_periodic_colouring_is_proper(ncell):
     lay, ncol, per = e.mc_colouring()
     assert lay == 1 and 2 <= ncol < 64
     for a in range(3):
-        assert ncell[a] % per[a] == 0 and per[a] >= 3      # periodic directions: the period divides the extent
+        # periodic directions: the period divides the extent (periods down to 2 are admissible when no stencil shift aliases an
+        # atom with itself in the quotient: bcc Fe with 4 shells takes the 8-colouring of period (2, 2, 2) where it divides)
+        assert ncell[a] % per[a] == 0 and per[a] >= 2
     col = e.get_mc_colours()
     assert col.min() == 0 and col.max() == ncol - 1
     assert _proper(e, col)

@@ -27,6 +27,11 @@ SYMBOLS = {
     'cudamdsim_measurementphase_': (None, []),
     'cudamdsim_initialphase_': (None, [vp] * 6),
     'cudamcsim_evolve_': (None, [vp] * 7),
+    'relax_': (None, [vp] * 8),
+    'get_emom_': (None, [vp] * 3),
+    'put_emom_': (None, [vp] * 3),
+    'get_beff_': (None, [vp] * 3),
+    'get_energy_': (None, [vp]),
     'cmdsim_initiateconstants_': (None, []),
     'cmdsim_initiatefortran_': (None, []),
     'cmdsim_measurementphase_': (None, []),
@@ -56,6 +61,7 @@ SYMBOLS = {
     'asd_commit': (C.c_int, [vp]),
     'asd_effective_field': (C.c_int, [vp, vp, vp, vp, vp]),
     'asd_sd_steps': (C.c_int, [vp, C.c_long, C.c_long]),
+    'asd_sd_run': (C.c_int, [vp, C.c_long, C.c_long, C.c_long, vp, C.POINTER(C.c_long)]),
     'asd_mc_sweeps': (C.c_int, [vp, C.c_char, C.c_long, C.c_long, C.c_double, C.c_double, vp]),
     'asd_set_mc_layout': (C.c_int, [vp, C.c_int]),
     'asd_mc_colouring': (C.c_int, [vp, c_int_p, c_int_p, c_int_p]),

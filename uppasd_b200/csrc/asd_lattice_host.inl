@@ -385,6 +385,10 @@ static int lattice_colours(asd_engine* e) {
                   const int* sh = S.cell_shift.data() + 3 * (i0 * S.maxslot + q);
                   const int j0 = S.cell_atom[i0 * S.maxslot + q] - 1;
                   const int c[3] = {c1, c2, c3};
+                  // an open direction shorter than the shift: no cell has this neighbour (e.g. BC 0 along a one-cell axis)
+                  bool exists = true;
+                  for (int a = 0; a < 3; a++) if (!d.periodic[a] && std::abs(sh[a]) >= Ng[a]) exists = false;
+                  if (!exists) continue;
                   int n[3];
                   for (int a = 0; a < 3; a++) n[a] = ((c[a] + sh[a]) % P[a] + P[a]) % P[a];
                   const int v = site(j0, n[0], n[1], n[2]);

@@ -247,6 +247,79 @@ void cudamcsim_evolve_(char* mode, unsigned int* nsweeps, unsigned int* first_sw
    copy_to_fortran(true);
 }
 
+// ---- pyasd's second caller (source/pyasd.f90): the bind(c) entry points the Python driver (uppasd.pyasd) binds, acting on
+//      the engine and the module arrays that FortranData_Initiate handed over.  Same names, argument order and meaning; every
+//      argument by reference, characters as char*.
+// relax_  (pyasd.f90:255-298): imode 'M' / 'H' -> mc_minimal: instep sweeps of mc_evolve at itemperature (mc_driver.f90:457-541);
+//         otherwise damping = idamping and sd_minimal(emomM, emom, mmom, instep, 1, itemperature): instep midpoint steps at
+//         itemperature with the module time step (sd_driver.f90:1162-1340).  itimestep is accepted and NOT used, exactly like the
+//         reference.  moments(3, natom, mensemble) = emomM on return; the module arrays emom / emomM / mmom are updated too.
+static long pyasd_step = 1;      // noise / draw counter: consecutive relax_ calls continue one random stream
+void relax_(double* moments, int* natom, int* mensemble, char* imode, int* instep, double* itemperature, double* itimestep,
+            double* idamping) {
+   using namespace legacy;
+   (void)itimestep;
+   if (!matrices_ok) { std::fprintf(stderr, "uppasd_b200: relax_: not initiated!\n"); return; }
+   if (*natom != eng->N || *mensemble != eng->M) { std::fprintf(stderr, "uppasd_b200: relax_: shape (%d, %d) is not the engine's (%d, %d)\n", *natom, *mensemble, eng->N, eng->M); std::exit(EXIT_FAILURE); }
+   const int N = eng->N, n = std::max(*instep, 0);
+   if (*imode == 'M' || *imode == 'H') {
+      // mc_evolve's extfield argument is hfield(1:3); the handed-over external_field array holds it for every atom
+      const double ext[3] = {fd.external_field ? fd.external_field[0] : 0.0, fd.external_field ? fd.external_field[1] : 0.0,
+                             fd.external_field ? fd.external_field[2] : 0.0};
+      if (asd_mc_sweeps(eng, *imode, n, pyasd_step, *itemperature, fd.temprescale ? *fd.temprescale : 1.0, ext)) die("relax_");
+   } else {
+      std::vector<double> lam(N, *idamping), temp(N, *itemperature);
+      if (asd_set_llg(eng, 1, *fd.delta_t, fd.Landeg, lam.data(), temp.data(), fd.temprescale ? *fd.temprescale : 1.0, *fd.mompar, eng->seed)) die("relax_");
+      if (asd_sd_steps(eng, n, pyasd_step)) die("relax_");
+      // back to the measurement-phase parameters (damping1 stays idamping in the reference; the legacy loop re-reads *fd.damping)
+      std::vector<double> lam0(N, *fd.damping);
+      if (asd_set_llg(eng, eng->SDEalgh, *fd.delta_t, fd.Landeg, fd.lambda1_array ? fd.lambda1_array : lam0.data(), fd.temperature,
+                      fd.temprescale ? *fd.temprescale : 1.0, *fd.mompar, eng->seed)) die("relax_");
+   }
+   pyasd_step += n;
+   copy_to_fortran(true);
+   std::memcpy(moments, fd.emomM, (size_t)3 * N * eng->M * sizeof(double));
+}
+
+// get_emom_ (pyasd.f90:316-328): moments = emom
+void get_emom_(double* moments, int* natom, int* mensemble) {
+   using namespace legacy;
+   if (!matrices_ok || *natom != eng->N || *mensemble != eng->M) { std::fprintf(stderr, "uppasd_b200: get_emom_: not initiated or wrong shape\n"); return; }
+   if (asd_get_moments(eng, moments, nullptr, nullptr)) die("get_emom_");
+}
+
+// put_emom_ (pyasd.f90:330-350): emom = moments, emom2 = emom, emomM = moments * mmom
+void put_emom_(const double* moments, int* natom, int* mensemble) {
+   using namespace legacy;
+   if (!matrices_ok || *natom != eng->N || *mensemble != eng->M) { std::fprintf(stderr, "uppasd_b200: put_emom_: not initiated or wrong shape\n"); return; }
+   const size_t NM = (size_t)eng->N * eng->M;
+   if (asd_get_moments(eng, nullptr, nullptr, fd.mmom)) die("put_emom_");      // the magnitudes the device holds (mompar may have changed them)
+   if (fd.emom != moments) std::memcpy(fd.emom, moments, 3 * NM * sizeof(double));
+   if (fd.emom2) std::memcpy(fd.emom2, moments, 3 * NM * sizeof(double));
+   for (size_t q = 0; q < NM; q++)
+      for (int a = 0; a < 3; a++) fd.emomM[3 * q + a] = moments[3 * q + a] * fd.mmom[q];
+   if (asd_set_moments(eng, moments, fd.mmom, fd.mmom0)) die("put_emom_");
+}
+
+// get_beff_ (pyasd.f90:356-369): call effective_field(); fields = beff
+void get_beff_(double* fields, int* natom, int* mensemble) {
+   using namespace legacy;
+   if (!matrices_ok || *natom != eng->N || *mensemble != eng->M) { std::fprintf(stderr, "uppasd_b200: get_beff_: not initiated or wrong shape\n"); return; }
+   if (asd_effective_field(eng, fields, nullptr, nullptr, nullptr)) die("get_beff_");
+   if (fd.beff && fd.beff != fields) std::memcpy(fd.beff, fields, (size_t)3 * eng->N * eng->M * sizeof(double));
+}
+
+// get_energy_ (pyasd.f90:505-517): call effective_field(energy); energy = energy / (Natom * Mensemble)
+void get_energy_(double* energy) {
+   using namespace legacy;
+   if (!matrices_ok) { std::fprintf(stderr, "uppasd_b200: get_energy_: not initiated!\n"); return; }
+   std::vector<double> en(eng->M, 0.0);
+   if (asd_effective_field(eng, nullptr, nullptr, nullptr, en.data())) die("get_energy_");
+   double tot = 0.0;
+   for (double v : en) tot += v;
+   *energy = tot / ((double)eng->N * eng->M);
+}
+
 void cmdsim_initiateconstants_(void) { cudamdsim_initiateconstants_(); }
 void cmdsim_initiatefortran_(void) { cudamdsim_initiatematrices_(); }
 void cmdsim_measurementphase_(void) { cudamdsim_measurementphase_(); }

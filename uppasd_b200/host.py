@@ -122,7 +122,8 @@ class Engine:
 
     # ---- compute -----------------------------------------------------------------------------------
     def get_moments(self, out=None):
-        """out: optional (emom, emomM, mmom) Fortran-ordered arrays to fill (e.g. views of pinned host memory)"""
+        """out: optional (emom, emomM, mmom) Fortran-ordered arrays to fill (e.g. views of pinned host memory); an entry that is
+        None is not copied (the C ABI takes NULL for it)"""
         if out is None:
             emom = np.zeros((3, self.N, self.M), order='F')
             emomM = np.zeros((3, self.N, self.M), order='F')
@@ -142,6 +143,15 @@ class Engine:
 
     def sd_steps(self, nsteps, first_step=1):
         self._chk(self.lib.asd_sd_steps(self.h, nsteps, first_step))
+
+    def sd_run(self, nsteps, first_step=1, sample_every=1, out=None):
+        """the measurement-phase loop in one call (asd_sd_run): msum(3, M, nsamples), sampled after every sample_every-th step;
+        one device-to-host copy and one synchronisation at the end.  out: optional Fortran-ordered landing array"""
+        ns = nsteps // sample_every if sample_every > 0 else 1
+        msum = out if out is not None else np.zeros((3, self.M, max(ns, 1)), order='F')
+        got = C.c_long(0)
+        self._chk(self.lib.asd_sd_run(self.h, nsteps, first_step, sample_every, _p(msum), C.byref(got)))
+        return msum[:, :, :got.value]
 
     def mc_sweeps(self, mode, nsweeps, temperature, first_sweep=1, temprescale=1.0, extfield=None):
         ef = np.ascontiguousarray(extfield, dtype=np.float64) if extfield is not None else None
@@ -445,3 +455,31 @@ class FortranHost:
         ef = (C.c_double * 3)(*extfield)
         self.lib.cudamcsim_evolve_(b(C.c_char(mode.encode())), b(C.c_uint(nsweeps)), b(C.c_uint(first_sweep)), b(C.c_double(temp)),
                                    b(C.c_double(temprescale)), ef, b(C.c_int(1 if upload else 0)))
+
+    # --- pyasd's entry points (source/pyasd.f90), called the way the Python package uppasd calls them ---
+    def relax(self, mode, nstep, temperature, timestep, damping):
+        """relax_: returns moments(3, N, M) = emomM"""
+        b = C.byref
+        mom = np.zeros((3, self.N, self.M), order='F')
+        self.lib.relax_(_p(mom), b(C.c_int(self.N)), b(C.c_int(self.M)), b(C.c_char(mode.encode())), b(C.c_int(nstep)),
+                        b(C.c_double(temperature)), b(C.c_double(timestep)), b(C.c_double(damping)))
+        return mom
+
+    def get_emom(self):
+        mom = np.zeros((3, self.N, self.M), order='F')
+        self.lib.get_emom_(_p(mom), C.byref(C.c_int(self.N)), C.byref(C.c_int(self.M)))
+        return mom
+
+    def put_emom(self, moments):
+        m = _f64(moments, (3, self.N, self.M))
+        self.lib.put_emom_(_p(m), C.byref(C.c_int(self.N)), C.byref(C.c_int(self.M)))
+
+    def get_beff(self):
+        f = np.zeros((3, self.N, self.M), order='F')
+        self.lib.get_beff_(_p(f), C.byref(C.c_int(self.N)), C.byref(C.c_int(self.M)))
+        return f
+
+    def get_energy(self):
+        en = C.c_double(0.0)
+        self.lib.get_energy_(C.byref(en))
+        return en.value
