@@ -260,3 +260,28 @@ def test_input_edge_cases(tmp_path):
     open(os.path.join(d, 'empty'), 'w').close()
     nn, red, xc, nnt = asdio.read_pairfile(os.path.join(d, 'empty'), atype, bas, inp['cell'], 1, 'C', 1)
     assert list(nn) == [0]
+
+
+def test_inpsd_keywords_outside_the_path_are_not_silent(tmp_path):
+    """a keyword that switches on physics this path does not implement must not run to completion with reference-
+    format files.  read_inpsd records Hamiltonian / dynamics keywords in `unserved` (driver.Simulation raises Unsupported),
+    measurements it does not write in `unwritten`, unknown keywords in `ignored`; keywords at their 'off' value are fine."""
+    from uppasd_b200 import asdio, driver
+    p = tmp_path / 'inpsd.dat'
+    p.write_text('simid x\nncell 2 2 2\ndo_dip 1\nstt A\ndo_bpulse 0\ndo_lsf N\nchir ./chirfile\ndo_sc C\ndo_ams N\nfoo_bar 3\n'
+                 'do_cumu A\nskyno Y\ngradtemp 1\nmult_axis N\n')
+    d = asdio.read_inpsd(str(p))
+    assert [k for k, _ in d['unserved']] == ['do_dip', 'stt', 'chir', 'gradtemp']
+    assert d['unwritten'] == ['do_sc', 'do_cumu A', 'skyno Y'] and d['ignored'] == ['foo_bar']
+    with pytest.raises(driver.Unsupported, match='do_dip 1, stt A'):
+        driver.Simulation(d, directory=str(tmp_path))
+    # every run directory of the reference that this path serves stays accepted (measurement-only extras are warnings)
+    import glob
+    import json
+    for f in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', '*.json')):
+        raw = json.load(open(f)).get('raw', {})
+        if 'inpsd.dat' in raw:
+            q = tmp_path / ('inpsd_' + os.path.basename(f))
+            q.write_text(raw['inpsd.dat'])
+            dd = asdio.read_inpsd(str(q))
+            assert dd['unserved'] == [] and dd['ignored'] == [], (f, dd['unserved'], dd['ignored'])

@@ -68,10 +68,51 @@ _SCALAR_FLAG = {'aunits', 'posfiletype', 'do_reduced', 'do_sortcoup', 'do_avrg',
 _FILES = {'posfile', 'momfile', 'exchange', 'dm', 'bq', 'anisotropy', 'restartfile'}
 
 
+# Reference keywords that change the Hamiltonian, the dynamics or what a measurement means, and that this path does NOT serve
+# (inputhandler.f90's `select case`; the reading modules of prn_*, sLLG, fieldpulse, temperature).  keyword -> the values that
+# leave the feature off.  Any other value is recorded in d['unserved'] and driver.Simulation refuses the run (Unsupported):
+# a run directory must never complete with reference-format files and different physics.
+_OFF = ('n', '0', 'f', '.false.', 'false')
+UNSERVED = {
+    # Hamiltonian terms outside SURVEY 8 (a)
+    'do_dip': _OFF, 'pd': None, 'biqdm': None, 'chir': None, 'sa': None, 'ring': None, 'fourx': None,
+    'do_lsf': _OFF, 'ind_mom_flag': _OFF, 'mult_axis': _OFF, 'random_anisotropy': _OFF, 'exc_inter': _OFF, 'do_ewald': _OFF,
+    'do_macro_cells': _OFF, 'do_efield': _OFF, 'efield': None, 'demag': _OFF, 'do_sparse': _OFF, 'exchangedlm': None,
+    'jij_scale': ('1', '1.0', '1.d0', '1.0d0'), 'dm_scale': ('1', '1.0', '1.d0', '1.0d0'), 'ea_model': _OFF, 'rdm_model': _OFF,
+    'locfield': _OFF, 'siteatomfield': None, 'do_fixed_mom': _OFF, 'do_mom_legacy': _OFF, 'multiscale': None,
+    # dynamics outside the two solvers / the constant uniform temperature
+    'stt': _OFF, 'do_she': _OFF, 'do_sot': _OFF, 'do_bpulse': ('0',), 'bpulsefile': None, 'do_qhb': _OFF, 'gradtemp': ('0',), 'grad': _OFF,
+    'do_3tm': _OFF, 'do_site_damping': _OFF, 'do_site_ip_damping': _OFF, 'damping2': ('0', '0.0', '0.d0', '0.0d0'),
+    'ip_damping2': ('0', '0.0', '0.d0', '0.0d0'), 'compensate_drift': ('0',), 'llg': ('1',), 'relaxtime': ('0', '0.0', '0.d0'),
+    'do_ld': _OFF, 'do_sld': _OFF, 'do_gneb': _OFF, 'do_kmc': _OFF, 'do_wl': _OFF, 'para_rng': _OFF, 'ziggurat': ('y', 't'),
+}
+# measurements of the reference this driver does not write: the run is the same physics, the files are absent.  Recorded in
+# d['unwritten']; the driver warns once per keyword (the reference's own regression directories switch many of them on).
+UNWRITTEN = {
+    'do_sc': _OFF, 'do_ams': _OFF, 'do_magdos': _OFF, 'do_autocorr': _OFF, 'do_currents': _OFF, 'do_pol': _OFF, 'do_loc_pol': _OFF,
+    'do_prn_beff': _OFF, 'do_prn_binteff': _OFF, 'do_prn_torques': _OFF, 'do_prn_induced': _OFF, 'do_stiffness': _OFF,
+    'do_dm_stiffness': _OFF, 'do_larmor_loc': _OFF, 'do_larmor_dos': _OFF, 'do_skyno_den': _OFF, 'do_skyno_cmass': _OFF,
+    'do_proj_skyno': _OFF, 'do_mc_avrg': _OFF, 'do_chiral': _OFF, 'do_thermfield': _OFF, 'do_spintemp': _OFF, 'do_bls': _OFF,
+    'do_sc_local_axis': _OFF, 'do_sc_proj': _OFF, 'do_sc_projch': _OFF, 'do_sc_bimag': _OFF, 'do_sc_complex': _OFF,
+    'do_sc_dosonly': _OFF, 'do_sc_proj_axis': _OFF, 'do_bls_local_axis': _OFF, 'do_qt_traj': _OFF, 'do_connected': _OFF,
+}
+# keywords of the reference that change nothing on this path (printing, memory, tolerances of other modes): accepted silently
+_NEUTRAL = {'do_meminfo', 'do_storeham', 'do_hoc_debug', 'evolveout', 'heisout', 'logsamp', 'real_time_measure', 'gpu_rng', 'use_vsl',
+            'block_size', 'block_size_x', 'block_size_y', 'block_size_z', 'mseed', 'set_landeg', 'mcavrg_step', 'mcavrg_buff',
+            'natoms', 'ntypes', 'do_anisotropy', 'do_prn_poscar', 'prn_ovf', 'read_ovf', 'ip_nstep', 'calc_jtensor',
+            # parameters of measurements that are themselves recorded as unwritten / of modes that are refused
+            'sc_nstep', 'sc_step', 'sc_sep', 'sc_average', 'sc_window_fun', 'sc_local_axis_mix', 'qpoints', 'qfile', 'bls_nstep',
+            'bls_step', 'ene_step', 'ene_buff', 'acfile', 'max_pol_nn', 'jvec', 'adibeta', 'beff_step', 'beff_buff', 'binteff_step',
+            'binteff_buff', 'torques_step', 'torques_buff', 'thermfield_step', 'thermfield_buff', 'larm_step', 'larm_buff',
+            'larm_dos_size', 'pol_step', 'pol_buff', 'current_step', 'current_buff', 'ind_step', 'ind_buff', 'spintemp_step'}
+
+
 def read_inpsd(path):
-    """Keywords of the hot-path slice; anything else is ignored, as the reference's per-module `select case`
-    passes ignore keywords of other modules."""
+    """Keywords of the hot-path slice.  A keyword of the reference that switches on physics or a measurement outside this slice
+    is recorded in d['unserved'] (driver.Simulation raises Unsupported for it), a measurement this driver does not write in
+    d['unwritten'], every other unrecognised keyword in d['ignored'] (the driver warns about both kinds)."""
     d = defaults()
+    d['unserved'], d['unwritten'], d['ignored'] = [], [], []
     base = os.path.dirname(os.path.abspath(path))
     with open(path) as fh:
         lines = fh.read().splitlines()
@@ -134,8 +175,25 @@ def read_inpsd(path):
                     d['trajectories'].append((int(_num(r[0])), int(_num(r[1])), int(_num(r[2]))))
             elif key == 'map_multiple':
                 d['map_multiple'] = _flag(v[0]) in ('T', 'Y')
+            elif key == 'do_cumu' or key == 'skyno':
+                pass
+            elif key in UNSERVED:
+                off = UNSERVED[key]
+                val = v[0].lower().strip('.') if v else ''
+                if off is None or val not in [o.strip('.') for o in off]:
+                    d['unserved'].append((key, ' '.join(v)))
+            elif key in UNWRITTEN:
+                val = v[0].lower().strip('.') if v else ''
+                if val not in [o.strip('.') for o in UNWRITTEN[key]]:
+                    d['unwritten'].append(key)
+            elif key not in _NEUTRAL:
+                d['ignored'].append(key)
         except (IndexError, ValueError) as exc:
             raise InputError('cannot read keyword %s in %s: %s' % (key, path, exc))
+    if d['do_cumu'] not in ('Y', 'N'):
+        d['unwritten'].append('do_cumu ' + d['do_cumu'])      # 'A' (cumulants of every ensemble) is not written here
+    if d['skyno'] not in ('N', 'T'):
+        d['unwritten'].append('skyno ' + d['skyno'])          # 'Y' (finite-difference skyrmion number): only the triangulated 'T' form
     if d['ipsdealgh'] == -1:
         d['ipsdealgh'] = d['sdealgh']             # uppasd.f90:885
     return d

@@ -35,6 +35,13 @@ class Simulation:
         self.c = dict(consts or CONSTANTS)
         if inp['aunits'] == 'Y':                       # inputhandler.f90:1685-1704
             self.c = dict(gama=1.0, k_bolt=1.0, mub=1.0, mry=1.0)
+        if inp.get('unserved'):
+            raise Unsupported('inpsd.dat switches on features outside the hot path served here: '
+                              + ', '.join('%s %s' % kv for kv in inp['unserved']))
+        for key in inp.get('unwritten', []):
+            warnings.warn('inpsd.dat asks for %r: that measurement is not written by this driver (the dynamics are unaffected)' % key)
+        for key in inp.get('ignored', []):
+            warnings.warn('inpsd.dat keyword %r is not known to this driver and was ignored' % key)
         if inp['do_ralloy'] != 0:
             raise Unsupported('do_ralloy is outside the hot path served here')
         if inp['do_jtensor'] == 1 and (inp['mode'] != 'S' or inp['ip_mode'] not in ('N', 'S')):
