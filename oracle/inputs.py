@@ -38,7 +38,7 @@ DEFAULTS = dict(
     mensemble=1, tseed=1, sdealgh=1, initmag=3, mode='S', temp=0.0, nstep=1, damping=0.05, timestep=1.0e-16,
     hfield=(0.0, 0.0, 0.0), do_reduced='N', do_sortcoup='N', mompar=0, landeg_glob=2.0, do_dm=0, do_bq=0, do_jtensor=0,
     do_anisotropy=0, mcnstep=0, avrg_step=100, cumu_step=50, cumu_buff=10, do_avrg='N', do_cumu='N',
-    plotenergy=0, map_multiple=False, gpu_mode=0, ip_mode='N', aunits='N',
+    plotenergy=0, map_multiple=False, gpu_mode=0, ip_mode='N', aunits='N', do_ralloy=0,
 )
 
 
@@ -86,6 +86,8 @@ def read_inpsd(path):
             d['mensemble'] = int(v[0])
         elif key == 'tseed':
             d['tseed'] = int(v[0])
+        elif key == 'do_ralloy':
+            d['do_ralloy'] = int(v[0])
         elif key == 'sdealgh':
             d['sdealgh'] = int(v[0])
         elif key == 'initmag':
@@ -258,3 +260,97 @@ def load_fixture(fx):
     if inp.get('do_jtensor', 0) == 1:
         ex = lambda S: read_tensor_file(fx['jfile'], nt, atype_inp, S['bas'], inp['cell'], inp['maptype'], inp['posfiletype'])
     return inp, bas, atype_inp, ammom, aemom, landeg, ex, mk('dmfile', 3, False), mk('bqfile', 1, False), aniso
+
+
+# ---- random alloys (do_ralloy 1) ------------------------------------------------------------------------------------
+def read_positions_alloy(path, cell, posfiletype='C'):
+    """read_positions_alloy (inputhandler_ext.f90:139-216): rows `site type chem conc x y z`.
+    Returns bas(3,NA), atype_inp(NA), nch(NA), chconc(NA,Nchmax)."""
+    rows = _rows(path) if isinstance(path, str) else path
+    na = max(int(r[0]) for r in rows)
+    nchmax = max(int(r[2]) for r in rows)
+    bas = np.zeros((3, na), order='F')
+    atype = np.zeros(na, dtype=np.int32)
+    nch = np.zeros(na, dtype=np.int32)
+    chconc = np.zeros((na, nchmax), order='F')
+    for r in rows:
+        isite, itype, ichem = int(r[0]), int(r[1]), int(r[2])
+        p = np.array([_f(x) for x in r[4:7]])
+        if posfiletype == 'D':
+            p = p[0] * cell[0] + p[1] * cell[1] + p[2] * cell[2]
+        bas[:, isite - 1] = p
+        nch[isite - 1] = max(nch[isite - 1], ichem)
+        atype[isite - 1] = itype
+        chconc[isite - 1, ichem - 1] = _f(r[3])
+    return bas, atype, nch, chconc
+
+
+def read_moments_alloy(path, na, nchmax, landeg_glob=2.0):
+    """read_moments (inputhandler_ext.f90:228-321), set_landeg 0, no LSF / induced moments: rows `site chem mom ex ey ez`.
+    Returns ammom_inp(NA,Nchmax), aemom_inp(3,NA,Nchmax), Landeg_ch(NA,Nchmax)."""
+    ammom = np.zeros((na, nchmax), order='F')
+    aemom = np.zeros((3, na, nchmax), order='F')
+    for r in (_rows(path) if isinstance(path, str) else path):
+        isite, ichem = int(r[0]), int(r[1])
+        ammom[isite - 1, ichem - 1] = _f(r[2])
+        e = np.array([_f(x) for x in r[3:6]])
+        nrm = np.sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2])
+        aemom[:, isite - 1, ichem - 1] = e / nrm
+    return ammom, aemom, np.full((na, nchmax), landeg_glob, order='F')
+
+
+def read_pair_file_alloy(path, nt, nchmax, atype_inp, bas, cell, maptype, posfiletype):
+    """read_exchange with do_ralloy 1 (inputhandler_ext.f90:444-627, the `else` branches at :487-531): rows
+    `isite jsite ichem jchem r1 r2 r3 J`; the shell is identified by the vector as for do_ralloy 0, the coupling is filed under
+    jc(itype, shell, ichem, jchem).  Returns nn(NT), redcoord(NT,ms,3), xc(1,NT,ms,Nchmax,Nchmax), nntype(NT,ms)."""
+    rows = _rows(path) if isinstance(path, str) else path
+    tol = 1.0e-5
+    nn = np.zeros(nt, dtype=np.int32)
+    red = [[] for _ in range(nt)]
+    val = [[] for _ in range(nt)]
+    ntyp = [[] for _ in range(nt)]
+    for r in rows:
+        isite, jsite, ichem, jchem = int(r[0]), int(r[1]), int(r[2]), int(r[3])
+        r_tmp = [_f(x) for x in r[4:7]]
+        j_tmp = _f(r[7])
+        itype = int(atype_inp[isite - 1])
+        r_red = _neigh_vec(r_tmp, isite, jsite, bas, cell, maptype, posfiletype)
+        unique = True
+        for ish in range(nn[itype - 1]):
+            c = red[itype - 1][ish]
+            norm = (r_red[0] - c[0]) ** 2 + (r_red[1] - c[1]) ** 2 + (r_red[2] - c[2]) ** 2
+            if norm < tol:
+                unique = False
+                val[itype - 1][ish][ichem - 1, jchem - 1] = j_tmp
+        if unique:
+            nn[itype - 1] += 1
+            red[itype - 1].append(r_red)
+            m = np.zeros((nchmax, nchmax))
+            m[ichem - 1, jchem - 1] = j_tmp
+            val[itype - 1].append(m)
+            ntyp[itype - 1].append(int(atype_inp[jsite - 1]))
+    ms = int(nn.max())
+    redcoord = np.zeros((nt, ms, 3), order='F')
+    xc = np.zeros((1, nt, ms, nchmax, nchmax), order='F')
+    nntype = np.zeros((nt, ms), dtype=np.int32, order='F')
+    for t in range(nt):
+        for s in range(nn[t]):
+            redcoord[t, s, :] = red[t][s]
+            xc[0, t, s] = val[t][s]
+            nntype[t, s] = ntyp[t][s]
+    return nn, redcoord, xc, nntype
+
+
+def load_alloy_fixture(fx):
+    """argument tuple of oracle.orc.build_alloy_system from a fixture with raw token rows (posfile, momfile, jfile)"""
+    inp = dict(fx['inp'])
+    inp['cell'] = np.array(inp['cell'], dtype=float)
+    inp['ncell'] = tuple(inp['ncell'])
+    inp['bc'] = tuple(inp['bc'])
+    inp['hfield'] = tuple(inp['hfield'])
+    bas, atype_inp, nch, chconc = read_positions_alloy(fx['posfile'], inp['cell'], inp['posfiletype'])
+    na, nchmax = chconc.shape
+    nt = int(atype_inp.max())
+    ammom, aemom, landeg = read_moments_alloy(fx['momfile'], na, nchmax, inp['landeg_glob'])
+    ex = lambda S: read_pair_file_alloy(fx['jfile'], nt, nchmax, atype_inp, S['bas'], inp['cell'], inp['maptype'], inp['posfiletype'])
+    return inp, bas, atype_inp, nch, chconc, ammom, aemom, landeg, ex

@@ -166,6 +166,99 @@ def build_system(inp, bas, atype_inp, ammom_inp, aemom_inp, landeg_ch, exchange,
     return S
 
 
+def setup_chemicaldata(NA, ncell, nch, chconc, tseed):
+    """setup_chemicaldata (geometry.f90:190-329), do_ralloy 1: chemical type of every site of the full supercell.
+    The generator is re-initialised with tseed just before (uppasd.f90:903-906); per basis site Ncell uniforms are drawn and
+    the cells are dealt to the species in the order of repeated maxloc(rn) with the maximum zeroed after each pick (:266-270),
+    i.e. by descending random number, the lowest index first among equal values; species ich gets qch = nint(conc * Ncell)
+    consecutive picks (:251-265,271-276).  Returns achtype(Natom_full), 0 = vacancy (dilute system)."""
+    n1, n2, n3 = ncell
+    ncellt = n1 * n2 * n3
+    achtype = np.zeros(NA * ncellt, dtype=np.int32)
+    rng_init(tseed)
+    for ia in range(1, NA + 1):
+        qch = [int(np.rint(chconc[ia - 1, ich] * ncellt)) if ich < nch[ia - 1] else 0 for ich in range(chconc.shape[1])]
+        rn = rng_uniform(ncellt)
+        atoms = np.argsort(-rn, kind='stable') + 1            # atoms(i, ia) = i-th largest random number's cell
+        ns = 1
+        for ich in range(1, nch[ia - 1] + 1):
+            ne = ns + qch[ich - 1] - 1
+            for i in range(ns, min(ne, ncellt) + 1):
+                achtype[(atoms[i - 1] - 1) * NA + ia - 1] = ich
+            ns = ne + 1
+    return achtype
+
+
+def build_alloy_system(inp, bas, atype_inp, nch, chconc, ammom_inp, aemom_inp, landeg_ch, exchange):
+    """build_system for a random alloy (do_ralloy 1, non-dilute, scalar exchange only): occupancy (setup_chemicaldata), the
+    neighbour map of the full supercell, the mount with chemistry-dependent couplings (orc_mount_alloy) and the moments of
+    setup_moment / magninit's Initmag 3 for alloys (magnetizationinit.f90:244-258,586-597).  nHam = Natom."""
+    L = lib()
+    N1, N2, N3 = inp['ncell']
+    NA = bas.shape[1]
+    N = NA * N1 * N2 * N3
+    M = inp['mensemble']
+    cell = np.array(inp['cell'], dtype=np.float64)
+    S = dict(Natom=N, NA=NA, NT=int(atype_inp.max()), ncell=(N1, N2, N3), cell=cell, bc=inp['bc'], Mensemble=M)
+    S['const'] = dict(AUNITS if inp.get('aunits', 'N') == 'Y' else CONST)
+    S['bas'] = np.asfortranarray(bas, dtype=np.float64).copy(order='F')
+    S['atype_inp'] = np.ascontiguousarray(atype_inp, dtype=np.int32)
+    anumb_inp = np.arange(1, NA + 1, dtype=np.int32)
+    S['coord'] = np.zeros((3, N), order='F')
+    S['atype'] = np.zeros(N, dtype=np.int32)
+    S['anumb'] = np.zeros(N, dtype=np.int32)
+    c1, c2, c3 = (np.ascontiguousarray(cell[i]) for i in range(3))
+    L.orc_setup_geometry(NA, N1, N2, N3, _p(c1), _p(c2), _p(c3), _p(S['bas']), _p(S['atype_inp']), _p(anumb_inp),
+                         _p(S['coord']), _p(S['atype']), _p(S['anumb']))
+    achtype = setup_chemicaldata(NA, (N1, N2, N3), nch, chconc, inp['tseed'])
+    if (achtype == 0).any():
+        raise ValueError('dilute alloys (vacant sites) are not restated')
+    # geometry.f90:285-300 for a fully occupied supercell: acellnumb = identity
+    S['achtype'] = achtype
+    S['asite_ch'] = S['anumb'].copy()
+    S['atype_ch'] = S['atype'].copy()
+    S['achem_ch'] = achtype.copy()
+    S['nHam'] = N
+    S['aHam'] = np.arange(1, N + 1, dtype=np.int32)
+    S['do_jtensor'] = 0
+    nn, redcoord, xc, nntype = exchange(S) if callable(exchange) else exchange
+    nn = np.ascontiguousarray(nn, dtype=np.int32)
+    ms = redcoord.shape[1]
+    redcoord = np.asfortranarray(redcoord, dtype=np.float64)
+    nnt = np.asfortranarray(nntype, dtype=np.int32) if nntype is not None else None
+    h = C.c_void_p(L.orc_nm_create(N, S['NT'], NA, N1, N2, N3, _p(c1), _p(c2), _p(c3), C.c_char(S['bc'][0].encode()),
+                                   C.c_char(S['bc'][1].encode()), C.c_char(S['bc'][2].encode()), _p(S['atype']), _p(S['bas']),
+                                   ms, inp['sym'], _p(nn), _p(redcoord), _p(nnt)))
+    z = L.orc_nm_max_no_neigh(h)
+    nlist = np.zeros((z, N), dtype=np.int32, order='F')
+    nlistsize = np.zeros(N, dtype=np.int32)
+    ncoup = np.zeros((1, z, N), order='F')
+    xc = np.asfortranarray(xc, dtype=np.float64)
+    am = np.asfortranarray(ammom_inp, dtype=np.float64)
+    nchmax = am.shape[1]
+    L.orc_mount_alloy(h, N, S['NT'], NA, nchmax, _p(S['atype_ch']), _p(S['asite_ch']), _p(S['achem_ch']), z, _p(nn), _p(xc), _p(am),
+                      1, 1, int(inp['do_sortcoup'] == 'Y'), int(inp['map_multiple']), _d(consts(S)['mry']), _d(consts(S)['mub']),
+                      _p(nlistsize), _p(nlist), _p(ncoup))
+    L.orc_nm_free(h)
+    S['exchange'] = dict(list=nlist, listsize=nlistsize, coup=np.asfortranarray(ncoup[0]), z=z)
+    S['dm'] = S['bq'] = S['aniso'] = None
+    S['ammom_inp'] = am
+    # setup_moment (magnetizationinit.f90:586-597) and Initmag 3 (:244-258) for alloys
+    site, chem = S['anumb'] - 1, achtype - 1
+    mm = np.abs(am[site, chem])
+    S['mmom'] = np.asfortranarray(np.repeat(mm[:, None], M, axis=1))
+    S['mmom0'] = S['mmom'].copy(order='F')
+    S['mmomi'] = np.asfortranarray(1.0 / S['mmom'])
+    S['Landeg'] = np.asfortranarray(landeg_ch)[site, chem] * 0.5
+    ae = np.asfortranarray(aemom_inp)[:, site, chem]
+    S['emom'] = np.asfortranarray(np.repeat(ae[:, :, None], M, axis=2))
+    S['emomM'] = np.asfortranarray(S['emom'] * S['mmom'][None])
+    S['external_field'] = np.zeros((3, N, M), order='F')
+    for a in range(3):
+        S['external_field'][a, :, :] = inp['hfield'][a]
+    return S
+
+
 def ham_struct(S):
     """OrcHam view over a system dict (keeps references alive in S['_keep'])."""
     H = OrcHam()

@@ -381,6 +381,63 @@ void orc_mount(void* h, int Natom, int NT, int NA, int nHam, const int* anumb, c
    }
 }
 
+// hamiltonianinit.f90:985-1157 (setup_neighbour_hamiltonian), the do_ralloy = 1 branch (:1075-1084) for a NON-DILUTE random alloy
+// (every site occupied: Natom = Natom_full, acellnumb is the identity, so setup_nm's map is the one of do_ralloy = 0,
+// neighbourmap.f90:257-262,309).  conf_num = 1, no LSF, nHam = Natom.
+//   xc(hdim, NT, max_no_shells, Nchmax, Nchmax); ammom_inp(NA, Nchmax); atype_ch / asite_ch / achem_ch (Natom):
+//   ncoup(:, ncount, i) = xc(:, atype_ch(i), k, achem_ch(i), achem_ch(j)) * fc2 / m(asite_ch(i), achem_ch(i))**lexp
+//                                                                                / m(asite_ch(j), achem_ch(j))**lexp
+void orc_mount_alloy(void* h, int Natom, int NT, int NA, int Nchmax, const int* atype_ch, const int* asite_ch, const int* achem_ch,
+                     int max_no_neigh, const int* nn, const double* xc, const double* ammom_inp, int hdim, int lexp,
+                     int do_sortcoup, int map_multiple, double mry, double mub, int* nlistsize, int* nlist, double* ncoup) {
+   auto* R = (NeighbourMap*)h;
+   const int max_no_shells = R->max_no_shells, maxNN = R->maxNN;
+   auto NM = [&](long iat, int ish, int e) { return R->nm[(iat - 1) + (size_t)Natom * ((ish - 1) + (size_t)maxNN * (e - 1))]; };
+   auto NMDIM = [&](int ish, long iat) { return R->nmdim[(ish - 1) + (size_t)maxNN * (iat - 1)]; };
+   auto NL = [&](int l, long i) -> int& { return nlist[(l - 1) + (size_t)max_no_neigh * (i - 1)]; };
+   auto NC = [&](int a, int l, long i) -> double& { return ncoup[(a - 1) + (size_t)hdim * ((l - 1) + (size_t)max_no_neigh * (i - 1))]; };
+   auto XC = [&](int a, int it, int k, int ci, int cj) {
+      return xc[(a - 1) + (size_t)hdim * ((it - 1) + (size_t)NT * ((k - 1) + (size_t)max_no_shells * ((ci - 1) + (size_t)Nchmax * (cj - 1))))];
+   };
+   auto AM = [&](int site, int chem) { return ammom_inp[(site - 1) + (size_t)NA * (chem - 1)]; };
+   for (size_t q = 0; q < (size_t)hdim * max_no_neigh * Natom; q++) ncoup[q] = 0.0;
+   const double fc2 = 2.0 * mry / mub;
+   for (long i = 1; i <= Natom; i++) {
+      int ncount = 1;
+      for (int k = 1; k <= nn[atype_ch[i - 1] - 1]; k++)
+         for (int j = 1; j <= NMDIM(k, i); j++) {
+            int nb = NM(i, k, j);
+            if (nb > 0) {
+               bool exis = false;
+               for (int l = 1; l <= ncount - 1; l++)
+                  if (NL(l, i) == nb) exis = true;
+               if (!exis || map_multiple) {
+                  NL(ncount, i) = nb;
+                  const double mi = AM(asite_ch[i - 1], achem_ch[i - 1]), mj = AM(asite_ch[nb - 1], achem_ch[nb - 1]);
+                  if (std::fabs(mi * mj) < (double)1e-6f) {
+                     for (int a = 1; a <= hdim; a++) NC(a, ncount, i) = 0.0;
+                  } else {
+                     double pi_ = (lexp == 2) ? mi * mi : mi, pj_ = (lexp == 2) ? mj * mj : mj;
+                     for (int a = 1; a <= hdim; a++)
+                        NC(a, ncount, i) = XC(a, atype_ch[i - 1], k, achem_ch[i - 1], achem_ch[nb - 1]) * fc2 / pi_ / pj_;
+                  }
+                  ncount++;
+               }
+            }
+         }
+      nlistsize[i - 1] = ncount - 1;
+   }
+   if (do_sortcoup) {
+      for (long i = 1; i <= Natom; i++)
+         for (int j = 1; j <= nlistsize[i - 1]; j++)
+            for (int k = 1; k <= nlistsize[i - 1] - j; k++)
+               if (NL(k, i) > NL(k + 1, i)) {
+                  int t = NL(k, i); NL(k, i) = NL(k + 1, i); NL(k + 1, i) = t;
+                  for (int a = 1; a <= hdim; a++) { double c = NC(a, k, i); NC(a, k, i) = NC(a, k + 1, i); NC(a, k + 1, i) = c; }
+               }
+   }
+}
+
 // hamiltonianinit.f90:895-913 (setup_anisotropies, do_ralloy=0, no random anisotropy, mult_axis='N').
 // anisotropytype(NA), anisotropy(NA,6) column-major; outputs taniso(N), eaniso(3,N), kaniso(2,N), sb(N).
 void orc_setup_anisotropies(int Natom, int NA, const int* anumb, const int* anisotropytype, const double* anisotropy,

@@ -37,7 +37,7 @@ def fixture(dirname, inpname='inpsd.dat', extra_inp=None, subst=None):
     if extra_inp:
         inp.update(extra_inp)
     files = inp.pop('files')
-    out = {'source': 'tests/%s/%s' % (dirname, inpname)}
+    out = {'source': os.path.normpath('tests/%s/%s' % (dirname, inpname))}
     keymap = {'posfile': 'posfile', 'momfile': 'momfile', 'exchange': 'jfile', 'dm': 'dmfile', 'bq': 'bqfile',
               'anisotropy': 'kfile'}
     for k, v in files.items():
@@ -172,6 +172,13 @@ def main():
         'averages': {'800': [-8.05438058e-05, -6.4699084e-05, -6.60907331e-05, 0.000122642819]},
         'tol': 1e-8, 'yaml': 'tests/regulartests.yaml:158-170'}
     fx['scsurf'] = f
+    # --- random alloys (do_ralloy 1; BASELINE config 3).  The reference's test tree has no random-alloy case (no golden output):
+    #     the INPUTS come from its examples, the expected values are properties (species counts, symmetric couplings) and the
+    #     agreement of the product with the oracle's restatement of setup_chemicaldata / setup_neighbour_hamiltonian.
+    #     examples/Mappings/RandomAlloy: bcc, two sites with Fe(80)Co(20) / Fe(20)Co(80)-like occupancy, 2 shells, sym 1
+    fx['randomalloy'] = fixture('../examples/Mappings/RandomAlloy')
+    #     examples/Mappings/FeCo/random: bcc primitive cell, one site, 50/50, z = 258 (the FeCo couplings of tests/FeCo)
+    fx['feco_random'] = fixture('../examples/Mappings/FeCo/random')
     for k, v in fx.items():
         with open(os.path.join(HERE, k + '.json'), 'w') as fh:
             json.dump(v, fh, indent=1, default=lambda o: list(o))

@@ -643,7 +643,7 @@ def test_pyasd_entry_points():
     beff = fh.get_beff()
     assert np.abs(beff - rb).max() <= 1e-12 * np.abs(rb).max()
     assert np.array_equal(fh.arr['beff'], beff)
-    assert abs(fh.get_energy() - ren.sum() / (N * M)) <= 1e-12 * abs(ren.sum() / (N * M))
+    assert abs(fh.get_energy() - ren / (N * M)) <= 1e-12 * abs(ren / (N * M))      # the oracle's energy: all atoms, all ensembles
     # relax_ in SD mode: solver 1 whatever SDEalgh the run uses, damping of the call, the module's delta_t
     mom = fh.relax('S', 25, 0.0, 123.0, 0.3)
     st = orc.SdState(S, 1, inp['timestep'], 0.3)

@@ -95,6 +95,7 @@ UNWRITTEN = {
     'do_proj_skyno': _OFF, 'do_mc_avrg': _OFF, 'do_chiral': _OFF, 'do_thermfield': _OFF, 'do_spintemp': _OFF, 'do_bls': _OFF,
     'do_sc_local_axis': _OFF, 'do_sc_proj': _OFF, 'do_sc_projch': _OFF, 'do_sc_bimag': _OFF, 'do_sc_complex': _OFF,
     'do_sc_dosonly': _OFF, 'do_sc_proj_axis': _OFF, 'do_bls_local_axis': _OFF, 'do_qt_traj': _OFF, 'do_connected': _OFF,
+    'do_projch_avrg': _OFF,
 }
 # keywords of the reference that change nothing on this path (printing, memory, tolerances of other modes): accepted silently
 _NEUTRAL = {'do_meminfo', 'do_storeham', 'do_hoc_debug', 'evolveout', 'heisout', 'logsamp', 'real_time_measure', 'gpu_rng', 'use_vsl',
@@ -104,7 +105,8 @@ _NEUTRAL = {'do_meminfo', 'do_storeham', 'do_hoc_debug', 'evolveout', 'heisout',
             'sc_nstep', 'sc_step', 'sc_sep', 'sc_average', 'sc_window_fun', 'sc_local_axis_mix', 'qpoints', 'qfile', 'bls_nstep',
             'bls_step', 'ene_step', 'ene_buff', 'acfile', 'max_pol_nn', 'jvec', 'adibeta', 'beff_step', 'beff_buff', 'binteff_step',
             'binteff_buff', 'torques_step', 'torques_buff', 'thermfield_step', 'thermfield_buff', 'larm_step', 'larm_buff',
-            'larm_dos_size', 'pol_step', 'pol_buff', 'current_step', 'current_buff', 'ind_step', 'ind_buff', 'spintemp_step'}
+            'larm_dos_size', 'pol_step', 'pol_buff', 'current_step', 'current_buff', 'ind_step', 'ind_buff', 'spintemp_step',
+            'magdos_freq', 'magdos_hfreq', 'magdos_lfreq', 'magdos_sigma', 'eta_max', 'eta_min'}
 
 
 def read_inpsd(path):
@@ -261,6 +263,69 @@ def read_pairfile(path, atype, bas, cell, maptype, posfiletype, ncomp):
             red[t, s] = vec
             xc[:, t, s] = val
             nntype[t, s] = jt
+    return nn, red, xc, nntype
+
+
+# ---- random alloys (do_ralloy 1): the three files carry a chemical-type column (inputhandler_ext.f90:139-216, 228-321, 487-531)
+def read_posfile_alloy(path, cell, posfiletype='C'):
+    """rows `site type chem concentration x y z`: bas(3,NA), atype(NA), nch(NA), chconc(NA,Nchmax)"""
+    rows = _data_rows(path)
+    na = max(int(r[0]) for r in rows)
+    nchmax = max(int(r[2]) for r in rows)
+    bas, atype = np.zeros((3, na)), np.zeros(na, dtype=np.int32)
+    nch, chconc = np.zeros(na, dtype=np.int32), np.zeros((na, nchmax))
+    for r in rows:
+        i, ich = int(r[0]) - 1, int(r[2])
+        p = np.array([_num(x) for x in r[4:7]])
+        bas[:, i] = p[0] * cell[0] + p[1] * cell[1] + p[2] * cell[2] if posfiletype == 'D' else p
+        atype[i] = int(r[1])
+        nch[i] = max(nch[i], ich)
+        chconc[i, ich - 1] = _num(r[3])
+    return bas, atype, nch, chconc
+
+
+def read_momfile_alloy(path, na, nchmax, landeg_glob=2.0):
+    """rows `site chem moment ex ey ez`: ammom(NA,Nchmax), aemom(3,NA,Nchmax) normalised, Landeg(NA,Nchmax)"""
+    ammom, aemom = np.zeros((na, nchmax)), np.zeros((3, na, nchmax))
+    for r in _data_rows(path):
+        i, c = int(r[0]) - 1, int(r[1]) - 1
+        ammom[i, c] = _num(r[2])
+        e = np.array([_num(x) for x in r[3:6]])
+        aemom[:, i, c] = e / np.sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2])
+    return ammom, aemom, np.full((na, nchmax), landeg_glob)
+
+
+def read_pairfile_alloy(path, atype, nchmax, bas, cell, maptype, posfiletype):
+    """rows `isite jsite ichem jchem r1 r2 r3 J`: nn(NT), redcoord(NT,maxshell,3), xc(NT,maxshell,Nchmax,Nchmax), nntype(NT,maxshell);
+    shells are told apart by their vector exactly as in read_pairfile, the value is filed under (ichem, jchem)"""
+    nt = int(atype.max())
+    shells = [[] for _ in range(nt)]
+    for r in _data_rows(path):
+        isite, jsite, ichem, jchem = int(r[0]), int(r[1]), int(r[2]), int(r[3])
+        rt = [_num(x) for x in r[4:7]]
+        if maptype == 2:
+            vec = np.array([bas[a, jsite - 1] - bas[a, isite - 1] + cell[0][a] * rt[0] + cell[1][a] * rt[1] + cell[2][a] * rt[2]
+                            for a in range(3)])
+        elif posfiletype == 'D':
+            vec = np.array([rt[0] * cell[0][a] + rt[1] * cell[1][a] + rt[2] * cell[2][a] for a in range(3)])
+        else:
+            vec = np.array(rt)
+        lst = shells[int(atype[isite - 1]) - 1]
+        for ent in lst:
+            if ((vec - ent[0]) ** 2).sum() < 1.0e-5:
+                ent[1][ichem - 1, jchem - 1] = _num(r[7])
+                break
+        else:
+            m = np.zeros((nchmax, nchmax))
+            m[ichem - 1, jchem - 1] = _num(r[7])
+            lst.append([vec, m, int(atype[jsite - 1])])
+    nn = np.array([len(s) for s in shells], dtype=np.int32)
+    ms = max(1, int(nn.max()))
+    red, xc = np.zeros((nt, ms, 3)), np.zeros((nt, ms, nchmax, nchmax))
+    nntype = np.zeros((nt, ms), dtype=np.int32)
+    for t, lst in enumerate(shells):
+        for s, (vec, m, jt) in enumerate(lst):
+            red[t, s], xc[t, s], nntype[t, s] = vec, m, jt
     return nn, red, xc, nntype
 
 

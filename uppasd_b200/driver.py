@@ -12,10 +12,11 @@ inpsd.dat this path serves, with every per-step loop body replaced by calls into
 Only what the hot path needs is here; keywords outside it are ignored, features outside it are refused loudly.
 """
 import os
+import warnings
 
 import numpy as np
 
-from . import asdio, host, lattice, observables, refrng
+from . import alloy, asdio, host, lattice, observables, refrng
 
 # source/Parameters/constants.f90:14-29
 CONSTANTS = dict(gama=1.760859644e11, k_bolt=1.38064852e-23, mub=9.274009994e-24, mry=2.179872325e-21)
@@ -42,8 +43,20 @@ class Simulation:
             warnings.warn('inpsd.dat asks for %r: that measurement is not written by this driver (the dynamics are unaffected)' % key)
         for key in inp.get('ignored', []):
             warnings.warn('inpsd.dat keyword %r is not known to this driver and was ignored' % key)
-        if inp['do_ralloy'] != 0:
-            raise Unsupported('do_ralloy is outside the hot path served here')
+        if inp['map_multiple']:
+            # the device table builder drops a second coupling between the same pair like the reference does WITHOUT map_multiple
+            # (hamiltonianinit.f90:1059); keeping duplicates is not implemented, so refuse rather than mount shorter lists
+            raise Unsupported('map_multiple T (several couplings between one pair of atoms) is not served')
+        if inp['do_ralloy'] not in (0, 1):
+            raise Unsupported('do_ralloy %d' % inp['do_ralloy'])
+        if inp['do_ralloy'] == 1:
+            # random alloy: occupancy from the reference's generator, one coupling row per atom (uppasd_b200/alloy.py)
+            if inp.get('dm') or inp.get('bq') or inp.get('anisotropy') or inp['do_jtensor'] == 1:
+                raise Unsupported('do_ralloy 1 is served for scalar exchange only (no dm / bq / anisotropy / do_jtensor)')
+            if inp['do_reduced'] == 'Y':
+                raise Unsupported('do_ralloy 1 needs one Hamiltonian row per atom (do_reduced N)')
+            if inp['initmag'] != 3:
+                raise Unsupported('do_ralloy 1: initmag %d (only 3, moments from the momfile)' % inp['initmag'])
         if inp['do_jtensor'] == 1 and (inp['mode'] != 'S' or inp['ip_mode'] not in ('N', 'S')):
             raise Unsupported('do_jtensor 1 is served for spin dynamics only (mode / ip_mode S)')
         if inp['mode'] not in ('S', 'M', 'H') or inp['ip_mode'] not in ('N', 'S', 'M', 'H'):
@@ -54,7 +67,68 @@ class Simulation:
         self._setup(device)
 
     # ------------------------------------------------------------------------------------------------
+    def _setup_alloy(self, device):
+        """do_ralloy 1 (fully occupied supercell): neighbour lists of the underlying lattice built on the device, the shell of
+        every list entry carried through the builder in place of a coupling, then the chemistry-dependent couplings mounted
+        per atom (alloy.mount) and handed to a second engine together with the supercell shape"""
+        inp, c = self.inp, self.c
+        cell = np.asarray(inp['cell'], dtype=float)
+        bas, atype_inp, nch, chconc = asdio.read_posfile_alloy(inp['posfile'], cell, inp['posfiletype'])
+        bas = lattice.fold_basis(cell, bas)
+        na, nchmax = chconc.shape
+        if np.abs(np.array([chconc[i, :nch[i]].sum() for i in range(na)]) - 1.0).max() > 1e-9:
+            raise Unsupported('do_ralloy 1: dilute alloys (site concentrations that do not add up to 1) are not served')
+        n1, n2, n3 = inp['ncell']
+        natom, mens = na * n1 * n2 * n3, inp['mensemble']
+        self.na, self.natom, self.mens = na, natom, mens
+        ammom, aemom, landeg = asdio.read_momfile_alloy(inp['momfile'], na, nchmax, inp['landeg_glob'])
+        self.anumb = (np.arange(natom, dtype=np.int32) % na) + 1
+        self.atype = atype_inp[self.anumb - 1]
+        self.achtype = alloy.occupancy(na, (n1, n2, n3), nch, chconc, inp['tseed'])
+        if (self.achtype == 0).any():
+            raise Unsupported('do_ralloy 1: the concentrations leave sites vacant for this supercell size')
+        idx = np.arange(natom)
+        i0, ix, iy, iz = idx % na, (idx // na) % n1, (idx // (na * n1)) % n2, idx // (na * n1 * n2)
+        self.coord = (np.outer(cell[0], ix) + np.outer(cell[1], iy) + np.outer(cell[2], iz)) + bas[:, i0]
+        if inp['do_prnstruct'] in (1, 2, 4):
+            self.out.coord(self.coord, self.atype, self.anumb)
+        nn, red, xc, nntype = asdio.read_pairfile_alloy(inp['exchange'], atype_inp, nchmax, bas, cell, inp['maptype'], inp['posfiletype'])
+        ns, ca, cs, sh = lattice.stencil(cell, bas, atype_inp, nn, red, inp['sym'], nntype, ncell=(n1, n2, n3))
+        # pass 1: the lattice's neighbour lists, every entry tagged with its shell (the "coupling" of the builder)
+        t = host.Engine(device)
+        t.set_constants(c['gama'], c['k_bolt'], c['mub'], c['mry'])
+        t.set_system(natom, 1, natom, None)
+        t.build_lattice_table(0, na, (n1, n2, n3), inp['bc'], ns, ca, cs, np.asarray(sh, dtype=np.float64)[:, :, None] + 1.0)
+        nlist, nlistsize, tag = t.get_table(0)
+        t.close()
+        shell = np.clip(np.rint(tag).astype(np.int64) - 1, 0, None)
+        ncoup = alloy.mount(nlist, nlistsize, shell, self.atype, self.anumb, self.achtype, xc, ammom, c['mry'], c['mub'])
+        self.tables = dict(nlist=nlist, nlistsize=nlistsize, ncoup=ncoup)
+        # pass 2: the engine of the run, one coupling row per atom, atoms in brick order through the supercell hint
+        e = host.Engine(device)
+        e.set_constants(c['gama'], c['k_bolt'], c['mub'], c['mry'])
+        e.set_system(natom, mens, natom, None)
+        e.set_lattice_hint(na, (n1, n2, n3), inp['bc'])
+        e.set_exchange(nlist, nlistsize, ncoup)
+        site, chem = self.anumb - 1, self.achtype - 1
+        self.landeg = 0.5 * landeg[site, chem]
+        self.engine = e
+        self._set_field(inp['ip_hfield'] if inp['ip_mode'] != 'N' else inp['hfield'])
+        self._llg(inp['sdealgh'], inp['timestep'], inp['damping'], inp['temp'])
+        e.commit()
+        mmom = np.asfortranarray(np.repeat(np.abs(ammom[site, chem])[:, None], mens, axis=1))
+        if inp['initmag'] == 3:
+            emom = np.asfortranarray(np.repeat(aemom[:, site, chem][:, :, None], mens, axis=2))
+        else:
+            # Initmag 1 continues the generator that dealt the species (same stream, magnetizationinit.f90:141-178): not restated
+            raise Unsupported('do_ralloy 1 with initmag 1')
+        self.mmom0 = mmom.copy(order='F')
+        e.set_moments(emom, mmom, self.mmom0)
+        self.atype_cell = atype_inp
+
     def _setup(self, device):
+        if self.inp['do_ralloy'] == 1:
+            return self._setup_alloy(device)
         inp, c = self.inp, self.c
         cell = np.asarray(inp['cell'], dtype=float)
         bas, atype_inp = asdio.read_posfile(inp['posfile'], cell, inp['posfiletype'])
@@ -125,7 +199,6 @@ class Simulation:
         if inp['skyno'] == 'T':
             e.set_triangulation(lattice.triangulation(n1, n2, n3, na))          # uppasd.f90:1284-1286
         elif inp['skyno'] == 'Y':
-            import warnings
             warnings.warn('skyno Y (finite-difference Pontryagin density) is not on this path; use skyno T (triangulation)')
 
     def _set_field(self, h):
