@@ -54,10 +54,16 @@ void fortrandata_setmatrices_(double* ncoup, unsigned int* nlist, unsigned int* 
 /* replaces fortranData.cpp:183-185 (chelper.f90:186). */
 void fortrandata_setinputdata_(int* gpu_mode, int* gpu_rng, int* gpu_rng_seed);
 
-/* replace fort_helper.cpp:52-64 (called from sd_driver.f90:1140-1142). */
+/* replace fort_helper.cpp:52-64 (called from sd_driver.f90:1140-1142).
+ * cudamdsim_measurementphase_ samples asynchronously: the state of a sampled step is staged on the device, copied to pinned host
+ * memory on a second stream and handed to fortran_measure_moment by a worker thread while the time loop continues (three
+ * snapshots in flight; gpu_files/cudaMeasurement.cu:109-182 and measurementQueue.cpp:63-121 in the reference); the status line
+ * takes Mbar from the on-device sums.  ASD_LEGACY_SYNC=1 selects blocking copies into the module arrays instead.
+ * asd_legacy_async_samples(): samples served by the asynchronous path so far. */
 void cudamdsim_initiateconstants_(void);
 void cudamdsim_initiatematrices_(void);
 void cudamdsim_measurementphase_(void);
+long asd_legacy_async_samples(void);
 
 /* gpu_mode 2 entry points (fort_helper.cpp:18-45, sd_driver.f90:1145-1147).  This build has no CPU twin:
  * they run the same CUDA engine. */

@@ -668,3 +668,40 @@ def test_pyasd_entry_points():
         momc = fh.relax(mode, 10, 5.0, 0.0, 0.0)
         e.mc_sweeps(mode, 10, 5.0, first_sweep=first, extfield=S['external_field'][:, 0, 0])
         assert np.array_equal(momc, e.get_moments()[1]), mode
+
+
+def test_legacy_measurement_phase_samples_asynchronously(monkeypatch):
+    """cudamdsim_measurementphase_: sampled steps are staged on the device, land in pinned host memory on a copy stream and are
+    measured by a worker thread while the time loop goes on (gpu_files/cudaMeasurement.cu:109-182, measurementQueue.cpp:63-121 in
+    the reference).  Every sample must be the state of ITS step, delivered in order: identical to the blocking path
+    (ASD_LEGACY_SYNC=1), also when samples are denser than the ring is deep and the host routine is slower than a step."""
+    import time
+    from uppasd_b200 import capi, host
+    fx, inp, S = load_golden('bccfe_cuda')
+    out = {}
+    for tag, sync in (('async', '0'), ('sync', '1')):
+        monkeypatch.setenv('ASD_LEGACY_SYNC', sync)
+        fh = host.FortranHost(S, orc.CONST, sdealgh=5, nstep=60, delta_t=1e-16, damping=0.1, temp=300.0, gpu_rng_seed=3, avrg_step=2)
+        seen = []
+        plain = fh._measure_moment
+
+        def slow(emomM, emom, mmom, mstep, plain=plain, seen=seen):
+            time.sleep(0.002)
+            e = np.ctypeslib.as_array(emom, shape=(fh.M, fh.N, 3)).copy()
+            m = np.ctypeslib.as_array(mmom, shape=(fh.M, fh.N)).copy()
+            eM = np.ctypeslib.as_array(emomM, shape=(fh.M, fh.N, 3))
+            assert np.array_equal(eM, e * m[:, :, None])
+            seen.append(mstep[0])
+            plain(emomM, emom, mmom, mstep)
+        fh._cbs = (fh._cbs[0], capi.CB_MEASURE(slow), fh._cbs[2], fh._cbs[3])
+        before = fh.lib.asd_legacy_async_samples()
+        fh.run()
+        served = fh.lib.asd_legacy_async_samples() - before
+        out[tag] = (dict(fh.averages), list(seen), served, fh.arr['emom'].copy())
+    a, s = out['async'], out['sync']
+    assert s[2] == 0 and a[2] == 30                      # 30 sampled steps went through the ring; the final sample is synchronous
+    assert a[1] == s[1] == sorted(s[1]) and len(a[1]) == 31
+    assert a[0].keys() == s[0].keys()
+    for k in a[0]:
+        assert a[0][k] == s[0][k], k                     # the very same numbers
+    assert np.array_equal(a[3], s[3])

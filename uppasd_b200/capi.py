@@ -25,6 +25,7 @@ SYMBOLS = {
     'cudamdsim_initiateconstants_': (None, []),
     'cudamdsim_initiatematrices_': (None, []),
     'cudamdsim_measurementphase_': (None, []),
+    'asd_legacy_async_samples': (C.c_long, []),
     'cudamdsim_initialphase_': (None, [vp] * 6),
     'cudamcsim_evolve_': (None, [vp] * 7),
     'relax_': (None, [vp] * 8),

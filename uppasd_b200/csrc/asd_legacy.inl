@@ -12,7 +12,11 @@
 // Deliberate differences: SDEalgh is honoured (1 = midpoint, 5 = Depondt; the reference CUDA path always ran
 // Depondt -- set ASD_LEGACY_FORCE_DEPONDT=1 to mimic that).
 
+#include <condition_variable>
 #include <ctime>
+#include <deque>
+#include <mutex>
+#include <thread>
 
 extern "C" {
 // gfortran-mangled host callbacks (c_helper.h:12-37); weak so that a non-Fortran host can register pointers instead
@@ -85,9 +89,132 @@ static void copy_to_fortran(bool all) {
       if (fd.emom2) std::memcpy(fd.emom2, fd.emom, 3 * NM * sizeof(double));
    }
 }
+
+// ---- asynchronous measurement path (replaces gpu_files/cudaMeasurement.cu:109-182 + measurementQueue.cpp:63-121) ----
+// A sampled step must hand emomM / emom / mmom of THAT step to the host's measurement routine.  Instead of stopping the time
+// loop for the 56 N M bytes, the step's state is unpacked into one of NSLOT device staging sets on the compute stream, an event
+// hands it to a copy stream that lands it in pinned host memory, and a worker thread calls fortran_measure_moment on the
+// landed buffers while the compute stream is already integrating the following steps.  The host routine receives the buffers
+// as its arguments (chelper.f90:106-126 measures ext_emomM / ext_emom / ext_mmom), so the Fortran module arrays are not touched
+// until the final copy-back.  ASD_LEGACY_SYNC=1 keeps the blocking copy into the module arrays (needed by a host whose
+// measurement reads the module arrays themselves, e.g. do_sc through correlation_wrapper).
+struct SnapshotRing {
+   static constexpr int NSLOT = 3;
+   struct Slot { double *d_e = nullptr, *d_eM = nullptr, *d_m = nullptr, *h_e = nullptr, *h_eM = nullptr, *h_m = nullptr; cudaEvent_t packed = nullptr, landed = nullptr; };
+   Slot slot[NSLOT];
+   cudaStream_t copy = nullptr;
+   size_t NM = 0;
+   int next = 0;
+   bool ready = false, stop = false;
+   std::thread worker;
+   std::mutex mu;
+   std::condition_variable cv, cv_free;
+   std::deque<std::pair<int, size_t>> queue;      // (slot, mstep) in sampling order
+   int busy[NSLOT] = {0, 0, 0};
+   long served = 0;
+
+   int init(asd_engine* e) {
+      release();
+      NM = (size_t)e->N * e->M;
+      if (cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking) != cudaSuccess) return -1;
+      for (auto& s : slot) {
+         if (cudaMalloc((void**)&s.d_e, 3 * NM * sizeof(double)) != cudaSuccess || cudaMalloc((void**)&s.d_eM, 3 * NM * sizeof(double)) != cudaSuccess ||
+             cudaMalloc((void**)&s.d_m, NM * sizeof(double)) != cudaSuccess || cudaMallocHost((void**)&s.h_e, 3 * NM * sizeof(double)) != cudaSuccess ||
+             cudaMallocHost((void**)&s.h_eM, 3 * NM * sizeof(double)) != cudaSuccess || cudaMallocHost((void**)&s.h_m, NM * sizeof(double)) != cudaSuccess ||
+             cudaEventCreateWithFlags(&s.packed, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&s.landed, cudaEventDisableTiming) != cudaSuccess) {
+            release();
+            return -1;
+         }
+      }
+      stop = false;
+      worker = std::thread([this]() { this->run(); });
+      ready = true;
+      return 0;
+   }
+   void run() {
+      for (;;) {
+         std::pair<int, size_t> job;
+         {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [this]() { return stop || !queue.empty(); });
+            if (queue.empty()) return;
+            job = queue.front();
+            queue.pop_front();
+         }
+         Slot& s = slot[job.first];
+         cudaEventSynchronize(s.landed);
+         const size_t mstep = job.second;
+         if (cb_measure) cb_measure(s.h_eM, s.h_e, s.h_m, &mstep);
+         else if (__chelper_MOD_fortran_measure_moment) __chelper_MOD_fortran_measure_moment(s.h_eM, s.h_e, s.h_m, &mstep);
+         {
+            std::lock_guard<std::mutex> lk(mu);
+            busy[job.first] = 0;
+            served++;
+         }
+         cv_free.notify_all();
+      }
+   }
+   // enqueue the state of the engine's stream position as the sample of step mstep
+   int sample(asd_engine* e, size_t mstep) {
+      const int q = next;
+      next = (next + 1) % NSLOT;
+      {
+         std::unique_lock<std::mutex> lk(mu);
+         cv_free.wait(lk, [&]() { return busy[q] == 0; });       // the worker is done with this slot's previous sample
+         busy[q] = 1;
+      }
+      Slot& s = slot[q];
+      if (ensure_layout(e, e->state_layout == 2 ? 2 : 1)) return -1;      // the first sample precedes the first step: state not uploaded yet
+      Layout& L = (e->state_layout == 2) ? e->mc : e->sd;
+      dim3 g, b;
+      launch_cfg(L.Npad, e->M, g, b);
+      unpack_kernel<<<g, b, 0, e->stream>>>(e->N, L.Npad, e->M, L.d_orig.p, e->cur.p, s.d_e, s.d_eM, s.d_m);
+      e->launches++;
+      if (cudaGetLastError() != cudaSuccess) return -1;
+      cudaEventRecord(s.packed, e->stream);
+      cudaStreamWaitEvent(copy, s.packed, 0);
+      cudaMemcpyAsync(s.h_e, s.d_e, 3 * NM * sizeof(double), cudaMemcpyDeviceToHost, copy);
+      cudaMemcpyAsync(s.h_eM, s.d_eM, 3 * NM * sizeof(double), cudaMemcpyDeviceToHost, copy);
+      cudaMemcpyAsync(s.h_m, s.d_m, NM * sizeof(double), cudaMemcpyDeviceToHost, copy);
+      cudaEventRecord(s.landed, copy);
+      {
+         std::lock_guard<std::mutex> lk(mu);
+         queue.emplace_back(q, mstep);
+      }
+      cv.notify_one();
+      return 0;
+   }
+   void drain() {
+      if (!ready) return;
+      std::unique_lock<std::mutex> lk(mu);
+      cv_free.wait(lk, [this]() { return queue.empty() && busy[0] == 0 && busy[1] == 0 && busy[2] == 0; });
+   }
+   ~SnapshotRing() { if (worker.joinable()) { { std::lock_guard<std::mutex> lk(mu); stop = true; queue.clear(); } cv.notify_all(); worker.detach(); } }
+   void release() {
+      if (worker.joinable()) {
+         { std::lock_guard<std::mutex> lk(mu); stop = true; }
+         cv.notify_all();
+         worker.join();
+      }
+      for (auto& s : slot) {
+         if (s.d_e) cudaFree(s.d_e); if (s.d_eM) cudaFree(s.d_eM); if (s.d_m) cudaFree(s.d_m);
+         if (s.h_e) cudaFreeHost(s.h_e); if (s.h_eM) cudaFreeHost(s.h_eM); if (s.h_m) cudaFreeHost(s.h_m);
+         if (s.packed) cudaEventDestroy(s.packed); if (s.landed) cudaEventDestroy(s.landed);
+         s = Slot();
+      }
+      if (copy) { cudaStreamDestroy(copy); copy = nullptr; }
+      queue.clear();
+      busy[0] = busy[1] = busy[2] = 0;
+      ready = false;
+   }
+};
+static SnapshotRing ring;
 }  // namespace legacy
 
 extern "C" {
+
+/* samples served by the asynchronous measurement path so far (0: the blocking path is in use) */
+long asd_legacy_async_samples(void) { return legacy::ring.served; }
 
 void fortrandata_setconstants_(char* p1, int* p2, unsigned int* p3, unsigned int* p4, unsigned int* p5, unsigned int* p6,
                                unsigned int* p7, double* p8, double* p9, double* p10, double* p11, double* p12,
@@ -190,16 +317,35 @@ void cudamdsim_measurementphase_(void) {
    std::printf("uppasd_b200: md simulation starting\n");
    if (!matrices_ok) { std::fprintf(stderr, "uppasd_b200: not initiated!\n"); return; }
    const size_t rstep = *fd.rstep, nstep = *fd.nstep;
+   const char* senv = std::getenv("ASD_LEGACY_SYNC");
+   bool async = !(senv && senv[0] == '1');
+   if (async && ring.init(eng) != 0) async = false;       // no room for the staging ring: blocking copies
    size_t pending_first = 0, pending = 0;  // steps enqueued lazily so that runs of unsampled steps cost no host sync
    auto flush_steps = [&]() {
       if (pending) { if (asd_sd_steps(eng, (long)pending, (long)pending_first)) die("sd_steps"); pending = 0; }
    };
+   std::vector<double> msum((size_t)3 * eng->M);
    for (size_t mstep = rstep + 1; mstep <= rstep + nstep; mstep++) {
-      if (do_measurements(mstep)) { flush_steps(); copy_to_fortran(false); measure_moment(mstep); }
-      // progress line every 5 % (cudaMdSimulation.cu:283-297)
+      if (do_measurements(mstep)) {
+         flush_steps();
+         if (async) { if (ring.sample(eng, mstep)) die("measurement snapshot"); }
+         else { copy_to_fortran(false); measure_moment(mstep); }
+      }
+      // progress line every 5 % (cudaMdSimulation.cu:283-297).  Mbar = calc_mavrg of the current state (prn_averages.f90:414-456):
+      // mean over the ensembles of |sum_i emomM| / Natom, from the per-tile sums the corrector launch leaves on the device
+      // (24 M bytes to the host instead of the 56 N M bytes the reference copies for fortran_calc_simulation_status_variables).
       if (nstep > 20 ? (mstep % ((rstep + nstep) / 20) == 0) : true) {
-         flush_steps(); copy_to_fortran(false);
-         if (fd.mavg) status(fd.mavg);
+         flush_steps();
+         if (async) {
+            if (asd_measure(eng, msum.data(), nullptr)) die("status");
+            double mb = 0.0;
+            for (int k = 0; k < eng->M; k++)
+               mb += std::sqrt(msum[3 * k] * msum[3 * k] + msum[3 * k + 1] * msum[3 * k + 1] + msum[3 * k + 2] * msum[3 * k + 2]) / eng->N;
+            if (fd.mavg) *fd.mavg = mb / eng->M;
+         } else {
+            copy_to_fortran(false);
+            if (fd.mavg) status(fd.mavg);
+         }
          if (nstep > 20) std::printf("CUDA: %3ld%% done. Mbar: %10.6f. U: %8.5f.\n", (long)(mstep * 100 / (rstep + nstep)), fd.mavg ? *fd.mavg : 0.0, fd.binderc ? *fd.binderc : 0.0);
          else std::printf("CUDA: Iteration %ld Mbar %13.6f\n", (long)mstep, fd.mavg ? *fd.mavg : 0.0);
       }
@@ -207,11 +353,13 @@ void cudamdsim_measurementphase_(void) {
       pending++;
    }
    flush_steps();
+   if (async) ring.drain();                 // every sampled step has been measured, in order, before the final one
    const size_t last = rstep + nstep + 1;
    copy_to_fortran(true);
    if (do_measurements(last)) measure_moment(last);
    flush_measurements(last);
    if (asd_synchronize(eng)) die("synchronize");
+   if (async) ring.release();
 }
 
 // ---- new sibling entries in the same F77 style (boundaries the reference never had) ----------------
