@@ -222,3 +222,21 @@ def test_block_sweep_observables_and_default_choice(monkeypatch):
         emom = e.get_moments()[0]
         assert np.abs(np.sqrt((emom ** 2).sum(axis=0)) - 1.0).max() < 1e-12
     assert 0.8 < mags['M'] < 0.995 and abs(mags['M'] - mags['H']) < 0.01, mags
+
+
+@pytest.mark.parametrize('mode', ['M', 'H'])
+def test_chain_parity_warp_specialised_sweep(mode, monkeypatch):
+    """ASD_MC_NT=512: the warp-specialised form of the run-form block sweep (8 sweep warps + 8 draw warps, double-buffered draw
+    records of 256 attempts, named barriers) runs the same chain as every other form"""
+    monkeypatch.setenv('ASD_RESIDENT', '0')
+    monkeypatch.setenv('ASD_MC_TS', '1024')
+    monkeypatch.setenv('ASD_MC_NT', '512')
+    from util import fixture_args
+    args = fixture_args('bccfe', mens=2, ncell=(64, 8, 8), do_reduced='Y')
+    S = orc.build_system(*args)
+    _random_start(S, 8)
+    e = lattice_engine(args, S, seed=17)
+    e.set_mc_layout(2)
+    assert e.mc_colouring()[0] == 2
+    err, moved = _chain_parity(e, S, mode, 500.0, 6, extfield=(0.0, 0.5, 0.0))
+    assert moved > 0.1 and err <= CHAIN_TOL[mode], (mode, err)

@@ -705,3 +705,45 @@ def test_legacy_measurement_phase_samples_asynchronously(monkeypatch):
     for k in a[0]:
         assert a[0][k] == s[0][k], k                     # the very same numbers
     assert np.array_equal(a[3], s[3])
+
+
+@pytest.mark.parametrize('alg', [1, 5])
+@pytest.mark.parametrize('path', ['resident', 'stage', 'runs'])
+def test_time_dependent_uniform_field(alg, path, monkeypatch):
+    """asd_set_time_field: the global time-dependent field (pulse / microwave field of calc_external_time_fields,
+    calculatefields.f90:92-185) that effective_field adds to beff2 next to external_field (hamiltonianactions.f90:241), one
+    vector per step and ensemble, read by the stage kernels from a schedule uploaded once.  Oracle: the same steps with
+    external_field + time field as its external field; steps outside the schedule see none."""
+    from uppasd_b200 import host
+    monkeypatch.setenv('ASD_RESIDENT', '1' if path == 'resident' else '0')
+    if path == 'runs':
+        import bench
+        S = bench.oracle_bcc((64, 4, 4), mensemble=2)
+        e, n = bench.bcc_engine((64, 4, 4), alg, 0.0, 0.5, 2, 0, 0)
+        assert e.layout_info()['runs'] == 4
+        dt, damp = 1e-16, 0.5
+    else:
+        fx, inp, S = load_golden('kagome')
+        dt, damp = inp['timestep'], inp['damping']
+        e = host.engine_from_system(S, orc.consts(S), sdealgh=alg, delta_t=dt, damping=damp, temp=0.0)
+    M = S['Mensemble']
+    nst, first = 12, 101
+    rng = np.random.default_rng(5)
+    tf = np.asfortranarray(rng.normal(size=(3, M, nst)) * 40.0)            # tesla-sized pulses: visible against the exchange field
+    e.set_time_field(first + 2, tf[:, :, 2:10])                            # schedule covers steps first + 2 .. first + 9 only
+    e.sd_steps(nst, first_step=first)
+    st = orc.SdState(S, alg, dt, damp)
+    ext0 = S['external_field'].copy(order='F')
+    for s in range(nst):
+        S['external_field'][...] = ext0
+        if 2 <= s < 10:
+            S['external_field'] += tf[:, None, :, s]
+        st.step()
+    S['external_field'][...] = ext0
+    got = e.get_moments()[0]
+    assert np.abs(got - st.emom).max() <= 1e-12
+    # the field matters (a run without it ends elsewhere), and clearing the schedule removes it
+    e.set_moments(S['emom'], S['mmom'])
+    e.set_time_field(0, None)
+    e.sd_steps(nst, first_step=first)
+    assert np.abs(e.get_moments()[0] - got).max() > 1e-6

@@ -56,6 +56,7 @@ SYMBOLS = {
     'asd_set_anisotropy': (C.c_int, [vp, vp, vp, vp, vp]),
     'asd_set_external_field': (C.c_int, [vp, vp]),
     'asd_set_torque': (C.c_int, [vp, vp]),
+    'asd_set_time_field': (C.c_int, [vp, C.c_long, C.c_long, vp]),
     'asd_set_llg': (C.c_int, [vp, C.c_int, C.c_double, vp, vp, vp, C.c_double, C.c_int, C.c_ulonglong]),
     'asd_set_moments': (C.c_int, [vp, vp, vp, vp]),
     'asd_get_moments': (C.c_int, [vp, vp, vp, vp]),

@@ -202,6 +202,9 @@ struct asd_engine {
    int state_layout = 0;  // 0 = none, 1 = sd, 2 = mc
    DevBuf<SpinVec> cur, pred;
    DevBuf<double> b2eff, esite, part, red, ring;   // ring: per-sample sums of asd_sd_run
+   DevBuf<double> tfield;               // time-dependent uniform field of the steps tf_first .. tf_first + tf_n - 1 ([step][M][3])
+   long long tf_first = 0;
+   int tf_n = 0;
    double* h_red = nullptr;             // pinned host landing zone of the per-ensemble sums (4 doubles each)
    size_t h_red_n = 0;
    DevBuf<double> msum_part;            // per-tile sums of emomM left by the last corrector launch of asd_sd_steps
@@ -711,6 +714,7 @@ static int fill_llg(asd_engine* e, Layout& L, LlgParams& p, unsigned long long s
       if ((rr = L.d_frozen.upload(h, e->stream))) return rr;
    }
    p.frozen = e->frozen.empty() ? nullptr : L.d_frozen.p;
+   p.tfield = e->tf_n > 0 ? e->tfield.p : nullptr; p.tf_first = e->tf_first; p.tf_n = e->tf_n;
    p.delta_t = e->delta_t; p.gamma = e->gamma; p.k_bolt = e->k_bolt; p.mub = e->mub; p.temprescale = e->temprescale;
    p.mompar = e->mompar; p.mmom0 = L.d_mmom0.p;
    p.seed = e->seed; p.step = step;
@@ -1476,6 +1480,21 @@ int asd_set_torque(asd_engine* e, const double* f) {
    if (e->N == 0) return fail(-2, "asd_set_system must be called first");
    if (f) e->btorque.assign(f, f + 3 * (size_t)e->N * e->M); else e->btorque.clear();
    e->committed = false;
+   return 0;
+}
+
+int asd_set_time_field(asd_engine* e, long first_step, long nsteps, const double* tfield) {
+   if (e->N == 0) return fail(-2, "asd_set_system must be called first");
+   CU(cudaSetDevice(e->device));
+   if (!tfield || nsteps <= 0) { e->tf_n = 0; return 0; }
+   if (nsteps > 100000000L / std::max(e->M, 1)) return fail(-1, "asd_set_time_field: schedule too long (%ld steps)", nsteps);
+   const size_t n = (size_t)nsteps * e->M * 3;
+   // host layout tfield(3, Mensemble, nsteps) is exactly the device layout [step][M][3]
+   int r = e->tfield.alloc(n);
+   if (r) return r;
+   CU(cudaMemcpyAsync(e->tfield.p, tfield, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+   CU(cudaStreamSynchronize(e->stream));
+   e->tf_first = first_step; e->tf_n = (int)nsteps;
    return 0;
 }
 

@@ -14,10 +14,17 @@ static bool mc_block_candidate(const asd_engine* e) {
 }
 
 template <class K>
-static void mc_block_run_launch(K kernel, int nt, dim3 g, size_t smem, cudaStream_t st, const Tables& t, const McParams& p, const McBlock& mb,
+static void mc_block_run_launch(K kernel, dim3 g, size_t smem, cudaStream_t st, const Tables& t, const McParams& p, const McBlock& mb,
                                 const McRuns& mr, const McTicket& tk, int first, SpinVec* cur) {
    allow_smem(kernel, smem);
-   kernel<<<g, nt, smem, st>>>(t, p, mb, mr, tk, first, cur);
+   kernel<<<g, 256, smem, st>>>(t, p, mb, mr, tk, first, cur);
+}
+
+template <class K>
+static void mc_block_ws_launch(K kernel, dim3 g, size_t smem, cudaStream_t st, const Tables& t, const McParams& p, const McBlock& mb,
+                               const McRuns& mr, const McTicket& tk, SpinVec* cur) {
+   allow_smem(kernel, smem);
+   kernel<<<g, 512, smem, st>>>(t, p, mb, mr, tk, cur);
 }
 
 template <class K>
@@ -143,7 +150,8 @@ static int mc_block_prepare(asd_engine* e) {
       if (!xs && ts == 1024 && ncol <= 56 && t.z <= MCR_ZMAX && !(renv && atoi(renv) == 0)) {
          McRuns& mr = B.mr;
          memset(&mr, 0, sizeof mr);
-         mr.q = B.nt / 128;
+         mr.q = 2;
+         mr.batch = (B.nt == 512) ? MCR_BATCH_WS : MCR_BATCH;
          const int spcap = MCR_ZMAX;
          DevBuf<unsigned short> d_arr;
          DevBuf<double> d_cseq;
@@ -181,8 +189,9 @@ static int mc_block_prepare(asd_engine* e) {
             const int gmax = *std::max_element(ok.begin(), ok.end());
             mr.gwords = (mr.ncw + gmax * (MCR_HDR + mr.q * mr.sp) + 7) & ~7;
             mr.gtab = B.gtab.p;
-            B.smem_run = (size_t)5 * MCR_BATCH * sizeof(double) + (B.nt == 512 ? (size_t)2 * 8 * 16 * 3 * sizeof(double) : 0) +
-                         (size_t)mr.gwords * 2 + (size_t)MCR_BATCH * 2 + (size_t)3 * (ucap + 16) * sizeof(double);
+            // 256 threads: one record buffer of MCR_BATCH attempts; 512 threads (warp-specialised): two of MCR_BATCH_WS -- the same bytes
+            B.smem_run = (size_t)5 * MCR_BATCH * sizeof(double) + (size_t)mr.gwords * 2 + (size_t)MCR_BATCH * 2 +
+                         (size_t)3 * (ucap + 16) * sizeof(double);
             if (gmax > 0 && B.smem_run <= (size_t)113 * 1024) {
                for (int c = 0; c < ntc; c++) {
                   int* lst = B.h_tilelist.data() + B.class_first[c];
@@ -263,10 +272,13 @@ static int mc_sweeps_block(asd_engine* e, McParams& p, long nsweeps, long first_
          tk.counter = B.counter.p; tk.base = B.tickets; tk.epoch = ++B.epoch; tk.done = B.done.p; tk.adj = B.adj.p; tk.nadj = B.nadj.p;
          tk.tclass = B.tclass.p; tk.cap = B.adjcap; tk.ntile = B.ntile;
          const dim3 gr((unsigned)((long)B.ntile * e->M));
-#define ASD_MCR(HB, NT) mc_block_run_launch(mc_block_run_kernel<HB, NT, true>, NT, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, 0, e->cur.p)
-         if (B.nt == 512) { if (hb) ASD_MCR(true, 512); else ASD_MCR(false, 512); }
-         else { if (hb) ASD_MCR(true, 256); else ASD_MCR(false, 256); }
-#undef ASD_MCR
+         if (B.nt == 512) {
+            if (hb) mc_block_ws_launch(mc_block_ws_kernel<true>, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, e->cur.p);
+            else mc_block_ws_launch(mc_block_ws_kernel<false>, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, e->cur.p);
+         } else {
+            if (hb) mc_block_run_launch(mc_block_run_kernel<true, true>, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, 0, e->cur.p);
+            else mc_block_run_launch(mc_block_run_kernel<false, true>, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, 0, e->cur.p);
+         }
          B.tickets += (unsigned long long)B.ntile * e->M;
          e->launches++;
          continue;
@@ -275,10 +287,8 @@ static int mc_sweeps_block(asd_engine* e, McParams& p, long nsweeps, long first_
          const int nrun = B.class_run[c];
          if (nrun > 0) {
             const dim3 gr((unsigned)nrun, (unsigned)e->M);
-#define ASD_MCR(HB, NT) mc_block_run_launch(mc_block_run_kernel<HB, NT, false>, NT, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, B.class_first[c], e->cur.p)
-            if (B.nt == 512) { if (hb) ASD_MCR(true, 512); else ASD_MCR(false, 512); }
-            else { if (hb) ASD_MCR(true, 256); else ASD_MCR(false, 256); }
-#undef ASD_MCR
+            if (hb) mc_block_run_launch(mc_block_run_kernel<true, false>, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, B.class_first[c], e->cur.p);
+            else mc_block_run_launch(mc_block_run_kernel<false, false>, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, B.class_first[c], e->cur.p);
             e->launches++;
          }
          if (nrun == B.class_count[c]) continue;

@@ -35,7 +35,8 @@ __device__ unsigned long long g_mc_prof[8];
 #endif
 
 constexpr int MCR_GMAX = 80;      // groups per tile the table has room for (64 for a full 1024-slot tile of 16-atom groups)
-constexpr int MCR_BATCH = 512;    // attempts whose draws are resident at a time
+constexpr int MCR_BATCH = 512;    // attempts whose draws are resident at a time (256-thread kernel)
+constexpr int MCR_BATCH_WS = 256; // same, warp-specialised kernel (two record buffers)
 constexpr int MCR_HDR = 8;        // 16-bit words of a group header: pos0, cnt, selfbase, ham, steps, -, -, -
 constexpr int MCR_NBMAX = 6;      // draw batches per tile
 constexpr int MCR_PHMAX = 62;     // colour phases per tile (colours + batch splits) the row header has room for
@@ -57,6 +58,7 @@ struct McRuns {
    int ncw;                       // 16-bit words of the row header (multiple of 8): nph, -, ... | phases x {first group | new
                                   // batch << 15, end group, end group of the batch, -}: the colour phases in sweep order
    int zero;                      // list position of the 16 zero records ( = ucap)
+   int batch;                     // attempts per draw batch the phase list is cut for (MCR_BATCH or MCR_BATCH_WS)
    const unsigned short* __restrict__ gtab;   // [ntile][gstride]: header | groups x {header, bases[q][sp]}
    double cseq[MCR_CSEQ];         // [NH][sp] coupling of every step, 0 beyond the row's last step
 };
@@ -161,13 +163,13 @@ mc_block_groups_kernel(int ts, int ncol, int z, size_t Npad, const int* __restri
    for (int q = mr.ncw + G * gw + tid; q < mr.gstride; q += 256) row[q] = 0;
    __syncthreads();
    if (tid == 0) {
-      // draw batches: consecutive groups whose attempts fit MCR_BATCH records; phases: the colours of a batch, in order
+      // draw batches: consecutive groups whose attempts fit mr.batch records; phases: the colours of a batch, in order
       int nbt = 0, g = 0, nph = 0;
       while (g < G && nbt < MCR_NBMAX && !bad) {
          nbt++;
          const int gs = g;
          const int pb = row[mr.ncw + (size_t)g * gw];
-         while (g < G && (int)row[mr.ncw + (size_t)g * gw] + (int)row[mr.ncw + (size_t)g * gw + 1] - pb <= MCR_BATCH) g++;
+         while (g < G && (int)row[mr.ncw + (size_t)g * gw] + (int)row[mr.ncw + (size_t)g * gw + 1] - pb <= mr.batch) g++;
          bool first = true;
          for (int c = 0; c < ncol; c++) {
             const int ga = max(cgs[c], gs), gb = min(cgs[c + 1], g);
@@ -211,186 +213,291 @@ __device__ __forceinline__ SpinVec ld_spin_cg(const SpinVec* p) {
    return v;
 }
 
-// 1024-slot tiles, reduced Hamiltonian, exchange only (no DM / BQ tables).  HB: heat bath.  NT threads: 256 (one warp per group,
-// two lanes per atom) or 512 (two warps per group, four lanes per atom; the warps join through shared memory and a named barrier).
-template <bool HB, int NT, bool TICKET>
-__global__ void __launch_bounds__(NT, 2)
-mc_block_run_kernel(const __grid_constant__ Tables t, const __grid_constant__ McParams p, const __grid_constant__ McBlock mb,
-                    const __grid_constant__ McRuns mr, const __grid_constant__ McTicket tk, const int class_first,
-                    SpinVec* __restrict__ cur) {
-   constexpr int TS = 1024, SB = (NT == 512) ? 4 : 7, RW = 5;      // RW: doubles per draw record {d0, d1, d2, d3, |m|}
-   constexpr int WP = NT / 256;                                     // warps per group
-   constexpr unsigned FULL = 0xffffffffu;
-   extern __shared__ double sm[];
-   __shared__ unsigned long long s_ticket;
-   __shared__ unsigned short blist[3 * MCR_BATCH];      // Metropolis: the attempts of a batch sorted by trial-move type
-   __shared__ int bcnt[3];
-   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+// ---- pieces shared by the sweep kernels -------------------------------------------------------------------------------------
+struct McTileCtx {
    int tile, k;
-   if (TICKET) {
-      if (tid == 0) s_ticket = atomicAdd(tk.counter, 1ull) - tk.base;
-      __syncthreads();
-      const unsigned long long n = s_ticket;
-      k = (int)(n % (unsigned)t.M);
-      tile = __ldg(mb.tilelist + (int)(n / (unsigned)t.M));
-   } else {
-      tile = __ldg(mb.tilelist + class_first + (int)blockIdx.x);
-      k = blockIdx.y;
-   }
-   SpinVec* __restrict__ S = cur + (size_t)k * t.Npad;
-   MC_PROF_T(t_0);
-   // shared memory: draw records [512][5] | partial fields [2][8][16][3] (NT = 512) | group table | slots [512] | emomM of the list + 16 zero records
-   double* __restrict__ rec = sm;
-   double* __restrict__ fpart = rec + RW * MCR_BATCH;
-   unsigned short* __restrict__ gt = reinterpret_cast<unsigned short*>(fpart + (WP > 1 ? 2 * 8 * 16 * 3 : 0));
-   unsigned short* __restrict__ rslot = gt + mr.gwords;
-   double* __restrict__ s3 = reinterpret_cast<double*>(rslot + MCR_BATCH);
-   {
-      const uint4* __restrict__ src = reinterpret_cast<const uint4*>(mr.gtab + (size_t)tile * mr.gstride);
-      uint4* __restrict__ dst = reinterpret_cast<uint4*>(gt);
-      for (int q = tid; q < mr.gwords / 8; q += NT) dst[q] = __ldg(src + q);
-   }
-   for (int q = tid; q < 48; q += NT) s3[3 * mr.zero + q] = 0.0;
-   const int cnt = __ldg(mb.ucount + tile);
-   const int* __restrict__ ul = mb.ulist + (size_t)tile * mb.ucap;
-   if (TICKET) {
-      // the gather list towards L2 while the first trial moves are drawn (stale lines are harmless: L2 is the coherence point)
-      for (int u = tid; u < cnt; u += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(S + __ldg(ul + u)));
-   }
-   __syncthreads();
-   const unsigned short* __restrict__ co = mb.corder + (size_t)tile * TS;
-   const int nph = gt[0];
-   const unsigned short* __restrict__ grec = gt + mr.ncw;
-   const int sp = mr.sp, gw = MCR_HDR + mr.q * sp;
-   const double pi = 3.141592653589793;
-   const double beta_h = 1.0 / p.k_bolt / (p.temprescale * p.temperature);
-   const double beta_m = 1.0 / p.k_bolt / (p.temprescale * p.temperature + 1.0e-15);
-   const int l = lane & 15, half = lane >> 4;
-   const int pair = warp / WP, wp = warp % WP, myq = 2 * wp + half;     // lane-slot of the atom this lane works for
+   SpinVec* __restrict__ S;                       // spins of ensemble k
+   const unsigned short* __restrict__ co;         // colour order of the tile
+   const unsigned short* __restrict__ grec;       // group records
+   int gw, sp;
+   double* __restrict__ s3;                       // emomM of the gather list
+   double beta_h, beta_m;
+};
 
-   // ---- (B) draws of the attempts [pb, pe) of the colour order (own spins: only this tile writes them in this sweep).
-   //      Metropolis: choose_random_flip picks one of three trial moves per attempt; a warp whose lanes disagree would run all
-   //      three (sincos + sqrt | Philox + Box-Muller + sqrt + divisions | negation).  Pass 1 draws the uniforms and files every
-   //      attempt under its move type, pass 2 works through the three lists with all lanes on the same path. ----
-   auto draw_batch = [&](int pb, int pe) {
-      if (!HB) {
-         if (tid < 3) bcnt[tid] = 0;
-         __syncthreads();
-      }
-      // two attempts per thread and round: their dependent global loads (slot -> original index, own spin) fly together
-#pragma unroll 1
-      for (int base = pb + tid; base < pe; base += 2 * NT) {
-         int slot[2], o[2];
-         SpinVec own[2];
-         bool val[2];
-#pragma unroll
-         for (int a = 0; a < 2; a++) {
-            val[a] = base + a * NT < pe;
-            slot[a] = val[a] ? (int)co[base + a * NT] : 0;
-         }
-#pragma unroll
-         for (int a = 0; a < 2; a++) {
-            const int i = tile * TS + slot[a];
-            o[a] = __ldg(t.orig + i);
-            own[a] = ld_spin_cg(S + i);
-         }
-#pragma unroll
-         for (int a = 0; a < 2; a++) {
-            if (!val[a]) continue;
-            double u[4];
-            uniform4(p.seed, (uint32_t)o[a] + t.atom_offset, (uint32_t)k + t.ens_offset, p.sweep, 1u, u);
-            const int r = base + a * NT - pb;
-            double* __restrict__ dr = rec + RW * r;
-            if (HB) {
-               double sphi, cphi;
-               sincos(pi * (2.0 * u[1] - 1.0), &sphi, &cphi);
-               dr[0] = u[0]; dr[1] = cphi; dr[2] = sphi; dr[3] = 0.0;
-            } else {
-               const int ftype = min((int)floor(3.0 * u[0]), 2);
-               if (ftype == 0) { dr[0] = u[1]; dr[1] = u[2]; }
-               else { dr[0] = own[a].x; dr[1] = own[a].y; dr[2] = own[a].z; }
-               dr[3] = u[3];
-               blist[ftype * MCR_BATCH + atomicAdd(&bcnt[ftype], 1)] = (unsigned short)r;
-            }
-            dr[4] = own[a].m;
-            rslot[r] = (unsigned short)slot[a];
-         }
-      }
-      if (!HB) {
-         __syncthreads();
-         const int n0 = bcnt[0], n1 = bcnt[1], n2 = bcnt[2];
-#pragma unroll 1
-         for (int q = tid; q < n0; q += NT) {
-            double* __restrict__ dr = rec + RW * (int)blist[q];
-            double sphi, cphi;
-            sincos(dr[0] * 2 * pi, &sphi, &cphi);
-            const double ct = 1.0 - 2.0 * dr[1];
-            const double st = sqrt(fmax(1.0 - ct * ct, 0.0));
-            dr[0] = st * cphi; dr[1] = st * sphi; dr[2] = ct;
-         }
-#pragma unroll 1
-         for (int q = tid; q < n1; q += NT) {
-            const int r = blist[MCR_BATCH + q];
-            double* __restrict__ dr = rec + RW * r;
-            const int o = __ldg(t.orig + tile * TS + (int)rslot[r]);
-            double ga, gb, gc;
-            gauss3f(p.seed, (uint32_t)o + t.atom_offset, (uint32_t)k + t.ens_offset, p.sweep, 2u, ga, gb, gc);
-            const double ax = dr[0] + ga * p.delta, ay = dr[1] + gb * p.delta, az = dr[2] + gc * p.delta;
-            const double len = sqrt(ax * ax + ay * ay + az * az);
-            dr[0] = ax / len; dr[1] = ay / len; dr[2] = az / len;
-         }
-         for (int q = tid; q < n2; q += NT) {
-            double* __restrict__ dr = rec + RW * (int)blist[2 * MCR_BATCH + q];
-            dr[0] = -dr[0]; dr[1] = -dr[1]; dr[2] = -dr[2];
-         }
-      }
-   };
-   auto batch_range = [&](int gs, int ge, int& pb, int& pe) {
-      pb = grec[(size_t)gs * gw];
-      pe = (int)grec[(size_t)(ge - 1) * gw] + (int)grec[(size_t)(ge - 1) * gw + 1];
-   };
-   int pb = 0, pe = 0;
-   if (TICKET && nph > 0) {
-      // first batch of draws BEFORE the gather: fills the wait for the neighbour tiles and the flight time of the prefetch
-      batch_range(gt[MCR_PH0] & 0x7fff, gt[MCR_PH0 + 2], pb, pe);
-      draw_batch(pb, pe);
-      MC_PROF_T(t_b1);
-      MC_PROF_ADD(1, t_0, t_b1);
-      // ---- wait for the neighbour tiles of lower classes ----
-      const int na = __ldg(tk.nadj + tile);
-      const unsigned myc = __ldg(tk.tclass + tile);
-      if (tid < na) {
-         const int other = __ldg(tk.adj + (size_t)tile * tk.cap + tid);
-         if (__ldg(tk.tclass + other) < myc) {
-            const unsigned int* f = tk.done + (size_t)k * tk.ntile + other;
-            unsigned v;
-            while (true) {
-               asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-               if (v == tk.epoch) break;
-               __nanosleep(200);
-            }
-         }
-      }
-      __syncthreads();
-      MC_PROF_T(t_w);
-      MC_PROF_ADD(4, t_b1, t_w);
+// (B) draws of the attempts [pb, pe) of the colour order into rec / rslot, by ND threads (this one is number dtid); bar() is a
+// barrier of exactly those threads.  Own spins: only this tile writes them in this sweep, and an atom is drawn before its visit.
+//   Metropolis: choose_random_flip picks one of three trial moves per attempt; a warp whose lanes disagree would run all three
+//   (sincos + sqrt | Philox + Box-Muller + sqrt + divisions | negation).  Pass 1 draws the uniforms and files every attempt
+//   under its move type, pass 2 works through the three lists with all lanes on the same path.  Two attempts per thread and
+//   round in pass 1: their dependent global loads (slot -> original index, own spin) fly together.
+template <bool HB, int ND, class Bar>
+__device__ __forceinline__ void mc_draw_batch(const Tables& t, const McParams& p, const McTileCtx& c, int dtid, int pb, int pe,
+                                              double* __restrict__ rec, unsigned short* __restrict__ rslot,
+                                              unsigned short* __restrict__ blist, int* __restrict__ bcnt, int bstride, Bar bar) {
+   constexpr int TS = 1024, RW = 5;
+   const double pi = 3.141592653589793;
+   if (!HB) {
+      if (dtid < 3) bcnt[dtid] = 0;
+      bar();
    }
-   MC_PROF_T(t_s0);
-   // ---- (A) gather list -> shared memory ----
+#pragma unroll 1
+   for (int base = pb + dtid; base < pe; base += 2 * ND) {
+      int slot[2], o[2];
+      SpinVec own[2];
+      bool val[2];
+#pragma unroll
+      for (int a = 0; a < 2; a++) {
+         val[a] = base + a * ND < pe;
+         slot[a] = val[a] ? (int)c.co[base + a * ND] : 0;
+      }
+#pragma unroll
+      for (int a = 0; a < 2; a++) {
+         const int i = c.tile * TS + slot[a];
+         o[a] = __ldg(t.orig + i);
+         own[a] = ld_spin_cg(c.S + i);
+      }
+#pragma unroll
+      for (int a = 0; a < 2; a++) {
+         if (!val[a]) continue;
+         double u[4];
+         uniform4(p.seed, (uint32_t)o[a] + t.atom_offset, (uint32_t)c.k + t.ens_offset, p.sweep, 1u, u);
+         const int r = base + a * ND - pb;
+         double* __restrict__ dr = rec + RW * r;
+         if (HB) {
+            double sphi, cphi;
+            sincos(pi * (2.0 * u[1] - 1.0), &sphi, &cphi);
+            dr[0] = u[0]; dr[1] = cphi; dr[2] = sphi; dr[3] = 0.0;
+         } else {
+            const int ftype = min((int)floor(3.0 * u[0]), 2);
+            if (ftype == 0) { dr[0] = u[1]; dr[1] = u[2]; }
+            else { dr[0] = own[a].x; dr[1] = own[a].y; dr[2] = own[a].z; }
+            dr[3] = u[3];
+            blist[ftype * bstride + atomicAdd(&bcnt[ftype], 1)] = (unsigned short)r;
+         }
+         dr[4] = own[a].m;
+         rslot[r] = (unsigned short)slot[a];
+      }
+   }
+   if (!HB) {
+      bar();
+      const int n0 = bcnt[0], n1 = bcnt[1], n2 = bcnt[2];
+#pragma unroll 1
+      for (int q = dtid; q < n0; q += ND) {
+         double* __restrict__ dr = rec + RW * (int)blist[q];
+         double sphi, cphi;
+         sincos(dr[0] * 2 * pi, &sphi, &cphi);
+         const double ct = 1.0 - 2.0 * dr[1];
+         const double st = sqrt(fmax(1.0 - ct * ct, 0.0));
+         dr[0] = st * cphi; dr[1] = st * sphi; dr[2] = ct;
+      }
+#pragma unroll 1
+      for (int q = dtid; q < n1; q += ND) {
+         const int r = blist[bstride + q];
+         double* __restrict__ dr = rec + RW * r;
+         const int o = __ldg(t.orig + c.tile * TS + (int)rslot[r]);
+         double ga, gb, gc;
+         gauss3f(p.seed, (uint32_t)o + t.atom_offset, (uint32_t)c.k + t.ens_offset, p.sweep, 2u, ga, gb, gc);
+         const double ax = dr[0] + ga * p.delta, ay = dr[1] + gb * p.delta, az = dr[2] + gc * p.delta;
+         const double len = sqrt(ax * ax + ay * ay + az * az);
+         dr[0] = ax / len; dr[1] = ay / len; dr[2] = az / len;
+      }
+      for (int q = dtid; q < n2; q += ND) {
+         double* __restrict__ dr = rec + RW * (int)blist[2 * bstride + q];
+         dr[0] = -dr[0]; dr[1] = -dr[1]; dr[2] = -dr[2];
+      }
+   }
+}
+
+// (C) one group of <= 16 same-colour atoms, handled by one warp: lanes l and l + 16 share atom l (each sums the steps of its lane-slot,
+// one shuffle joins them), lanes 0..15 then decide (calculate_energy + flip_a, or flip_h) and store.  pb: first attempt of the batch
+// whose records are in rec / rslot.
+template <bool HB>
+__device__ __forceinline__ void mc_sweep_group(const Tables& t, const McParams& p, const McRuns& mr, const McTileCtx& c, int gq, int lane,
+                                               int pb, const double* __restrict__ rec, const unsigned short* __restrict__ rslot) {
+   constexpr int TS = 1024, RW = 5;
+   constexpr unsigned FULL = 0xffffffffu;
+   const int l = lane & 15, half = lane >> 4;
+   const unsigned short* __restrict__ gr = c.grec + (size_t)gq * c.gw;
+   const uint2 hd = *reinterpret_cast<const uint2*>(gr);
+   const int pos0 = hd.x & 0xffffu, gcnt = hd.x >> 16, sp0 = hd.y & 0xffffu, ih = hd.y >> 16, ns = gr[4];
+   const bool act = l < gcnt;
+   const int le = act ? l : 0;
+   const double* __restrict__ lane3 = c.s3 + 3 * le;
+   const unsigned short* __restrict__ bq = gr + MCR_HDR + half * c.sp;
+   const int cs0 = ih * c.sp;
+   double f[3] = {0.0, 0.0, 0.0};
+#pragma unroll 2
+   for (int s4 = 0; s4 < ns; s4 += 4) {
+      const uint2 bw = *reinterpret_cast<const uint2*>(bq + s4);
+      const unsigned b[4] = {bw.x & 0xffffu, bw.x >> 16, bw.y & 0xffffu, bw.y >> 16};
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+         const double* __restrict__ m = lane3 + 3u * b[u];
+         const double cc = mr.cseq[cs0 + s4 + u];
+         f[0] = fma(cc, m[0], f[0]); f[1] = fma(cc, m[1], f[1]); f[2] = fma(cc, m[2], f[2]);
+      }
+   }
+#pragma unroll
+   for (int a = 0; a < 3; a++) f[a] += __shfl_xor_sync(FULL, f[a], 16);
+   if (act && half == 0) {
+      const int r = pos0 + l - pb;
+      const double* __restrict__ dr = rec + RW * r;
+      const double d0 = dr[0], d1 = dr[1], d2 = dr[2], d3 = dr[3], m = dr[4];
+      double* __restrict__ mine = c.s3 + 3 * (sp0 + l);
+      const double cm[3] = {mine[0], mine[1], mine[2]};
+      const int i = c.tile * TS + (int)rslot[r];
+      double ox, oy, oz;
+      bool changed;
+      if (HB) {
+         // ---- flip_h: total field = beff1 + beff2 of effective_field_single; external field from the tables ----
+         double bs[3] = {f[0], f[1], f[2]}, bqf[3] = {0.0, 0.0, 0.0}, h[3];
+         aniso_field<true>(t, i, ih, cm[0], cm[1], cm[2], bs[0], bs[1], bs[2], bqf[0], bqf[1], bqf[2]);
+         ext_field(t, i, c.k, h);
+         const double tot[3] = {bs[0] + (bqf[0] + h[0]), bs[1] + (bqf[1] + h[1]), bs[2] + (bqf[2] + h[2])};
+         const double zx = c.beta_h * tot[0] * p.mub * m, zy = c.beta_h * tot[1] * p.mub * m, zz = c.beta_h * tot[2] * p.mub * m;
+         const double zarg = sqrt(zx * zx + zy * zy + zz * zz);
+         const double zctheta = zz / zarg;
+         const double zstheta = sqrt(1.0 - zctheta * zctheta) + 1e-14;
+         double zcphi = zx / (zarg * zstheta), zsphi = zy / (zarg * zstheta);
+         if (zx == 0.0 && zy == 0.0) { zcphi = 1.0; zsphi = 0.0; }     // degenerate frame (see mc_update_site)
+         const double em2 = exp(-2.0 * zarg);
+         const double ctheta = 1.0 + (1.0 / zarg) * log((1.0 - em2) * d0 + em2 + 1e-14);
+         const double stheta = sqrt(fmax(1.0 - ctheta * ctheta, 0.0));
+         const double s0 = stheta * d1, s1 = stheta * d2, s2 = ctheta;
+         ox = zcphi * zctheta * s0 - zsphi * s1 + zcphi * zstheta * s2;
+         oy = zsphi * zctheta * s0 + zcphi * s1 + zsphi * zstheta * s2;
+         oz = -zstheta * s0 + zctheta * s2;
+         changed = true;
+      } else {
+         // ---- calculate_energy + flip_a ----
+         const double tm[3] = {d0 * m, d1 * m, d2 * m};
+         double e_c = 0.0, e_t = 0.0;
+         aniso_energy<true>(t, i, ih, cm, tm, e_c, e_t);
+         e_c -= cm[0] * f[0] + cm[1] * f[1] + cm[2] * f[2];
+         e_t -= tm[0] * f[0] + tm[1] * f[1] + tm[2] * f[2];
+         e_c -= p.extfield[0] * cm[0] + p.extfield[1] * cm[1] + p.extfield[2] * cm[2];
+         e_t -= p.extfield[0] * tm[0] + p.extfield[1] * tm[1] + p.extfield[2] * tm[2];
+         const double de = p.mub * (e_t - e_c);
+         changed = de <= 0.0 || d3 < exp(-c.beta_m * de);
+         ox = d0; oy = d1; oz = d2;
+      }
+      if (changed) {
+         SpinVec out;
+         out.x = ox; out.y = oy; out.z = oz; out.m = m;
+         c.S[i] = out;
+         mine[0] = ox * m; mine[1] = oy * m; mine[2] = oz * m;
+      }
+   }
+}
+
+// gather list -> shared memory, by NT threads
+template <int NT, int SB>
+__device__ __forceinline__ void mc_stage_list(const McTileCtx& c, int tid, int cnt, const int* __restrict__ ul) {
    for (int u0 = tid; u0 < cnt; u0 += SB * NT) {
       int sl[SB];
 #pragma unroll
       for (int a = 0; a < SB; a++) sl[a] = (u0 + a * NT < cnt) ? __ldg(ul + u0 + a * NT) : 0;
       SpinVec v[SB];
 #pragma unroll
-      for (int a = 0; a < SB; a++) v[a] = ld_spin_cg(S + sl[a]);
+      for (int a = 0; a < SB; a++) v[a] = ld_spin_cg(c.S + sl[a]);
 #pragma unroll
       for (int a = 0; a < SB; a++)
          if (u0 + a * NT < cnt) {
-            double* __restrict__ m = s3 + 3 * (u0 + a * NT);
+            double* __restrict__ m = c.s3 + 3 * (u0 + a * NT);
             m[0] = v[a].x * v[a].m; m[1] = v[a].y * v[a].m; m[2] = v[a].z * v[a].m;
          }
    }
+}
+
+// wait until every neighbour tile of a lower class has published this sweep's epoch
+__device__ __forceinline__ void mc_wait_tiles(const McTicket& tk, int tile, int k, int tid) {
+   const int na = __ldg(tk.nadj + tile);
+   const unsigned myc = __ldg(tk.tclass + tile);
+   if (tid < na) {
+      const int other = __ldg(tk.adj + (size_t)tile * tk.cap + tid);
+      if (__ldg(tk.tclass + other) < myc) {
+         const unsigned int* f = tk.done + (size_t)k * tk.ntile + other;
+         unsigned v;
+         while (true) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v == tk.epoch) break;
+            __nanosleep(200);
+         }
+      }
+   }
+}
+
+// 1024-slot tiles, 256 threads (one warp per group, two lanes per atom), reduced Hamiltonian, exchange only (no DM / BQ tables).
+// HB: heat bath.  TICKET: whole-sweep scheduling (above), else one launch per tile class.
+template <bool HB, bool TICKET>
+__global__ void __launch_bounds__(256, 2)
+mc_block_run_kernel(const __grid_constant__ Tables t, const __grid_constant__ McParams p, const __grid_constant__ McBlock mb,
+                    const __grid_constant__ McRuns mr, const __grid_constant__ McTicket tk, const int class_first,
+                    SpinVec* __restrict__ cur) {
+   constexpr int NT = 256, RW = 5;      // RW: doubles per draw record {d0, d1, d2, d3, |m|}
+   extern __shared__ double sm[];
+   __shared__ unsigned long long s_ticket;
+   __shared__ unsigned short blist[3 * MCR_BATCH];      // Metropolis: the attempts of a batch sorted by trial-move type
+   __shared__ int bcnt[3];
+   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+   McTileCtx c;
+   if (TICKET) {
+      if (tid == 0) s_ticket = atomicAdd(tk.counter, 1ull) - tk.base;
+      __syncthreads();
+      const unsigned long long n = s_ticket;
+      c.k = (int)(n % (unsigned)t.M);
+      c.tile = __ldg(mb.tilelist + (int)(n / (unsigned)t.M));
+   } else {
+      c.tile = __ldg(mb.tilelist + class_first + (int)blockIdx.x);
+      c.k = blockIdx.y;
+   }
+   const int tile = c.tile;
+   c.S = cur + (size_t)c.k * t.Npad;
+   MC_PROF_T(t_0);
+   // shared memory: draw records [batch][5] | group table | slots [batch] | emomM of the list + 16 zero records
+   double* __restrict__ rec = sm;
+   unsigned short* __restrict__ gt = reinterpret_cast<unsigned short*>(rec + RW * MCR_BATCH);
+   unsigned short* __restrict__ rslot = gt + mr.gwords;
+   c.s3 = reinterpret_cast<double*>(rslot + MCR_BATCH);
+   {
+      const uint4* __restrict__ src = reinterpret_cast<const uint4*>(mr.gtab + (size_t)tile * mr.gstride);
+      uint4* __restrict__ dst = reinterpret_cast<uint4*>(gt);
+      for (int q = tid; q < mr.gwords / 8; q += NT) dst[q] = __ldg(src + q);
+   }
+   for (int q = tid; q < 48; q += NT) c.s3[3 * mr.zero + q] = 0.0;
+   const int cnt = __ldg(mb.ucount + tile);
+   const int* __restrict__ ul = mb.ulist + (size_t)tile * mb.ucap;
+   if (TICKET) {
+      // the gather list towards L2 while the first trial moves are drawn (stale lines are harmless: L2 is the coherence point)
+      for (int u = tid; u < cnt; u += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.S + __ldg(ul + u)));
+   }
+   __syncthreads();
+   c.co = mb.corder + (size_t)tile * 1024;
+   const int nph = gt[0];
+   c.grec = gt + mr.ncw;
+   c.sp = mr.sp; c.gw = MCR_HDR + mr.q * mr.sp;
+   c.beta_h = 1.0 / p.k_bolt / (p.temprescale * p.temperature);
+   c.beta_m = 1.0 / p.k_bolt / (p.temprescale * p.temperature + 1.0e-15);
+   auto bar = []() { __syncthreads(); };
+   auto batch_range = [&](int gs, int ge, int& pb, int& pe) {
+      pb = c.grec[(size_t)gs * c.gw];
+      pe = (int)c.grec[(size_t)(ge - 1) * c.gw] + (int)c.grec[(size_t)(ge - 1) * c.gw + 1];
+   };
+   int pb = 0, pe = 0;
+   if (TICKET && nph > 0) {
+      // first batch of draws BEFORE the gather: fills the wait for the neighbour tiles and the flight time of the prefetch
+      batch_range(gt[MCR_PH0] & 0x7fff, gt[MCR_PH0 + 2], pb, pe);
+      mc_draw_batch<HB, NT>(t, p, c, tid, pb, pe, rec, rslot, blist, bcnt, MCR_BATCH, bar);
+      MC_PROF_T(t_b1);
+      MC_PROF_ADD(1, t_0, t_b1);
+      mc_wait_tiles(tk, tile, c.k, tid);
+      __syncthreads();
+      MC_PROF_T(t_w);
+      MC_PROF_ADD(4, t_b1, t_w);
+   }
+   MC_PROF_T(t_s0);
+   // ---- (A) gather list -> shared memory ----
+   mc_stage_list<NT, 7>(c, tid, cnt, ul);
    __syncthreads();
    MC_PROF_T(t_a);
    MC_PROF_ADD(0, t_s0, t_a);
@@ -401,106 +508,15 @@ mc_block_run_kernel(const __grid_constant__ Tables t, const __grid_constant__ Mc
          // ---- new batch: its draws ----
          MC_PROF_T(t_b0);
          batch_range(ga, (int)(pw.y & 0xffffu), pb, pe);
-         draw_batch(pb, pe);
+         mc_draw_batch<HB, NT>(t, p, c, tid, pb, pe, rec, rslot, blist, bcnt, MCR_BATCH, bar);
          __syncthreads();
          MC_PROF_T(t_b1);
          MC_PROF_ADD(1, t_b0, t_b1);
       }
       MC_PROF_T(t_c0);
-      // ---- (C) one colour of the batch; one group per warp (pair), Q lanes share an atom ----
-      {
-         {
-         int pass = 0;
-         for (int gq = ga + pair; gq < gb; gq += 8, pass ^= 1) {
-            const unsigned short* __restrict__ gr = grec + (size_t)gq * gw;
-            const uint2 hd = *reinterpret_cast<const uint2*>(gr);
-            const int pos0 = hd.x & 0xffffu, gcnt = hd.x >> 16, sp0 = hd.y & 0xffffu, ih = hd.y >> 16, ns = gr[4];
-            const bool act = l < gcnt;
-            const int le = act ? l : 0;
-            const double* __restrict__ lane3 = s3 + 3 * le;
-            const unsigned short* __restrict__ bq = gr + MCR_HDR + myq * sp;
-            const int cs0 = ih * sp;
-            double f[3] = {0.0, 0.0, 0.0};
-            MC_PROF_T(t_l0);
-#pragma unroll 2
-            for (int s4 = 0; s4 < ns; s4 += 4) {
-               const uint2 bw = *reinterpret_cast<const uint2*>(bq + s4);
-               const unsigned b[4] = {bw.x & 0xffffu, bw.x >> 16, bw.y & 0xffffu, bw.y >> 16};
-#pragma unroll
-               for (int u = 0; u < 4; u++) {
-                  const double* __restrict__ m = lane3 + 3u * b[u];
-                  const double cc = mr.cseq[cs0 + s4 + u];
-                  f[0] = fma(cc, m[0], f[0]); f[1] = fma(cc, m[1], f[1]); f[2] = fma(cc, m[2], f[2]);
-               }
-            }
-#pragma unroll
-            for (int a = 0; a < 3; a++) f[a] += __shfl_xor_sync(FULL, f[a], 16);
-            if (WP > 1) {
-               double* __restrict__ fp = fpart + ((pass * 8 + pair) * 16 + l) * 3;     // double-buffered by pass
-               if (wp == 1 && half == 0) { fp[0] = f[0]; fp[1] = f[1]; fp[2] = f[2]; }
-               asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
-               if (wp == 0 && half == 0) { f[0] += fp[0]; f[1] += fp[1]; f[2] += fp[2]; }
-            }
-            MC_PROF_T(t_l1);
-            MC_PROF_ADD(5, t_l0, t_l1);
-            if (act && half == 0 && wp == 0) {
-               const int r = pos0 + l - pb;
-               const double* __restrict__ dr = rec + RW * r;
-               const double d0 = dr[0], d1 = dr[1], d2 = dr[2], d3 = dr[3], m = dr[4];
-               double* __restrict__ mine = s3 + 3 * (sp0 + l);
-               const double cm[3] = {mine[0], mine[1], mine[2]};
-               const int i = tile * TS + (int)rslot[r];
-               double ox, oy, oz;
-               bool changed;
-               if (HB) {
-                  // ---- flip_h: total field = beff1 + beff2 of effective_field_single; external field from the tables ----
-                  double bs[3] = {f[0], f[1], f[2]}, bqf[3] = {0.0, 0.0, 0.0}, h[3];
-                  aniso_field<true>(t, i, ih, cm[0], cm[1], cm[2], bs[0], bs[1], bs[2], bqf[0], bqf[1], bqf[2]);
-                  ext_field(t, i, k, h);
-                  const double tot[3] = {bs[0] + (bqf[0] + h[0]), bs[1] + (bqf[1] + h[1]), bs[2] + (bqf[2] + h[2])};
-                  const double zx = beta_h * tot[0] * p.mub * m, zy = beta_h * tot[1] * p.mub * m, zz = beta_h * tot[2] * p.mub * m;
-                  const double zarg = sqrt(zx * zx + zy * zy + zz * zz);
-                  const double zctheta = zz / zarg;
-                  const double zstheta = sqrt(1.0 - zctheta * zctheta) + 1e-14;
-                  double zcphi = zx / (zarg * zstheta), zsphi = zy / (zarg * zstheta);
-                  if (zx == 0.0 && zy == 0.0) { zcphi = 1.0; zsphi = 0.0; }     // degenerate frame (see mc_update_site)
-                  const double em2 = exp(-2.0 * zarg);
-                  const double ctheta = 1.0 + (1.0 / zarg) * log((1.0 - em2) * d0 + em2 + 1e-14);
-                  const double stheta = sqrt(fmax(1.0 - ctheta * ctheta, 0.0));
-                  const double s0 = stheta * d1, s1 = stheta * d2, s2 = ctheta;
-                  ox = zcphi * zctheta * s0 - zsphi * s1 + zcphi * zstheta * s2;
-                  oy = zsphi * zctheta * s0 + zcphi * s1 + zsphi * zstheta * s2;
-                  oz = -zstheta * s0 + zctheta * s2;
-                  changed = true;
-               } else {
-                  // ---- calculate_energy + flip_a ----
-                  const double tm[3] = {d0 * m, d1 * m, d2 * m};
-                  double e_c = 0.0, e_t = 0.0;
-                  aniso_energy<true>(t, i, ih, cm, tm, e_c, e_t);
-                  e_c -= cm[0] * f[0] + cm[1] * f[1] + cm[2] * f[2];
-                  e_t -= tm[0] * f[0] + tm[1] * f[1] + tm[2] * f[2];
-                  e_c -= p.extfield[0] * cm[0] + p.extfield[1] * cm[1] + p.extfield[2] * cm[2];
-                  e_t -= p.extfield[0] * tm[0] + p.extfield[1] * tm[1] + p.extfield[2] * tm[2];
-                  const double de = p.mub * (e_t - e_c);
-                  changed = de <= 0.0 || d3 < exp(-beta_m * de);
-                  ox = d0; oy = d1; oz = d2;
-               }
-               if (changed) {
-                  SpinVec out;
-                  out.x = ox; out.y = oy; out.z = oz; out.m = m;
-                  S[i] = out;
-                  mine[0] = ox * m; mine[1] = oy * m; mine[2] = oz * m;
-               }
-            }
-            MC_PROF_T(t_l2);
-            MC_PROF_ADD(6, t_l1, t_l2);
-         }
-         MC_PROF_T(t_l3);
-         __syncthreads();
-         MC_PROF_T(t_l4);
-         MC_PROF_ADD(7, t_l3, t_l4);
-      }
-      }
+      // ---- (C) one colour of the batch; one group per warp ----
+      for (int gq = ga + warp; gq < gb; gq += 8) mc_sweep_group<HB>(t, p, mr, c, gq, lane, pb, rec, rslot);
+      __syncthreads();
       MC_PROF_T(t_c1);
       MC_PROF_ADD(2, t_c0, t_c1);
       if (pw.x & 0x8000u) { MC_PROF_ADD(3, t_0, t_0 + 1); }
@@ -509,8 +525,104 @@ mc_block_run_kernel(const __grid_constant__ Tables t, const __grid_constant__ Mc
       // publish: every writer's stores are ordered before the flag (fence), the flag after every writer (barrier)
       __threadfence();
       __syncthreads();
-      if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(tk.done + (size_t)k * tk.ntile + tile), "r"(tk.epoch) : "memory");
+      if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(tk.done + (size_t)c.k * tk.ntile + tile), "r"(tk.epoch) : "memory");
    }
+}
+
+// WARP-SPECIALISED form (whole-sweep scheduling only): 512 threads = 8 SWEEP warps + 8 DRAW warps.  The sweep of a tile alternates
+// between a phase that is bound by dependent-instruction latency (the trial moves: Philox, sincos, sqrt, divisions) and phases bound by
+// shared-memory bandwidth (the neighbour loops); with two CTAs per SM (the gather list fills shared memory) the two kinds of work only
+// overlap by accident.  Here the draw warps produce the records of batch b + 1 (256 attempts, double-buffered) WHILE the sweep warps
+// run the colours of batch b; all 512 threads draw the first batch, wait for the neighbour tiles and stage the gather list.
+// Barriers: id 1 = the 8 sweep warps (between colours), id 2 = the 8 draw warps (inside a batch), id 0 = everybody (batch switch).
+template <bool HB>
+__global__ void __launch_bounds__(512, 2)
+mc_block_ws_kernel(const __grid_constant__ Tables t, const __grid_constant__ McParams p, const __grid_constant__ McBlock mb,
+                   const __grid_constant__ McRuns mr, const __grid_constant__ McTicket tk, SpinVec* __restrict__ cur) {
+   constexpr int NT = 512, RW = 5, B = MCR_BATCH_WS;
+   extern __shared__ double sm[];
+   __shared__ unsigned long long s_ticket;
+   __shared__ unsigned short blist[3 * B];              // pass-2 lists of the batch being drawn
+   __shared__ int bcnt[3];
+   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+   const bool drawer = warp >= 8;
+   McTileCtx c;
+   if (tid == 0) s_ticket = atomicAdd(tk.counter, 1ull) - tk.base;
+   __syncthreads();
+   {
+      const unsigned long long n = s_ticket;
+      c.k = (int)(n % (unsigned)t.M);
+      c.tile = __ldg(mb.tilelist + (int)(n / (unsigned)t.M));
+   }
+   const int tile = c.tile;
+   c.S = cur + (size_t)c.k * t.Npad;
+   // shared memory: draw records [2][B][5] | group table | slots [2][B] | emomM of the list + 16 zero records
+   double* __restrict__ rec = sm;
+   unsigned short* __restrict__ gt = reinterpret_cast<unsigned short*>(rec + 2 * RW * B);
+   unsigned short* __restrict__ rslot = gt + mr.gwords;
+   c.s3 = reinterpret_cast<double*>(rslot + 2 * B);
+   {
+      const uint4* __restrict__ src = reinterpret_cast<const uint4*>(mr.gtab + (size_t)tile * mr.gstride);
+      uint4* __restrict__ dst = reinterpret_cast<uint4*>(gt);
+      for (int q = tid; q < mr.gwords / 8; q += NT) dst[q] = __ldg(src + q);
+   }
+   for (int q = tid; q < 48; q += NT) c.s3[3 * mr.zero + q] = 0.0;
+   const int cnt = __ldg(mb.ucount + tile);
+   const int* __restrict__ ul = mb.ulist + (size_t)tile * mb.ucap;
+   for (int u = tid; u < cnt; u += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(c.S + __ldg(ul + u)));
+   __syncthreads();
+   c.co = mb.corder + (size_t)tile * 1024;
+   const int nph = gt[0];
+   c.grec = gt + mr.ncw;
+   c.sp = mr.sp; c.gw = MCR_HDR + mr.q * mr.sp;
+   c.beta_h = 1.0 / p.k_bolt / (p.temprescale * p.temperature);
+   c.beta_m = 1.0 / p.k_bolt / (p.temprescale * p.temperature + 1.0e-15);
+   auto bar_all = []() { __syncthreads(); };
+   auto bar_draw = []() { asm volatile("bar.sync 2, 256;" ::: "memory"); };
+   auto batch_range = [&](int gs, int ge, int& pb, int& pe) {
+      pb = c.grec[(size_t)gs * c.gw];
+      pe = (int)c.grec[(size_t)(ge - 1) * c.gw] + (int)c.grec[(size_t)(ge - 1) * c.gw + 1];
+   };
+   if (nph > 0) {
+      int pb, pe;
+      batch_range(gt[MCR_PH0] & 0x7fff, gt[MCR_PH0 + 2], pb, pe);
+      mc_draw_batch<HB, NT>(t, p, c, tid, pb, pe, rec, rslot, blist, bcnt, B, bar_all);
+   }
+   mc_wait_tiles(tk, tile, c.k, tid);
+   __syncthreads();
+   mc_stage_list<NT, 4>(c, tid, cnt, ul);
+   __syncthreads();
+   // ---- batches: sweep warps on buffer (b & 1), draw warps fill buffer ((b + 1) & 1) ----
+   int ph = 0, b = 0;
+   while (ph < nph) {
+      // phases [ph, pn) = batch b; the next batch starts at phase pn
+      int pn = ph + 1;
+      while (pn < nph && !(gt[MCR_PH0 + 4 * pn] & 0x8000u)) pn++;
+      int pb, pe;
+      batch_range(gt[MCR_PH0 + 4 * ph] & 0x7fff, gt[MCR_PH0 + 4 * ph + 2], pb, pe);
+      if (drawer) {
+         if (pn < nph) {
+            int qb, qe;
+            batch_range(gt[MCR_PH0 + 4 * pn] & 0x7fff, gt[MCR_PH0 + 4 * pn + 2], qb, qe);
+            const int nb = (b + 1) & 1;
+            mc_draw_batch<HB, 256>(t, p, c, tid - 256, qb, qe, rec + nb * RW * B, rslot + nb * B, blist, bcnt, B, bar_draw);
+         }
+      } else {
+         const double* __restrict__ rb = rec + (b & 1) * RW * B;
+         const unsigned short* __restrict__ sb = rslot + (b & 1) * B;
+         for (int q = ph; q < pn; q++) {
+            const uint2 pw = *reinterpret_cast<const uint2*>(gt + MCR_PH0 + 4 * q);
+            const int ga = pw.x & 0x7fff, gb = pw.x >> 16;
+            for (int gq = ga + warp; gq < gb; gq += 8) mc_sweep_group<HB>(t, p, mr, c, gq, lane, pb, rb, sb);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+         }
+      }
+      __syncthreads();      // batch switch: buffer (b + 1) & 1 complete, buffer b & 1 free
+      ph = pn; b++;
+   }
+   __threadfence();
+   __syncthreads();
+   if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(tk.done + (size_t)c.k * tk.ntile + tile), "r"(tk.epoch) : "memory");
 }
 
 }  // namespace asd

@@ -30,6 +30,10 @@ namespace asd {
 #define ASD_RUN_UNROLL 4
 #endif
 
+#ifndef ASD_INT_UNROLL
+#define ASD_INT_UNROLL 1
+#endif
+constexpr int INT_UNROLL = ASD_INT_UNROLL;   // atoms of a thread whose integrators are interleaved (1: one rolled loop)
 constexpr int RUN_UNROLL = ASD_RUN_UNROLL;   // entries of the union walk in flight per mask loop
 constexpr int RUN_MAXPAIR = 256;   // R * z must stay below this (j and the entry counts are bytes)
 
@@ -259,7 +263,7 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
    const int ilast = t.Nown - 1;
    SpinVec own = S[min(i0, ilast)], old;
    if (STAGE == 2) old = curk[min(i0, ilast)];
-#pragma unroll 1
+#pragma unroll (INT_UNROLL)
    for (int r = 0; r < R; r++) {
       const int i = i0 + 32 * r;
       const int io = mt[0].y;
@@ -272,6 +276,7 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
          site_field<true, false, ASD_CHUNK, XS>(t, S, i, ih, own, smc, smd, smb, bs, bq, s3);
          double h[3];
          ext_field(t, i, k, h);
+         add_time_field(p, t.M, k, p.step, h);
          const double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
          const SpinVec o = integrate_site<SOLVER, STAGE>(t, p, i, k, io, b, own, (STAGE == 1) ? own : old, b2eff, gn[0]);
          if (STAGE == 1) predk[i] = o; else curk[i] = o;
