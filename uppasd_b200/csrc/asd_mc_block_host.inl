@@ -2,7 +2,8 @@
 
 // Does the block sweep serve this engine?  Device-built lattice (the periodic colouring needs the stencils), reduced
 // Hamiltonian, scalar exchange, not a slab.  mc_layout 2 / ASD_MC_BLOCK=1 force it (tests on small lattices), ASD_MC_BLOCK=0
-// switches it off; by default it takes over once a tile-colour class fills the GPU.
+// switches it off; by default it takes over once a tile-colour class fills the GPU AND every tile is in the run form (see the
+// end of mc_block_prepare).
 static bool mc_block_candidate(const asd_engine* e) {
    if (!e->lattice_built || e->slab.on || e->jtensor || !e->sd.reduced || e->sd.t.z <= 0) return false;
    if (e->mc_layout == 0 || e->mc_layout == 1) return false;
@@ -10,7 +11,7 @@ static bool mc_block_candidate(const asd_engine* e) {
    if (env && atoi(env) == 0) return false;
    if (e->mc_layout == 2 || (env && atoi(env) == 1)) return true;
    if (std::getenv("ASD_MC_TILES") && atoi(std::getenv("ASD_MC_TILES")) != 0) return false;
-   return (long)e->sd.t.Nown * e->M >= 600000L;
+   return (long)e->sd.t.Nown * e->M >= 400000L;
 }
 
 template <class K>
@@ -50,8 +51,9 @@ static int mc_block_prepare(asd_engine* e) {
    const int super = d.NA * d.P * d.SY * d.SZ;
    int sms = 148;
    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
-   // tile size: the whole super-brick when its tile-colour classes still fill the GPU, else one 256-slot brick group
-   int ts = (super == 1024 && ((long)Nown / 1024) * e->M >= 16L * sms) ? 1024 : 256;
+   // tile size: the whole super-brick (the run form with whole-sweep scheduling needs it: every tile of the sweep is in one launch, so
+   // two CTAs per SM worth of tiles is enough to fill the GPU), else one 256-slot brick group
+   int ts = (super == 1024 && ((long)Nown / 1024) * e->M >= 2L * sms) ? 1024 : 256;
    const char* tenv = std::getenv("ASD_MC_TS");
    if (tenv && (atoi(tenv) == 256 || (atoi(tenv) == 1024 && super == 1024))) ts = atoi(tenv);
    const bool xs = t.zdm > 0 || t.zbq > 0;
@@ -234,7 +236,14 @@ static int mc_block_prepare(asd_engine* e) {
       }
    }
    B.ts = ts; B.ucap = ucap; B.ncol = ncol; B.ntile = ntile;
-   B.on = true;
+   // By default the block sweep takes over only in its run form with whole-sweep scheduling (measured: bcc Fe 128^3 9.2e9 attempts/s
+   // against 6.4e9 of the colour-major launches).  The generic per-atom-word form (DM / BQ tables, irregular tiles) is slower than the
+   // colour-major launches on the layouts measured (2-D triangular + DMI 1024^2 x 2: 6.8e9 vs 1.2e10) and runs on request only.
+   {
+      const char* env = std::getenv("ASD_MC_BLOCK");
+      const bool forced = e->mc_layout == 2 || (env && atoi(env) == 1);
+      B.on = forced || B.ticket;
+   }
    if (std::getenv("ASD_DEBUG"))
    {
       int nrun = 0;
