@@ -78,6 +78,7 @@ struct Tables {
    int zq;
    const int4* __restrict__ nl4;
    const int* __restrict__ nlrow;   // [Npad][z] atom-major copy of nl (Monte Carlo layout): a sub-warp reads one atom's list coalesced
+   const double* __restrict__ cprow; // [Npad][z] atom-major copy of the per-atom couplings (non-reduced Monte Carlo layout), zero-padded
    const double4* __restrict__ cp4;
    // staged tile gather: per 256-slot tile a sorted list (ulist) of the unique slots its atoms gather from; the
    // tile's CTA stages emomM of those slots in shared memory once, and nl16 holds the exchange neighbours as

@@ -99,6 +99,7 @@ struct Layout {
    DevBuf<int> d_ham, d_orig, d_nl, d_lsize, d_dml, d_dmsize, d_bql, d_bqsize, d_taniso;
    DevBuf<int4> d_nl4;
    DevBuf<int> d_nlrow;             // atom-major exchange table of the MC layout (mc_colour_coop_kernel)
+   DevBuf<double> d_cprow;          // atom-major per-atom couplings next to it (non-reduced layouts)
    DevBuf<int2> d_classes;          // {first, count} of every colour class (mc_sweeps_persistent_kernel)
    DevBuf<int> d_ucount, d_ulist;   // staged tile path (asd_tiles.cuh)
    DevBuf<uint4> d_nl16, d_dm16, d_bq16;
@@ -665,22 +666,31 @@ static int build_layout(asd_engine* e, Layout& L, bool colour_major) {
    L.zs[0] = e->ex.z; L.zs[1] = e->dm.z; L.zs[2] = e->bq.z;
    L.d_nlrow.release();
    L.d_classes.release();
-   if (colour_major && L.reduced && !e->jtensor) {
-      // atom-major copy for the cooperative colour kernel (small colour classes / long lists)
+   L.d_cprow.release();
+   // atom-major copies for the cooperative colour kernels (small colour classes / long lists); per-atom couplings (do_reduced N,
+   // random alloys) up to 2e8 table entries (1.6 GB of couplings)
+   if (colour_major && !e->jtensor && (L.reduced || (size_t)Npad * e->ex.z <= (size_t)200000000)) {
       const int z = e->ex.z;
       std::vector<int> rowm((size_t)Npad * z);
+      std::vector<double> rowc;
+      if (!L.reduced) rowc.assign((size_t)Npad * z, 0.0);
       for (long s = 0; s < Npad; s++) {
          const int o = L.orig[s];
          for (int j = 0; j < z; j++) {
             int v = (int)s;
-            if (o >= 0 && j < e->ex.lsize[e->aHam[o] - 1]) v = L.slot_of[e->ex.list[(size_t)j + (size_t)z * o] - 1];
+            if (o >= 0 && j < e->ex.lsize[e->aHam[o] - 1]) {
+               v = L.slot_of[e->ex.list[(size_t)j + (size_t)z * o] - 1];
+               if (!L.reduced) rowc[(size_t)s * z + j] = e->ex.coup[(size_t)j + (size_t)z * (e->aHam[o] - 1)];
+            }
             rowm[(size_t)s * z + j] = v;
          }
       }
       if ((r = L.d_nlrow.upload(rowm, st))) return r;
+      if (!L.reduced && (r = L.d_cprow.upload(rowc, st))) return r;
    }
    r = finish_layout(e, L);
    L.t.nlrow = L.d_nlrow.p;
+   L.t.cprow = L.d_cprow.p;
    return r;
 }
 
@@ -1282,7 +1292,7 @@ static int mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, d
       int sms = 148, coop = 0;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
       cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device);
-      bool use = L.reduced && L.t.nlrow && coop && ncol >= 12 && mx * 8 <= (long)sms * 2048 && L.t.z >= 32 && nsweeps > 0;
+      bool use = L.t.nlrow && (L.reduced || L.t.cprow) && coop && ncol >= 12 && mx * 8 <= (long)sms * 2048 && L.t.z >= 32 && nsweeps > 0;
       if (env) use = use && atoi(env) != 0;
       if (use) {
          int r;
@@ -1300,8 +1310,10 @@ static int mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, d
          int nc = ncol, ns = (int)nsweeps;
          SpinVec* curp = e->cur.p;
          void* args[] = {(void*)&L.t, (void*)&p, (void*)&cls, (void*)&nc, (void*)&ns, (void*)&curp};
-         const void* fn = lpa == 8 ? (const void*)mc_sweeps_persistent_kernel<8> : lpa == 16 ? (const void*)mc_sweeps_persistent_kernel<16>
-                                                                                            : (const void*)mc_sweeps_persistent_kernel<32>;
+         const void* fn = L.reduced ? (lpa == 8 ? (const void*)mc_sweeps_persistent_kernel<8, true> : lpa == 16 ? (const void*)mc_sweeps_persistent_kernel<16, true>
+                                                                                                            : (const void*)mc_sweeps_persistent_kernel<32, true>)
+                                    : (lpa == 8 ? (const void*)mc_sweeps_persistent_kernel<8, false> : lpa == 16 ? (const void*)mc_sweeps_persistent_kernel<16, false>
+                                                                                                             : (const void*)mc_sweeps_persistent_kernel<32, false>);
          int per_sm = 0;
          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, L.smem_bytes));
          if (per_sm > 0) {
@@ -1322,7 +1334,7 @@ static int mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, d
          dim3 g((p.count + 255) / 256, e->M), b(256);
          // small classes: LPA lanes per update so that a launch still fills the GPU (ASD_MC_LPA forces a width)
          int lpa = 1;
-         if (L.reduced && L.t.nlrow) {
+         if (L.t.nlrow && (L.reduced || L.t.cprow)) {
             const long attempts = (long)p.count * e->M;
             while (lpa < 32 && attempts * lpa < 300000L && 4 * lpa <= L.t.z) lpa *= 2;
             const char* env = std::getenv("ASD_MC_LPA");
@@ -1330,13 +1342,16 @@ static int mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, d
          }
          if (lpa > 1) {
             const dim3 gc((unsigned)(((long)p.count * lpa + 255) / 256), e->M);
+#define ASD_COOP(W) do { if (L.reduced) mc_colour_coop_kernel<W, true><<<gc, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p); \
+                        else mc_colour_coop_kernel<W, false><<<gc, b, 0, e->stream>>>(L.t, p, e->cur.p); } while (0)
             switch (lpa) {
-               case 2: mc_colour_coop_kernel<2><<<gc, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p); break;
-               case 4: mc_colour_coop_kernel<4><<<gc, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p); break;
-               case 8: mc_colour_coop_kernel<8><<<gc, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p); break;
-               case 16: mc_colour_coop_kernel<16><<<gc, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p); break;
-               default: mc_colour_coop_kernel<32><<<gc, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p); break;
+               case 2: ASD_COOP(2); break;
+               case 4: ASD_COOP(4); break;
+               case 8: ASD_COOP(8); break;
+               case 16: ASD_COOP(16); break;
+               default: ASD_COOP(32); break;
             }
+#undef ASD_COOP
          } else if (L.reduced) mc_colour_kernel<true><<<g, b, L.smem_bytes, e->stream>>>(L.t, p, e->cur.p, nullptr);
          else mc_colour_kernel<false><<<g, b, 0, e->stream>>>(L.t, p, e->cur.p, nullptr);
          e->launches++;

@@ -196,7 +196,9 @@ mc_colour_kernel(const __grid_constant__ Tables t, const __grid_constant__ McPar
 // draws, acceptance).  A launch then has LPA times more threads in flight and LPA times fewer dependent gathers per
 // thread: the colour launches of such systems are latency-bound, not bandwidth-bound.
 // one cooperative update: the LPA lanes of a group (q = lane within the group) work on attempt (li, k) of the class
-template <int LPA>
+// REDUCED = false: one coupling row per atom (do_reduced N, random alloys), read from the atom-major copy t.cprow next to t.nlrow;
+// rows are zero-padded beyond the atom's list length and the padding entries of nlrow point at the atom itself.
+template <int LPA, bool REDUCED>
 __device__ __forceinline__ void mc_coop_update(const Tables& t, const McParams& p, SpinVec* __restrict__ cur, int li, int k, int q,
                                                const double* smc, const double* smd, const double* smb) {
    SpinVec* __restrict__ S = cur + (size_t)k * t.Npad;
@@ -204,25 +206,30 @@ __device__ __forceinline__ void mc_coop_update(const Tables& t, const McParams& 
    if (li < p.count) {
       i = p.first + li;
       o = __ldg(t.orig + i);
-      if (o >= 0) { ih = __ldg(t.ham + i); n = __ldg(t.lsize + ih); }
+      if (o >= 0) {
+         if (REDUCED) { ih = __ldg(t.ham + i); n = __ldg(t.lsize + ih); }
+         else n = t.z;
+      }
    }
    const int* __restrict__ row = t.nlrow + (size_t)i * t.z;
-   const double* __restrict__ crow = smc ? smc + (size_t)ih * t.z : t.cp + (size_t)ih * t.z;
+   const double* __restrict__ crow = REDUCED ? (smc ? smc + (size_t)ih * t.z : t.cp + (size_t)ih * t.z) : t.cprow + (size_t)i * t.z;
    double f[3] = {0.0, 0.0, 0.0};
    for (int j0 = q; j0 < n; j0 += 4 * LPA) {
       int nb[4];
       SpinVec v[4];
+      double c[4];
 #pragma unroll
       for (int a = 0; a < 4; a++) nb[a] = (j0 + a * LPA < n) ? __ldg(row + j0 + a * LPA) : i;
+#pragma unroll
+      for (int a = 0; a < 4; a++) c[a] = (j0 + a * LPA < n) ? (REDUCED ? crow[j0 + a * LPA] : __ldg(crow + j0 + a * LPA)) : 0.0;
 #pragma unroll
       for (int a = 0; a < 4; a++) v[a] = S[nb[a]];
 #pragma unroll
       for (int a = 0; a < 4; a++)
          if (j0 + a * LPA < n) {
-            const double c = crow[j0 + a * LPA];
-            f[0] = fma(c, v[a].x * v[a].m, f[0]);
-            f[1] = fma(c, v[a].y * v[a].m, f[1]);
-            f[2] = fma(c, v[a].z * v[a].m, f[2]);
+            f[0] = fma(c[a], v[a].x * v[a].m, f[0]);
+            f[1] = fma(c[a], v[a].y * v[a].m, f[1]);
+            f[2] = fma(c[a], v[a].z * v[a].m, f[2]);
          }
    }
 #pragma unroll
@@ -233,32 +240,27 @@ __device__ __forceinline__ void mc_coop_update(const Tables& t, const McParams& 
    }
    if (q == 0 && o >= 0) {
       SpinVec out;
-      if (mc_update_site<true, false>(t, p, S, i, k, o, ih, smc, smd, smb, out, f)) S[i] = out;
+      if (mc_update_site<REDUCED, false>(t, p, S, i, k, o, ih, smc, smd, smb, out, f)) S[i] = out;
    }
 }
-
-template <int LPA>
+template <int LPA, bool REDUCED>
 __global__ void __launch_bounds__(256)
 mc_colour_coop_kernel(const __grid_constant__ Tables t, const __grid_constant__ McParams p, SpinVec* __restrict__ cur) {
    extern __shared__ double sm[];
-   const double *smc, *smd, *smb;
-   stage_couplings(t, sm, smc, smd, smb);
+   const double *smc = nullptr, *smd = nullptr, *smb = nullptr;
+   if (REDUCED) stage_couplings(t, sm, smc, smd, smb);
    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-   mc_coop_update<LPA>(t, p, cur, gt / LPA, blockIdx.y, gt % LPA, smc, smd, smb);
+   mc_coop_update<LPA, REDUCED>(t, p, cur, gt / LPA, blockIdx.y, gt % LPA, smc, smd, smb);
 }
-
-// Many small colour classes: ALL colours of ALL requested sweeps in ONE cooperative launch, a grid-wide barrier between
-// colours instead of a kernel boundary (114 launches of ~14 us per sweep for FeCo B2 otherwise).  The grid is sized
-// to be co-resident (cudaLaunchCooperativeKernel); groups of LPA lanes stride over the count * M attempts of a class.
-template <int LPA>
+template <int LPA, bool REDUCED>
 __global__ void __launch_bounds__(256)
 mc_sweeps_persistent_kernel(const __grid_constant__ Tables t, const __grid_constant__ McParams p0, const int2* __restrict__ classes,
                             int ncol, int nsweeps, SpinVec* __restrict__ cur) {
    namespace cg = cooperative_groups;
    cg::grid_group grid = cg::this_grid();
    extern __shared__ double sm[];
-   const double *smc, *smd, *smb;
-   stage_couplings(t, sm, smc, smd, smb);
+   const double *smc = nullptr, *smd = nullptr, *smb = nullptr;
+   if (REDUCED) stage_couplings(t, sm, smc, smd, smb);
    McParams p = p0;
    const int q = threadIdx.x % LPA;
    const long g0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) / LPA, ng = (long)gridDim.x * blockDim.x / LPA;
@@ -272,7 +274,7 @@ mc_sweeps_persistent_kernel(const __grid_constant__ Tables t, const __grid_const
          for (long a0 = 0; a0 < total; a0 += ng) {
             const long a = a0 + g0;
             const bool live = a < total;
-            mc_coop_update<LPA>(t, p, cur, live ? (int)(a % cl.y) : p.count, live ? (int)(a / cl.y) : 0, q, smc, smd, smb);
+            mc_coop_update<LPA, REDUCED>(t, p, cur, live ? (int)(a % cl.y) : p.count, live ? (int)(a / cl.y) : 0, q, smc, smd, smb);
          }
          grid.sync();
       }
