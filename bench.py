@@ -12,8 +12,10 @@ N > 1 shards independent ensembles (Mensemble = N, one per GPU, no data-path com
 All timing is on the device (CUDA events on the engine's stream), max over ranks, after a barrier.
 
 The one JSON line also carries `secondary`: the Monte Carlo sweep rate of the same supercell (Metropolis and heat bath,
-attempts/s against the 256 B/attempt figure of SURVEY 8d) and, for N > 1, the slab-decomposed single supercell with the
-fused NVLink halo push (BASELINE config 5: bcc 512 x 512 x 256 on 8 GPUs, 256^3 below), strong scaling.
+attempts/s against the 256 B/attempt figure of SURVEY 8d), BASELINE configs 3 (FeCo random alloy, Mensemble 8: Monte Carlo
+and LLG) and 4 (2-D triangular Heisenberg + DMI lattice: LLG and heat bath) through the run-directory driver, and, for N > 1,
+the slab-decomposed single supercell with the fused NVLink halo push (BASELINE config 5: bcc 512 x 512 x 256 on 8 GPUs,
+256^3 below), strong scaling.
 """
 import argparse
 import json
@@ -203,6 +205,101 @@ def traffic_from_profiles(kernel_key):
         except Exception:
             return None
     return None
+
+
+def _config3_dir(d, ncell, mens):
+    """BASELINE config 3 as the reference's example states it (examples/Mappings/FeCo/random: bcc primitive cell, 50/50 random
+    occupancy, z = 258), materialised from tests/golden/feco_random.json with the supercell / ensemble count of the run"""
+    fx = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'feco_random.json')))
+    for k, v in fx['raw'].items():
+        open(os.path.join(d, k), 'w').write(v)
+    drop = ('ncell', 'mensemble', 'ip_mode', 'mode', 'sdealgh', 'temp')
+    lines = [l for l in fx['raw']['inpsd.dat'].splitlines() if not (l.split() and l.split()[0].lower() in drop)]
+    lines += ['ncell %d %d %d' % tuple(ncell), 'mensemble %d' % mens, 'ip_mode N', 'mode M', 'sdealgh 1', 'temp 600']
+    open(os.path.join(d, 'inpsd.dat'), 'w').write('\n'.join(lines) + '\n')
+    return os.path.join(d, 'inpsd.dat')
+
+
+def _config4_dir(d, ncell, mens):
+    """BASELINE config 4: 2-D triangular lattice, nearest-neighbour Heisenberg exchange + interfacial DMI + uniaxial anisotropy +
+    field along -z (the ingredients of examples/SpecialFeatures/SkyrmionLattice), reduced Hamiltonian"""
+    a1, a2 = (1.0, 0.0, 0.0), (-0.5, 0.8660254037844386, 0.0)
+    nbr = [(1, 0), (0, 1), (-1, -1), (-1, 0), (0, -1), (1, 1)]
+    vec = lambda n: np.array([n[0] * a1[0] + n[1] * a2[0], n[0] * a1[1] + n[1] * a2[1], 0.0])
+    open(os.path.join(d, 'posfile'), 'w').write('1 1 0.0 0.0 0.0\n')
+    open(os.path.join(d, 'momfile'), 'w').write('1 1 1.5 0.1 0.05 1.0\n')
+    with open(os.path.join(d, 'jfile'), 'w') as fh:
+        for n in nbr:
+            fh.write('1 1 %.10f %.10f %.10f 1.0\n' % tuple(vec(n)))
+    with open(os.path.join(d, 'dmfile'), 'w') as fh:
+        for n in nbr:
+            r = vec(n)
+            dm = 0.35 * np.cross([0.0, 0.0, 1.0], r / np.linalg.norm(r))
+            fh.write('1 1 %.10f %.10f %.10f %.10f %.10f %.10f\n' % (*r, *dm))
+    open(os.path.join(d, 'kfile'), 'w').write('1 1 0.05 0.0 0.0 0.0 1.0 0.0\n')
+    open(os.path.join(d, 'inpsd.dat'), 'w').write(
+        'simid skyrm_2D\nncell %d %d 1\nBC P P 0\ncell %.10f %.10f %.10f\n     %.10f %.10f %.10f\n     0.0 0.0 1.0\nSym 0\n'
+        'posfile ./posfile\nmomfile ./momfile\nexchange ./jfile\ndm ./dmfile\nanisotropy ./kfile\ndo_reduced Y\nMensemble %d\n'
+        'Initmag 3\nSDEalgh 1\nmode S\ntemp 10\nhfield 0.0 0.0 -2.5\ndamping 0.3\ntimestep 1.0d-16\nNstep 10\ndo_avrg N\n'
+        % (ncell[0], ncell[1], *a1, *a2, mens))
+    return os.path.join(d, 'inpsd.dat')
+
+
+def config_blocks(world, rank, local, dist, torch, peak):
+    """secondary.config3 / secondary.config4: the two BASELINE configurations that are not bcc Fe, through the run-directory
+    driver (uppasd_b200/driver.py), one independent copy per GPU (weak scaling): attempts/s and atom-steps/s summed over ranks"""
+    import tempfile
+    import warnings
+    from uppasd_b200 import driver
+    out = {}
+
+    def agg(ms):
+        t = torch.tensor([ms], device='cuda', dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        try:
+            sim = driver.Simulation(_config3_dir(tempfile.mkdtemp(), (32, 32, 32), 8), device=local, seed=1000 + rank)
+            e, n, m = sim.engine, sim.natom, sim.mens
+            z = int(sim.tables['nlist'].shape[0])
+            blk = {'workload': 'FeCo random alloy (bcc primitive cell, 50/50, z = %d, one coupling row per atom) 32^3 = %d atoms x %d '
+                               'ensembles per GPU, T = 600 K' % (z, n, m)}
+            for mode, key in (('M', 'metropolis'), ('H', 'heat_bath')):
+                e.mc_sweeps(mode, 3, 600.0)
+                ms = agg(e.time_mc_sweeps(mode, 20, 600.0))
+                rate = world * n * m * 20 / (ms * 1e-3)
+                blk[key] = {'value': rate, 'unit': 'attempts/s', 'ms_per_sweep': ms / 20,
+                            'frac_of_peak': (56.0 + 12.0 * z) * rate / world / 1e9 / peak}
+            e.sd_steps(3)
+            ms = agg(e.time_sd_steps(20, first_step=4))
+            rate = world * n * m * 20 / (ms * 1e-3)
+            blk['llg'] = {'value': rate, 'unit': 'atom-steps/s', 'ms_per_step': ms / 20, 'frac_of_peak': (136.0 + 24.0 * z) * rate / world / 1e9 / peak}
+            e.close()
+            out['config3'] = blk
+        except Exception as ex:
+            out['config3'] = {'error': repr(ex)[:300]}
+        try:
+            sim = driver.Simulation(_config4_dir(tempfile.mkdtemp(), (1024, 1024), 2), device=local, seed=2000 + rank)
+            e, n, m = sim.engine, sim.natom, sim.mens
+            balg = 136.0 + 8 * 6 + 8 * 6 + 104
+            blk = {'workload': '2-D triangular lattice 1024 x 1024 x %d ensembles per GPU, Heisenberg + interfacial DMI + uniaxial anisotropy '
+                               '+ field, reduced Hamiltonian, T = 10 K' % m}
+            sim.relax('S', nstep=10, temperature=10.0, timestep=1e-16, damping=0.3)
+            ms = agg(e.time_sd_steps(100, first_step=1000))
+            rate = world * n * m * 100 / (ms * 1e-3)
+            blk['llg'] = {'value': rate, 'unit': 'atom-steps/s', 'ms_per_step': ms / 100, 'alg_bytes_per_atom_step': balg,
+                          'frac_of_peak': balg * rate / world / 1e9 / peak}
+            e.mc_sweeps('H', 3, 10.0)
+            ms = agg(e.time_mc_sweeps('H', 20, 10.0))
+            rate = world * n * m * 20 / (ms * 1e-3)
+            blk['heat_bath'] = {'value': rate, 'unit': 'attempts/s', 'ms_per_sweep': ms / 20}
+            e.close()
+            out['config4'] = blk
+        except Exception as ex:
+            out['config4'] = {'error': repr(ex)[:300]}
+    return out
 
 
 def slab_block(a, world, rank, local, dist, torch, out, warmup, steps):
@@ -414,6 +511,7 @@ def main():
             secondary['mc'] = mc
         except Exception as ex:                                   # the headline line must survive
             secondary['mc'] = {'error': repr(ex)[:300]}
+        secondary.update(config_blocks(world, rank, local, dist, torch, peak))
 
     if rank == 0:
         b1, b2 = B_ALG[a.solver]

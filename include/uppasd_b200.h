@@ -173,12 +173,13 @@ int asd_set_anisotropy(asd_engine* e, const int* taniso, const double* eaniso, c
 int asd_set_external_field(asd_engine* e, const double* external_field);
 int asd_set_torque(asd_engine* e, const double* btorque);
 
-/* Time-dependent uniform field: the global part of calc_external_time_fields (pulse, microwave, demagnetisation field;
- * calculatefields.f90:92-185), which hamiltonianactions.f90:241 adds to beff2 next to external_field.  tfield(3, Mensemble, nsteps)
- * holds the field of the steps first_step .. first_step + nsteps - 1 (the value of mstep the step is run with); it is uploaded once
- * and read by the stage kernels through their parameters -- no re-upload of the per-site external_field between steps.  Steps
- * outside the schedule see no time-dependent field; NULL or nsteps <= 0 clears it.  LLG steps only (the reference's Monte Carlo
- * takes its field as the extfield argument of mc_evolve). */
+/* Time-dependent uniform field: the global part of calc_external_time_fields (magnetic-field pulse, microwave field;
+ * calculatefields.f90:92-185), which hamiltonianactions.f90:241 adds to beff2 next to external_field.  tfield(3, nsteps) holds the
+ * field of the steps first_step .. first_step + nsteps - 1 (the value of mstep the step is run with), the same for every
+ * ensemble (the one ensemble-dependent term of the reference, the demagnetisation field, is outside this path).  The stage
+ * kernels take the vector of their step as a kernel parameter -- no re-upload of the per-site external_field between steps.
+ * Steps outside the schedule see no time-dependent field; NULL or nsteps <= 0 clears it.  LLG steps only (the reference's Monte
+ * Carlo takes its field as the extfield argument of mc_evolve). */
 int asd_set_time_field(asd_engine* e, long first_step, long nsteps, const double* tfield);
 
 /* LLG parameters (evolution.f90:38-44): SDEalgh 1 (midpoint) or 5 (Depondt); per-site arrays of length N.

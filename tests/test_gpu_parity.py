@@ -712,7 +712,7 @@ def test_legacy_measurement_phase_samples_asynchronously(monkeypatch):
 def test_time_dependent_uniform_field(alg, path, monkeypatch):
     """asd_set_time_field: the global time-dependent field (pulse / microwave field of calc_external_time_fields,
     calculatefields.f90:92-185) that effective_field adds to beff2 next to external_field (hamiltonianactions.f90:241), one
-    vector per step and ensemble, read by the stage kernels from a schedule uploaded once.  Oracle: the same steps with
+    vector per step, handed to the stage kernels as a parameter from a schedule set once.  Oracle: the same steps with
     external_field + time field as its external field; steps outside the schedule see none."""
     from uppasd_b200 import host
     monkeypatch.setenv('ASD_RESIDENT', '1' if path == 'resident' else '0')
@@ -729,15 +729,15 @@ def test_time_dependent_uniform_field(alg, path, monkeypatch):
     M = S['Mensemble']
     nst, first = 12, 101
     rng = np.random.default_rng(5)
-    tf = np.asfortranarray(rng.normal(size=(3, M, nst)) * 40.0)            # tesla-sized pulses: visible against the exchange field
-    e.set_time_field(first + 2, tf[:, :, 2:10])                            # schedule covers steps first + 2 .. first + 9 only
+    tf = np.asfortranarray(rng.normal(size=(3, nst)) * 40.0)               # tesla-sized pulses: visible against the exchange field
+    e.set_time_field(first + 2, tf[:, 2:10])                               # schedule covers steps first + 2 .. first + 9 only
     e.sd_steps(nst, first_step=first)
     st = orc.SdState(S, alg, dt, damp)
     ext0 = S['external_field'].copy(order='F')
     for s in range(nst):
         S['external_field'][...] = ext0
         if 2 <= s < 10:
-            S['external_field'] += tf[:, None, :, s]
+            S['external_field'] += tf[:, s][:, None, None]
         st.step()
     S['external_field'][...] = ext0
     got = e.get_moments()[0]

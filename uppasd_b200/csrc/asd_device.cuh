@@ -133,18 +133,22 @@ struct LlgParams {
    // fixed-moment run (Nred < Natom, red_atom_list of evolve_first, evolution.f90:38-44): frozen[slot] != 0 marks an atom
    // that is NOT in the list of evolving atoms -- the integrators skip it, every neighbour still sees its moment
    const unsigned char* __restrict__ frozen;
-   // time-dependent uniform field (asd_set_time_field): tfield[step - tf_first][M][3], added to the external field of the steps
-   // tf_first .. tf_first + tf_n - 1 (time_external_field of hamiltonianactions.f90:241; calculatefields.f90:92-185, global part)
+   // time-dependent uniform field (asd_set_time_field; time_external_field of hamiltonianactions.f90:241, global part of
+   // calculatefields.f90:92-185): tf = the vector of THIS step (stage launches: set by the host per step, zero without a schedule,
+   // added unconditionally -- a branch here cost the register-blocked run kernel 18 %, measured); tfield[step - tf_first][3] = the
+   // device copy of the schedule for the resident kernel, which advances the step itself
+   double tf[3];
    const double* __restrict__ tfield;
    long long tf_first;
    int tf_n;
 };
 
-__device__ __forceinline__ void add_time_field(const LlgParams& p, int M, int k, unsigned long long step, double h[3]) {
+// resident kernel: the schedule entry of `step`
+__device__ __forceinline__ void add_time_field(const LlgParams& p, unsigned long long step, double h[3]) {
    if (p.tfield) {
       const long long q = (long long)step - p.tf_first;
       if (q >= 0 && q < p.tf_n) {
-         const double* __restrict__ f = p.tfield + ((size_t)q * M + k) * 3;
+         const double* __restrict__ f = p.tfield + (size_t)q * 3;
          h[0] += __ldg(f); h[1] += __ldg(f + 1); h[2] += __ldg(f + 2);
       }
    }
@@ -902,7 +906,7 @@ llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPa
       }
       double h[3];
       ext_field(t, i, k, h);
-      add_time_field(p, t.M, k, p.step, h);
+      h[0] += p.tf[0]; h[1] += p.tf[1]; h[2] += p.tf[2];
       // beff = beff1 + beff2, beff2 = beff_q + external_field (hamiltonianactions.f90:240-243)
       const double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
       SpinVec old;
@@ -1069,7 +1073,7 @@ llg_resident_kernel(const __grid_constant__ Tables t, const __grid_constant__ Ll
          resident_pairs<REDUCED>(t, shc, idx + (size_t)a * zt * nt + threadIdx.x, nt, i, ih, own, smc, smd, smb, bs, bq);
          site_field<REDUCED, false, ASD_CHUNK, false, false>(t, shc, i, ih, own, smc, smd, smb, bs, bq);
          ext_field(t, i, k, h);
-         add_time_field(p, t.M, k, step, h);
+         add_time_field(p, step, h);
          const double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
          store_spin_cluster(cl, shp, i, integrate_site<SOLVER, 1, true>(t, p, i, k, io, b, own, own, b2eff, nullptr, step), nrank);
       }
@@ -1086,7 +1090,7 @@ llg_resident_kernel(const __grid_constant__ Tables t, const __grid_constant__ Ll
          resident_pairs<REDUCED>(t, shp, idx + (size_t)a * zt * nt + threadIdx.x, nt, i, ih, own, smc, smd, smb, bs, bq);
          site_field<REDUCED, false, ASD_CHUNK, false, false>(t, shp, i, ih, own, smc, smd, smb, bs, bq);
          ext_field(t, i, k, h);
-         add_time_field(p, t.M, k, step, h);
+         add_time_field(p, step, h);
          const double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
          store_spin_cluster(cl, shc, i, integrate_site<SOLVER, 2, true>(t, p, i, k, io, b, own, old, b2eff, nullptr, step), nrank);
       }

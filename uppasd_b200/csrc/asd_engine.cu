@@ -203,7 +203,8 @@ struct asd_engine {
    int state_layout = 0;  // 0 = none, 1 = sd, 2 = mc
    DevBuf<SpinVec> cur, pred;
    DevBuf<double> b2eff, esite, part, red, ring;   // ring: per-sample sums of asd_sd_run
-   DevBuf<double> tfield;               // time-dependent uniform field of the steps tf_first .. tf_first + tf_n - 1 ([step][M][3])
+   DevBuf<double> tfield;               // time-dependent uniform field of the steps tf_first .. tf_first + tf_n - 1 ([step][3])
+   std::vector<double> h_tfield;        // host copy: the stage launches take the vector of their step as a kernel parameter
    long long tf_first = 0;
    int tf_n = 0;
    double* h_red = nullptr;             // pinned host landing zone of the per-ensemble sums (4 doubles each)
@@ -1113,6 +1114,11 @@ static int sd_steps(asd_engine* e, long nsteps, long first_step) {
    }
    for (long s = 0; s < nsteps; s++) {
       p.step = (unsigned long long)(first_step + s);
+      {
+         const long long q = (long long)p.step - e->tf_first;
+         const bool on = e->tf_n > 0 && q >= 0 && q < e->tf_n;
+         for (int a = 0; a < 3; a++) p.tf[a] = on ? e->h_tfield[(size_t)3 * q + a] : 0.0;
+      }
       const bool last = (s == nsteps - 1);
       // the last corrector launch also leaves the per-tile sums of emomM (not on the fixed-moment path, whose tiles differ)
       p.msum_part = (last && p.frozen == nullptr) ? e->msum_part.p : nullptr;
@@ -1501,10 +1507,10 @@ int asd_set_torque(asd_engine* e, const double* f) {
 int asd_set_time_field(asd_engine* e, long first_step, long nsteps, const double* tfield) {
    if (e->N == 0) return fail(-2, "asd_set_system must be called first");
    CU(cudaSetDevice(e->device));
-   if (!tfield || nsteps <= 0) { e->tf_n = 0; return 0; }
-   if (nsteps > 100000000L / std::max(e->M, 1)) return fail(-1, "asd_set_time_field: schedule too long (%ld steps)", nsteps);
-   const size_t n = (size_t)nsteps * e->M * 3;
-   // host layout tfield(3, Mensemble, nsteps) is exactly the device layout [step][M][3]
+   if (!tfield || nsteps <= 0) { e->tf_n = 0; e->h_tfield.clear(); return 0; }
+   if (nsteps > 100000000L) return fail(-1, "asd_set_time_field: schedule too long (%ld steps)", nsteps);
+   const size_t n = (size_t)nsteps * 3;
+   e->h_tfield.assign(tfield, tfield + n);
    int r = e->tfield.alloc(n);
    if (r) return r;
    CU(cudaMemcpyAsync(e->tfield.p, tfield, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));

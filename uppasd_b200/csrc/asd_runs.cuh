@@ -276,7 +276,9 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
          site_field<true, false, ASD_CHUNK, XS>(t, S, i, ih, own, smc, smd, smb, bs, bq, s3);
          double h[3];
          ext_field(t, i, k, h);
-         add_time_field(p, t.M, k, p.step, h);
+#ifndef ASD_NO_TFIELD
+         h[0] += p.tf[0]; h[1] += p.tf[1]; h[2] += p.tf[2];
+#endif
          const double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
          const SpinVec o = integrate_site<SOLVER, STAGE>(t, p, i, k, io, b, own, (STAGE == 1) ? own : old, b2eff, gn[0]);
          if (STAGE == 1) predk[i] = o; else curk[i] = o;

@@ -97,13 +97,13 @@ class Engine:
         self._chk(self.lib.asd_set_torque(self.h, _p(_f64(bt, (3, self.N, self.M)))))
 
     def set_time_field(self, first_step, tfield):
-        """tfield(3, M, nsteps): uniform time-dependent field of the steps first_step ... (None clears)"""
+        """tfield(3, nsteps): uniform time-dependent field of the steps first_step ... (None clears)"""
         if tfield is None:
             self._chk(self.lib.asd_set_time_field(self.h, 0, 0, None))
             return
         f = _f64(tfield)
-        assert f.shape[:2] == (3, self.M), f.shape
-        self._chk(self.lib.asd_set_time_field(self.h, first_step, f.shape[2], _p(f)))
+        assert f.ndim == 2 and f.shape[0] == 3, f.shape
+        self._chk(self.lib.asd_set_time_field(self.h, first_step, f.shape[1], _p(f)))
 
     def set_llg(self, sdealgh, delta_t, landeg=None, lambda1=None, temp=None, temprescale=1.0, mompar=0, seed=20261017):
         def arr(x):
