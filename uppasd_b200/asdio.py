@@ -362,7 +362,9 @@ def read_restart(path, natom, mensemble):
         it, k, i = int(r[0]), int(r[1]) - 1, int(r[2]) - 1
         rstep = it
         mmom[i, k] = _num(r[3])
-        emom[:, i, k] = [_num(x) for x in r[4:7]]
+        e = np.array([_num(x) for x in r[4:7]])
+        # read_mag_conf_std normalises every row (restart.f90:354-357, f_normalize_vec = vec / norm2(vec)): the file holds 9 digits
+        emom[:, i, k] = e / np.sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2])
     return rstep, emom, mmom
 
 

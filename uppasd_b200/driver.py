@@ -368,7 +368,8 @@ class Simulation:
     def relax(self, mode='S', nstep=10, temperature=0.0, timestep=1.0e-16, damping=0.5):
         """pyasd.f90:255-298 relax_: nstep steps / sweeps without measurements, returns moments(3,N,M)"""
         e = self.engine
-        first = getattr(self, '_relax_step', 1)
+        # the noise / draw counter continues after the phases already run (a fresh counter would replay the initial phase's stream)
+        first = getattr(self, '_relax_step', getattr(self, '_noise_offset', 1))
         if mode == 'S':
             self._llg(self.inp['sdealgh'], timestep, damping, temperature)
             e.sd_steps(nstep, first_step=first)
