@@ -511,6 +511,20 @@ def main():
             secondary['mc'] = mc
         except Exception as ex:                                   # the headline line must survive
             secondary['mc'] = {'error': repr(ex)[:300]}
+        try:
+            # the other integrator of the path (Depondt, SDEalgh 5) and the T = 0 rate of the headline solver, same supercell
+            for key, alg, temp in (('llg_depondt', 5, a.temp), ('llg_t0', a.solver, 0.0)):
+                e.set_llg(alg, 1e-16, landeg=1.0, lambda1=a.damping, temp=temp, seed=20261017)
+                e.sd_steps(3, first_step=1)
+                tm = torch.tensor([e.time_sd_steps(steps, first_step=4)], device='cuda', dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                rate = world * n * steps / (float(tm.item()) * 1e-3)
+                bb = sum(B_ALG[alg])
+                secondary[key] = {'value': rate, 'unit': 'atom-steps/s', 'ms_per_step': float(tm.item()) / steps, 'solver': alg, 'temp': temp,
+                                  'step_alg_bytes_per_atom': bb, 'step_frac_of_peak': bb * rate / world / 1e9 / peak}
+        except Exception as ex:
+            secondary['llg_depondt'] = {'error': repr(ex)[:300]}
         secondary.update(config_blocks(world, rank, local, dist, torch, peak))
 
     if rank == 0:
