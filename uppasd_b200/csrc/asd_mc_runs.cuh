@@ -326,8 +326,9 @@ __device__ __forceinline__ void mc_sweep_group(const Tables& t, const McParams& 
    const unsigned short* __restrict__ bq = gr + MCR_HDR + half * c.sp;
    const int cs0 = ih * c.sp;
    double f[3] = {0.0, 0.0, 0.0};
+   int s4 = 0;
 #pragma unroll 2
-   for (int s4 = 0; s4 < ns; s4 += 4) {
+   for (; s4 + 4 <= ns; s4 += 4) {
       const uint2 bw = *reinterpret_cast<const uint2*>(bq + s4);
       const unsigned b[4] = {bw.x & 0xffffu, bw.x >> 16, bw.y & 0xffffu, bw.y >> 16};
 #pragma unroll
@@ -336,6 +337,12 @@ __device__ __forceinline__ void mc_sweep_group(const Tables& t, const McParams& 
          const double cc = mr.cseq[cs0 + s4 + u];
          f[0] = fma(cc, m[0], f[0]); f[1] = fma(cc, m[1], f[1]); f[2] = fma(cc, m[2], f[2]);
       }
+   }
+   // the last 1..3 steps one by one (bcc Fe: 25 steps = 6 blocks + 1) instead of a padded block of zero records
+   for (; s4 < ns; s4++) {
+      const double* __restrict__ m = lane3 + 3u * (unsigned)bq[s4];
+      const double cc = mr.cseq[cs0 + s4];
+      f[0] = fma(cc, m[0], f[0]); f[1] = fma(cc, m[1], f[1]); f[2] = fma(cc, m[2], f[2]);
    }
 #pragma unroll
    for (int a = 0; a < 3; a++) f[a] += __shfl_xor_sync(FULL, f[a], 16);
