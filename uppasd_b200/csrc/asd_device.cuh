@@ -482,7 +482,9 @@ __device__ __forceinline__ void aniso_field(const Tables& t, int i, int ih, doub
 template <bool REDUCED, bool EXCH = true, int CH = ASD_CHUNK, bool XS = false, bool PAIRS = true>
 __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __restrict__ S, int i, int ih,
                                            const SpinVec& own, const double* smc, const double* smd,
-                                           const double* smb, double bs[3], double bq[3], const double* __restrict__ s3 = nullptr) {
+                                           const double* smb, double bs[3], double bq[3], const double* __restrict__ s3 = nullptr,
+                                           const uint4* dmw0 = nullptr) {
+   // dmw0: the first DM position word of this atom when the caller fetched it ahead of time (asd_runs.cuh)
    double fx = EXCH ? 0.0 : bs[0], fy = EXCH ? 0.0 : bs[1], fz = EXCH ? 0.0 : bs[2];
    const int Npad = t.Npad;
    // ---- Heisenberg (hamiltonianactions.f90:461-464) ----
@@ -541,7 +543,24 @@ __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __res
       const int n = REDUCED ? __ldg(t.dmsize + ih) : t.zdm;
       const bool smem_dm = XS && t.dm16 != nullptr;
       uint4 wd = make_uint4(0u, 0u, 0u, 0u);
-      for (int j = 0; j < n; j++) {
+      int jstart = 0;
+      if (XS && REDUCED && smem_dm && smd != nullptr && dmw0 != nullptr) {
+         // register-blocked kernel: the first eight DM neighbours from the prefetched position word, D vectors and moments from
+         // shared memory, fully unrolled (the generic loop below costs 42 instructions per neighbour: variable shifts to extract the
+         // position, generic loads of D, a dependent global load of the word; ncu r2q: a quarter of the instructions of config 4)
+         __builtin_assume(__isShared(smd));
+         const uint4 w = *dmw0;
+         const unsigned li[8] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16, w.z & 0xffffu, w.z >> 16, w.w & 0xffffu, w.w >> 16};
+         const double* __restrict__ D0 = smd + (size_t)ih * t.zdm * 3;
+#pragma unroll
+         for (int j = 0; j < 8; j++)
+            if (j < n) {
+               const double* __restrict__ m = s3 + li[j] * 3u;
+               dm_term(D0[3 * j], D0[3 * j + 1], D0[3 * j + 2], m[0], m[1], m[2], fx, fy, fz);
+            }
+         jstart = 8;
+      }
+      for (int j = jstart; j < n; j++) {
          double Dx, Dy, Dz;
          if (REDUCED) {
             const double* __restrict__ d = (smd ? smd : t.dmv) + ((size_t)ih * t.zdm + j) * 3;
@@ -552,7 +571,7 @@ __device__ __forceinline__ void site_field(const Tables& t, const SpinVec* __res
          }
          double mx, my, mz;
          if (smem_dm) {
-            if ((j & 7) == 0) wd = __ldg(t.dm16 + (size_t)(j >> 3) * Npad + i);
+            if ((j & 7) == 0) wd = (j == 0 && dmw0) ? *dmw0 : __ldg(t.dm16 + (size_t)(j >> 3) * Npad + i);
             const unsigned c = ((j >> 1) & 3) == 0 ? wd.x : ((j >> 1) & 3) == 1 ? wd.y : ((j >> 1) & 3) == 2 ? wd.z : wd.w;
             const double* __restrict__ m = s3 + ((j & 1) ? (c >> 16) : (c & 0xffffu)) * 3u;
             mx = m[0]; my = m[1]; mz = m[2];

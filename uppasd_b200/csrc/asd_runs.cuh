@@ -185,6 +185,16 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
       mt[r] = __ldg(t.meta + ii);
       if (i >= t.Nown) mt[r].y = -1;
    }
+   // XS: the first DM position word of the 4 atoms (one 16-byte load each) joins the independent loads of the prologue; fetched
+   // inside the integrator loop it was a dependent global load per atom (ncu r2p: 10 % of the stall samples of config 4)
+   uint4 dmw[R];
+   if (XS) {
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+         const int i = i0 + 32 * r;
+         dmw[r] = (t.dm16 != nullptr && i < t.Nown) ? __ldg(t.dm16 + i) : make_uint4(0u, 0u, 0u, 0u);
+      }
+   }
    const int cnt = __ldg(t.ucount + tile);
    const int* __restrict__ ul = t.ulist + (size_t)tile * t.ucap;
    const int ncpl = t.sm_dm + t.sm_bq;                       // exchange couplings ride in the constant bank
@@ -273,7 +283,7 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
       if (STAGE == 2) old_n = curk[inext];
       if (io >= 0) {
          double bs[3] = {f[0][0], f[0][1], f[0][2]}, bq[3];
-         site_field<true, false, ASD_CHUNK, XS>(t, S, i, ih, own, smc, smd, smb, bs, bq, s3);
+         site_field<true, false, ASD_CHUNK, XS>(t, S, i, ih, own, smc, smd, smb, bs, bq, s3, (XS && t.dm16 != nullptr) ? &dmw[0] : nullptr);
          double h[3];
          ext_field(t, i, k, h);
 #ifndef ASD_NO_TFIELD
@@ -296,6 +306,7 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
          f[q][0] = f[q + 1][0]; f[q][1] = f[q + 1][1]; f[q][2] = f[q + 1][2];
          mt[q] = mt[q + 1];
          gn[q][0] = gn[q + 1][0]; gn[q][1] = gn[q + 1][1]; gn[q][2] = gn[q + 1][2];
+         if (XS) dmw[q] = dmw[q + 1];
       }
    }
    if (MSUM) {
