@@ -469,7 +469,10 @@ def main():
     k2 = steps
     keep4, h_s = pinned(np.zeros((3, 1, k2), order='F'))
     del emomM
-    e.sd_run(2, first_step=9_000, sample_every=1)          # sample ring + pinned landing zone allocated outside the timed region
+    # staging buffers of the three calls (device I/O buffers, sample ring, pinned landing zone) are allocated by a first, untimed pass
+    e.set_moments(h_e, h_m)
+    e.sd_run(2, first_step=9_000, sample_every=1)
+    e.get_moments(out=(h_e, None, None))
     barrier()
     t0 = time.perf_counter()
     e.set_moments(h_e, h_m)

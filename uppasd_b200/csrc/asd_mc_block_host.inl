@@ -280,6 +280,12 @@ static int mc_sweeps_block(asd_engine* e, McParams& p, long nsweeps, long first_
          // one launch for the whole sweep: tickets in class order, dependencies through done[] (asd_mc_runs.cuh)
          tk.counter = B.counter.p; tk.base = B.tickets; tk.epoch = ++B.epoch; tk.done = B.done.p; tk.adj = B.adj.p; tk.nadj = B.nadj.p;
          tk.tclass = B.tclass.p; tk.cap = B.adjcap; tk.ntile = B.ntile;
+         {
+            const char* la = std::getenv("ASD_MC_LOOKAHEAD");
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+            tk.lookahead = la ? atoi(la) : sms;       // measured on bcc 128^3: 0 -> 0.456, 148 -> 0.443, 296 -> 0.451, 592 -> 0.469 ms per sweep
+         }
          const dim3 gr((unsigned)((long)B.ntile * e->M));
          if (B.nt == 512) {
             if (hb) mc_block_ws_launch(mc_block_ws_kernel<true>, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, e->cur.p);

@@ -204,6 +204,7 @@ struct McTicket {
    const int* __restrict__ nadj;               // [ntile]
    const unsigned char* __restrict__ tclass;   // [ntile] class of every tile
    int cap, ntile;
+   int lookahead;                              // tickets ahead whose tile is prefetched into L2 ( = CTAs resident on the GPU)
 };
 
 __device__ __forceinline__ SpinVec ld_spin_cg(const SpinVec* p) {
@@ -460,6 +461,23 @@ mc_block_run_kernel(const __grid_constant__ Tables t, const __grid_constant__ Mc
    }
    const int tile = c.tile;
    c.S = cur + (size_t)c.k * t.Npad;
+   if (TICKET && tk.lookahead > 0 && tid < 5) {
+      // L2 prefetch for the CTA that will hold ticket n + lookahead (it starts about one CTA lifetime from now): what its first
+      // phases read with dependent loads -- colour order, original indices and own spins (draws), group table, gather list
+      const unsigned long long n2 = s_ticket + (unsigned long long)tk.lookahead;
+      if (n2 < (unsigned long long)tk.ntile * (unsigned)t.M) {
+         const int k2 = (int)(n2 % (unsigned)t.M);
+         const size_t t2 = (size_t)__ldg(mb.tilelist + (int)(n2 / (unsigned)t.M));
+         const void* ptr = nullptr;
+         unsigned bytes = 0;
+         if (tid == 0) { ptr = cur + (size_t)k2 * t.Npad + t2 * 1024; bytes = 1024u * 32u; }
+         if (tid == 1) { ptr = mb.corder + t2 * 1024; bytes = 1024u * 2u; }
+         if (tid == 2) { ptr = t.orig + t2 * 1024; bytes = 1024u * 4u; }
+         if (tid == 3) { ptr = mr.gtab + t2 * mr.gstride; bytes = (unsigned)mr.gwords * 2u; }
+         if (tid == 4) { ptr = mb.ulist + t2 * mb.ucap; bytes = (unsigned)mb.ucap * 4u; }
+         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes & ~15u) : "memory");
+      }
+   }
    MC_PROF_T(t_0);
    // shared memory: draw records [batch][5] | group table | slots [batch] | emomM of the list + 16 zero records
    double* __restrict__ rec = sm;
