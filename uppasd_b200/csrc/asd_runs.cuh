@@ -225,6 +225,33 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
    float gn[R][3];
 #pragma unroll
    for (int r = 0; r < R; r++) { gn[r][0] = 0.f; gn[r][1] = 0.f; gn[r][2] = 0.f; }
+   // short gather lists (layouts with few neighbours: DM systems, 2-D lattices): rounds of 2 x 3 spins per thread -- the long form
+   // below executes its 14 predicated load / convert / store slots whatever the list length (ncu r2s: 670 of 3770 instructions of
+   // config 4).  Only in the XS kernels, so that the code of the headline kernel is not touched.
+   if (XS && t.ucap <= 6 * NT) {
+      constexpr int SS = 3;
+      for (int u0 = threadIdx.x; u0 < cnt; u0 += 2 * SS * NT) {
+         int sl[2 * SS];
+#pragma unroll
+         for (int a = 0; a < 2 * SS; a++) sl[a] = (u0 + a * NT < cnt) ? __ldg(ul + u0 + a * NT) : 0;
+         SpinVec v[2 * SS];
+#pragma unroll
+         for (int a = 0; a < 2 * SS; a++) v[a] = S[sl[a]];
+         if (u0 == (int)threadIdx.x && p.thermal) {
+#pragma unroll
+            for (int r = 0; r < R; r++)
+               gauss3f_raw(p.seed, (uint32_t)mt[r].y + t.atom_offset, (uint32_t)k + t.ens_offset, p.step, 0u, gn[r][0], gn[r][1], gn[r][2]);
+         }
+#pragma unroll
+         for (int a = 0; a < 2 * SS; a++) {
+            const int u = u0 + a * NT;
+            if (u < cnt) {
+               double* __restrict__ m = s3 + 3 * u;
+               m[0] = v[a].x * v[a].m; m[1] = v[a].y * v[a].m; m[2] = v[a].z * v[a].m;
+            }
+         }
+      }
+   } else
    // gather list -> shared memory in rounds of 2 x SB spins per thread: the indices of both halves are fetched first
    // (one round trip), the spins of the second half fly while the first half is converted and stored
    for (int u0 = threadIdx.x; u0 < cnt; u0 += 2 * SB * NT) {
