@@ -922,7 +922,10 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
       const int NW = L.t.tile_slots / 128;
       const size_t smem = (size_t)((L.t.sm_dm + L.t.sm_bq + 1) & ~1) * sizeof(double) + (size_t)3 * (L.t.ucap + 32) * sizeof(double) +
                           (size_t)NW * L.t.urow * sizeof(uint4);
-      const bool xs = L.t.dm16 != nullptr || L.t.bq16 != nullptr;
+      // the XS instantiation also carries the staging loop for short gather lists (asd_runs.cuh): layouts with few neighbours take it
+      // whether or not they have DM / BQ tables (ASD_SHORT_STAGING=0: only layouts with such tables)
+      static const bool short_env = !(std::getenv("ASD_SHORT_STAGING") && atoi(std::getenv("ASD_SHORT_STAGING")) == 0);
+      const bool xs = L.t.dm16 != nullptr || L.t.bq16 != nullptr || (short_env && L.t.ucap <= 6 * 256);
       static const bool pdl_env = !(std::getenv("ASD_PDL") && atoi(std::getenv("ASD_PDL")) == 0);
       const bool pdl = pdl_env && !EDGE && !e->slab.on && big_grid;
 #define ASD_LAUNCH_RUNS(NWV, XSV)                                                                                                  \
