@@ -582,3 +582,68 @@ def pontryagin_tri(emom, simp):
         d = 1.0 + (m1 * m2).sum(axis=0) + (m1 * m3).sum(axis=0) + (m2 * m3).sum(axis=0)
         per[k] = (2.0 * np.arctan(vol / d)).sum() / (4.0 * np.pi)
     return per.sum() / M, per
+
+
+# ---- magnetic-field pulse (do_bpulse 1-4) -------------------------------------------------------------------------------
+def bpulse_setup(do_bpulse, b0, step, par):
+    """read_bpulse's derived constants ba, bb (fieldpulse.f90:196-209); par = bpulse_par(1:npar)"""
+    bp = list(par) + [0.0] * (10 - len(par))
+    ba = bb = 0.0
+    if do_bpulse == 1:
+        ba = (bp[0] - bp[1]) / np.log(bp[4] / bp[5])
+        bb = (bp[2] - bp[3]) / np.log(bp[4] / bp[5])
+    elif do_bpulse == 2:
+        ba = 1.0
+        bb = -1.0 / (2.0 * bp[2] ** 2)
+    elif do_bpulse == 3:
+        ba = bp[2] / (bp[1] - bp[0])
+        bb = 1.0 / ((bp[1] - bp[0]) ** bp[2] * np.exp(-ba * bp[1]))
+    return dict(do_bpulse=do_bpulse, b0=list(b0), step=int(step), bp=bp, ba=float(ba), bb=float(bb))
+
+
+def bpulse_field(B, t):
+    """bpulse (fieldpulse.f90:34-67) with exppulse / gaussianpulse / polexppulse / squarepulse (:73-119): bpulsefield(3) at time t"""
+    bp, ba, bb, k = B['bp'], B['ba'], B['bb'], B['do_bpulse']
+    if k == 1:
+        if t <= bp[1]:
+            tp = bp[5] * np.exp((t - bp[1]) / ba)
+        elif t > bp[1] and t < bp[2]:
+            tp = bp[5]
+        else:
+            tp = bp[5] * np.exp((bp[2] - t) / bb)
+    elif k == 2:
+        tp = bp[5] * ba * np.exp(bb * (t - bp[1]) ** 2)
+    elif k == 3:
+        tp = bp[5] * bb * (t - bp[0]) ** bp[2] * np.exp(-ba * t)
+    elif k == 4:
+        if t < bp[1]:
+            tp = 0.0
+        elif t >= bp[1] and t < bp[2]:
+            tp = bp[5]
+        else:
+            tp = 0.0
+    else:
+        tp = 0.0
+    return np.array([B['b0'][0] * tp, B['b0'][1] * tp, B['b0'][2] * tp])
+
+
+def sd_run_bpulse(S, sdealgh, delta_t, damping, B, rstep, nstep):
+    """sd_mphase with a field pulse (sd_driver.f90:389-393, 703-722, 770-779): the pulse is evaluated at delta_t * rstep before the
+    first step and re-evaluated at delta_t * mstep after the moment update of every bpulse_step-th step; effective_field adds it
+    to beff2 as time_external_field (hamiltonianactions.f90:241).  Returns the final SdState and the fields the steps saw."""
+    st = SdState(S, sdealgh, delta_t, damping)
+    ext0 = S['external_field'].copy(order='F')
+    field = bpulse_field(B, delta_t * rstep)
+    scount = 1
+    seen = []
+    for mstep in range(rstep + 1, rstep + nstep + 1):
+        S['external_field'][...] = ext0 + field[:, None, None]
+        seen.append(field.copy())
+        st.step()
+        if scount == B['step']:
+            field = bpulse_field(B, delta_t * mstep)
+            scount = 1
+        else:
+            scount += 1
+    S['external_field'][...] = ext0
+    return st, np.array(seen).T

@@ -285,3 +285,45 @@ def test_inpsd_keywords_outside_the_path_are_not_silent(tmp_path):
             q.write_text(raw['inpsd.dat'])
             dd = asdio.read_inpsd(str(q))
             assert dd['unserved'] == [] and dd['ignored'] == [], (f, dd['unserved'], dd['ignored'])
+
+
+BPULSE_FILES = {
+    1: 'exp pulse\n0.0 0.0 30.0\n1.0e-16\n1\n6\n0.0\n4.0e-15\n1.0e-14\n1.4e-14\n0.01\n1.0\n',
+    2: 'gaussian\n10.0 0.0 20.0\n1.0e-16\n2\n6\n0.0\n6.0e-15\n2.0e-15\n0.0\n0.0\n1.5\n',
+    3: 'polexp\n0.0 25.0 0.0\n1.0e-16\n1\n6\n0.0\n5.0e-15\n2.0\n0.0\n0.0\n1.0\n',
+    4: 'square\n0.0 0.0 -40.0\n1.0e-16\n3\n6\n0.0\n3.0e-15\n9.0e-15\n0.0\n0.0\n1.0\n',
+}
+
+
+@pytest.mark.parametrize('kind', [1, 2, 3, 4])
+def test_field_pulse_schedule_equals_the_oracle_restatement(kind, tmp_path):
+    """do_bpulse 1-4 (fieldpulse.f90:34-119, 178-212; evaluation times sd_driver.f90:389-393, 770-779): the product's schedule
+    (uppasd_b200/fields.py) against the oracle's step-by-step restatement, and the shapes against their definitions"""
+    from uppasd_b200 import fields
+    p = tmp_path / 'bpulsefile'
+    p.write_text(BPULSE_FILES[kind])
+    P = fields.read_bpulse(str(p), kind)
+    dt, rstep, nstep = 1.0e-16, 7, 160
+    tf = fields.bpulse_schedule(kind, P, dt, rstep, nstep)
+    B = orc.bpulse_setup(kind, P['b0'], P['step'], P['par'][:6])
+    assert abs(B['ba'] - P['ba']) <= 1e-15 * abs(P['ba']) and abs(B['bb'] - P['bb']) <= 1e-15 * abs(P['bb'])
+    field, scount = orc.bpulse_field(B, dt * rstep), 1
+    for s in range(nstep):
+        assert np.abs(tf[:, s] - field).max() <= 1e-13 * max(1.0, np.abs(field).max()), (kind, s)
+        if scount == B['step']:
+            field, scount = orc.bpulse_field(B, dt * (rstep + 1 + s)), 1
+        else:
+            scount += 1
+    amp = np.abs(tf).max(axis=0) / np.abs(np.array(P['b0'])).max()
+    if kind == 4:                       # square: 0 before par(2), par(6) until par(3), 0 after; held for bpulse_step steps
+        assert set(np.round(amp, 12)) == {0.0, 1.0} and amp[0] == 0.0 and amp[-1] == 0.0
+    if kind == 1:                       # plateau at par(6), exponential head from par(5) at par(1)
+        assert abs(amp.max() - 1.0) < 1e-12 and amp[0] < 0.1
+    if kind == 2:                       # Gaussian centred at par(2) with width par(3)
+        assert abs(amp.max() - 1.5) < 0.01 and abs(np.argmax(amp) + rstep - 60) <= 2
+    pin = tmp_path / 'inpsd.dat'
+    pin.write_text('simid x\ndo_bpulse %d\nbpulsefile ./bpulsefile\n' % kind)
+    d = asdio.read_inpsd(str(pin))
+    assert d['do_bpulse'] == kind and d['unserved'] == [] and d['bpulsefile'].endswith('bpulsefile')
+    pin.write_text('simid x\ndo_bpulse 5\n')
+    assert asdio.read_inpsd(str(pin))['unserved'] == [('do_bpulse', '5')]

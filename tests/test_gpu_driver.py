@@ -2,13 +2,16 @@
 (materialised from tests/golden/*.json) -> `uppasd_b200.driver.Simulation(...).run()` -> the reference's measurement
 files, read back row by row like tests/bergtest.py does and compared with the values its YAML files pin
 (tests/regulartests.yaml, tests/regressionResaro.yaml, tests/cudatests.yaml; tolerances = bergtest's)."""
+import json
 import os
 
 import numpy as np
 import pytest
 
+from oracle import inputs, orc
 from test_asdio_host import materialise
 from uppasd_b200 import asdio
+from util import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
@@ -209,3 +212,39 @@ def test_kagome_tensor_run_directory(tmp_path):
     cu = [x for x in asdio.read_out(os.path.join(d, 'cumulants.kagome_T.out')) if int(x[0]) == 171][0]
     for a, b in zip(cu[1:5], exp['cumulants']['171']):
         assert abs(a - b) <= 1e-8, (cu, exp)
+
+
+@pytest.mark.parametrize('kind,alg', [(1, 1), (4, 5)])
+def test_field_pulse_through_the_driver(kind, alg, tmp_path):
+    """do_bpulse in a run directory: the driver reads the bpulsefile, hands the schedule of the measurement phase to the engine once
+    (asd_set_time_field) and the stage kernels add the pulse of their step; final state against the oracle's sd_mphase loop with the
+    pulse evaluated step by step (sd_driver.f90:389-393, 703-722, 770-779), T = 0, to 1e-12"""
+    from test_asdio_host import BPULSE_FILES
+    from uppasd_b200 import driver, fields
+    fx = json.load(open(os.path.join(GOLDEN, 'kagome.json')))
+    d = tmp_path / 'run'
+    d.mkdir()
+    for k, v in fx['raw'].items():
+        (d / k).write_text(v)
+    drop = ('nstep', 'sdealgh', 'do_avrg', 'temp', 'initmag', 'mensemble')
+    lines = [l for l in fx['raw']['inpsd.dat'].splitlines() if not (l.split() and l.split()[0].lower() in drop)]
+    lines += ['nstep 120', 'sdealgh %d' % alg, 'do_avrg N', 'temp 0.0', 'initmag 3', 'mensemble 2', 'do_bpulse %d' % kind, 'bpulsefile ./bpulsefile']
+    (d / 'inpsd.dat').write_text('\n'.join(lines) + '\n')
+    (d / 'bpulsefile').write_text(BPULSE_FILES[kind])
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        sim = driver.Simulation(str(d / 'inpsd.dat'))
+        sim.run()
+    inp = sim.inp
+    args = list(inputs.load_fixture(fx))
+    args[0] = dict(args[0], mensemble=2)
+    S = orc.build_system(*args)
+    P = fields.read_bpulse(str(d / 'bpulsefile'), kind)
+    B = orc.bpulse_setup(kind, P['b0'], P['step'], P['par'][:6])
+    st, seen = orc.sd_run_bpulse(S, alg, inp['timestep'], inp['damping'], B, 0, 120)
+    assert np.abs(seen).max() > 1.0                                   # the pulse is there
+    assert np.abs(sim.bpulse - seen).max() <= 1e-13 * np.abs(seen).max()
+    got = sim.engine.get_moments()[0]
+    assert np.abs(got - st.emom).max() <= 1e-12
+    assert np.abs(got - S['emom']).max() > 1e-3

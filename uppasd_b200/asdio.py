@@ -56,16 +56,16 @@ def defaults():
         ip_hfield=(0.0, 0.0, 0.0), ip_temp=0.0, ip_nphase=[], ip_mcanneal=[], ip_mcnstep=0, do_reduced='N', do_sortcoup='N',
         mompar=0, landeg_glob=2.0, do_avrg='Y', avrg_step=100, avrg_buff=10, do_cumu='N', cumu_step=50, cumu_buff=10,
         plotenergy=0, do_tottraj='N', tottraj_step=1000, tottraj_buff=10, trajectories=[], do_prnstruct=0,
-        gpu_mode=0, gpu_rng_seed=0, do_jtensor=0, map_multiple=False, relaxed_if=False, do_proj_avrg='N', do_cumu_proj='N', skyno='N',
+        gpu_mode=0, gpu_rng_seed=0, do_jtensor=0, do_bpulse=0, bpulsefile=None, map_multiple=False, relaxed_if=False, do_proj_avrg='N', do_cumu_proj='N', skyno='N',
         skyno_step=100, skyno_buff=10)
 
 
 _SCALAR_INT = {'sym', 'maptype', 'do_ralloy', 'mensemble', 'tseed', 'sdealgh', 'ipsdealgh', 'initmag', 'nstep', 'mcnstep',
                'mompar', 'avrg_step', 'avrg_buff', 'cumu_step', 'cumu_buff', 'plotenergy', 'tottraj_step', 'tottraj_buff',
-               'do_prnstruct', 'gpu_mode', 'gpu_rng_seed', 'do_jtensor', 'ip_mcnstep', 'skyno_step', 'skyno_buff'}
+               'do_prnstruct', 'gpu_mode', 'gpu_rng_seed', 'do_jtensor', 'ip_mcnstep', 'skyno_step', 'skyno_buff', 'do_bpulse'}
 _SCALAR_REAL = {'alat', 'temp', 'damping', 'timestep', 'ip_temp'}
 _SCALAR_FLAG = {'aunits', 'posfiletype', 'do_reduced', 'do_sortcoup', 'do_avrg', 'do_cumu', 'do_tottraj', 'mode', 'ip_mode', 'do_proj_avrg', 'do_cumu_proj', 'skyno'}
-_FILES = {'posfile', 'momfile', 'exchange', 'dm', 'bq', 'anisotropy', 'restartfile'}
+_FILES = {'posfile', 'momfile', 'exchange', 'dm', 'bq', 'anisotropy', 'restartfile', 'bpulsefile'}
 
 
 # Reference keywords that change the Hamiltonian, the dynamics or what a measurement means, and that this path does NOT serve
@@ -81,7 +81,7 @@ UNSERVED = {
     'jij_scale': ('1', '1.0', '1.d0', '1.0d0'), 'dm_scale': ('1', '1.0', '1.d0', '1.0d0'), 'ea_model': _OFF, 'rdm_model': _OFF,
     'locfield': _OFF, 'siteatomfield': None, 'do_fixed_mom': _OFF, 'do_mom_legacy': _OFF, 'multiscale': None,
     # dynamics outside the two solvers / the constant uniform temperature
-    'stt': _OFF, 'do_she': _OFF, 'do_sot': _OFF, 'do_bpulse': ('0',), 'bpulsefile': None, 'do_qhb': _OFF, 'gradtemp': ('0',), 'grad': _OFF,
+    'stt': _OFF, 'do_she': _OFF, 'do_sot': _OFF, 'do_qhb': _OFF, 'gradtemp': ('0',), 'grad': _OFF,
     'do_3tm': _OFF, 'do_site_damping': _OFF, 'do_site_ip_damping': _OFF, 'damping2': ('0', '0.0', '0.d0', '0.0d0'),
     'ip_damping2': ('0', '0.0', '0.d0', '0.0d0'), 'compensate_drift': ('0',), 'llg': ('1',), 'relaxtime': ('0', '0.0', '0.d0'),
     'do_ld': _OFF, 'do_sld': _OFF, 'do_gneb': _OFF, 'do_kmc': _OFF, 'do_wl': _OFF, 'para_rng': _OFF, 'ziggurat': ('y', 't'),
@@ -192,6 +192,8 @@ def read_inpsd(path):
                 d['ignored'].append(key)
         except (IndexError, ValueError) as exc:
             raise InputError('cannot read keyword %s in %s: %s' % (key, path, exc))
+    if d['do_bpulse'] not in (0, 1, 2, 3, 4):
+        d['unserved'].append(('do_bpulse', str(d['do_bpulse'])))     # 5 / 6: site-dependent static fields from files
     if d['do_cumu'] not in ('Y', 'N'):
         d['unwritten'].append('do_cumu ' + d['do_cumu'])      # 'A' (cumulants of every ensemble) is not written here
     if d['skyno'] not in ('N', 'T'):

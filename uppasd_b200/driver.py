@@ -16,7 +16,7 @@ import warnings
 
 import numpy as np
 
-from . import alloy, asdio, host, lattice, observables, refrng
+from . import alloy, asdio, fields, host, lattice, observables, refrng
 
 # source/Parameters/constants.f90:14-29
 CONSTANTS = dict(gama=1.760859644e11, k_bolt=1.38064852e-23, mub=9.274009994e-24, mry=2.179872325e-21)
@@ -332,6 +332,13 @@ class Simulation:
         if mode == 'S':
             self._llg(inp['sdealgh'], inp['timestep'], inp['damping'], inp['temp'])
             mstep, last = self.rstep + 1, self.rstep + inp['nstep']
+            if inp['do_bpulse'] in (1, 2, 3, 4):
+                # magnetic-field pulse: the whole schedule of the phase goes to the engine once (fields.py, asd_set_time_field)
+                P = fields.read_bpulse(inp['bpulsefile'] or os.path.join(self.dir, 'bpulsefile'), inp['do_bpulse'])
+                self.bpulse = fields.bpulse_schedule(inp['do_bpulse'], P, inp['timestep'], self.rstep, inp['nstep'])
+                e.set_time_field(off + mstep, self.bpulse)
+                if inp['plotenergy'] > 0:
+                    warnings.warn('do_bpulse: the Zeeman column of totenergy does not include the pulse field')
             while mstep <= last:
                 self._measure(mstep, mode)
                 if inp['plotenergy'] > 0 and (mstep - 1) % inp['avrg_step'] == 0:
@@ -340,6 +347,8 @@ class Simulation:
                 e.sd_steps(n, first_step=off + mstep)
                 mstep += n
             self._measure(mstep, mode)                          # sd_driver.f90:839-849: final measure + flush
+            if inp['do_bpulse'] in (1, 2, 3, 4):
+                e.set_time_field(0, None)
         else:
             mstep, last = 1, inp['mcnstep']
             while mstep <= last:
