@@ -88,3 +88,6 @@ def test_c_example_matches_the_python_host(tmp_path):
     em = e.get_moments()[0]
     assert np.abs(np.array(nums[:3]) - em[:, 0, 0]).max() <= 1e-12
     assert abs(np.linalg.norm(nums[:3]) - 1.0) <= 1e-11 and abs(nums[0] - 1.0) > 1e-6     # it precessed
+    # asd_sd_run: 10 samples, the last one is the sum of the final moments (= asd_measure's, printed before it)
+    assert 'samples = 10' in out
+    assert np.abs(np.array(nums[-3:]) - np.array(nums[3:6])).max() <= 1e-12
