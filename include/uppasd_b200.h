@@ -271,7 +271,8 @@ int asd_time_mc_sweeps(asd_engine* e, char mode, long nsweeps, double temperatur
 /* which field path the LLG stage kernels of the committed layout use: info[0] = 1 if the tile's gather list is staged
  * in shared memory, info[1] = R of the run-compressed register-blocked kernel (0: one atom per thread), info[2] =
  * largest gather list of a tile, info[3] = largest number of distinct neighbour runs of a group of R runs,
- * info[4] = slots per tile (256, 512 or 1024), info[5] = 1 if the DM / BQ neighbours are read from shared memory too */
+ * info[4] = slots per tile (256, 512 or 1024), info[5] = bit 0: the DM / BQ neighbours are read from shared memory too,
+ * bit 1: the gather list is staged from the moment planes emomM[M][3][Npad] with asynchronous copies (MM instantiations) */
 int asd_layout_info(asd_engine* e, int* info6);
 long asd_launch_count(asd_engine* e);
 int asd_synchronize(asd_engine* e);

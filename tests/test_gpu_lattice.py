@@ -321,3 +321,52 @@ def test_headline_128_cubed_against_oracle_and_direct_kernel(monkeypatch):
         assert np.abs(a - b).max() <= 1e-12, (solver, np.abs(a - b).max())
         assert np.abs(a - a0).max() > 1e-6                      # the spins did move
         er.close(); ed.close()
+
+
+def test_moment_planes_follow_every_writer_of_the_spins(monkeypatch):
+    """MM instantiation of the run kernel (gather list staged from the moment planes emomM[M][3][Npad], asd_runs.cuh): the planes
+    are rebuilt whenever something other than an MM stage launch wrote the spins.  Same calls on an engine built with ASD_MM=0
+    (gather list staged from the spins through registers): bit-identical states after steps, Monte Carlo sweeps, a new
+    asd_set_moments, a fixed-moment interlude (direct kernel) and the stage-timing entry point."""
+    fx, _, _ = load_golden('bccfe_cuda')
+    args = list(inputs.load_fixture(fx))
+    args[0] = dict(args[0], ncell=(64, 4, 8), mensemble=2, do_reduced='Y')
+    S = orc.build_system(*args)
+    inp = args[0]
+    rng = np.random.default_rng(11)
+    e0 = rng.normal(size=(3, S['Natom'], 2)); e0 /= np.sqrt((e0 ** 2).sum(axis=0))
+    S['emom'] = np.asfortranarray(e0)
+    S['emomM'] = np.asfortranarray(e0 * S['mmom'][None])
+    e1 = rng.normal(size=(3, S['Natom'], 2)); e1 /= np.sqrt((e1 ** 2).sum(axis=0))
+    e1 = np.asfortranarray(e1)
+    red = np.arange(1, S['Natom'] + 1)[np.arange(S['Natom']) % 5 != 2]
+    for solver in (1, 5):
+        monkeypatch.delenv('ASD_MM', raising=False)
+        a = _bcc_engine(S, inp, args, solver, 300.0)
+        monkeypatch.setenv('ASD_MM', '0')
+        b = _bcc_engine(S, inp, args, solver, 300.0)
+        monkeypatch.delenv('ASD_MM', raising=False)
+        assert a.layout_info()['runs'] == 4 and b.layout_info()['runs'] == 4
+        assert a.layout_info()['planes'] == 1 and b.layout_info()['planes'] == 0
+        for e in (a, b):
+            e.sd_steps(7, first_step=1)
+        assert np.array_equal(a.get_moments()[0], b.get_moments()[0]), (solver, 'steps')
+        for e in (a, b):
+            e.mc_sweeps('M', 3, 300.0)
+            e.sd_steps(5, first_step=8)
+        assert np.array_equal(a.get_moments()[0], b.get_moments()[0]), (solver, 'after Monte Carlo sweeps')
+        for e in (a, b):
+            e.set_moments(e1, S['mmom'])
+            e.sd_steps(5, first_step=13)
+        assert np.array_equal(a.get_moments()[0], b.get_moments()[0]), (solver, 'after asd_set_moments')
+        for e in (a, b):
+            e.set_evolving_atoms(red)
+            e.sd_steps(3, first_step=18)
+            e.set_evolving_atoms(None)
+            e.sd_steps(4, first_step=21)
+        assert np.array_equal(a.get_moments()[0], b.get_moments()[0]), (solver, 'after a fixed-moment interlude')
+        for e in (a, b):
+            e.time_sd_steps(0, first_step=25, stages=True)
+            e.sd_steps(2, first_step=26)
+        assert np.array_equal(a.get_moments()[0], b.get_moments()[0]), (solver, 'after the stage-timing entry')
+        a.close(); b.close()

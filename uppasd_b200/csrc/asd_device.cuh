@@ -96,6 +96,7 @@ struct Tables {
    int runs;              // 0: off, else 4: the LLG stage kernels use llg_runs_kernel (4 x-runs per warp)
    int urow;              // row stride of utab in 16-byte words
    const uint4* __restrict__ utab;    // [groups][urow]
+   int mm;          // 1: the union rows carry 8 * base and the run kernels stage from the moment planes (MM instantiations)
    int pf_tiles;    // L2 bulk-prefetch distance in 256-atom tiles (0 = off)
    int cpl_param;   // 1: reduced exchange couplings live in cpl_small (kernel parameter = constant bank)
    double cpl_small[256];
@@ -126,6 +127,9 @@ struct LlgParams {
    // uniform case (per_site == 0): site-independent factors evaluated once on the host with the same IEEE
    // operations the kernel would use (division and square root are correctly rounded on both sides)
    double u_lldamp, u_dt, u_sqrtdt, u_Dk, u_Dp;
+   // thermal amplitude without its 1/sqrt(m) factor: sigma = u_sig * m^-1/2 (u_sig1: midpoint, sqrt(2 u_Dk T temprescale);
+   // u_sig5: Depondt, sqrt(u_Dp T temprescale))
+   double u_sig1, u_sig5;
    // fused observable: when non-null, the corrector launch also leaves sum_i emomM of every tile in
    // msum_part[k][ntile][4] (asd_measure then only adds the per-tile partials: no second pass over the spins)
    double* msum_part;
@@ -138,6 +142,9 @@ struct LlgParams {
    // added unconditionally -- a branch here cost the register-blocked run kernel 18 %, measured); tfield[step - tf_first][3] = the
    // device copy of the schedule for the resident kernel, which advances the step itself
    double tf[3];
+   // moment planes of the MM run kernels (asd_runs.cuh): emomM of `cur` / `pred` as [M][3][Npad], null on every other path
+   double* mm_cur;
+   double* mm_pred;
    const double* __restrict__ tfield;
    long long tf_first;
    int tf_n;
@@ -632,6 +639,17 @@ __device__ __forceinline__ void stage_couplings(const Tables& t, double* sm, con
    if (n2) smb = sm + n0 + n1;
 }
 
+// m^-1/2 for the thermal amplitude (sigma ~ sqrt(T / m), randomnumbers.f90:667-670): single-precision seed + two Newton steps in
+// double (relative error < 4e-16), no division, no square root, no slow-path branch -- the division 1/m and the square root of
+// the literal formula cost the register-blocked kernel 45 instructions per atom-stage in its serial part.  m > 0.
+__device__ __forceinline__ double rsqrt_nr(double m) {
+   double y = (double)rsqrtf((float)m);
+   const double hm = 0.5 * m;
+   y = fma(y, fma(-hm * y, y, 0.5), y);
+   y = fma(y, fma(-hm * y, y, 0.5), y);
+   return y;
+}
+
 // Cayley transform of the semi-implicit midpoint scheme (midpoint.f90:153-164): (I+skew A)^-1 (I+skew A)^T e
 __device__ __forceinline__ void cayley(const double e[3], const double A[3], double out[3]) {
    const double detAi = 1.0 / (1.0 + (A[0] * A[0] + A[1] * A[1] + A[2] * A[2]));
@@ -746,7 +764,9 @@ __global__ void halo_push_kernel(int Nown, int M, size_t Npad, const SpinVec* __
 // FROZEN (compile time): the kernel honours LlgParams::frozen.  Only the one-atom-per-thread direct kernel and the resident
 // kernel are compiled with it (the check costs the register-blocked run kernel 1.5 %, measured); the engine routes
 // fixed-moment runs to them.
-template <int SOLVER, int STAGE, bool FROZEN = false>
+// LEAN (compile time): the caller guarantees uniform damping / g factor / temperature (per_site == 0), no torque field and
+// mompar == 0; the run kernel's plain-Heisenberg instantiation uses it (the runtime checks cost its serial part 30 %).
+template <int SOLVER, int STAGE, bool FROZEN = false, bool LEAN = false>
 __device__ __forceinline__ SpinVec integrate_site(const Tables& t, const LlgParams& p, int i, int k, int io, const double b[3],
                                                   const SpinVec& own, const SpinVec& c0, double* __restrict__ b2eff,
                                                   const float* gpre = nullptr, unsigned long long step_arg = ~0ull) {
@@ -759,8 +779,10 @@ __device__ __forceinline__ SpinVec integrate_site(const Tables& t, const LlgPara
       if (STAGE == 2 && p.mompar) o.m = calcm(p.mompar, c0.m, __ldg(p.mmom0 + (size_t)k * t.Npad + i), c0.z);
       return o;
    }
+   const bool per_site = !LEAN && p.per_site;
+   const int mompar = LEAN ? 0 : p.mompar;
    double lam, lg, temp;
-   if (p.per_site) { lam = __ldg(p.lambda_a + i); lg = __ldg(p.landeg_a + i); temp = __ldg(p.temp_a + i); }
+   if (per_site) { lam = __ldg(p.lambda_a + i); lg = __ldg(p.landeg_a + i); temp = __ldg(p.temp_a + i); }
    else { lam = p.lambda; lg = p.landeg; temp = p.temp; }
    const double e[3] = {c0.x, c0.y, c0.z};
    const double m = c0.m;
@@ -768,23 +790,24 @@ __device__ __forceinline__ SpinVec integrate_site(const Tables& t, const LlgPara
    if (gpre) { g[0] = (double)gpre[0]; g[1] = (double)gpre[1]; g[2] = (double)gpre[2]; }
    else if (p.thermal) gauss3f(p.seed, (uint32_t)io + t.atom_offset, (uint32_t)k + t.ens_offset, nstep, 0u, g[0], g[1], g[2]);
    double bt[3] = {0.0, 0.0, 0.0};
-   if (t.btorque) {
+   if (!LEAN && t.btorque) {
       const double* __restrict__ q = t.btorque + (size_t)k * 3 * t.Npad + i;
       bt[0] = __ldg(q); bt[1] = __ldg(q + t.Npad); bt[2] = __ldg(q + 2 * (size_t)t.Npad);
    }
-   const double lldamp = p.per_site ? 1.0 / (1.0 + lam * lam) : p.u_lldamp;
+   const double lldamp = per_site ? 1.0 / (1.0 + lam * lam) : p.u_lldamp;
    SpinVec o;
    if (SOLVER == 1) {
       // ---- Mentink's semi-implicit midpoint (midpoint.f90) ----
-      const double dt = p.per_site ? p.delta_t * 1.0 * p.gamma * lldamp : p.u_dt;  // bn = 1
-      const double sqrtdt = p.per_site ? sqrt(dt) : p.u_sqrtdt;
+      const double dt = per_site ? p.delta_t * 1.0 * p.gamma * lldamp : p.u_dt;  // bn = 1
+      const double sqrtdt = per_site ? sqrt(dt) : p.u_sqrtdt;
       const double dtg = dt * lg, sqrtdtg = sqrtdt * lg;
       // rannum (randomnumbers.f90:667-670,735-746): sigma = sqrt(2 D), D = lam/(1+lam^2) k_B/(gamma mu_B) gamma / m * T
       double sigma = 0.0;
       if (p.thermal) {
-         const double Dk = p.per_site ? (lam / (1 + lam * lam) * p.k_bolt / p.gamma / (p.mub)) * (p.gamma / 1.0) : p.u_Dk;
-         const double D = Dk * (1.0 / m) * temp * p.temprescale;
-         sigma = sqrt(2.0 * D);
+         // sigma = sqrt(2 D), D = Dk / m * T * temprescale, evaluated as sqrt(2 Dk T temprescale) * m^-1/2
+         double sg = p.u_sig1;
+         if (per_site) sg = sqrt(2.0 * ((lam / (1 + lam * lam) * p.k_bolt / p.gamma / (p.mub)) * (p.gamma / 1.0)) * temp * p.temprescale);
+         sigma = sg * rsqrt_nr(m);
       }
       const double r[3] = {g[0] * sigma, g[1] * sigma, g[2] * sigma};
       // etp: the spin the torque is evaluated with (old spin in stage 1, midpoint spin in stage 2)
@@ -804,14 +827,16 @@ __device__ __forceinline__ SpinVec integrate_site(const Tables& t, const LlgPara
          o.x = 0.5 * (e[0] + et[0]); o.y = 0.5 * (e[1] + et[1]); o.z = 0.5 * (e[2] + et[2]); o.m = m;
       } else {
          o.x = et[0]; o.y = et[1]; o.z = et[2];
-         o.m = p.mompar ? calcm(p.mompar, m, __ldg(p.mmom0 + (size_t)k * t.Npad + i), et[2]) : m;
+         o.m = mompar ? calcm(mompar, m, __ldg(p.mmom0 + (size_t)k * t.Npad + i), et[2]) : m;
       }
    } else {
       // ---- Depondt (depondt.f90) ----
       double sigma = 0.0;
       if (p.thermal) {
-         const double Dp = p.per_site ? (2.0 * lam * p.k_bolt) / (p.delta_t * p.gamma * p.mub) : p.u_Dp;
-         sigma = sqrt(Dp * p.temprescale * temp / m);
+         // sigma = sqrt(Dp temprescale T / m), evaluated as sqrt(Dp temprescale T) * m^-1/2
+         double sg = p.u_sig5;
+         if (per_site) sg = sqrt((2.0 * lam * p.k_bolt) / (p.delta_t * p.gamma * p.mub) * p.temprescale * temp);
+         sigma = sg * rsqrt_nr(m);
       }
       const double bl[3] = {b[0] + g[0] * sigma, b[1] + g[1] * sigma, b[2] + g[2] * sigma};
       // damping cross product uses the spin the field was evaluated with (old spin / predictor spin)
@@ -833,7 +858,7 @@ __device__ __forceinline__ SpinVec integrate_site(const Tables& t, const LlgPara
          bd[2] = 0.5 * bd[2] + 0.5 * b2[2 * (size_t)t.Npad];
          rodrigues(bd, e, rot, out);
          o.x = out[0]; o.y = out[1]; o.z = out[2];
-         o.m = p.mompar ? calcm(p.mompar, m, __ldg(p.mmom0 + (size_t)k * t.Npad + i), out[2]) : m;
+         o.m = mompar ? calcm(mompar, m, __ldg(p.mmom0 + (size_t)k * t.Npad + i), out[2]) : m;
       }
    }
    return o;

@@ -211,6 +211,10 @@ struct asd_engine {
    size_t h_red_n = 0;
    DevBuf<double> msum_part;            // per-tile sums of emomM left by the last corrector launch of asd_sd_steps
    bool msum_fresh = false;
+   // moment planes of the MM run kernels: emomM of cur / pred as [M][3][Npad]; mm_valid: mm_cur mirrors `cur` (every writer of
+   // `cur` other than the MM stage launches clears it, sd_steps rebuilds the planes when it is false)
+   DevBuf<double> mm_cur, mm_pred;
+   bool mm_valid = false;
    int msum_ntile = 0;
    DevBuf<double> io_e, io_eM, io_m;   // staging of asd_set_moments / asd_get_moments (kept between calls)
    DevBuf<unsigned int> acc;
@@ -311,7 +315,7 @@ static int build_tiles(asd_engine* e, Layout& L, int ts) {
 static int build_runs(asd_engine* e, Layout& L) {
    constexpr int R = 4;
    Tables& t = L.t;
-   t.runs = 0; t.urow = 0; t.utab = nullptr;
+   t.runs = 0; t.urow = 0; t.utab = nullptr; t.mm = 0;
    if (!t.staged || !L.reduced || !t.cpl_param || L.is_mc || !has_lattice(e)) return 0;
    if (t.z * R >= RUN_MAXPAIR) return 0;
    const int ngroup = (t.Nown + R * 32 - 1) / (R * 32);
@@ -320,7 +324,7 @@ static int build_runs(asd_engine* e, Layout& L) {
    cudaStream_t st = e->stream;
    int r;
    if ((r = L.d_gcount.alloc(ngroup))) return r;
-   run_union_kernel<R><<<ngroup, 32, 0, st>>>(t.Nown, L.Npad, t.z, t.nl16, t.meta, t.lsize, 0, 0, L.d_gcount.p, nullptr);
+   run_union_kernel<R><<<ngroup, 32, 0, st>>>(t.Nown, L.Npad, t.z, t.nl16, t.meta, t.lsize, 0, 0, L.d_gcount.p, nullptr, 24u);
    e->launches++;
    CU(cudaGetLastError());
    std::vector<int> cnt(ngroup);
@@ -340,10 +344,21 @@ static int build_runs(asd_engine* e, Layout& L) {
       mx = std::max(mx, c);
    }
    if (mx == 0 || mx > 255) return 0;
+   // MM instantiations of the run kernel (gather list staged from the moment planes with cp.async): 1024-slot tiles whose list fits
+   // the fixed plane stride, no slab (the halo push writes spins only), none of the XS cases (DM / BQ positions, short lists)
+   {
+      const char* menv = std::getenv("ASD_MM");
+      const bool xs = t.dm16 != nullptr || t.bq16 != nullptr || t.ucap <= 6 * 256;
+      // ... and only plain Heisenberg layouts: paired with the LEAN integrator loop the planes give 0.456 -> 0.429 ms per step at
+      // bcc 128^3, with the general loop 0.468 (measured, profiles/README: the general instantiation is at its register limit)
+      const bool plain = !e->have_aniso && t.zdm == 0 && t.zbq == 0 && !t.jtens;
+      t.mm = (!(menv && atoi(menv) == 0) && t.tile_slots == 1024 && t.ucap + 32 <= MM_PLANE && !e->slab.on && !xs && plain) ? 1 : 0;
+   }
+   const unsigned pos_scale = t.mm ? 8u : 24u;
    const int urow = 1 + mx + 1;   // header word + entries + one spare (zero) entry
    if ((r = L.d_utab.alloc((size_t)galloc * urow))) return r;
    CU(cudaMemsetAsync(L.d_utab.p, 0, (size_t)galloc * urow * sizeof(uint4), st));
-   run_union_kernel<R><<<ngroup, 32, 0, st>>>(t.Nown, L.Npad, t.z, t.nl16, t.meta, t.lsize, 1, urow, L.d_gcount.p, L.d_utab.p);
+   run_union_kernel<R><<<ngroup, 32, 0, st>>>(t.Nown, L.Npad, t.z, t.nl16, t.meta, t.lsize, 1, urow, L.d_gcount.p, L.d_utab.p, pos_scale);
    e->launches++;
    CU(cudaGetLastError());
    CU(cudaStreamSynchronize(st));
@@ -730,6 +745,8 @@ static int fill_llg(asd_engine* e, Layout& L, LlgParams& p, unsigned long long s
    p.mompar = e->mompar; p.mmom0 = L.d_mmom0.p;
    p.seed = e->seed; p.step = step;
    p.thermal = e->llg_thermal ? 1 : 0;
+   p.mm_cur = (L.t.runs && L.t.mm) ? e->mm_cur.p : nullptr;
+   p.mm_pred = (L.t.runs && L.t.mm) ? e->mm_pred.p : nullptr;
    {
       // same expressions, same order as the per-site branch of llg_stage_kernel (volatile: no host-side contraction)
       volatile double lam = p.lambda, one = 1.0;
@@ -751,6 +768,13 @@ static int fill_llg(asd_engine* e, Layout& L, LlgParams& p, unsigned long long s
       volatile double q0 = p.delta_t * p.gamma;
       volatile double q1 = q0 * p.mub;
       p.u_Dp = n1 / q1;
+      volatile double s0 = 2.0 * p.u_Dk;
+      volatile double s1 = s0 * p.temp;
+      volatile double s2 = s1 * p.temprescale;
+      p.u_sig1 = std::sqrt(s2);
+      volatile double r0 = p.u_Dp * p.temprescale;
+      volatile double r1 = r0 * p.temp;
+      p.u_sig5 = std::sqrt(r1);
    }
    return 0;
 }
@@ -763,6 +787,7 @@ static int fill_llg(asd_engine* e, Layout& L, LlgParams& p, unsigned long long s
 static int upload_state_from(asd_engine* e, Layout& L, const double* emom, const double* mmom, const double* mmom0) {
    const size_t NM = (size_t)e->N * e->M;
    e->msum_fresh = false;
+   e->mm_valid = false;
    int r;
    if ((r = e->io_e.alloc(3 * NM))) return r;
    if ((r = e->io_m.alloc(NM))) return r;
@@ -920,7 +945,8 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
    const bool pdl_s = pdl_all && !EDGE && !e->slab.on && big_grid;
    if (L.t.runs && !fr) {
       const int NW = L.t.tile_slots / 128;
-      const size_t smem = (size_t)((L.t.sm_dm + L.t.sm_bq + 1) & ~1) * sizeof(double) + (size_t)3 * (L.t.ucap + 32) * sizeof(double) +
+      const bool mm = L.t.mm && p.mm_cur != nullptr;
+      const size_t smem = (size_t)((L.t.sm_dm + L.t.sm_bq + 1) & ~1) * sizeof(double) + (size_t)3 * (mm ? MM_PLANE : (L.t.ucap + 32)) * sizeof(double) +
                           (size_t)NW * L.t.urow * sizeof(uint4);
       // the XS instantiation also carries the staging loop for short gather lists (asd_runs.cuh): layouts with few neighbours take it
       // whether or not they have DM / BQ tables (ASD_SHORT_STAGING=0: only layouts with such tables)
@@ -928,9 +954,9 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
       const bool xs = L.t.dm16 != nullptr || L.t.bq16 != nullptr || (short_env && L.t.ucap <= 6 * 256);
       static const bool pdl_env = !(std::getenv("ASD_PDL") && atoi(std::getenv("ASD_PDL")) == 0);
       const bool pdl = pdl_env && !EDGE && !e->slab.on && big_grid;
-#define ASD_LAUNCH_RUNS(NWV, XSV)                                                                                                  \
+#define ASD_LAUNCH_RUNS(NWV, XSV, LEANV, MMV)                                                                                                \
       do {                                                                                                                         \
-         allow_smem(llg_runs_kernel<SOLVER, STAGE, NWV, EDGE, MSUM, XSV>, smem);                                                   \
+         allow_smem(llg_runs_kernel<SOLVER, STAGE, NWV, EDGE, MSUM, XSV, LEANV, MMV>, smem);                                                   \
          if (pdl) {                                                                                                                \
             /* programmatic dependent launch: the CTAs of this stage become resident while the previous stage drains its last */  \
             /* wave, run the prologue that only touches tables and wait (griddepcontrol.wait) before the first spin is read */    \
@@ -941,14 +967,24 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                         \
             at[0].val.programmaticStreamSerializationAllowed = 1;                                                                  \
             cfg.attrs = at; cfg.numAttrs = 1;                                                                                      \
-            cudaLaunchKernelEx(&cfg, llg_runs_kernel<SOLVER, STAGE, NWV, EDGE, MSUM, XSV>, L.t, p, ep, tr, e->cur.p, e->pred.p,    \
+            cudaLaunchKernelEx(&cfg, llg_runs_kernel<SOLVER, STAGE, NWV, EDGE, MSUM, XSV, LEANV, MMV>, L.t, p, ep, tr, e->cur.p, e->pred.p,    \
                                e->b2eff.p);                                                                                        \
          } else                                                                                                                    \
-            llg_runs_kernel<SOLVER, STAGE, NWV, EDGE, MSUM, XSV><<<g, NWV * 32, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p); \
+            llg_runs_kernel<SOLVER, STAGE, NWV, EDGE, MSUM, XSV, LEANV, MMV><<<g, NWV * 32, smem, e->stream>>>(L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p); \
       } while (0)
-      if (NW == 8) { if (xs) ASD_LAUNCH_RUNS(8, true); else ASD_LAUNCH_RUNS(8, false); }
-      else if (NW == 4) ASD_LAUNCH_RUNS(4, false);
-      else ASD_LAUNCH_RUNS(2, false);
+      // plain Heisenberg system, uniform field and LLG parameters: the instantiation without the runtime checks of the general form
+      static const bool lean_env = !(std::getenv("ASD_LEAN") && atoi(std::getenv("ASD_LEAN")) == 0);
+      const bool lean = lean_env && !EDGE && !xs && NW == 8 && !p.per_site && p.mompar == 0 && L.t.btorque == nullptr && L.t.ext_uniform &&
+                        !L.t.do_aniso && L.t.zdm == 0 && L.t.zbq == 0 && !L.t.jtens;
+      if (NW == 8) {
+         if (xs) ASD_LAUNCH_RUNS(8, true, false, false);
+         else if (mm && lean) ASD_LAUNCH_RUNS(8, false, (!EDGE), (!EDGE));
+         else if (mm) ASD_LAUNCH_RUNS(8, false, false, (!EDGE));
+         else if (lean) ASD_LAUNCH_RUNS(8, false, (!EDGE), false);
+         else ASD_LAUNCH_RUNS(8, false, false, false);
+      }
+      else if (NW == 4) ASD_LAUNCH_RUNS(4, false, false, false);
+      else ASD_LAUNCH_RUNS(2, false, false, false);
 #undef ASD_LAUNCH_RUNS
    } else if (L.t.staged && !fr) {
       const size_t smem = L.smem_bytes + (size_t)3 * L.t.ucap * sizeof(double);
@@ -1095,12 +1131,44 @@ static int launch_resident(asd_engine* e, Layout& L, const LlgParams& p, const R
                     : launch_resident2<SOLVER, false>(e, t, p, rp, nsteps, first_step);
 }
 
+// moment planes of the MM run kernels: allocated on first use, rebuilt from `cur` whenever something else wrote the spins
+__global__ void moment_planes_kernel(size_t Npad, int M, const SpinVec* __restrict__ S, double* __restrict__ P) {
+   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const int k = blockIdx.y;
+   if (i < Npad) {
+      const SpinVec v = S[(size_t)k * Npad + i];
+      double* __restrict__ W = P + (size_t)k * 3 * Npad + i;
+      W[0] = v.x * v.m; W[Npad] = v.y * v.m; W[2 * Npad] = v.z * v.m;
+   }
+}
+
+static int mm_prepare(asd_engine* e, Layout& L) {
+   if (!(L.t.runs && L.t.mm) || !e->frozen.empty()) { e->mm_valid = false; return 0; }   // (fixed-moment runs take the direct kernel)
+   const size_t n = (size_t)3 * L.Npad * e->M;
+   int r;
+   if (e->mm_cur.n < n || e->mm_pred.n < n) {
+      if ((r = e->mm_cur.alloc(n))) return r;
+      if ((r = e->mm_pred.alloc(n))) return r;
+      CU(cudaMemsetAsync(e->mm_pred.p, 0, n * sizeof(double), e->stream));
+      e->mm_valid = false;
+   }
+   static const bool always = std::getenv("ASD_MM_ALWAYS") && atoi(std::getenv("ASD_MM_ALWAYS")) != 0;
+   if (!e->mm_valid || always) {
+      moment_planes_kernel<<<dim3((unsigned)((L.Npad + 255) / 256), e->M), 256, 0, e->stream>>>((size_t)L.Npad, e->M, e->cur.p, e->mm_cur.p);
+      e->launches++;
+      CU(cudaGetLastError());
+      e->mm_valid = true;
+   }
+   return 0;
+}
+
 static int sd_steps(asd_engine* e, long nsteps, long first_step) {
    int r = ensure_layout(e, 1);
    if (r) return r;
    Layout& L = e->sd;
    if (e->SDEalgh != 1 && e->SDEalgh != 5) return fail(-7, "SDEalgh %d is not on this path (1 = midpoint, 5 = Depondt)", e->SDEalgh);
    if (e->SDEalgh == 5 && e->b2eff.n < (size_t)3 * L.Npad * e->M) { if ((r = e->b2eff.alloc((size_t)3 * L.Npad * e->M))) return r; }
+   if ((r = mm_prepare(e, L))) return r;
    LlgParams p;
    if ((r = fill_llg(e, L, p, 0))) return r;
    if (e->slab.on && !e->slab.connected) return fail(-11, "slab: not connected to the ring neighbours");
@@ -1108,6 +1176,7 @@ static int sd_steps(asd_engine* e, long nsteps, long first_step) {
    ResidentPlan rp;
    if (nsteps > 0 && resident_applies(e, L, rp)) {
       e->msum_fresh = false;
+      e->mm_valid = false;
       const int rr = e->SDEalgh == 1 ? launch_resident<1>(e, L, p, rp, nsteps, first_step) : launch_resident<5>(e, L, p, rp, nsteps, first_step);
       if (rr != RESIDENT_UNAVAILABLE) return rr;
    }
@@ -1251,6 +1320,7 @@ static int mc_sweeps(asd_engine* e, char mode, long nsweeps, long first_sweep, d
    // expression in the Fortran, i.e. the single-precision 0.08; ignores temprescale like the reference
    p.delta = (double)(2.0f / 25.0f) * std::pow(e->k_bolt * temperature / e->mub, 0.20);
    e->msum_fresh = false;
+   e->mm_valid = false;
    if (mc_block_candidate(e)) {
       int rb = mc_block_prepare(e);
       if (rb) return rb;
@@ -1594,6 +1664,7 @@ int asd_get_moments(asd_engine* e, double* emom, double* emomM, double* mmom) {
 int asd_commit(asd_engine* e) {
    if (e->N == 0) return fail(-2, "asd_set_system must be called first");
    CU(cudaSetDevice(e->device));
+   e->mm_valid = false;
    if (e->committed && !e->slab.on) { int r = stash_state_to_host(e); if (r) return r; }
    if (!e->lattice_built) {
       if (!e->ex.present()) return fail(-2, "no exchange table (asd_set_exchange / asd_build_lattice_table)");
@@ -2088,7 +2159,7 @@ int asd_layout_info(asd_engine* e, int* info5 /* 6 ints */) {
    const Tables& t = e->sd.t;
    info5[0] = t.staged; info5[1] = t.runs; info5[2] = t.ucap; info5[3] = t.runs ? t.urow - 2 : 0;   // urow = header + entries + spare
    info5[4] = t.tile_slots;
-   info5[5] = (t.runs && (t.dm16 != nullptr || t.bq16 != nullptr)) ? 1 : 0;
+   info5[5] = ((t.runs && (t.dm16 != nullptr || t.bq16 != nullptr)) ? 1 : 0) | ((t.runs && t.mm) ? 2 : 0);
    return 0;
 }
 

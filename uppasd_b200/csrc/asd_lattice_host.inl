@@ -309,6 +309,7 @@ int asd_init_moments_tilted(asd_engine* e, double amplitude, int NA, const doubl
    CU(cudaStreamSynchronize(e->stream));
    e->state_layout = 1;
    e->msum_fresh = false;
+   e->mm_valid = false;
    if ((r = slab_push_state(e))) return r;
    e->h_emom.clear(); e->h_mmom.clear();
    if (e->mompar != 0) return fail(-1, "mompar != 0 needs asd_set_moments (mmom0)");

@@ -33,18 +33,22 @@ namespace asd {
 #ifndef ASD_INT_UNROLL
 #define ASD_INT_UNROLL 1
 #endif
+#ifndef ASD_ABL
+#define ASD_ABL 0      // development only: ablation bits (1: no integrator math, 2: no union walk, 4: no staging) -- results are WRONG
+#endif
 constexpr int INT_UNROLL = ASD_INT_UNROLL;   // atoms of a thread whose integrators are interleaved (1: one rolled loop)
 constexpr int RUN_UNROLL = ASD_RUN_UNROLL;   // entries of the union walk in flight per mask loop
 constexpr int RUN_MAXPAIR = 256;   // R * z must stay below this (j and the entry counts are bytes)
 
 // One warp per group of R runs.  pass 0: gcount[g] = number of union entries, or -1 if the group is not regular;
 // pass 1: writes the row  utab[g][rowlen] (16-byte words):  word 0 = end[m], m = 0..15, as bytes (one past the last entry
-// whose mask is <= m), then entries {x = 24 * base (byte offset of the record in the staged list), y / z = byte offsets
+// whose mask is <= m), then entries {x = pos_scale * base (byte offset of the record in the staged list: 24 for the list of
+// 24-byte records, 8 for the component planes of the MM kernels), y / z = byte offsets
 // of the couplings of runs 0..3 in Tables::cpl_small, 16 bits each}; at least one spare (zero) entry ends the row.
 template <int R>
 __global__ void __launch_bounds__(32)
 run_union_kernel(int Nown, int Npad, int z, const uint4* __restrict__ nl16, const int2* __restrict__ meta, const int* __restrict__ lsize,
-                 int pass, int rowlen, int* __restrict__ gcount, uint4* __restrict__ utab) {
+                 int pass, int rowlen, int* __restrict__ gcount, uint4* __restrict__ utab, unsigned pos_scale) {
    __shared__ unsigned short base[RUN_MAXPAIR], rj[RUN_MAXPAIR];
    __shared__ unsigned int lkey[RUN_MAXPAIR];
    __shared__ uint4 lent[RUN_MAXPAIR];
@@ -99,7 +103,7 @@ run_union_kernel(int Nown, int Npad, int z, const uint4* __restrict__ nl16, cons
                }
             const int at = atomicAdd(&nlead, 1);
             lkey[at] = (mask << 8) | (rj[p] & 255u);   // pair p is the first use: lowest run, its j
-            lent[at] = make_uint4((unsigned)base[p] * 24u, off[0] | (off[1] << 16), off[2] | (off[3] << 16), 0u);
+            lent[at] = make_uint4((unsigned)base[p] * pos_scale, off[0] | (off[1] << 16), off[2] | (off[3] << 16), 0u);
          }
       }
    }
@@ -125,11 +129,13 @@ run_union_kernel(int Nown, int Npad, int z, const uint4* __restrict__ nl16, cons
 }
 
 // inner loops of the union walk, one per mask value (ascending, like the entries)
-template <int R, int MASK>
+// PL: distance in doubles between the components of one staged moment (1: 24-byte records, MM_PLANE: component planes)
+constexpr int MM_PLANE = 3232;     // positions per component plane of the MM kernels (layouts with ucap + 32 <= MM_PLANE)
+template <int R, int MASK, int PL = 1>
 struct RunLoop {
    static __device__ __forceinline__ void run(const Tables& t, const uint4* __restrict__ ent, const unsigned char* __restrict__ endb,
                                               const double* __restrict__ srec, double (&f)[R][3]) {
-      RunLoop<R, MASK - 1>::run(t, ent, endb, srec, f);
+      RunLoop<R, MASK - 1, PL>::run(t, ent, endb, srec, f);
       const int e0 = endb[MASK - 1], e1 = endb[MASK];
       uint4 nx = ent[e0];                   // one entry ahead: its decode overlaps the loads of the current one
 #pragma unroll (RUN_UNROLL)
@@ -137,7 +143,7 @@ struct RunLoop {
          const uint4 en = nx;
          nx = ent[e + 1];                   // rows carry one spare entry
          const double* __restrict__ m = reinterpret_cast<const double*>(reinterpret_cast<const char*>(srec) + en.x);
-         const double mx = m[0], my = m[1], mz = m[2];
+         const double mx = m[0], my = m[PL], mz = m[2 * PL];
          const char* __restrict__ cb = reinterpret_cast<const char*>(t.cpl_small);
 #pragma unroll
          for (int r = 0; r < R; r++)
@@ -152,8 +158,8 @@ struct RunLoop {
       }
    }
 };
-template <int R>
-struct RunLoop<R, 0> {
+template <int R, int PL>
+struct RunLoop<R, 0, PL> {
    static __device__ __forceinline__ void run(const Tables&, const uint4*, const unsigned char*, const double*, double (&)[R][3]) {}
 };
 
@@ -161,7 +167,16 @@ struct RunLoop<R, 0> {
 // 1024 slots = 1, 2, 4 bricks of a super-brick): NW warps, thread (warp w, lane l) owns the atoms
 // tile*TS + (w*4 + r)*32 + l, r = 0..3.  Same contract as llg_stage_kernel (asd_device.cuh).
 // XS: the layout's DM / BQ neighbours are in the gather list too (dm16 / bq16) and are read from shared memory.
-template <int SOLVER, int STAGE, int NW, bool EDGE, bool MSUM, bool XS>
+// LEAN: plain Heisenberg system with a uniform field and uniform LLG parameters (the engine checks: no DM / BQ / anisotropy /
+// tensor couplings, uniform external field, uniform damping / g factor / temperature, no torque field, mompar 0) -- the integrator
+// loop then carries none of the runtime checks and predicated loads of the general form (270 -> 150 instructions per atom-stage).
+// MM: the gather list is staged from the MOMENT PLANES -- emomM = e * m of every slot as three component planes [M][3][Npad]
+// (p.mm_cur / p.mm_pred), which every MM launch keeps up to date next to the spins it writes -- with 8-byte asynchronous copies
+// (cp.async) straight into component planes in shared memory: no registers, no conversion, all copies of a thread in flight at
+// once, 24 instead of 32 bytes per gathered spin.  (Ablation, profiles/README: staging through registers cost 0.10 of the 0.47 ms
+// step and did not overlap with anything.)  Layouts with ucap + 32 <= MM_PLANE, no slab, no XS tables; the union rows carry
+// 8 * base.
+template <int SOLVER, int STAGE, int NW, bool EDGE, bool MSUM, bool XS, bool LEAN = false, bool MM = false>
 __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : (NW == 4) ? 4 : 6)
 llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgParams p, const __grid_constant__ EdgeParams ep,
                 const TileRange tr, SpinVec* __restrict__ cur, SpinVec* __restrict__ pred, double* __restrict__ b2eff) {
@@ -199,7 +214,7 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
    const int* __restrict__ ul = t.ulist + (size_t)tile * t.ucap;
    const int ncpl = t.sm_dm + t.sm_bq;                       // exchange couplings ride in the constant bank
    double* __restrict__ s3 = sm + ((ncpl + 1) & ~1);          // keeps the union rows 16-byte aligned
-   uint4* __restrict__ rows = reinterpret_cast<uint4*>(s3 + 3 * (t.ucap + 32));
+   uint4* __restrict__ rows = reinterpret_cast<uint4*>(s3 + 3 * (MM ? MM_PLANE : (t.ucap + 32)));
    const int nrow = NW * t.urow;
    const uint4* __restrict__ rsrc = t.utab + (size_t)tile * nrow;
    // union rows: asynchronous 16-byte copies straight into shared memory (no registers held while they fly)
@@ -214,9 +229,14 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
    asm volatile("griddepcontrol.wait;" ::: "memory");
    // L2 prefetch of what the CTA one wave later needs first: its own spins, gather list and union rows
-   if (t.pf_tiles > 0 && threadIdx.x < 3) {
+   if (t.pf_tiles > 0 && threadIdx.x < (MM ? 6 : 3)) {
       const size_t nt = (size_t)tile + t.pf_tiles;
       if (nt * TS < (size_t)t.Nown) {
+         if (MM && threadIdx.x >= 3) {
+            // the tile's own part of the moment planes (a third of its gather list)
+            const double* __restrict__ G = ((STAGE == 1) ? p.mm_cur : p.mm_pred) + ((size_t)k * 3 + (threadIdx.x - 3)) * t.Npad + nt * TS;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(G), "r"((unsigned)(TS * 8)) : "memory");
+         }
          if (threadIdx.x == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(S + nt * TS), "r"((unsigned)(TS * 32)) : "memory");
          if (threadIdx.x == 1) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(t.ulist + nt * t.ucap), "r"((unsigned)t.ucap * 4u) : "memory");
          if (threadIdx.x == 2) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(t.utab + nt * nrow), "r"((unsigned)nrow * 16u) : "memory");
@@ -228,7 +248,29 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
    // short gather lists (layouts with few neighbours: DM systems, 2-D lattices): rounds of 2 x 3 spins per thread -- the long form
    // below executes its 14 predicated load / convert / store slots whatever the list length (ncu r2s: 670 of 3770 instructions of
    // config 4).  Only in the XS kernels, so that the code of the headline kernel is not touched.
-   if (XS && t.ucap <= 6 * NT) {
+   if (MM) {
+      const double* __restrict__ G = ((STAGE == 1) ? p.mm_cur : p.mm_pred) + (size_t)k * 3 * t.Npad;
+      constexpr int MB = 14;    // list positions per thread and round: every index first, then 3 copies per position
+      for (int u0 = threadIdx.x; u0 < cnt; u0 += MB * NT) {
+         int sl[MB];
+#pragma unroll
+         for (int a = 0; a < MB; a++) sl[a] = (u0 + a * NT < cnt) ? __ldg(ul + u0 + a * NT) : -1;
+#pragma unroll
+         for (int a = 0; a < MB; a++)
+            if (sl[a] >= 0) {
+               const unsigned dst = (unsigned)__cvta_generic_to_shared(s3 + u0 + a * NT);
+               const double* __restrict__ g = G + sl[a];
+               asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(g) : "memory");
+               asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * MM_PLANE), "l"(g + t.Npad) : "memory");
+               asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 16u * MM_PLANE), "l"(g + 2 * (size_t)t.Npad) : "memory");
+            }
+      }
+      if (p.thermal) {
+#pragma unroll
+         for (int r = 0; r < R; r++)
+            gauss3f_raw(p.seed, (uint32_t)mt[r].y + t.atom_offset, (uint32_t)k + t.ens_offset, p.step, 0u, gn[r][0], gn[r][1], gn[r][2]);
+      }
+   } else if (XS && t.ucap <= 6 * NT) {
       constexpr int SS = 3;
       for (int u0 = threadIdx.x; u0 < cnt; u0 += 2 * SS * NT) {
          int sl[2 * SS];
@@ -254,7 +296,7 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
    } else
    // gather list -> shared memory in rounds of 2 x SB spins per thread: the indices of both halves are fetched first
    // (one round trip), the spins of the second half fly while the first half is converted and stored
-   for (int u0 = threadIdx.x; u0 < cnt; u0 += 2 * SB * NT) {
+   for (int u0 = threadIdx.x; u0 < ((ASD_ABL & 4) ? 0 : cnt); u0 += 2 * SB * NT) {
       int sl[2 * SB];
 #pragma unroll
       for (int a = 0; a < 2 * SB; a++) sl[a] = (u0 + a * NT < cnt) ? __ldg(ul + u0 + a * NT) : 0;
@@ -280,7 +322,7 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
          }
       }
    }
-   asm volatile("cp.async.wait_group 0;" ::: "memory");
+   asm volatile("cp.async.wait_all;" ::: "memory");
    stage_couplings(t, sm, smc, smd, smb);   // ends with __syncthreads() when it stages anything
    if (ncpl == 0) __syncthreads();
    // ---- Heisenberg sums of the 4 atoms of this thread: every distinct neighbour run read once ----
@@ -290,9 +332,10 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
    int ih = -1;
 #pragma unroll
    for (int r = 0; r < R; r++) ih = max(ih, __shfl_sync(0xffffffffu, mt[r].y >= 0 ? mt[r].x : -1, 0));
-   if (ih >= 0) {
+   if (ih >= 0 && !(ASD_ABL & 2)) {
       const uint4* __restrict__ row = rows + wp * t.urow;
-      RunLoop<R, (1 << R) - 1>::run(t, row + 1, reinterpret_cast<const unsigned char*>(row), s3 + 3 * ln, f);
+      if (MM) RunLoop<R, (1 << R) - 1, MM_PLANE>::run(t, row + 1, reinterpret_cast<const unsigned char*>(row), s3 + ln, f);
+      else RunLoop<R, (1 << R) - 1>::run(t, row + 1, reinterpret_cast<const unsigned char*>(row), s3 + 3 * ln, f);
    }
    // ---- integrators: one rolled loop over the 4 atoms (the register arrays rotate, so the body exists once); the
    //      own spin (and the old spin of a corrector) of the next atom is loaded one iteration ahead ----
@@ -309,16 +352,30 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
       SpinVec old_n;
       if (STAGE == 2) old_n = curk[inext];
       if (io >= 0) {
-         double bs[3] = {f[0][0], f[0][1], f[0][2]}, bq[3];
-         site_field<true, false, ASD_CHUNK, XS>(t, S, i, ih, own, smc, smd, smb, bs, bq, s3, (XS && t.dm16 != nullptr) ? &dmw[0] : nullptr);
+         double bs[3] = {f[0][0], f[0][1], f[0][2]}, bq[3] = {0.0, 0.0, 0.0};
          double h[3];
-         ext_field(t, i, k, h);
+         if (LEAN) { h[0] = t.hext[0]; h[1] = t.hext[1]; h[2] = t.hext[2]; }
+         else {
+            site_field<true, false, ASD_CHUNK, XS>(t, S, i, ih, own, smc, smd, smb, bs, bq, s3, (XS && t.dm16 != nullptr) ? &dmw[0] : nullptr);
+            ext_field(t, i, k, h);
+         }
 #ifndef ASD_NO_TFIELD
          h[0] += p.tf[0]; h[1] += p.tf[1]; h[2] += p.tf[2];
 #endif
-         const double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
-         const SpinVec o = integrate_site<SOLVER, STAGE>(t, p, i, k, io, b, own, (STAGE == 1) ? own : old, b2eff, gn[0]);
+         double b[3];
+         if (LEAN) { b[0] = bs[0] + h[0]; b[1] = bs[1] + h[1]; b[2] = bs[2] + h[2]; }
+         else { b[0] = bs[0] + (bq[0] + h[0]); b[1] = bs[1] + (bq[1] + h[1]); b[2] = bs[2] + (bq[2] + h[2]); }
+#if (ASD_ABL & 1)
+         SpinVec o = (STAGE == 1) ? own : old;
+         o.x += 1e-300 * (b[0] + gn[0][0]); o.y += 1e-300 * (b[1] + gn[0][1]); o.z += 1e-300 * (b[2] + gn[0][2]);
+#else
+         const SpinVec o = integrate_site<SOLVER, STAGE, false, LEAN>(t, p, i, k, io, b, own, (STAGE == 1) ? own : old, b2eff, gn[0]);
+#endif
          if (STAGE == 1) predk[i] = o; else curk[i] = o;
+         if (MM) {
+            double* __restrict__ W = ((STAGE == 1) ? p.mm_pred : p.mm_cur) + (size_t)k * 3 * t.Npad + i;
+            W[0] = o.x * o.m; W[t.Npad] = o.y * o.m; W[2 * (size_t)t.Npad] = o.z * o.m;
+         }
          if (MSUM) { mnew[0] += o.x * o.m; mnew[1] += o.y * o.m; mnew[2] += o.z * o.m; }
          if (EDGE) {
             const int lo = __ldg(ep.hdst_lo + i), hi = __ldg(ep.hdst_hi + i);

@@ -242,10 +242,11 @@ class Engine:
         return tot.value
 
     def layout_info(self):
-        """dict(staged, runs, ucap, union, tile_slots): the field path of the LLG stage kernels"""
+        """dict(staged, runs, ucap, union, tile_slots, extra_staged, planes): the field path of the LLG stage kernels"""
         info = (C.c_int * 6)()
         self._chk(self.lib.asd_layout_info(self.h, info))
-        return dict(staged=info[0], runs=info[1], ucap=info[2], union=info[3], tile_slots=info[4], extra_staged=info[5])
+        return dict(staged=info[0], runs=info[1], ucap=info[2], union=info[3], tile_slots=info[4], extra_staged=info[5] & 1,
+                    planes=(info[5] >> 1) & 1)
 
     def launch_count(self):
         return self.lib.asd_launch_count(self.h)
