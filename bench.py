@@ -539,7 +539,7 @@ def main():
         ach = b2 * n / t2 / 1e9
         lay = e.layout_info()
         if lay['runs']:
-            kname = 'llg_runs_kernel<solver=%d,stage=2,tile=%d>' % (a.solver, lay['tile_slots'])
+            kname = 'llg_runs_kernel<solver=%d,stage=2,tile=%d%s>' % (a.solver, lay['tile_slots'], ',planes' if lay.get('planes') else '')
             tables = '%.0f MB of gather lists + run-compressed tables' % ((4.0 * lay['ucap'] + 16.0 * (lay['union'] + 2) * lay['tile_slots'] / 128) / lay['tile_slots'] * n / 1e6 + 8.0 * n / 1e6)
         else:
             kname = 'llg_stage_kernel<solver=%d,stage=2,%s,%s>' % (a.solver, 'full' if a.full_ham else 'reduced', 'staged' if lay['staged'] else 'direct')
@@ -552,7 +552,8 @@ def main():
             'scaling': 'strong' if slab else 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': workload, 'spins_per_gpu': n, 'ensembles': 1 if slab else world, 'parallelism': par,
                        'field_path': lay,
-                       'l2_policy': 'inputs larger than L2 (%s + spins %.0f MB per GPU vs 126 MB L2)' % (tables, 64.0 * n / 1e6)},
+                       'l2_policy': 'inputs larger than L2 (%s + spins %s%.0f MB per GPU vs 126 MB L2)'
+                                    % (tables, 'and moment planes ' if lay.get('planes') else '', (112.0 if lay.get('planes') else 64.0) * n / 1e6)},
             'clocks': sampler.summary(),
             'e2e': {'value': e2e, 'unit': 'atom-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'steps': k2, 'note': 'asd_set_moments from pinned host memory (H2D of emom + mmom) + asd_sd_run(K, sample sum M '

@@ -17,7 +17,7 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS):
         return OUT
     flags = [f for f in FLAGS if f != '--use_fast_math=false']
-    for k in ('ASD_MINB', 'ASD_CHUNK', 'ASD_MINB_STAGED', 'ASD_NPF', 'ASD_MC_MINB', 'ASD_MC_CHUNK', 'ASD_RUN_UNROLL', 'ASD_MC_PROF', 'ASD_INT_UNROLL', 'ASD_NO_TFIELD', 'ASD_ABL'):
+    for k in ('ASD_MINB', 'ASD_CHUNK', 'ASD_MINB_STAGED', 'ASD_NPF', 'ASD_MC_MINB', 'ASD_MC_CHUNK', 'ASD_RUN_UNROLL', 'ASD_MC_PROF', 'ASD_INT_UNROLL', 'ASD_NO_TFIELD', 'ASD_ABL', 'ASD_NO_OWNPF', 'ASD_WALK_U', 'ASD_WALK_X'):
         if os.environ.get(k):
             flags.append('-D%s=%s' % (k, os.environ[k]))
     cmd = [NVCC] + flags + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT, SRC]

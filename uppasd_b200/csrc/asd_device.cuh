@@ -96,6 +96,7 @@ struct Tables {
    int runs;              // 0: off, else 4: the LLG stage kernels use llg_runs_kernel (4 x-runs per warp)
    int urow;              // row stride of utab in 16-byte words
    const uint4* __restrict__ utab;    // [groups][urow]
+   int union_max;   // largest number of distinct neighbour runs of a group (asd_layout_info)
    int mm;          // 1: the union rows carry 8 * base and the run kernels stage from the moment planes (MM instantiations)
    int pf_tiles;    // L2 bulk-prefetch distance in 256-atom tiles (0 = off)
    int cpl_param;   // 1: reduced exchange couplings live in cpl_small (kernel parameter = constant bank)

@@ -324,26 +324,6 @@ static int build_runs(asd_engine* e, Layout& L) {
    cudaStream_t st = e->stream;
    int r;
    if ((r = L.d_gcount.alloc(ngroup))) return r;
-   run_union_kernel<R><<<ngroup, 32, 0, st>>>(t.Nown, L.Npad, t.z, t.nl16, t.meta, t.lsize, 0, 0, L.d_gcount.p, nullptr, 24u);
-   e->launches++;
-   CU(cudaGetLastError());
-   std::vector<int> cnt(ngroup);
-   CU(cudaMemcpyAsync(cnt.data(), L.d_gcount.p, (size_t)ngroup * sizeof(int), cudaMemcpyDeviceToHost, st));
-   CU(cudaStreamSynchronize(st));
-   int mx = 0;
-   for (int c : cnt) {
-      if (c < 0) {
-         if (std::getenv("ASD_DEBUG")) {
-            int hist[6] = {0, 0, 0, 0, 0, 0};
-            for (int q : cnt) if (q < 0 && q >= -5) hist[-q]++;
-            fprintf(stderr, "[asd] run table refused: %d groups; not a lane prefix %d, mixed rows %d, too many pairs %d, split neighbour run %d, duplicate neighbour %d\n",
-                    ngroup, hist[1], hist[2], hist[3], hist[4], hist[5]);
-         }
-         return 0;
-      }
-      mx = std::max(mx, c);
-   }
-   if (mx == 0 || mx > 255) return 0;
    // MM instantiations of the run kernel (gather list staged from the moment planes with cp.async): 1024-slot tiles whose list fits
    // the fixed plane stride, no slab (the halo push writes spins only), none of the XS cases (DM / BQ positions, short lists)
    {
@@ -352,16 +332,41 @@ static int build_runs(asd_engine* e, Layout& L) {
       // ... and only plain Heisenberg layouts: paired with the LEAN integrator loop the planes give 0.456 -> 0.429 ms per step at
       // bcc 128^3, with the general loop 0.468 (measured, profiles/README: the general instantiation is at its register limit)
       const bool plain = !e->have_aniso && t.zdm == 0 && t.zbq == 0 && !t.jtens;
-      t.mm = (!(menv && atoi(menv) == 0) && t.tile_slots == 1024 && t.ucap + 32 <= MM_PLANE && !e->slab.on && !xs && plain) ? 1 : 0;
+      t.mm = (!(menv && atoi(menv) == 0) && t.tile_slots == 1024 && t.ucap + 32 <= MM_PLANE - 32 && !e->slab.on && !xs && plain) ? 1 : 0;
    }
    const unsigned pos_scale = t.mm ? 8u : 24u;
-   const int urow = 1 + mx + 1;   // header word + entries + one spare (zero) entry
+   const int pad = t.mm ? WALK_U : 1;                       // union rows of MM layouts: mask classes padded to the walk's unroll
+   const unsigned null_pos = (unsigned)(MM_PLANE - 32);     // the zero moment the MM kernel keeps for the null entries
+   run_union_kernel<R><<<ngroup, 32, 0, st>>>(t.Nown, L.Npad, t.z, t.nl16, t.meta, t.lsize, 0, 0, L.d_gcount.p, nullptr, pos_scale, pad, null_pos);
+   e->launches++;
+   CU(cudaGetLastError());
+   std::vector<int> cnt(ngroup);
+   CU(cudaMemcpyAsync(cnt.data(), L.d_gcount.p, (size_t)ngroup * sizeof(int), cudaMemcpyDeviceToHost, st));
+   CU(cudaStreamSynchronize(st));
+   int mx = 0, mxu = 0;
+   for (int c : cnt) {
+      if (c < 0) {
+         if (std::getenv("ASD_DEBUG")) {
+            int hist[6] = {0, 0, 0, 0, 0, 0};
+            for (int q : cnt) if (q < 0 && q >= -5) hist[-q]++;
+            fprintf(stderr, "[asd] run table refused: %d groups; not a lane prefix %d, mixed rows %d, too many pairs %d, split neighbour run %d, duplicate neighbour %d\n",
+                    ngroup, hist[1], hist[2], hist[3], hist[4], hist[5]);
+         }
+         t.mm = 0;
+         return 0;
+      }
+      mx = std::max(mx, c >> 10);      // entries with the padding of the mask classes
+      mxu = std::max(mxu, c & 1023);   // distinct neighbour runs
+   }
+   if (mx == 0 || mx > 255) { t.mm = 0; return 0; }
+   const int urow = 1 + mx + pad;   // header word + entries + `pad` spare (zero) entries
    if ((r = L.d_utab.alloc((size_t)galloc * urow))) return r;
    CU(cudaMemsetAsync(L.d_utab.p, 0, (size_t)galloc * urow * sizeof(uint4), st));
-   run_union_kernel<R><<<ngroup, 32, 0, st>>>(t.Nown, L.Npad, t.z, t.nl16, t.meta, t.lsize, 1, urow, L.d_gcount.p, L.d_utab.p, pos_scale);
+   run_union_kernel<R><<<ngroup, 32, 0, st>>>(t.Nown, L.Npad, t.z, t.nl16, t.meta, t.lsize, 1, urow, L.d_gcount.p, L.d_utab.p, pos_scale, pad, null_pos);
    e->launches++;
    CU(cudaGetLastError());
    CU(cudaStreamSynchronize(st));
+   t.union_max = mxu;
    t.runs = R; t.urow = urow; t.utab = L.d_utab.p;
    return 0;
 }
@@ -974,13 +979,14 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
       } while (0)
       // plain Heisenberg system, uniform field and LLG parameters: the instantiation without the runtime checks of the general form
       static const bool lean_env = !(std::getenv("ASD_LEAN") && atoi(std::getenv("ASD_LEAN")) == 0);
-      const bool lean = lean_env && !EDGE && !xs && NW == 8 && !p.per_site && p.mompar == 0 && L.t.btorque == nullptr && L.t.ext_uniform &&
+      // (only together with the moment planes: without them the LEAN loop measured SLOWER than the general one, 0.487 against
+      // 0.456 ms per step -- ptxas then issues the first spin loads of the staging loop after all fourteen index loads)
+      const bool lean = lean_env && mm && !EDGE && !xs && NW == 8 && !p.per_site && p.mompar == 0 && L.t.btorque == nullptr && L.t.ext_uniform &&
                         !L.t.do_aniso && L.t.zdm == 0 && L.t.zbq == 0 && !L.t.jtens;
       if (NW == 8) {
          if (xs) ASD_LAUNCH_RUNS(8, true, false, false);
          else if (mm && lean) ASD_LAUNCH_RUNS(8, false, (!EDGE), (!EDGE));
          else if (mm) ASD_LAUNCH_RUNS(8, false, false, (!EDGE));
-         else if (lean) ASD_LAUNCH_RUNS(8, false, (!EDGE), false);
          else ASD_LAUNCH_RUNS(8, false, false, false);
       }
       else if (NW == 4) ASD_LAUNCH_RUNS(4, false, false, false);
@@ -2157,7 +2163,7 @@ int asd_slab_status(asd_engine* e, unsigned long long* epoch, int* error_flag) {
 int asd_layout_info(asd_engine* e, int* info5 /* 6 ints */) {
    if (!e->committed) return fail(-2, "asd_commit has not been called");
    const Tables& t = e->sd.t;
-   info5[0] = t.staged; info5[1] = t.runs; info5[2] = t.ucap; info5[3] = t.runs ? t.urow - 2 : 0;   // urow = header + entries + spare
+   info5[0] = t.staged; info5[1] = t.runs; info5[2] = t.ucap; info5[3] = t.runs ? t.union_max : 0;
    info5[4] = t.tile_slots;
    info5[5] = ((t.runs && (t.dm16 != nullptr || t.bq16 != nullptr)) ? 1 : 0) | ((t.runs && t.mm) ? 2 : 0);
    return 0;

@@ -36,6 +36,15 @@ namespace asd {
 #ifndef ASD_ABL
 #define ASD_ABL 0      // development only: ablation bits (1: no integrator math, 2: no union walk, 4: no staging) -- results are WRONG
 #endif
+#ifndef ASD_WALK_U
+#define ASD_WALK_U 2
+#endif
+// MM layouts: every mask class of a union row is padded with null entries (zero moment) to a multiple of WALK_U entries, and the
+// walk runs WALK_U entries per iteration with no remainder loop (1: no padding, the loop form of the other layouts)
+constexpr int WALK_U = ASD_WALK_U;
+#ifndef ASD_WALK_X
+#define ASD_WALK_X 1
+#endif
 constexpr int INT_UNROLL = ASD_INT_UNROLL;   // atoms of a thread whose integrators are interleaved (1: one rolled loop)
 constexpr int RUN_UNROLL = ASD_RUN_UNROLL;   // entries of the union walk in flight per mask loop
 constexpr int RUN_MAXPAIR = 256;   // R * z must stay below this (j and the entry counts are bytes)
@@ -48,7 +57,10 @@ constexpr int RUN_MAXPAIR = 256;   // R * z must stay below this (j and the entr
 template <int R>
 __global__ void __launch_bounds__(32)
 run_union_kernel(int Nown, int Npad, int z, const uint4* __restrict__ nl16, const int2* __restrict__ meta, const int* __restrict__ lsize,
-                 int pass, int rowlen, int* __restrict__ gcount, uint4* __restrict__ utab, unsigned pos_scale) {
+                 int pass, int rowlen, int* __restrict__ gcount, uint4* __restrict__ utab, unsigned pos_scale, int pad, unsigned null_pos) {
+   // pad > 1: every mask class is filled up to a multiple of `pad` entries with null entries {pos_scale * null_pos, 0, 0} (the
+   // kernel keeps a zero moment there); pass 0 then reports (padded entries << 10) | entries
+   __shared__ int pstart[17], pcnt[16];
    __shared__ unsigned short base[RUN_MAXPAIR], rj[RUN_MAXPAIR];
    __shared__ unsigned int lkey[RUN_MAXPAIR];
    __shared__ uint4 lent[RUN_MAXPAIR];
@@ -110,56 +122,99 @@ run_union_kernel(int Nown, int Npad, int z, const uint4* __restrict__ nl16, cons
    __syncwarp();
    const int nl = nlead;
    if (dup) { ok = false; if (!why) why = -5; }
+   if (lane < 16) {
+      int c = 0;
+      for (int q = 0; q < nl; q++) c += (int)(lkey[q] >> 8) == lane;
+      pcnt[lane] = c;
+   }
+   __syncwarp();
+   if (lane == 0) {
+      pstart[0] = 0;
+      for (int m = 0; m < 16; m++) pstart[m + 1] = pstart[m] + (pcnt[m] + pad - 1) / pad * pad;
+   }
+   __syncwarp();
    if (pass == 0) {
-      if (lane == 0) gcount[g] = ok ? nl : why;
+      if (lane == 0) gcount[g] = ok ? ((pstart[16] << 10) | nl) : why;
       return;
    }
    if (!ok) return;
    uint4* __restrict__ row = utab + (size_t)g * rowlen;
    for (int l = lane; l < nl; l += 32) {
+      const unsigned ml = lkey[l] >> 8;
       int rank = 0;
-      for (int q = 0; q < nl; q++) rank += lkey[q] < lkey[l];
-      row[1 + rank] = lent[l];
+      for (int q = 0; q < nl; q++) rank += (lkey[q] >> 8) == ml && lkey[q] < lkey[l];
+      row[1 + pstart[ml] + rank] = lent[l];
    }
    if (lane < 16) {
-      int c = 0;
-      for (int q = 0; q < nl; q++) c += (int)(lkey[q] >> 8) <= lane;
-      reinterpret_cast<unsigned char*>(row)[lane] = (unsigned char)c;
+      for (int q = pstart[lane] + pcnt[lane]; q < pstart[lane + 1]; q++) row[1 + q] = make_uint4(null_pos * pos_scale, 0u, 0u, 0u);
+      reinterpret_cast<unsigned char*>(row)[lane] = (unsigned char)pstart[lane + 1];
    }
 }
 
 // inner loops of the union walk, one per mask value (ascending, like the entries)
 // PL: distance in doubles between the components of one staged moment (1: 24-byte records, MM_PLANE: component planes)
 constexpr int MM_PLANE = 3232;     // positions per component plane of the MM kernels (layouts with ucap + 32 <= MM_PLANE)
-template <int R, int MASK, int PL = 1>
+template <int R, int MASK, int PL = 1, int U = 1>
 struct RunLoop {
+   static __device__ __forceinline__ void use(const Tables& t, const uint4& en, const double* __restrict__ srec, double (&f)[R][3]) {
+      const double* __restrict__ m = reinterpret_cast<const double*>(reinterpret_cast<const char*>(srec) + en.x);
+      const double mx = m[0], my = m[PL], mz = m[2 * PL];
+      const char* __restrict__ cb = reinterpret_cast<const char*>(t.cpl_small);
+#pragma unroll
+      for (int r = 0; r < R; r++)
+         if (MASK & (1 << r)) {
+            const unsigned w = (r < 2) ? en.y : en.z;
+            const unsigned off = (r & 1) ? (w >> 16) : (w & 0xffffu);
+            const double c = *reinterpret_cast<const double*>(cb + off);
+            f[r][0] = fma(c, mx, f[r][0]);
+            f[r][1] = fma(c, my, f[r][1]);
+            f[r][2] = fma(c, mz, f[r][2]);
+         }
+   }
    static __device__ __forceinline__ void run(const Tables& t, const uint4* __restrict__ ent, const unsigned char* __restrict__ endb,
                                               const double* __restrict__ srec, double (&f)[R][3]) {
-      RunLoop<R, MASK - 1, PL>::run(t, ent, endb, srec, f);
+      RunLoop<R, MASK - 1, PL, U>::run(t, ent, endb, srec, f);
       const int e0 = endb[MASK - 1], e1 = endb[MASK];
-      uint4 nx = ent[e0];                   // one entry ahead: its decode overlaps the loads of the current one
+      if (U == 1) {
+         uint4 nx = ent[e0];                   // one entry ahead: its decode overlaps the loads of the current one
 #pragma unroll (RUN_UNROLL)
-      for (int e = e0; e < e1; e++) {
-         const uint4 en = nx;
-         nx = ent[e + 1];                   // rows carry one spare entry
-         const double* __restrict__ m = reinterpret_cast<const double*>(reinterpret_cast<const char*>(srec) + en.x);
-         const double mx = m[0], my = m[PL], mz = m[2 * PL];
-         const char* __restrict__ cb = reinterpret_cast<const char*>(t.cpl_small);
+         for (int e = e0; e < e1; e++) {
+            const uint4 en = nx;
+            nx = ent[e + 1];                   // rows carry one spare entry
+            use(t, en, srec, f);
+         }
+      } else if (U == 2 && ASD_WALK_X) {
+         // classes padded to an even number of entries (null entries read a zero moment): four entries per iteration -- the first
+         // pair was fetched by the previous iteration, the second pair flies while the first is used -- and one closing pair
+         int e = e0;
+         uint4 n0 = ent[e], n1 = ent[e + 1];
+#pragma unroll 1
+         for (; e + 4 <= e1; e += 4) {
+            const uint4 b0 = ent[e + 2], b1 = ent[e + 3];
+            use(t, n0, srec, f); use(t, n1, srec, f);
+            n0 = ent[e + 4]; n1 = ent[e + 5];        // rows carry two spare entries
+            use(t, b0, srec, f); use(t, b1, srec, f);
+         }
+         if (e < e1) { use(t, n0, srec, f); use(t, n1, srec, f); }
+      } else {
+         // classes padded to a multiple of U entries (null entries read a zero moment): U entries per iteration, the next U
+         // fetched one iteration ahead (rows carry U spare entries), no remainder loop
+         uint4 nx[U];
 #pragma unroll
-         for (int r = 0; r < R; r++)
-            if (MASK & (1 << r)) {
-               const unsigned w = (r < 2) ? en.y : en.z;
-               const unsigned off = (r & 1) ? (w >> 16) : (w & 0xffffu);
-               const double c = *reinterpret_cast<const double*>(cb + off);
-               f[r][0] = fma(c, mx, f[r][0]);
-               f[r][1] = fma(c, my, f[r][1]);
-               f[r][2] = fma(c, mz, f[r][2]);
-            }
+         for (int u = 0; u < U; u++) nx[u] = ent[e0 + u];
+#pragma unroll 1
+         for (int e = e0; e < e1; e += U) {
+            uint4 en[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) { en[u] = nx[u]; nx[u] = ent[e + U + u]; }
+#pragma unroll
+            for (int u = 0; u < U; u++) use(t, en[u], srec, f);
+         }
       }
    }
 };
-template <int R, int PL>
-struct RunLoop<R, 0, PL> {
+template <int R, int PL, int U>
+struct RunLoop<R, 0, PL, U> {
    static __device__ __forceinline__ void run(const Tables&, const uint4*, const unsigned char*, const double*, double (&)[R][3]) {}
 };
 
@@ -249,6 +304,8 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
    // below executes its 14 predicated load / convert / store slots whatever the list length (ncu r2s: 670 of 3770 instructions of
    // config 4).  Only in the XS kernels, so that the code of the headline kernel is not touched.
    if (MM) {
+      // the zero moment the null entries of padded union rows read: positions MM_PLANE - 32 .. MM_PLANE - 1 of every plane
+      if (WALK_U > 1 && threadIdx.x < 96) s3[(threadIdx.x >> 5) * MM_PLANE + (MM_PLANE - 32) + (threadIdx.x & 31)] = 0.0;
       const double* __restrict__ G = ((STAGE == 1) ? p.mm_cur : p.mm_pred) + (size_t)k * 3 * t.Npad;
       constexpr int MB = 14;    // list positions per thread and round: every index first, then 3 copies per position
       for (int u0 = threadIdx.x; u0 < cnt; u0 += MB * NT) {
@@ -325,6 +382,15 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
    asm volatile("cp.async.wait_all;" ::: "memory");
    stage_couplings(t, sm, smc, smd, smb);   // ends with __syncthreads() when it stages anything
    if (ncpl == 0) __syncthreads();
+#ifndef ASD_NO_OWNPF
+   if (MM) {
+      // the own (and old) spin of the first atom is needed right after the union walk: bring its line into L1 now (no register is
+      // held across the walk; the loads of atoms 2..4 already fly one integrator iteration ahead)
+      const int ifirst = min(i0, t.Nown - 1);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(S + ifirst));
+      if (STAGE == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(curk + ifirst));
+   }
+#endif
    // ---- Heisenberg sums of the 4 atoms of this thread: every distinct neighbour run read once ----
    double f[R][3];
 #pragma unroll
@@ -334,7 +400,7 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
    for (int r = 0; r < R; r++) ih = max(ih, __shfl_sync(0xffffffffu, mt[r].y >= 0 ? mt[r].x : -1, 0));
    if (ih >= 0 && !(ASD_ABL & 2)) {
       const uint4* __restrict__ row = rows + wp * t.urow;
-      if (MM) RunLoop<R, (1 << R) - 1, MM_PLANE>::run(t, row + 1, reinterpret_cast<const unsigned char*>(row), s3 + ln, f);
+      if (MM) RunLoop<R, (1 << R) - 1, MM_PLANE, WALK_U>::run(t, row + 1, reinterpret_cast<const unsigned char*>(row), s3 + ln, f);
       else RunLoop<R, (1 << R) - 1>::run(t, row + 1, reinterpret_cast<const unsigned char*>(row), s3 + 3 * ln, f);
    }
    // ---- integrators: one rolled loop over the 4 atoms (the register arrays rotate, so the body exists once); the
