@@ -370,3 +370,47 @@ def test_moment_planes_follow_every_writer_of_the_spins(monkeypatch):
             e.sd_steps(2, first_step=26)
         assert np.array_equal(a.get_moments()[0], b.get_moments()[0]), (solver, 'after the stage-timing entry')
         a.close(); b.close()
+
+
+def test_run_kernel_with_anisotropy_and_field_against_oracle(monkeypatch):
+    """Heisenberg + single-ion anisotropy (uniaxial on one sublattice, uniaxial + cubic `type 7` on the other) + a uniform field on a
+    bcc lattice whose layout takes the moment-plane instantiation of the run kernel with the LEAN integrator loop (asd_runs.cuh):
+    both solvers against the oracle at T = 0 to 1e-12 (hamiltonianactions.f90:225-239,842-919), and at 300 K bit for bit against
+    the general instantiation (ASD_MM=0) with the same noise stream."""
+    import json
+    import os
+    from util import GOLDEN, lattice_engine
+    with open(os.path.join(GOLDEN, 'bccfe_cuda.json')) as fh:
+        fx = json.load(fh)
+    args = list(inputs.load_fixture(fx))
+    args[0] = dict(args[0], ncell=(64, 8, 8), mensemble=2, do_reduced='Y', hfield=(0.3, -0.2, 1.1))
+    args[9] = (np.array([1, 7], dtype=np.int32),
+               np.asfortranarray([[0.12, 0.03, 0.0, 0.6, 0.8, 0.0], [-0.08, 0.05, 1.0, 0.0, 0.0, 0.35]]))
+    S = orc.build_system(*args)
+    inp = args[0]
+    rng = np.random.default_rng(17)
+    e0 = rng.normal(size=(3, S['Natom'], 2)); e0 /= np.sqrt((e0 ** 2).sum(axis=0))
+    S['emom'] = np.asfortranarray(e0)
+    S['emomM'] = np.asfortranarray(e0 * S['mmom'][None])
+    assert S['aniso'] is not None and np.abs(S['external_field']).max() > 0
+    for solver in (1, 5):
+        monkeypatch.delenv('ASD_MM', raising=False)
+        e = lattice_engine(args, S, solver, inp['timestep'], 0.3)
+        info = e.layout_info()
+        assert info['runs'] == 4 and info['tile_slots'] == 1024 and info['planes'] == 1, info
+        beff, _ = e.effective_field()
+        rb, _ = orc.effective_field(S)
+        assert np.abs(beff - rb).max() <= 1e-12 * np.abs(rb).max()
+        st = orc.SdState(S, solver, inp['timestep'], 0.3)
+        e.sd_steps(30)
+        for _ in range(30):
+            st.step()
+        assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12, solver
+        a = lattice_engine(args, S, solver, inp['timestep'], 0.3, temp=300.0)
+        monkeypatch.setenv('ASD_MM', '0')
+        b = lattice_engine(args, S, solver, inp['timestep'], 0.3, temp=300.0)
+        assert a.layout_info()['planes'] == 1 and b.layout_info()['planes'] == 0 and b.layout_info()['runs'] == 4
+        a.sd_steps(20); b.sd_steps(20)
+        assert np.array_equal(a.get_moments()[0], b.get_moments()[0]), solver
+        for x in (e, a, b):
+            x.close()

@@ -331,7 +331,7 @@ static int build_runs(asd_engine* e, Layout& L) {
       const bool xs = t.dm16 != nullptr || t.bq16 != nullptr || t.ucap <= 6 * 256;
       // ... and only plain Heisenberg layouts: paired with the LEAN integrator loop the planes give 0.456 -> 0.429 ms per step at
       // bcc 128^3, with the general loop 0.468 (measured, profiles/README: the general instantiation is at its register limit)
-      const bool plain = !e->have_aniso && t.zdm == 0 && t.zbq == 0 && !t.jtens;
+      const bool plain = t.zdm == 0 && t.zbq == 0 && !t.jtens;
       t.mm = (!(menv && atoi(menv) == 0) && t.tile_slots == 1024 && t.ucap + 32 <= MM_PLANE - 32 && !e->slab.on && !xs && plain) ? 1 : 0;
    }
    const unsigned pos_scale = t.mm ? 8u : 24u;
@@ -982,15 +982,16 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
       // (only together with the moment planes: without them the LEAN loop measured SLOWER than the general one, 0.487 against
       // 0.456 ms per step -- ptxas then issues the first spin loads of the staging loop after all fourteen index loads)
       const bool lean = lean_env && mm && !EDGE && !xs && NW == 8 && !p.per_site && p.mompar == 0 && L.t.btorque == nullptr && L.t.ext_uniform &&
-                        !L.t.do_aniso && L.t.zdm == 0 && L.t.zbq == 0 && !L.t.jtens;
+                        L.t.zdm == 0 && L.t.zbq == 0 && !L.t.jtens;
       if (NW == 8) {
-         if (xs) ASD_LAUNCH_RUNS(8, true, false, false);
-         else if (mm && lean) ASD_LAUNCH_RUNS(8, false, (!EDGE), (!EDGE));
-         else if (mm) ASD_LAUNCH_RUNS(8, false, false, (!EDGE));
-         else ASD_LAUNCH_RUNS(8, false, false, false);
+         if (xs) ASD_LAUNCH_RUNS(8, true, 0, false);
+         else if (mm && lean && L.t.do_aniso) ASD_LAUNCH_RUNS(8, false, (EDGE ? 0 : 2), (!EDGE));
+         else if (mm && lean) ASD_LAUNCH_RUNS(8, false, (EDGE ? 0 : 1), (!EDGE));
+         else if (mm) ASD_LAUNCH_RUNS(8, false, 0, (!EDGE));
+         else ASD_LAUNCH_RUNS(8, false, 0, false);
       }
-      else if (NW == 4) ASD_LAUNCH_RUNS(4, false, false, false);
-      else ASD_LAUNCH_RUNS(2, false, false, false);
+      else if (NW == 4) ASD_LAUNCH_RUNS(4, false, 0, false);
+      else ASD_LAUNCH_RUNS(2, false, 0, false);
 #undef ASD_LAUNCH_RUNS
    } else if (L.t.staged && !fr) {
       const size_t smem = L.smem_bytes + (size_t)3 * L.t.ucap * sizeof(double);

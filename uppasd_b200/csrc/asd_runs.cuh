@@ -222,7 +222,7 @@ struct RunLoop<R, 0, PL, U> {
 // 1024 slots = 1, 2, 4 bricks of a super-brick): NW warps, thread (warp w, lane l) owns the atoms
 // tile*TS + (w*4 + r)*32 + l, r = 0..3.  Same contract as llg_stage_kernel (asd_device.cuh).
 // XS: the layout's DM / BQ neighbours are in the gather list too (dm16 / bq16) and are read from shared memory.
-// LEAN: plain Heisenberg system with a uniform field and uniform LLG parameters (the engine checks: no DM / BQ / anisotropy /
+// LEAN (1; 2 = with single-ion anisotropy): Heisenberg system with a uniform field and uniform LLG parameters (the engine checks: no DM / BQ /
 // tensor couplings, uniform external field, uniform damping / g factor / temperature, no torque field, mompar 0) -- the integrator
 // loop then carries none of the runtime checks and predicated loads of the general form (270 -> 150 instructions per atom-stage).
 // MM: the gather list is staged from the MOMENT PLANES -- emomM = e * m of every slot as three component planes [M][3][Npad]
@@ -231,7 +231,7 @@ struct RunLoop<R, 0, PL, U> {
 // once, 24 instead of 32 bytes per gathered spin.  (Ablation, profiles/README: staging through registers cost 0.10 of the 0.47 ms
 // step and did not overlap with anything.)  Layouts with ucap + 32 <= MM_PLANE, no slab, no XS tables; the union rows carry
 // 8 * base.
-template <int SOLVER, int STAGE, int NW, bool EDGE, bool MSUM, bool XS, bool LEAN = false, bool MM = false>
+template <int SOLVER, int STAGE, int NW, bool EDGE, bool MSUM, bool XS, int LEAN = 0, bool MM = false>
 __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : (NW == 4) ? 4 : 6)
 llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgParams p, const __grid_constant__ EdgeParams ep,
                 const TileRange tr, SpinVec* __restrict__ cur, SpinVec* __restrict__ pred, double* __restrict__ b2eff) {
@@ -420,8 +420,12 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
       if (io >= 0) {
          double bs[3] = {f[0][0], f[0][1], f[0][2]}, bq[3] = {0.0, 0.0, 0.0};
          double h[3];
-         if (LEAN) { h[0] = t.hext[0]; h[1] = t.hext[1]; h[2] = t.hext[2]; }
-         else {
+         if (LEAN) {
+            h[0] = t.hext[0]; h[1] = t.hext[1]; h[2] = t.hext[2];
+            // LEAN == 2: single-ion anisotropy is the one extra term (its own instantiation: a runtime test here cost the plain
+            // system 4.7 %, measured)
+            if (LEAN == 2) aniso_field<true>(t, i, ih, own.x * own.m, own.y * own.m, own.z * own.m, bs[0], bs[1], bs[2], bq[0], bq[1], bq[2]);
+         } else {
             site_field<true, false, ASD_CHUNK, XS>(t, S, i, ih, own, smc, smd, smb, bs, bq, s3, (XS && t.dm16 != nullptr) ? &dmw[0] : nullptr);
             ext_field(t, i, k, h);
          }
@@ -429,13 +433,13 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
          h[0] += p.tf[0]; h[1] += p.tf[1]; h[2] += p.tf[2];
 #endif
          double b[3];
-         if (LEAN) { b[0] = bs[0] + h[0]; b[1] = bs[1] + h[1]; b[2] = bs[2] + h[2]; }
+         if (LEAN == 1) { b[0] = bs[0] + h[0]; b[1] = bs[1] + h[1]; b[2] = bs[2] + h[2]; }
          else { b[0] = bs[0] + (bq[0] + h[0]); b[1] = bs[1] + (bq[1] + h[1]); b[2] = bs[2] + (bq[2] + h[2]); }
 #if (ASD_ABL & 1)
          SpinVec o = (STAGE == 1) ? own : old;
          o.x += 1e-300 * (b[0] + gn[0][0]); o.y += 1e-300 * (b[1] + gn[0][1]); o.z += 1e-300 * (b[2] + gn[0][2]);
 #else
-         const SpinVec o = integrate_site<SOLVER, STAGE, false, LEAN>(t, p, i, k, io, b, own, (STAGE == 1) ? own : old, b2eff, gn[0]);
+         const SpinVec o = integrate_site<SOLVER, STAGE, false, (LEAN != 0)>(t, p, i, k, io, b, own, (STAGE == 1) ? own : old, b2eff, gn[0]);
 #endif
          if (STAGE == 1) predk[i] = o; else curk[i] = o;
          if (MM) {
