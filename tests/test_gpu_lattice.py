@@ -414,3 +414,48 @@ def test_run_kernel_with_anisotropy_and_field_against_oracle(monkeypatch):
         assert np.array_equal(a.get_moments()[0], b.get_moments()[0]), solver
         for x in (e, a, b):
             x.close()
+
+
+def test_fcc_four_sublattices_take_the_run_kernel(monkeypatch):
+    """fcc in its conventional cell (four basis atoms, two shells, z = 12 + 6): the super-brick holds 2048 slots and the run kernel
+    works on 1024-slot tiles (half a super-brick).  Both solvers against the oracle at T = 0 to 1e-12; at 300 K the same noise
+    stream as the staged one-atom-per-thread kernel (ASD_RUNS=0), which sums the neighbours in list order: 1e-9 after 20 steps."""
+    import copy
+    import json
+    import os
+    from util import GOLDEN, lattice_engine
+    with open(os.path.join(GOLDEN, 'bccfe_cuda.json')) as fh:
+        fx = copy.deepcopy(json.load(fh))
+    fx['posfile'] = [['1', '1', '0.0', '0.0', '0.0'], ['2', '1', '0.5', '0.5', '0.0'], ['3', '1', '0.5', '0.0', '0.5'], ['4', '1', '0.0', '0.5', '0.5']]
+    fx['momfile'] = [[str(i), '1', '1.7', '0.3', '0.4', '0.85', '2.0'] for i in (1, 2, 3, 4)]
+    fx['jfile'] = [['1', '1', '0.5', '0.5', '0.0', '1.2'], ['1', '1', '1.0', '0.0', '0.0', '-0.15']]
+    args = list(inputs.load_fixture(fx))
+    args[0] = dict(args[0], ncell=(64, 8, 8), mensemble=2, do_reduced='Y', hfield=(0.0, 0.0, 0.5))
+    S = orc.build_system(*args)
+    inp = args[0]
+    assert S['Natom'] == 4 * 64 * 8 * 8 and S['exchange']['z'] == 18 and S['nHam'] == 4
+    rng = np.random.default_rng(23)
+    e0 = rng.normal(size=(3, S['Natom'], 2)); e0 /= np.sqrt((e0 ** 2).sum(axis=0))
+    S['emom'] = np.asfortranarray(e0)
+    S['emomM'] = np.asfortranarray(e0 * S['mmom'][None])
+    for solver in (1, 5):
+        monkeypatch.delenv('ASD_RUNS', raising=False)
+        e = lattice_engine(args, S, solver, inp['timestep'], 0.3)
+        info = e.layout_info()
+        assert info['runs'] == 4 and info['tile_slots'] == 1024, info
+        beff, _ = e.effective_field()
+        rb, _ = orc.effective_field(S)
+        assert np.abs(beff - rb).max() <= 1e-12 * np.abs(rb).max()
+        st = orc.SdState(S, solver, inp['timestep'], 0.3)
+        e.sd_steps(30)
+        for _ in range(30):
+            st.step()
+        assert np.abs(e.get_moments()[0] - st.emom).max() <= 1e-12, solver
+        a = lattice_engine(args, S, solver, inp['timestep'], 0.3, temp=300.0)
+        monkeypatch.setenv('ASD_RUNS', '0')
+        b = lattice_engine(args, S, solver, inp['timestep'], 0.3, temp=300.0)
+        assert b.layout_info()['runs'] == 0 and b.layout_info()['staged'] == 1
+        a.sd_steps(20); b.sd_steps(20)
+        assert np.abs(a.get_moments()[0] - b.get_moments()[0]).max() <= 1e-9, solver
+        for x in (e, a, b):
+            x.close()

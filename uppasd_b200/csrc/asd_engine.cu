@@ -427,9 +427,10 @@ static int finish_layout(asd_engine* e, Layout& L) {
       }
       // tile size of the run kernel: the whole super-brick by default
       int big = (has_lattice(e) && !L.is_mc) ? e->lat.NA * e->lat.P * e->lat.SY * e->lat.SZ : 256;   // slots of a super-brick
-      if (big != 1024) big = 256;   // smaller tiles only on request (ASD_RUNS): measured slower than the staged kernel
-      // short lists without DM / BQ work (fcc, z = 18): the step is integrator-bound and the staged kernel's 32 warps/SM win
-      if (t.z < 24 && t.zdm == 0 && t.zbq == 0) big = 256;
+      // 1024-slot tiles when they divide the super-brick (bcc: the super-brick itself; fcc, four basis atoms: half of it); smaller
+      // tiles only on request (ASD_RUNS): measured slower than the staged kernel.  (Short lists, fcc z = 18: the run kernel on
+      // the moment planes 0.347 ms per step at 128 x 128 x 64 x 4, the staged one-atom-per-thread kernel 0.377.)
+      big = (big >= 1024 && big % 1024 == 0) ? 1024 : 256;
       const char* renv = std::getenv("ASD_RUNS");
       if (renv) big = atoi(renv);
       if (big != 0 && big != 256 && big != 512 && big != 1024) return fail(-1, "ASD_RUNS must be 0, 256, 512 or 1024");
@@ -983,8 +984,11 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
       // 0.456 ms per step -- ptxas then issues the first spin loads of the staging loop after all fourteen index loads)
       const bool lean = lean_env && mm && !EDGE && !xs && NW == 8 && !p.per_site && p.mompar == 0 && L.t.btorque == nullptr && L.t.ext_uniform &&
                         L.t.zdm == 0 && L.t.zbq == 0 && !L.t.jtens;
+      // XS layouts (DM / BQ tables, short lists): the general field terms with the lean integrator (uniform LLG parameters, no torque field)
+      const bool ilean = lean_env && !EDGE && NW == 8 && !p.per_site && p.mompar == 0 && L.t.btorque == nullptr;
       if (NW == 8) {
-         if (xs) ASD_LAUNCH_RUNS(8, true, 0, false);
+         if (xs && ilean) ASD_LAUNCH_RUNS(8, true, (EDGE ? 0 : 3), false);
+         else if (xs) ASD_LAUNCH_RUNS(8, true, 0, false);
          else if (mm && lean && L.t.do_aniso) ASD_LAUNCH_RUNS(8, false, (EDGE ? 0 : 2), (!EDGE));
          else if (mm && lean) ASD_LAUNCH_RUNS(8, false, (EDGE ? 0 : 1), (!EDGE));
          else if (mm) ASD_LAUNCH_RUNS(8, false, 0, (!EDGE));

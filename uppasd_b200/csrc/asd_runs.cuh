@@ -222,7 +222,7 @@ struct RunLoop<R, 0, PL, U> {
 // 1024 slots = 1, 2, 4 bricks of a super-brick): NW warps, thread (warp w, lane l) owns the atoms
 // tile*TS + (w*4 + r)*32 + l, r = 0..3.  Same contract as llg_stage_kernel (asd_device.cuh).
 // XS: the layout's DM / BQ neighbours are in the gather list too (dm16 / bq16) and are read from shared memory.
-// LEAN (1; 2 = with single-ion anisotropy): Heisenberg system with a uniform field and uniform LLG parameters (the engine checks: no DM / BQ /
+// LEAN (1; 2 = with single-ion anisotropy; 3 = general field terms, lean integrator only): Heisenberg system with a uniform field and uniform LLG parameters (the engine checks: no DM / BQ /
 // tensor couplings, uniform external field, uniform damping / g factor / temperature, no torque field, mompar 0) -- the integrator
 // loop then carries none of the runtime checks and predicated loads of the general form (270 -> 150 instructions per atom-stage).
 // MM: the gather list is staged from the MOMENT PLANES -- emomM = e * m of every slot as three component planes [M][3][Npad]
@@ -420,7 +420,7 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
       if (io >= 0) {
          double bs[3] = {f[0][0], f[0][1], f[0][2]}, bq[3] = {0.0, 0.0, 0.0};
          double h[3];
-         if (LEAN) {
+         if (LEAN == 1 || LEAN == 2) {
             h[0] = t.hext[0]; h[1] = t.hext[1]; h[2] = t.hext[2];
             // LEAN == 2: single-ion anisotropy is the one extra term (its own instantiation: a runtime test here cost the plain
             // system 4.7 %, measured)
