@@ -276,6 +276,9 @@ def config_blocks(world, rank, local, dist, torch, peak):
             ms = agg(e.time_sd_steps(20, first_step=4))
             rate = world * n * m * 20 / (ms * 1e-3)
             blk['llg'] = {'value': rate, 'unit': 'atom-steps/s', 'ms_per_step': ms / 20, 'frac_of_peak': (136.0 + 24.0 * z) * rate / world / 1e9 / peak}
+            blk['note'] = ('frac_of_peak counts the per-atom tables (4z index + 8z coupling bytes) once per (atom, ensemble) and stage as SURVEY 8d '
+                           'does; here they are shared by the %d ensembles and (%.0f MB) stay in the 126 MB L2, so a value above 1 is not HBM traffic'
+                           % (m, 12.0 * z * n / 1e6))
             e.close()
             out['config3'] = blk
         except Exception as ex:
