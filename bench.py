@@ -196,6 +196,29 @@ def cpu_leg(ncell, solver, temp, damping, steps, warmup, settle_s=0.0, one_threa
     return n * steps / dt, dt / steps * 1e3, n, threads, one
 
 
+def bind_near_gpu(torch, local):
+    """Multi-rank runs: pin this process to the CPUs NVML reports as local to its GPU (intersected with the CPUs the container
+    allows), so that the pinned host buffers of the end-to-end leg are allocated on the GPU's own NUMA node and the state copies
+    of the eight ranks do not all cross one socket link.  Returns a short description for the JSON line, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        bus = '%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        near = {64 * w + b for w, x in enumerate(words) for b in range(64) if (int(x) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        target = near & allowed
+        if target and target != allowed:
+            os.sched_setaffinity(0, target)
+            return {'cpus_near_gpu': len(near), 'bound_to': len(target), 'allowed': len(allowed)}
+        return {'cpus_near_gpu': len(near), 'bound_to': 0, 'allowed': len(allowed)}
+    except Exception as ex:   # no NVML, no permission: run unbound
+        return {'error': repr(ex)[:120]}
+
+
 def traffic_from_profiles(kernel_key):
     """dram bytes per launch of the dominant kernel from the committed ncu summary (profiles/traffic.json), or None"""
     p = os.path.join(ROOT, 'profiles', 'traffic.json')
@@ -424,6 +447,7 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     torch.cuda.set_device(local)
+    numa = bind_near_gpu(torch, local) if world > 1 else None   # (N = 1 keeps every core for the CPU baseline leg)
     slab = (world, rank, dist) if a.decomp == 'slab' else None
     e, n = bcc_engine(a.ncell, a.solver, a.temp, a.damping, 1, 0 if slab else rank, local, slab=slab, reduced=not a.full_ham)
     sync = torch.zeros(1, device='cuda')
@@ -554,7 +578,7 @@ def main():
             'warmup': warmup, 'ms_per_step': ms / steps, 'higher_is_better': True,
             'scaling': 'strong' if slab else 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': workload, 'spins_per_gpu': n, 'ensembles': 1 if slab else world, 'parallelism': par,
-                       'field_path': lay,
+                       'field_path': lay, 'numa': numa,
                        'l2_policy': 'inputs larger than L2 (%s + spins %s%.0f MB per GPU vs 126 MB L2)'
                                     % (tables, 'and moment planes ' if lay.get('planes') else '', (112.0 if lay.get('planes') else 64.0) * n / 1e6)},
             'clocks': sampler.summary(),

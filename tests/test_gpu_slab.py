@@ -70,6 +70,29 @@ def test_slab_matches_undecomposed(solver, temp, nslabs, ncell):
         assert err == 0 and ep == 1 + 2 * done
 
 
+@pytest.mark.parametrize('solver', [1, 5])
+@pytest.mark.parametrize('nslabs', [2, 4])
+def test_slab_on_moment_planes(solver, nslabs):
+    """Slabs whose layout takes the moment-plane instantiations of the run kernel (asd_runs.cuh): a boundary atom's emomM is pushed
+    into the neighbours' planes next to its spin, and the planes of the halo are derived after the neighbours' first push has
+    landed.  Thermal run, bit for bit against the undecomposed supercell; a Monte Carlo interlude invalidates and rebuilds the planes."""
+    ncell = (64, 8, 32)
+    ref = _bcc(ncell, solver, 300.0)[0]
+    sl = _bcc(ncell, solver, 300.0, nslabs=nslabs)
+    assert ref.layout_info()['planes'] == 1 and all(e.layout_info()['planes'] == 1 for e in sl), [e.layout_info() for e in sl]
+    done = 0
+    for n in (1, 2, 9):
+        ref.sd_steps(n, first_step=done + 1)
+        for s in range(n):
+            for e in sl:
+                e.sd_steps(1, first_step=done + 1 + s)
+        done += n
+        a, b = _gather(sl), ref.get_moments()[0]
+        assert np.array_equal(a, b), (solver, nslabs, done, np.abs(a - b).max())
+    for e in sl:
+        assert e.slab_status()[1] == 0
+
+
 def test_slab_observables_and_ensembles():
     ncell = (32, 4, 8)
     ref = _bcc(ncell, 1, 300.0, mens=3)[0]

@@ -699,6 +699,8 @@ struct EdgeParams {
    const int* __restrict__ hdst_hi;   // [Nown] halo slot in the UPPER neighbour, or -1
    SpinVec* peer_lo;                  // the buffer this stage writes (cur or pred), as mapped from the neighbours
    SpinVec* peer_hi;
+   double* peer_mlo;                  // moment planes of that buffer in the neighbours (MM run kernels), [M][3][Npad]
+   double* peer_mhi;
    unsigned long long* flag_lo;       // flag word of the lower neighbour that THIS rank owns (its "upper" word)
    unsigned long long* flag_hi;
    unsigned long long epoch;          // value to publish

@@ -127,8 +127,10 @@ struct Slab {
    DevBuf<int> err;
    SpinVec* peer_cur[2] = {nullptr, nullptr};    // [0] lower neighbour, [1] upper neighbour
    SpinVec* peer_pred[2] = {nullptr, nullptr};
+   double* peer_mcur[2] = {nullptr, nullptr};    // the neighbours' moment planes (MM run kernels push emomM next to the spin)
+   double* peer_mpred[2] = {nullptr, nullptr};
    unsigned long long* peer_flags[2] = {nullptr, nullptr};
-   void* opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+   void* opened[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
    int n_opened = 0;
    unsigned long long epoch = 0;       // exchanges completed (identical on every rank)
    bool connected = false;
@@ -325,14 +327,15 @@ static int build_runs(asd_engine* e, Layout& L) {
    int r;
    if ((r = L.d_gcount.alloc(ngroup))) return r;
    // MM instantiations of the run kernel (gather list staged from the moment planes with cp.async): 1024-slot tiles whose list fits
-   // the fixed plane stride, no slab (the halo push writes spins only), none of the XS cases (DM / BQ positions, short lists)
+   // the fixed plane stride, none of the XS cases (DM / BQ positions, short lists); a slab pushes the planes of its boundary atoms
+   // into the neighbours' halos next to the spins
    {
       const char* menv = std::getenv("ASD_MM");
       const bool xs = t.dm16 != nullptr || t.bq16 != nullptr || t.ucap <= 6 * 256;
       // ... and only plain Heisenberg layouts: paired with the LEAN integrator loop the planes give 0.456 -> 0.429 ms per step at
       // bcc 128^3, with the general loop 0.468 (measured, profiles/README: the general instantiation is at its register limit)
       const bool plain = t.zdm == 0 && t.zbq == 0 && !t.jtens;
-      t.mm = (!(menv && atoi(menv) == 0) && t.tile_slots == 1024 && t.ucap + 32 <= MM_PLANE - 32 && !e->slab.on && !xs && plain) ? 1 : 0;
+      t.mm = (!(menv && atoi(menv) == 0) && t.tile_slots == 1024 && t.ucap + 32 <= MM_PLANE - 32 && !xs && plain) ? 1 : 0;
    }
    const unsigned pos_scale = t.mm ? 8u : 24u;
    const int pad = t.mm ? WALK_U : 1;                       // union rows of MM layouts: mask classes padded to the walk's unroll
@@ -982,16 +985,16 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
       static const bool lean_env = !(std::getenv("ASD_LEAN") && atoi(std::getenv("ASD_LEAN")) == 0);
       // (only together with the moment planes: without them the LEAN loop measured SLOWER than the general one, 0.487 against
       // 0.456 ms per step -- ptxas then issues the first spin loads of the staging loop after all fourteen index loads)
-      const bool lean = lean_env && mm && !EDGE && !xs && NW == 8 && !p.per_site && p.mompar == 0 && L.t.btorque == nullptr && L.t.ext_uniform &&
+      const bool lean = lean_env && mm && !xs && NW == 8 && !p.per_site && p.mompar == 0 && L.t.btorque == nullptr && L.t.ext_uniform &&
                         L.t.zdm == 0 && L.t.zbq == 0 && !L.t.jtens;
       // XS layouts (DM / BQ tables, short lists): the general field terms with the lean integrator (uniform LLG parameters, no torque field)
       const bool ilean = lean_env && !EDGE && NW == 8 && !p.per_site && p.mompar == 0 && L.t.btorque == nullptr;
       if (NW == 8) {
          if (xs && ilean) ASD_LAUNCH_RUNS(8, true, (EDGE ? 0 : 3), false);
          else if (xs) ASD_LAUNCH_RUNS(8, true, 0, false);
-         else if (mm && lean && L.t.do_aniso) ASD_LAUNCH_RUNS(8, false, (EDGE ? 0 : 2), (!EDGE));
-         else if (mm && lean) ASD_LAUNCH_RUNS(8, false, (EDGE ? 0 : 1), (!EDGE));
-         else if (mm) ASD_LAUNCH_RUNS(8, false, 0, (!EDGE));
+         else if (mm && lean && L.t.do_aniso) ASD_LAUNCH_RUNS(8, false, (EDGE ? 0 : 2), true);
+         else if (mm && lean) ASD_LAUNCH_RUNS(8, false, (EDGE ? 0 : 1), true);
+         else if (mm) ASD_LAUNCH_RUNS(8, false, 0, true);
          else ASD_LAUNCH_RUNS(8, false, 0, false);
       }
       else if (NW == 4) ASD_LAUNCH_RUNS(4, false, 0, false);
@@ -1037,6 +1040,8 @@ static EdgeParams edge_params(asd_engine* e, int stage, unsigned long long epoch
    ep.hdst_lo = sb.hdst_lo.p; ep.hdst_hi = sb.hdst_hi.p;
    ep.peer_lo = (stage == 1) ? sb.peer_pred[0] : sb.peer_cur[0];
    ep.peer_hi = (stage == 1) ? sb.peer_pred[1] : sb.peer_cur[1];
+   ep.peer_mlo = (stage == 1) ? sb.peer_mpred[0] : sb.peer_mcur[0];
+   ep.peer_mhi = (stage == 1) ? sb.peer_mpred[1] : sb.peer_mcur[1];
    // this rank is the UPPER neighbour of its lower neighbour: it owns word [1] there, and word [0] above
    ep.flag_lo = e->lat.has_lo ? sb.peer_flags[0] + 1 : nullptr;
    ep.flag_hi = e->lat.has_hi ? sb.peer_flags[1] + 0 : nullptr;
@@ -1165,6 +1170,12 @@ static int mm_prepare(asd_engine* e, Layout& L) {
    }
    static const bool always = std::getenv("ASD_MM_ALWAYS") && atoi(std::getenv("ASD_MM_ALWAYS")) != 0;
    if (!e->mm_valid || always) {
+      if (e->slab.on && e->slab.connected) {
+         // the halo slots of `cur` are the neighbours' to fill: their last exchange must have landed before the planes are derived
+         Slab& sb = e->slab;
+         halo_wait_kernel<<<1, 1, 0, e->stream>>>(sb.flags.p, e->lat.has_lo, e->lat.has_hi, sb.epoch, sb.timeout_ticks, sb.err.p);
+         e->launches++;
+      }
       moment_planes_kernel<<<dim3((unsigned)((L.Npad + 255) / 256), e->M), 256, 0, e->stream>>>((size_t)L.Npad, e->M, e->cur.p, e->mm_cur.p);
       e->launches++;
       CU(cudaGetLastError());
@@ -1458,6 +1469,12 @@ static int slab_commit(asd_engine* e) {
    int r;
    if ((r = e->cur.alloc((size_t)L.Npad * e->M))) return r;
    if ((r = e->pred.alloc((size_t)L.Npad * e->M))) return r;
+   // the moment planes are part of what the ring neighbours map (exported with cur / pred), whether or not this layout uses them
+   if ((r = e->mm_cur.alloc((size_t)3 * L.Npad * e->M))) return r;
+   if ((r = e->mm_pred.alloc((size_t)3 * L.Npad * e->M))) return r;
+   CU(cudaMemset(e->mm_cur.p, 0, (size_t)3 * L.Npad * e->M * sizeof(double)));
+   CU(cudaMemset(e->mm_pred.p, 0, (size_t)3 * L.Npad * e->M * sizeof(double)));
+   e->mm_valid = false;
    if ((r = sb.flags.alloc(2))) return r;
    if ((r = sb.ctr.alloc(1))) return r;
    if ((r = sb.err.alloc(1))) return r;
@@ -2102,10 +2119,12 @@ int asd_slab_export(asd_engine* e, void* handles) {
    CU(cudaIpcGetMemHandle(&h[0], e->cur.p));
    CU(cudaIpcGetMemHandle(&h[1], e->pred.p));
    CU(cudaIpcGetMemHandle(&h[2], e->slab.flags.p));
+   CU(cudaIpcGetMemHandle(&h[3], e->mm_cur.p));
+   CU(cudaIpcGetMemHandle(&h[4], e->mm_pred.p));
    return 0;
 }
 
-int asd_slab_handle_bytes(void) { return (int)(3 * sizeof(cudaIpcMemHandle_t)); }
+int asd_slab_handle_bytes(void) { return (int)(5 * sizeof(cudaIpcMemHandle_t)); }
 
 int asd_slab_connect_ipc(asd_engine* e, const void* lower, const void* upper) {
    Slab& sb = e->slab;
@@ -2116,15 +2135,20 @@ int asd_slab_connect_ipc(asd_engine* e, const void* lower, const void* upper) {
    for (int q = 0; q < sb.n_opened; q++) cudaIpcCloseMemHandle(sb.opened[q]);
    sb.n_opened = 0;
    sb.connected = false;
-   const bool same = memcmp(lower, upper, 3 * sizeof(cudaIpcMemHandle_t)) == 0;   // two slabs: one neighbour on both sides
+   const bool same = memcmp(lower, upper, 5 * sizeof(cudaIpcMemHandle_t)) == 0;   // two slabs: one neighbour on both sides
    for (int side = 0; side < 2; side++) {
-      if (side == 1 && same) { sb.peer_cur[1] = sb.peer_cur[0]; sb.peer_pred[1] = sb.peer_pred[0]; sb.peer_flags[1] = sb.peer_flags[0]; break; }
-      void* p[3];
-      for (int q = 0; q < 3; q++) {
+      if (side == 1 && same) {
+         sb.peer_cur[1] = sb.peer_cur[0]; sb.peer_pred[1] = sb.peer_pred[0]; sb.peer_flags[1] = sb.peer_flags[0];
+         sb.peer_mcur[1] = sb.peer_mcur[0]; sb.peer_mpred[1] = sb.peer_mpred[0];
+         break;
+      }
+      void* p[5];
+      for (int q = 0; q < 5; q++) {
          CU(cudaIpcOpenMemHandle(&p[q], hs[side][q], cudaIpcMemLazyEnablePeerAccess));
-         if (sb.n_opened < 6) sb.opened[sb.n_opened++] = p[q];
+         if (sb.n_opened < 10) sb.opened[sb.n_opened++] = p[q];
       }
       sb.peer_cur[side] = (SpinVec*)p[0]; sb.peer_pred[side] = (SpinVec*)p[1]; sb.peer_flags[side] = (unsigned long long*)p[2];
+      sb.peer_mcur[side] = (double*)p[3]; sb.peer_mpred[side] = (double*)p[4];
    }
    sb.connected = true;
    return 0;
@@ -2146,6 +2170,7 @@ int asd_slab_connect_local(asd_engine* e, asd_engine* lower, asd_engine* upper) 
          cudaGetLastError();
       }
       sb.peer_cur[side] = nb[side]->cur.p; sb.peer_pred[side] = nb[side]->pred.p; sb.peer_flags[side] = nb[side]->slab.flags.p;
+      sb.peer_mcur[side] = nb[side]->mm_cur.p; sb.peer_mpred[side] = nb[side]->mm_pred.p;
    }
    sb.connected = true;
    return 0;

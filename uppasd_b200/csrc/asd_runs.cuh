@@ -229,7 +229,7 @@ struct RunLoop<R, 0, PL, U> {
 // (p.mm_cur / p.mm_pred), which every MM launch keeps up to date next to the spins it writes -- with 8-byte asynchronous copies
 // (cp.async) straight into component planes in shared memory: no registers, no conversion, all copies of a thread in flight at
 // once, 24 instead of 32 bytes per gathered spin.  (Ablation, profiles/README: staging through registers cost 0.10 of the 0.47 ms
-// step and did not overlap with anything.)  Layouts with ucap + 32 <= MM_PLANE, no slab, no XS tables; the union rows carry
+// step and did not overlap with anything.)  Layouts with ucap + 64 <= MM_PLANE, no XS tables (a slab pushes the planes of its boundary atoms too); the union rows carry
 // 8 * base.
 template <int SOLVER, int STAGE, int NW, bool EDGE, bool MSUM, bool XS, int LEAN = 0, bool MM = false>
 __global__ void __launch_bounds__(NW * 32, (NW == 8) ? 2 : (NW == 4) ? 4 : 6)
@@ -451,6 +451,12 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
             const int lo = __ldg(ep.hdst_lo + i), hi = __ldg(ep.hdst_hi + i);
             if (lo >= 0) ep.peer_lo[(size_t)k * t.Npad + lo] = o;
             if (hi >= 0) ep.peer_hi[(size_t)k * t.Npad + hi] = o;
+            if (MM) {
+               // ... and its emomM into the neighbours' moment planes, which is what their MM launches gather from
+               const double ox = o.x * o.m, oy = o.y * o.m, oz = o.z * o.m;
+               if (lo >= 0) { double* __restrict__ q = ep.peer_mlo + (size_t)k * 3 * t.Npad + lo; q[0] = ox; q[t.Npad] = oy; q[2 * (size_t)t.Npad] = oz; }
+               if (hi >= 0) { double* __restrict__ q = ep.peer_mhi + (size_t)k * 3 * t.Npad + hi; q[0] = ox; q[t.Npad] = oy; q[2 * (size_t)t.Npad] = oz; }
+            }
          }
       }
       own = own_n;
