@@ -372,7 +372,8 @@ def slab_block(a, world, rank, local, dist, torch, out, warmup, steps):
         rate = ntot * steps / (ms * 1e-3)
         blk = {'workload': 'bccFe %dx%dx%d (%d spins), ONE supercell in %d z-slabs, LLG solver %d, T=%g K' % (*ncell, int(ntot), world, a.solver, a.temp),
                'value': rate, 'unit': 'atom-steps/s', 'scaling': 'strong', 'ms_per_step': ms / steps, 'steps': steps, 'warmup': warmup,
-               'halo': {'planes': 2, 'bytes_per_exchange_per_side': 2 * ncell[0] * ncell[1] * 2 * 32, 'exchanges_per_step': 2,
+               'halo': {'planes': 2, 'bytes_per_exchange_per_side': 2 * ncell[0] * ncell[1] * 2 * (24 if e.layout_info().get('planes') else 32),
+                        'exchanges_per_step': 2, 'payload': 'emomM (moment planes)' if e.layout_info().get('planes') else 'spins',
                         'transport': 'peer stores over NVLink from the boundary-tile launches (CUDA IPC), epoch flags',
                         'timeout_flag': int(ef.item())},
                'step_frac_of_peak': (b1 + b2) * rate / 1e9 / (peak * world)}
@@ -597,7 +598,7 @@ def main():
                          'step_frac_of_peak': (b1 + b2) * world * n * steps / (ms * 1e-3) / 1e9 / (peak * world)},
         }
         if slab:
-            out['config']['halo'] = {'planes': 2, 'bytes_per_exchange_per_side': 2 * a.ncell[0] * a.ncell[1] * 2 * 32,
+            out['config']['halo'] = {'planes': 2, 'bytes_per_exchange_per_side': 2 * a.ncell[0] * a.ncell[1] * 2 * (24 if lay.get('planes') else 32),
                                      'exchanges_per_step': 2, 'timeout_flag': slab_err}
         if secondary:
             out['secondary'] = secondary

@@ -313,7 +313,7 @@ int asd_set_ensemble_offset(asd_engine* e, unsigned int first_ensemble);
  * coordinates: one halo exchange per colour, fused into the boundary-tile launches in the same way.
  * Arrays passed to / returned by asd_set_moments / asd_get_moments / asd_measure are those of the local slab. */
 int asd_set_slab(asd_engine* e, int nslabs, int slab_index, int halo_planes);
-/* after asd_commit: IPC handles (asd_slab_handle_bytes() bytes) of this slab's cur / pred / flag buffers ... */
+/* after asd_commit: IPC handles (asd_slab_handle_bytes() bytes) of this slab's cur / pred / flag buffers and its two moment-plane buffers ... */
 int asd_slab_handle_bytes(void);
 int asd_slab_export(asd_engine* e, void* handles);
 /* ... which the ring neighbours open (one process per GPU; exchange the bytes with any host transport) */

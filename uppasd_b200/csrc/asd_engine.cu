@@ -992,8 +992,8 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
       if (NW == 8) {
          if (xs && ilean) ASD_LAUNCH_RUNS(8, true, (EDGE ? 0 : 3), false);
          else if (xs) ASD_LAUNCH_RUNS(8, true, 0, false);
-         else if (mm && lean && L.t.do_aniso) ASD_LAUNCH_RUNS(8, false, (EDGE ? 0 : 2), true);
-         else if (mm && lean) ASD_LAUNCH_RUNS(8, false, (EDGE ? 0 : 1), true);
+         else if (mm && lean && L.t.do_aniso) ASD_LAUNCH_RUNS(8, false, 2, true);
+         else if (mm && lean) ASD_LAUNCH_RUNS(8, false, 1, true);
          else if (mm) ASD_LAUNCH_RUNS(8, false, 0, true);
          else ASD_LAUNCH_RUNS(8, false, 0, false);
       }
@@ -1222,6 +1222,9 @@ static int sd_steps(asd_engine* e, long nsteps, long first_step) {
    }
    if (nsteps > 0) { e->msum_fresh = (p.frozen == nullptr); e->msum_ntile = ntile; }
    CU(cudaGetLastError());
+   // a slab on the moment planes exchanged emomM only: bring the SPINS of the neighbours' halos up to date once per call (field /
+   // energy evaluation and the Monte Carlo tile kernels read them)
+   if (nsteps > 0 && e->slab.on && p.mm_cur != nullptr && (r = slab_push_state(e))) return r;
    return 0;
 }
 
@@ -1945,6 +1948,7 @@ int asd_time_sd_steps(asd_engine* e, long nsteps, long first_step, float* total_
       CU(cudaEventElapsedTime(&stage_ms[0], a, b));
       CU(cudaEventElapsedTime(&stage_ms[1], b, c));
       cudaEventDestroy(c);
+      if (e->slab.on && p.mm_cur != nullptr && (r = slab_push_state(e))) return r;
    }
    cudaEventDestroy(a); cudaEventDestroy(b);
    return r;

@@ -449,10 +449,12 @@ llg_runs_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPar
          if (MSUM) { mnew[0] += o.x * o.m; mnew[1] += o.y * o.m; mnew[2] += o.z * o.m; }
          if (EDGE) {
             const int lo = __ldg(ep.hdst_lo + i), hi = __ldg(ep.hdst_hi + i);
-            if (lo >= 0) ep.peer_lo[(size_t)k * t.Npad + lo] = o;
-            if (hi >= 0) ep.peer_hi[(size_t)k * t.Npad + hi] = o;
-            if (MM) {
-               // ... and its emomM into the neighbours' moment planes, which is what their MM launches gather from
+            if (!MM) {
+               if (lo >= 0) ep.peer_lo[(size_t)k * t.Npad + lo] = o;
+               if (hi >= 0) ep.peer_hi[(size_t)k * t.Npad + hi] = o;
+            } else {
+               // MM layouts: the neighbours' launches gather from the moment planes only, so emomM (24 bytes) is what crosses
+               // NVLink per stage; the spins of the halo are refreshed once, when asd_sd_steps returns (slab_push_state)
                const double ox = o.x * o.m, oy = o.y * o.m, oz = o.z * o.m;
                if (lo >= 0) { double* __restrict__ q = ep.peer_mlo + (size_t)k * 3 * t.Npad + lo; q[0] = ox; q[t.Npad] = oy; q[2 * (size_t)t.Npad] = oz; }
                if (hi >= 0) { double* __restrict__ q = ep.peer_mhi + (size_t)k * 3 * t.Npad + hi; q[0] = ox; q[t.Npad] = oy; q[2 * (size_t)t.Npad] = oz; }
