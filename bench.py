@@ -62,6 +62,7 @@ class ClockSampler(threading.Thread):
             phys = int(vis.split(',')[index]) if vis and vis.split(',')[index].isdigit() else index
             self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.nv = pynvml
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)))   # before the timed region
         except Exception:
             self.nv = None
 
@@ -72,11 +73,9 @@ class ClockSampler(threading.Thread):
                     'hw_thermal_slowdown': nv.nvmlClocksThrottleReasonHwThermalSlowdown,
                     'sw_thermal_slowdown': nv.nvmlClocksThrottleReasonSwThermalSlowdown,
                     'sw_power_cap': nv.nvmlClocksThrottleReasonSwPowerCap}
-            try:
-                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
-            except Exception:
-                pass
-            while not self.stop_flag:
+            # the first sample is taken the moment the thread starts (the timed region of a 20-step run is ~10 ms: with eight ranks
+            # querying NVML at once a sample takes several ms) and the loop always completes the sample it began
+            while True:
                 try:
                     self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -85,12 +84,14 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(k)
                 except Exception:
                     pass
-                time.sleep(0.005)
+                if self.stop_flag:
+                    break
+                time.sleep(0.002)
             return
         q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        while not self.stop_flag:
+        while True:
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
                                       '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
@@ -102,6 +103,8 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(names[i])
             except Exception:
                 pass
+            if self.stop_flag:
+                break
             time.sleep(0.05)
 
     def summary(self):
