@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
 exec > gpurun_out/one.log 2>&1
-timeout 900 python -m pytest tests/test_gpu_lattice.py -m gpu -x -q -k anisotropy 2>&1 | tail -40
+python scripts/layoutprobe.py
