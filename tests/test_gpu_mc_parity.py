@@ -240,3 +240,21 @@ def test_chain_parity_warp_specialised_sweep(mode, monkeypatch):
     assert e.mc_colouring()[0] == 2
     err, moved = _chain_parity(e, S, mode, 500.0, 6, extfield=(0.0, 0.5, 0.0))
     assert moved > 0.1 and err <= CHAIN_TOL[mode], (mode, err)
+
+
+@pytest.mark.parametrize('mode', ['M', 'H'])
+def test_chain_parity_predrawn_trial_moves(mode, monkeypatch):
+    """ASD_MC_PREDRAW=1: the trial moves of a sweep drawn for the whole lattice by mc_predraw_kernel before the sweep kernel of the
+    run-form block sweep (an option kept for A/B runs: measured slower than drawing inside the sweep CTAs) -- the same chain"""
+    monkeypatch.setenv('ASD_RESIDENT', '0')
+    monkeypatch.setenv('ASD_MC_TS', '1024')
+    monkeypatch.setenv('ASD_MC_PREDRAW', '1')
+    from util import fixture_args
+    args = fixture_args('bccfe', mens=2, ncell=(64, 8, 8), do_reduced='Y')
+    S = orc.build_system(*args)
+    _random_start(S, 8)
+    e = lattice_engine(args, S, seed=17)
+    e.set_mc_layout(2)
+    assert e.mc_colouring()[0] == 2
+    err, moved = _chain_parity(e, S, mode, 500.0, 6, extfield=(0.0, 0.5, 0.0))
+    assert moved > 0.1 and err <= CHAIN_TOL[mode], (mode, err)

@@ -166,6 +166,7 @@ struct McBlockState {
    DevBuf<int> ulist, ucount, cstart, tilelist;
    DevBuf<uint4> nl16, dm16, bq16;
    DevBuf<unsigned short> selfpos, corder;
+   DevBuf<double> drec;                                     // [M][ntile][1024][5] pre-drawn trial moves of the running sweep
 };
 
 struct asd_engine {

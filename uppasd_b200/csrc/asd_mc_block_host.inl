@@ -274,8 +274,28 @@ static int mc_sweeps_block(asd_engine* e, McParams& p, long nsweeps, long first_
    const bool xs = L.t.zdm > 0 || L.t.zbq > 0, hb = p.mode == 'H';
    McTicket tk;
    memset(&tk, 0, sizeof tk);
+   // ASD_MC_PREDRAW=1: trial moves of a sweep drawn for the whole lattice by one data-parallel launch (mc_predraw_kernel) before the
+   // sweep kernel(s) of the run form (256-thread kernel on 1024-slot tiles).  NOT the default: measured SLOWER on bcc 128^3 (0.532
+   // against 0.442 ms per sweep, profiles/r03p): inside the sweep CTAs the draws overlap the other CTA's colour phases and fill the
+   // dependency wait, while the separate launch adds 168 MB of record traffic each way and its own divergent transcendental code
+   bool any_run = B.ticket;
+   for (int nr : B.class_run) any_run = any_run || nr > 0;
+   const char* penv = std::getenv("ASD_MC_PREDRAW");
+   const bool predraw = (penv && atoi(penv) != 0) && any_run && B.nt == 256 && B.ts == 1024;
+   McRuns mr = B.mr;
+   mr.drec = nullptr; mr.ntile = B.ntile;
+   if (predraw) {
+      if ((r = B.drec.alloc((size_t)e->M * B.ntile * 1024 * 5))) return r;
+      mr.drec = B.drec.p;
+   }
    for (long s = 0; s < nsweeps; s++) {
       p.sweep = (unsigned long long)(first_sweep + s);
+      if (predraw) {
+         const dim3 gp((unsigned)(((size_t)B.ntile * 1024 + 255) / 256), (unsigned)e->M);
+         if (hb) mc_predraw_kernel<true><<<gp, 256, 0, e->stream>>>(L.t, p, B.corder.p, B.ntile, e->cur.p, B.drec.p);
+         else mc_predraw_kernel<false><<<gp, 256, 0, e->stream>>>(L.t, p, B.corder.p, B.ntile, e->cur.p, B.drec.p);
+         e->launches++;
+      }
       if (B.ticket) {
          // one launch for the whole sweep: tickets in class order, dependencies through done[] (asd_mc_runs.cuh)
          tk.counter = B.counter.p; tk.base = B.tickets; tk.epoch = ++B.epoch; tk.done = B.done.p; tk.adj = B.adj.p; tk.nadj = B.nadj.p;
@@ -291,8 +311,8 @@ static int mc_sweeps_block(asd_engine* e, McParams& p, long nsweeps, long first_
             if (hb) mc_block_ws_launch(mc_block_ws_kernel<true>, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, e->cur.p);
             else mc_block_ws_launch(mc_block_ws_kernel<false>, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, e->cur.p);
          } else {
-            if (hb) mc_block_run_launch(mc_block_run_kernel<true, true>, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, 0, e->cur.p);
-            else mc_block_run_launch(mc_block_run_kernel<false, true>, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, 0, e->cur.p);
+            if (hb) mc_block_run_launch(mc_block_run_kernel<true, true>, gr, B.smem_run, e->stream, L.t, p, mb, mr, tk, 0, e->cur.p);
+            else mc_block_run_launch(mc_block_run_kernel<false, true>, gr, B.smem_run, e->stream, L.t, p, mb, mr, tk, 0, e->cur.p);
          }
          B.tickets += (unsigned long long)B.ntile * e->M;
          e->launches++;
@@ -302,8 +322,8 @@ static int mc_sweeps_block(asd_engine* e, McParams& p, long nsweeps, long first_
          const int nrun = B.class_run[c];
          if (nrun > 0) {
             const dim3 gr((unsigned)nrun, (unsigned)e->M);
-            if (hb) mc_block_run_launch(mc_block_run_kernel<true, false>, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, B.class_first[c], e->cur.p);
-            else mc_block_run_launch(mc_block_run_kernel<false, false>, gr, B.smem_run, e->stream, L.t, p, mb, B.mr, tk, B.class_first[c], e->cur.p);
+            if (hb) mc_block_run_launch(mc_block_run_kernel<true, false>, gr, B.smem_run, e->stream, L.t, p, mb, mr, tk, B.class_first[c], e->cur.p);
+            else mc_block_run_launch(mc_block_run_kernel<false, false>, gr, B.smem_run, e->stream, L.t, p, mb, mr, tk, B.class_first[c], e->cur.p);
             e->launches++;
          }
          if (nrun == B.class_count[c]) continue;

@@ -60,6 +60,9 @@ struct McRuns {
    int zero;                      // list position of the 16 zero records ( = ucap)
    int batch;                     // attempts per draw batch the phase list is cut for (MCR_BATCH or MCR_BATCH_WS)
    const unsigned short* __restrict__ gtab;   // [ntile][gstride]: header | groups x {header, bases[q][sp]}
+   const double* __restrict__ drec;           // [M][ntile][1024][5] trial-move records of THIS sweep drawn by mc_predraw_kernel (colour
+                                              // order of the tile), or null: the sweep kernel draws them itself (mc_draw_batch)
+   int ntile;
    double cseq[MCR_CSEQ];         // [NH][sp] coupling of every step, 0 beyond the row's last step
 };
 
@@ -309,6 +312,66 @@ __device__ __forceinline__ void mc_draw_batch(const Tables& t, const McParams& p
    }
 }
 
+// The trial moves of a sweep depend on the draws and on the atom's OWN spin at the start of the sweep only (an atom is drawn before its
+// one visit), so they can be produced for the whole lattice by an ordinary data-parallel launch at full occupancy instead of inside the
+// sweep CTAs, where 16 warps per SM cannot hide their dependent-instruction latency (21 k of the 60 k cycles of a tile, profiles/README).
+// One thread per (ensemble, tile, position in the tile's colour order); same expressions as mc_draw_batch.
+template <bool HB>
+__global__ void __launch_bounds__(256)
+mc_predraw_kernel(const __grid_constant__ Tables t, const __grid_constant__ McParams p, const unsigned short* __restrict__ corder, int ntile,
+                  const SpinVec* __restrict__ cur, double* __restrict__ drec) {
+   constexpr int TS = 1024, RW = 5;
+   const double pi = 3.141592653589793;
+   const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // tile * 1024 + position
+   const int k = blockIdx.y;
+   if (g >= (size_t)ntile * TS) return;
+   const unsigned slot = corder[g];
+   if (slot == 0xffffu) return;
+   const int i = (int)(g / TS) * TS + (int)slot;
+   const int o = __ldg(t.orig + i);
+   const SpinVec own = cur[(size_t)k * t.Npad + i];
+   double u[4];
+   uniform4(p.seed, (uint32_t)o + t.atom_offset, (uint32_t)k + t.ens_offset, p.sweep, 1u, u);
+   double d0, d1, d2, d3;
+   if (HB) {
+      double sphi, cphi;
+      sincos(pi * (2.0 * u[1] - 1.0), &sphi, &cphi);
+      d0 = u[0]; d1 = cphi; d2 = sphi; d3 = 0.0;
+   } else {
+      const int ftype = min((int)floor(3.0 * u[0]), 2);
+      d3 = u[3];
+      if (ftype == 0) {
+         double sphi, cphi;
+         sincos(u[1] * 2 * pi, &sphi, &cphi);
+         const double ct = 1.0 - 2.0 * u[2];
+         const double st = sqrt(fmax(1.0 - ct * ct, 0.0));
+         d0 = st * cphi; d1 = st * sphi; d2 = ct;
+      } else if (ftype == 1) {
+         double ga, gb, gc;
+         gauss3f(p.seed, (uint32_t)o + t.atom_offset, (uint32_t)k + t.ens_offset, p.sweep, 2u, ga, gb, gc);
+         const double ax = own.x + ga * p.delta, ay = own.y + gb * p.delta, az = own.z + gc * p.delta;
+         const double len = sqrt(ax * ax + ay * ay + az * az);
+         d0 = ax / len; d1 = ay / len; d2 = az / len;
+      } else {
+         d0 = -own.x; d1 = -own.y; d2 = -own.z;
+      }
+   }
+   double* __restrict__ dr = drec + ((size_t)k * ntile * TS + g) * RW;
+   dr[0] = d0; dr[1] = d1; dr[2] = d2; dr[3] = d3; dr[4] = own.m;
+}
+
+// records of the attempts [pb, pe) of the tile's colour order from the pre-drawn array into rec / rslot (ND threads, this one dtid)
+template <int ND>
+__device__ __forceinline__ void mc_load_batch(const McTileCtx& c, const double* __restrict__ dtile, int dtid, int pb, int pe,
+                                              double* __restrict__ rec, unsigned short* __restrict__ rslot) {
+   constexpr int RW = 5;
+   const int n = pe - pb;
+   const double* __restrict__ src = dtile + (size_t)RW * pb;
+#pragma unroll 5
+   for (int q = dtid; q < RW * n; q += ND) rec[q] = __ldg(src + q);
+   for (int r = dtid; r < n; r += ND) rslot[r] = c.co[pb + r];
+}
+
 // (C) one group of <= 16 same-colour atoms, handled by one warp: lanes l and l + 16 share atom l (each sums the steps of its lane-slot,
 // one shuffle joins them), lanes 0..15 then decide (calculate_energy + flip_a, or flip_h) and store.  pb: first attempt of the batch
 // whose records are in rec / rslot.
@@ -504,6 +567,7 @@ mc_block_run_kernel(const __grid_constant__ Tables t, const __grid_constant__ Mc
    c.beta_h = 1.0 / p.k_bolt / (p.temprescale * p.temperature);
    c.beta_m = 1.0 / p.k_bolt / (p.temprescale * p.temperature + 1.0e-15);
    auto bar = []() { __syncthreads(); };
+   const double* __restrict__ dtile = mr.drec ? mr.drec + ((size_t)c.k * mr.ntile + tile) * (1024 * RW) : nullptr;
    auto batch_range = [&](int gs, int ge, int& pb, int& pe) {
       pb = c.grec[(size_t)gs * c.gw];
       pe = (int)c.grec[(size_t)(ge - 1) * c.gw] + (int)c.grec[(size_t)(ge - 1) * c.gw + 1];
@@ -512,7 +576,8 @@ mc_block_run_kernel(const __grid_constant__ Tables t, const __grid_constant__ Mc
    if (TICKET && nph > 0) {
       // first batch of draws BEFORE the gather: fills the wait for the neighbour tiles and the flight time of the prefetch
       batch_range(gt[MCR_PH0] & 0x7fff, gt[MCR_PH0 + 2], pb, pe);
-      mc_draw_batch<HB, NT>(t, p, c, tid, pb, pe, rec, rslot, blist, bcnt, MCR_BATCH, bar);
+      if (dtile) mc_load_batch<NT>(c, dtile, tid, pb, pe, rec, rslot);
+      else mc_draw_batch<HB, NT>(t, p, c, tid, pb, pe, rec, rslot, blist, bcnt, MCR_BATCH, bar);
       MC_PROF_T(t_b1);
       MC_PROF_ADD(1, t_0, t_b1);
       mc_wait_tiles(tk, tile, c.k, tid);
@@ -533,7 +598,8 @@ mc_block_run_kernel(const __grid_constant__ Tables t, const __grid_constant__ Mc
          // ---- new batch: its draws ----
          MC_PROF_T(t_b0);
          batch_range(ga, (int)(pw.y & 0xffffu), pb, pe);
-         mc_draw_batch<HB, NT>(t, p, c, tid, pb, pe, rec, rslot, blist, bcnt, MCR_BATCH, bar);
+         if (dtile) mc_load_batch<NT>(c, dtile, tid, pb, pe, rec, rslot);
+         else mc_draw_batch<HB, NT>(t, p, c, tid, pb, pe, rec, rslot, blist, bcnt, MCR_BATCH, bar);
          __syncthreads();
          MC_PROF_T(t_b1);
          MC_PROF_ADD(1, t_b0, t_b1);
