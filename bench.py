@@ -377,7 +377,8 @@ def slab_block(a, world, rank, local, dist, torch, out, warmup, steps):
                'value': rate, 'unit': 'atom-steps/s', 'scaling': 'strong', 'ms_per_step': ms / steps, 'steps': steps, 'warmup': warmup,
                'halo': {'planes': 2, 'bytes_per_exchange_per_side': 2 * ncell[0] * ncell[1] * 2 * (24 if e.layout_info().get('planes') else 32),
                         'exchanges_per_step': 2, 'payload': 'emomM (moment planes)' if e.layout_info().get('planes') else 'spins',
-                        'transport': 'peer stores over NVLink from the boundary-tile launches (CUDA IPC), epoch flags',
+                        'transport': ('peer stores over NVLink (CUDA IPC) from a side-stream launch concurrent with the interior tiles, epoch flags'
+                                      if e.layout_info().get('planes') else 'peer stores over NVLink from the boundary-tile launches (CUDA IPC), epoch flags'),
                         'timeout_flag': int(ef.item())},
                'step_frac_of_peak': (b1 + b2) * rate / 1e9 / (peak * world)}
         e.close()
@@ -576,7 +577,8 @@ def main():
             kname = 'llg_stage_kernel<solver=%d,stage=2,%s,%s>' % (a.solver, 'full' if a.full_ham else 'reduced', 'staged' if lay['staged'] else 'direct')
             tables = 'index tables %.0f MB' % ((7 * 16 + 24) * n / 1e6)
         par = ('ensemble-sharded x%d (one %d-spin ensemble per GPU, no communication)' % (world, n)) if not slab else \
-              ('z-slabs x%d of one supercell, halo push fused into the boundary-tile launches (peer stores over NVLink)' % world)
+              ('z-slabs x%d of one supercell, halo exchange by peer stores over NVLink (side-stream launch on moment-plane layouts, else fused '
+               'into the boundary-tile launches)' % world)
         out = {
             'metric': 'atom-steps/sec', 'value': value, 'unit': 'atom-steps/s', 'n_gpus': world, 'steps': steps,
             'warmup': warmup, 'ms_per_step': ms / steps, 'higher_is_better': True,

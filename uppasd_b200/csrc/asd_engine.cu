@@ -134,6 +134,11 @@ struct Slab {
    int n_opened = 0;
    unsigned long long epoch = 0;       // exchanges completed (identical on every rank)
    bool connected = false;
+   // moment-plane layouts: the halo exchange of a stage is its own small launch on a high-priority side stream, concurrent with the
+   // interior tiles of the stage (evB: boundary tiles done -> push may start; evP: push done -> its source buffer may be rewritten)
+   cudaStream_t push_stream = nullptr;
+   cudaEvent_t evB = nullptr, evP = nullptr;
+   bool push_pending = false;
    long long timeout_ticks = 8000000000LL;  // ~4 s at 1.9 GHz
 };
 
@@ -963,6 +968,8 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
       static const bool short_env = !(std::getenv("ASD_SHORT_STAGING") && atoi(std::getenv("ASD_SHORT_STAGING")) == 0);
       const bool xs = L.t.dm16 != nullptr || L.t.bq16 != nullptr || (short_env && L.t.ucap <= 6 * 256);
       static const bool pdl_env = !(std::getenv("ASD_PDL") && atoi(std::getenv("ASD_PDL")) == 0);
+      // (slabs: dependent launches measured no gain with the side-stream exchange and a loss after the fused boundary launch,
+      // 1.97 against 1.87 ms per step on a 512 x 512 x 32 slab: off)
       const bool pdl = pdl_env && !EDGE && !e->slab.on && big_grid;
 #define ASD_LAUNCH_RUNS(NWV, XSV, LEANV, MMV)                                                                                                \
       do {                                                                                                                         \
@@ -1053,6 +1060,45 @@ static EdgeParams edge_params(asd_engine* e, int stage, unsigned long long epoch
 
 // one stage over the whole engine: plain launch, or (slab) wait for the halos -> boundary tiles with the fused halo
 // push -> interior tiles, which overlap the NVLink stores of the boundary launch
+// halo exchange of a moment-plane layout: emomM of the atoms in the boundary tiles [0, ta) and [tb, nt) that a ring neighbour mirrors,
+// from this slab's planes P[M][3][Npad] into the neighbours' planes (peer stores over NVLink); the last CTA publishes the epoch
+__global__ void __launch_bounds__(256)
+halo_push_planes_kernel(int ta, int tb, int nt, int ts, int Nown, size_t Npad, const double* __restrict__ P, EdgeParams ep) {
+   const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+   const int k = blockIdx.y;
+   const long tq = q / ts;
+   if (tq < (long)ta + (nt - tb)) {
+      const long tile = tq < ta ? tq : (long)tb + (tq - ta);
+      const long i = tile * ts + q % ts;
+      if (i < Nown) {
+         const int lo = __ldg(ep.hdst_lo + i), hi = __ldg(ep.hdst_hi + i);
+         if (lo >= 0 || hi >= 0) {
+            const double* __restrict__ src = P + (size_t)k * 3 * Npad + i;
+            const double mx = src[0], my = src[Npad], mz = src[2 * Npad];
+            if (lo >= 0) { double* __restrict__ d = ep.peer_mlo + (size_t)k * 3 * Npad + lo; d[0] = mx; d[Npad] = my; d[2 * Npad] = mz; }
+            if (hi >= 0) { double* __restrict__ d = ep.peer_mhi + (size_t)k * 3 * Npad + hi; d[0] = mx; d[Npad] = my; d[2 * Npad] = mz; }
+         }
+      }
+   }
+   __threadfence_system();
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      const unsigned int total = gridDim.x * gridDim.y;
+      if (atomicAdd(ep.ctr, 1u) == total - 1) {
+         *ep.ctr = 0;
+         __threadfence_system();
+         if (ep.flag_lo) st_release_sys(ep.flag_lo, ep.epoch);
+         if (ep.flag_hi) st_release_sys(ep.flag_hi, ep.epoch);
+      }
+   }
+}
+
+// main stream waits for the last halo push of the side stream (before the buffer it read is rewritten / before anything else uses ep.ctr)
+static void slab_join_push(asd_engine* e) {
+   Slab& sb = e->slab;
+   if (sb.push_pending) { cudaStreamWaitEvent(e->stream, sb.evP, 0); sb.push_pending = false; }
+}
+
 template <int SOLVER, int STAGE>
 static void launch_stage(asd_engine* e, Layout& L, const LlgParams& p) {
    Slab& sb = e->slab;
@@ -1061,6 +1107,30 @@ static void launch_stage(asd_engine* e, Layout& L, const LlgParams& p) {
    memset(&none, 0, sizeof none);
    if (!sb.on) {
       launch_stage_range<SOLVER, STAGE, false>(e, L, p, none, TileRange{0, ntile, 0}, ntile);
+      return;
+   }
+   static const bool side_env = !(std::getenv("ASD_SLAB_SIDE") && atoi(std::getenv("ASD_SLAB_SIDE")) == 0);
+   if (side_env && L.t.runs && L.t.mm && p.mm_cur != nullptr && sb.push_stream != nullptr) {
+      // moment-plane layout: boundary tiles and interior tiles take the SAME kernels (no remote stores, no fences in them); the
+      // boundary planes cross NVLink in a small launch of their own on a high-priority side stream while the interior tiles run
+      slab_join_push(e);
+      halo_wait_kernel<<<1, 1, 0, e->stream>>>(sb.flags.p, e->lat.has_lo, e->lat.has_hi, sb.epoch, sb.timeout_ticks, sb.err.p);
+      e->launches++;
+      int ta, tb, nt;
+      slab_split(e, L.t.tile_slots, ta, tb, nt);
+      const int nb = ta + (nt - tb);
+      launch_stage_range<SOLVER, STAGE, false>(e, L, p, none, TileRange{0, ta, tb}, nb);
+      cudaEventRecord(sb.evB, e->stream);
+      launch_stage_range<SOLVER, STAGE, false>(e, L, p, none, TileRange{ta, tb - ta, 0}, tb - ta);
+      cudaStreamWaitEvent(sb.push_stream, sb.evB, 0);
+      const EdgeParams ep = edge_params(e, STAGE, sb.epoch + 1);
+      const long nslot = (long)nb * L.t.tile_slots;
+      halo_push_planes_kernel<<<dim3((unsigned)((nslot + 255) / 256), e->M), 256, 0, sb.push_stream>>>(
+         ta, tb, nt, L.t.tile_slots, L.t.Nown, (size_t)L.Npad, (STAGE == 1) ? p.mm_pred : p.mm_cur, ep);
+      e->launches++;
+      cudaEventRecord(sb.evP, sb.push_stream);
+      sb.push_pending = true;
+      sb.epoch += 1;
       return;
    }
    halo_wait_kernel<<<1, 1, 0, e->stream>>>(sb.flags.p, e->lat.has_lo, e->lat.has_hi, sb.epoch, sb.timeout_ticks, sb.err.p);
@@ -1079,6 +1149,7 @@ static int slab_push_state(asd_engine* e) {
    if (!sb.on) return 0;
    if (!sb.connected) return fail(-11, "slab: asd_slab_connect_* must be called before the moments are set");
    Layout& L = e->sd;
+   slab_join_push(e);
    const EdgeParams ep = edge_params(e, 2, sb.epoch + 1);
    halo_push_kernel<<<dim3((L.t.Nown + 255) / 256, e->M), 256, 0, e->stream>>>(L.t.Nown, e->M, (size_t)L.Npad, e->cur.p, ep);
    e->launches++;
@@ -1479,6 +1550,14 @@ static int slab_commit(asd_engine* e) {
    CU(cudaMemset(e->mm_cur.p, 0, (size_t)3 * L.Npad * e->M * sizeof(double)));
    CU(cudaMemset(e->mm_pred.p, 0, (size_t)3 * L.Npad * e->M * sizeof(double)));
    e->mm_valid = false;
+   if (sb.push_stream == nullptr) {
+      int lo_pri = 0, hi_pri = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+      CU(cudaStreamCreateWithPriority(&sb.push_stream, cudaStreamNonBlocking, hi_pri));
+      CU(cudaEventCreateWithFlags(&sb.evB, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&sb.evP, cudaEventDisableTiming));
+   }
+   sb.push_pending = false;
    if ((r = sb.flags.alloc(2))) return r;
    if ((r = sb.ctr.alloc(1))) return r;
    if ((r = sb.err.alloc(1))) return r;
@@ -1524,6 +1603,7 @@ void asd_destroy(asd_engine* e) {
    if (!e) return;
    cudaSetDevice(e->device);
    if (e->stream) { cudaStreamSynchronize(e->stream); }
+   if (e->slab.push_stream) { cudaStreamSynchronize(e->slab.push_stream); cudaStreamDestroy(e->slab.push_stream); cudaEventDestroy(e->slab.evB); cudaEventDestroy(e->slab.evP); }
    for (int q = 0; q < e->slab.n_opened; q++) cudaIpcCloseMemHandle(e->slab.opened[q]);
    if (e->h_red) cudaFreeHost(e->h_red);
    cudaStream_t s = e->stream;
