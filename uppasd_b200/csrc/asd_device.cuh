@@ -876,7 +876,8 @@ __device__ __forceinline__ SpinVec integrate_site(const Tables& t, const LlgPara
 //   STAGED: tile path (shared-memory gather list).  EDGE: boundary tiles of a slab, see EdgeParams.
 //   MSUM: the launch also leaves the per-tile sums of the new emomM in p.msum_part (corrector launches only).
 // ------------------------------------------------------------------------------------------------
-template <int SOLVER, int STAGE, bool REDUCED, bool STAGED, bool EDGE, bool MSUM>
+// ILEAN: the lean integrator (uniform LLG parameters, no torque field, mompar 0: checked by the engine per launch).
+template <int SOLVER, int STAGE, bool REDUCED, bool STAGED, bool EDGE, bool MSUM, bool ILEAN = false>
 __global__ void __launch_bounds__(256, STAGED ? ASD_MINB_STAGED : ASD_MINB)
 llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgParams p, const __grid_constant__ EdgeParams ep,
                  const TileRange tr, SpinVec* __restrict__ cur, SpinVec* __restrict__ pred, double* __restrict__ b2eff) {
@@ -958,7 +959,7 @@ llg_stage_kernel(const __grid_constant__ Tables t, const __grid_constant__ LlgPa
       const double b[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
       SpinVec old;
       if (STAGE == 2) old = curk[i];
-      const SpinVec o = integrate_site<SOLVER, STAGE, !STAGED>(t, p, i, k, io, b, own, (STAGE == 1) ? own : old, b2eff);
+      const SpinVec o = integrate_site<SOLVER, STAGE, !STAGED, ILEAN>(t, p, i, k, io, b, own, (STAGE == 1) ? own : old, b2eff);
       if (STAGE == 1) predk[i] = o; else curk[i] = o;
       if (MSUM) { mnew[0] = o.x * o.m; mnew[1] = o.y * o.m; mnew[2] = o.z * o.m; }
       if (EDGE) {
