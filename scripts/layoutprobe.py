@@ -25,7 +25,6 @@ def probe(ncell, bc):
     e.close()
 
 
-for nc in ((64, 4, 8), (64, 6, 8), (96, 8, 8), (64, 8, 6), (64, 10, 10), (128, 8, 8)):
+shapes = [tuple(int(x) for x in a.split('x')) for a in sys.argv[1:]] or [(64, 4, 8), (64, 6, 8), (96, 8, 8), (64, 8, 6), (64, 10, 10), (128, 8, 8)]
+for nc in shapes:
     probe(nc, ('P', 'P', 'P'))
-probe((64, 8, 8), ('0', '0', '0'))
-probe((64, 8, 8), ('P', '0', 'P'))

@@ -105,13 +105,13 @@ def _bcc_engine(S, inp, args, solver, temp, seed=11):
     return e
 
 
-@pytest.mark.parametrize('ncell,tile', [((64, 4, 4), 1024), ((64, 6, 4), 1024), ((128, 8, 2), 1024), ((64, 6, 8), 1024), ((96, 8, 6), 1024)])
+@pytest.mark.parametrize('ncell,tile', [((64, 4, 4), 1024), ((64, 6, 4), 1024), ((128, 8, 2), 1024), ((64, 6, 8), 1024), ((96, 8, 6), 1024), ((40, 8, 8), 1024)])
 def test_run_kernel_against_oracle_and_staged_kernel(ncell, tile, monkeypatch):
     """The run-compressed register-blocked kernel (asd_runs.cuh) on lattices whose x extent is a multiple of 32 -- one,
     several and partly empty super-bricks: field-level parity is implied by the trajectory (every step evaluates the
     field twice); both solvers against the oracle at T = 0 to 1e-12, and against the one-atom-per-thread staged
-    kernel with the same noise stream at 300 K.  The last two shapes take the moment-plane instantiation (gather list staged from
-    emomM[M][3][Npad] with cp.async, padded union rows) on partly empty super-bricks."""
+    kernel with the same noise stream at 300 K.  The last three shapes take the moment-plane instantiation (gather list staged from
+    emomM[M][3][Npad] with cp.async, padded union rows) on partly empty super-bricks; (40, 8, 8) has a partly filled brick along x (8 of 32 cells)."""
     fx, _, _ = load_golden('bccfe_cuda')
     args = list(inputs.load_fixture(fx))
     args[0] = dict(args[0], ncell=ncell, mensemble=2, do_reduced='Y')
