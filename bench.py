@@ -431,7 +431,7 @@ def main():
         # the configuration it names (default bcc 128^3): every step is a full step of that supercell; the step count is
         # bounded (<= 20) so that the run ends within a few minutes on any host
         k = max(1, min(steps, 20))
-        w = min(warmup, 2)
+        w = min(warmup, 5)       # a CPU step of the named supercell takes ~0.1 s: the requested warm-up (3 in the driver's run) is honoured
         v, ms, n, cores, one = cpu_leg(cpu_ncell, a.solver, a.temp, a.damping, k, w, settle_s=6.0 if world > 1 else 0.0, one_thread_steps=1)
         if a.cpu_ncell:
             workload += ' [CPU sample: bcc %dx%dx%d]' % tuple(cpu_ncell)
