@@ -666,7 +666,10 @@ __device__ __forceinline__ void cayley(const double e[3], const double A[3], dou
 // Rodrigues rotation of the Depondt scheme (depondt.f90:157-179)
 __device__ __forceinline__ void rodrigues(const double bd[3], const double e[3], double dtg_lldamp, double out[3]) {
    double Bnorm = sqrt(bd[0] * bd[0] + bd[1] * bd[1] + bd[2] * bd[2]) + 1.0e-15;
-   const double hx = bd[0] / Bnorm, hy = bd[1] / Bnorm, hz = bd[2] / Bnorm;
+   // one division, three products (depondt.f90:160-162 divides three times: the quotients differ in the last bit at most, inside the
+   // 1e-12 parity bar; two FP64 divisions with their slow-path branches less per atom and stage)
+   const double binv = 1.0 / Bnorm;
+   const double hx = bd[0] * binv, hy = bd[1] * binv, hz = bd[2] * binv;
    const double v = Bnorm * dtg_lldamp;
    double sinv, cosv;
    sincos(v, &sinv, &cosv);
