@@ -63,15 +63,17 @@ __device__ __forceinline__ bool mc_update_site(const Tables& t, const McParams& 
       const double beta = 1.0 / p.k_bolt / (p.temprescale * p.temperature);
       const double zx = beta * tot[0] * p.mub * m, zy = beta * tot[1] * p.mub * m, zz = beta * tot[2] * p.mub * m;
       const double zarg = sqrt(zx * zx + zy * zy + zz * zz);
-      const double zctheta = zz / zarg;
+      // (flip_h divides four times -- zz / zarg, zx / (zarg zstheta), zy / (zarg zstheta), 1 / zarg; here: two reciprocals and products,
+      //  last-bit differences at most; the same in every Monte Carlo kernel: an FP64 division costs ~15 dependent instructions)
+      const double rzarg = 1.0 / zarg; const double zctheta = zz * rzarg;
       const double zstheta = sqrt(1.0 - zctheta * zctheta) + 1e-14;
-      double zcphi = zx / (zarg * zstheta), zsphi = zy / (zarg * zstheta);
+      const double rzs = 1.0 / (zarg * zstheta); double zcphi = zx * rzs, zsphi = zy * rzs;
       // Deviation from flip_h (documented in DESIGN.md): a field exactly along +-z makes the reference's frame
       // degenerate (zcphi = zsphi = 0 -> the new spin loses its transverse part and is no longer a unit vector);
       // any azimuth is valid there, take phi_field = 0.
       if (zx == 0.0 && zy == 0.0) { zcphi = 1.0; zsphi = 0.0; }
       const double em2 = exp(-2.0 * zarg);
-      const double ctheta = 1.0 + (1.0 / zarg) * log((1.0 - em2) * u[0] + em2 + 1e-14);
+      const double ctheta = 1.0 + rzarg * log((1.0 - em2) * u[0] + em2 + 1e-14);
       const double stheta = sqrt(fmax(1.0 - ctheta * ctheta, 0.0));
       double sphi, cphi;
       sincos(pi * (2.0 * u[1] - 1.0), &sphi, &cphi);
@@ -95,7 +97,7 @@ __device__ __forceinline__ bool mc_update_site(const Tables& t, const McParams& 
       gauss3f(p.seed, (uint32_t)o + t.atom_offset, (uint32_t)k + t.ens_offset, p.sweep, 2u, g0, g1, g2);
       const double ax = own.x + g0 * p.delta, ay = own.y + g1 * p.delta, az = own.z + g2 * p.delta;
       const double l = sqrt(ax * ax + ay * ay + az * az);
-      nx = ax / l; ny = ay / l; nz = az / l;
+      const double rl = 1.0 / l; nx = ax * rl; ny = ay * rl; nz = az * rl;
    } else {
       nx = -own.x; ny = -own.y; nz = -own.z;
    }

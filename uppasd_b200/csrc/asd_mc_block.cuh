@@ -211,7 +211,7 @@ mc_block_kernel(const __grid_constant__ Tables t, const __grid_constant__ McPara
                gauss3f(p.seed, (uint32_t)o + t.atom_offset, (uint32_t)k + t.ens_offset, p.sweep, 2u, g0, g1, g2);
                const double ax = own.x + g0 * p.delta, ay = own.y + g1 * p.delta, az = own.z + g2 * p.delta;
                const double l = sqrt(ax * ax + ay * ay + az * az);
-               d0 = ax / l; d1 = ay / l; d2 = az / l;
+               const double rl = 1.0 / l; d0 = ax * rl; d1 = ay * rl; d2 = az * rl;
             } else {
                d0 = -own.x; d1 = -own.y; d2 = -own.z;
             }
@@ -328,12 +328,12 @@ mc_block_kernel(const __grid_constant__ Tables t, const __grid_constant__ McPara
                const double tot[3] = {bs[0] + (bq[0] + h[0]), bs[1] + (bq[1] + h[1]), bs[2] + (bq[2] + h[2])};
                const double zx = beta_h * tot[0] * p.mub * m, zy = beta_h * tot[1] * p.mub * m, zz = beta_h * tot[2] * p.mub * m;
                const double zarg = sqrt(zx * zx + zy * zy + zz * zz);
-               const double zctheta = zz / zarg;
+               const double rzarg = 1.0 / zarg; const double zctheta = zz * rzarg;
                const double zstheta = sqrt(1.0 - zctheta * zctheta) + 1e-14;
-               double zcphi = zx / (zarg * zstheta), zsphi = zy / (zarg * zstheta);
+               const double rzs = 1.0 / (zarg * zstheta); double zcphi = zx * rzs, zsphi = zy * rzs;
                if (zx == 0.0 && zy == 0.0) { zcphi = 1.0; zsphi = 0.0; }     // degenerate frame (see mc_update_site)
                const double em2 = exp(-2.0 * zarg);
-               const double ctheta = 1.0 + (1.0 / zarg) * log((1.0 - em2) * dr[0] + em2 + 1e-14);
+               const double ctheta = 1.0 + rzarg * log((1.0 - em2) * dr[0] + em2 + 1e-14);
                const double stheta = sqrt(fmax(1.0 - ctheta * ctheta, 0.0));
                const double s0 = stheta * dr[1], s1 = stheta * dr[2], s2 = ctheta;
                out.x = zcphi * zctheta * s0 - zsphi * s1 + zcphi * zstheta * s2;

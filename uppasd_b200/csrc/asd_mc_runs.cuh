@@ -303,7 +303,7 @@ __device__ __forceinline__ void mc_draw_batch(const Tables& t, const McParams& p
          gauss3f(p.seed, (uint32_t)o + t.atom_offset, (uint32_t)c.k + t.ens_offset, p.sweep, 2u, ga, gb, gc);
          const double ax = dr[0] + ga * p.delta, ay = dr[1] + gb * p.delta, az = dr[2] + gc * p.delta;
          const double len = sqrt(ax * ax + ay * ay + az * az);
-         dr[0] = ax / len; dr[1] = ay / len; dr[2] = az / len;
+         const double rl = 1.0 / len; dr[0] = ax * rl; dr[1] = ay * rl; dr[2] = az * rl;
       }
       for (int q = dtid; q < n2; q += ND) {
          double* __restrict__ dr = rec + RW * (int)blist[2 * bstride + q];
@@ -351,7 +351,7 @@ mc_predraw_kernel(const __grid_constant__ Tables t, const __grid_constant__ McPa
          gauss3f(p.seed, (uint32_t)o + t.atom_offset, (uint32_t)k + t.ens_offset, p.sweep, 2u, ga, gb, gc);
          const double ax = own.x + ga * p.delta, ay = own.y + gb * p.delta, az = own.z + gc * p.delta;
          const double len = sqrt(ax * ax + ay * ay + az * az);
-         d0 = ax / len; d1 = ay / len; d2 = az / len;
+         const double rl = 1.0 / len; d0 = ax * rl; d1 = ay * rl; d2 = az * rl;
       } else {
          d0 = -own.x; d1 = -own.y; d2 = -own.z;
       }
@@ -427,12 +427,12 @@ __device__ __forceinline__ void mc_sweep_group(const Tables& t, const McParams& 
          const double tot[3] = {bs[0] + (bqf[0] + h[0]), bs[1] + (bqf[1] + h[1]), bs[2] + (bqf[2] + h[2])};
          const double zx = c.beta_h * tot[0] * p.mub * m, zy = c.beta_h * tot[1] * p.mub * m, zz = c.beta_h * tot[2] * p.mub * m;
          const double zarg = sqrt(zx * zx + zy * zy + zz * zz);
-         const double zctheta = zz / zarg;
+         const double rzarg = 1.0 / zarg; const double zctheta = zz * rzarg;
          const double zstheta = sqrt(1.0 - zctheta * zctheta) + 1e-14;
-         double zcphi = zx / (zarg * zstheta), zsphi = zy / (zarg * zstheta);
+         const double rzs = 1.0 / (zarg * zstheta); double zcphi = zx * rzs, zsphi = zy * rzs;
          if (zx == 0.0 && zy == 0.0) { zcphi = 1.0; zsphi = 0.0; }     // degenerate frame (see mc_update_site)
          const double em2 = exp(-2.0 * zarg);
-         const double ctheta = 1.0 + (1.0 / zarg) * log((1.0 - em2) * d0 + em2 + 1e-14);
+         const double ctheta = 1.0 + rzarg * log((1.0 - em2) * d0 + em2 + 1e-14);
          const double stheta = sqrt(fmax(1.0 - ctheta * ctheta, 0.0));
          const double s0 = stheta * d1, s1 = stheta * d2, s2 = ctheta;
          ox = zcphi * zctheta * s0 - zsphi * s1 + zcphi * zstheta * s2;
