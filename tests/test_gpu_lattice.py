@@ -461,3 +461,55 @@ def test_fcc_four_sublattices_take_the_run_kernel(monkeypatch):
         assert np.abs(a.get_moments()[0] - b.get_moments()[0]).max() <= 1e-9, solver
         for x in (e, a, b):
             x.close()
+
+
+@pytest.mark.parametrize('what', ['per_site_damping', 'site_field', 'torque', 'mompar'])
+def test_general_instantiation_on_moment_planes(what, monkeypatch):
+    """A moment-plane layout whose run takes the GENERAL integrator loop (llg_runs_kernel<.., LEAN 0, MM>): per-site damping, a
+    site-dependent external field, a spin-transfer-torque field, or mompar 1 switch the LEAN flavour off at launch time.  Both
+    solvers against the oracle at T = 0 to 1e-12."""
+    from util import fixture_args, lattice_engine
+    args = fixture_args('bccfe_cuda', mens=2, ncell=(64, 8, 8), do_reduced='Y')
+    S = orc.build_system(*args)
+    inp = args[0]
+    rng = np.random.default_rng(29)
+    N = S['Natom']
+    e0 = rng.normal(size=(3, N, 2)); e0 /= np.sqrt((e0 ** 2).sum(axis=0))
+    S['emom'] = np.asfortranarray(e0)
+    S['emomM'] = np.asfortranarray(e0 * S['mmom'][None])
+    damping = 0.3
+    mompar = 0
+    bt = None
+    if what == 'per_site_damping':
+        damping = 0.05 + 0.4 * rng.random(N)
+    if what == 'site_field':
+        S['external_field'] = np.asfortranarray(rng.normal(size=(3, N, 2)) * 2.0)
+    if what == 'torque':
+        bt = np.asfortranarray(rng.normal(size=(3, N, 2)) * 0.5)
+    if what == 'mompar':
+        mompar = 1
+    for solver in (1, 5):
+        from uppasd_b200 import host, lattice
+        c = orc.consts(S)
+        e = host.Engine()
+        e.set_constants(c['gama'], c['k_bolt'], c['mub'], c['mry'])
+        e.set_system(N, 2, S['nHam'], S['aHam'])
+        nn, red, xc, nntype = args[6](S)
+        ns, ca, cs, sh = lattice.stencil(inp['cell'], S['bas'], S['atype_inp'], nn, red, inp['sym'], nntype, ncell=inp['ncell'])
+        cp = lattice.couplings(ns, ca, sh, S['atype_inp'], xc, S['ammom_inp'], c['mry'], c['mub'], 1)
+        e.build_lattice_table(0, S['NA'], inp['ncell'], inp['bc'], ns, ca, cs, cp)
+        e.set_external_field(S['external_field'])
+        if bt is not None:
+            e.set_torque(bt)
+        e.set_llg(solver, inp['timestep'], landeg=S['Landeg'], lambda1=damping, temp=0.0, mompar=mompar)
+        e.set_moments(S['emom'], S['mmom'], S['mmom0'])
+        e.commit()
+        assert e.layout_info()['planes'] == 1 and e.layout_info()['runs'] == 4
+        st = orc.SdState(S, solver, inp['timestep'], damping, mompar=mompar, btorque=bt)
+        e.sd_steps(25)
+        for _ in range(25):
+            st.step()
+        emom, emomM, mmom = e.get_moments()
+        assert np.abs(emom - st.emom).max() <= 1e-12, (what, solver, np.abs(emom - st.emom).max())
+        assert np.abs(mmom - st.mmom).max() <= 1e-12 * np.abs(st.mmom).max(), (what, solver)
+        e.close()
