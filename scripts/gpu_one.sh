@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
 exec > gpurun_out/one.log 2>&1
-timeout 900 python -m pytest tests/test_gpu_lattice.py -m gpu -x -q -k "general_instantiation" 2>&1 | tail -25
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+AB_REPS=1 python scripts/abbench.py; AB_SOLVER=5 AB_REPS=1 python scripts/abbench.py
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -2
