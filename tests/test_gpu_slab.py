@@ -227,3 +227,24 @@ def test_lattice_mc_layout_agrees_with_colour_major_on_observables():
         res.append((ms.mean(), ms.mean(axis=0).std() / np.sqrt(ms.shape[1]) + ms.std() / np.sqrt(ms.size)))
     (m0, s0), (m1, s1) = res
     assert abs(m0 - m1) < 5 * (s0 + s1) + 2e-3, res
+
+
+@pytest.mark.parametrize('solver', [1, 5])
+def test_single_slab_whose_ring_neighbour_is_itself(solver):
+    """nslabs = 1: the slab machinery (halo wait, boundary / interior launches, side-stream exchange of the moment planes, refresh of
+    the halo spins when asd_sd_steps returns) on one periodic supercell whose lower and upper neighbour are the slab itself -- bit
+    for bit the undecomposed run, fields included."""
+    import bench
+    ncell = (64, 8, 16)
+    ref, n = bench.bcc_engine(ncell, solver, 300.0, 0.5, 2, 0, 0)
+    sl, _ = bench.bcc_engine(ncell, solver, 300.0, 0.5, 2, 0, 0, slab=(1, 0, None))
+    assert sl.layout_info()['planes'] == 1 and ref.layout_info()['planes'] == 1
+    for nst in (1, 4, 9):
+        ref.sd_steps(nst, first_step=1)
+        sl.sd_steps(nst, first_step=1)
+        assert np.array_equal(ref.get_moments()[0], sl.get_moments()[0]), (solver, nst)
+    assert sl.slab_status()[1] == 0
+    b_ref = ref.effective_field(energy=False)[0]
+    b_sl = sl.effective_field(energy=False)[0]
+    assert np.abs(b_sl - b_ref).max() <= 1e-13 * np.abs(b_ref).max()
+    ref.close(); sl.close()
