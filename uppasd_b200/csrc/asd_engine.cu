@@ -1011,10 +1011,15 @@ static void launch_stage_range2(asd_engine* e, Layout& L, const LlgParams& p, co
    } else if (L.t.staged && !fr) {
       const size_t smem = L.smem_bytes + (size_t)3 * L.t.ucap * sizeof(double);
       static const bool lean_env2 = !(std::getenv("ASD_LEAN") && atoi(std::getenv("ASD_LEAN")) == 0);
-      if (L.reduced && lean_env2 && !EDGE && !p.per_site && p.mompar == 0 && L.t.btorque == nullptr) {
+      const bool ilean2 = lean_env2 && !EDGE && !p.per_site && p.mompar == 0 && L.t.btorque == nullptr;
+      if (L.reduced && ilean2) {
          // the lean integrator (asd_runs.cuh) in the one-atom-per-thread staged kernel of layouts without the run regularity
          allow_smem(llg_stage_kernel<SOLVER, STAGE, true, true, false, MSUM, true>, smem);
          launch_dep(pdl_s, llg_stage_kernel<SOLVER, STAGE, true, true, false, MSUM, true>, g, b, smem, e->stream, L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
+      } else if (ilean2) {
+         // ... and with one coupling row per atom (do_reduced N, random alloys)
+         allow_smem(llg_stage_kernel<SOLVER, STAGE, false, true, false, MSUM, true>, smem);
+         launch_dep(pdl_s, llg_stage_kernel<SOLVER, STAGE, false, true, false, MSUM, true>, g, b, smem, e->stream, L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
       } else if (L.reduced) {
          allow_smem(llg_stage_kernel<SOLVER, STAGE, true, true, EDGE, MSUM>, smem);
          launch_dep(pdl_s, llg_stage_kernel<SOLVER, STAGE, true, true, EDGE, MSUM>, g, b, smem, e->stream, L.t, p, ep, tr, e->cur.p, e->pred.p, e->b2eff.p);
